@@ -1,0 +1,918 @@
+// C-ABI of libicpb200.so (include/icpb200.h): contexts, handles, host-side
+// orchestration of the kernels in nn.cu / cloud.cu / map.cu.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "icpb_internal.h"
+
+using namespace icpb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+enum WsId {
+    WS_DESCS = 0, WS_STATES, WS_PARAMS, WS_TGT_SOA, WS_PM1, WS_PM2, WS_PG, WS_IDX, WS_DIST, WS_CHUNKS, WS_ALT,
+    WS_IDX_TRACE, WS_DIST_TRACE, WS_MISC, WS_DEPTH, WS_BGR, WS_KEEP, WS_TILESTATE, WS_IMG_A, WS_IMG_B, WS_NORMALS,
+    WS_RT, WS_COUNT
+};
+
+int fail(icpb_ctx *ctx, int status, const char *what, cudaError_t ce = cudaSuccess)
+{
+    std::string msg = what;
+    if (ce != cudaSuccess) {
+        msg += ": ";
+        msg += cudaGetErrorString(ce);
+    }
+    if (ctx) ctx->err = msg;
+    else g_create_error = msg;
+    return status;
+}
+
+#define CU(ctx, call)                                                         \
+    do {                                                                      \
+        cudaError_t ce__ = (call);                                            \
+        if (ce__ != cudaSuccess) return fail((ctx), ICPB_ERR_CUDA, #call, ce__); \
+    } while (0)
+
+// grow-only workspace buffer
+int ws_get(icpb_ctx *ctx, int id, size_t bytes, void **out, bool zero_new = false)
+{
+    icpb_ctx::Buf &b = ctx->ws[id];
+    if (b.bytes < bytes) {
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (b.p) CU(ctx, cudaFree(b.p));
+        b.p = nullptr;
+        b.bytes = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        CU(ctx, cudaMalloc(&b.p, want));
+        b.bytes = want;
+        if (zero_new) CU(ctx, cudaMemsetAsync(b.p, 0, want, ctx->stream));
+    }
+    *out = b.p;
+    return ICPB_OK;
+}
+
+int pinned_get(icpb_ctx *ctx, size_t bytes, void **out)
+{
+    if (ctx->pinned_bytes < bytes) {
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->pinned) CU(ctx, cudaFreeHost(ctx->pinned));
+        ctx->pinned = nullptr;
+        ctx->pinned_bytes = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        CU(ctx, cudaMallocHost(&ctx->pinned, want));
+        ctx->pinned_bytes = want;
+    }
+    *out = ctx->pinned;
+    return ICPB_OK;
+}
+
+int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    if (!v || !*v) return dflt;
+    return atoi(v);
+}
+
+// Work decomposition of nn_partial: QPT queries per thread, `splits` target ranges.
+void choose_nn_config(const icpb_ctx *ctx, int max_n, int max_m, int batch, int *qpt, int *splits)
+{
+    int q = 8;
+    const long long slots = (long long)ctx->sm_count * 4; // ~4 resident 128-thread CTAs per SM
+    // small problems: smaller query tiles give the grid more CTAs before the targets must be split
+    if ((long long)((max_n + kNnThreads * 8 - 1) / (kNnThreads * 8)) * batch < slots / 8) q = 4;
+    q = env_int("ICPB_QPT", q);
+    if (q != 2 && q != 4 && q != 8) q = 8;
+    const int tiles = (max_n + kNnThreads * q - 1) / (kNnThreads * q);
+    const int ngroups = (max_m + kGroup - 1) / kGroup;
+    long long s = (slots + (long long)tiles * batch - 1) / ((long long)tiles * batch);
+    s = std::max<long long>(1, std::min<long long>(s, std::max(1, ngroups / 4)));
+    s = env_int("ICPB_SPLITS", (int)s);
+    s = std::max<long long>(1, std::min<long long>(s, ngroups));
+    *qpt = q;
+    *splits = (int)s;
+}
+
+struct RegHost {
+    icpb_cloud *data;
+    const icpb_cloud *target;
+};
+
+// The device-resident registration loop for `count` independent problems.
+int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_icp_params *prm,
+                      icpb_icp_result *results, bool keep_transformed)
+{
+    if (count <= 0) return fail(ctx, ICPB_ERR_INVALID, "count <= 0");
+    int max_n = 0, max_m = 0;
+    size_t tot_n = 0, tot_groups = 0, tot_chunks = 0;
+    for (int b = 0; b < count; ++b) {
+        if (!regs[b].data || !regs[b].target) return fail(ctx, ICPB_ERR_INVALID, "null cloud");
+        if (regs[b].data->ctx != ctx || regs[b].target->ctx != ctx)
+            return fail(ctx, ICPB_ERR_INVALID, "cloud belongs to another context");
+        if (regs[b].data->n <= 0 || regs[b].target->n <= 0)
+            return fail(ctx, ICPB_ERR_EMPTY, "empty cloud (the reference dereferences begin(), icp.cpp:572)");
+        max_n = std::max(max_n, regs[b].data->n);
+        max_m = std::max(max_m, regs[b].target->n);
+        tot_n += ((size_t)regs[b].data->n + 31) / 32 * 32;
+        tot_groups += ((size_t)regs[b].target->n + kGroup - 1) / kGroup;
+        tot_chunks += ((size_t)regs[b].data->n + kChunk - 1) / kChunk;
+    }
+    if (prm->max_iterations < 0) return fail(ctx, ICPB_ERR_INVALID, "max_iterations < 0");
+    const int passes = prm->max_iterations + 1;
+    const bool trace = (prm->idx_trace != nullptr) || (prm->dist_trace != nullptr);
+    if (trace && count != 1) return fail(ctx, ICPB_ERR_INVALID, "traces are only supported for a single registration");
+
+    int qpt, splits;
+    choose_nn_config(ctx, max_n, max_m, count, &qpt, &splits);
+
+    RegDesc *d_descs;
+    IcpState *d_states;
+    IcpParamsDev *d_prm;
+    float *d_soa, *d_pm1, *d_pm2, *d_dist;
+    int *d_pg, *d_idx;
+    double *d_chunks;
+    float4 *d_alt;
+    int rc;
+    if ((rc = ws_get(ctx, WS_DESCS, sizeof(RegDesc) * count, (void **)&d_descs))) return rc;
+    if ((rc = ws_get(ctx, WS_STATES, sizeof(IcpState) * count, (void **)&d_states))) return rc;
+    if ((rc = ws_get(ctx, WS_PARAMS, sizeof(IcpParamsDev), (void **)&d_prm))) return rc;
+    if ((rc = ws_get(ctx, WS_TGT_SOA, tot_groups * kGroup * 3 * sizeof(float), (void **)&d_soa))) return rc;
+    if ((rc = ws_get(ctx, WS_PM1, tot_n * splits * sizeof(float), (void **)&d_pm1))) return rc;
+    if ((rc = ws_get(ctx, WS_PM2, tot_n * splits * sizeof(float), (void **)&d_pm2))) return rc;
+    if ((rc = ws_get(ctx, WS_PG, tot_n * splits * sizeof(int), (void **)&d_pg))) return rc;
+    if ((rc = ws_get(ctx, WS_IDX, tot_n * sizeof(int), (void **)&d_idx))) return rc;
+    if ((rc = ws_get(ctx, WS_DIST, tot_n * sizeof(float), (void **)&d_dist))) return rc;
+    if ((rc = ws_get(ctx, WS_CHUNKS, tot_chunks * kTerms * sizeof(double), (void **)&d_chunks))) return rc;
+    if ((rc = ws_get(ctx, WS_ALT, tot_n * sizeof(float4), (void **)&d_alt))) return rc;
+    int *d_idx_trace = nullptr;
+    float *d_dist_trace = nullptr;
+    if (prm->idx_trace) {
+        if ((rc = ws_get(ctx, WS_IDX_TRACE, (size_t)passes * max_n * sizeof(int), (void **)&d_idx_trace))) return rc;
+        CU(ctx, cudaMemsetAsync(d_idx_trace, 0xff, (size_t)passes * max_n * sizeof(int), ctx->stream));
+    }
+    if (prm->dist_trace) {
+        if ((rc = ws_get(ctx, WS_DIST_TRACE, (size_t)passes * max_n * sizeof(float), (void **)&d_dist_trace)))
+            return rc;
+        CU(ctx, cudaMemsetAsync(d_dist_trace, 0, (size_t)passes * max_n * sizeof(float), ctx->stream));
+    }
+
+    // host staging: descs | states | params in one pinned block
+    const size_t hb = sizeof(RegDesc) * count + sizeof(IcpState) * count + sizeof(IcpParamsDev);
+    void *hp;
+    if ((rc = pinned_get(ctx, hb, &hp))) return rc;
+    RegDesc *h_descs = (RegDesc *)hp;
+    IcpState *h_states = (IcpState *)(h_descs + count);
+    IcpParamsDev *h_prm = (IcpParamsDev *)(h_states + count);
+
+    size_t off_n = 0, off_g = 0, off_c = 0;
+    for (int b = 0; b < count; ++b) {
+        const int n = regs[b].data->n, m = regs[b].target->n;
+        const int n_stride = (n + 31) / 32 * 32;
+        const int ngroups = (m + kGroup - 1) / kGroup;
+        RegDesc &d = h_descs[b];
+        d.D[0] = regs[b].data->d_pts;
+        d.D[1] = d_alt + off_n;
+        d.tgt = regs[b].target->d_pts;
+        d.tgt_soa = d_soa + off_g * kGroup * 3;
+        d.n = n; d.m = m; d.ngroups = ngroups; d.n_stride = n_stride;
+        d.pm1 = d_pm1 + off_n * splits;
+        d.pm2 = d_pm2 + off_n * splits;
+        d.pg = d_pg + off_n * splits;
+        d.idx = d_idx + off_n;
+        d.dist = d_dist + off_n;
+        d.chunk_sums = d_chunks + off_c * kTerms;
+        d.st = d_states + b;
+        d.idx_trace = d_idx_trace;
+        d.dist_trace = d_dist_trace;
+        IcpState &s = h_states[b];
+        memset(&s, 0, sizeof(s));
+        const float I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        for (int k = 0; k < 9; ++k) { s.rigid[k] = I3[k]; s.camR[k] = I3[k]; s.PR[k] = I3[k]; s.Rf[k] = I3[k]; }
+        off_n += n_stride;
+        off_g += ngroups;
+        off_c += (n + kChunk - 1) / kChunk;
+    }
+    h_prm->max_iterations = prm->max_iterations;
+    h_prm->threshold = prm->threshold;
+    h_prm->max_nn_distance = prm->max_nn_distance;
+    h_prm->solve_mode = prm->solve_mode;
+    for (int k = 0; k < 3; ++k) h_prm->last_translation[k] = prm->last_translation[k];
+
+    cudaStream_t st = ctx->stream;
+    CU(ctx, cudaMemcpyAsync(d_descs, h_descs, sizeof(RegDesc) * count, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(d_states, h_states, sizeof(IcpState) * count, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(d_prm, h_prm, sizeof(IcpParamsDev), cudaMemcpyHostToDevice, st));
+
+    long long launches = 0;
+    CU(ctx, cudaEventRecord(ctx->ev0, st));
+    for (int b = 0; b < count; ++b) {
+        launch_target_prep(h_descs[b].tgt, h_descs[b].m, const_cast<float *>(h_descs[b].tgt_soa), h_descs[b].ngroups, st);
+        ++launches;
+    }
+    const bool prof = ctx->profiling;
+    if (prof) {
+        while ((int)ctx->prof_events.size() < 2 * passes) {
+            cudaEvent_t e;
+            CU(ctx, cudaEventCreate(&e));
+            ctx->prof_events.push_back(e);
+        }
+    }
+    for (int pass = 0; pass < passes; ++pass) {
+        if (prof) CU(ctx, cudaEventRecord(ctx->prof_events[2 * pass], st));
+        launch_nn_partial(d_descs, count, max_n, qpt, splits, pass, st);
+        if (prof) CU(ctx, cudaEventRecord(ctx->prof_events[2 * pass + 1], st));
+        launch_nn_finalize(d_descs, d_prm, count, max_n, splits, pass, st);
+        launches += 2;
+    }
+    launch_pending_translate(d_descs, count, max_n, st);
+    ++launches;
+    CU(ctx, cudaEventRecord(ctx->ev1, st));
+    CU(ctx, cudaGetLastError());
+
+    CU(ctx, cudaMemcpyAsync(h_states, d_states, sizeof(IcpState) * count, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    CU(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    float nn_ms = 0.f;
+    int nn_launches = 0;
+    if (prof) {
+        // passes after convergence exit at once; count only the ones that did the scan
+        int executed = 0;
+        for (int b = 0; b < count; ++b) executed = std::max(executed, h_states[b].passes);
+        for (int pass = 0; pass < executed; ++pass) {
+            float t = 0.f;
+            CU(ctx, cudaEventElapsedTime(&t, ctx->prof_events[2 * pass], ctx->prof_events[2 * pass + 1]));
+            nn_ms += t;
+            ++nn_launches;
+        }
+    }
+
+    for (int b = 0; b < count; ++b) {
+        const IcpState &s = h_states[b];
+        if (keep_transformed && s.last_buf == 1) {
+            CU(ctx, cudaMemcpyAsync(h_descs[b].D[0], h_descs[b].D[1], sizeof(float4) * h_descs[b].n,
+                                    cudaMemcpyDeviceToDevice, st));
+        }
+        if (results) {
+            icpb_icp_result &r = results[b];
+            memset(&r, 0, sizeof(r));
+            r.iterations = s.iterations;
+            r.nn_passes = s.passes;
+            r.n_assoc = s.n_assoc;
+            r.mse = s.mse;
+            for (int rr = 0; rr < 3; ++rr) {
+                for (int c = 0; c < 3; ++c) r.rigid[4 * rr + c] = s.rigid[3 * rr + c];
+                r.rigid[4 * rr + 3] = s.offset[rr]; // icp.cpp:266-268
+            }
+            r.rigid[15] = 1.f; // row 3 is never written by the reference (icp.cpp:29)
+            memcpy(r.cam_rotation, s.camR, sizeof(s.camR));
+            memcpy(r.cam_position, s.camP, sizeof(s.camP));
+            memcpy(r.offset, s.offset, sizeof(s.offset));
+            memcpy(r.pose_R, s.PR, sizeof(s.PR));
+            memcpy(r.pose_t, s.Pt, sizeof(s.Pt));
+            r.small_assoc_exit = s.small_exit;
+            r.exact_rescans = s.rescans;
+            r.gpu_ms = ms;
+            r.kernel_launches = (int)launches;
+            r.nn_partial_ms = nn_ms;
+            r.nn_partial_launches = nn_launches;
+            r.nn_qpt = qpt;
+            r.nn_splits = splits;
+        }
+    }
+    if (trace) {
+        const int n = regs[0].data->n;
+        if (prm->idx_trace)
+            CU(ctx, cudaMemcpyAsync(prm->idx_trace, d_idx_trace, (size_t)passes * n * sizeof(int),
+                                    cudaMemcpyDeviceToHost, st));
+        if (prm->dist_trace)
+            CU(ctx, cudaMemcpyAsync(prm->dist_trace, d_dist_trace, (size_t)passes * n * sizeof(float),
+                                    cudaMemcpyDeviceToHost, st));
+    }
+    CU(ctx, cudaStreamSynchronize(st));
+    ctx->launches += launches;
+    return ICPB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int icpb_version(void) { return ICPB_VERSION; }
+
+const char *icpb_status_string(int status)
+{
+    switch (status) {
+    case ICPB_OK: return "ok";
+    case ICPB_ERR_INVALID: return "invalid argument";
+    case ICPB_ERR_EMPTY: return "empty cloud";
+    case ICPB_ERR_CUDA: return "CUDA error";
+    case ICPB_ERR_CAPACITY: return "capacity exceeded";
+    default: return "unknown status";
+    }
+}
+
+const char *icpb_last_error(const icpb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int icpb_device_count(int *count)
+{
+    if (!count) return ICPB_ERR_INVALID;
+    int c = 0;
+    cudaError_t ce = cudaGetDeviceCount(&c);
+    if (ce != cudaSuccess) {
+        *count = 0;
+        return fail(nullptr, ICPB_ERR_CUDA, "cudaGetDeviceCount", ce);
+    }
+    *count = c;
+    return ICPB_OK;
+}
+
+static int ctx_create_common(int device, void *stream, bool own, icpb_ctx **out)
+{
+    if (!out) return fail(nullptr, ICPB_ERR_INVALID, "out == NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count == 0)
+        return fail(nullptr, ICPB_ERR_CUDA, "no CUDA device (libicpb200 has no CPU fallback)", ce);
+    if (device < 0 || device >= count) return fail(nullptr, ICPB_ERR_INVALID, "device index out of range");
+    CU(nullptr, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(nullptr, ICPB_ERR_CUDA, "device is not sm_100-class; this library is built for sm_100a only");
+    icpb_ctx *ctx = new (std::nothrow) icpb_ctx();
+    if (!ctx) return fail(nullptr, ICPB_ERR_INVALID, "out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->ws.resize(WS_COUNT);
+    ctx->own_stream = own;
+    if (own) {
+        ce = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (ce != cudaSuccess) { delete ctx; return fail(nullptr, ICPB_ERR_CUDA, "cudaStreamCreate", ce); }
+    } else {
+        ctx->stream = (cudaStream_t)stream;
+    }
+    cudaEventCreate(&ctx->ev0);
+    cudaEventCreate(&ctx->ev1);
+    cudaEventCreate(&ctx->evt0);
+    cudaEventCreate(&ctx->evt1);
+    *out = ctx;
+    return ICPB_OK;
+}
+
+int icpb_ctx_create(int device, icpb_ctx **out) { return ctx_create_common(device, nullptr, true, out); }
+
+int icpb_ctx_create_on_stream(int device, void *cuda_stream, icpb_ctx **out)
+{
+    return ctx_create_common(device, cuda_stream, false, out);
+}
+
+int icpb_ctx_destroy(icpb_ctx *ctx)
+{
+    if (!ctx) return ICPB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &b : ctx->ws)
+        if (b.p) cudaFree(b.p);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaEventDestroy(ctx->evt0);
+    cudaEventDestroy(ctx->evt1);
+    for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return ICPB_OK;
+}
+
+int icpb_ctx_sync(icpb_ctx *ctx)
+{
+    if (!ctx) return ICPB_ERR_INVALID;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return ICPB_OK;
+}
+
+void *icpb_ctx_stream(icpb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int icpb_timer_start(icpb_ctx *ctx)
+{
+    if (!ctx) return ICPB_ERR_INVALID;
+    CU(ctx, cudaEventRecord(ctx->evt0, ctx->stream));
+    return ICPB_OK;
+}
+
+int icpb_timer_stop(icpb_ctx *ctx, float *elapsed_ms)
+{
+    if (!ctx || !elapsed_ms) return ICPB_ERR_INVALID;
+    CU(ctx, cudaEventRecord(ctx->evt1, ctx->stream));
+    CU(ctx, cudaEventSynchronize(ctx->evt1));
+    CU(ctx, cudaEventElapsedTime(elapsed_ms, ctx->evt0, ctx->evt1));
+    return ICPB_OK;
+}
+
+int icpb_ctx_set_profiling(icpb_ctx *ctx, int enabled)
+{
+    if (!ctx) return ICPB_ERR_INVALID;
+    ctx->profiling = enabled != 0;
+    return ICPB_OK;
+}
+
+int icpb_ctx_launch_count(icpb_ctx *ctx, long long *count)
+{
+    if (!ctx || !count) return ICPB_ERR_INVALID;
+    *count = ctx->launches;
+    return ICPB_OK;
+}
+
+int icpb_measure_fp32_peak(icpb_ctx *ctx, int repeats, double *tflops, float *ms_out)
+{
+    if (!ctx || !tflops) return ICPB_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
+    float *d_out;
+    int rc;
+    if ((rc = ws_get(ctx, WS_MISC, (size_t)blocks * threads * sizeof(float), (void **)&d_out))) return rc;
+    float best = 1e30f;
+    if (repeats < 1) repeats = 1;
+    launch_fp32_peak(d_out, blocks, threads, iters, ctx->stream); // warm-up
+    for (int r = 0; r < repeats; ++r) {
+        CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        launch_fp32_peak(d_out, blocks, threads, iters, ctx->stream);
+        CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        CU(ctx, cudaEventSynchronize(ctx->ev1));
+        float ms;
+        CU(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        best = std::min(best, ms);
+    }
+    ctx->launches += repeats + 1;
+    const double flops = (double)blocks * threads * iters * 64.0 * 2.0; // 8 unrolled x 8 chains FMAs
+    *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return ICPB_OK;
+}
+
+// ---- clouds -------------------------------------------------------------------
+
+int icpb_cloud_create(icpb_ctx *ctx, int capacity, icpb_cloud **out)
+{
+    if (!ctx || !out || capacity < 0) return fail(ctx, ICPB_ERR_INVALID, "icpb_cloud_create: bad argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    icpb_cloud *c = new (std::nothrow) icpb_cloud();
+    if (!c) return fail(ctx, ICPB_ERR_INVALID, "out of host memory");
+    c->ctx = ctx;
+    c->capacity = std::max(capacity, 1);
+    cudaError_t ce = cudaMalloc((void **)&c->d_pts, sizeof(float4) * (size_t)c->capacity);
+    if (ce != cudaSuccess) { delete c; return fail(ctx, ICPB_ERR_CUDA, "cudaMalloc(cloud)", ce); }
+    *out = c;
+    return ICPB_OK;
+}
+
+int icpb_cloud_destroy(icpb_cloud *cloud)
+{
+    if (!cloud) return ICPB_OK;
+    cudaSetDevice(cloud->ctx->device);
+    cudaStreamSynchronize(cloud->ctx->stream);
+    cudaFree(cloud->d_pts);
+    delete cloud;
+    return ICPB_OK;
+}
+
+int icpb_cloud_size(const icpb_cloud *cloud, int *n)
+{
+    if (!cloud || !n) return ICPB_ERR_INVALID;
+    *n = cloud->n;
+    return ICPB_OK;
+}
+
+int icpb_cloud_upload(icpb_cloud *cloud, const icpb_point *points, int n)
+{
+    if (!cloud || n < 0 || (n > 0 && !points)) return ICPB_ERR_INVALID;
+    icpb_ctx *ctx = cloud->ctx;
+    if (n > cloud->capacity) return fail(ctx, ICPB_ERR_CAPACITY, "icpb_cloud_upload: n > capacity");
+    static_assert(sizeof(icpb_point) == sizeof(float4), "color_point_t is 16 bytes");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (n) CU(ctx, cudaMemcpyAsync(cloud->d_pts, points, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cloud->n = n;
+    return ICPB_OK;
+}
+
+int icpb_cloud_upload_xyz(icpb_cloud *cloud, const float *xyz, int n)
+{
+    if (!cloud || n < 0 || (n > 0 && !xyz)) return ICPB_ERR_INVALID;
+    icpb_ctx *ctx = cloud->ctx;
+    if (n > cloud->capacity) return fail(ctx, ICPB_ERR_CAPACITY, "icpb_cloud_upload_xyz: n > capacity");
+    void *hp;
+    int rc;
+    if ((rc = pinned_get(ctx, sizeof(icpb_point) * (size_t)std::max(n, 1), &hp))) return rc;
+    icpb_point *p = (icpb_point *)hp;
+    for (int i = 0; i < n; ++i) {
+        p[i].x = xyz[3 * i]; p[i].y = xyz[3 * i + 1]; p[i].z = xyz[3 * i + 2];
+        p[i].c0 = p[i].c1 = p[i].c2 = p[i].pad = 0;
+    }
+    return icpb_cloud_upload(cloud, p, n);
+}
+
+int icpb_cloud_download(icpb_cloud *cloud, icpb_point *out, int capacity, int *n)
+{
+    if (!cloud || (!out && capacity > 0)) return ICPB_ERR_INVALID;
+    icpb_ctx *ctx = cloud->ctx;
+    if (n) *n = cloud->n;
+    if (capacity < cloud->n) return fail(ctx, ICPB_ERR_CAPACITY, "icpb_cloud_download: capacity < size");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (cloud->n)
+        CU(ctx, cudaMemcpyAsync(out, cloud->d_pts, sizeof(float4) * (size_t)cloud->n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return ICPB_OK;
+}
+
+int icpb_cloud_copy(icpb_cloud *dst, const icpb_cloud *src)
+{
+    if (!dst || !src) return ICPB_ERR_INVALID;
+    icpb_ctx *ctx = dst->ctx;
+    if (src->n > dst->capacity) return fail(ctx, ICPB_ERR_CAPACITY, "icpb_cloud_copy: capacity");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (src->n)
+        CU(ctx, cudaMemcpyAsync(dst->d_pts, src->d_pts, sizeof(float4) * (size_t)src->n, cudaMemcpyDeviceToDevice, ctx->stream));
+    dst->n = src->n;
+    return ICPB_OK;
+}
+
+int icpb_cloud_upload_device(icpb_cloud *cloud, const void *device_points, int n)
+{
+    if (!cloud || n < 0 || (n > 0 && !device_points)) return ICPB_ERR_INVALID;
+    icpb_ctx *ctx = cloud->ctx;
+    if (n > cloud->capacity) return fail(ctx, ICPB_ERR_CAPACITY, "icpb_cloud_upload_device: n > capacity");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (n)
+        CU(ctx, cudaMemcpyAsync(cloud->d_pts, device_points, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    cloud->n = n;
+    return ICPB_OK;
+}
+
+const void *icpb_cloud_device_ptr(const icpb_cloud *cloud) { return cloud ? cloud->d_pts : nullptr; }
+
+void icpb_intrinsics_reference_v1(icpb_intrinsics *K)
+{
+    if (!K) return;
+    K->fx_u = 468.60f; K->cx_u = 318.27f; K->fx_v = 468.60f; K->cx_v = 318.27f; K->depth_scale = 5000.0f;
+}
+
+void icpb_intrinsics_reference_v2(icpb_intrinsics *K)
+{
+    if (!K) return;
+    K->fx_u = 363.58f; K->cx_u = 250.32f; K->fx_v = 363.58f; K->cx_v = 250.32f; K->depth_scale = 5000.0f;
+}
+
+int icpb_cloud_from_depth_device(icpb_cloud *cloud, const void *d_depth, const void *d_bgr, int w, int h,
+                                 const icpb_intrinsics *K, int rule, uint32_t rule_arg, uint32_t seed,
+                                 const void *d_keep_stream, int keep_stream_len)
+{
+    if (!cloud || !d_depth || !K || w <= 0 || h <= 0) return ICPB_ERR_INVALID;
+    icpb_ctx *ctx = cloud->ctx;
+    if (rule < ICPB_SUB_NONE || rule > ICPB_SUB_STREAM) return fail(ctx, ICPB_ERR_INVALID, "unknown subsample rule");
+    if (rule == ICPB_SUB_STREAM && !d_keep_stream) return fail(ctx, ICPB_ERR_INVALID, "keep_stream == NULL");
+    if (((uintptr_t)d_depth & 15) != 0) return fail(ctx, ICPB_ERR_INVALID, "depth must be 16-byte aligned");
+    CU(ctx, cudaSetDevice(ctx->device));
+    BackprojectArgs a;
+    a.depth = (const uint16_t *)d_depth;
+    a.bgr = (const uint8_t *)d_bgr;
+    a.w = w; a.h = h; a.K = *K;
+    a.rule = rule; a.rule_arg = rule_arg; a.seed = seed;
+    a.keep_stream = (const uint8_t *)d_keep_stream;
+    a.keep_stream_len = keep_stream_len;
+    a.out = cloud->d_pts;
+    a.capacity = cloud->capacity;
+    a.n_tiles = backproject_tiles(w, h);
+    void *ts;
+    int rc;
+    // [ticket (u32) | pad][out_count (i32) | pad][2*n_tiles status words]: fixed positions, so a
+    // different image size never reinterprets stale status words as the ticket
+    if ((rc = ws_get(ctx, WS_TILESTATE, sizeof(unsigned long long) * (2 * (size_t)a.n_tiles + 2), &ts, true))) return rc;
+    a.ticket = (unsigned int *)ts;
+    a.out_count = (int *)((unsigned long long *)ts + 1);
+    a.tile_state = (unsigned long long *)ts + 2;
+    launch_backproject(a, ctx->stream);
+    ctx->launches += 1;
+    void *hp;
+    if ((rc = pinned_get(ctx, 64, &hp))) return rc;
+    CU(ctx, cudaMemcpyAsync(hp, a.out_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaGetLastError());
+    int n = *(int *)hp;
+    if (n < 0) {
+        cloud->n = 0;
+        CU(ctx, cudaMemsetAsync(ts, 0, sizeof(unsigned long long) * 2, ctx->stream));
+        return fail(ctx, ICPB_ERR_CUDA, "icpb_cloud_from_depth: tile scan timed out (internal error)");
+    }
+    if (n > cloud->capacity) {
+        cloud->n = cloud->capacity;
+        return fail(ctx, ICPB_ERR_CAPACITY, "icpb_cloud_from_depth: more points than the cloud's capacity");
+    }
+    cloud->n = n;
+    return ICPB_OK;
+}
+
+int icpb_cloud_from_depth(icpb_cloud *cloud, const uint16_t *depth, const uint8_t *bgr, int w, int h,
+                          const icpb_intrinsics *K, int rule, uint32_t rule_arg, uint32_t seed,
+                          const uint8_t *keep_stream, int keep_stream_len)
+{
+    if (!cloud || !depth || !K || w <= 0 || h <= 0) return ICPB_ERR_INVALID;
+    icpb_ctx *ctx = cloud->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)w * h;
+    void *d_depth, *d_bgr = nullptr, *d_keep = nullptr;
+    int rc;
+    if ((rc = ws_get(ctx, WS_DEPTH, npx * sizeof(uint16_t), &d_depth))) return rc;
+    CU(ctx, cudaMemcpyAsync(d_depth, depth, npx * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (bgr) {
+        if ((rc = ws_get(ctx, WS_BGR, npx * 3, &d_bgr))) return rc;
+        CU(ctx, cudaMemcpyAsync(d_bgr, bgr, npx * 3, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (rule == ICPB_SUB_STREAM) {
+        if (!keep_stream || keep_stream_len <= 0) return fail(ctx, ICPB_ERR_INVALID, "keep_stream missing");
+        if ((rc = ws_get(ctx, WS_KEEP, (size_t)keep_stream_len, &d_keep))) return rc;
+        CU(ctx, cudaMemcpyAsync(d_keep, keep_stream, (size_t)keep_stream_len, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return icpb_cloud_from_depth_device(cloud, d_depth, d_bgr, w, h, K, rule, rule_arg, seed, d_keep, keep_stream_len);
+}
+
+int icpb_cloud_transform(icpb_cloud *cloud, const float R[9], const float t[3])
+{
+    if (!cloud) return ICPB_ERR_INVALID;
+    icpb_ctx *ctx = cloud->ctx;
+    if (cloud->n == 0 || (!R && !t)) return ICPB_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    float *d_rt;
+    int rc;
+    if ((rc = ws_get(ctx, WS_RT, 16 * sizeof(float), (void **)&d_rt))) return rc;
+    void *hp;
+    if ((rc = pinned_get(ctx, 16 * sizeof(float), &hp))) return rc;
+    float *h = (float *)hp;
+    for (int k = 0; k < 9; ++k) h[k] = R ? R[k] : 0.f;
+    for (int k = 0; k < 3; ++k) h[9 + k] = t ? t[k] : 0.f;
+    CU(ctx, cudaMemcpyAsync(d_rt, h, 12 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    launch_transform(cloud->d_pts, cloud->n, d_rt, d_rt + 9, R != nullptr, t != nullptr, ctx->stream);
+    ctx->launches += 1;
+    CU(ctx, cudaStreamSynchronize(ctx->stream)); // the pinned staging block is reused by later calls
+    CU(ctx, cudaGetLastError());
+    return ICPB_OK;
+}
+
+int icpb_cloud_center(icpb_cloud *cloud, double center[3])
+{
+    if (!cloud || !center) return ICPB_ERR_INVALID;
+    icpb_ctx *ctx = cloud->ctx;
+    if (cloud->n <= 0) return fail(ctx, ICPB_ERR_EMPTY, "icpb_cloud_center: empty cloud");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int nchunks = (cloud->n + kChunk - 1) / kChunk;
+    double *d_chunks;
+    void *misc;
+    int rc;
+    if ((rc = ws_get(ctx, WS_CHUNKS, (size_t)nchunks * kTerms * sizeof(double), (void **)&d_chunks))) return rc;
+    if ((rc = ws_get(ctx, WS_MISC, 64, &misc, true))) return rc;
+    double *d_out = (double *)misc;
+    unsigned int *d_counter = (unsigned int *)((char *)misc + 32);
+    CU(ctx, cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), ctx->stream));
+    launch_center(cloud->d_pts, cloud->n, d_chunks, d_out, d_counter, ctx->stream);
+    ctx->launches += 1;
+    CU(ctx, cudaMemcpyAsync(center, d_out, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaGetLastError());
+    return ICPB_OK;
+}
+
+// ---- image-space stages ----------------------------------------------------------
+
+int icpb_normals_from_depth(icpb_ctx *ctx, const uint16_t *depth, int w, int h, float *normals)
+{
+    if (!ctx || !depth || !normals || w <= 0 || h <= 0) return ICPB_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)w * h;
+    void *d_depth, *d_n;
+    int rc;
+    if ((rc = ws_get(ctx, WS_DEPTH, npx * sizeof(uint16_t), &d_depth))) return rc;
+    if ((rc = ws_get(ctx, WS_NORMALS, npx * 3 * sizeof(float), &d_n))) return rc;
+    CU(ctx, cudaMemcpyAsync(d_depth, depth, npx * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+    launch_normals((const uint16_t *)d_depth, w, h, (float *)d_n, ctx->stream);
+    ctx->launches += 1;
+    CU(ctx, cudaMemcpyAsync(normals, d_n, npx * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaGetLastError());
+    return ICPB_OK;
+}
+
+int icpb_depth_filter(icpb_ctx *ctx, const uint16_t *depth, int w, int h, int min_d, int max_d, uint16_t *out)
+{
+    if (!ctx || !depth || !out || w <= 0 || h <= 0) return ICPB_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)w * h * sizeof(uint16_t);
+    void *d_in, *d_a, *d_b;
+    int rc;
+    if ((rc = ws_get(ctx, WS_DEPTH, bytes, &d_in))) return rc;
+    if ((rc = ws_get(ctx, WS_IMG_A, bytes, &d_a))) return rc;
+    if ((rc = ws_get(ctx, WS_IMG_B, bytes, &d_b))) return rc;
+    CU(ctx, cudaMemcpyAsync(d_in, depth, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    launch_depth_filter((const uint16_t *)d_in, (uint16_t *)d_a, nullptr, (uint16_t *)d_b, w, h, min_d, max_d, ctx->stream);
+    ctx->launches += 2;
+    CU(ctx, cudaMemcpyAsync(out, d_b, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaGetLastError());
+    return ICPB_OK;
+}
+
+// ---- registration -------------------------------------------------------------------
+
+int icpb_nn_search_device(icpb_ctx *ctx, const icpb_cloud *data, const icpb_cloud *target, const int32_t **d_idx,
+                          const float **d_dist)
+{
+    if (!ctx || !data || !target) return ICPB_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    icpb_icp_params prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.max_iterations = 0;
+    prm.threshold = 0.f;
+    prm.max_nn_distance = 0.75f;
+    RegHost r{const_cast<icpb_cloud *>(data), target};
+    icpb_icp_result res;
+    int rc = run_registrations(ctx, &r, 1, &prm, &res, false);
+    if (rc) return rc;
+    if (d_idx) *d_idx = (const int32_t *)ctx->ws[WS_IDX].p;
+    if (d_dist) *d_dist = (const float *)ctx->ws[WS_DIST].p;
+    return ICPB_OK;
+}
+
+int icpb_nn_search(icpb_ctx *ctx, const icpb_cloud *data, const icpb_cloud *target, int32_t *idx, float *dist,
+                   int *exact_rescans)
+{
+    if (!ctx || !data || !target) return ICPB_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    icpb_icp_params prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.max_nn_distance = 0.75f;
+    RegHost r{const_cast<icpb_cloud *>(data), target};
+    icpb_icp_result res;
+    int rc = run_registrations(ctx, &r, 1, &prm, &res, false);
+    if (rc) return rc;
+    if (idx)
+        CU(ctx, cudaMemcpyAsync(idx, ctx->ws[WS_IDX].p, sizeof(int32_t) * (size_t)data->n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dist)
+        CU(ctx, cudaMemcpyAsync(dist, ctx->ws[WS_DIST].p, sizeof(float) * (size_t)data->n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (exact_rescans) *exact_rescans = res.exact_rescans;
+    return ICPB_OK;
+}
+
+int icpb_icp_register(icpb_ctx *ctx, icpb_cloud *data, const icpb_cloud *target, const icpb_icp_params *params,
+                      icpb_icp_result *result)
+{
+    if (!ctx || !data || !target || !params) return ICPB_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    RegHost r{data, target};
+    return run_registrations(ctx, &r, 1, params, result, true);
+}
+
+int icpb_icp_register_batch(icpb_ctx *ctx, icpb_cloud *const *data, const icpb_cloud *const *target, int count,
+                            const icpb_icp_params *params, icpb_icp_result *results)
+{
+    if (!ctx || !data || !target || !params || count <= 0) return ICPB_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    std::vector<RegHost> regs((size_t)count);
+    for (int b = 0; b < count; ++b) regs[b] = RegHost{data[b], target[b]};
+    return run_registrations(ctx, regs.data(), count, params, results, true);
+}
+
+// ---- certainty map ---------------------------------------------------------------------
+
+int icpb_map_create(icpb_ctx *ctx, const int dims[3], float cell, int z_lo, int z_hi, icpb_map **out)
+{
+    if (!ctx || !dims || !out) return ICPB_ERR_INVALID;
+    if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0 || !(cell > 0.f) || z_lo < 0 || z_hi > dims[2] || z_lo >= z_hi)
+        return fail(ctx, ICPB_ERR_INVALID, "icpb_map_create: bad dims / cell / slab");
+    CU(ctx, cudaSetDevice(ctx->device));
+    icpb_map *m = new (std::nothrow) icpb_map();
+    if (!m) return fail(ctx, ICPB_ERR_INVALID, "out of host memory");
+    m->ctx = ctx;
+    for (int k = 0; k < 3; ++k) m->dev.dims[k] = dims[k];
+    m->dev.cell = cell;
+    m->dev.z_lo = z_lo;
+    m->dev.z_hi = z_hi;
+    m->dev.zs = z_hi - z_lo;
+    m->bytes = (long long)dims[0] * dims[1] * m->dev.zs;
+    const size_t alloc = ((size_t)m->bytes + 3) / 4 * 4;
+    cudaError_t ce = cudaMalloc((void **)&m->dev.grid, alloc);
+    if (ce != cudaSuccess) { delete m; return fail(ctx, ICPB_ERR_CUDA, "cudaMalloc(map)", ce); }
+    ce = cudaMemsetAsync(m->dev.grid, 0, alloc, ctx->stream); // map.cpp:23-30
+    if (ce != cudaSuccess) { cudaFree(m->dev.grid); delete m; return fail(ctx, ICPB_ERR_CUDA, "cudaMemset(map)", ce); }
+    *out = m;
+    return ICPB_OK;
+}
+
+int icpb_map_destroy(icpb_map *map)
+{
+    if (!map) return ICPB_OK;
+    cudaSetDevice(map->ctx->device);
+    cudaStreamSynchronize(map->ctx->stream);
+    cudaFree(map->dev.grid);
+    delete map;
+    return ICPB_OK;
+}
+
+int icpb_map_clear(icpb_map *map)
+{
+    if (!map) return ICPB_ERR_INVALID;
+    icpb_ctx *ctx = map->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemsetAsync(map->dev.grid, 0, ((size_t)map->bytes + 3) / 4 * 4, ctx->stream));
+    return ICPB_OK;
+}
+
+int icpb_map_update_endpoints(icpb_map *map, const icpb_cloud *points, int rule, int delta, int max_conf)
+{
+    if (!map || !points) return ICPB_ERR_INVALID;
+    icpb_ctx *ctx = map->ctx;
+    if (rule != ICPB_RULE_A && rule != ICPB_RULE_C) return fail(ctx, ICPB_ERR_INVALID, "unknown update rule");
+    if (delta < 0 || delta > 255) return fail(ctx, ICPB_ERR_INVALID, "delta out of [0,255]");
+    CU(ctx, cudaSetDevice(ctx->device));
+    launch_map_endpoints(map->dev, points->d_pts, points->n, rule, delta, max_conf, ctx->stream);
+    ctx->launches += points->n > 0;
+    CU(ctx, cudaGetLastError());
+    return ICPB_OK;
+}
+
+int icpb_map_integrate_rays(icpb_map *map, const icpb_cloud *points, const float origin[3], int delta_dec,
+                            int delta_inc, long long *voxels_visited)
+{
+    if (!map || !points || !origin) return ICPB_ERR_INVALID;
+    icpb_ctx *ctx = map->ctx;
+    if (delta_dec < 0 || delta_dec > 255 || delta_inc < 0 || delta_inc > 255)
+        return fail(ctx, ICPB_ERR_INVALID, "delta out of [0,255]");
+    CU(ctx, cudaSetDevice(ctx->device));
+    unsigned long long *d_vis = nullptr;
+    if (voxels_visited) {
+        void *misc;
+        int rc;
+        if ((rc = ws_get(ctx, WS_MISC, 64, &misc, true))) return rc;
+        d_vis = (unsigned long long *)((char *)misc + 48);
+        CU(ctx, cudaMemsetAsync(d_vis, 0, sizeof(unsigned long long), ctx->stream));
+    }
+    launch_map_rays(map->dev, points->d_pts, points->n, origin, delta_dec, d_vis, ctx->stream);        // phase 1
+    launch_map_endpoints(map->dev, points->d_pts, points->n, ICPB_RULE_A, delta_inc, 0, ctx->stream);  // phase 2
+    ctx->launches += 2 * (points->n > 0);
+    CU(ctx, cudaGetLastError());
+    if (voxels_visited) {
+        unsigned long long v = 0;
+        CU(ctx, cudaMemcpyAsync(&v, d_vis, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        *voxels_visited = (long long)v;
+    }
+    return ICPB_OK;
+}
+
+int icpb_map_voxel_coords(const icpb_map *map, const float p[3], int v[3])
+{
+    if (!map || !p || !v) return ICPB_ERR_INVALID;
+    for (int k = 0; k < 3; ++k) { // map.cpp:55-85
+        int q = (int)(p[k] / map->dev.cell);
+        if (q < 0) q = 0;
+        if (q >= map->dev.dims[k]) q = map->dev.dims[k] - 1;
+        v[k] = q;
+    }
+    return ICPB_OK;
+}
+
+int icpb_map_size_bytes(const icpb_map *map, long long *size)
+{
+    if (!map || !size) return ICPB_ERR_INVALID;
+    *size = map->bytes;
+    return ICPB_OK;
+}
+
+int icpb_map_download(icpb_map *map, uint8_t *out, long long capacity)
+{
+    if (!map || !out) return ICPB_ERR_INVALID;
+    icpb_ctx *ctx = map->ctx;
+    if (capacity < map->bytes) return fail(ctx, ICPB_ERR_CAPACITY, "icpb_map_download: capacity < size");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(out, map->dev.grid, (size_t)map->bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return ICPB_OK;
+}
+
+int icpb_map_upload(icpb_map *map, const uint8_t *in, long long size)
+{
+    if (!map || !in) return ICPB_ERR_INVALID;
+    icpb_ctx *ctx = map->ctx;
+    if (size != map->bytes) return fail(ctx, ICPB_ERR_INVALID, "icpb_map_upload: size mismatch");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(map->dev.grid, in, (size_t)size, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return ICPB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,291 @@
+// Image-space stages: depth -> XYZ back-projection with order-preserving
+// compaction, normals, depth pre-filter.
+//
+// Replaces (reference file:line):
+//   PointCloud::PointCloud(cv::Mat&, cv::Mat[, keypoints])  pointcloud.cpp:11-58, 109-165  (P1)
+//   getNormalMap                                            SLAM.cpp:412-430               (P3)
+//   filterDepthImage                                        SLAM.cpp:553-573               (8f-1)
+//
+// Built with -fmad=false; float divisions are IEEE (nvcc default -prec-div=true).
+#include "icpb_internal.h"
+
+namespace icpb {
+
+constexpr int kBpThreads = 256;
+constexpr int kBpPix = 8;                         // pixels per thread: one 16-byte load of u16
+constexpr int kBpTile = kBpThreads * kBpPix;      // 2048 pixels per CTA
+
+int backproject_tiles(int w, int h) { return (w * h + kBpTile - 1) / kBpTile; }
+
+// murmur3 finaliser; the ICPB_SUB_HASH stand-in for rand() (pointcloud.cpp:28)
+__device__ __forceinline__ uint32_t hash32(uint32_t seed, uint32_t pixel)
+{
+    uint32_t h = seed ^ (pixel * 0x9E3779B9u);
+    h ^= h >> 16;
+    h *= 0x85EBCA6Bu;
+    h ^= h >> 13;
+    h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return h;
+}
+
+// ---- decoupled look-back over 64-bit status words ---------------------------
+// word = (epoch*4 + flag) << 32 | value ; flag 1 = tile aggregate, 2 = inclusive prefix.
+// Words left over from earlier launches carry an older epoch and read as "not ready".
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Called by one full warp; returns the exclusive prefix of `tile`.  The spin is
+// bounded: a predecessor that never publishes (an internal error) makes the
+// launch report failure instead of hanging the GPU.
+__device__ uint32_t lookback(unsigned long long *state, int tile, uint32_t epoch, int *failed)
+{
+    const int lane = threadIdx.x & 31;
+    uint32_t exclusive = 0;
+    int base = tile - 1;
+    unsigned int spins = 0;
+    while (base >= 0) {
+        if (++spins > (1u << 24)) { *failed = 1; break; }
+        int j = base - lane;
+        uint32_t flag = 2, val = 0;
+        if (j >= 0) {
+            unsigned long long v = ld_volatile_u64(&state[j]);
+            uint32_t hi = (uint32_t)(v >> 32);
+            flag = ((hi >> 2) == epoch) ? (hi & 3u) : 0u;
+            val = (uint32_t)v;
+        }
+        if (__any_sync(0xffffffffu, flag == 0)) continue; // a predecessor has not published yet
+        uint32_t incl_mask = __ballot_sync(0xffffffffu, flag == 2);
+        int first = incl_mask ? (__ffs(incl_mask) - 1) : 31;
+        uint32_t c = (lane <= first) ? val : 0;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+        exclusive += c;
+        if (incl_mask) break;
+        base -= 32;
+    }
+    return exclusive;
+}
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *s_warp, uint32_t &total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += o;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    uint32_t wbase = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < kBpThreads / 32; ++k) {
+        uint32_t c = s_warp[k];
+        if (k < wid) wbase += c;
+        tot += c;
+    }
+    __syncthreads();
+    total = tot;
+    return wbase + inc - v;
+}
+
+// P1.  One CTA per 2048-pixel tile, tiles taken by ticket so that every
+// predecessor a tile waits for has already started.  Two chained scans: the
+// ordinal among NON-ZERO pixels (consumed by the subsample rule exactly where
+// the reference consumes one rand(), pointcloud.cpp:22-28) and the output
+// position among KEPT pixels (raster order == push_back order, :54).
+__global__ void __launch_bounds__(kBpThreads) backproject_kernel(BackprojectArgs a, uint32_t epoch)
+{
+    __shared__ uint32_t s_warp[kBpThreads / 32];
+    __shared__ uint32_t s_bcast[2];
+    __shared__ int s_tile;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        unsigned int t = atomicAdd(a.ticket, 1u);
+        if (t == (unsigned int)(a.n_tiles - 1)) *a.ticket = 0; // last ticket of this launch: re-arm
+        s_tile = (int)t;
+    }
+    __syncthreads();
+    const int tile = s_tile;
+    if (tile < 0 || tile >= a.n_tiles) { // corrupted ticket: report, never spin
+        if (tid == 0) *a.out_count = -1;
+        return;
+    }
+    int failed = 0;
+    unsigned long long *stateV = a.tile_state;
+    unsigned long long *stateK = a.tile_state + a.n_tiles;
+    const int npx = a.w * a.h;
+    const int p0 = tile * kBpTile + tid * kBpPix;
+
+    uint16_t dpx[kBpPix];
+    if (p0 + kBpPix <= npx) {
+        uint4 raw = *reinterpret_cast<const uint4 *>(a.depth + p0);
+        dpx[0] = raw.x & 0xffff; dpx[1] = raw.x >> 16; dpx[2] = raw.y & 0xffff; dpx[3] = raw.y >> 16;
+        dpx[4] = raw.z & 0xffff; dpx[5] = raw.z >> 16; dpx[6] = raw.w & 0xffff; dpx[7] = raw.w >> 16;
+    } else {
+#pragma unroll
+        for (int k = 0; k < kBpPix; ++k) dpx[k] = (p0 + k < npx) ? a.depth[p0 + k] : (uint16_t)0;
+    }
+    uint32_t nvalid = 0;
+#pragma unroll
+    for (int k = 0; k < kBpPix; ++k) nvalid += (dpx[k] != 0);
+
+    uint32_t tile_valid;
+    uint32_t v_off = block_exclusive_scan(nvalid, s_warp, tile_valid);
+    const unsigned long long tag = (unsigned long long)(epoch << 2) << 32;
+    if (tid == 0) {
+        unsigned long long fl = (tile == 0) ? 2ull : 1ull;
+        st_volatile_u64(&stateV[tile], tag | (fl << 32) | tile_valid);
+    }
+    if (tid < 32) {
+        uint32_t ex = (tile == 0) ? 0u : lookback(stateV, tile, epoch, &failed);
+        if (tid == 0) {
+            if (tile != 0) st_volatile_u64(&stateV[tile], tag | (2ull << 32) | (ex + tile_valid));
+            s_bcast[0] = ex;
+        }
+    }
+    __syncthreads();
+    const uint32_t v_base = s_bcast[0] + v_off;
+
+    // keep decisions
+    uint32_t keep_mask = 0, ord = v_base;
+    const uint32_t rule_arg = a.rule_arg ? a.rule_arg : 1u;
+#pragma unroll
+    for (int k = 0; k < kBpPix; ++k) {
+        if (dpx[k] != 0) {
+            bool keep;
+            switch (a.rule) {
+            case ICPB_SUB_STRIDE: keep = (ord % rule_arg) == 0; break;
+            case ICPB_SUB_HASH: keep = (hash32(a.seed, (uint32_t)(p0 + k)) % rule_arg) == 0; break;
+            case ICPB_SUB_STREAM: keep = (ord < (uint32_t)a.keep_stream_len) && a.keep_stream[ord] != 0; break;
+            default: keep = true; break;
+            }
+            if (keep) keep_mask |= 1u << k;
+            ++ord;
+        }
+    }
+    const uint32_t nkeep = __popc(keep_mask);
+    uint32_t tile_keep;
+    uint32_t k_off = block_exclusive_scan(nkeep, s_warp, tile_keep);
+    if (tid == 0) {
+        unsigned long long fl = (tile == 0) ? 2ull : 1ull;
+        st_volatile_u64(&stateK[tile], tag | (fl << 32) | tile_keep);
+    }
+    if (tid < 32) {
+        uint32_t ex = (tile == 0) ? 0u : lookback(stateK, tile, epoch, &failed);
+        if (tid == 0) {
+            if (tile != 0) st_volatile_u64(&stateK[tile], tag | (2ull << 32) | (ex + tile_keep));
+            s_bcast[1] = ex;
+            if (failed) *a.out_count = -1;
+            else if (tile == a.n_tiles - 1) *a.out_count = (int)(ex + tile_keep);
+        }
+    }
+    __syncthreads();
+    uint32_t o = s_bcast[1] + k_off;
+
+    // pointcloud.cpp:37-39 (134-136): all float, left to right, true division
+#pragma unroll
+    for (int k = 0; k < kBpPix; ++k) {
+        if (keep_mask & (1u << k)) {
+            const int p = p0 + k;
+            const int v = p / a.w, u = p - v * a.w;
+            float pz = ((float)dpx[k]) / a.K.depth_scale;
+            float px = ((float)u - a.K.cx_u) * pz / a.K.fx_u;
+            float py = ((float)v - a.K.cx_v) * pz / a.K.fx_v;
+            uint32_t cbits = 0;
+            if (a.bgr) {
+                const uint8_t *c = a.bgr + (size_t)p * 3;
+                cbits = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16); // :47
+            }
+            if ((int)o < a.capacity) a.out[o] = make_float4(px, py, pz, __uint_as_float(cbits));
+            ++o;
+        }
+    }
+}
+
+void launch_backproject(const BackprojectArgs &a, cudaStream_t s)
+{
+    static uint32_t epoch = 0; // per-process launch counter; stale tile words never match it
+    epoch = (epoch + 1) & 0x3fffffffu;
+    if (epoch == 0) epoch = 1;
+    backproject_kernel<<<a.n_tiles, kBpThreads, 0, s>>>(a, epoch);
+}
+
+// P3, SLAM.cpp:412-430.  Central differences on raw depth units; normalize as
+// cv::normalize(Vec3f): v * (1.0 / sqrt(sum v^2)) in double, rounded to float.
+// Border rows / cols (never written, or read out of bounds, by the reference)
+// are defined as zeros.
+__global__ void normals_kernel(const uint16_t *__restrict__ depth, int w, int h, float *__restrict__ normals)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    int r = blockIdx.y;
+    if (c >= w) return;
+    float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+    if (r >= 1 && r < h - 1 && c >= 1 && c < w - 1) {
+        float up = (float)depth[(size_t)(r - 1) * w + c];
+        float dn = (float)depth[(size_t)(r + 1) * w + c];
+        float lf = (float)depth[(size_t)r * w + c - 1];
+        float rt = (float)depth[(size_t)r * w + c + 1];
+        float dzdx = (dn - up) / 2.0f;
+        float dzdy = (rt - lf) / 2.0f;
+        float v0 = -dzdx, v1 = -dzdy, v2 = 1.0f;
+        double nv = sqrt(((double)v0 * (double)v0 + (double)v1 * (double)v1) + (double)v2 * (double)v2);
+        double inv = 1.0 / nv;
+        n0 = (float)((double)v0 * inv);
+        n1 = (float)((double)v1 * inv);
+        n2 = (float)((double)v2 * inv);
+    }
+    float *o = normals + ((size_t)r * w + c) * 3;
+    o[0] = n0; o[1] = n1; o[2] = n2;
+}
+
+void launch_normals(const uint16_t *depth, int w, int h, float *normals, cudaStream_t s)
+{
+    dim3 grid((w + 127) / 128, h);
+    normals_kernel<<<grid, 128, 0, s>>>(depth, w, h, normals);
+}
+
+// 8f-1, SLAM.cpp:553-573: range threshold (:559-565), then 5x5 rect dilate and
+// erode anchored at (3,3) (:567-573): window offsets [-3,+1] on both axes,
+// out-of-image pixels ignored.
+template <bool kDilate, bool kThreshold>
+__global__ void morph5_kernel(const uint16_t *__restrict__ in, uint16_t *__restrict__ out, int w, int h, int min_d,
+                              int max_d)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    int best = kDilate ? 0 : 65535;
+    for (int dy = -3; dy <= 1; ++dy) {
+        int yy = y + dy;
+        if (yy < 0 || yy >= h) continue;
+        for (int dx = -3; dx <= 1; ++dx) {
+            int xx = x + dx;
+            if (xx < 0 || xx >= w) continue;
+            int v = in[(size_t)yy * w + xx];
+            if (kThreshold) v = (v > max_d || v < min_d) ? 0 : v;
+            best = kDilate ? max(best, v) : min(best, v);
+        }
+    }
+    out[(size_t)y * w + x] = (uint16_t)best;
+}
+
+void launch_depth_filter(const uint16_t *in, uint16_t *tmp_a, uint16_t *tmp_b, uint16_t *out, int w, int h,
+                         int min_d, int max_d, cudaStream_t s)
+{
+    (void)tmp_b;
+    dim3 grid((w + 127) / 128, h);
+    morph5_kernel<true, true><<<grid, 128, 0, s>>>(in, tmp_a, w, h, min_d, max_d);
+    morph5_kernel<false, false><<<grid, 128, 0, s>>>(tmp_a, out, w, h, min_d, max_d);
+}
+
+} // namespace icpb

@@ -1,0 +1,156 @@
+// Internal declarations shared by the translation units of libicpb200.so.
+// Nothing here is part of the C-ABI (include/icpb200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "icpb200.h"
+
+namespace icpb {
+
+// ---- tunables of the brute-force NN kernel (DESIGN.md "N1-N3") -----------
+constexpr int kGroup = 32;          // targets per min-tracking group (exactly re-scanned per query)
+constexpr int kNnThreads = 128;     // threads per CTA of nn_partial
+constexpr int kStageGroups = 16;    // groups per shared-memory stage (16*32*12 B = 6 KB)
+constexpr int kStages = 4;          // TMA bulk-copy ring depth
+constexpr int kChunk = 256;         // canonical reduction chunk (CANON-3)
+constexpr int kTerms = 20;          // a(3) b(3) b a^T(9) d(1) a-b(3) count(1)
+constexpr float kPadCoord = 1.0e18f; // padding targets: (a-b)^2 ~ 3e36, finite, never the minimum
+// second-best group minimum within this relative band of the best => exact FP64 rescan
+constexpr float kBandRel = 1.0f + 1.9073486328125e-06f; // 1 + 2^-19
+constexpr float kBandAbs = 1.0e-30f;
+
+// Per-registration device state: iteration control and pose, kept on the
+// device for the whole loop (icp.cpp:22-25 globals + locals of :28-285).
+struct IcpState {
+    float Rf[9];
+    float tf[3];
+    int apply;          // 1: next pass applies (Rf, tf) to the data cloud while loading it
+    int done;           // loop finished; later passes are no-ops
+    int iterations;     // i of icp.cpp:152
+    int passes;         // association passes executed
+    int last_buf;       // ping-pong buffer holding the cloud the last pass associated
+    int n_assoc;
+    float mse;
+    int small_exit;
+    int pending_translate; // <3 associations rule: apply tf as a plain translation after the loop
+    int rescans;
+    unsigned int block_counter;
+    float rigid[9];
+    float camR[9];
+    float camP[3];
+    float offset[3];
+    double PR[9];
+    double Pt[3];
+};
+
+struct IcpParamsDev {
+    int max_iterations;
+    float threshold;
+    float max_nn_distance;
+    int solve_mode;
+    float last_translation[3];
+};
+
+// One registration problem as the kernels see it (indexed by blockIdx.z).
+struct RegDesc {
+    float4 *D[2];            // ping-pong data cloud buffers (16-B points)
+    const float4 *tgt;       // target, AoS (exact rescans, gathers)
+    const float *tgt_soa;    // target, negated group-tiled SoA: [group][x[32] y[32] z[32]]
+    int n, m, ngroups;
+    int n_stride;            // row stride of the per-split partial arrays
+    float *pm1, *pm2;        // [S][n_stride] best / second-best group minimum (approximate squared distance)
+    int *pg;                 // [S][n_stride] group holding pm1
+    int *idx;                // [n] nearest target index
+    float *dist;             // [n] nearest distance (reference arithmetic)
+    double *chunk_sums;      // [chunks][kTerms]
+    IcpState *st;
+    int *idx_trace;          // nullable [(max_it+1)][n]
+    float *dist_trace;
+};
+
+// ---- launchers (defined in the .cu files) ---------------------------------
+void launch_target_prep(const float4 *tgt, int m, float *soa, int ngroups, cudaStream_t s);
+void launch_nn_partial(const RegDesc *descs, int batch, int max_n, int qpt, int splits, int pass,
+                       cudaStream_t s);
+void launch_nn_finalize(const RegDesc *descs, const IcpParamsDev *prm, int batch, int max_n, int splits,
+                        int pass, cudaStream_t s);
+void launch_transform(float4 *pts, int n, const float *R, const float *t, int have_R, int have_t,
+                      cudaStream_t s);
+void launch_pending_translate(const RegDesc *descs, int batch, int max_n, cudaStream_t s);
+void launch_center(const float4 *pts, int n, double *chunk_sums, double *out3, unsigned int *counter,
+                   cudaStream_t s);
+void launch_fp32_peak(float *out, int blocks, int threads, int iters, cudaStream_t s);
+
+struct BackprojectArgs {
+    const uint16_t *depth;
+    const uint8_t *bgr;     // nullable
+    int w, h;
+    icpb_intrinsics K;
+    int rule;
+    uint32_t rule_arg, seed;
+    const uint8_t *keep_stream; // nullable
+    int keep_stream_len;
+    float4 *out;
+    int capacity;
+    int *out_count;          // device: number of points written
+    unsigned long long *tile_state; // device scratch, zeroed by the launcher
+    unsigned int *ticket;
+    int n_tiles;
+};
+int backproject_tiles(int w, int h);
+void launch_backproject(const BackprojectArgs &a, cudaStream_t s);
+void launch_normals(const uint16_t *depth, int w, int h, float *normals, cudaStream_t s);
+void launch_depth_filter(const uint16_t *in, uint16_t *tmp_a, uint16_t *tmp_b, uint16_t *out, int w, int h,
+                         int min_d, int max_d, cudaStream_t s);
+
+struct MapDev {
+    uint8_t *grid;    // slab storage: [(x*dimY + y)*zs + (z - z_lo)], zs = z_hi - z_lo padded to 4
+    int dims[3];
+    int z_lo, z_hi, zs;
+    float cell;
+};
+void launch_map_endpoints(const MapDev &m, const float4 *pts, int n, int rule, int delta, int max_conf,
+                          cudaStream_t s);
+void launch_map_rays(const MapDev &m, const float4 *pts, int n, const float origin[3], int delta_dec,
+                     unsigned long long *visited, cudaStream_t s);
+
+} // namespace icpb
+
+// ---- handle definitions -----------------------------------------------------
+struct icpb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
+    std::string err;
+    long long launches = 0;
+    int sm_count = 148;
+    // grow-only device workspace
+    struct Buf {
+        void *p = nullptr;
+        size_t bytes = 0;
+    };
+    std::vector<Buf> ws; // indexed by the WS_* ids in api.cu
+    void *pinned = nullptr;
+    size_t pinned_bytes = 0;
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;
+};
+
+struct icpb_cloud {
+    icpb_ctx *ctx = nullptr;
+    float4 *d_pts = nullptr;
+    int capacity = 0;
+    int n = 0;
+};
+
+struct icpb_map {
+    icpb_ctx *ctx = nullptr;
+    icpb::MapDev dev{};
+    long long bytes = 0;
+};

@@ -1,0 +1,824 @@
+// Brute-force nearest-neighbour association + rigid solve, device resident.
+//
+// Replaces (reference file:line, relative to the reference repository):
+//   icp::distance                          icp.cpp:606-620   (N1)
+//   icp::getNearestPoint                   icp.cpp:566-593   (N2)
+//   icp::findGlobalNearestNeighborAssociations icp.cpp:541-563 (N3)
+//   the solve / pose update / convergence test of icp::getTransformation
+//                                          icp.cpp:155-258   (S1-S3)
+//   icp::calculateOffset icp.cpp:314-344, icp::meanSquareError icp.cpp:622-638
+//   PointCloud::rotate / translate         pointcloud.cpp:321-359 (P2, fused into the query load)
+//
+// Built with -fmad=false: every float / double expression below is evaluated
+// with separately rounded IEEE operations, like the reference's /fp:precise
+// build.  The only fused multiply-adds are the explicit fma.rn.f32x2 of the
+// approximate filter, whose result never reaches an output.
+#include <math_constants.h>
+
+#include "icpb_internal.h"
+
+namespace icpb {
+
+// --------------------------------------------------------------------------
+// packed FP32x2 helpers (sm_100a FADD2 / FMUL2 / FFMA2) and 3-input min (FMNMX3)
+// --------------------------------------------------------------------------
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pack2(float lo, float hi)
+{
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b)
+{
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b)
+{
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
+{
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ float min3(float a, float b, float c)
+{
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// --------------------------------------------------------------------------
+// mbarrier + 1-D bulk TMA (cp.async.bulk -> SASS UBLKCP)
+// --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// --------------------------------------------------------------------------
+// exact reference arithmetic
+// --------------------------------------------------------------------------
+
+// icp.cpp:606-620: float differences; squares and their left-to-right sum in
+// double (pow(float,2) promotes); ONE rounding to float; correctly rounded
+// float sqrt.  No FMA anywhere (-fmad=false).
+__device__ __forceinline__ float exact_distance(float ax, float ay, float az, float bx, float by, float bz)
+{
+    float x = ax - bx;
+    float y = ay - by;
+    float z = az - bz;
+    double s = ((double)x * (double)x + (double)y * (double)y) + (double)z * (double)z;
+    float xyz = (float)s;
+    return sqrtf(xyz);
+}
+
+// pointcloud.cpp:321-331 (rotate: OpenCV 3x3 by 3xN float gemm = float, no
+// FMA, left to right) followed by :349-359 (translate: float add).
+__device__ __forceinline__ float4 apply_rt(float4 p, const float *R, const float *t)
+{
+    float4 o;
+    o.x = ((R[0] * p.x + R[1] * p.y) + R[2] * p.z) + t[0];
+    o.y = ((R[3] * p.x + R[4] * p.y) + R[5] * p.z) + t[1];
+    o.z = ((R[6] * p.x + R[7] * p.y) + R[8] * p.z) + t[2];
+    o.w = p.w;
+    return o;
+}
+
+// --------------------------------------------------------------------------
+// target preparation: AoS -> negated, group-tiled SoA, padded to whole groups
+// --------------------------------------------------------------------------
+__global__ void target_prep_kernel(const float4 *__restrict__ tgt, int m, float *__restrict__ soa, int ngroups)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ngroups * kGroup) return;
+    float x = -kPadCoord, y = -kPadCoord, z = -kPadCoord;
+    if (t < m) {
+        float4 p = tgt[t];
+        x = -p.x; y = -p.y; z = -p.z;
+    }
+    int g = t / kGroup, l = t % kGroup;
+    float *base = soa + (size_t)g * (3 * kGroup);
+    base[l] = x;
+    base[kGroup + l] = y;
+    base[2 * kGroup + l] = z;
+}
+
+void launch_target_prep(const float4 *tgt, int m, float *soa, int ngroups, cudaStream_t s)
+{
+    int total = ngroups * kGroup;
+    target_prep_kernel<<<(total + 255) / 256, 256, 0, s>>>(tgt, m, soa, ngroups);
+}
+
+// --------------------------------------------------------------------------
+// nn_partial: the N x M scan (approximate FP32 filter, group minima)
+// --------------------------------------------------------------------------
+//
+// Each thread keeps QPT queries in registers and streams the targets of its
+// split through shared memory (bulk-TMA ring).  Per (query, target) pair the
+// FMA pipe sees 3 FADD + 1 FMUL + 2 FFMA (packed two targets at a time), and
+// the ALU pipe half an FMNMX3.  Per group of 32 targets it keeps the best and
+// second-best GROUP minimum and the best group's id; nn_finalize re-evaluates
+// the best group in the reference's exact arithmetic.
+template <int QPT>
+__global__ void __launch_bounds__(kNnThreads) nn_partial_kernel(const RegDesc *__restrict__ descs, int splits,
+                                                                int pass)
+{
+    const RegDesc &d = descs[blockIdx.z];
+    IcpState *st = d.st;
+    if (st->done) return;
+    const int n = d.n;
+    const int q0 = blockIdx.x * (kNnThreads * QPT);
+    if (q0 >= n) return;
+    const int split = blockIdx.y;
+    const int tid = threadIdx.x;
+
+    const int gps = (d.ngroups + splits - 1) / splits;
+    const int g_begin = split * gps;
+    const int g_end = min(d.ngroups, g_begin + gps);
+    const int n_tiles = (g_end > g_begin) ? (g_end - g_begin + kStageGroups - 1) / kStageGroups : 0;
+
+    constexpr int kStageFloats = kStageGroups * kGroup * 3;
+    __shared__ __align__(128) float s_tile[kStages][kStageFloats];
+    __shared__ __align__(8) uint64_t s_full[kStages];
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&s_full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const float *soa = d.tgt_soa;
+    auto issue = [&](int tile) {
+        int gb = g_begin + tile * kStageGroups;
+        int ng = min(kStageGroups, g_end - gb);
+        uint32_t bytes = (uint32_t)ng * (kGroup * 3 * sizeof(float));
+        int s = tile % kStages;
+        mbar_expect_tx(&s_full[s], bytes);
+        tma_bulk_g2s(&s_tile[s][0], soa + (size_t)gb * (kGroup * 3), bytes, &s_full[s]);
+    };
+    if (tid == 0) {
+        for (int t = 0; t < kStages && t < n_tiles; ++t) issue(t);
+    }
+
+    // ---- queries: load, apply the pending rigid motion, hand on to the next buffer
+    const float4 *src = d.D[pass & 1];
+    float4 *dst = d.D[(pass + 1) & 1];
+    const int apply = st->apply;
+    float R[9], T[3];
+    if (apply) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[k] = st->Rf[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) T[k] = st->tf[k];
+    }
+    float ax[QPT], ay[QPT], az[QPT];
+#pragma unroll
+    for (int q = 0; q < QPT; ++q) {
+        int i = q0 + q * kNnThreads + tid;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n) {
+            p = src[i];
+            if (apply) p = apply_rt(p, R, T);
+            if (split == 0) dst[i] = p;
+        }
+        ax[q] = p.x; ay[q] = p.y; az[q] = p.z;
+    }
+
+    float m1[QPT], m2[QPT];
+    int g1[QPT];
+#pragma unroll
+    for (int q = 0; q < QPT; ++q) {
+        m1[q] = CUDART_INF_F; m2[q] = CUDART_INF_F; g1[q] = g_begin < d.ngroups ? g_begin : 0;
+    }
+
+    for (int tile = 0; tile < n_tiles; ++tile) {
+        const int s = tile % kStages;
+        mbar_wait(&s_full[s], (uint32_t)((tile / kStages) & 1));
+        const int gb = g_begin + tile * kStageGroups;
+        const int ng = min(kStageGroups, g_end - gb);
+        for (int gi = 0; gi < ng; ++gi) {
+            const float4 *s4 = reinterpret_cast<const float4 *>(&s_tile[s][gi * (kGroup * 3)]);
+            float gm[QPT];
+#pragma unroll
+            for (int q = 0; q < QPT; ++q) gm[q] = CUDART_INF_F;
+#pragma unroll 2
+            for (int j = 0; j < kGroup / 4; ++j) {
+                const float4 X = s4[j];
+                const float4 Y = s4[kGroup / 4 + j];
+                const float4 Z = s4[2 * (kGroup / 4) + j];
+                const u64 x01 = pack2(X.x, X.y), x23 = pack2(X.z, X.w);
+                const u64 y01 = pack2(Y.x, Y.y), y23 = pack2(Y.z, Y.w);
+                const u64 z01 = pack2(Z.x, Z.y), z23 = pack2(Z.z, Z.w);
+#pragma unroll
+                for (int q = 0; q < QPT; ++q) {
+                    const u64 qx = pack2(ax[q], ax[q]);
+                    const u64 qy = pack2(ay[q], ay[q]);
+                    const u64 qz = pack2(az[q], az[q]);
+                    u64 dxa = add2(qx, x01), dxb = add2(qx, x23);
+                    u64 dya = add2(qy, y01), dyb = add2(qy, y23);
+                    u64 dza = add2(qz, z01), dzb = add2(qz, z23);
+                    u64 sa = mul2(dxa, dxa), sb = mul2(dxb, dxb);
+                    sa = fma2(dya, dya, sa); sb = fma2(dyb, dyb, sb);
+                    sa = fma2(dza, dza, sa); sb = fma2(dzb, dzb, sb);
+                    float s0, s1, s2, s3;
+                    unpack2(sa, s0, s1);
+                    unpack2(sb, s2, s3);
+                    gm[q] = min3(gm[q], s0, s1);
+                    gm[q] = min3(gm[q], s2, s3);
+                }
+            }
+            const int g = gb + gi;
+#pragma unroll
+            for (int q = 0; q < QPT; ++q) {
+                m2[q] = fminf(m2[q], fmaxf(m1[q], gm[q]));
+                if (gm[q] < m1[q]) { m1[q] = gm[q]; g1[q] = g; }
+            }
+        }
+        __syncthreads(); // every warp is done with stage s
+        if (tid == 0 && tile + kStages < n_tiles) issue(tile + kStages);
+    }
+
+    const size_t row = (size_t)split * d.n_stride;
+#pragma unroll
+    for (int q = 0; q < QPT; ++q) {
+        int i = q0 + q * kNnThreads + tid;
+        if (i < n) {
+            d.pm1[row + i] = m1[q];
+            d.pm2[row + i] = m2[q];
+            d.pg[row + i] = g1[q];
+        }
+    }
+}
+
+void launch_nn_partial(const RegDesc *descs, int batch, int max_n, int qpt, int splits, int pass, cudaStream_t s)
+{
+    dim3 block(kNnThreads);
+    if (qpt == 8) {
+        dim3 grid((max_n + kNnThreads * 8 - 1) / (kNnThreads * 8), splits, batch);
+        nn_partial_kernel<8><<<grid, block, 0, s>>>(descs, splits, pass);
+    } else if (qpt == 4) {
+        dim3 grid((max_n + kNnThreads * 4 - 1) / (kNnThreads * 4), splits, batch);
+        nn_partial_kernel<4><<<grid, block, 0, s>>>(descs, splits, pass);
+    } else {
+        dim3 grid((max_n + kNnThreads * 2 - 1) / (kNnThreads * 2), splits, batch);
+        nn_partial_kernel<2><<<grid, block, 0, s>>>(descs, splits, pass);
+    }
+}
+
+// --------------------------------------------------------------------------
+// canonical FP64 block-ordered reduction pieces (CANON-3)
+// --------------------------------------------------------------------------
+__device__ __forceinline__ double warp_fold(double v)
+{
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v = v + __shfl_down_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// --------------------------------------------------------------------------
+// 3x3 SVD (one-sided Jacobi, double) -- stands in for cv::SVD, icp.cpp:215.
+// Same operation sequence as the host-side oracle so results are bit equal.
+// --------------------------------------------------------------------------
+__device__ void svd3(const double *Ain, double *U, double *w, double *Vt)
+{
+    double A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int k = 0; k < 9; ++k) A[k] = Ain[k];
+    const double eps = 2.220446049250313e-16;
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        int changed = 0;
+        for (int k = 0; k < 3; ++k) {
+            const int p = (k == 2) ? 1 : 0;
+            const int q = (k == 0) ? 1 : 2;
+            double alpha = (A[p] * A[p] + A[3 + p] * A[3 + p]) + A[6 + p] * A[6 + p];
+            double beta = (A[q] * A[q] + A[3 + q] * A[3 + q]) + A[6 + q] * A[6 + q];
+            double gamma = (A[p] * A[q] + A[3 + p] * A[3 + q]) + A[6 + p] * A[6 + q];
+            if (fabs(gamma) <= eps * sqrt(alpha * beta)) continue;
+            changed = 1;
+            double zeta = (beta - alpha) / (2.0 * gamma);
+            double az = fabs(zeta);
+            double t = 1.0 / (az + sqrt(1.0 + zeta * zeta));
+            if (zeta < 0.0) t = -t;
+            double c = 1.0 / sqrt(1.0 + t * t);
+            double s = c * t;
+            for (int r = 0; r < 3; ++r) {
+                double a = A[3 * r + p], b = A[3 * r + q];
+                A[3 * r + p] = c * a - s * b;
+                A[3 * r + q] = s * a + c * b;
+                double va = V[3 * r + p], vb = V[3 * r + q];
+                V[3 * r + p] = c * va - s * vb;
+                V[3 * r + q] = s * va + c * vb;
+            }
+        }
+        if (!changed) break;
+    }
+    for (int k = 0; k < 3; ++k) w[k] = sqrt((A[k] * A[k] + A[3 + k] * A[3 + k]) + A[6 + k] * A[6 + k]);
+    for (int i = 0; i < 2; ++i) {
+        int best = i;
+        for (int j = i + 1; j < 3; ++j)
+            if (w[j] > w[best]) best = j;
+        if (best != i) {
+            double tw = w[i]; w[i] = w[best]; w[best] = tw;
+            for (int r = 0; r < 3; ++r) {
+                double ta = A[3 * r + i]; A[3 * r + i] = A[3 * r + best]; A[3 * r + best] = ta;
+                double tv = V[3 * r + i]; V[3 * r + i] = V[3 * r + best]; V[3 * r + best] = tv;
+            }
+        }
+    }
+    for (int k = 0; k < 3; ++k) {
+        if (w[k] > 0.0) {
+            for (int r = 0; r < 3; ++r) U[3 * r + k] = A[3 * r + k] / w[k];
+        } else {
+            for (int r = 0; r < 3; ++r) U[3 * r + k] = 0.0;
+        }
+    }
+    if (!(w[2] > 0.0) && w[1] > 0.0) {
+        U[2] = U[3] * U[7] - U[6] * U[4];
+        U[5] = U[6] * U[1] - U[0] * U[7];
+        U[8] = U[0] * U[4] - U[3] * U[1];
+    }
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) Vt[3 * i + j] = V[3 * j + i];
+}
+
+// cv::Mat operator* on 3x3 CV_32F (icp.cpp:218,231,237): float, no FMA.
+__device__ void gemm33f(const float *A, const float *B, float *C)
+{
+    float T[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) T[3 * i + j] = (A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j]) + A[3 * i + 2] * B[6 + j];
+    for (int k = 0; k < 9; ++k) C[k] = T[k];
+}
+// cv::determinant on 3x3 CV_32F (icp.cpp:220): evaluated in double.
+__device__ double det33f(const float *m)
+{
+    double m00 = m[0], m01 = m[1], m02 = m[2], m10 = m[3], m11 = m[4], m12 = m[5], m20 = m[6], m21 = m[7],
+           m22 = m[8];
+    return m00 * (m11 * m22 - m12 * m21) - m01 * (m10 * m22 - m12 * m20) + m02 * (m10 * m21 - m11 * m20);
+}
+// Mat::inv() on 3x3 CV_32F (icp.cpp:235): adjugate in double times 1/det.
+__device__ void inv33f(const float *Sf, float *D)
+{
+    double d = det33f(Sf);
+    if (d == 0.0) {
+        for (int k = 0; k < 9; ++k) D[k] = 0.f;
+        return;
+    }
+    d = 1.0 / d;
+    double S[9];
+    for (int i = 0; i < 9; ++i) S[i] = Sf[i];
+    float T[9];
+    T[0] = (float)((S[4] * S[8] - S[5] * S[7]) * d);
+    T[1] = (float)((S[2] * S[7] - S[1] * S[8]) * d);
+    T[2] = (float)((S[1] * S[5] - S[2] * S[4]) * d);
+    T[3] = (float)((S[5] * S[6] - S[3] * S[8]) * d);
+    T[4] = (float)((S[0] * S[8] - S[2] * S[6]) * d);
+    T[5] = (float)((S[2] * S[3] - S[0] * S[5]) * d);
+    T[6] = (float)((S[3] * S[7] - S[4] * S[6]) * d);
+    T[7] = (float)((S[1] * S[6] - S[0] * S[7]) * d);
+    T[8] = (float)((S[0] * S[4] - S[1] * S[3]) * d);
+    for (int k = 0; k < 9; ++k) D[k] = T[k];
+}
+
+// meanSquareError, icp.cpp:622-638: (sum(errors)/n)^2.
+__device__ float mse_from_sums(const double *sums)
+{
+    if (!(sums[19] > 0.0)) return 0.f;
+    float e = (float)(sums[15] / sums[19]);
+    return (float)((double)e * (double)e);
+}
+
+// The body of the while loop of icp.cpp:155-258 for one iteration, minus the
+// association itself.  Runs in one thread.
+__device__ void solve_step(IcpState *st, const IcpParamsDev *prm, const double *sums, int pass)
+{
+    st->passes = pass + 1;
+    st->last_buf = (pass + 1) & 1;
+    st->apply = 0;
+    const float mse = mse_from_sums(sums);
+    const int n_assoc = (int)sums[19];
+    st->mse = mse;
+    st->n_assoc = n_assoc;
+    const int i = st->iterations;
+    if (!(mse > prm->threshold && i < prm->max_iterations)) { // icp.cpp:155
+        st->done = 1;
+        return;
+    }
+    if (n_assoc < 3) { // icp.cpp:163-182
+        st->iterations = prm->max_iterations;
+        for (int k = 0; k < 3; ++k) {
+            st->offset[k] = -prm->last_translation[k];
+            st->tf[k] = prm->last_translation[k];
+            st->Pt[k] += (double)prm->last_translation[k];
+        }
+        st->pending_translate = 1;
+        st->small_exit = 1;
+        st->done = 1;
+        return;
+    }
+    float Rf[9], tf[3];
+    double U[9], w[3], Vt[9], Rd[9];
+    if (prm->solve_mode == ICPB_SOLVE_REFERENCE) {
+        svd3(&sums[6], U, w, Vt); // icp.cpp:212-215, M = sum b a^T (uncentred)
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c)
+                Rd[3 * r + c] = (Vt[r] * U[3 * c] + Vt[3 + r] * U[3 * c + 1]) + Vt[6 + r] * U[3 * c + 2]; // :218
+        float R[9];
+        for (int k = 0; k < 9; ++k) R[k] = (float)Rd[k];
+        if (det33f(R) < 0) { R[2] *= -1; R[5] *= -1; R[8] *= -1; } // :220-223
+        if (i == 0) { for (int k = 0; k < 9; ++k) st->rigid[k] = R[k]; } // :227-229
+        else gemm33f(R, st->rigid, st->rigid);                           // :230-233
+        inv33f(R, Rf);                                                   // :235
+        gemm33f(st->camR, Rf, st->camR);                                 // :237
+        for (int k = 0; k < 3; ++k) {
+            st->offset[k] = (float)(sums[16 + k] / sums[19]);            // :240, :314-344
+            tf[k] = -st->offset[k];                                      // :245
+            st->camP[k] -= st->offset[k];                                // :246
+        }
+    } else {
+        // rigid_transform_3D.py:14-37 with A = data, B = matches
+        double cnt = sums[19];
+        double cA[3] = {sums[0] / cnt, sums[1] / cnt, sums[2] / cnt};
+        double cB[3] = {sums[3] / cnt, sums[4] / cnt, sums[5] / cnt};
+        double H[9];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) H[3 * r + c] = sums[6 + 3 * c + r] - (cnt * cA[r]) * cB[c];
+        svd3(H, U, w, Vt);
+        for (int p = 0; p < 2; ++p) {
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c)
+                    Rd[3 * r + c] = (Vt[r] * U[3 * c] + Vt[3 + r] * U[3 * c + 1]) + Vt[6 + r] * U[3 * c + 2];
+            double det = Rd[0] * (Rd[4] * Rd[8] - Rd[5] * Rd[7]) - Rd[1] * (Rd[3] * Rd[8] - Rd[5] * Rd[6]) +
+                         Rd[2] * (Rd[3] * Rd[7] - Rd[4] * Rd[6]);
+            if (p == 0 && det < 0) { Vt[6] *= -1; Vt[7] *= -1; Vt[8] *= -1; }
+            else break;
+        }
+        for (int k = 0; k < 9; ++k) Rf[k] = (float)Rd[k];
+        for (int r = 0; r < 3; ++r) {
+            tf[r] = (float)(cB[r] - ((Rd[3 * r] * cA[0] + Rd[3 * r + 1] * cA[1]) + Rd[3 * r + 2] * cA[2]));
+            st->offset[r] = -tf[r];
+        }
+    }
+    // composed pose, in double, from the float motion actually applied
+    double NR[9], Nt[3];
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c)
+            NR[3 * r + c] = ((double)Rf[3 * r] * st->PR[c] + (double)Rf[3 * r + 1] * st->PR[3 + c]) +
+                            (double)Rf[3 * r + 2] * st->PR[6 + c];
+        Nt[r] = (((double)Rf[3 * r] * st->Pt[0] + (double)Rf[3 * r + 1] * st->Pt[1]) + (double)Rf[3 * r + 2] * st->Pt[2]) +
+                (double)tf[r];
+    }
+    for (int k = 0; k < 9; ++k) { st->PR[k] = NR[k]; st->Rf[k] = Rf[k]; }
+    for (int k = 0; k < 3; ++k) { st->Pt[k] = Nt[k]; st->tf[k] = tf[k]; }
+    st->apply = 1;
+    st->iterations = i + 1;
+}
+
+// --------------------------------------------------------------------------
+// nn_finalize: exact resolution, association sums, solve
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__restrict__ descs,
+                                                             const IcpParamsDev *__restrict__ prm, int splits,
+                                                             int pass)
+{
+    const RegDesc &d = descs[blockIdx.z];
+    IcpState *st = d.st;
+    if (st->done) return;
+    const int n = d.n, m = d.m;
+    const int chunk = blockIdx.x;
+    if (chunk * kChunk >= n) return;
+    const int nchunks = (n + kChunk - 1) / kChunk;
+    const int tid = threadIdx.x;
+    const int i = chunk * kChunk + tid;
+    const bool valid = i < n;
+
+    __shared__ float4 s_pts[kChunk];
+    __shared__ int s_list[kChunk];
+    __shared__ int s_cnt;
+    __shared__ float s_rd[kChunk / 32];
+    __shared__ int s_ri[kChunk / 32];
+    __shared__ double s_w[kChunk / 32][kTerms];
+    __shared__ double s_tot[kTerms];
+    __shared__ int s_last;
+
+    if (tid == 0) s_cnt = 0;
+    const float4 *cur = d.D[(pass + 1) & 1];
+    float4 a = valid ? cur[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    s_pts[tid] = a;
+    __syncthreads();
+
+    // ---- combine the per-split (best, second-best, group) records, ascending split order
+    float m1 = CUDART_INF_F, m2 = CUDART_INF_F;
+    int g = 0;
+    if (valid) {
+        for (int s = 0; s < splits; ++s) {
+            size_t o = (size_t)s * d.n_stride + i;
+            float p1 = d.pm1[o], p2 = d.pm2[o];
+            int pgv = d.pg[o];
+            m2 = fminf(fminf(m2, p2), fmaxf(m1, p1));
+            if (p1 < m1) { m1 = p1; g = pgv; }
+        }
+    }
+    int best_i = 0;
+    float best_d = 0.f;
+    bool ambiguous = valid && !(m2 > m1 * kBandRel + kBandAbs);
+    if (valid && !ambiguous) {
+        // exact re-evaluation of the winning group (reference arithmetic, ascending index, strict <)
+        const int t0 = g * kGroup;
+        const int t1 = min(m, t0 + kGroup);
+        float4 b = d.tgt[t0];
+        best_d = exact_distance(a.x, a.y, a.z, b.x, b.y, b.z);
+        best_i = t0;
+        for (int t = t0 + 1; t < t1; ++t) {
+            b = d.tgt[t];
+            float dd = exact_distance(a.x, a.y, a.z, b.x, b.y, b.z);
+            if (dd < best_d) { best_d = dd; best_i = t; }
+        }
+    }
+    if (ambiguous) {
+        int slot = atomicAdd(&s_cnt, 1);
+        s_list[slot] = tid;
+    }
+    __syncthreads();
+
+    // ---- near-tie queries: CTA-cooperative full scan in exact arithmetic
+    const int n_amb = s_cnt;
+    for (int e = 0; e < n_amb; ++e) {
+        const int owner = s_list[e];
+        const float4 q = s_pts[owner];
+        float bd = CUDART_INF_F;
+        int bi = 0x7fffffff;
+        for (int t = tid; t < m; t += kChunk) {
+            float4 b = d.tgt[t];
+            float dd = exact_distance(q.x, q.y, q.z, b.x, b.y, b.z);
+            if (dd < bd) { bd = dd; bi = t; }
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            float od = __shfl_xor_sync(0xffffffffu, bd, off);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        if ((tid & 31) == 0) { s_rd[tid >> 5] = bd; s_ri[tid >> 5] = bi; }
+        __syncthreads();
+        if (tid == owner) {
+            bd = s_rd[0]; bi = s_ri[0];
+            for (int wv = 1; wv < kChunk / 32; ++wv) {
+                float od = s_rd[wv];
+                int oi = s_ri[wv];
+                if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+            }
+            if (bi == 0x7fffffff) { // every distance was NaN: the reference keeps target[0]
+                float4 b = d.tgt[0];
+                bi = 0;
+                bd = exact_distance(q.x, q.y, q.z, b.x, b.y, b.z);
+            }
+            best_d = bd; best_i = bi;
+        }
+        __syncthreads();
+    }
+
+    if (valid) {
+        d.idx[i] = best_i;
+        d.dist[i] = best_d;
+        if (d.idx_trace) d.idx_trace[(size_t)pass * n + i] = best_i;
+        if (d.dist_trace) d.dist_trace[(size_t)pass * n + i] = best_d;
+    }
+
+    // ---- association sums (CANON-3 level 1)
+    double t[kTerms];
+    const bool accepted = valid && (best_d < prm->max_nn_distance); // icp.cpp:553
+    if (accepted) {
+        float4 b = d.tgt[best_i];
+        t[0] = a.x; t[1] = a.y; t[2] = a.z;
+        t[3] = b.x; t[4] = b.y; t[5] = b.z;
+        t[6] = (double)b.x * (double)a.x; t[7] = (double)b.x * (double)a.y; t[8] = (double)b.x * (double)a.z;
+        t[9] = (double)b.y * (double)a.x; t[10] = (double)b.y * (double)a.y; t[11] = (double)b.y * (double)a.z;
+        t[12] = (double)b.z * (double)a.x; t[13] = (double)b.z * (double)a.y; t[14] = (double)b.z * (double)a.z;
+        t[15] = best_d;
+        t[16] = (double)(a.x - b.x); t[17] = (double)(a.y - b.y); t[18] = (double)(a.z - b.z);
+        t[19] = 1.0;
+    } else {
+#pragma unroll
+        for (int k = 0; k < kTerms; ++k) t[k] = 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < kTerms; ++k) {
+        double v = warp_fold(t[k]);
+        if ((tid & 31) == 0) s_w[tid >> 5][k] = v;
+    }
+    __syncthreads();
+    if (tid < kTerms) {
+        double s = s_w[0][tid];
+        for (int wv = 1; wv < kChunk / 32; ++wv) s = s + s_w[wv][tid];
+        d.chunk_sums[(size_t)chunk * kTerms + tid] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        if (n_amb) atomicAdd(&st->rescans, n_amb);
+        unsigned int ticket = atomicAdd(&st->block_counter, 1u);
+        s_last = (ticket == (unsigned int)(nchunks - 1));
+    }
+    __syncthreads();
+    if (!s_last) return;
+
+    // ---- last CTA of this registration: CANON-3 level 2, then the solve
+    __threadfence();
+    for (int k = 0; k < kTerms; ++k) {
+        double acc = 0.0;
+        for (int c = tid; c < nchunks; c += kChunk) acc = acc + __ldcg(&d.chunk_sums[(size_t)c * kTerms + k]);
+        double v = warp_fold(acc);
+        if ((tid & 31) == 0) s_w[tid >> 5][k] = v;
+    }
+    __syncthreads();
+    if (tid < kTerms) {
+        double s = s_w[0][tid];
+        for (int wv = 1; wv < kChunk / 32; ++wv) s = s + s_w[wv][tid];
+        s_tot[tid] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        st->block_counter = 0;
+        solve_step(st, prm, s_tot, pass);
+    }
+}
+
+void launch_nn_finalize(const RegDesc *descs, const IcpParamsDev *prm, int batch, int max_n, int splits, int pass,
+                        cudaStream_t s)
+{
+    dim3 grid((max_n + kChunk - 1) / kChunk, 1, batch);
+    nn_finalize_kernel<<<grid, kChunk, 0, s>>>(descs, prm, splits, pass);
+}
+
+// --------------------------------------------------------------------------
+// stand-alone P2 transform, and the deferred translation of the <3 rule
+// --------------------------------------------------------------------------
+__global__ void transform_kernel(float4 *pts, int n, const float *__restrict__ Rp, const float *__restrict__ tp,
+                                 int have_R, int have_t)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = pts[i];
+    if (have_R) {
+        float x = (Rp[0] * p.x + Rp[1] * p.y) + Rp[2] * p.z;
+        float y = (Rp[3] * p.x + Rp[4] * p.y) + Rp[5] * p.z;
+        float z = (Rp[6] * p.x + Rp[7] * p.y) + Rp[8] * p.z;
+        p.x = x; p.y = y; p.z = z;
+    }
+    if (have_t) { p.x += tp[0]; p.y += tp[1]; p.z += tp[2]; }
+    pts[i] = p;
+}
+
+void launch_transform(float4 *pts, int n, const float *R, const float *t, int have_R, int have_t, cudaStream_t s)
+{
+    if (n <= 0) return;
+    transform_kernel<<<(n + 255) / 256, 256, 0, s>>>(pts, n, R, t, have_R, have_t);
+}
+
+__global__ void pending_translate_kernel(const RegDesc *__restrict__ descs)
+{
+    const RegDesc &d = descs[blockIdx.z];
+    const IcpState *st = d.st;
+    if (!st->pending_translate) return;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n) return;
+    float4 *buf = d.D[st->last_buf];
+    float4 p = buf[i];
+    p.x += st->tf[0]; p.y += st->tf[1]; p.z += st->tf[2];
+    buf[i] = p;
+}
+
+void launch_pending_translate(const RegDesc *descs, int batch, int max_n, cudaStream_t s)
+{
+    dim3 grid((max_n + 255) / 256, 1, batch);
+    pending_translate_kernel<<<grid, 256, 0, s>>>(descs);
+}
+
+// --------------------------------------------------------------------------
+// PointCloud::center (pointcloud.cpp:43-45,100-102) in the canonical FP64 order
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(kChunk) center_kernel(const float4 *__restrict__ pts, int n, double *chunk_sums,
+                                                        double *out3, unsigned int *counter)
+{
+    const int tid = threadIdx.x;
+    const int i = blockIdx.x * kChunk + tid;
+    const int nchunks = (n + kChunk - 1) / kChunk;
+    __shared__ double s_w[kChunk / 32][3];
+    __shared__ int s_last;
+    double t[3] = {0.0, 0.0, 0.0};
+    if (i < n) {
+        float4 p = pts[i];
+        t[0] = p.x; t[1] = p.y; t[2] = p.z;
+    }
+    for (int k = 0; k < 3; ++k) {
+        double v = warp_fold(t[k]);
+        if ((tid & 31) == 0) s_w[tid >> 5][k] = v;
+    }
+    __syncthreads();
+    if (tid < 3) {
+        double s = s_w[0][tid];
+        for (int wv = 1; wv < kChunk / 32; ++wv) s = s + s_w[wv][tid];
+        chunk_sums[(size_t)blockIdx.x * 3 + tid] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(counter, 1u) == (unsigned int)(nchunks - 1));
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int k = 0; k < 3; ++k) {
+        double acc = 0.0;
+        for (int c = tid; c < nchunks; c += kChunk) acc = acc + __ldcg(&chunk_sums[(size_t)c * 3 + k]);
+        double v = warp_fold(acc);
+        if ((tid & 31) == 0) s_w[tid >> 5][k] = v;
+    }
+    __syncthreads();
+    if (tid < 3) {
+        double s = s_w[0][tid];
+        for (int wv = 1; wv < kChunk / 32; ++wv) s = s + s_w[wv][tid];
+        out3[tid] = s / (double)n;
+    }
+    if (tid == 0) *counter = 0;
+}
+
+void launch_center(const float4 *pts, int n, double *chunk_sums, double *out3, unsigned int *counter, cudaStream_t s)
+{
+    center_kernel<<<(n + kChunk - 1) / kChunk, kChunk, 0, s>>>(pts, n, chunk_sums, out3, counter);
+}
+
+// --------------------------------------------------------------------------
+// FP32 FMA peak micro-benchmark (roofline denominator of nn_partial)
+// --------------------------------------------------------------------------
+__global__ void fp32_peak_kernel(float *out, int iters)
+{
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+    float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float b = 0.999f, c = 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = __fmaf_rn(a0, b, c); a1 = __fmaf_rn(a1, b, c); a2 = __fmaf_rn(a2, b, c); a3 = __fmaf_rn(a3, b, c);
+            a4 = __fmaf_rn(a4, b, c); a5 = __fmaf_rn(a5, b, c); a6 = __fmaf_rn(a6, b, c); a7 = __fmaf_rn(a7, b, c);
+        }
+    }
+    float r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+void launch_fp32_peak(float *out, int blocks, int threads, int iters, cudaStream_t s)
+{
+    fp32_peak_kernel<<<blocks, threads, 0, s>>>(out, iters);
+}
+
+} // namespace icpb

@@ -1,0 +1,351 @@
+"""ctypes binding over the C-ABI of libicpb200.so (include/icpb200.h).
+
+This is harness plumbing for tests/ and bench.py: every compute call goes
+through the same extern "C" entry points a C++ host would bind.  There is no
+CPU fallback: importing works without a GPU (so the symbol table can be
+checked), but any compute call fails loudly when the library or a CUDA
+device is missing.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+LIB_PATH = os.path.join(_PKG, "lib", "libicpb200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "icpb200.h")
+
+POINT_DTYPE = np.dtype(
+    [("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("c0", "u1"), ("c1", "u1"), ("c2", "u1"), ("pad", "u1")]
+)
+
+OK, ERR_INVALID, ERR_EMPTY, ERR_CUDA, ERR_CAPACITY = 0, 1, 2, 3, 4
+SUB_NONE, SUB_STRIDE, SUB_HASH, SUB_STREAM = 0, 1, 2, 3
+SOLVE_REFERENCE, SOLVE_KABSCH = 0, 1
+RULE_A, RULE_C = 0, 1
+
+
+class IcpbError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"icpb status {status}: {message}")
+        self.status = status
+
+
+class Intrinsics(C.Structure):
+    _fields_ = [("fx_u", C.c_float), ("cx_u", C.c_float), ("fx_v", C.c_float), ("cx_v", C.c_float),
+                ("depth_scale", C.c_float)]
+
+
+class IcpParams(C.Structure):
+    _fields_ = [("max_iterations", C.c_int), ("threshold", C.c_float), ("max_nn_distance", C.c_float),
+                ("solve_mode", C.c_int), ("last_translation", C.c_float * 3),
+                ("idx_trace", C.c_void_p), ("dist_trace", C.c_void_p)]
+
+
+class IcpResult(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("nn_passes", C.c_int), ("n_assoc", C.c_int), ("mse", C.c_float),
+                ("rigid", C.c_float * 16), ("cam_rotation", C.c_float * 9), ("cam_position", C.c_float * 3),
+                ("offset", C.c_float * 3), ("pose_R", C.c_double * 9), ("pose_t", C.c_double * 3),
+                ("small_assoc_exit", C.c_int), ("exact_rescans", C.c_int), ("gpu_ms", C.c_float),
+                ("kernel_launches", C.c_int), ("nn_partial_ms", C.c_float), ("nn_partial_launches", C.c_int),
+                ("nn_qpt", C.c_int), ("nn_splits", C.c_int)]
+
+    def to_dict(self):
+        return {
+            "iterations": self.iterations, "nn_passes": self.nn_passes, "n_assoc": self.n_assoc, "mse": self.mse,
+            "rigid": np.array(self.rigid[:], dtype=np.float32).reshape(4, 4),
+            "cam_rotation": np.array(self.cam_rotation[:], dtype=np.float32).reshape(3, 3),
+            "cam_position": np.array(self.cam_position[:], dtype=np.float32),
+            "offset": np.array(self.offset[:], dtype=np.float32),
+            "pose_R": np.array(self.pose_R[:]).reshape(3, 3), "pose_t": np.array(self.pose_t[:]),
+            "small_assoc_exit": self.small_assoc_exit, "exact_rescans": self.exact_rescans,
+            "gpu_ms": self.gpu_ms, "kernel_launches": self.kernel_launches,
+            "nn_partial_ms": self.nn_partial_ms, "nn_partial_launches": self.nn_partial_launches,
+            "nn_qpt": self.nn_qpt, "nn_splits": self.nn_splits,
+        }
+
+
+_lib = None
+
+
+def load():
+    """Load libicpb200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise IcpbError(ERR_CUDA, f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
+                                  "(make -C icp-slam-prototype_b200); there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    lib.icpb_status_string.restype = C.c_char_p
+    lib.icpb_last_error.restype = C.c_char_p
+    lib.icpb_last_error.argtypes = [C.c_void_p]
+    lib.icpb_ctx_stream.restype = C.c_void_p
+    lib.icpb_ctx_stream.argtypes = [C.c_void_p]
+    lib.icpb_cloud_device_ptr.restype = C.c_void_p
+    lib.icpb_cloud_device_ptr.argtypes = [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def reference_intrinsics_v1():
+    K = Intrinsics()
+    load().icpb_intrinsics_reference_v1(C.byref(K))
+    return K
+
+
+def reference_intrinsics_v2():
+    K = Intrinsics()
+    load().icpb_intrinsics_reference_v2(C.byref(K))
+    return K
+
+
+def device_count():
+    n = C.c_int(0)
+    rc = load().icpb_device_count(C.byref(n))
+    return n.value if rc == OK else 0
+
+
+class Context:
+    def __init__(self, device=0, stream=None):
+        self.lib = load()
+        h = C.c_void_p()
+        if stream is None:
+            rc = self.lib.icpb_ctx_create(int(device), C.byref(h))
+        else:
+            rc = self.lib.icpb_ctx_create_on_stream(int(device), C.c_void_p(stream), C.byref(h))
+        if rc != OK:
+            raise IcpbError(rc, self.lib.icpb_last_error(None).decode())
+        self.h = h
+        self.device = device
+
+    def check(self, rc):
+        if rc != OK:
+            raise IcpbError(rc, self.lib.icpb_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.lib.icpb_ctx_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def sync(self):
+        self.check(self.lib.icpb_ctx_sync(self.h))
+
+    def timer_start(self):
+        self.check(self.lib.icpb_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        self.check(self.lib.icpb_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def set_profiling(self, enabled=True):
+        self.check(self.lib.icpb_ctx_set_profiling(self.h, int(bool(enabled))))
+
+    def launch_count(self):
+        n = C.c_longlong(0)
+        self.check(self.lib.icpb_ctx_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def measure_fp32_peak(self, repeats=5):
+        tf = C.c_double(0)
+        ms = C.c_float(0)
+        self.check(self.lib.icpb_measure_fp32_peak(self.h, repeats, C.byref(tf), C.byref(ms)))
+        return tf.value, ms.value
+
+    # ---- clouds
+    def cloud(self, capacity):
+        return Cloud(self, capacity)
+
+    def cloud_from_points(self, pts, capacity=None):
+        c = Cloud(self, capacity or max(len(pts), 1))
+        c.upload(pts)
+        return c
+
+    # ---- image stages
+    def normals(self, depth):
+        depth = np.ascontiguousarray(depth, dtype=np.uint16)
+        h, w = depth.shape
+        out = np.zeros((h, w, 3), dtype=np.float32)
+        self.check(self.lib.icpb_normals_from_depth(self.h, _p(depth), w, h, _p(out)))
+        return out
+
+    def depth_filter(self, depth, min_d=1000, max_d=25000):
+        depth = np.ascontiguousarray(depth, dtype=np.uint16)
+        h, w = depth.shape
+        out = np.zeros((h, w), dtype=np.uint16)
+        self.check(self.lib.icpb_depth_filter(self.h, _p(depth), w, h, int(min_d), int(max_d), _p(out)))
+        return out
+
+    # ---- registration
+    def nn_search(self, data, target):
+        idx = np.zeros(data.n, dtype=np.int32)
+        dist = np.zeros(data.n, dtype=np.float32)
+        resc = C.c_int(0)
+        self.check(self.lib.icpb_nn_search(self.h, data.h, target.h, _p(idx), _p(dist), C.byref(resc)))
+        return idx, dist, resc.value
+
+    def icp_register(self, data, target, max_iterations=20, threshold=0.0, max_nn_distance=0.75,
+                     solve_mode=SOLVE_REFERENCE, last_translation=(0, 0, 0), trace=False):
+        it = dt = None
+        prm = IcpParams(max_iterations, threshold, max_nn_distance, solve_mode, (C.c_float * 3)(*last_translation),
+                        None, None)
+        if trace:
+            it = np.full((max_iterations + 1, data.n), -1, dtype=np.int32)
+            dt = np.zeros((max_iterations + 1, data.n), dtype=np.float32)
+            prm.idx_trace = it.ctypes.data
+            prm.dist_trace = dt.ctypes.data
+        res = IcpResult()
+        self.check(self.lib.icpb_icp_register(self.h, data.h, target.h, C.byref(prm), C.byref(res)))
+        return res.to_dict(), it, dt
+
+    def icp_register_batch(self, datas, targets, max_iterations=20, threshold=0.0, max_nn_distance=0.75,
+                           solve_mode=SOLVE_REFERENCE):
+        n = len(datas)
+        prm = IcpParams(max_iterations, threshold, max_nn_distance, solve_mode, (C.c_float * 3)(0, 0, 0), None, None)
+        dh = (C.c_void_p * n)(*[d.h for d in datas])
+        th = (C.c_void_p * n)(*[t.h for t in targets])
+        res = (IcpResult * n)()
+        self.check(self.lib.icpb_icp_register_batch(self.h, dh, th, n, C.byref(prm), res))
+        return [r.to_dict() for r in res]
+
+    # ---- map
+    def map(self, dims, cell, z_lo=0, z_hi=None):
+        return Map(self, dims, cell, z_lo, dims[2] if z_hi is None else z_hi)
+
+
+class Cloud:
+    def __init__(self, ctx, capacity):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx.check(ctx.lib.icpb_cloud_create(ctx.h, int(capacity), C.byref(h)))
+        self.h = h
+        self.capacity = capacity
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.icpb_cloud_destroy(self.h)
+            self.h = None
+
+    @property
+    def n(self):
+        n = C.c_int(0)
+        self.ctx.check(self.ctx.lib.icpb_cloud_size(self.h, C.byref(n)))
+        return n.value
+
+    def upload(self, pts):
+        pts = np.ascontiguousarray(pts)
+        assert pts.dtype == POINT_DTYPE
+        self.ctx.check(self.ctx.lib.icpb_cloud_upload(self.h, _p(pts), len(pts)))
+
+    def upload_xyz(self, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        self.ctx.check(self.ctx.lib.icpb_cloud_upload_xyz(self.h, _p(xyz), len(xyz)))
+
+    def upload_device(self, ptr, n):
+        self.ctx.check(self.ctx.lib.icpb_cloud_upload_device(self.h, C.c_void_p(ptr), int(n)))
+
+    def device_ptr(self):
+        return self.ctx.lib.icpb_cloud_device_ptr(self.h)
+
+    def download(self):
+        n = self.n
+        out = np.zeros(max(n, 1), dtype=POINT_DTYPE)
+        nn = C.c_int(0)
+        self.ctx.check(self.ctx.lib.icpb_cloud_download(self.h, _p(out), len(out), C.byref(nn)))
+        return out[:n]
+
+    def copy_from(self, other):
+        self.ctx.check(self.ctx.lib.icpb_cloud_copy(self.h, other.h))
+
+    def from_depth(self, depth, bgr=None, K=None, rule=SUB_NONE, rule_arg=1, seed=0, keep_stream=None):
+        depth = np.ascontiguousarray(depth, dtype=np.uint16)
+        h, w = depth.shape
+        K = K or reference_intrinsics_v1()
+        if bgr is not None:
+            bgr = np.ascontiguousarray(bgr, dtype=np.uint8)
+        ks_len = 0
+        if keep_stream is not None:
+            keep_stream = np.ascontiguousarray(keep_stream, dtype=np.uint8)
+            ks_len = len(keep_stream)
+        self.ctx.check(self.ctx.lib.icpb_cloud_from_depth(self.h, _p(depth), _p(bgr), w, h, C.byref(K), rule,
+                                                         C.c_uint32(rule_arg), C.c_uint32(seed), _p(keep_stream),
+                                                         ks_len))
+        return self.n
+
+    def from_depth_device(self, d_depth, w, h, d_bgr=None, K=None, rule=SUB_NONE, rule_arg=1, seed=0):
+        K = K or reference_intrinsics_v1()
+        self.ctx.check(self.ctx.lib.icpb_cloud_from_depth_device(
+            self.h, C.c_void_p(d_depth), C.c_void_p(d_bgr) if d_bgr else None, w, h, C.byref(K), rule,
+            C.c_uint32(rule_arg), C.c_uint32(seed), None, 0))
+        return self.n
+
+    def transform(self, R=None, t=None):
+        Rp = None if R is None else np.ascontiguousarray(R, dtype=np.float32).reshape(9)
+        tp = None if t is None else np.ascontiguousarray(t, dtype=np.float32).reshape(3)
+        self.ctx.check(self.ctx.lib.icpb_cloud_transform(self.h, _p(Rp), _p(tp)))
+
+    def center(self):
+        c = (C.c_double * 3)()
+        self.ctx.check(self.ctx.lib.icpb_cloud_center(self.h, c))
+        return np.array(c[:])
+
+
+class Map:
+    def __init__(self, ctx, dims, cell, z_lo, z_hi):
+        self.ctx = ctx
+        self.dims = tuple(int(d) for d in dims)
+        self.z_lo, self.z_hi = int(z_lo), int(z_hi)
+        h = C.c_void_p()
+        d = (C.c_int * 3)(*self.dims)
+        ctx.check(ctx.lib.icpb_map_create(ctx.h, d, C.c_float(cell), self.z_lo, self.z_hi, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.icpb_map_destroy(self.h)
+            self.h = None
+
+    def clear(self):
+        self.ctx.check(self.ctx.lib.icpb_map_clear(self.h))
+
+    def update_endpoints(self, cloud, rule=RULE_A, delta=25, max_conf=180):
+        self.ctx.check(self.ctx.lib.icpb_map_update_endpoints(self.h, cloud.h, rule, delta, max_conf))
+
+    def integrate_rays(self, cloud, origin, delta_dec=25, delta_inc=25, count_visits=True):
+        o = (C.c_float * 3)(*origin)
+        v = C.c_longlong(0)
+        self.ctx.check(self.ctx.lib.icpb_map_integrate_rays(self.h, cloud.h, o, delta_dec, delta_inc,
+                                                           C.byref(v) if count_visits else None))
+        return v.value
+
+    def voxel_coords(self, p):
+        pp = (C.c_float * 3)(*p)
+        v = (C.c_int * 3)()
+        self.ctx.check(self.ctx.lib.icpb_map_voxel_coords(self.h, pp, v))
+        return tuple(v[:])
+
+    def size_bytes(self):
+        s = C.c_longlong(0)
+        self.ctx.check(self.ctx.lib.icpb_map_size_bytes(self.h, C.byref(s)))
+        return s.value
+
+    def download(self):
+        """Returns the slab as [X, Y, z_hi - z_lo] uint8 (reference order world[x][y][z])."""
+        out = np.zeros((self.dims[0], self.dims[1], self.z_hi - self.z_lo), dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.icpb_map_download(self.h, _p(out), out.size))
+        return out
+
+    def upload(self, grid):
+        grid = np.ascontiguousarray(grid, dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.icpb_map_upload(self.h, _p(grid), grid.size))

@@ -1,0 +1,202 @@
+/*
+ * icpb200.h -- C-ABI of libicpb200.so: the B200-native (sm_100a) registration
+ * + mapping hot path of BenniG123/icp-slam-prototype.
+ *
+ * The reference has no FFI: its boundary is the C++ declarations in icp.hpp,
+ * pointcloud.hpp and map.hpp (cv::Mat / std::vector by value).  Each entry
+ * point below names the reference interface it replaces (file:line relative
+ * to the reference repository).  Header-compatible C++ wrappers with the
+ * reference's own names live in include/icpb200/{icp,pointcloud,map}.hpp and
+ * marshal to these calls.
+ *
+ * Conventions: plain pointers + sizes, POD structs, opaque handles that own
+ * device memory, caller-owned host buffers, int status returns (0 = ok), no
+ * exceptions, no C++ types.  One context = one device + one CUDA stream;
+ * calls on one context are serialised by the caller.  There is NO CPU
+ * fallback: without a usable CUDA device every compute call fails with
+ * ICPB_ERR_CUDA.
+ */
+#ifndef ICPB200_H
+#define ICPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICPB_VERSION 100
+
+enum {
+    ICPB_OK = 0,
+    ICPB_ERR_INVALID = 1,   /* bad argument */
+    ICPB_ERR_EMPTY = 2,     /* empty cloud where the reference would dereference begin() (icp.cpp:572) */
+    ICPB_ERR_CUDA = 3,      /* CUDA runtime / no device */
+    ICPB_ERR_CAPACITY = 4   /* output does not fit the handle's capacity */
+};
+
+typedef struct icpb_ctx icpb_ctx;
+typedef struct icpb_cloud icpb_cloud;
+typedef struct icpb_map icpb_map;
+
+/* color_point_t, pointcloud.hpp:13-19 (cv::Point3f + cv::Vec3b + 1 pad = 16 B). */
+typedef struct {
+    float x, y, z;
+    uint8_t c0, c1, c2, pad;
+} icpb_point;
+
+/* x = (u - cx_u) * z / fx_u ; y = (v - cx_v) * z / fx_v ; z = d / depth_scale.
+ * The reference uses CX and FX on both axes (pointcloud.cpp:38-39):
+ * icpb_intrinsics_reference_v1() reproduces that. */
+typedef struct {
+    float fx_u, cx_u, fx_v, cx_v, depth_scale;
+} icpb_intrinsics;
+
+/* Stand-ins for `rand() % SUBSAMPLE_FACTOR` (pointcloud.cpp:28,125). */
+enum {
+    ICPB_SUB_NONE = 0,   /* keep every non-zero pixel (factor 1) */
+    ICPB_SUB_STRIDE = 1, /* keep non-zero pixel k iff k % arg == 0 */
+    ICPB_SUB_HASH = 2,   /* keep iff hash32(seed, pixel) % arg == 0 */
+    ICPB_SUB_STREAM = 3  /* keep non-zero pixel k iff keep_stream[k] != 0 (replays libc rand()) */
+};
+
+enum { ICPB_SOLVE_REFERENCE = 0, /* icp.cpp:199-246: uncentred SVD, offset = mean(a-b) */
+       ICPB_SOLVE_KABSCH = 1 };  /* rigid_transform_3D.py:9-40 */
+
+enum { ICPB_RULE_A = 0,  /* map.cpp:249-253 / 104-113 */
+       ICPB_RULE_C = 1 };/* map.cpp:139-149 */
+
+typedef struct {
+    int max_iterations;        /* SLAM.cpp:277: 16 */
+    float threshold;           /* SLAM.cpp:277: 1e-4 */
+    float max_nn_distance;     /* MAX_NN_COLOR_DISTANCE, icp.hpp:8 */
+    int solve_mode;            /* ICPB_SOLVE_* */
+    float last_translation[3]; /* icp.cpp:25, consumed by the <3 associations rule (icp.cpp:163-182) */
+    int32_t *idx_trace;        /* optional host buffer (max_iterations+1)*n: nearest index per pass */
+    float *dist_trace;         /* optional host buffer, same shape */
+} icpb_icp_params;
+
+typedef struct {
+    int iterations;
+    int nn_passes;
+    int n_assoc;
+    float mse;
+    float rigid[16];        /* getTransformation's return value, icp.cpp:227-233,266-268 */
+    float cam_rotation[9];  /* delta applied to cameraRotation (icp.cpp:237), starting from identity */
+    float cam_position[3];  /* delta applied to cameraPosition (icp.cpp:246), starting from 0 */
+    float offset[3];        /* last offset (icp.cpp:240) */
+    double pose_R[9];       /* composed transform applied to the data cloud */
+    double pose_t[3];
+    int small_assoc_exit;
+    int exact_rescans;      /* queries that needed the full exact FP64 rescan (diagnostic) */
+    float gpu_ms;           /* device time of the registration loop (CUDA events on the context stream) */
+    int kernel_launches;    /* kernels launched by this call */
+    float nn_partial_ms;    /* profiling mode only: summed device time of the nn_partial launches */
+    int nn_partial_launches;
+    int nn_qpt, nn_splits;  /* work decomposition chosen for nn_partial */
+} icpb_icp_result;
+
+/* ---- library / context ------------------------------------------------- */
+int icpb_version(void);
+const char *icpb_status_string(int status);
+/* Last error text of a context (or of the failed icpb_ctx_create when ctx == NULL). */
+const char *icpb_last_error(const icpb_ctx *ctx);
+int icpb_device_count(int *count);
+/* Replaces the file-scope globals of icp.cpp:22-26 with an explicit handle. */
+int icpb_ctx_create(int device, icpb_ctx **out);
+/* Same, but work is enqueued on an existing cudaStream_t (e.g. torch's). */
+int icpb_ctx_create_on_stream(int device, void *cuda_stream, icpb_ctx **out);
+int icpb_ctx_destroy(icpb_ctx *ctx);
+int icpb_ctx_sync(icpb_ctx *ctx);
+void *icpb_ctx_stream(icpb_ctx *ctx);
+/* CUDA-event stopwatch on the context stream (used by bench.py). */
+int icpb_timer_start(icpb_ctx *ctx);
+int icpb_timer_stop(icpb_ctx *ctx, float *elapsed_ms);
+/* Profiling mode: bracket every nn_partial launch with CUDA events on the context
+ * stream and report their summed duration in icpb_icp_result (roofline evidence). */
+int icpb_ctx_set_profiling(icpb_ctx *ctx, int enabled);
+/* Kernels launched on this context since creation. */
+int icpb_ctx_launch_count(icpb_ctx *ctx, long long *count);
+/* Dense FP32 FMA micro-benchmark: the measured roofline denominator for the
+ * compute-bound NN kernel. */
+int icpb_measure_fp32_peak(icpb_ctx *ctx, int repeats, double *tflops, float *ms);
+
+/* ---- point clouds: class icp::PointCloud, pointcloud.hpp:27-49 ---------- */
+int icpb_cloud_create(icpb_ctx *ctx, int capacity, icpb_cloud **out);
+int icpb_cloud_destroy(icpb_cloud *cloud);
+int icpb_cloud_size(const icpb_cloud *cloud, int *n);
+/* PointCloud(std::vector<cv::Point3f>) pointcloud.cpp:256-287 / direct point_list_t upload. */
+int icpb_cloud_upload(icpb_cloud *cloud, const icpb_point *points, int n);
+int icpb_cloud_upload_xyz(icpb_cloud *cloud, const float *xyz, int n);
+int icpb_cloud_download(icpb_cloud *cloud, icpb_point *out, int capacity, int *n);
+int icpb_cloud_copy(icpb_cloud *dst, const icpb_cloud *src);
+/* Adopt n points already in device memory (16 B each), e.g. after an all-gather. */
+int icpb_cloud_upload_device(icpb_cloud *cloud, const void *device_points, int n);
+const void *icpb_cloud_device_ptr(const icpb_cloud *cloud);
+/* PointCloud(cv::Mat& data, cv::Mat colorMat), pointcloud.cpp:109-165 (and :11-58):
+ * host depth (u16, h*w) and optional BGR (u8, h*w*3). */
+int icpb_cloud_from_depth(icpb_cloud *cloud, const uint16_t *depth, const uint8_t *bgr, int w, int h,
+                          const icpb_intrinsics *K, int rule, uint32_t rule_arg, uint32_t seed,
+                          const uint8_t *keep_stream, int keep_stream_len);
+/* Same with depth / bgr already resident on the device. */
+int icpb_cloud_from_depth_device(icpb_cloud *cloud, const void *d_depth, const void *d_bgr, int w, int h,
+                                 const icpb_intrinsics *K, int rule, uint32_t rule_arg, uint32_t seed,
+                                 const void *d_keep_stream, int keep_stream_len);
+/* PointCloud::rotate pointcloud.cpp:321-331 then PointCloud::translate :349-359 (either may be NULL). */
+int icpb_cloud_transform(icpb_cloud *cloud, const float R[9], const float t[3]);
+/* PointCloud::center (pointcloud.cpp:43-45,100-102), canonical FP64 block-ordered mean. */
+int icpb_cloud_center(icpb_cloud *cloud, double center[3]);
+void icpb_intrinsics_reference_v1(icpb_intrinsics *K); /* pointcloud.hpp:7-10 */
+void icpb_intrinsics_reference_v2(icpb_intrinsics *K); /* SLAM.cpp:26-29 */
+
+/* ---- image-space stages ------------------------------------------------- */
+/* getNormalMap, SLAM.cpp:412-430: host u16 depth -> host float h*w*3. */
+int icpb_normals_from_depth(icpb_ctx *ctx, const uint16_t *depth, int w, int h, float *normals);
+/* filterDepthImage, SLAM.cpp:553-573 (range threshold + 5x5 close, anchor (3,3)). */
+int icpb_depth_filter(icpb_ctx *ctx, const uint16_t *depth, int w, int h, int min_d, int max_d,
+                      uint16_t *out);
+
+/* ---- registration: namespace icp, icp.hpp:22-45 -------------------------- */
+/* findGlobalNearestNeighborAssociations icp.cpp:541-563 + getNearestPoint :566-593 +
+ * distance :606-620, un-compacted: idx[i] = lowest index of the nearest target,
+ * dist[i] = its distance; the caller applies `dist < MAX_NN_COLOR_DISTANCE`.
+ * idx / dist are HOST buffers of n entries (either may be NULL). */
+int icpb_nn_search(icpb_ctx *ctx, const icpb_cloud *data, const icpb_cloud *target, int32_t *idx,
+                   float *dist, int *exact_rescans);
+/* Device-resident variant: results stay on the device (pointers owned by the ctx). */
+int icpb_nn_search_device(icpb_ctx *ctx, const icpb_cloud *data, const icpb_cloud *target,
+                          const int32_t **d_idx, const float **d_dist);
+/* getTransformation icp.cpp:28-285 with the all-point association (icp.cpp:149/253):
+ * the data cloud is transformed in place; the whole loop runs on the device. */
+int icpb_icp_register(icpb_ctx *ctx, icpb_cloud *data, const icpb_cloud *target,
+                      const icpb_icp_params *params, icpb_icp_result *result);
+/* `count` independent registrations (BASELINE config 4); results[i] for pair i. */
+int icpb_icp_register_batch(icpb_ctx *ctx, icpb_cloud *const *data, const icpb_cloud *const *target,
+                            int count, const icpb_icp_params *params, icpb_icp_result *results);
+
+/* ---- certainty map: class map::Map, map.hpp:20-37 ------------------------ */
+/* Map::Map map.cpp:17-31; world[x][y][z] z-fastest (map.hpp:25).  The reference
+ * macros are dims 300^3, cell 10/300 m (map.hpp:9-10,17); README.md:8-12 is
+ * 300x300x250 at 0.02 m.  [z_lo, z_hi) is the z-slab this handle owns
+ * (0, dims[2] for the whole map). */
+int icpb_map_create(icpb_ctx *ctx, const int dims[3], float cell, int z_lo, int z_hi, icpb_map **out);
+int icpb_map_destroy(icpb_map *map);
+int icpb_map_clear(icpb_map *map);
+/* Map::update overloads, map.cpp:88-119 / 122-151 / 220-269: saturating endpoint increments. */
+int icpb_map_update_endpoints(icpb_map *map, const icpb_cloud *points, int rule, int delta, int max_conf);
+/* Map::rayTrace map.cpp:272-439 (semantics in DESIGN.md "M4"): integer ray walk from the
+ * origin voxel, decrements with clamp at 0, then rule-A endpoint increments. */
+int icpb_map_integrate_rays(icpb_map *map, const icpb_cloud *points, const float origin[3],
+                            int delta_dec, int delta_inc, long long *voxels_visited);
+/* Map::getVoxelCoordinates map.cpp:55-85 (host-side scalar helper). */
+int icpb_map_voxel_coords(const icpb_map *map, const float p[3], int v[3]);
+/* Slab download in the reference's linear order restricted to the slab:
+ * out[(x*dimY + y)*(z_hi-z_lo) + (z - z_lo)]. */
+int icpb_map_download(icpb_map *map, uint8_t *out, long long capacity);
+int icpb_map_upload(icpb_map *map, const uint8_t *in, long long size);
+int icpb_map_size_bytes(const icpb_map *map, long long *size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICPB200_H */

@@ -1,0 +1,141 @@
+"""GPU parity: back-projection (P1), transform (P2), normals (P3), depth filter (8f-1) vs the CPU oracle.
+Bar: bit-exact points, order and count."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _frame(seed=0, sensor=None):
+    from icpb200 import synth
+    sensor = sensor or synth.KINECT_V1
+    poses = synth.trajectory(3, seed=synth.MASTER_SEED + seed)
+    R, t = poses[2]
+    return synth.render_depth(R, t, sensor, seed=synth.MASTER_SEED + seed), synth.render_color(sensor, seed)
+
+
+def _same_points(a, b):
+    assert len(a) == len(b), (len(a), len(b))
+    assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
+@pytest.mark.parametrize("rule,arg", [(0, 1), (1, 40), (1, 7), (2, 40), (2, 3)])
+def test_backproject_rules_v1(ctx, orc, rule, arg):
+    import icpb200
+    depth, bgr = _frame(1)
+    c = ctx.cloud(depth.size)
+    n = c.from_depth(depth, bgr, icpb200.reference_intrinsics_v1(), rule, arg, seed=1234)
+    ref, _, _ = orc.backproject(depth, bgr, orc.kinect_v1(), rule, arg, seed=1234)
+    assert n == len(ref)
+    _same_points(c.download(), ref)
+    c.close()
+
+
+def test_backproject_v2_no_color(ctx, orc):
+    import icpb200
+    from icpb200 import synth
+    depth, _ = _frame(2, synth.KINECT_V2)
+    c = ctx.cloud(depth.size)
+    c.from_depth(depth, None, icpb200.reference_intrinsics_v2())
+    ref, _, _ = orc.backproject(depth, None, orc.kinect_v2())
+    _same_points(c.download(), ref)
+    c.close()
+
+
+def test_backproject_rand_stream(ctx, orc):
+    """ICPB_SUB_STREAM replays `rand() % 40` (pointcloud.cpp:28): one decision per non-zero pixel."""
+    import icpb200
+    depth, bgr = _frame(3)
+    rng = np.random.default_rng(7)
+    stream = (rng.integers(0, 40, int((depth > 0).sum())) == 0).astype(np.uint8)
+    c = ctx.cloud(depth.size)
+    c.from_depth(depth, bgr, None, icpb200.SUB_STREAM, 40, 0, stream)
+    ref, _, _ = orc.backproject(depth, bgr, None, orc.SUB_STREAM, 40, 0, stream)
+    _same_points(c.download(), ref)
+    assert 0.015 * depth.size < len(ref) < 0.035 * depth.size
+    c.close()
+
+
+def test_backproject_every_depth_value(ctx, orc):
+    """T1: every uint16 depth value, on a sweep of pixel coordinates."""
+    import icpb200
+    w, h = 640, 480
+    depth = (np.arange(w * h, dtype=np.uint32) * 7919 % 65536).astype(np.uint16).reshape(h, w)
+    depth.ravel()[:65536] = np.arange(65536, dtype=np.uint16)
+    c = ctx.cloud(depth.size)
+    c.from_depth(depth, None, None)
+    ref, _, _ = orc.backproject(depth, None, None)
+    _same_points(c.download(), ref)
+    c.close()
+
+
+@pytest.mark.parametrize("w,h", [(8, 1), (16, 3), (33, 5), (2048, 1), (2056, 2), (100, 77)])
+def test_backproject_ragged_and_empty(ctx, orc, w, h):
+    rng = np.random.default_rng(w * h)
+    depth = rng.integers(0, 3, (h, w)).astype(np.uint16) * rng.integers(1000, 20000, (h, w)).astype(np.uint16)
+    K = orc.kinect_v1()
+    import icpb200
+    c = ctx.cloud(max(depth.size, 1))
+    if (w * h) % 8 != 0:
+        pass  # tail path
+    n = c.from_depth(depth, None, None)
+    ref, _, _ = orc.backproject(depth, None, K)
+    assert n == len(ref)
+    _same_points(c.download(), ref)
+    zero = np.zeros((h, w), np.uint16)
+    assert c.from_depth(zero, None, None) == 0
+    c.close()
+
+
+def test_backproject_capacity_error(ctx, orc):
+    import icpb200
+    depth, _ = _frame(1)
+    c = ctx.cloud(1000)
+    with pytest.raises(icpb200.IcpbError) as e:
+        c.from_depth(depth, None, None)
+    assert e.value.status == icpb200.ERR_CAPACITY
+    c.close()
+
+
+def test_transform_matches_oracle(ctx, orc, pair10k):
+    from icpb200 import synth
+    data, _ = pair10k
+    R = synth.rot_axis_angle([1, 2, 3], 0.1).astype(np.float32)
+    t = np.array([5, 5, 5], np.float32)
+    c = ctx.cloud_from_points(data)
+    c.transform(R, t)
+    ref = orc.translate(orc.rotate(data, R), t)
+    _same_points(c.download(), ref)
+    c.transform(None, -t)
+    _same_points(c.download(), orc.translate(ref, -t))
+    c.close()
+
+
+def test_center_canonical(ctx, orc, pair10k):
+    data, _ = pair10k
+    c = ctx.cloud_from_points(data)
+    got = c.center()
+    terms = orc.xyz_of(data).astype(np.float64)
+    want = orc.canon_reduce(terms) / len(data)
+    assert np.array_equal(got, want)
+    # the reference's float running mean agrees to float accuracy (pointcloud.cpp:43-45,100-102)
+    assert np.allclose(got, terms.mean(0), rtol=0, atol=1e-9)
+    c.close()
+
+
+def test_normals(ctx, orc):
+    depth, _ = _frame(4)
+    got = ctx.normals(depth)
+    want = orc.normals(depth)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_depth_filter(ctx, orc):
+    from icpb200 import synth
+    R, t = synth.trajectory(1)[0]
+    raw = synth.render_depth(R, t, synth.KINECT_V2, dropout=0.1)
+    raw[10:20, 30:60] = 40000   # beyond MAX_16_CHANNEL_DISTANCE
+    raw[100:110, 5:9] = 500     # closer than MIN_16_CHANNEL_DISTANCE
+    got = ctx.depth_filter(raw, 1000, 25000)
+    want = orc.depth_filter(raw, 1000, 25000)
+    assert np.array_equal(got, want)

@@ -1,0 +1,121 @@
+"""GPU parity: the device-resident registration loop (S1-S3 + N1-N3 + P2) vs the CPU oracle.
+Bars: nearest indices bit-exact on every pass; pose within 1e-5 rad / 1e-5 m (north_star)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROT_TOL_RAD = 1e-5
+TRANS_TOL_M = 1e-5
+
+
+def rot_angle(Ra, Rb):
+    """Rotation angle between two (nearly) orthonormal matrices.  sin(angle) from the skew part of
+    Ra^T Rb: well conditioned at small angles, unlike arccos((trace-1)/2) (the composed pose is a
+    product of float-rounded factors, so trace(R^T R) is 3 - O(1e-7), not 3)."""
+    D = Ra.T @ Rb
+    S = (D - D.T) / 2.0
+    s = np.sqrt(S[0, 1] ** 2 + S[0, 2] ** 2 + S[1, 2] ** 2)
+    c = (np.trace(D) - 1.0) / 2.0
+    return float(np.arctan2(s, c))
+
+
+def _run(ctx, orc, data, target, mode, iters=20, threshold=0.0, max_d=0.75, last_t=(0, 0, 0)):
+    dc = ctx.cloud_from_points(data)
+    tc = ctx.cloud_from_points(target)
+    res, it, dt = ctx.icp_register(dc, tc, iters, threshold, max_d, mode, last_t, trace=True)
+    out = dc.download()
+    dc.close(); tc.close()
+    ref, rout, rit, rdt = orc.icp(data, target, iters, threshold, max_d, mode, last_t, n_threads=8, trace=True)
+    return res, it, dt, out, ref, rit, rdt, rout
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_icp_config1_trace_and_pose(ctx, orc, pair10k, mode):
+    data, target = pair10k
+    res, it, dt, out, ref, rit, rdt, rout = _run(ctx, orc, data, target, mode)
+    assert res["iterations"] == ref["iterations"] == 20
+    assert res["nn_passes"] == ref["nn_passes"] == 21
+    for k in range(21):
+        assert np.array_equal(it[k], rit[k]), f"pass {k}: {(it[k] != rit[k]).sum()} index mismatches"
+        assert np.array_equal(dt[k].view(np.uint32), rdt[k].view(np.uint32)), f"pass {k}: distances differ"
+    assert res["n_assoc"] == ref["n_assoc"]
+    assert rot_angle(res["pose_R"], ref["pose_R"]) <= ROT_TOL_RAD
+    assert np.abs(res["pose_t"] - ref["pose_t"]).max() <= TRANS_TOL_M
+    # canonical arithmetic: in fact bit-equal
+    assert np.array_equal(res["pose_R"], ref["pose_R"]) and np.array_equal(res["pose_t"], ref["pose_t"])
+    assert np.array_equal(res["rigid"], ref["rigid"])
+    assert np.array_equal(res["cam_rotation"], ref["cam_rotation"])
+    assert np.array_equal(res["cam_position"], ref["cam_position"])
+    assert res["mse"] == ref["mse"]
+    assert np.array_equal(out.view(np.uint8), rout.view(np.uint8)), "transformed cloud differs"
+
+
+def test_icp_threshold_early_exit(ctx, orc, pair10k):
+    data, target = pair10k
+    data, target = data[:3000], target[:4000]
+    res, it, dt, out, ref, rit, rdt, rout = _run(ctx, orc, data, target, 0, iters=16, threshold=5e-3)
+    assert 0 < ref["iterations"] < 16
+    assert res["iterations"] == ref["iterations"] and res["nn_passes"] == ref["nn_passes"]
+    assert np.array_equal(it[: ref["nn_passes"]], rit[: ref["nn_passes"]])
+    assert np.array_equal(out.view(np.uint8), rout.view(np.uint8))
+
+
+def test_icp_less_than_three_associations(ctx, orc):
+    """icp.cpp:163-182: < 3 associations replays the last motion and stops."""
+    rng = np.random.default_rng(3)
+    target = orc.make_points(rng.uniform(4, 6, (300, 3)))
+    data = orc.make_points(np.concatenate([rng.uniform(40, 60, (200, 3)), rng.uniform(4, 6, (2, 3))]))
+    res, it, dt, out, ref, rit, rdt, rout = _run(ctx, orc, data, target, 0, iters=8, last_t=(0.01, -0.02, 0.03))
+    assert ref["small_assoc_exit"] == 1 and res["small_assoc_exit"] == 1
+    assert res["iterations"] == ref["iterations"] == 8 and res["nn_passes"] == ref["nn_passes"] == 1
+    assert np.array_equal(out.view(np.uint8), rout.view(np.uint8))
+    assert np.array_equal(res["offset"], ref["offset"])
+
+
+def test_icp_zero_associations(ctx, orc):
+    rng = np.random.default_rng(4)
+    target = orc.make_points(rng.uniform(4, 6, (100, 3)))
+    data = orc.make_points(rng.uniform(40, 60, (100, 3)))
+    res, it, dt, out, ref, rit, rdt, rout = _run(ctx, orc, data, target, 0, iters=5)
+    assert res["n_assoc"] == ref["n_assoc"] == 0 and res["iterations"] == ref["iterations"] == 0
+    assert np.array_equal(out.view(np.uint8), data.view(np.uint8))
+
+
+def test_icp_recovers_known_motion_kabsch(ctx, orc):
+    """Kabsch mode on a well-conditioned cloud recovers a known rigid motion (rigid_transform_3D.py:42-97)."""
+    from icpb200 import synth
+    rng = np.random.default_rng(11)
+    base = rng.uniform(3, 7, (4000, 3))
+    R = synth.rot_axis_angle([0.3, -0.5, 0.8], np.deg2rad(2.0))
+    t = np.array([0.02, -0.01, 0.015])
+    moved = (base - 5.0) @ R.T + 5.0 + t
+    target = orc.make_points(moved)
+    data = orc.make_points(base)
+    dc = ctx.cloud_from_points(data); tc = ctx.cloud_from_points(target)
+    res, _, _ = ctx.icp_register(dc, tc, 30, 0.0, 0.75, 1)
+    out = orc.xyz_of(dc.download())
+    assert np.abs(out - moved).max() < 1e-4
+    dc.close(); tc.close()
+
+
+def test_icp_batch_matches_single(ctx, orc, pair10k):
+    """BASELINE config 4 shape: a batch of independent registrations == the same registrations one by one."""
+    data, target = pair10k
+    sizes = [(2000, 2500), (1500, 1500), (2048, 1000), (777, 3001)]
+    singles, datas, targets = [], [], []
+    for k, (n, m) in enumerate(sizes):
+        d = data[k * 100: k * 100 + n]; t = target[k * 50: k * 50 + m]
+        dc = ctx.cloud_from_points(d); tc = ctx.cloud_from_points(t)
+        r, _, _ = ctx.icp_register(dc, tc, 6, 0.0, 0.75, 0)
+        singles.append((r, dc.download()))
+        dc.close()
+        datas.append(ctx.cloud_from_points(d)); targets.append(tc)
+    res = ctx.icp_register_batch(datas, targets, 6, 0.0, 0.75, 0)
+    for k in range(len(sizes)):
+        assert np.array_equal(res[k]["pose_R"], singles[k][0]["pose_R"])
+        assert np.array_equal(res[k]["pose_t"], singles[k][0]["pose_t"])
+        assert res[k]["n_assoc"] == singles[k][0]["n_assoc"]
+        assert np.array_equal(datas[k].download().view(np.uint8), singles[k][1].view(np.uint8))
+    for c in datas + targets:
+        c.close()

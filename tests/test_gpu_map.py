@@ -1,0 +1,126 @@
+"""GPU parity: certainty grid (M1-M4) vs the CPU oracle.  Bar: bit-exact grid."""
+import hashlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REF_DIMS, REF_CELL = (300, 300, 300), np.float32(10.0) / np.float32(300.0)   # map.hpp:9-10,17
+README_DIMS, README_CELL = (300, 300, 250), 0.02                               # README.md:8-12
+
+
+def _world_cloud(orc, seed=0, sensor=None, stride=1):
+    from icpb200 import synth
+    sensor = sensor or synth.KINECT_V2
+    R, t = synth.trajectory(4, seed=synth.MASTER_SEED + seed)[3]
+    depth = synth.render_depth(R, t, sensor, seed=seed)
+    pts, _, _ = orc.backproject(depth, None, orc.kinect_v2() if sensor is synth.KINECT_V2 else orc.kinect_v1())
+    pts = orc.translate(orc.rotate(pts, R.astype(np.float32)), t.astype(np.float32))
+    return pts[::stride], t.astype(np.float32)
+
+
+@pytest.mark.parametrize("rule,delta", [(0, 25), (0, 180), (1, 25), (1, 60)])
+@pytest.mark.parametrize("dims,cell", [(REF_DIMS, REF_CELL), (README_DIMS, README_CELL)])
+def test_endpoint_rules(ctx, orc, rule, delta, dims, cell):
+    pts, _ = _world_cloud(orc, 1)
+    m = ctx.map(dims, float(cell))
+    c = ctx.cloud_from_points(pts)
+    grid = np.zeros(dims, np.uint8)
+    for _ in range(3):
+        m.update_endpoints(c, rule, delta, 180)
+        orc.map_update_endpoints(grid, dims, float(cell), pts, rule, delta, 180)
+    got = m.download()
+    assert hashlib.sha256(got.tobytes()).hexdigest() == hashlib.sha256(grid.tobytes()).hexdigest()
+    assert got.max() == 255 and 0 < (got > 0).sum()
+    m.close(); c.close()
+
+
+def test_endpoint_multiplicities(ctx, orc):
+    """T4: 0..20 hits per voxel at both deltas; result must be f^k(c) for every voxel."""
+    dims, cell = (32, 32, 32), 0.1
+    rng = np.random.default_rng(0)
+    for rule, delta in [(0, 25), (0, 180), (1, 25), (1, 180)]:
+        vox = rng.integers(0, 32, (400, 3))
+        mult = rng.integers(0, 21, 400)
+        xyz = np.repeat((vox + 0.5) * cell, mult, axis=0).astype(np.float32)
+        rng.shuffle(xyz)
+        pts = orc.make_points(xyz)
+        start = rng.integers(0, 256, dims).astype(np.uint8)
+        m = ctx.map(dims, cell)
+        m.upload(start)
+        c = ctx.cloud_from_points(pts)
+        m.update_endpoints(c, rule, delta, 180)
+        want = start.copy()
+        orc.map_update_endpoints(want, dims, cell, pts, rule, delta, 180)
+        assert np.array_equal(m.download(), want)
+        m.close(); c.close()
+
+
+def test_out_of_range_points_are_clamped_in(ctx, orc):
+    dims, cell = (20, 20, 20), 0.1
+    xyz = np.array([[-5, 1, 1], [1, -0.05, 1], [1, 1, 99], [2.0, 2.0, 2.0], [1.95, 1.999999, 0.0]], np.float32)
+    pts = orc.make_points(xyz)
+    m = ctx.map(dims, cell)
+    c = ctx.cloud_from_points(pts)
+    m.update_endpoints(c, 0, 25, 180)
+    want = np.zeros(dims, np.uint8)
+    orc.map_update_endpoints(want, dims, cell, pts, 0, 25, 180)
+    assert np.array_equal(m.download(), want)
+    for p in xyz:
+        assert m.voxel_coords(p) == orc.voxel_coords(p, cell, dims)
+    m.close(); c.close()
+
+
+@pytest.mark.parametrize("dims,cell", [(README_DIMS, README_CELL), ((150, 150, 125), 0.04)])
+def test_ray_integration_frames(ctx, orc, dims, cell):
+    m = ctx.map(dims, cell)
+    grid = np.zeros(dims, np.uint8)
+    for f in range(3):
+        pts, origin = _world_cloud(orc, f, stride=3)
+        c = ctx.cloud_from_points(pts)
+        v = m.integrate_rays(c, origin, 25, 25)
+        rv = orc.map_integrate_rays(grid, dims, cell, pts, origin, 25, 25)
+        assert v == rv and v > 0
+        c.close()
+    got = m.download()
+    assert np.array_equal(got, grid), f"{(got != grid).sum()} voxels differ"
+    m.close()
+
+
+def test_ray_decrement_clamps_at_zero(ctx, orc):
+    dims, cell = (64, 64, 64), 0.05
+    rng = np.random.default_rng(2)
+    start = rng.integers(0, 60, dims).astype(np.uint8)
+    xyz = rng.uniform(0.1, 3.1, (5000, 3)).astype(np.float32)
+    pts = orc.make_points(xyz)
+    origin = (1.6, 1.6, 1.6)
+    m = ctx.map(dims, cell); m.upload(start)
+    c = ctx.cloud_from_points(pts)
+    m.integrate_rays(c, origin, 25, 25)
+    want = start.copy()
+    orc.map_integrate_rays(want, dims, cell, pts, origin, 25, 25)
+    assert np.array_equal(m.download(), want)
+    m.close(); c.close()
+
+
+def test_z_slabs_concatenate_to_the_full_grid(ctx, orc):
+    """Config 5 shape on one GPU: slab owners see every ray, write only their z-range; the
+    concatenation equals the un-sharded grid byte for byte."""
+    dims, cell = (120, 120, 100), 0.05
+    pts, origin = _world_cloud(orc, 5, stride=2)
+    c = ctx.cloud_from_points(pts)
+    full = ctx.map(dims, cell)
+    full.integrate_rays(c, origin, 25, 25)
+    want = full.download()
+    parts = []
+    for g in range(4):
+        s = ctx.map(dims, cell, g * 25, (g + 1) * 25)
+        s.integrate_rays(c, origin, 25, 25)
+        parts.append(s.download())
+        s.close()
+    assert np.array_equal(np.concatenate(parts, axis=2), want)
+    ref = np.zeros(dims, np.uint8)
+    orc.map_integrate_rays(ref, dims, cell, pts, origin, 25, 25)
+    assert np.array_equal(want, ref)
+    full.close(); c.close()

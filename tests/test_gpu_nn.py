@@ -1,0 +1,90 @@
+"""GPU parity: brute-force NN (N1-N3) through the C-ABI vs the CPU oracle.  Bar: bit-exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(ctx, orc, data, target, expect_rescans=None):
+    import icpb200
+    dc = ctx.cloud_from_points(data)
+    tc = ctx.cloud_from_points(target)
+    idx, dist, resc = ctx.nn_search(dc, tc)
+    ridx, rdist = orc.nn(data, target, n_threads=8)
+    dc.close(); tc.close()
+    assert np.array_equal(idx, ridx), f"{(idx != ridx).sum()} index mismatches"
+    assert np.array_equal(dist.view(np.uint32), rdist.view(np.uint32)), "distances not bit-equal"
+    if expect_rescans is not None:
+        assert expect_rescans(resc), resc
+    return resc
+
+
+def test_nn_config1(ctx, orc, pair10k):
+    data, target = pair10k
+    _check(ctx, orc, data, target)
+
+
+@pytest.mark.parametrize("n,m", [(1, 1), (1, 33), (7, 5), (31, 32), (257, 1000), (1025, 4097), (3000, 31)])
+def test_nn_ragged_sizes(ctx, orc, n, m):
+    rng = np.random.default_rng(n * 1000 + m)
+    data = orc.make_points(rng.uniform(3, 8, (n, 3)))
+    target = orc.make_points(rng.uniform(3, 8, (m, 3)))
+    _check(ctx, orc, data, target)
+
+
+def test_nn_lattice_ties(ctx, orc):
+    """Targets on a lattice, queries at cell centres: many exactly equal distances -> lowest index wins."""
+    g = np.arange(0, 8, dtype=np.float32) * 0.25 + 4.0
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    target = orc.make_points(np.stack([X.ravel(), Y.ravel(), Z.ravel()], 1))
+    q = g[:-1] + 0.125
+    X, Y, Z = np.meshgrid(q, q, q, indexing="ij")
+    data = orc.make_points(np.stack([X.ravel(), Y.ravel(), Z.ravel()], 1))
+    resc = _check(ctx, orc, data, target, expect_rescans=lambda r: r > 0)
+    assert resc > 0
+
+
+def test_nn_duplicate_targets(ctx, orc):
+    rng = np.random.default_rng(5)
+    base = rng.uniform(3, 8, (500, 3)).astype(np.float32)
+    target = orc.make_points(np.concatenate([base, base, base[::-1]], 0))   # every point three times
+    data = orc.make_points(base[:200] + rng.normal(0, 1e-3, (200, 3)).astype(np.float32))
+    _check(ctx, orc, data, target, expect_rescans=lambda r: r > 0)
+
+
+def test_nn_identical_clouds(ctx, orc):
+    rng = np.random.default_rng(6)
+    pts = orc.make_points(rng.uniform(3, 8, (2048, 3)))
+    dc = ctx.cloud_from_points(pts)
+    tc = ctx.cloud_from_points(pts)
+    idx, dist, _ = ctx.nn_search(dc, tc)
+    assert np.array_equal(idx, np.arange(2048)) and np.all(dist == 0)
+
+
+def test_nn_sqrt_collapsed_ties(ctx, orc):
+    """Distinct squared distances that round to the same float sqrt: ties are judged on the sqrt (icp.cpp:578)."""
+    rng = np.random.default_rng(8)
+    n = 512
+    data = orc.make_points(np.tile(np.array([[5.0, 5.0, 5.0]], np.float32), (n, 1)))
+    # targets at nearly equal radius from the query: radii differ by a few float ulps
+    dirs = rng.standard_normal((4096, 3))
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    radius = 1.0 + rng.integers(0, 4, 4096) * 2.0 ** -24
+    target = orc.make_points(np.array([5.0, 5.0, 5.0]) + dirs * radius[:, None])
+    _check(ctx, orc, data, target, expect_rescans=lambda r: r > 0)
+
+
+def test_nn_far_and_near_scales(ctx, orc):
+    rng = np.random.default_rng(9)
+    data = orc.make_points(rng.uniform(-50, 50, (1500, 3)))
+    target = orc.make_points(np.concatenate([rng.uniform(-50, 50, (2500, 3)), rng.uniform(-1e-3, 1e-3, (500, 3))]))
+    _check(ctx, orc, data, target)
+
+
+def test_nn_empty_cloud_is_an_error(ctx, orc):
+    import icpb200
+    dc = ctx.cloud(4)
+    tc = ctx.cloud_from_points(orc.make_points(np.ones((3, 3), np.float32)))
+    with pytest.raises(icpb200.IcpbError) as e:
+        ctx.nn_search(dc, tc)
+    assert e.value.status == icpb200.ERR_EMPTY
