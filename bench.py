@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Benchmark of the registration hot path (BASELINE.json metric: ICP registrations/s).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+One "step" = one full registration of a synthetic Kinect v1 frame pair: 20 ICP
+iterations (21 brute-force association passes, icp.cpp:149-258), threshold 0 so
+none exits early.  Default workload = BASELINE.json configs[1]: full-resolution
+640x480 (~292k valid points per cloud), one B200 per rank, weak scaling (every
+rank registers its own frame pair).  Prints ONE JSON line on rank 0.
+
+--impl reference times the CPU restatement of the reference path (oracle/, all
+host threads) on a bounded sample of the same workload and extrapolates; it is
+the only place besides the cpu_baseline leg where bench.py executes oracle/.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "icp-slam-prototype_b200", "python"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "icp_registrations_per_s"
+UNIT = "registrations/s"
+ITERS = 20
+FLOP_PER_PAIR = 8  # 3 sub + 3 mul + 2 add, icp.cpp:607-611
+
+WORKLOADS = {
+    "fullres": dict(name="configs[1]: full-resolution Kinect v1 640x480 frame-pair ICP, 20 iterations", points=None),
+    "10k": dict(name="configs[0]: Kinect v1 frame pair subsampled to 10k points, 20 iterations", points=10000),
+}
+
+
+def make_pair(seed_offset, points):
+    """Synthetic frame pair -> (depth_prev, depth_cur, bgr, data_pts, target_pts) via the oracle-free generator."""
+    from icpb200 import synth
+    d0, d1, col, _ = synth.frame_pair(seed=synth.MASTER_SEED + 17 * seed_offset)
+    return d0, d1, col
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[4 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def cpu_sample_registration_rate(data, target, n_threads, sample_queries, seed=0):
+    """Times ONE association pass of the oracle on a seeded sample of the queries against the full
+    target and extrapolates linearly to N queries x (ITERS+1) passes."""
+    from oracle import oracle as orc
+    rng = np.random.default_rng(seed)
+    n = len(data)
+    k = min(sample_queries, n)
+    sel = np.sort(rng.choice(n, size=k, replace=False))
+    sample = np.ascontiguousarray(data[sel])
+    t0 = time.perf_counter()
+    orc.nn(sample, target, n_threads=n_threads)
+    dt = time.perf_counter() - t0
+    per_reg = dt * (n / k) * (ITERS + 1)
+    return 1.0 / per_reg, dt, k
+
+
+def run_reference(args, rank, world):
+    """CPU reference arm: rank 0 alone runs; other ranks exit 0 without work."""
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    orc.build()
+    wl = WORKLOADS[args.workload]
+    d0, d1, col = make_pair(0, wl["points"])
+    from icpb200 import synth
+    p0, _, _ = orc.backproject(d0, col)
+    p1, _, _ = orc.backproject(d1, col)
+    cam = np.array([5, 5, 5], np.float32)
+    target = orc.translate(p0, cam)
+    data = orc.translate(p1, cam)
+    if wl["points"]:
+        data = synth.subsample_exact(data, wl["points"], 1)
+        target = synth.subsample_exact(target, wl["points"], 2)
+    threads = os.cpu_count() or 1
+    # bounded sample: ~1-2 s of wall time per step on a many-core host
+    sample_q = max(256, min(len(data), int(2.0e9 * threads / 8 / max(len(target), 1) / 6.5)))
+    vals = []
+    for s in range(args.warmup + args.steps):
+        v, dt, k = cpu_sample_registration_rate(data, target, threads, sample_q, seed=s)
+        if s >= args.warmup:
+            vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = 1000.0 / value
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "n_data": int(len(data)), "n_target": int(len(target)),
+                   "nn_passes": ITERS + 1},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"each step: one association pass of {k} seeded queries against the full "
+                                   f"{len(target)}-point target with {threads} OpenMP threads, extrapolated "
+                                   f"linearly to {len(data)} queries x {ITERS + 1} passes"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args, rank, world, local):
+    import torch
+    import icpb200
+    from icpb200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libicpb200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    wl = WORKLOADS[args.workload]
+    d0, d1, col = make_pair(rank, wl["points"])
+    h, w = d0.shape
+    ctx = icpb200.Context(local)
+    K = icpb200.reference_intrinsics_v1()
+    cam = np.array([5, 5, 5], np.float32)  # icp.cpp:53
+
+    # pinned host frames for the e2e leg
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    hd0, hd1, hcol = pin(d0), pin(d1), pin(col)
+
+    target = ctx.cloud(w * h)
+    pristine = ctx.cloud(w * h)
+    work = ctx.cloud(w * h)
+    target.from_depth(hd0, hcol, K); target.transform(None, cam)
+    pristine.from_depth(hd1, hcol, K); pristine.transform(None, cam)
+    if wl["points"]:
+        tp = synth.subsample_exact(target.download(), wl["points"], 2)
+        dp = synth.subsample_exact(pristine.download(), wl["points"], 1)
+        target.upload(tp); pristine.upload(dp)
+    n, m = pristine.n, target.n
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
+
+    def step(profile=False):
+        flush.zero_()
+        torch.cuda.synchronize()
+        ctx.timer_start()
+        work.copy_from(pristine)
+        res, _, _ = ctx.icp_register(work, target, ITERS, 0.0, 0.75, icpb200.SOLVE_REFERENCE)
+        ms = ctx.timer_stop()
+        return ms, res
+
+    for _ in range(args.warmup):
+        step()
+    fp32_tf, _ = ctx.measure_fp32_peak(5)
+
+    ctx.set_profiling(True)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = ctx.launch_count()
+    step_ms, nn_ms, nn_launches, res = [], 0.0, 0, None
+    for _ in range(args.steps):
+        ms, res = step()
+        step_ms.append(ms)
+        nn_ms += res["nn_partial_ms"]; nn_launches += res["nn_partial_launches"]
+    l1 = ctx.launch_count()
+    barrier()
+    clocks = sampler.stop()
+    ctx.set_profiling(False)
+    total_ms = float(np.sum(step_ms))
+    assert res["iterations"] == ITERS and res["nn_passes"] == ITERS + 1
+
+    # ---- e2e: host frames -> C-ABI -> pose on the host, copies inside the timed region
+    e2e_ms = []
+    c_prev, c_cur = ctx.cloud(w * h), ctx.cloud(w * h)
+    for s in range(args.warmup + args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        ctx.timer_start()
+        if wl["points"]:
+            c_prev.upload(tp); c_cur.upload(dp)
+        else:
+            c_prev.from_depth(hd0, hcol, K); c_prev.transform(None, cam)
+            c_cur.from_depth(hd1, hcol, K); c_cur.transform(None, cam)
+        r2, _, _ = ctx.icp_register(c_cur, c_prev, ITERS, 0.0, 0.75, icpb200.SOLVE_REFERENCE)
+        ms = ctx.timer_stop()
+        if s >= args.warmup:
+            e2e_ms.append(ms)
+    if wl["points"]:
+        h2d = 2 * wl["points"] * 16
+    else:
+        h2d = 2 * (hd0.nbytes + hcol.nbytes)
+    d2h = 2 * 4 + 400  # two point counts + the result/state block
+
+    if world > 1:
+        t = torch.tensor([total_ms, float(np.sum(e2e_ms))], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_total = t.tolist()
+    else:
+        e2e_total = float(np.sum(e2e_ms))
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        value = world * 1000.0 / ms_per_step
+        e2e_value = world * 1000.0 / (e2e_total / args.steps)
+        flop_per_launch = float(FLOP_PER_PAIR) * n * m
+        avg_launch_s = (nn_ms / max(nn_launches, 1)) * 1e-3
+        achieved = flop_per_launch / avg_launch_s / 1e12
+        nominal = 148 * 128 * 2 * (clocks["sm_max_mhz"] if clocks else 1965.0) * 1e6 / 1e12
+        peak = max(fp32_tf, 1e-9)
+        # CPU baseline: oracle port, 1 thread (the reference is single threaded), bounded sample
+        from oracle import oracle as orc
+        orc.build()
+        dpts, tpts = pristine.download(), target.download()
+        sample_q = max(64, min(n, int(12.0 / (m * 7.0e-9))))  # ~12 s of single-thread work
+        cpu_v, cpu_dt, cpu_k = cpu_sample_registration_rate(dpts, tpts, 1, sample_q)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "n_data": n, "n_target": m, "icp_iterations": ITERS,
+                       "nn_passes": ITERS + 1, "solve_mode": "reference", "per_rank": "one frame pair per GPU",
+                       "l2": "flushed between timed steps (256 MiB device write)",
+                       "nn_qpt": res["nn_qpt"], "nn_splits": res["nn_splits"],
+                       "exact_rescans_last_step": res["exact_rescans"]},
+            "extra": {"nn_correspondences_per_s": world * n * (ITERS + 1) / (ms_per_step * 1e-3),
+                      "nn_pairs_per_s": world * float(n) * m * (ITERS + 1) / (ms_per_step * 1e-3),
+                      "nn_partial_share_of_step": nn_ms / total_ms if world == 1 else None,
+                      "fp32_peak_nominal_tflops": nominal, "fp32_peak_ffma_microbench_tflops": fp32_tf},
+            "roofline": {"bound": "fp32", "kernel": "nn_partial_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": "FFMA micro-benchmark measured in this run (MEASURED_PEAKS.json holds "
+                                        "only HBM and bf16 tensor peaks; the NN scan is FP32 CUDA-core bound)",
+                         "flop_per_launch": flop_per_launch, "avg_launch_ms": avg_launch_s * 1e3,
+                         "launches_timed": nn_launches},
+            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": f"one association pass of {cpu_k} seeded queries against the full "
+                                       f"{m}-point target ({cpu_dt:.2f} s), extrapolated linearly to {n} queries "
+                                       f"x {ITERS + 1} passes"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(l1 - l0),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="fullres", choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank, world, local = dist_setup(args.gpus)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3  # timing rule: at least 3 warm-up steps
+        run_b200(args, rank, world, local)
+
+
+if __name__ == "__main__":
+    main()
