@@ -15,8 +15,18 @@ namespace icpb {
 // ---- tunables of the brute-force NN kernel (DESIGN.md "N1-N3") -----------
 constexpr int kGroup = 32;          // targets per min-tracking group (exactly re-scanned per query)
 constexpr int kNnThreads = 128;     // threads per CTA of nn_partial
-constexpr int kStageGroups = 16;    // groups per shared-memory stage (16*32*12 B = 6 KB)
-constexpr int kStages = 4;          // TMA bulk-copy ring depth
+#ifndef ICPB_STAGE_GROUPS
+#define ICPB_STAGE_GROUPS 16
+#endif
+#ifndef ICPB_STAGES
+#define ICPB_STAGES 4
+#endif
+#ifndef ICPB_UNROLL_J
+#define ICPB_UNROLL_J 2
+#endif
+constexpr int kStageGroups = ICPB_STAGE_GROUPS; // groups per shared-memory stage (16*32*12 B = 6 KB)
+constexpr int kStages = ICPB_STAGES;            // TMA bulk-copy ring depth
+constexpr int kUnrollJ = ICPB_UNROLL_J;        // unroll of the 4-target inner step
 constexpr int kChunk = 256;         // canonical reduction chunk (CANON-3)
 constexpr int kTerms = 20;          // a(3) b(3) b a^T(9) d(1) a-b(3) count(1)
 constexpr float kPadCoord = 1.0e18f; // padding targets: (a-b)^2 ~ 3e36, finite, never the minimum

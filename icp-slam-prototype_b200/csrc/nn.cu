@@ -174,7 +174,7 @@ template <int QPT>
 __global__ void __launch_bounds__(kNnThreads) nn_partial_kernel(const RegDesc *__restrict__ descs, int splits,
                                                                 int pass)
 {
-    const RegDesc &d = descs[blockIdx.z];
+    const RegDesc d = descs[blockIdx.z]; // by value: no pointer reloads after stores
     IcpState *st = d.st;
     if (st->done) return;
     const int n = d.n;
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(kNnThreads) nn_partial_kernel(const RegDesc *_
             float gm[QPT];
 #pragma unroll
             for (int q = 0; q < QPT; ++q) gm[q] = CUDART_INF_F;
-#pragma unroll 2
+#pragma unroll kUnrollJ
             for (int j = 0; j < kGroup / 4; ++j) {
                 const float4 X = s4[j];
                 const float4 Y = s4[kGroup / 4 + j];
@@ -330,55 +330,73 @@ __device__ __forceinline__ double warp_fold(double v)
 // 3x3 SVD (one-sided Jacobi, double) -- stands in for cv::SVD, icp.cpp:215.
 // Same operation sequence as the host-side oracle so results are bit equal.
 // --------------------------------------------------------------------------
-__device__ void svd3(const double *Ain, double *U, double *w, double *Vt)
+// One Jacobi rotation on the column pair (P, Q); compile-time indices keep A and V in registers.
+template <int P, int Q>
+__device__ __forceinline__ int jacobi_pair(double (&A)[9], double (&V)[9])
+{
+    const double eps = 2.220446049250313e-16;
+    double alpha = (A[P] * A[P] + A[3 + P] * A[3 + P]) + A[6 + P] * A[6 + P];
+    double beta = (A[Q] * A[Q] + A[3 + Q] * A[3 + Q]) + A[6 + Q] * A[6 + Q];
+    double gamma = (A[P] * A[Q] + A[3 + P] * A[3 + Q]) + A[6 + P] * A[6 + Q];
+    if (fabs(gamma) <= eps * sqrt(alpha * beta)) return 0;
+    double zeta = (beta - alpha) / (2.0 * gamma);
+    double az = fabs(zeta);
+    double t = 1.0 / (az + sqrt(1.0 + zeta * zeta));
+    if (zeta < 0.0) t = -t;
+    double c = 1.0 / sqrt(1.0 + t * t);
+    double sn = c * t;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        double a = A[3 * r + P], b = A[3 * r + Q];
+        A[3 * r + P] = c * a - sn * b;
+        A[3 * r + Q] = sn * a + c * b;
+        double va = V[3 * r + P], vb = V[3 * r + Q];
+        V[3 * r + P] = c * va - sn * vb;
+        V[3 * r + Q] = sn * va + c * vb;
+    }
+    return 1;
+}
+
+template <int I, int J>
+__device__ __forceinline__ void swap_cols(double (&A)[9], double (&V)[9], double (&w)[3])
+{
+    double tw = w[I]; w[I] = w[J]; w[J] = tw;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        double ta = A[3 * r + I]; A[3 * r + I] = A[3 * r + J]; A[3 * r + J] = ta;
+        double tv = V[3 * r + I]; V[3 * r + I] = V[3 * r + J]; V[3 * r + J] = tv;
+    }
+}
+
+__device__ void svd3(const double *Ain, double (&U)[9], double (&w)[3], double (&Vt)[9])
 {
     double A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+#pragma unroll
     for (int k = 0; k < 9; ++k) A[k] = Ain[k];
-    const double eps = 2.220446049250313e-16;
     for (int sweep = 0; sweep < 30; ++sweep) {
-        int changed = 0;
-        for (int k = 0; k < 3; ++k) {
-            const int p = (k == 2) ? 1 : 0;
-            const int q = (k == 0) ? 1 : 2;
-            double alpha = (A[p] * A[p] + A[3 + p] * A[3 + p]) + A[6 + p] * A[6 + p];
-            double beta = (A[q] * A[q] + A[3 + q] * A[3 + q]) + A[6 + q] * A[6 + q];
-            double gamma = (A[p] * A[q] + A[3 + p] * A[3 + q]) + A[6 + p] * A[6 + q];
-            if (fabs(gamma) <= eps * sqrt(alpha * beta)) continue;
-            changed = 1;
-            double zeta = (beta - alpha) / (2.0 * gamma);
-            double az = fabs(zeta);
-            double t = 1.0 / (az + sqrt(1.0 + zeta * zeta));
-            if (zeta < 0.0) t = -t;
-            double c = 1.0 / sqrt(1.0 + t * t);
-            double s = c * t;
-            for (int r = 0; r < 3; ++r) {
-                double a = A[3 * r + p], b = A[3 * r + q];
-                A[3 * r + p] = c * a - s * b;
-                A[3 * r + q] = s * a + c * b;
-                double va = V[3 * r + p], vb = V[3 * r + q];
-                V[3 * r + p] = c * va - s * vb;
-                V[3 * r + q] = s * va + c * vb;
-            }
-        }
+        int changed = jacobi_pair<0, 1>(A, V);
+        changed |= jacobi_pair<0, 2>(A, V);
+        changed |= jacobi_pair<1, 2>(A, V);
         if (!changed) break;
     }
+#pragma unroll
     for (int k = 0; k < 3; ++k) w[k] = sqrt((A[k] * A[k] + A[3 + k] * A[3 + k]) + A[6 + k] * A[6 + k]);
-    for (int i = 0; i < 2; ++i) {
-        int best = i;
-        for (int j = i + 1; j < 3; ++j)
-            if (w[j] > w[best]) best = j;
-        if (best != i) {
-            double tw = w[i]; w[i] = w[best]; w[best] = tw;
-            for (int r = 0; r < 3; ++r) {
-                double ta = A[3 * r + i]; A[3 * r + i] = A[3 * r + best]; A[3 * r + best] = ta;
-                double tv = V[3 * r + i]; V[3 * r + i] = V[3 * r + best]; V[3 * r + best] = tv;
-            }
-        }
+    // the oracle's selection sort (descending, first maximum wins), spelled out with constant indices
+    {
+        int best = 0;
+        if (w[1] > w[best]) best = 1;
+        if (w[2] > w[best]) best = 2;
+        if (best == 1) swap_cols<0, 1>(A, V, w);
+        else if (best == 2) swap_cols<0, 2>(A, V, w);
+        if (w[2] > w[1]) swap_cols<1, 2>(A, V, w);
     }
+#pragma unroll
     for (int k = 0; k < 3; ++k) {
         if (w[k] > 0.0) {
+#pragma unroll
             for (int r = 0; r < 3; ++r) U[3 * r + k] = A[3 * r + k] / w[k];
         } else {
+#pragma unroll
             for (int r = 0; r < 3; ++r) U[3 * r + k] = 0.0;
         }
     }
@@ -387,7 +405,9 @@ __device__ void svd3(const double *Ain, double *U, double *w, double *Vt)
         U[5] = U[6] * U[1] - U[0] * U[7];
         U[8] = U[0] * U[4] - U[3] * U[1];
     }
+#pragma unroll
     for (int i = 0; i < 3; ++i)
+#pragma unroll
         for (int j = 0; j < 3; ++j) Vt[3 * i + j] = V[3 * j + i];
 }
 
@@ -440,7 +460,21 @@ __device__ float mse_from_sums(const double *sums)
 
 // The body of the while loop of icp.cpp:155-258 for one iteration, minus the
 // association itself.  Runs in one thread.
-__device__ void solve_step(IcpState *st, const IcpParamsDev *prm, const double *sums, int pass)
+__device__ void solve_step_local(IcpState *st, const IcpParamsDev *prm, const double *sums, int pass);
+
+// Works on a register / local copy of the state: one global read and one global write of the block.
+__device__ __noinline__ void solve_step(IcpState *gst, const IcpParamsDev *gprm, const double *sums, int pass)
+{
+    IcpState st = *gst;
+    IcpParamsDev prm = *gprm;
+    double lsums[kTerms];
+#pragma unroll
+    for (int k = 0; k < kTerms; ++k) lsums[k] = sums[k];
+    solve_step_local(&st, &prm, lsums, pass);
+    *gst = st;
+}
+
+__device__ __forceinline__ void solve_step_local(IcpState *st, const IcpParamsDev *prm, const double *sums, int pass)
 {
     st->passes = pass + 1;
     st->last_buf = (pass + 1) & 1;
@@ -470,7 +504,9 @@ __device__ void solve_step(IcpState *st, const IcpParamsDev *prm, const double *
     double U[9], w[3], Vt[9], Rd[9];
     if (prm->solve_mode == ICPB_SOLVE_REFERENCE) {
         svd3(&sums[6], U, w, Vt); // icp.cpp:212-215, M = sum b a^T (uncentred)
+#pragma unroll
         for (int r = 0; r < 3; ++r)
+#pragma unroll
             for (int c = 0; c < 3; ++c)
                 Rd[3 * r + c] = (Vt[r] * U[3 * c] + Vt[3 + r] * U[3 * c + 1]) + Vt[6 + r] * U[3 * c + 2]; // :218
         float R[9];
@@ -491,11 +527,16 @@ __device__ void solve_step(IcpState *st, const IcpParamsDev *prm, const double *
         double cA[3] = {sums[0] / cnt, sums[1] / cnt, sums[2] / cnt};
         double cB[3] = {sums[3] / cnt, sums[4] / cnt, sums[5] / cnt};
         double H[9];
+#pragma unroll
         for (int r = 0; r < 3; ++r)
+#pragma unroll
             for (int c = 0; c < 3; ++c) H[3 * r + c] = sums[6 + 3 * c + r] - (cnt * cA[r]) * cB[c];
         svd3(H, U, w, Vt);
+#pragma unroll
         for (int p = 0; p < 2; ++p) {
+#pragma unroll
             for (int r = 0; r < 3; ++r)
+#pragma unroll
                 for (int c = 0; c < 3; ++c)
                     Rd[3 * r + c] = (Vt[r] * U[3 * c] + Vt[3 + r] * U[3 * c + 1]) + Vt[6 + r] * U[3 * c + 2];
             double det = Rd[0] * (Rd[4] * Rd[8] - Rd[5] * Rd[7]) - Rd[1] * (Rd[3] * Rd[8] - Rd[5] * Rd[6]) +
@@ -531,7 +572,7 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
                                                              const IcpParamsDev *__restrict__ prm, int splits,
                                                              int pass)
 {
-    const RegDesc &d = descs[blockIdx.z];
+    const RegDesc d = descs[blockIdx.z]; // by value: no pointer reloads after stores
     IcpState *st = d.st;
     if (st->done) return;
     const int n = d.n, m = d.m;
@@ -561,12 +602,24 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
     float m1 = CUDART_INF_F, m2 = CUDART_INF_F;
     int g = 0;
     if (valid) {
-        for (int s = 0; s < splits; ++s) {
-            size_t o = (size_t)s * d.n_stride + i;
-            float p1 = d.pm1[o], p2 = d.pm2[o];
-            int pgv = d.pg[o];
-            m2 = fminf(fminf(m2, p2), fmaxf(m1, p1));
-            if (p1 < m1) { m1 = p1; g = pgv; }
+        // loads first (independent, batched), then the order-dependent combine on registers
+        constexpr int kB = 8;
+        for (int s0 = 0; s0 < splits; s0 += kB) {
+            float p1[kB], p2[kB];
+            int pgv[kB];
+#pragma unroll
+            for (int k = 0; k < kB; ++k) {
+                const int s = min(s0 + k, splits - 1);
+                const size_t o = (size_t)s * d.n_stride + i;
+                p1[k] = __ldcg(&d.pm1[o]); p2[k] = __ldcg(&d.pm2[o]); pgv[k] = __ldcg(&d.pg[o]);
+            }
+#pragma unroll
+            for (int k = 0; k < kB; ++k) {
+                if (s0 + k < splits) {
+                    m2 = fminf(fminf(m2, p2[k]), fmaxf(m1, p1[k]));
+                    if (p1[k] < m1) { m1 = p1[k]; g = pgv[k]; }
+                }
+            }
         }
     }
     int best_i = 0;
@@ -575,14 +628,15 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
     if (valid && !ambiguous) {
         // exact re-evaluation of the winning group (reference arithmetic, ascending index, strict <)
         const int t0 = g * kGroup;
-        const int t1 = min(m, t0 + kGroup);
         float4 b = d.tgt[t0];
         best_d = exact_distance(a.x, a.y, a.z, b.x, b.y, b.z);
         best_i = t0;
-        for (int t = t0 + 1; t < t1; ++t) {
-            b = d.tgt[t];
+#pragma unroll 8
+        for (int k = 1; k < kGroup; ++k) {
+            const int t = t0 + k;
+            b = d.tgt[min(t, m - 1)];
             float dd = exact_distance(a.x, a.y, a.z, b.x, b.y, b.z);
-            if (dd < best_d) { best_d = dd; best_i = t; }
+            if (t < m && dd < best_d) { best_d = dd; best_i = t; }
         }
     }
     if (ambiguous) {
@@ -675,11 +729,22 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
 
     // ---- last CTA of this registration: CANON-3 level 2, then the solve
     __threadfence();
-    for (int k = 0; k < kTerms; ++k) {
-        double acc = 0.0;
-        for (int c = tid; c < nchunks; c += kChunk) acc = acc + __ldcg(&d.chunk_sums[(size_t)c * kTerms + k]);
-        double v = warp_fold(acc);
-        if ((tid & 31) == 0) s_w[tid >> 5][k] = v;
+    {
+        double acc[kTerms];
+#pragma unroll
+        for (int k = 0; k < kTerms; ++k) acc[k] = 0.0;
+        for (int c = tid; c < nchunks; c += kChunk) {
+            double v[kTerms];
+#pragma unroll
+            for (int k = 0; k < kTerms; ++k) v[k] = __ldcg(&d.chunk_sums[(size_t)c * kTerms + k]); // issued together
+#pragma unroll
+            for (int k = 0; k < kTerms; ++k) acc[k] = acc[k] + v[k];
+        }
+#pragma unroll
+        for (int k = 0; k < kTerms; ++k) {
+            double v = warp_fold(acc[k]);
+            if ((tid & 31) == 0) s_w[tid >> 5][k] = v;
+        }
     }
     __syncthreads();
     if (tid < kTerms) {
@@ -689,7 +754,7 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
     }
     __syncthreads();
     if (tid == 0) {
-        st->block_counter = 0;
+        st->block_counter = 0; // re-armed before solve_step copies the state
         solve_step(st, prm, s_tot, pass);
     }
 }

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-LIB_PATH = os.path.join(_PKG, "lib", "libicpb200.so")
+LIB_PATH = os.environ.get("ICPB_LIB") or os.path.join(_PKG, "lib", "libicpb200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "icpb200.h")
 
 POINT_DTYPE = np.dtype(
