@@ -76,7 +76,8 @@ def test_oracle_icp_golden(orc):
 def test_oracle_rays_golden(orc):
     z = _load("rays_small.npz")
     grid = z["start"].copy()
-    v = orc.map_integrate_rays(grid, tuple(z["dims"]), float(z["cell"]), z["points"], tuple(z["origin"]), 25, 25)
+    v = orc.map_integrate_rays(grid, tuple(int(d) for d in z["dims"]), float(z["cell"]), z["points"],
+                               tuple(float(x) for x in z["origin"]), 25, 25)
     assert v == int(z["orc_visited"]) and np.array_equal(grid, z["orc_grid"])
 
 
