@@ -1,0 +1,551 @@
+// Host side of the drop-in headers (include/icpb200/{icp,pointcloud,map}.hpp): the reference's C++ entry
+// points, marshalled onto the C-ABI of libicpb200.so.  Bulk paths (depth -> XYZ, rotate / translate,
+// association scans, the registration loop, grid updates) run on the B200; only the scalar helpers the
+// reference also evaluates per call (distance, meanSquareError, calculateOffset, makeRotationMatrix,
+// getVoxelCoordinates, key-point lifting, mapCloud bookkeeping) are host code.  No CPU fallback: without a
+// usable device the first bulk call prints the library's error and aborts.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <unordered_set>
+
+#include "icpb200.h"
+#include "icpb200/map.hpp"
+
+namespace {
+
+struct Host {
+    icpb_ctx *ctx = nullptr;
+    icpb_cloud *slot[3] = {nullptr, nullptr, nullptr};
+    int cap[3] = {0, 0, 0};
+};
+
+Host &H()
+{
+    static Host h;
+    if (!h.ctx) {
+        const char *dev = getenv("ICPB_DEVICE");
+        int rc = icpb_ctx_create(dev ? atoi(dev) : 0, &h.ctx);
+        if (rc != ICPB_OK) {
+            fprintf(stderr, "icpb200: %s (%s)\n", icpb_last_error(nullptr), icpb_status_string(rc));
+            abort();
+        }
+    }
+    return h;
+}
+
+void check(int rc, const char *what)
+{
+    if (rc != ICPB_OK) {
+        fprintf(stderr, "icpb200: %s failed: %s\n", what, icpb_last_error(H().ctx));
+        abort();
+    }
+}
+
+// Device scratch cloud `i` with room for n points.
+icpb_cloud *scratch(int i, int n)
+{
+    Host &h = H();
+    if (h.cap[i] < n || !h.slot[i]) {
+        if (h.slot[i]) icpb_cloud_destroy(h.slot[i]);
+        int cap = n + n / 4 + 16;
+        check(icpb_cloud_create(h.ctx, cap, &h.slot[i]), "icpb_cloud_create");
+        h.cap[i] = cap;
+    }
+    return h.slot[i];
+}
+
+icpb_cloud *upload(int i, const point_list_t &pts)
+{
+    icpb_cloud *c = scratch(i, (int)pts.size());
+    check(icpb_cloud_upload(c, reinterpret_cast<const icpb_point *>(pts.data()), (int)pts.size()), "icpb_cloud_upload");
+    return c;
+}
+
+void download(icpb_cloud *c, point_list_t &pts)
+{
+    int n = 0;
+    check(icpb_cloud_size(c, &n), "icpb_cloud_size");
+    pts.resize((size_t)n);
+    if (n) check(icpb_cloud_download(c, reinterpret_cast<icpb_point *>(pts.data()), n, &n), "icpb_cloud_download");
+}
+
+// cv::Mat operator* on 3x3 CV_32F: float, no FMA, left to right (what OpenCV's small-matrix gemm does).
+void mul33(const float *A, const float *B, float *C)
+{
+    float T[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) T[3 * i + j] = (A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j]) + A[3 * i + 2] * B[6 + j];
+    for (int k = 0; k < 9; ++k) C[k] = T[k];
+}
+
+cv::Mat mat33(const float *v)
+{
+    cv::Mat m(3, 3, CV_32FC1);
+    for (int k = 0; k < 9; ++k) m.at<float>(k / 3, k % 3) = v[k];
+    return m;
+}
+
+// file-scope state of icp.cpp:22-26
+struct IcpGlobals {
+    float cameraRotation[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    float lastTranslation[3] = {0, 0, 0};
+    cv::Point3f cameraPosition;
+    map::Map *map = nullptr;
+    bool started = false;
+};
+IcpGlobals &G()
+{
+    static IcpGlobals g;
+    if (!g.map) g.map = new map::Map();
+    return g;
+}
+
+void lift(const cv::Mat &data, const cv::Mat &colorMat, int x, int y, color_point_t &out)
+{
+    // pointcloud.cpp:37-39 / 85-87 (CX and FX on both axes)
+    float p_z = ((float)data.at<uint16_t>(y, x)) / 5000.0f;
+    float p_x = (x - CX) * p_z / FX;
+    float p_y = (y - CX) * p_z / FX;
+    out.point = cv::Point3f(p_x, p_y, p_z);
+    out.color = colorMat.empty() ? cv::Vec3b() : colorMat.at<cv::Vec3b>(y, x);
+}
+
+} // namespace
+
+// ================================================================ pointcloud.hpp
+namespace icp {
+
+static void build_from_depth(PointCloud &pc, cv::Mat &data, cv::Mat &colorMat)
+{
+    const int w = data.cols, h = data.rows;
+    const uint16_t *d = reinterpret_cast<const uint16_t *>(data.data);
+    // One rand() per non-zero pixel in raster order, exactly where the reference draws it (pointcloud.cpp:22-28)
+    std::vector<uint8_t> keep;
+    keep.reserve((size_t)w * h);
+    for (int i = 0; i < w * h; ++i)
+        if (d[i] != 0) keep.push_back((rand() % SUBSAMPLE_FACTOR) == 0);
+    if (keep.empty()) keep.push_back(0);
+    icpb_intrinsics K;
+    icpb_intrinsics_reference_v1(&K);
+    icpb_cloud *c = scratch(0, w * h);
+    check(icpb_cloud_from_depth(c, d, colorMat.empty() ? nullptr : colorMat.data, w, h, &K, ICPB_SUB_STREAM, SUBSAMPLE_FACTOR, 0,
+                                keep.data(), (int)keep.size()),
+          "icpb_cloud_from_depth");
+    download(c, pc.points);
+    // center: float running sum, then / count (pointcloud.cpp:43-45,100-102; 0/0 = NaN when empty, as there)
+    pc.center = cv::Point3f(0, 0, 0);
+    for (const color_point_t &p : pc.points) { pc.center.x += p.point.x; pc.center.y += p.point.y; pc.center.z += p.point.z; }
+    int index = (int)pc.points.size();
+    pc.center.x /= index; pc.center.y /= index; pc.center.z /= index;
+}
+
+PointCloud::PointCloud(cv::Mat &data, cv::Mat colorMat, std::vector<cv::KeyPoint> keypointsList)
+{
+    build_from_depth(*this, data, colorMat);
+    for (const cv::KeyPoint &kp : keypointsList) { // pointcloud.cpp:64-97
+        int x = (int)std::lrint(kp.pt.x), y = (int)std::lrint(kp.pt.y); // Point2f -> Point2i rounds (saturate_cast)
+        if (data.at<uint16_t>(y, x) == 0) continue;
+        color_point_t p;
+        lift(data, colorMat, x, y, p);
+        keypoints.push_back(p);
+    }
+    center_points();
+}
+
+PointCloud::PointCloud(cv::Mat &data, cv::Mat colorMat)
+{
+    build_from_depth(*this, data, colorMat);
+    center_points();
+}
+
+PointCloud::PointCloud(std::vector<cv::Point3f> data) // pointcloud.cpp:256-287
+{
+    center = cv::Point3f(0, 0, 0);
+    int index = 0;
+    for (const cv::Point3f &p : data) {
+        color_point_t c;
+        c.point = p;
+        points.push_back(c);
+        center.x += p.x; center.y += p.y; center.z += p.z;
+        index++;
+    }
+    center.x /= index; center.y /= index; center.z /= index;
+    center_points();
+}
+
+PointCloud::PointCloud() { center = cv::Point3f(0, 0, 0); }
+
+void PointCloud::center_points() {} // pointcloud.cpp:296-319 mutates local copies only: a no-op
+
+void PointCloud::rotate(cv::Mat &R) // pointcloud.cpp:321-346 (about the world origin; center untouched)
+{
+    float r[9];
+    for (int k = 0; k < 9; ++k) r[k] = R.at<float>(k / 3, k % 3);
+    if (!points.empty()) {
+        icpb_cloud *c = upload(0, points);
+        check(icpb_cloud_transform(c, r, nullptr), "icpb_cloud_transform");
+        download(c, points);
+    }
+    if (!keypoints.empty()) {
+        icpb_cloud *c = upload(0, keypoints);
+        check(icpb_cloud_transform(c, r, nullptr), "icpb_cloud_transform");
+        download(c, keypoints);
+    }
+}
+
+void PointCloud::translate(cv::Point3f offset) // pointcloud.cpp:349-359
+{
+    const float t[3] = {offset.x, offset.y, offset.z};
+    if (!points.empty()) {
+        icpb_cloud *c = upload(0, points);
+        check(icpb_cloud_transform(c, nullptr, t), "icpb_cloud_transform");
+        download(c, points);
+    }
+    if (!keypoints.empty()) {
+        icpb_cloud *c = upload(0, keypoints);
+        check(icpb_cloud_transform(c, nullptr, t), "icpb_cloud_transform");
+        download(c, keypoints);
+    }
+    center += offset;
+}
+
+static cv::Mat list_matrix(const point_list_t &pts, cv::Point3f add)
+{
+    cv::Mat M((int)pts.size(), 3, CV_32FC1);
+    for (size_t i = 0; i < pts.size(); ++i) {
+        M.at<float>((int)i, 0) = pts[i].point.x + add.x;
+        M.at<float>((int)i, 1) = pts[i].point.y + add.y;
+        M.at<float>((int)i, 2) = pts[i].point.z + add.z;
+    }
+    return M;
+}
+cv::Mat PointCloud::centered_matrix() { return list_matrix(points, cv::Point3f(0, 0, 0)); }            // :361-371 (no centring)
+cv::Mat PointCloud::centered_keypoint_matrix() { return list_matrix(keypoints, cv::Point3f(0, 0, 0)); } // :373-383
+cv::Mat PointCloud::matrix() { return list_matrix(points, center); }                                    // :385-395
+void PointCloud::displayColorPoints(cv::viz::Viz3d &, std::string, int) {}
+void PointCloud::displayKeyPoints(cv::viz::Viz3d &, std::string, int, cv::viz::Color) {}
+void PointCloud::displayAll(cv::viz::Viz3d &, std::string, int, cv::viz::Color) {}
+
+// ================================================================ icp.hpp
+
+float distance(cv::Point3f a, cv::Point3f b) // icp.cpp:595-602
+{
+    float x = a.x - b.x, y = a.y - b.y, z = a.z - b.z;
+    return (float)std::sqrt(std::pow((double)x, 2) + std::pow((double)y, 2) + std::pow((double)z, 2));
+}
+
+float distance(color_point_t a, color_point_t b) // icp.cpp:606-620 (COLOR_WEIGHT 0)
+{
+    float x = a.point.x - b.point.x, y = a.point.y - b.point.y, z = a.point.z - b.point.z;
+    float xyz = (float)((double)x * (double)x + (double)y * (double)y + (double)z * (double)z);
+    return std::sqrt(xyz);
+}
+
+float meanSquareError(std::vector<float> errors) // icp.cpp:622-638
+{
+    float error_sum = 0;
+    for (size_t i = 0; i < errors.size(); i++) error_sum += errors[i];
+    if (errors.size() > 0) {
+        error_sum /= errors.size();
+        error_sum = (float)std::pow((double)error_sum, 2);
+    }
+    return error_sum;
+}
+
+cv::Point3f calculateOffset(associations_t associations) // icp.cpp:314-344
+{
+    cv::Point3f offset(0, 0, 0);
+    int offset_count = 0;
+    for (const auto &pr : associations) {
+        offset += pr.first.point - pr.second.point;
+        offset_count++;
+    }
+    if (offset_count > 0) { offset.x /= offset_count; offset.y /= offset_count; offset.z /= offset_count; }
+    return offset;
+}
+
+cv::Mat makeRotationMatrix(float x, float y, float z) // icp.cpp:640-653
+{
+    double rotX = x * PI / 180, rotY = y * PI / 180, rotZ = z * PI / 180;
+    float d[9] = {1, 0, 0, 0, (float)cos(rotX), (float)sin(rotX), 0, (float)-sin(rotX), (float)cos(rotX)};
+    float f[9] = {(float)cos(rotY), 0, (float)-sin(rotY), 0, 1, 0, (float)sin(rotY), 0, (float)cos(rotY)};
+    float g[9] = {(float)cos(rotZ), (float)sin(rotZ), 0, (float)-sin(rotZ), (float)cos(rotZ), 0, 0, 0, 1};
+    float ab[9], abc[9];
+    mul33(d, f, ab);
+    mul33(ab, g, abc);
+    return mat33(abc);
+}
+
+void showAssocations(associations_t, std::vector<float>, cv::viz::Viz3d &) {}
+
+// Shared body of the association scans: exact brute-force NN on the device, compaction on the host.
+static void associate(const point_list_t &queries, const point_list_t &targets, float max_d, std::vector<float> &errors,
+                      associations_t &associations, point_list_t *rejects)
+{
+    const int n = (int)queries.size();
+    if (n == 0) return;
+    icpb_cloud *dc = upload(0, queries);
+    icpb_cloud *tc = upload(1, targets);
+    std::vector<int32_t> idx((size_t)n);
+    std::vector<float> dist((size_t)n);
+    check(icpb_nn_search(H().ctx, dc, tc, idx.data(), dist.data(), nullptr), "icpb_nn_search");
+    for (int i = 0; i < n; ++i) {
+        if (dist[i] < max_d) {
+            associations.push_back(std::make_pair(queries[i], targets[(size_t)idx[i]]));
+            errors.push_back(dist[i]);
+        } else if (rejects) {
+            rejects->push_back(queries[i]);
+        }
+    }
+}
+
+void findGlobalNearestNeighborAssociations(PointCloud &data, PointCloud &previous, std::vector<float> &errors,
+                                           associations_t &associations) // icp.cpp:541-563
+{
+    errors.clear();
+    associations.clear();
+    associate(data.points, previous.points, MAX_NN_COLOR_DISTANCE, errors, associations, nullptr);
+}
+
+void findGlobalKeyPointAssociations(PointCloud &data, std::vector<float> &errors, associations_t &associations,
+                                    point_list_t &nonAssociations) // icp.cpp:488-515
+{
+    map::Map &m = *G().map;
+    if (m.mapCloud.keypoints.size() == 0) return; // :490-491 (nothing is cleared)
+    errors.clear();
+    associations.clear();
+    associate(data.keypoints, m.mapCloud.keypoints, MAX_NN_KEYPOINT_DISTANCE, errors, associations, &nonAssociations);
+}
+
+// icp.cpp:347-369.  The reference's voxel-table search (:371-486) is dead code with out-of-bounds reads; an exact
+// indexed search must return what the brute-force scan over the mapped points returns, so that is what runs.
+void findMappedNearestNeighborAssociations(PointCloud &data, std::vector<float> &errors, associations_t &associations)
+{
+    errors.clear();
+    associations.clear();
+    map::Map &m = *G().map;
+    if (m.mapCloud.points.empty()) return;
+    associate(data.points, m.mapCloud.points, MAX_NN_COLOR_DISTANCE, errors, associations, nullptr);
+}
+
+static float nearest_one(const color_point_t &point, color_point_t &nearest, const point_list_t &targets)
+{
+    point_list_t q(1, point);
+    icpb_cloud *dc = upload(0, q);
+    icpb_cloud *tc = upload(1, targets);
+    int32_t idx = 0;
+    float d = 0.f;
+    check(icpb_nn_search(H().ctx, dc, tc, &idx, &d, nullptr), "icpb_nn_search");
+    nearest = targets[(size_t)idx];
+    return d;
+}
+float getNearestPoint(color_point_t point, color_point_t &nearest, PointCloud &cloud) { return nearest_one(point, nearest, cloud.points); }       // :566-593
+float getNearestKeyPoint(color_point_t point, color_point_t &nearest, PointCloud &cloud) { return nearest_one(point, nearest, cloud.keypoints); } // :517-539
+
+void resetState()
+{
+    IcpGlobals &g = G();
+    const float I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int k = 0; k < 9; ++k) g.cameraRotation[k] = I[k];
+    for (int k = 0; k < 3; ++k) g.lastTranslation[k] = 0.f;
+    g.cameraPosition = cv::Point3f(0, 0, 0);
+    g.started = false;
+    g.map->clear();
+    g.map->mapCloud = PointCloud();
+}
+cv::Mat cameraRotationState() { return mat33(G().cameraRotation); }
+cv::Point3f cameraPositionState() { return G().cameraPosition; }
+
+// icp.cpp:28-285 with the all-point association (:149/:253) against the previous frame's cloud placed at the
+// current camera pose.  Depth -> XYZ, the 20-iteration loop and the pose update all stay on the device.
+cv::Mat getTransformation(cv::Mat &data, cv::Mat &previous, cv::Mat color, std::vector<cv::KeyPoint> keypoints,
+                          cv::Mat &rotation, int maxIterations, float threshold, cv::viz::Viz3d &depthWindow)
+{
+    (void)rotation;
+    IcpGlobals &g = G();
+    PointCloud dataCloud(data, color, keypoints);       // :38
+    PointCloud previousCloud(previous, color, keypoints); // :39 (previous depth with the CURRENT colour / key-points)
+    if (!g.started) {                                   // :47-68
+        const float I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        for (int k = 0; k < 9; ++k) g.cameraRotation[k] = I[k];
+        g.cameraPosition = cv::Point3f(5, 5, 5);
+        for (int k = 0; k < 3; ++k) g.lastTranslation[k] = 0.f;
+        cv::Mat R0 = mat33(g.cameraRotation);
+        previousCloud.rotate(R0);
+        previousCloud.translate(g.cameraPosition);
+        g.map->update(previousCloud, MAX_CONFIDENCE, depthWindow);
+        g.map->mapCloud.points = previousCloud.points;
+        g.started = true;
+    } else {
+        cv::Mat Rc = mat33(g.cameraRotation);
+        previousCloud.rotate(Rc);
+        previousCloud.translate(g.cameraPosition);
+    }
+    // :70-71 on the device, then the loop
+    icpb_cloud *dc = upload(0, dataCloud.points);
+    icpb_cloud *tc = upload(1, previousCloud.points);
+    const float cp[3] = {g.cameraPosition.x, g.cameraPosition.y, g.cameraPosition.z};
+    check(icpb_cloud_transform(dc, g.cameraRotation, cp), "icpb_cloud_transform");
+    icpb_icp_params prm;
+    prm.max_iterations = maxIterations;
+    prm.threshold = threshold;
+    prm.max_nn_distance = MAX_NN_COLOR_DISTANCE;
+    prm.solve_mode = ICPB_SOLVE_REFERENCE;
+    for (int k = 0; k < 3; ++k) prm.last_translation[k] = g.lastTranslation[k];
+    prm.idx_trace = nullptr;
+    prm.dist_trace = nullptr;
+    icpb_icp_result res;
+    cv::Mat rigid(4, 4, CV_32FC1);
+    if (dataCloud.points.empty() || previousCloud.points.empty()) {
+        for (int k = 0; k < 16; ++k) rigid.at<float>(k / 4, k % 4) = (k % 5 == 0) ? 1.f : 0.f;
+        return rigid;
+    }
+    check(icpb_icp_register(H().ctx, dc, tc, &prm, &res), "icpb_icp_register");
+    // cameraRotation *= R (:237) and cameraPosition -= offset (:246), accumulated over the iterations
+    mul33(g.cameraRotation, res.cam_rotation, g.cameraRotation);
+    g.cameraPosition += cv::Point3f(res.cam_position[0], res.cam_position[1], res.cam_position[2]);
+    for (int k = 0; k < 3; ++k) g.lastTranslation[k] = -res.offset[k]; // :260
+    std::cout << res.mse;                                               // :264
+    // :270 (the all-point twin of :271): certainty update from the registered key-points
+    download(dc, dataCloud.points);
+    if (!dataCloud.keypoints.empty()) {
+        icpb_cloud *kc = upload(2, dataCloud.keypoints);
+        check(icpb_cloud_transform(kc, g.cameraRotation, nullptr), "icpb_cloud_transform");
+        const float np[3] = {g.cameraPosition.x, g.cameraPosition.y, g.cameraPosition.z};
+        check(icpb_cloud_transform(kc, nullptr, np), "icpb_cloud_transform");
+        download(kc, dataCloud.keypoints);
+        g.map->update(dataCloud, DELTA_CONFIDENCE, depthWindow);
+    }
+    std::cout << std::endl << g.map->mapCloud.points.size() << std::endl; // :279
+    for (int k = 0; k < 16; ++k) rigid.at<float>(k / 4, k % 4) = res.rigid[k];
+    return rigid;
+}
+
+} // namespace icp
+
+// ================================================================ map.hpp
+namespace map {
+
+Map::Map() : world(nullptr), dev_(nullptr) {}
+
+Map::~Map()
+{
+    if (dev_) icpb_map_destroy(dev_);
+    delete[] reinterpret_cast<unsigned char *>(world);
+}
+
+void Map::ensure()
+{
+    if (dev_) return;
+    const int dims[3] = {MAP_HEIGHT, MAP_HEIGHT, MAP_HEIGHT};
+    check(icpb_map_create(H().ctx, dims, float(CELL_PHYSICAL_HEIGHT), 0, MAP_HEIGHT, &dev_), "icpb_map_create");
+    world = reinterpret_cast<unsigned char (*)[MAP_HEIGHT][MAP_HEIGHT]>(new unsigned char[(size_t)MAP_HEIGHT * MAP_HEIGHT * MAP_HEIGHT]());
+}
+
+void Map::clear()
+{
+    ensure();
+    check(icpb_map_clear(dev_), "icpb_map_clear");
+    std::memset(world, 0, (size_t)MAP_HEIGHT * MAP_HEIGHT * MAP_HEIGHT);
+}
+
+void Map::syncWorld()
+{
+    ensure();
+    check(icpb_map_download(dev_, reinterpret_cast<uint8_t *>(world), (long long)MAP_HEIGHT * MAP_HEIGHT * MAP_HEIGHT), "icpb_map_download");
+}
+
+cv::Point3i Map::getVoxelCoordinates(cv::Point3f point) // map.cpp:55-85
+{
+    cv::Point3i p;
+    float c = float(CELL_PHYSICAL_HEIGHT);
+    p.x = int(point.x / c); p.y = int(point.y / c); p.z = int(point.z / c);
+    if (p.x < 0) p.x = 0;
+    if (p.x >= MAP_HEIGHT) p.x = MAP_HEIGHT - 1;
+    if (p.y < 0) p.y = 0;
+    if (p.y >= MAP_HEIGHT) p.y = MAP_HEIGHT - 1;
+    if (p.z < 0) p.z = 0;
+    if (p.z >= MAP_HEIGHT) p.z = MAP_HEIGHT - 1;
+    return p;
+}
+
+void Map::updatePoints(const point_list_t &pts, int rule, int delta)
+{
+    ensure();
+    if (pts.empty()) return;
+    icpb_cloud *c = upload(2, pts);
+    check(icpb_map_update_endpoints(dev_, c, rule, delta, MAX_CONFIDENCE), "icpb_map_update_endpoints");
+}
+
+// map.cpp:220-269: rule A over the cloud's key-points; a key-point whose voxel reaches MAX_CONFIDENCE and has
+// no table entry yet joins mapCloud.keypoints.  The grid update runs on the device; the (tiny) mapCloud
+// bookkeeping replays the per-voxel hit sequence on the host from the pre-update mirror.
+void Map::update(icp::PointCloud data, int delta_confidence, cv::viz::Viz3d &)
+{
+    ensure();
+    syncWorld();
+    updatePoints(data.keypoints, ICPB_RULE_A, delta_confidence);
+    static std::unordered_set<long long> table; // voxels that hold a lookup-table entry
+    if (mapCloud.keypoints.empty()) table.clear();
+    for (const color_point_t &p : data.keypoints) {
+        cv::Point3i v = getVoxelCoordinates(p.point);
+        unsigned char *c = &world[v.x][v.y][v.z];
+        if (*c > (255 - delta_confidence)) *c = 255;
+        else *c += delta_confidence;
+        long long key = ((long long)v.x * MAP_HEIGHT + v.y) * MAP_HEIGHT + v.z;
+        if (!table.count(key) && *c >= MAX_CONFIDENCE) { table.insert(key); mapCloud.keypoints.push_back(p); }
+    }
+}
+
+void Map::update(associations_t associations, int delta_confidence) // map.cpp:88-119 (never called by the reference)
+{
+    point_list_t firsts;
+    for (const auto &pr : associations) firsts.push_back(pr.first);
+    updatePoints(firsts, ICPB_RULE_A, delta_confidence);
+}
+
+void Map::update(associations_t keyPointAssociations, std::vector<float>, point_list_t nonAssociations, int delta_confidence)
+{
+    if (keyPointAssociations.size() == 0) return; // map.cpp:124-126
+    updatePoints(nonAssociations, ICPB_RULE_C, delta_confidence); // map.cpp:130-151 (certainty part)
+}
+
+// map.cpp:272-439 with the semantics of DESIGN.md "M4": one ray between two voxels.
+void Map::rayTrace(cv::Point3i point, cv::Point3i origin, cv::viz::Viz3d &)
+{
+    ensure();
+    const float c = float(CELL_PHYSICAL_HEIGHT);
+    point_list_t one(1);
+    one[0].point = cv::Point3f((point.x + 0.5f) * c, (point.y + 0.5f) * c, (point.z + 0.5f) * c);
+    icpb_cloud *cl = upload(2, one);
+    const float o[3] = {(origin.x + 0.5f) * c, (origin.y + 0.5f) * c, (origin.z + 0.5f) * c};
+    check(icpb_map_integrate_rays(dev_, cl, o, DELTA_CONFIDENCE, 0, nullptr), "icpb_map_integrate_rays");
+}
+
+void Map::integrateRays(icp::PointCloud &cloud, cv::Point3f origin, int delta_dec, int delta_inc)
+{
+    ensure();
+    if (cloud.points.empty()) return;
+    icpb_cloud *cl = upload(2, cloud.points);
+    const float o[3] = {origin.x, origin.y, origin.z};
+    check(icpb_map_integrate_rays(dev_, cl, o, delta_dec, delta_inc, nullptr), "icpb_map_integrate_rays");
+}
+
+void Map::drawCertaintyMap(cv::viz::Viz3d &) {}
+
+bool Map::isOccupied(cv::Point3f p) // map.cpp:441-444
+{
+    syncWorld();
+    cv::Point3i v = getVoxelCoordinates(p);
+    return world[v.x][v.y][v.z] >= MAX_CONFIDENCE;
+}
+
+int Map::bound(int t, int ds) // map.cpp:209-217 (always 1/ds; unused by the reference)
+{
+    if (ds < 0) return bound(-t, -ds);
+    t = ((t % 1) + 1) % 1;
+    return (1 - t) / ds;
+}
+
+} // namespace map

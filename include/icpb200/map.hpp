@@ -1,0 +1,55 @@
+// Drop-in for the reference's map.hpp (map.hpp:1-40): same macros and class map::Map.  The certainty
+// grid lives on the B200; `world` is a host mirror refreshed by syncWorld() (the reference's 27 MB array
+// member, map.hpp:25).  pointLookupTable (432 MB in the reference, map.hpp:24) is not materialised.
+#ifndef MAP_HPP
+#define MAP_HPP
+
+#include "icp.hpp"
+#include "pointcloud.hpp"
+
+#define MAP_HEIGHT 300
+#define PHYSICAL_HEIGHT 10.0f
+#define DELTA_CONFIDENCE 25
+#define MIN_CONFIDENCE 50
+#define MAX_CONFIDENCE 180
+#define MAX_POINT_ADD_DISTANCE 0.05f
+#define MAX_KEYPOINT_ADD_DISTANCE 0.1f
+
+#define CELL_PHYSICAL_HEIGHT PHYSICAL_HEIGHT / ((float) MAP_HEIGHT)
+
+struct icpb_map;
+
+namespace map {
+class Map { // map.hpp:20-37
+public:
+    color_point_t empty;
+    icp::PointCloud mapCloud;
+    unsigned char (*world)[MAP_HEIGHT][MAP_HEIGHT]; // world[x][y][z], host mirror of the device grid
+
+    Map();
+    ~Map();
+    Map(const Map &) = delete;
+    Map &operator=(const Map &) = delete;
+    void update(icp::PointCloud data, int delta_confidence, cv::viz::Viz3d &depthWindow);                  // map.cpp:220-269
+    void update(associations_t associations, int delta_confidencec);                                        // map.cpp:88-119
+    void update(associations_t keyPointAssociations, std::vector<float> errors, point_list_t nonAssociations,
+                int delta_confidence);                                                                      // map.cpp:122-151
+    void rayTrace(cv::Point3i point, cv::Point3i origin, cv::viz::Viz3d &depthWindow);                      // map.cpp:272-439
+    void drawCertaintyMap(cv::viz::Viz3d &depthWindow);
+    cv::Point3i getVoxelCoordinates(cv::Point3f);                                                           // map.cpp:55-85
+    bool isOccupied(cv::Point3f);                                                                           // map.cpp:441-444
+    int bound(int t, int ds);
+
+    // Additions over the reference
+    void integrateRays(icp::PointCloud &cloud, cv::Point3f origin, int delta_dec, int delta_inc); // whole-cloud M4
+    void syncWorld();                                                                             // device -> world
+    void clear();
+
+private:
+    icpb_map *dev_;
+    void ensure();
+    void updatePoints(const point_list_t &pts, int rule, int delta);
+};
+} // namespace map
+
+#endif

@@ -1,0 +1,93 @@
+// Exercises the drop-in headers (reference names, reference call shapes) end to end on a GPU.
+// usage: test_compat <in.bin> <out_dir>   -- driven by tests/test_gpu_compat.py, which checks every output
+// against the CPU oracle.  in.bin: int32 w, h; u16 depth_prev[h*w]; u16 depth_cur[h*w]; u8 bgr[h*w*3].
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <vector>
+
+#include "icpb200/icp.hpp"
+#include "icpb200/map.hpp"
+#include "icpb200/pointcloud.hpp"
+
+static void dump(const std::string &path, const void *p, size_t bytes)
+{
+    std::ofstream f(path, std::ios::binary);
+    f.write((const char *)p, (std::streamsize)bytes);
+}
+
+int main(int argc, char **argv)
+{
+    if (argc < 3) return 2;
+    std::ifstream in(argv[1], std::ios::binary);
+    int w = 0, h = 0;
+    in.read((char *)&w, 4); in.read((char *)&h, 4);
+    cv::Mat prev(h, w, CV_16UC1), cur(h, w, CV_16UC1), bgr(h, w, CV_8UC3);
+    in.read((char *)prev.data, (std::streamsize)w * h * 2);
+    in.read((char *)cur.data, (std::streamsize)w * h * 2);
+    in.read((char *)bgr.data, (std::streamsize)w * h * 3);
+    if (!in) return 3;
+    const std::string out = argv[2];
+    cv::viz::Viz3d win;
+
+    // P1: constructors consume libc rand() like the reference (pointcloud.cpp:125)
+    srand(1);
+    icp::PointCloud data(cur, bgr);
+    icp::PointCloud target(prev, bgr);
+    dump(out + "/data_pts.bin", data.points.data(), data.points.size() * sizeof(color_point_t));
+    dump(out + "/target_pts.bin", target.points.data(), target.points.size() * sizeof(color_point_t));
+    float centers[6] = {data.center.x, data.center.y, data.center.z, target.center.x, target.center.y, target.center.z};
+    dump(out + "/centers.bin", centers, sizeof(centers));
+
+    // P2
+    cv::Mat R = icp::makeRotationMatrix(3.f, -2.f, 1.f);
+    dump(out + "/rotation.bin", R.data, 9 * sizeof(float));
+    data.rotate(R);
+    data.translate(cv::Point3f(5, 5, 5));
+    target.translate(cv::Point3f(5, 5, 5));
+    dump(out + "/data_moved.bin", data.points.data(), data.points.size() * sizeof(color_point_t));
+
+    // N1-N3
+    std::vector<float> errors;
+    associations_t assoc;
+    icp::findGlobalNearestNeighborAssociations(data, target, errors, assoc);
+    dump(out + "/errors.bin", errors.data(), errors.size() * sizeof(float));
+    std::vector<color_point_t> firsts, seconds;
+    for (auto &pr : assoc) { firsts.push_back(pr.first); seconds.push_back(pr.second); }
+    dump(out + "/assoc_first.bin", firsts.data(), firsts.size() * sizeof(color_point_t));
+    dump(out + "/assoc_second.bin", seconds.data(), seconds.size() * sizeof(color_point_t));
+    color_point_t nn;
+    float d0 = icp::getNearestPoint(data.points[0], nn, target);
+    cv::Point3f off = icp::calculateOffset(assoc);
+    float scal[6] = {icp::meanSquareError(errors), off.x, off.y, off.z, d0, icp::distance(data.points[0], nn)};
+    dump(out + "/scalars.bin", scal, sizeof(scal));
+
+    // M2-M4
+    map::Map m;
+    m.update(assoc, DELTA_CONFIDENCE);
+    m.update(assoc, DELTA_CONFIDENCE);
+    m.integrateRays(data, cv::Point3f(5, 5, 5), DELTA_CONFIDENCE, DELTA_CONFIDENCE);
+    m.syncWorld();
+    dump(out + "/world.bin", m.world, (size_t)MAP_HEIGHT * MAP_HEIGHT * MAP_HEIGHT);
+    cv::Point3i v = m.getVoxelCoordinates(data.points[0].point);
+    int vox[4] = {v.x, v.y, v.z, m.isOccupied(data.points[0].point) ? 1 : 0};
+    dump(out + "/voxel.bin", vox, sizeof(vox));
+
+    // getTransformation twice (first call initialises the globals, icp.cpp:47-68)
+    srand(7);
+    cv::Mat rot;
+    std::vector<cv::KeyPoint> kps;
+    for (int i = 0; i < 50; ++i) { cv::KeyPoint k; k.pt = cv::Point2f((float)(20 + (i * 37) % (w - 40)), (float)(20 + (i * 53) % (h - 40))); kps.push_back(k); }
+    cv::Mat T1 = icp::getTransformation(cur, prev, bgr, kps, rot, 3, 0.f, win);
+    cv::Mat T2 = icp::getTransformation(prev, cur, bgr, kps, rot, 3, 0.f, win);
+    dump(out + "/T1.bin", T1.data, 16 * sizeof(float));
+    dump(out + "/T2.bin", T2.data, 16 * sizeof(float));
+    cv::Mat cr = icp::cameraRotationState();
+    cv::Point3f cp = icp::cameraPositionState();
+    float pose[12] = {0};
+    for (int k = 0; k < 9; ++k) pose[k] = cr.at<float>(k / 3, k % 3);
+    pose[9] = cp.x; pose[10] = cp.y; pose[11] = cp.z;
+    dump(out + "/pose.bin", pose, sizeof(pose));
+    printf("\ncompat ok: n_data=%zu n_target=%zu assoc=%zu\n", data.points.size(), target.points.size(), assoc.size());
+    return 0;
+}
