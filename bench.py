@@ -32,6 +32,8 @@ UNIT = "registrations/s"
 ITERS = 20
 FLOP_PER_PAIR = 8  # 3 sub + 3 mul + 2 add, icp.cpp:607-611
 
+EXTRA_WORKLOADS = ("batch10k", "map1cm", "trajectory")
+
 WORKLOADS = {
     "fullres": dict(name="configs[1]: full-resolution Kinect v1 640x480 frame-pair ICP, 20 iterations", points=None),
     "10k": dict(name="configs[0]: Kinect v1 frame pair subsampled to 10k points, 20 iterations", points=10000),
@@ -318,7 +320,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="fullres", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="fullres", choices=sorted(WORKLOADS) + list(EXTRA_WORKLOADS))
+    ap.add_argument("--frames", type=int, default=0, help="frames for the map1cm / trajectory workloads")
+    ap.add_argument("--batch", type=int, default=1024, help="registrations for the batch10k workload (whole job)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank, world, local = dist_setup(args.gpus)
@@ -327,7 +331,11 @@ def main():
     else:
         if args.warmup < 3:
             args.warmup = 3  # timing rule: at least 3 warm-up steps
-        run_b200(args, rank, world, local)
+        if args.workload in EXTRA_WORKLOADS:
+            import bench_extra
+            getattr(bench_extra, "run_" + args.workload)(args, rank, world, local)
+        else:
+            run_b200(args, rank, world, local)
 
 
 if __name__ == "__main__":

@@ -561,6 +561,17 @@ int icpb_cloud_upload_device(icpb_cloud *cloud, const void *device_points, int n
 
 const void *icpb_cloud_device_ptr(const icpb_cloud *cloud) { return cloud ? cloud->d_pts : nullptr; }
 
+int icpb_cloud_download_device(icpb_cloud *cloud, void *device_dst, int capacity)
+{
+    if (!cloud || (!device_dst && cloud->n > 0)) return ICPB_ERR_INVALID;
+    icpb_ctx *ctx = cloud->ctx;
+    if (capacity < cloud->n) return fail(ctx, ICPB_ERR_CAPACITY, "icpb_cloud_download_device: capacity < size");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (cloud->n)
+        CU(ctx, cudaMemcpyAsync(device_dst, cloud->d_pts, sizeof(float4) * (size_t)cloud->n, cudaMemcpyDeviceToDevice, ctx->stream));
+    return ICPB_OK;
+}
+
 void icpb_intrinsics_reference_v1(icpb_intrinsics *K)
 {
     if (!K) return;

@@ -255,6 +255,9 @@ class Cloud:
     def upload_device(self, ptr, n):
         self.ctx.check(self.ctx.lib.icpb_cloud_upload_device(self.h, C.c_void_p(ptr), int(n)))
 
+    def download_device(self, ptr, capacity):
+        self.ctx.check(self.ctx.lib.icpb_cloud_download_device(self.h, C.c_void_p(ptr), int(capacity)))
+
     def device_ptr(self):
         return self.ctx.lib.icpb_cloud_device_ptr(self.h)
 

@@ -1,0 +1,108 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed for the collectives.
+
+Only two things shard: (1) batches of independent registrations - contiguous blocks of the batch per rank,
+no data-path collective, results gathered at the end; (2) the voxel map - disjoint z-slabs per rank, one
+all-gather of the frame's lifted points per frame so that every slab owner walks every ray.
+
+The functions take torch tensors on whatever device the process group's backend serves (cuda for nccl,
+cpu for gloo), so the same host logic is covered by world-size-2 gloo tests without a GPU."""
+import numpy as np
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous block [lo, hi) of n_items owned by `rank` (sizes differ by at most one)."""
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def slab_bounds(dim_z, rank, world):
+    """z-slab [z_lo, z_hi) of a map with dim_z layers owned by `rank`."""
+    return shard_range(dim_z, rank, world)
+
+
+def row_band(height, rank, world):
+    """Image rows [r0, r1) a rank back-projects before the exchange."""
+    return shard_range(height, rank, world)
+
+
+def mask_rows(depth, r0, r1):
+    """The rank's share of a depth frame: rows outside [r0, r1) zeroed.  Zero pixels produce no points
+    (pointcloud.cpp:22), so lifting the masked full frame yields exactly the band's points, in raster order."""
+    out = np.zeros_like(depth)
+    out[r0:r1] = depth[r0:r1]
+    return out
+
+
+def all_gather_points(local, group=None):
+    """local: [n_local, 4] float32 tensor (16-byte points).  Returns [N, 4]: all ranks' points concatenated in
+    rank order - raster order when ranks hold consecutive row bands."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    n_local = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+    counts = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(counts, n_local, group=group)
+    counts = [int(c.item()) for c in counts]
+    cap = max(max(counts), 1)
+    padded = torch.zeros((cap, 4), dtype=torch.float32, device=local.device)
+    padded[: local.shape[0]] = local
+    gathered = torch.empty((world * cap, 4), dtype=torch.float32, device=local.device)
+    dist.all_gather_into_tensor(gathered, padded, group=group)
+    parts = [gathered[r * cap: r * cap + counts[r]] for r in range(world)]
+    return torch.cat(parts, dim=0), counts
+
+
+def gather_results(rows, group=None):
+    """rows: [n_local, k] float64 tensor of per-registration results; returns all rows in rank order."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    n_local = torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)
+    counts = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(counts, n_local, group=group)
+    counts = [int(c.item()) for c in counts]
+    cap = max(max(counts), 1)
+    padded = torch.zeros((cap, rows.shape[1]), dtype=rows.dtype, device=rows.device)
+    padded[: rows.shape[0]] = rows
+    out = torch.empty((world * cap, rows.shape[1]), dtype=rows.dtype, device=rows.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return torch.cat([out[r * cap: r * cap + counts[r]] for r in range(world)], dim=0)
+
+
+class SlabMap:
+    """The certainty map of BASELINE config 5: rank g owns z in slab_bounds(Z, g, G) of a dims/cell grid.
+    integrate(depth, pose) lifts this rank's row band on its GPU, all-gathers the points over NCCL and walks
+    every ray into the local slab (icpb_map_integrate_rays clips writes to [z_lo, z_hi))."""
+
+    def __init__(self, ctx, dims, cell, rank, world, capacity):
+        self.ctx, self.dims, self.cell, self.rank, self.world = ctx, tuple(dims), cell, rank, world
+        self.z_lo, self.z_hi = slab_bounds(dims[2], rank, world)
+        self.map = ctx.map(dims, cell, self.z_lo, self.z_hi)
+        self.local = ctx.cloud(capacity)
+        self.full = ctx.cloud(capacity)
+
+    def integrate(self, depth, K, R_wc, t_wc, delta_dec=25, delta_inc=25, count_visits=False):
+        import torch
+        h, w = depth.shape
+        r0, r1 = row_band(h, self.rank, self.world)
+        self.local.from_depth(mask_rows(depth, r0, r1), None, K)
+        self.local.transform(np.asarray(R_wc, np.float32), np.asarray(t_wc, np.float32))
+        n = self.local.n
+        dev = torch.device("cuda", self.ctx.device)
+        mine = torch.empty((max(n, 1), 4), dtype=torch.float32, device=dev)
+        self.local.download_device(mine.data_ptr(), max(n, 1))
+        self.ctx.sync()
+        if self.world > 1:
+            allp, _ = all_gather_points(mine[:n])
+            torch.cuda.current_stream().synchronize()
+        else:
+            allp = mine[:n]
+        allp = allp.contiguous()
+        self.full.upload_device(allp.data_ptr(), allp.shape[0])
+        v = self.map.integrate_rays(self.full, tuple(float(x) for x in t_wc), delta_dec, delta_inc, count_visits)
+        self.ctx.sync()
+        return allp.shape[0], v
+
+    def download(self):
+        return self.map.download()

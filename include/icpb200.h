@@ -133,6 +133,8 @@ int icpb_cloud_copy(icpb_cloud *dst, const icpb_cloud *src);
 /* Adopt n points already in device memory (16 B each), e.g. after an all-gather. */
 int icpb_cloud_upload_device(icpb_cloud *cloud, const void *device_points, int n);
 const void *icpb_cloud_device_ptr(const icpb_cloud *cloud);
+/* Copy the cloud's points into caller-owned DEVICE memory (e.g. a torch tensor feeding an all-gather). */
+int icpb_cloud_download_device(icpb_cloud *cloud, void *device_dst, int capacity);
 /* PointCloud(cv::Mat& data, cv::Mat colorMat), pointcloud.cpp:109-165 (and :11-58):
  * host depth (u16, h*w) and optional BGR (u8, h*w*3). */
 int icpb_cloud_from_depth(icpb_cloud *cloud, const uint16_t *depth, const uint8_t *bgr, int w, int h,
