@@ -295,7 +295,10 @@ def run_b200(args, rank, world, local):
                       "nn_partial_share_of_step": nn_ms / total_ms if world == 1 else None,
                       "fp32_peak_nominal_tflops": nominal, "fp32_peak_ffma_microbench_tflops": fp32_tf},
             "roofline": {"bound": "fp32", "kernel": "nn_partial_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one nn_partial launch at this workload, from the
+                         # ncu --set full capture summarised in profiles/r01_ncu_nn_partial_fullres.txt (targets stay in L2)
+                         "traffic": 8211200 if not wl["points"] else None,
                          "peak_source": "FFMA micro-benchmark measured in this run (MEASURED_PEAKS.json holds "
                                         "only HBM and bf16 tensor peaks; the NN scan is FP32 CUDA-core bound)",
                          "flop_per_launch": flop_per_launch, "avg_launch_ms": avg_launch_s * 1e3,
