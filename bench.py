@@ -237,6 +237,21 @@ def run_b200(args, rank, world, local):
     total_ms = float(np.sum(step_ms))
     assert res["iterations"] == ITERS and res["nn_passes"] == ITERS + 1
 
+    # ---- the same registration through the exact cell-grid search (ICPB_NN_GRID): identical associations and pose
+    grid_ms = []
+    res_g = None
+    for s in range(args.warmup + args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        ctx.timer_start()
+        work.copy_from(pristine)
+        res_g, _, _ = ctx.icp_register(work, target, ITERS, 0.0, 0.75, icpb200.SOLVE_REFERENCE, nn_mode=icpb200.NN_GRID)
+        ms = ctx.timer_stop()
+        if s >= args.warmup:
+            grid_ms.append(ms)
+    grid_same_pose = bool(np.array_equal(res_g["pose_R"], res["pose_R"]) and np.array_equal(res_g["pose_t"], res["pose_t"])
+                          and res_g["n_assoc"] == res["n_assoc"])
+
     # ---- e2e: host frames -> C-ABI -> pose on the host, copies inside the timed region
     e2e_ms = []
     c_prev, c_cur = ctx.cloud(w * h), ctx.cloud(w * h)
@@ -293,7 +308,12 @@ def run_b200(args, rank, world, local):
             "extra": {"nn_correspondences_per_s": world * n * (ITERS + 1) / (ms_per_step * 1e-3),
                       "nn_pairs_per_s": world * float(n) * m * (ITERS + 1) / (ms_per_step * 1e-3),
                       "nn_partial_share_of_step": nn_ms / total_ms if world == 1 else None,
-                      "fp32_peak_nominal_tflops": nominal, "fp32_peak_ffma_microbench_tflops": fp32_tf},
+                      "fp32_peak_nominal_tflops": nominal, "fp32_peak_ffma_microbench_tflops": fp32_tf,
+                      "exact_grid_mode": {"note": "same registration with nn_mode=ICPB_NN_GRID (exact cell-grid search, "
+                                                  "bit-identical associations and pose); this rank only",
+                                          "ms_per_step": float(np.mean(grid_ms)),
+                                          "registrations_per_s": 1000.0 / float(np.mean(grid_ms)),
+                                          "cell_m": res_g["grid_cell_used"], "pose_identical_to_brute_force": grid_same_pose}},
             "roofline": {"bound": "fp32", "kernel": "nn_partial_kernel", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one nn_partial launch at this workload, from the

@@ -17,7 +17,7 @@ thread_local std::string g_create_error;
 enum WsId {
     WS_DESCS = 0, WS_STATES, WS_PARAMS, WS_TGT_SOA, WS_PM1, WS_PM2, WS_PG, WS_IDX, WS_DIST, WS_CHUNKS, WS_ALT,
     WS_IDX_TRACE, WS_DIST_TRACE, WS_MISC, WS_DEPTH, WS_BGR, WS_KEEP, WS_TILESTATE, WS_IMG_A, WS_IMG_B, WS_NORMALS,
-    WS_RT, WS_COUNT
+    WS_RT, WS_GRID_META, WS_GRID_COUNTS, WS_GRID_CURSOR, WS_GRID_SUMS, WS_GRID_SORTED, WS_GRID_BBOX, WS_GRID_HEAVY, WS_COUNT
 };
 
 int fail(icpb_ctx *ctx, int status, const char *what, cudaError_t ce = cudaSuccess)
@@ -164,6 +164,73 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         CU(ctx, cudaMemsetAsync(d_dist_trace, 0, (size_t)passes * max_n * sizeof(float), ctx->stream));
     }
 
+    // ---- ICPB_NN_GRID: bucket the (fixed) target once per registration
+    bool grid_mode = (prm->nn_mode == ICPB_NN_GRID) && count == 1;
+    if (prm->nn_mode == ICPB_NN_AUTO && count == 1)
+        grid_mode = (double)regs[0].data->n * (double)regs[0].target->n >= 2.0e9; // ~45k x 45k: measured crossover region
+    GridMeta gm;
+    memset(&gm, 0, sizeof(gm));
+    GridMeta *d_gmeta = nullptr;
+    int *d_gcounts = nullptr, *d_gcursor = nullptr, *d_gsums = nullptr;
+    float4 *d_gsorted = nullptr;
+    int *d_gheavy = nullptr;
+    long long grid_launches = 0;
+    if (grid_mode) {
+        const int m = regs[0].target->n;
+        unsigned int *d_bbox;
+        if ((rc = ws_get(ctx, WS_GRID_BBOX, 64, (void **)&d_bbox))) return rc;
+        void *hpb;
+        if ((rc = pinned_get(ctx, 64, &hpb))) return rc;
+        unsigned int *hb = (unsigned int *)hpb;
+        for (int k = 0; k < 3; ++k) { hb[k] = 0xffffffffu; hb[3 + k] = 0u; }
+        CU(ctx, cudaMemcpyAsync(d_bbox, hb, 24, cudaMemcpyHostToDevice, ctx->stream));
+        launch_grid_bbox(regs[0].target->d_pts, m, d_bbox, ctx->stream);
+        CU(ctx, cudaMemcpyAsync(hb, d_bbox, 24, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        float lo[3], hi[3];
+        for (int k = 0; k < 6; ++k) {
+            unsigned int u = hb[k];
+            u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u; // inverse of the ordered-uint map
+            float f;
+            memcpy(&f, &u, 4);
+            (k < 3 ? lo[k] : hi[k - 3]) = f;
+        }
+        // default cell: ~32 points per occupied cell (at most 0.2 m), taking a third of the bounding box's surface as the area
+        // the (surface-sampled) cloud covers; sweeps on full-resolution and 10k-point Kinect clouds sit near this
+        float h = prm->grid_cell;
+        if (!(h > 0.f)) {
+            const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+            const float area = 2.f * (ex * ey + ey * ez + ez * ex) / 3.f;
+            h = sqrtf(32.f * std::max(area, 1e-6f) / (float)m);
+            h = std::min(std::max(h, 0.01f), 0.2f);
+        }
+        for (;;) {
+            double cells = 1.0;
+            for (int k = 0; k < 3; ++k) {
+                gm.dim[k] = std::max(1, (int)floorf((hi[k] - lo[k]) / h) + 1);
+                cells *= gm.dim[k];
+            }
+            if (cells <= 48.0e6) break;
+            h *= 1.26f; // coarser cells until the table fits (~192 MB of int counters at most)
+        }
+        for (int k = 0; k < 3; ++k) gm.mn[k] = lo[k];
+        gm.h = h;
+        gm.ncells = gm.dim[0] * gm.dim[1] * gm.dim[2];
+        gm.max_nn = prm->max_nn_distance;
+        gm.max_r = (int)ceilf(prm->max_nn_distance / h) + 2;
+        // per-thread shells out to ~ICPB_GRID_LIGHT_CM (default 45 cm): typical ICP residuals resolve there;
+        // the few queries still open (no overlap, far from the target) are finished by one warp each
+        gm.light_r = std::max(2, (int)ceilf(0.01f * env_int("ICPB_GRID_LIGHT_CM", 45) / h));
+        const size_t cbytes = sizeof(int) * ((size_t)gm.ncells + 1);
+        if ((rc = ws_get(ctx, WS_GRID_META, sizeof(GridMeta), (void **)&d_gmeta))) return rc;
+        if ((rc = ws_get(ctx, WS_GRID_COUNTS, cbytes, (void **)&d_gcounts))) return rc;
+        if ((rc = ws_get(ctx, WS_GRID_CURSOR, cbytes, (void **)&d_gcursor))) return rc;
+        if ((rc = ws_get(ctx, WS_GRID_SUMS, sizeof(int) * ((size_t)gm.ncells / 4096 + 8), (void **)&d_gsums))) return rc;
+        if ((rc = ws_get(ctx, WS_GRID_SORTED, sizeof(float4) * (size_t)m, (void **)&d_gsorted))) return rc;
+        if ((rc = ws_get(ctx, WS_GRID_HEAVY, sizeof(int) * ((size_t)regs[0].data->n + passes + 8), (void **)&d_gheavy))) return rc;
+        grid_launches = 7;
+    }
+
     // host staging: descs | states | params in one pinned block
     const size_t hb = sizeof(RegDesc) * count + sizeof(IcpState) * count + sizeof(IcpParamsDev);
     void *hp;
@@ -192,6 +259,11 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         d.st = d_states + b;
         d.idx_trace = d_idx_trace;
         d.dist_trace = d_dist_trace;
+        d.grid = d_gmeta;
+        d.gsorted = d_gsorted;
+        d.gstart = d_gcounts;
+        d.gheavy = d_gheavy ? d_gheavy + passes + 8 : nullptr;
+        d.gheavy_count = d_gheavy;
         IcpState &s = h_states[b];
         memset(&s, 0, sizeof(s));
         const float I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -213,9 +285,17 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
 
     long long launches = 0;
     CU(ctx, cudaEventRecord(ctx->ev0, st));
-    for (int b = 0; b < count; ++b) {
-        launch_target_prep(h_descs[b].tgt, h_descs[b].m, const_cast<float *>(h_descs[b].tgt_soa), h_descs[b].ngroups, st);
-        ++launches;
+    if (grid_mode) {
+        CU(ctx, cudaMemcpyAsync(d_gmeta, &gm, sizeof(gm), cudaMemcpyHostToDevice, st));
+        CU(ctx, cudaMemsetAsync(d_gcounts, 0, sizeof(int) * ((size_t)gm.ncells + 1), st));
+        CU(ctx, cudaMemsetAsync(d_gheavy, 0, sizeof(int) * ((size_t)passes + 8), st));
+        launch_grid_build(h_descs[0].tgt, h_descs[0].m, gm, d_gcounts, d_gcursor, d_gsums, d_gsorted, st);
+        launches += grid_launches;
+    } else {
+        for (int b = 0; b < count; ++b) {
+            launch_target_prep(h_descs[b].tgt, h_descs[b].m, const_cast<float *>(h_descs[b].tgt_soa), h_descs[b].ngroups, st);
+            ++launches;
+        }
     }
     const bool prof = ctx->profiling;
     if (prof) {
@@ -227,10 +307,11 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
     }
     for (int pass = 0; pass < passes; ++pass) {
         if (prof) CU(ctx, cudaEventRecord(ctx->prof_events[2 * pass], st));
-        launch_nn_partial(d_descs, count, max_n, qpt, splits, pass, st);
+        if (grid_mode) launch_nn_grid(d_descs, count, max_n, pass, ctx->sm_count, st);
+        else launch_nn_partial(d_descs, count, max_n, qpt, splits, pass, st);
         if (prof) CU(ctx, cudaEventRecord(ctx->prof_events[2 * pass + 1], st));
-        launch_nn_finalize(d_descs, d_prm, count, max_n, splits, pass, st);
-        launches += 2;
+        launch_nn_finalize(d_descs, d_prm, count, max_n, grid_mode ? 0 : splits, pass, st);
+        launches += grid_mode ? 3 : 2;
     }
     launch_pending_translate(d_descs, count, max_n, st);
     ++launches;
@@ -286,6 +367,8 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
             r.nn_partial_launches = nn_launches;
             r.nn_qpt = qpt;
             r.nn_splits = splits;
+            r.nn_mode_used = grid_mode ? ICPB_NN_GRID : ICPB_NN_BRUTE;
+            r.grid_cell_used = grid_mode ? gm.h : 0.f;
         }
     }
     if (trace) {

@@ -1,0 +1,373 @@
+// Exact nearest-neighbour search over a uniform cell grid of the target cloud (ICPB_NN_GRID).
+//
+// The reference's intended fix for the N x M cost is its voxel-indexed search
+// (findMappedNearestNeighborAssociations / getNearestMappedPoint / processVoxel, icp.cpp:347-486), which is
+// dead and reads out of bounds there.  An exact indexed search must return what the brute-force scan of
+// icp.cpp:541-620 returns; this one does, for every query whose nearest neighbour is closer than
+// MAX_NN_COLOR_DISTANCE (the only ones the registration consumes, icp.cpp:553):
+//   * targets are bucketed into cubic cells (counting sort, x fastest, so a row of cells is one contiguous run);
+//   * a query visits cells in growing Chebyshev shells around its own cell; a candidate is evaluated in the
+//     reference's exact arithmetic whenever the FP32 filter cannot rule it out (same bound as nn.cu);
+//   * the best (distance, original index) pair is final once it is strictly below a lower bound on the
+//     distance to everything outside the visited cube -- nothing out there can win or tie;
+//   * a query with nothing closer than the acceptance radius reports idx -1 / dist +inf (it is rejected by
+//     icp.cpp:553 whatever its true neighbour is).
+#include <math_constants.h>
+
+#include "icpb_internal.h"
+
+namespace icpb {
+
+__device__ __forceinline__ unsigned int f2ord(float f)
+{
+    unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// bbox[0..2] = ordered-uint min, bbox[3..5] = ordered-uint max (initialised by the host to ~0u / 0u)
+__global__ void grid_bbox_kernel(const float4 *__restrict__ pts, int m, unsigned int *bbox)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
+    for (; i < m; i += gridDim.x * blockDim.x) {
+        float4 p = pts[i];
+        unsigned int v[3] = {f2ord(p.x), f2ord(p.y), f2ord(p.z)};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { lo[k] = min(lo[k], v[k]); hi[k] = max(hi[k], v[k]); }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            lo[k] = min(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], off));
+            hi[k] = max(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], off));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { atomicMin(&bbox[k], lo[k]); atomicMax(&bbox[3 + k], hi[k]); }
+    }
+}
+
+__device__ __forceinline__ int cell_axis(float p, float mn, float h, int n)
+{
+    int c = (int)floorf((p - mn) / h);
+    return min(max(c, 0), n - 1);
+}
+
+__device__ __forceinline__ int cell_of(const GridMeta &g, float x, float y, float z)
+{
+    int cx = cell_axis(x, g.mn[0], g.h, g.dim[0]);
+    int cy = cell_axis(y, g.mn[1], g.h, g.dim[1]);
+    int cz = cell_axis(z, g.mn[2], g.h, g.dim[2]);
+    return (cz * g.dim[1] + cy) * g.dim[0] + cx; // x fastest
+}
+
+__global__ void grid_count_kernel(const float4 *__restrict__ pts, int m, GridMeta g, int *counts)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    float4 p = pts[i];
+    atomicAdd(&counts[cell_of(g, p.x, p.y, p.z)], 1);
+}
+
+__global__ void grid_scatter_kernel(const float4 *__restrict__ pts, int m, GridMeta g, int *cursor, float4 *sorted)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    float4 p = pts[i];
+    int pos = atomicAdd(&cursor[cell_of(g, p.x, p.y, p.z)], 1);
+    p.w = __int_as_float(i); // original index; order inside a cell is irrelevant (lexicographic (d, index) minimum)
+    sorted[pos] = p;
+}
+
+// ---- exclusive scan over the cell counts (three small kernels; plumbing) -------------------------------------
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ int block_scan_excl(int v, int *s_warp, int &total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        int o = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += o;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int w = s_warp[lane];
+        int winc = w;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            int o = __shfl_up_sync(0xffffffffu, winc, off);
+            if (lane >= off) winc += o;
+        }
+        s_warp[lane] = winc - w; // exclusive over warps
+        if (lane == 31) s_warp[32] = winc;
+    }
+    __syncthreads();
+    total = s_warp[32];
+    int r = s_warp[wid] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const int *in, int n, int *block_sums)
+{
+    __shared__ int s_warp[33];
+    int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    int v = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) v += (base + k < n) ? in[base + k] : 0;
+    int total;
+    block_scan_excl(v, s_warp, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_sums_kernel(int *block_sums, int nblocks)
+{
+    __shared__ int s_warp[33];
+    int carry = 0;
+    for (int b0 = 0; b0 < nblocks; b0 += kScanThreads) {
+        int i = b0 + threadIdx.x;
+        int v = (i < nblocks) ? block_sums[i] : 0;
+        int total;
+        int ex = block_scan_excl(v, s_warp, total);
+        if (i < nblocks) block_sums[i] = carry + ex;
+        carry += total;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(int *data, int n, const int *block_sums)
+{
+    __shared__ int s_warp[33];
+    int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    int x[kScanItems], v = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) { x[k] = (base + k < n) ? data[base + k] : 0; v += x[k]; }
+    int total;
+    int ex = block_scan_excl(v, s_warp, total) + block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (base + k < n) data[base + k] = ex;
+        ex += x[k];
+    }
+}
+
+void launch_grid_bbox(const float4 *tgt, int m, unsigned int *bbox, cudaStream_t s)
+{
+    int blocks = min((m + 255) / 256, 1024);
+    grid_bbox_kernel<<<blocks, 256, 0, s>>>(tgt, m, bbox);
+}
+
+// counts: ncells+1 ints, zeroed by the caller; on return counts[c] = start of cell c, counts[ncells] = m.
+void launch_grid_build(const float4 *tgt, int m, const GridMeta &g, int *counts, int *cursor, int *block_sums,
+                       float4 *sorted, cudaStream_t s)
+{
+    const int n = g.ncells + 1;
+    grid_count_kernel<<<(m + 255) / 256, 256, 0, s>>>(tgt, m, g, counts);
+    const int nblocks = (n + kScanTile - 1) / kScanTile;
+    scan_reduce_kernel<<<nblocks, kScanThreads, 0, s>>>(counts, n, block_sums);
+    scan_sums_kernel<<<1, kScanThreads, 0, s>>>(block_sums, nblocks);
+    scan_apply_kernel<<<nblocks, kScanThreads, 0, s>>>(counts, n, block_sums);
+    cudaMemcpyAsync(cursor, counts, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, s);
+    grid_scatter_kernel<<<(m + 255) / 256, 256, 0, s>>>(tgt, m, g, cursor, sorted);
+}
+
+// ---- the search ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ float exact_distance_xyz(float ax, float ay, float az, float bx, float by, float bz, float &xyz)
+{
+    // icp.cpp:606-620 (see nn.cu): float differences, double squares summed left to right, one rounding, float sqrt
+    float x = ax - bx, y = ay - by, z = az - bz;
+    double s = ((double)x * (double)x + (double)y * (double)y) + (double)z * (double)z;
+    xyz = (float)s;
+    return sqrtf(xyz);
+}
+
+// Shared pieces of the two search kernels ----------------------------------------------------------------------
+
+struct Best {
+    float d, thr;
+    int i;
+};
+
+// Visit shell r (cells at Chebyshev distance exactly r from c0).  LANES threads share the work: lane `lane`
+// takes candidates lane, lane+LANES, ... of every contiguous run.
+template <int LANES>
+__device__ __forceinline__ void visit_shell(const GridMeta &g, const float4 *__restrict__ sorted, const int *__restrict__ start,
+                                            const float4 &p, int c0x, int c0y, int c0z, int r, int lane, Best &best)
+{
+    const int nx = g.dim[0], ny = g.dim[1], nz = g.dim[2];
+    const int xlo = max(c0x - r, 0), xhi = min(c0x + r, nx - 1);
+    for (int dz = -r; dz <= r; ++dz) {
+        const int z = c0z + dz;
+        if (z < 0 || z >= nz) continue;
+        for (int dy = -r; dy <= r; ++dy) {
+            const int y = c0y + dy;
+            if (y < 0 || y >= ny) continue;
+            const int rowbase = (z * ny + y) * nx;
+            const bool edge = (dz == -r) || (dz == r) || (dy == -r) || (dy == r);
+            const int nseg = edge ? 1 : 2; // edge rows: the whole x-run; inner rows: the two end cells
+            for (int sgm = 0; sgm < nseg; ++sgm) {
+                int a, b;
+                if (edge) { a = xlo; b = xhi; }
+                else {
+                    const int x = (sgm == 0) ? c0x - r : c0x + r;
+                    if (x < 0 || x >= nx) continue;
+                    a = b = x;
+                }
+                const int t0 = __ldg(&start[rowbase + a]);
+                const int t1 = __ldg(&start[rowbase + b + 1]);
+                for (int t = t0 + lane; t < t1; t += LANES) {
+                    const float4 q = __ldg(&sorted[t]);
+                    const float ex = p.x - q.x, ey = p.y - q.y, ez = p.z - q.z;
+                    const float sf = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, ex * ex));
+                    if (sf > best.thr) continue; // provably farther than the current best (nn.cu bound)
+                    float xyz;
+                    const float dd = exact_distance_xyz(p.x, p.y, p.z, q.x, q.y, q.z, xyz);
+                    const int oi = __float_as_int(q.w);
+                    if (dd < best.d || (dd == best.d && oi < best.i)) {
+                        best.d = dd; best.i = oi;
+                        best.thr = xyz * kBandRel + kBandAbs;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Lower bound on the distance from p to anything outside the cube of radius r around its cell (+inf when the
+// cube covers the grid), minus a slack for the float rounding of the cell assignment.
+__device__ __forceinline__ float shell_lower_bound(const GridMeta &g, const float4 &p, int c0x, int c0y, int c0z, int r)
+{
+    float lb = CUDART_INF_F;
+    const float q[3] = {p.x, p.y, p.z};
+    const int c0[3] = {c0x, c0y, c0z};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int lo_c = c0[k] - r, hi_c = c0[k] + r;
+        if (lo_c > 0) lb = fminf(lb, q[k] - (g.mn[k] + lo_c * g.h));
+        if (hi_c < g.dim[k] - 1) lb = fminf(lb, (g.mn[k] + (hi_c + 1) * g.h) - q[k]);
+    }
+    return (lb == CUDART_INF_F) ? lb : lb - 1e-3f * g.h;
+}
+
+// true when the query is farther than the acceptance radius from the target's bounding box
+__device__ __forceinline__ bool beyond_reach(const GridMeta &g, const float4 &p)
+{
+    const float q[3] = {p.x, p.y, p.z};
+    float out2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float lo = g.mn[k], hi = g.mn[k] + g.dim[k] * g.h;
+        float e = fmaxf(fmaxf(lo - q[k], q[k] - hi), 0.f);
+        out2 += e * e;
+    }
+    const float reach = g.max_nn + 2.f * g.h;
+    return out2 > reach * reach;
+}
+
+
+// Phase 1: one thread per query, the first shells.  Resolved queries write (idx, dist); the others leave their
+// partial best in (idx, dist) and append themselves to the heavy list of this pass.
+__global__ void __launch_bounds__(128) nn_grid_kernel(const RegDesc *__restrict__ descs, int pass)
+{
+    const RegDesc d = descs[blockIdx.z];
+    IcpState *st = d.st;
+    if (st->done) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n) return;
+
+    // P2 fused into the query load, as in nn_partial (pointcloud.cpp:321-359)
+    float4 p = d.D[pass & 1][i];
+    if (st->apply) {
+        const float *R = st->Rf, *T = st->tf;
+        float x = ((R[0] * p.x + R[1] * p.y) + R[2] * p.z) + T[0];
+        float y = ((R[3] * p.x + R[4] * p.y) + R[5] * p.z) + T[1];
+        float z = ((R[6] * p.x + R[7] * p.y) + R[8] * p.z) + T[2];
+        p.x = x; p.y = y; p.z = z;
+    }
+    d.D[(pass + 1) & 1][i] = p;
+
+    const GridMeta g = *d.grid;
+    Best best = {CUDART_INF_F, CUDART_INF_F, 0x7fffffff};
+    bool open = false;
+    if (!beyond_reach(g, p)) {
+        const int c0x = cell_axis(p.x, g.mn[0], g.h, g.dim[0]);
+        const int c0y = cell_axis(p.y, g.mn[1], g.h, g.dim[1]);
+        const int c0z = cell_axis(p.z, g.mn[2], g.h, g.dim[2]);
+        open = true;
+        for (int r = 0; r <= g.light_r && r <= g.max_r; ++r) {
+            visit_shell<1>(g, d.gsorted, d.gstart, p, c0x, c0y, c0z, r, 0, best);
+            const float lb = shell_lower_bound(g, p, c0x, c0y, c0z, r);
+            if (lb == CUDART_INF_F || best.d < lb || lb > g.max_nn || r == g.max_r) { open = false; break; }
+        }
+    }
+    if (open) {
+        const int slot = atomicAdd(&d.gheavy_count[pass], 1);
+        d.gheavy[slot] = i;
+    } else if (!(best.d < g.max_nn)) {
+        best.i = -1; best.d = CUDART_INF_F;
+    }
+    d.idx[i] = best.i;
+    d.dist[i] = best.d;
+}
+
+// Phase 2: one warp per heavy query, continuing from shell light_r+1 with the candidates of every run split
+// over the 32 lanes; the warp's lexicographic (distance, index) minimum is exchanged after every shell.
+__global__ void __launch_bounds__(128) nn_grid_heavy_kernel(const RegDesc *__restrict__ descs, int pass)
+{
+    const RegDesc d = descs[blockIdx.z];
+    IcpState *st = d.st;
+    if (st->done) return;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int count = d.gheavy_count[pass];
+    const GridMeta g = *d.grid;
+    for (int e = warp; e < count; e += nwarps) {
+        const int i = d.gheavy[e];
+        const float4 p = d.D[(pass + 1) & 1][i];
+        const int c0x = cell_axis(p.x, g.mn[0], g.h, g.dim[0]);
+        const int c0y = cell_axis(p.y, g.mn[1], g.h, g.dim[1]);
+        const int c0z = cell_axis(p.z, g.mn[2], g.h, g.dim[2]);
+        Best best;
+        best.d = d.dist[i]; best.i = d.idx[i];
+        {
+            // rebuild the filter threshold of the partial best: thr bounds s-tilde, and xyz <= d^2 (1 + 2^-22)
+            const float dd = best.d;
+            best.thr = (dd == CUDART_INF_F) ? CUDART_INF_F : (dd * dd) * (kBandRel + 4.8e-7f) + kBandAbs;
+        }
+        for (int r = g.light_r + 1; r <= g.max_r; ++r) {
+            visit_shell<32>(g, d.gsorted, d.gstart, p, c0x, c0y, c0z, r, lane, best);
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, best.d, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, best.i, off);
+                const float ot = __shfl_xor_sync(0xffffffffu, best.thr, off);
+                if (od < best.d || (od == best.d && oi < best.i)) { best.d = od; best.i = oi; best.thr = ot; }
+            }
+            const float lb = shell_lower_bound(g, p, c0x, c0y, c0z, r);
+            if (lb == CUDART_INF_F || best.d < lb || lb > g.max_nn) break;
+        }
+        if (lane == 0) {
+            if (!(best.d < g.max_nn)) { best.i = -1; best.d = CUDART_INF_F; }
+            d.idx[i] = best.i;
+            d.dist[i] = best.d;
+        }
+    }
+}
+
+void launch_nn_grid(const RegDesc *descs, int batch, int max_n, int pass, int sm_count, cudaStream_t s)
+{
+    dim3 grid((max_n + 127) / 128, 1, batch);
+    nn_grid_kernel<<<grid, 128, 0, s>>>(descs, pass);
+    dim3 hgrid(sm_count * 8, 1, batch);
+    nn_grid_heavy_kernel<<<hgrid, 128, 0, s>>>(descs, pass);
+}
+
+} // namespace icpb

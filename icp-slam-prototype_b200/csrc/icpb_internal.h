@@ -66,6 +66,17 @@ struct IcpParamsDev {
     float last_translation[3];
 };
 
+// Uniform cell grid over the target cloud (ICPB_NN_GRID, grid.cu).
+struct GridMeta {
+    float mn[3];   // lower corner of the target's bounding box
+    float h;       // cell edge
+    int dim[3];    // cells per axis (x fastest in the cell index)
+    int ncells;
+    int max_r;     // shells needed to cover the acceptance radius
+    int light_r;   // shells every query walks on its own thread before it is handed to a whole warp
+    float max_nn;  // acceptance radius (MAX_NN_COLOR_DISTANCE, icp.hpp:8)
+};
+
 // One registration problem as the kernels see it (indexed by blockIdx.z).
 struct RegDesc {
     float4 *D[2];            // ping-pong data cloud buffers (16-B points)
@@ -81,6 +92,11 @@ struct RegDesc {
     IcpState *st;
     int *idx_trace;          // nullable [(max_it+1)][n]
     float *dist_trace;
+    const GridMeta *grid;    // ICPB_NN_GRID only
+    const float4 *gsorted;   // targets sorted by cell, w = original index
+    const int *gstart;       // [ncells+1] first sorted slot of every cell
+    int *gheavy;             // [n] queries still open after the per-thread shells
+    int *gheavy_count;       // [passes] length of that list per pass (zeroed once per registration)
 };
 
 // ---- launchers (defined in the .cu files) ---------------------------------
@@ -95,6 +111,10 @@ void launch_pending_translate(const RegDesc *descs, int batch, int max_n, cudaSt
 void launch_center(const float4 *pts, int n, double *chunk_sums, double *out3, unsigned int *counter,
                    cudaStream_t s);
 void launch_fp32_peak(float *out, int blocks, int threads, int iters, cudaStream_t s);
+void launch_grid_bbox(const float4 *tgt, int m, unsigned int *bbox, cudaStream_t s);
+void launch_grid_build(const float4 *tgt, int m, const GridMeta &g, int *counts, int *cursor, int *block_sums,
+                       float4 *sorted, cudaStream_t s);
+void launch_nn_grid(const RegDesc *descs, int batch, int max_n, int pass, int sm_count, cudaStream_t s);
 
 struct BackprojectArgs {
     const uint16_t *depth;

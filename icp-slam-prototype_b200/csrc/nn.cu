@@ -598,88 +598,95 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
     s_pts[tid] = a;
     __syncthreads();
 
-    // ---- combine the per-split (best, second-best, group) records, ascending split order
-    float m1 = CUDART_INF_F, m2 = CUDART_INF_F;
-    int g = 0;
-    if (valid) {
-        // loads first (independent, batched), then the order-dependent combine on registers
-        constexpr int kB = 8;
-        for (int s0 = 0; s0 < splits; s0 += kB) {
-            float p1[kB], p2[kB];
-            int pgv[kB];
-#pragma unroll
-            for (int k = 0; k < kB; ++k) {
-                const int s = min(s0 + k, splits - 1);
-                const size_t o = (size_t)s * d.n_stride + i;
-                p1[k] = __ldcg(&d.pm1[o]); p2[k] = __ldcg(&d.pm2[o]); pgv[k] = __ldcg(&d.pg[o]);
-            }
-#pragma unroll
-            for (int k = 0; k < kB; ++k) {
-                if (s0 + k < splits) {
-                    m2 = fminf(fminf(m2, p2[k]), fmaxf(m1, p1[k]));
-                    if (p1[k] < m1) { m1 = p1[k]; g = pgv[k]; }
+    int best_i = 0;
+    float best_d = 0.f;
+    int n_amb = 0;
+    if (splits == 0) {
+        // ICPB_NN_GRID: nn_grid_kernel already resolved (idx, dist) exactly
+        if (valid) { best_i = d.idx[i]; best_d = d.dist[i]; }
+    } else {
+        // ---- combine the per-split (best, second-best, group) records, ascending split order
+        float m1 = CUDART_INF_F, m2 = CUDART_INF_F;
+        int g = 0;
+        if (valid) {
+            // loads first (independent, batched), then the order-dependent combine on registers
+            constexpr int kB = 8;
+            for (int s0 = 0; s0 < splits; s0 += kB) {
+                float p1[kB], p2[kB];
+                int pgv[kB];
+    #pragma unroll
+                for (int k = 0; k < kB; ++k) {
+                    const int s = min(s0 + k, splits - 1);
+                    const size_t o = (size_t)s * d.n_stride + i;
+                    p1[k] = __ldcg(&d.pm1[o]); p2[k] = __ldcg(&d.pm2[o]); pgv[k] = __ldcg(&d.pg[o]);
+                }
+    #pragma unroll
+                for (int k = 0; k < kB; ++k) {
+                    if (s0 + k < splits) {
+                        m2 = fminf(fminf(m2, p2[k]), fmaxf(m1, p1[k]));
+                        if (p1[k] < m1) { m1 = p1[k]; g = pgv[k]; }
+                    }
                 }
             }
         }
-    }
-    int best_i = 0;
-    float best_d = 0.f;
-    bool ambiguous = valid && !(m2 > m1 * kBandRel + kBandAbs);
-    if (valid && !ambiguous) {
-        // exact re-evaluation of the winning group (reference arithmetic, ascending index, strict <)
-        const int t0 = g * kGroup;
-        float4 b = d.tgt[t0];
-        best_d = exact_distance(a.x, a.y, a.z, b.x, b.y, b.z);
-        best_i = t0;
-#pragma unroll 8
-        for (int k = 1; k < kGroup; ++k) {
-            const int t = t0 + k;
-            b = d.tgt[min(t, m - 1)];
-            float dd = exact_distance(a.x, a.y, a.z, b.x, b.y, b.z);
-            if (t < m && dd < best_d) { best_d = dd; best_i = t; }
+        bool ambiguous = valid && !(m2 > m1 * kBandRel + kBandAbs);
+        if (valid && !ambiguous) {
+            // exact re-evaluation of the winning group (reference arithmetic, ascending index, strict <)
+            const int t0 = g * kGroup;
+            float4 b = d.tgt[t0];
+            best_d = exact_distance(a.x, a.y, a.z, b.x, b.y, b.z);
+            best_i = t0;
+    #pragma unroll 8
+            for (int k = 1; k < kGroup; ++k) {
+                const int t = t0 + k;
+                b = d.tgt[min(t, m - 1)];
+                float dd = exact_distance(a.x, a.y, a.z, b.x, b.y, b.z);
+                if (t < m && dd < best_d) { best_d = dd; best_i = t; }
+            }
         }
-    }
-    if (ambiguous) {
-        int slot = atomicAdd(&s_cnt, 1);
-        s_list[slot] = tid;
-    }
-    __syncthreads();
-
-    // ---- near-tie queries: CTA-cooperative full scan in exact arithmetic
-    const int n_amb = s_cnt;
-    for (int e = 0; e < n_amb; ++e) {
-        const int owner = s_list[e];
-        const float4 q = s_pts[owner];
-        float bd = CUDART_INF_F;
-        int bi = 0x7fffffff;
-        for (int t = tid; t < m; t += kChunk) {
-            float4 b = d.tgt[t];
-            float dd = exact_distance(q.x, q.y, q.z, b.x, b.y, b.z);
-            if (dd < bd) { bd = dd; bi = t; }
+        if (ambiguous) {
+            int slot = atomicAdd(&s_cnt, 1);
+            s_list[slot] = tid;
         }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            float od = __shfl_xor_sync(0xffffffffu, bd, off);
-            int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
-        }
-        if ((tid & 31) == 0) { s_rd[tid >> 5] = bd; s_ri[tid >> 5] = bi; }
         __syncthreads();
-        if (tid == owner) {
-            bd = s_rd[0]; bi = s_ri[0];
-            for (int wv = 1; wv < kChunk / 32; ++wv) {
-                float od = s_rd[wv];
-                int oi = s_ri[wv];
+
+        // ---- near-tie queries: CTA-cooperative full scan in exact arithmetic
+        n_amb = s_cnt;
+        for (int e = 0; e < n_amb; ++e) {
+            const int owner = s_list[e];
+            const float4 q = s_pts[owner];
+            float bd = CUDART_INF_F;
+            int bi = 0x7fffffff;
+            for (int t = tid; t < m; t += kChunk) {
+                float4 b = d.tgt[t];
+                float dd = exact_distance(q.x, q.y, q.z, b.x, b.y, b.z);
+                if (dd < bd) { bd = dd; bi = t; }
+            }
+    #pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                float od = __shfl_xor_sync(0xffffffffu, bd, off);
+                int oi = __shfl_xor_sync(0xffffffffu, bi, off);
                 if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
             }
-            if (bi == 0x7fffffff) { // every distance was NaN: the reference keeps target[0]
-                float4 b = d.tgt[0];
-                bi = 0;
-                bd = exact_distance(q.x, q.y, q.z, b.x, b.y, b.z);
+            if ((tid & 31) == 0) { s_rd[tid >> 5] = bd; s_ri[tid >> 5] = bi; }
+            __syncthreads();
+            if (tid == owner) {
+                bd = s_rd[0]; bi = s_ri[0];
+                for (int wv = 1; wv < kChunk / 32; ++wv) {
+                    float od = s_rd[wv];
+                    int oi = s_ri[wv];
+                    if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+                }
+                if (bi == 0x7fffffff) { // every distance was NaN: the reference keeps target[0]
+                    float4 b = d.tgt[0];
+                    bi = 0;
+                    bd = exact_distance(q.x, q.y, q.z, b.x, b.y, b.z);
+                }
+                best_d = bd; best_i = bi;
             }
-            best_d = bd; best_i = bi;
+            __syncthreads();
         }
-        __syncthreads();
+
     }
 
     if (valid) {

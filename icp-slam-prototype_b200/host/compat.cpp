@@ -395,6 +395,8 @@ cv::Mat getTransformation(cv::Mat &data, cv::Mat &previous, cv::Mat color, std::
     for (int k = 0; k < 3; ++k) prm.last_translation[k] = g.lastTranslation[k];
     prm.idx_trace = nullptr;
     prm.dist_trace = nullptr;
+    prm.nn_mode = ICPB_NN_BRUTE;
+    prm.grid_cell = 0.f;
     icpb_icp_result res;
     cv::Mat rigid(4, 4, CV_32FC1);
     if (dataCloud.points.empty() || previousCloud.points.empty()) {

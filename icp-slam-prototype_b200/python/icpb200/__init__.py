@@ -23,6 +23,7 @@ OK, ERR_INVALID, ERR_EMPTY, ERR_CUDA, ERR_CAPACITY = 0, 1, 2, 3, 4
 SUB_NONE, SUB_STRIDE, SUB_HASH, SUB_STREAM = 0, 1, 2, 3
 SOLVE_REFERENCE, SOLVE_KABSCH = 0, 1
 RULE_A, RULE_C = 0, 1
+NN_BRUTE, NN_GRID, NN_AUTO = 0, 1, 2
 
 
 class IcpbError(RuntimeError):
@@ -39,7 +40,7 @@ class Intrinsics(C.Structure):
 class IcpParams(C.Structure):
     _fields_ = [("max_iterations", C.c_int), ("threshold", C.c_float), ("max_nn_distance", C.c_float),
                 ("solve_mode", C.c_int), ("last_translation", C.c_float * 3),
-                ("idx_trace", C.c_void_p), ("dist_trace", C.c_void_p)]
+                ("idx_trace", C.c_void_p), ("dist_trace", C.c_void_p), ("nn_mode", C.c_int), ("grid_cell", C.c_float)]
 
 
 class IcpResult(C.Structure):
@@ -48,7 +49,7 @@ class IcpResult(C.Structure):
                 ("offset", C.c_float * 3), ("pose_R", C.c_double * 9), ("pose_t", C.c_double * 3),
                 ("small_assoc_exit", C.c_int), ("exact_rescans", C.c_int), ("gpu_ms", C.c_float),
                 ("kernel_launches", C.c_int), ("nn_partial_ms", C.c_float), ("nn_partial_launches", C.c_int),
-                ("nn_qpt", C.c_int), ("nn_splits", C.c_int)]
+                ("nn_qpt", C.c_int), ("nn_splits", C.c_int), ("nn_mode_used", C.c_int), ("grid_cell_used", C.c_float)]
 
     def to_dict(self):
         return {
@@ -61,7 +62,8 @@ class IcpResult(C.Structure):
             "small_assoc_exit": self.small_assoc_exit, "exact_rescans": self.exact_rescans,
             "gpu_ms": self.gpu_ms, "kernel_launches": self.kernel_launches,
             "nn_partial_ms": self.nn_partial_ms, "nn_partial_launches": self.nn_partial_launches,
-            "nn_qpt": self.nn_qpt, "nn_splits": self.nn_splits,
+            "nn_qpt": self.nn_qpt, "nn_splits": self.nn_splits, "nn_mode_used": self.nn_mode_used,
+            "grid_cell_used": self.grid_cell_used,
         }
 
 
@@ -196,10 +198,11 @@ class Context:
         return idx, dist, resc.value
 
     def icp_register(self, data, target, max_iterations=20, threshold=0.0, max_nn_distance=0.75,
-                     solve_mode=SOLVE_REFERENCE, last_translation=(0, 0, 0), trace=False):
+                     solve_mode=SOLVE_REFERENCE, last_translation=(0, 0, 0), trace=False, nn_mode=NN_BRUTE,
+                     grid_cell=0.0):
         it = dt = None
         prm = IcpParams(max_iterations, threshold, max_nn_distance, solve_mode, (C.c_float * 3)(*last_translation),
-                        None, None)
+                        None, None, nn_mode, grid_cell)
         if trace:
             it = np.full((max_iterations + 1, data.n), -1, dtype=np.int32)
             dt = np.zeros((max_iterations + 1, data.n), dtype=np.float32)
@@ -212,7 +215,8 @@ class Context:
     def icp_register_batch(self, datas, targets, max_iterations=20, threshold=0.0, max_nn_distance=0.75,
                            solve_mode=SOLVE_REFERENCE):
         n = len(datas)
-        prm = IcpParams(max_iterations, threshold, max_nn_distance, solve_mode, (C.c_float * 3)(0, 0, 0), None, None)
+        prm = IcpParams(max_iterations, threshold, max_nn_distance, solve_mode, (C.c_float * 3)(0, 0, 0), None, None,
+                        NN_BRUTE, 0.0)
         dh = (C.c_void_p * n)(*[d.h for d in datas])
         th = (C.c_void_p * n)(*[t.h for t in targets])
         res = (IcpResult * n)()

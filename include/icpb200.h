@@ -63,6 +63,13 @@ enum {
 enum { ICPB_SOLVE_REFERENCE = 0, /* icp.cpp:199-246: uncentred SVD, offset = mean(a-b) */
        ICPB_SOLVE_KABSCH = 1 };  /* rigid_transform_3D.py:9-40 */
 
+/* Association scan of the registration loop.  Both return the same associations (icp.cpp:541-563):
+ * BRUTE scans all N x M pairs (icp.cpp:566-593); GRID is an exact cell-grid search (the reference's intended
+ * voxel-indexed scan, icp.cpp:347-486) that reports idx -1 / dist +inf for queries with no neighbour inside
+ * max_nn_distance - those are rejected by icp.cpp:553 in either mode. */
+enum { ICPB_NN_BRUTE = 0, ICPB_NN_GRID = 1,
+       ICPB_NN_AUTO = 2 }; /* GRID when n*m is large enough for the bucketing to pay off, else BRUTE */
+
 enum { ICPB_RULE_A = 0,  /* map.cpp:249-253 / 104-113 */
        ICPB_RULE_C = 1 };/* map.cpp:139-149 */
 
@@ -74,6 +81,8 @@ typedef struct {
     float last_translation[3]; /* icp.cpp:25, consumed by the <3 associations rule (icp.cpp:163-182) */
     int32_t *idx_trace;        /* optional host buffer (max_iterations+1)*n: nearest index per pass */
     float *dist_trace;         /* optional host buffer, same shape */
+    int nn_mode;               /* ICPB_NN_BRUTE (default 0) or ICPB_NN_GRID */
+    float grid_cell;           /* ICPB_NN_GRID: cell edge in metres (0 = chosen from the target's density) */
 } icpb_icp_params;
 
 typedef struct {
@@ -94,6 +103,8 @@ typedef struct {
     float nn_partial_ms;    /* profiling mode only: summed device time of the nn_partial launches */
     int nn_partial_launches;
     int nn_qpt, nn_splits;  /* work decomposition chosen for nn_partial */
+    int nn_mode_used;       /* ICPB_NN_BRUTE or ICPB_NN_GRID */
+    float grid_cell_used;
 } icpb_icp_result;
 
 /* ---- library / context ------------------------------------------------- */

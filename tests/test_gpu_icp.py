@@ -119,3 +119,52 @@ def test_icp_batch_matches_single(ctx, orc, pair10k):
         assert np.array_equal(datas[k].download().view(np.uint8), singles[k][1].view(np.uint8))
     for c in datas + targets:
         c.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("cell", [0.0, 0.11])
+def test_icp_grid_mode_is_exact(ctx, orc, pair10k, mode, cell):
+    """ICPB_NN_GRID (the reference's intended voxel-indexed scan, icp.cpp:347-486, made exact): every accepted
+    association, every sum, the pose and the transformed cloud are bit-identical to the brute-force oracle."""
+    import icpb200
+    data, target = pair10k
+    dc, tc = ctx.cloud_from_points(data), ctx.cloud_from_points(target)
+    res, it, dt = ctx.icp_register(dc, tc, 20, 0.0, 0.75, mode, trace=True, nn_mode=icpb200.NN_GRID, grid_cell=cell)
+    out = dc.download()
+    dc.close(); tc.close()
+    ref, rout, rit, rdt = orc.icp(data, target, 20, 0.0, 0.75, mode, n_threads=8, trace=True)
+    assert res["nn_passes"] == ref["nn_passes"] == 21
+    for k in range(21):
+        acc = rdt[k] < 0.75
+        assert np.array_equal(it[k][acc], rit[k][acc]), f"pass {k}"
+        assert np.array_equal(dt[k][acc], rdt[k][acc]), f"pass {k}"
+        assert np.all(it[k][~acc] == -1) and np.all(np.isinf(dt[k][~acc]))
+    assert res["n_assoc"] == ref["n_assoc"] and res["mse"] == ref["mse"]
+    assert np.array_equal(res["pose_R"], ref["pose_R"]) and np.array_equal(res["pose_t"], ref["pose_t"])
+    assert np.array_equal(res["rigid"], ref["rigid"])
+    assert np.array_equal(out.view(np.uint8), rout.view(np.uint8))
+
+
+def test_icp_grid_mode_partial_overlap_and_ties(ctx, orc):
+    """Grid mode with rejected queries (no neighbour inside 0.75 m), queries outside the target's bounding box,
+    duplicated targets and lattice ties."""
+    import icpb200
+    rng = np.random.default_rng(21)
+    g = np.arange(0, 12, dtype=np.float32) * 0.1 + 4.0
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    lat = np.stack([X.ravel(), Y.ravel(), Z.ravel()], 1)
+    tgt = np.concatenate([lat, lat[:300], rng.uniform(4, 5.2, (1500, 3)).astype(np.float32)])
+    dat = np.concatenate([lat[:500] + np.float32(0.05), rng.uniform(2.5, 7.5, (2000, 3)).astype(np.float32),
+                          rng.uniform(20, 30, (50, 3)).astype(np.float32)])
+    data, target = orc.make_points(dat), orc.make_points(tgt)
+    dc, tc = ctx.cloud_from_points(data), ctx.cloud_from_points(target)
+    res, it, dt = ctx.icp_register(dc, tc, 4, 0.0, 0.75, 0, trace=True, nn_mode=icpb200.NN_GRID, grid_cell=0.07)
+    out = dc.download()
+    ref, rout, rit, rdt = orc.icp(data, target, 4, 0.0, 0.75, 0, n_threads=8, trace=True)
+    for k in range(5):
+        acc = rdt[k] < 0.75
+        assert 0 < acc.sum() < len(acc)
+        assert np.array_equal(it[k][acc], rit[k][acc]) and np.array_equal(dt[k][acc], rdt[k][acc])
+    assert np.array_equal(out.view(np.uint8), rout.view(np.uint8))
+    assert np.array_equal(res["pose_R"], ref["pose_R"])
+    dc.close(); tc.close()

@@ -14,6 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--points", type=int, default=0, help="0 = full resolution")
 ap.add_argument("--iters", type=int, default=1)
 ap.add_argument("--repeat", type=int, default=1)
+ap.add_argument("--grid", type=float, default=-1.0, help="use ICPB_NN_GRID with this cell size (0 = default)")
 ap.add_argument("--map", action="store_true", help="also run back-projection + map integration")
 a = ap.parse_args()
 
@@ -31,9 +32,9 @@ if a.points:
 ctx.set_profiling(True)
 for r in range(a.repeat):
     work.copy_from(dat)
-    res, _, _ = ctx.icp_register(work, tgt, a.iters, 0.0, 0.75, 0)
+    res, _, _ = ctx.icp_register(work, tgt, a.iters, 0.0, 0.75, 0, nn_mode=1 if a.grid >= 0 else 0, grid_cell=max(a.grid, 0.0))
     print(f"n={dat.n} m={tgt.n} passes={res['nn_passes']} gpu_ms={res['gpu_ms']:.3f} "
-          f"nn_partial_ms={res['nn_partial_ms']:.3f} qpt={res['nn_qpt']} splits={res['nn_splits']} "
+          f"nn_partial_ms={res['nn_partial_ms']:.3f} qpt={res['nn_qpt']} splits={res['nn_splits']} cell={res['grid_cell_used']:.3f} "
           f"rescans={res['exact_rescans']}")
 if a.map:
     m = ctx.map((300, 300, 250), 0.02)
