@@ -77,12 +77,15 @@ void launch_map_endpoints(const MapDev &m, const float4 *pts, int n, int rule, i
     map_endpoints_kernel<<<(n + 255) / 256, 256, 0, s>>>(m, pts, n, rule, delta, max_conf);
 }
 
-// M4 phase 1: exact integer Amanatides-Woo walk from the origin voxel centre to
-// the endpoint voxel centre.  Axis k crosses its i-th wall at t = (2i+1)/(2 n_k);
-// walls are ordered by the cross-multiplied integers e_k, ties x < y < z.
-// Every voxel entered except the endpoint voxel is decremented with clamp at 0.
-__global__ void map_rays_kernel(MapDev m, const float4 *__restrict__ pts, int n, int ox, int oy, int oz,
-                                int delta_dec, unsigned long long *visited)
+// M4 phase 1: exact integer Amanatides-Woo walk from the origin voxel centre to the endpoint voxel centre.
+// Axis k crosses its i-th wall at t = (2i+1)/(2 n_k); scaled by 2 P (P = product of max(n_k,1)) the wall times
+// are the integers e_k = (2i+1) P / n_k; the smallest goes first, ties x < y < z.  An axis that has crossed all
+// its walls carries e_k = (2 n_k + 1) P / n_k > 2 P, larger than every real wall time, and an axis with n_k = 0
+// starts at 3 P: neither is ever selected, so the loop needs no per-axis counters.  Every voxel entered except
+// the endpoint voxel is decremented with clamp at 0.  I = int when 3 * dims product < 2^31, else long long.
+template <typename I>
+__global__ void __launch_bounds__(128) map_rays_kernel(MapDev m, const float4 *__restrict__ pts, int n, int ox, int oy,
+                                                      int oz, int delta_dec, unsigned long long *visited)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long my_visits = 0;
@@ -91,27 +94,65 @@ __global__ void map_rays_kernel(MapDev m, const float4 *__restrict__ pts, int n,
         const int ex_ = voxel_axis(p.x, m.cell, m.dims[0]);
         const int ey_ = voxel_axis(p.y, m.cell, m.dims[1]);
         const int ez_ = voxel_axis(p.z, m.cell, m.dims[2]);
-        const long long nx = abs(ex_ - ox), ny = abs(ey_ - oy), nz = abs(ez_ - oz);
+        const int nx = abs(ex_ - ox), ny = abs(ey_ - oy), nz = abs(ez_ - oz);
         const int sx = (ex_ > ox) - (ex_ < ox), sy = (ey_ > oy) - (ey_ < oy), sz = (ez_ > oz) - (ez_ < oz);
-        const long long mx = nx ? nx : 1, my = ny ? ny : 1, mz = nz ? nz : 1;
-        const long long INF = (long long)1 << 62;
-        long long ex = nx ? my * mz : INF, ey = ny ? mx * mz : INF, ez = nz ? mx * my : INF;
-        const long long dxs = 2 * my * mz, dys = 2 * mx * mz, dzs = 2 * mx * my;
-        const long long steps = nx + ny + nz;
-        int x = ox, y = oy, z = oz;
-        long long cx = 0, cy = 0, cz = 0;
-        const int dimY = m.dims[1];
-        for (long long s = 0; s + 1 < steps; ++s) {
-            if (ex <= ey && ex <= ez) { x += sx; ++cx; ex = (cx < nx) ? ex + dxs : INF; }
-            else if (ey <= ez) { y += sy; ++cy; ey = (cy < ny) ? ey + dys : INF; }
-            else { z += sz; ++cz; ez = (cz < nz) ? ez + dzs : INF; }
-            if (z < m.z_lo || z >= m.z_hi) continue;
-            const size_t lin = ((size_t)x * dimY + y) * m.zs + (z - m.z_lo);
-            // phase 1 only lowers values, so a cached non-zero byte is at worst stale-high: the CAS re-reads it
-            if (m.grid[lin] != 0)
-                byte_rmw(m.grid, lin, [&](uint32_t c) { return c > (uint32_t)delta_dec ? c - delta_dec : 0u; });
-        }
+        const I mx = nx ? nx : 1, my = ny ? ny : 1, mz = nz ? nz : 1;
+        const I P3 = 3 * mx * my * mz;
+        I ex = nx ? my * mz : P3, ey = ny ? mx * mz : P3, ez = nz ? mx * my : P3;
+        const I dxs = 2 * my * mz, dys = 2 * mx * mz, dzs = 2 * mx * my;
+        const int steps = nx + ny + nz;
         my_visits = steps > 0 ? (unsigned long long)(steps - 1) : 0ull;
+        int z = oz;
+        int done_steps = 0;
+        bool live = true;
+        long long lin0 = ((long long)ox * m.dims[1] + oy) * m.zs + (oz - m.z_lo);
+        // Slab clipping: z moves monotonically, so the part of the walk inside [z_lo, z_hi) is one contiguous
+        // range of steps.  If the origin is outside the slab, jump to the state right after the z-step that
+        // enters it: that is z-step number k; by then every x / y wall with time <= (2k-1)/(2 nz) has been
+        // crossed (x and y go first on ties), i.e. floor(((2k-1) n + nz) / (2 nz)) of them.
+        bool entered_now = false;
+        if (oz < m.z_lo || oz >= m.z_hi) {
+            long long k = 0;
+            if (sz > 0 && oz < m.z_lo) k = (long long)m.z_lo - oz;
+            else if (sz < 0 && oz >= m.z_hi) k = (long long)oz - (m.z_hi - 1);
+            if (k <= 0 || k > nz) live = false; // the ray never enters this slab
+            else {
+                const long long cz = k;
+                const long long cx = nx ? min((long long)nx, ((2 * k - 1) * nx + nz) / (2LL * nz)) : 0;
+                const long long cy = ny ? min((long long)ny, ((2 * k - 1) * ny + nz) / (2LL * nz)) : 0;
+                z = oz + sz * (int)cz;
+                lin0 = ((long long)(ox + sx * (int)cx) * m.dims[1] + (oy + sy * (int)cy)) * m.zs + (z - m.z_lo);
+                if (nx) ex = (I)(2 * cx + 1) * my * mz;
+                if (ny) ey = (I)(2 * cy + 1) * mx * mz;
+                ez = (I)(2 * cz + 1) * mx * my;
+                done_steps = (int)(cx + cy + cz);
+                entered_now = true;
+            }
+        }
+        if (live) {
+            uint8_t *g = m.grid;
+            long long lin = lin0;
+            const long long stx = (long long)sx * m.dims[1] * m.zs, sty = (long long)sy * m.zs, stz = sz;
+            // the voxel just entered by the jump is itself a visit unless it is the endpoint
+            if (entered_now && done_steps <= steps - 1 && g[lin] != 0)
+                byte_rmw(g, (size_t)lin, [&](uint32_t c) { return c > (uint32_t)delta_dec ? c - delta_dec : 0u; });
+            const unsigned zs = (unsigned)m.zs;
+            int zrel = z - m.z_lo;
+            for (int s = done_steps; s + 1 < steps; ++s) {
+                const bool px = (ex <= ey) && (ex <= ez);
+                const bool py = !px && (ey <= ez);
+                const bool pz = !px && !py;
+                lin += px ? stx : (py ? sty : stz);
+                ex += px ? dxs : (I)0;
+                ey += py ? dys : (I)0;
+                ez += pz ? dzs : (I)0;
+                zrel += pz ? sz : 0;
+                if ((unsigned)zrel >= zs) break; // left the slab for good
+                // phase 1 only lowers values, so a cached non-zero byte is at worst stale-high: the CAS re-reads it
+                if (g[lin] != 0)
+                    byte_rmw(g, (size_t)lin, [&](uint32_t c) { return c > (uint32_t)delta_dec ? c - delta_dec : 0u; });
+            }
+        }
     }
     if (visited) {
 #pragma unroll
@@ -132,7 +173,11 @@ void launch_map_rays(const MapDev &m, const float4 *pts, int n, const float orig
         if (q >= m.dims[k]) q = m.dims[k] - 1;
         o[k] = q;
     }
-    map_rays_kernel<<<(n + 127) / 128, 128, 0, s>>>(m, pts, n, o[0], o[1], o[2], delta_dec, visited);
+    const double prod = 3.0 * m.dims[0] * m.dims[1] * m.dims[2];
+    if (prod < 2147483647.0)
+        map_rays_kernel<int><<<(n + 127) / 128, 128, 0, s>>>(m, pts, n, o[0], o[1], o[2], delta_dec, visited);
+    else
+        map_rays_kernel<long long><<<(n + 127) / 128, 128, 0, s>>>(m, pts, n, o[0], o[1], o[2], delta_dec, visited);
 }
 
 } // namespace icpb

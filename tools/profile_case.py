@@ -16,6 +16,7 @@ ap.add_argument("--iters", type=int, default=1)
 ap.add_argument("--repeat", type=int, default=1)
 ap.add_argument("--grid", type=float, default=-1.0, help="use ICPB_NN_GRID with this cell size (0 = default)")
 ap.add_argument("--map", action="store_true", help="also run back-projection + map integration")
+ap.add_argument("--cm", type=float, default=2.0, help="map cell in cm (2 -> 300x300x250, 1 -> 600x600x500)")
 a = ap.parse_args()
 
 d0, d1, col, _ = synth.frame_pair()
@@ -37,7 +38,16 @@ for r in range(a.repeat):
           f"nn_partial_ms={res['nn_partial_ms']:.3f} qpt={res['nn_qpt']} splits={res['nn_splits']} cell={res['grid_cell_used']:.3f} "
           f"rescans={res['exact_rescans']}")
 if a.map:
-    m = ctx.map((300, 300, 250), 0.02)
-    v = m.integrate_rays(dat, (5.0, 5.0, 5.0), 25, 25)
-    print("map voxels visited", v)
+    from icpb200 import synth as _s
+    cell = a.cm / 100.0
+    dims = (int(round(6 / cell)), int(round(6 / cell)), int(round(5 / cell)))
+    m = ctx.map(dims, cell)
+    poses = _s.trajectory(3, step_deg=0.8, step_m=0.02)
+    wc = ctx.cloud(w * h)
+    for f, (R, t) in enumerate(poses):
+        dpt = _s.render_depth(R, t, _s.KINECT_V1, seed=f)
+        wc.from_depth(dpt, None, K); wc.transform(R.astype(np.float32), t.astype(np.float32))
+        ctx.timer_start()
+        v = m.integrate_rays(wc, tuple(float(x) for x in t), 25, 25)
+        print("map", dims, "frame", f, "rays", wc.n, "voxels visited", v, "ms", round(ctx.timer_stop(), 3))
 ctx.close()
