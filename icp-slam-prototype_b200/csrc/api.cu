@@ -17,7 +17,7 @@ thread_local std::string g_create_error;
 enum WsId {
     WS_DESCS = 0, WS_STATES, WS_PARAMS, WS_TGT_SOA, WS_PM1, WS_PM2, WS_PG, WS_IDX, WS_DIST, WS_CHUNKS, WS_ALT,
     WS_IDX_TRACE, WS_DIST_TRACE, WS_MISC, WS_DEPTH, WS_BGR, WS_KEEP, WS_TILESTATE, WS_IMG_A, WS_IMG_B, WS_NORMALS,
-    WS_RT, WS_GRID_META, WS_GRID_COUNTS, WS_GRID_CURSOR, WS_GRID_SUMS, WS_GRID_SORTED, WS_GRID_BBOX, WS_GRID_HEAVY, WS_COUNT
+    WS_RT, WS_GRID_META, WS_GRID_COUNTS, WS_GRID_CURSOR, WS_GRID_SUMS, WS_GRID_SORTED, WS_GRID_BBOX, WS_GRID_HEAVY, WS_BATCHSTATE, WS_COUNT
 };
 
 int fail(icpb_ctx *ctx, int status, const char *what, cudaError_t ce = cudaSuccess)
@@ -687,6 +687,8 @@ int icpb_cloud_from_depth_device(icpb_cloud *cloud, const void *d_depth, const v
     a.out = cloud->d_pts;
     a.capacity = cloud->capacity;
     a.n_tiles = backproject_tiles(w, h);
+    a.frames = 1;
+    a.depth_stride = a.bgr_stride = a.out_stride = a.state_stride = 0;
     void *ts;
     int rc;
     // [ticket (u32) | pad][out_count (i32) | pad][2*n_tiles status words]: fixed positions, so a
@@ -713,6 +715,44 @@ int icpb_cloud_from_depth_device(icpb_cloud *cloud, const void *d_depth, const v
         return fail(ctx, ICPB_ERR_CAPACITY, "icpb_cloud_from_depth: more points than the cloud's capacity");
     }
     cloud->n = n;
+    return ICPB_OK;
+}
+
+int icpb_backproject_batch_device(icpb_ctx *ctx, const void *d_depth, const void *d_bgr, int frames, int w, int h,
+                                  const icpb_intrinsics *K, void *d_points, int capacity_per_frame, int *d_counts)
+{
+    if (!ctx || !d_depth || !K || !d_points || !d_counts || frames <= 0 || w <= 0 || h <= 0 || capacity_per_frame <= 0)
+        return ICPB_ERR_INVALID;
+    if ((((size_t)w * h * sizeof(uint16_t)) & 15) != 0 || ((uintptr_t)d_depth & 15) != 0)
+        return fail(ctx, ICPB_ERR_INVALID, "batched depth frames must be 16-byte aligned");
+    CU(ctx, cudaSetDevice(ctx->device));
+    BackprojectArgs a;
+    a.depth = (const uint16_t *)d_depth;
+    a.bgr = (const uint8_t *)d_bgr;
+    a.w = w; a.h = h; a.K = *K;
+    a.rule = ICPB_SUB_NONE; a.rule_arg = 1; a.seed = 0;
+    a.keep_stream = nullptr; a.keep_stream_len = 0;
+    a.out = (float4 *)d_points;
+    a.capacity = capacity_per_frame;
+    a.n_tiles = backproject_tiles(w, h);
+    a.frames = frames;
+    a.depth_stride = (long long)w * h;
+    a.bgr_stride = (long long)w * h * 3;
+    a.out_stride = capacity_per_frame;
+    a.state_stride = 2LL * a.n_tiles + 2;
+    void *ts;
+    int rc;
+    if ((rc = ws_get(ctx, WS_BATCHSTATE, sizeof(unsigned long long) * (size_t)a.state_stride * frames, &ts, true))) return rc;
+    a.ticket = (unsigned int *)ts;
+    a.out_count = (int *)((unsigned long long *)ts + 1);
+    a.tile_state = (unsigned long long *)ts + 2;
+    launch_backproject(a, ctx->stream);
+    ctx->launches += 1;
+    // counts: word 1 of every frame's state block -> d_counts[frame]
+    CU(ctx, cudaMemcpy2DAsync(d_counts, sizeof(int), (const char *)ts + sizeof(unsigned long long),
+                              sizeof(unsigned long long) * (size_t)a.state_stride, sizeof(int), (size_t)frames,
+                              cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(ctx, cudaGetLastError());
     return ICPB_OK;
 }
 

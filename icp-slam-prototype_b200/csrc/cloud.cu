@@ -105,6 +105,16 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *s
 // position among KEPT pixels (raster order == push_back order, :54).
 __global__ void __launch_bounds__(kBpThreads) backproject_kernel(BackprojectArgs a, uint32_t epoch)
 {
+    // batched launch: frame = blockIdx.y, every per-frame pointer advances by its stride
+    {
+        const long long f = blockIdx.y;
+        a.depth += f * a.depth_stride;
+        if (a.bgr) a.bgr += f * a.bgr_stride;
+        a.out += f * a.out_stride;
+        a.tile_state += f * a.state_stride;
+        a.ticket = (unsigned int *)((unsigned long long *)a.ticket + f * a.state_stride);
+        a.out_count = (int *)((unsigned long long *)a.out_count + f * a.state_stride);
+    }
     __shared__ uint32_t s_warp[kBpThreads / 32];
     __shared__ uint32_t s_bcast[2];
     __shared__ int s_tile;
@@ -139,22 +149,27 @@ __global__ void __launch_bounds__(kBpThreads) backproject_kernel(BackprojectArgs
 #pragma unroll
     for (int k = 0; k < kBpPix; ++k) nvalid += (dpx[k] != 0);
 
-    uint32_t tile_valid;
-    uint32_t v_off = block_exclusive_scan(nvalid, s_warp, tile_valid);
+    // the ordinal among non-zero pixels is only consumed by the STRIDE / STREAM rules: skip that scan otherwise
+    const bool need_ordinal = (a.rule == ICPB_SUB_STRIDE) || (a.rule == ICPB_SUB_STREAM);
     const unsigned long long tag = (unsigned long long)(epoch << 2) << 32;
-    if (tid == 0) {
-        unsigned long long fl = (tile == 0) ? 2ull : 1ull;
-        st_volatile_u64(&stateV[tile], tag | (fl << 32) | tile_valid);
-    }
-    if (tid < 32) {
-        uint32_t ex = (tile == 0) ? 0u : lookback(stateV, tile, epoch, &failed);
+    uint32_t v_base = 0;
+    if (need_ordinal) {
+        uint32_t tile_valid;
+        uint32_t v_off = block_exclusive_scan(nvalid, s_warp, tile_valid);
         if (tid == 0) {
-            if (tile != 0) st_volatile_u64(&stateV[tile], tag | (2ull << 32) | (ex + tile_valid));
-            s_bcast[0] = ex;
+            unsigned long long fl = (tile == 0) ? 2ull : 1ull;
+            st_volatile_u64(&stateV[tile], tag | (fl << 32) | tile_valid);
         }
+        if (tid < 32) {
+            uint32_t ex = (tile == 0) ? 0u : lookback(stateV, tile, epoch, &failed);
+            if (tid == 0) {
+                if (tile != 0) st_volatile_u64(&stateV[tile], tag | (2ull << 32) | (ex + tile_valid));
+                s_bcast[0] = ex;
+            }
+        }
+        __syncthreads();
+        v_base = s_bcast[0] + v_off;
     }
-    __syncthreads();
-    const uint32_t v_base = s_bcast[0] + v_off;
 
     // keep decisions
     uint32_t keep_mask = 0, ord = v_base;
@@ -190,25 +205,34 @@ __global__ void __launch_bounds__(kBpThreads) backproject_kernel(BackprojectArgs
         }
     }
     __syncthreads();
-    uint32_t o = s_bcast[1] + k_off;
-
+    // points go to shared memory at their tile-local position first, then leave with fully coalesced 16-byte stores
+    __shared__ float4 s_pts[kBpTile];
+    uint32_t lo = k_off;
     // pointcloud.cpp:37-39 (134-136): all float, left to right, true division
+    {
+        int v = p0 / a.w, u = p0 - v * a.w;
 #pragma unroll
-    for (int k = 0; k < kBpPix; ++k) {
-        if (keep_mask & (1u << k)) {
-            const int p = p0 + k;
-            const int v = p / a.w, u = p - v * a.w;
-            float pz = ((float)dpx[k]) / a.K.depth_scale;
-            float px = ((float)u - a.K.cx_u) * pz / a.K.fx_u;
-            float py = ((float)v - a.K.cx_v) * pz / a.K.fx_v;
-            uint32_t cbits = 0;
-            if (a.bgr) {
-                const uint8_t *c = a.bgr + (size_t)p * 3;
-                cbits = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16); // :47
+        for (int k = 0; k < kBpPix; ++k) {
+            if (keep_mask & (1u << k)) {
+                const int p = p0 + k;
+                float pz = ((float)dpx[k]) / a.K.depth_scale;
+                float px = ((float)u - a.K.cx_u) * pz / a.K.fx_u;
+                float py = ((float)v - a.K.cx_v) * pz / a.K.fx_v;
+                uint32_t cbits = 0;
+                if (a.bgr) {
+                    const uint8_t *c = a.bgr + (size_t)p * 3;
+                    cbits = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16); // :47
+                }
+                s_pts[lo++] = make_float4(px, py, pz, __uint_as_float(cbits));
             }
-            if ((int)o < a.capacity) a.out[o] = make_float4(px, py, pz, __uint_as_float(cbits));
-            ++o;
+            if (++u == a.w) { u = 0; ++v; }
         }
+    }
+    __syncthreads();
+    const uint32_t tile_base = s_bcast[1];
+    for (uint32_t j = tid; j < tile_keep; j += kBpThreads) {
+        const uint32_t o = tile_base + j;
+        if ((int)o < a.capacity) a.out[o] = s_pts[j];
     }
 }
 
@@ -217,7 +241,8 @@ void launch_backproject(const BackprojectArgs &a, cudaStream_t s)
     static uint32_t epoch = 0; // per-process launch counter; stale tile words never match it
     epoch = (epoch + 1) & 0x3fffffffu;
     if (epoch == 0) epoch = 1;
-    backproject_kernel<<<a.n_tiles, kBpThreads, 0, s>>>(a, epoch);
+    dim3 grid(a.n_tiles, a.frames > 0 ? a.frames : 1);
+    backproject_kernel<<<grid, kBpThreads, 0, s>>>(a, epoch);
 }
 
 // P3, SLAM.cpp:412-430.  Central differences on raw depth units; normalize as

@@ -131,6 +131,9 @@ struct BackprojectArgs {
     unsigned long long *tile_state; // device scratch, zeroed by the launcher
     unsigned int *ticket;
     int n_tiles;
+    // batched launch (blockIdx.y = frame): strides between consecutive frames, in elements
+    int frames;
+    long long depth_stride, bgr_stride, out_stride, state_stride; // pixels, bytes, points, u64 words
 };
 int backproject_tiles(int w, int h);
 void launch_backproject(const BackprojectArgs &a, cudaStream_t s);

@@ -174,6 +174,11 @@ class Context:
         c.upload(pts)
         return c
 
+    def backproject_batch_device(self, d_depth, d_bgr, frames, w, h, K, d_points, capacity_per_frame, d_counts):
+        self.check(self.lib.icpb_backproject_batch_device(
+            self.h, C.c_void_p(d_depth), C.c_void_p(d_bgr) if d_bgr else None, int(frames), int(w), int(h), C.byref(K),
+            C.c_void_p(d_points), int(capacity_per_frame), C.c_void_p(d_counts)))
+
     # ---- image stages
     def normals(self, depth):
         depth = np.ascontiguousarray(depth, dtype=np.uint16)

@@ -155,6 +155,11 @@ int icpb_cloud_from_depth(icpb_cloud *cloud, const uint16_t *depth, const uint8_
 int icpb_cloud_from_depth_device(icpb_cloud *cloud, const void *d_depth, const void *d_bgr, int w, int h,
                                  const icpb_intrinsics *K, int rule, uint32_t rule_arg, uint32_t seed,
                                  const void *d_keep_stream, int keep_stream_len);
+/* Batched form of the constructor for throughput work (no host synchronisation): `frames` depth images (and
+ * optional BGR images) back to back in device memory -> frame f's points at d_points + f*capacity_per_frame
+ * (16 B each), its point count in d_counts[f].  Keeps every non-zero pixel (ICPB_SUB_NONE). */
+int icpb_backproject_batch_device(icpb_ctx *ctx, const void *d_depth, const void *d_bgr, int frames, int w, int h,
+                                  const icpb_intrinsics *K, void *d_points, int capacity_per_frame, int *d_counts);
 /* PointCloud::rotate pointcloud.cpp:321-331 then PointCloud::translate :349-359 (either may be NULL). */
 int icpb_cloud_transform(icpb_cloud *cloud, const float R[9], const float t[3]);
 /* PointCloud::center (pointcloud.cpp:43-45,100-102), canonical FP64 block-ordered mean. */

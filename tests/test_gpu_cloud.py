@@ -139,3 +139,28 @@ def test_depth_filter(ctx, orc):
     got = ctx.depth_filter(raw, 1000, 25000)
     want = orc.depth_filter(raw, 1000, 25000)
     assert np.array_equal(got, want)
+
+
+def test_backproject_batch_device(ctx, orc):
+    """Batched, sync-free back-projection: frame f of the batch == the single-frame constructor == the oracle."""
+    import torch
+    import icpb200
+    from icpb200 import synth
+    frames = [_frame(s, synth.KINECT_V2)[0] for s in (1, 2, 3)] * 2
+    w, h = synth.KINECT_V2["w"], synth.KINECT_V2["h"]
+    dev = torch.device("cuda", 0)
+    d_depth = torch.from_numpy(np.stack(frames).astype(np.int16)).to(dev)    # u16 payload, viewed as i16 by torch
+    cap = w * h
+    d_pts = torch.zeros((len(frames), cap, 4), dtype=torch.float32, device=dev)
+    d_cnt = torch.zeros(len(frames), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    ctx.backproject_batch_device(d_depth.data_ptr(), None, len(frames), w, h, icpb200.reference_intrinsics_v2(),
+                                 d_pts.data_ptr(), cap, d_cnt.data_ptr())
+    ctx.sync()
+    cnt = d_cnt.cpu().numpy()
+    pts = d_pts.cpu().numpy()
+    for f, depth in enumerate(frames):
+        ref, _, _ = orc.backproject(depth, None, orc.kinect_v2())
+        assert cnt[f] == len(ref)
+        got = np.ascontiguousarray(pts[f, : cnt[f]]).view(orc.POINT_DTYPE).reshape(-1)
+        assert np.array_equal(got.view(np.uint8), ref.view(np.uint8))
