@@ -156,6 +156,16 @@ def run_map1cm(args, rank, world, local):
         dist.all_gather_object(hs, (sm.z_lo, sm.z_hi, h, int((slab > 0).sum())))
     else:
         hs = [(sm.z_lo, sm.z_hi, h, int((slab > 0).sum()))]
+    unsharded_ok = None
+    if world > 1 and rank == 0:
+        # T7: the slabs must be the single-GPU grid, byte for byte - recompute it unsharded here and compare digests
+        one = D.SlabMap(ctx, dims, cell, 0, 1, 640 * 480)
+        for (R, t), dpt in zip(poses, depths):
+            one.integrate(dpt, K, R, t, 25, 25, False)
+        g1 = one.download()
+        unsharded_ok = all(hashlib.sha256(np.ascontiguousarray(g1[:, :, lo:hi]).tobytes()).hexdigest() == hh
+                           for (lo, hi, hh, _) in hs)
+        assert unsharded_ok, "z-slab result differs from the single-GPU grid"
     if rank == 0:
         ms_per_step = tot / args.steps
         updates = visited + npts  # voxels visited by rays + endpoint updates, per pass over the sequence
@@ -166,6 +176,7 @@ def run_map1cm(args, rank, world, local):
                 "config": {"workload": f"configs[4]: {frames} full-res Kinect v1 frames into a 600x600x500 1 cm uint8 grid "
                                        "(180 MB), z-slab sharded, one all-gather of lifted points per frame",
                            "rays_per_pass": npts, "voxels_visited_per_pass": visited, "slabs": hs,
+                           "slabs_equal_single_gpu_grid": unsharded_ok,
                            "l2": "grid (180 MB) exceeds L2 at 1 GPU"},
                 "extra": {"frames_per_s": frames / (ms_per_step * 1e-3),
                           "algorithmic_GBps": alg_bytes / (ms_per_step * 1e-3) / 1e9}}
