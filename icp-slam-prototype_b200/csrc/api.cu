@@ -17,7 +17,7 @@ thread_local std::string g_create_error;
 enum WsId {
     WS_DESCS = 0, WS_STATES, WS_PARAMS, WS_TGT_SOA, WS_PM1, WS_PM2, WS_PG, WS_IDX, WS_DIST, WS_CHUNKS, WS_ALT,
     WS_IDX_TRACE, WS_DIST_TRACE, WS_MISC, WS_DEPTH, WS_BGR, WS_KEEP, WS_TILESTATE, WS_IMG_A, WS_IMG_B, WS_NORMALS,
-    WS_RT, WS_GRID_META, WS_GRID_COUNTS, WS_GRID_CURSOR, WS_GRID_SUMS, WS_GRID_SORTED, WS_GRID_BBOX, WS_GRID_HEAVY, WS_BATCHSTATE, WS_COUNT
+    WS_RT, WS_GRID_META, WS_GRID_COUNTS, WS_GRID_CURSOR, WS_GRID_SUMS, WS_GRID_SORTED, WS_GRID_BBOX, WS_GRID_HEAVY, WS_BATCHSTATE, WS_TRACK, WS_COUNT
 };
 
 int fail(icpb_ctx *ctx, int status, const char *what, cudaError_t ce = cudaSuccess)
@@ -957,6 +957,7 @@ int icpb_map_destroy(icpb_map *map)
     cudaSetDevice(map->ctx->device);
     cudaStreamSynchronize(map->ctx->stream);
     cudaFree(map->dev.grid);
+    if (map->table) cudaFree(map->table);
     delete map;
     return ICPB_OK;
 }
@@ -967,6 +968,7 @@ int icpb_map_clear(icpb_map *map)
     icpb_ctx *ctx = map->ctx;
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaMemsetAsync(map->dev.grid, 0, ((size_t)map->bytes + 3) / 4 * 4, ctx->stream));
+    if (map->table) CU(ctx, cudaMemsetAsync(map->table, 0xff, sizeof(int) * (size_t)map->bytes, ctx->stream));
     return ICPB_OK;
 }
 
@@ -980,6 +982,61 @@ int icpb_map_update_endpoints(icpb_map *map, const icpb_cloud *points, int rule,
     launch_map_endpoints(map->dev, points->d_pts, points->n, rule, delta, max_conf, ctx->stream);
     ctx->launches += points->n > 0;
     CU(ctx, cudaGetLastError());
+    return ICPB_OK;
+}
+
+int icpb_map_update_tracked(icpb_map *map, const icpb_cloud *points, int variant, int delta, int max_conf,
+                            icpb_cloud *map_cloud, int *n_appended)
+{
+    if (!map || !points || !map_cloud) return ICPB_ERR_INVALID;
+    icpb_ctx *ctx = map->ctx;
+    if (variant < ICPB_TRACK_INIT || variant > ICPB_TRACK_NONASSOC) return fail(ctx, ICPB_ERR_INVALID, "unknown variant");
+    if (delta < 0 || delta > 255) return fail(ctx, ICPB_ERR_INVALID, "delta out of [0,255]");
+    if (map->dev.z_lo != 0 || map->dev.z_hi != map->dev.dims[2])
+        return fail(ctx, ICPB_ERR_INVALID, "icpb_map_update_tracked needs a whole-map handle");
+    if (points->n > 65536) return fail(ctx, ICPB_ERR_CAPACITY, "icpb_map_update_tracked: more than 65536 points");
+    if (n_appended) *n_appended = 0;
+    if (points->n == 0) return ICPB_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!map->table) {
+        const size_t tb = sizeof(int) * (size_t)map->bytes;
+        CU(ctx, cudaMalloc((void **)&map->table, tb));
+        CU(ctx, cudaMemsetAsync(map->table, 0xff, tb, ctx->stream)); // -1 = empty (map.cpp:27)
+    }
+    void *wsp;
+    int rc;
+    if ((rc = ws_get(ctx, WS_TRACK, 16 + (sizeof(long long) + sizeof(int)) * 65536, &wsp))) return rc;
+    int *d_app = (int *)wsp;
+    launch_map_tracked(map->dev, map->table, points->d_pts, points->n, variant, delta, max_conf, map_cloud->d_pts,
+                       map_cloud->n, map_cloud->capacity, d_app, ctx->stream);
+    ctx->launches += 1;
+    int app = 0;
+    CU(ctx, cudaMemcpyAsync(&app, d_app, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaGetLastError());
+    if (map_cloud->n + app > map_cloud->capacity) {
+        map_cloud->n = map_cloud->capacity;
+        return fail(ctx, ICPB_ERR_CAPACITY, "icpb_map_update_tracked: map cloud capacity exceeded");
+    }
+    map_cloud->n += app;
+    if (n_appended) *n_appended = app;
+    return ICPB_OK;
+}
+
+int icpb_map_has_entry(icpb_map *map, const float p[3], int *has_entry)
+{
+    if (!map || !p || !has_entry) return ICPB_ERR_INVALID;
+    icpb_ctx *ctx = map->ctx;
+    *has_entry = 0;
+    if (!map->table) return ICPB_OK;
+    int v[3];
+    icpb_map_voxel_coords(map, p, v);
+    const size_t lin = ((size_t)v[0] * map->dev.dims[1] + v[1]) * map->dev.zs + (v[2] - map->dev.z_lo);
+    int e = -1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(&e, map->table + lin, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    *has_entry = e >= 0;
     return ICPB_OK;
 }
 

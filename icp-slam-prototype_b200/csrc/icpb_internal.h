@@ -149,6 +149,8 @@ struct MapDev {
 };
 void launch_map_endpoints(const MapDev &m, const float4 *pts, int n, int rule, int delta, int max_conf,
                           cudaStream_t s);
+void launch_map_tracked(const MapDev &m, int *table, const float4 *pts, int n, int variant, int delta, int max_conf,
+                        float4 *dst, int dst_n, int dst_capacity, int *d_appended, cudaStream_t s);
 void launch_map_rays(const MapDev &m, const float4 *pts, int n, const float origin[3], int delta_dec,
                      unsigned long long *visited, cudaStream_t s);
 
@@ -186,4 +188,5 @@ struct icpb_map {
     icpb_ctx *ctx = nullptr;
     icpb::MapDev dev{};
     long long bytes = 0;
+    int *table = nullptr; // lazily allocated lookup table: index into the map cloud, -1 = empty (map.hpp:24)
 };

@@ -77,6 +77,113 @@ void launch_map_endpoints(const MapDev &m, const float4 *pts, int n, int rule, i
     map_endpoints_kernel<<<(n + 255) / 256, 256, 0, s>>>(m, pts, n, rule, delta, max_conf);
 }
 
+// M3 with the reference's lookup-table / mapCloud bookkeeping (map.cpp:101-113, 136-149, 246-259).  One CTA,
+// n <= 65536 points (key-points in the reference).  For point i: rank = hits of lower index on the same voxel,
+// k = all hits on it.  The hit of rank 0 writes f^k(c0) (one writer per voxel, no atomics); the hit whose rank
+// equals r* = the first rank satisfying the variant's condition inserts, if the voxel has no table entry yet.
+// Inserted points are appended to dst in point order (block scans over chunks of 1024).
+constexpr int kTrackThreads = 1024;
+
+__device__ __forceinline__ uint32_t track_apply(uint32_t c, int variant, int delta, int max_conf)
+{
+    if (variant == ICPB_TRACK_NONASSOC) return ((int)c >= max_conf - delta) ? 255u : ((c + delta) & 0xffu);
+    return (c > (uint32_t)(255 - delta)) ? 255u : c + delta;
+}
+
+__global__ void __launch_bounds__(kTrackThreads) map_tracked_kernel(MapDev m, int *table, const float4 *__restrict__ pts,
+                                                                    int n, int variant, int delta, int max_conf,
+                                                                    float4 *dst, int dst_n, int dst_capacity,
+                                                                    int *d_appended, long long *vox_scratch)
+{
+    __shared__ long long s_vox[kTrackThreads];
+    __shared__ int s_warp[33];
+    __shared__ int s_base;
+    const int tid = threadIdx.x;
+    // voxel of every point (scratch in global memory: n <= 65536)
+    for (int i = tid; i < n; i += kTrackThreads) {
+        float4 p = pts[i];
+        int vx = voxel_axis(p.x, m.cell, m.dims[0]), vy = voxel_axis(p.y, m.cell, m.dims[1]);
+        int vz = voxel_axis(p.z, m.cell, m.dims[2]);
+        vox_scratch[i] = ((long long)vx * m.dims[1] + vy) * m.zs + vz;
+    }
+    if (tid == 0) s_base = dst_n;
+    __syncthreads();
+    // ---- phase A: decide everything from the PRE-update grid / table; nothing is written to them yet
+    int *flags = reinterpret_cast<int *>(vox_scratch + 65536); // bit 0 insert, bit 1 writer, bits 8..15 new value
+    for (int c0 = 0; c0 < n; c0 += kTrackThreads) {
+        const int i = c0 + tid;
+        const long long v = (i < n) ? vox_scratch[i] : -1;
+        int rank = 0, k = 0;
+        for (int t0 = 0; t0 < n; t0 += kTrackThreads) {
+            __syncthreads();
+            s_vox[tid] = (t0 + tid < n) ? vox_scratch[t0 + tid] : -2;
+            __syncthreads();
+            const int lim = min(kTrackThreads, n - t0);
+            for (int j = 0; j < lim; ++j) {
+                const bool same = (s_vox[j] == v);
+                k += same;
+                rank += same && (t0 + j < i);
+            }
+        }
+        if (i < n) {
+            // values before hit r: c_r = f^r(c0); r* = first hit rank whose condition holds
+            uint32_t c = m.grid[v];
+            int rstar = -1;
+            for (int r = 0; r < k; ++r) {
+                const uint32_t after = track_apply(c, variant, delta, max_conf);
+                bool cond;
+                if (variant == ICPB_TRACK_INIT) cond = (int)after >= max_conf;
+                else if (variant == ICPB_TRACK_ASSOC) cond = c > (uint32_t)(255 - delta);
+                else cond = (int)c >= max_conf - delta;
+                if (cond && rstar < 0) rstar = r;
+                c = after;
+            }
+            const int insert = (rank == rstar) && (table[v] < 0);
+            flags[i] = insert | ((rank == 0) ? 2 : 0) | ((int)c << 8);
+        }
+    }
+    __syncthreads();
+    // ---- phase B: one writer per voxel stores f^k(c0); inserted points are appended in point order
+    for (int c0 = 0; c0 < n; c0 += kTrackThreads) {
+        const int i = c0 + tid;
+        const int fl = (i < n) ? flags[i] : 0;
+        const int insert = fl & 1;
+        if (fl & 2) m.grid[vox_scratch[i]] = (uint8_t)(fl >> 8);
+        const int lane = tid & 31, wid = tid >> 5;
+        int inc = insert;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { int o = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += o; }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int w = s_warp[lane], winc = w;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { int o = __shfl_up_sync(0xffffffffu, winc, off); if (lane >= off) winc += o; }
+            s_warp[lane] = winc - w;
+            if (lane == 31) s_warp[32] = winc;
+        }
+        __syncthreads();
+        const int total = s_warp[32];
+        const int pos = s_base + s_warp[wid] + inc - insert;
+        if (insert) {
+            if (pos < dst_capacity) dst[pos] = pts[i];
+            table[vox_scratch[i]] = pos;
+        }
+        __syncthreads();
+        if (tid == 0) s_base += total;
+        __syncthreads();
+    }
+    if (tid == 0) *d_appended = s_base - dst_n;
+}
+
+void launch_map_tracked(const MapDev &m, int *table, const float4 *pts, int n, int variant, int delta, int max_conf,
+                        float4 *dst, int dst_n, int dst_capacity, int *d_appended, cudaStream_t s)
+{
+    long long *scratch = reinterpret_cast<long long *>(d_appended + 2);
+    map_tracked_kernel<<<1, kTrackThreads, 0, s>>>(m, table, pts, n, variant, delta, max_conf, dst, dst_n, dst_capacity,
+                                                   d_appended, scratch);
+}
+
 // M4 phase 1: exact integer Amanatides-Woo walk from the origin voxel centre to the endpoint voxel centre.
 // Axis k crosses its i-th wall at t = (2i+1)/(2 n_k); scaled by 2 P (P = product of max(n_k,1)) the wall times
 // are the integers e_k = (2i+1) P / n_k; the smallest goes first, ties x < y < z.  An axis that has crossed all

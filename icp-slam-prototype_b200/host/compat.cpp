@@ -7,7 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
-#include <unordered_set>
+#include <algorithm>
 
 #include "icpb200.h"
 #include "icpb200/map.hpp"
@@ -472,45 +472,45 @@ cv::Point3i Map::getVoxelCoordinates(cv::Point3f point) // map.cpp:55-85
     return p;
 }
 
-void Map::updatePoints(const point_list_t &pts, int rule, int delta)
+// The three Map::update overloads, certainty grid AND pointLookupTable / mapCloud bookkeeping, on the device
+// (icpb_map_update_tracked); the points it appends come back in point order and join the host-side list.
+static void tracked_update(icpb_map *dev, const point_list_t &pts, int variant, int delta, point_list_t &append_to)
 {
-    ensure();
-    if (pts.empty()) return;
-    icpb_cloud *c = upload(2, pts);
-    check(icpb_map_update_endpoints(dev_, c, rule, delta, MAX_CONFIDENCE), "icpb_map_update_endpoints");
+    const size_t kMax = 65536;
+    for (size_t off = 0; off < pts.size(); off += kMax) {
+        point_list_t part(pts.begin() + (long)off, pts.begin() + (long)std::min(pts.size(), off + kMax));
+        icpb_cloud *src = upload(2, part);
+        icpb_cloud *dst = scratch(1, (int)part.size());
+        check(icpb_cloud_upload(dst, nullptr, 0), "icpb_cloud_upload");
+        int appended = 0;
+        check(icpb_map_update_tracked(dev, src, variant, delta, MAX_CONFIDENCE, dst, &appended), "icpb_map_update_tracked");
+        if (appended) {
+            point_list_t got;
+            download(dst, got);
+            append_to.insert(append_to.end(), got.begin(), got.end());
+        }
+    }
 }
 
-// map.cpp:220-269: rule A over the cloud's key-points; a key-point whose voxel reaches MAX_CONFIDENCE and has
-// no table entry yet joins mapCloud.keypoints.  The grid update runs on the device; the (tiny) mapCloud
-// bookkeeping replays the per-voxel hit sequence on the host from the pre-update mirror.
-void Map::update(icp::PointCloud data, int delta_confidence, cv::viz::Viz3d &)
+void Map::update(icp::PointCloud data, int delta_confidence, cv::viz::Viz3d &) // map.cpp:220-269
 {
     ensure();
-    syncWorld();
-    updatePoints(data.keypoints, ICPB_RULE_A, delta_confidence);
-    static std::unordered_set<long long> table; // voxels that hold a lookup-table entry
-    if (mapCloud.keypoints.empty()) table.clear();
-    for (const color_point_t &p : data.keypoints) {
-        cv::Point3i v = getVoxelCoordinates(p.point);
-        unsigned char *c = &world[v.x][v.y][v.z];
-        if (*c > (255 - delta_confidence)) *c = 255;
-        else *c += delta_confidence;
-        long long key = ((long long)v.x * MAP_HEIGHT + v.y) * MAP_HEIGHT + v.z;
-        if (!table.count(key) && *c >= MAX_CONFIDENCE) { table.insert(key); mapCloud.keypoints.push_back(p); }
-    }
+    tracked_update(dev_, data.keypoints, ICPB_TRACK_INIT, delta_confidence, mapCloud.keypoints);
 }
 
 void Map::update(associations_t associations, int delta_confidence) // map.cpp:88-119 (never called by the reference)
 {
+    ensure();
     point_list_t firsts;
     for (const auto &pr : associations) firsts.push_back(pr.first);
-    updatePoints(firsts, ICPB_RULE_A, delta_confidence);
+    tracked_update(dev_, firsts, ICPB_TRACK_ASSOC, delta_confidence, mapCloud.points);
 }
 
 void Map::update(associations_t keyPointAssociations, std::vector<float>, point_list_t nonAssociations, int delta_confidence)
 {
     if (keyPointAssociations.size() == 0) return; // map.cpp:124-126
-    updatePoints(nonAssociations, ICPB_RULE_C, delta_confidence); // map.cpp:130-151 (certainty part)
+    ensure();
+    tracked_update(dev_, nonAssociations, ICPB_TRACK_NONASSOC, delta_confidence, mapCloud.keypoints); // map.cpp:130-151
 }
 
 // map.cpp:272-439 with the semantics of DESIGN.md "M4": one ray between two voxels.

@@ -24,6 +24,7 @@ SUB_NONE, SUB_STRIDE, SUB_HASH, SUB_STREAM = 0, 1, 2, 3
 SOLVE_REFERENCE, SOLVE_KABSCH = 0, 1
 RULE_A, RULE_C = 0, 1
 NN_BRUTE, NN_GRID, NN_AUTO = 0, 1, 2
+TRACK_INIT, TRACK_ASSOC, TRACK_NONASSOC = 0, 1, 2
 
 
 class IcpbError(RuntimeError):
@@ -333,6 +334,17 @@ class Map:
 
     def update_endpoints(self, cloud, rule=RULE_A, delta=25, max_conf=180):
         self.ctx.check(self.ctx.lib.icpb_map_update_endpoints(self.h, cloud.h, rule, delta, max_conf))
+
+    def update_tracked(self, cloud, variant, delta, max_conf, map_cloud):
+        n = C.c_int(0)
+        self.ctx.check(self.ctx.lib.icpb_map_update_tracked(self.h, cloud.h, variant, delta, max_conf, map_cloud.h, C.byref(n)))
+        return n.value
+
+    def has_entry(self, p):
+        pp = (C.c_float * 3)(*p)
+        e = C.c_int(0)
+        self.ctx.check(self.ctx.lib.icpb_map_has_entry(self.h, pp, C.byref(e)))
+        return bool(e.value)
 
     def integrate_rays(self, cloud, origin, delta_dec=25, delta_inc=25, count_visits=True):
         o = (C.c_float * 3)(*origin)

@@ -202,6 +202,21 @@ int icpb_map_destroy(icpb_map *map);
 int icpb_map_clear(icpb_map *map);
 /* Map::update overloads, map.cpp:88-119 / 122-151 / 220-269: saturating endpoint increments. */
 int icpb_map_update_endpoints(icpb_map *map, const icpb_cloud *points, int rule, int delta, int max_conf);
+/* The same updates WITH the lookup-table / mapCloud bookkeeping of the reference: the point whose hit first
+ * satisfies the variant's condition on a voxel without a table entry is recorded in the table and appended to
+ * `map_cloud` (in point order, like the push_back of the sequential loop).
+ *   ICPB_TRACK_INIT     Map::update(PointCloud, delta, win) map.cpp:246-259: rule A; insert when the value AFTER
+ *                       the hit is >= max_conf
+ *   ICPB_TRACK_ASSOC    Map::update(assoc, delta) map.cpp:101-113: rule A; insert in the saturating branch
+ *                       (value before the hit > 255 - delta)
+ *   ICPB_TRACK_NONASSOC Map::update(assoc, errors, nonAssoc, delta) map.cpp:136-149: rule C; insert in the
+ *                       promoting branch (value before the hit >= max_conf - delta)
+ * At most 65536 points per call (the reference feeds key-points here).  Whole-map handles only. */
+enum { ICPB_TRACK_INIT = 0, ICPB_TRACK_ASSOC = 1, ICPB_TRACK_NONASSOC = 2 };
+int icpb_map_update_tracked(icpb_map *map, const icpb_cloud *points, int variant, int delta, int max_conf,
+                            icpb_cloud *map_cloud, int *n_appended);
+/* 1 when the voxel of p holds a lookup-table entry (pointLookupTable[..] != empty, map.hpp:24). */
+int icpb_map_has_entry(icpb_map *map, const float p[3], int *has_entry);
 /* Map::rayTrace map.cpp:272-439 (semantics in DESIGN.md "M4"): integer ray walk from the
  * origin voxel, decrements with clamp at 0, then rule-A endpoint increments. */
 int icpb_map_integrate_rays(icpb_map *map, const icpb_cloud *points, const float origin[3],

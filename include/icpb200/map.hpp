@@ -1,6 +1,7 @@
 // Drop-in for the reference's map.hpp (map.hpp:1-40): same macros and class map::Map.  The certainty
-// grid lives on the B200; `world` is a host mirror refreshed by syncWorld() (the reference's 27 MB array
-// member, map.hpp:25).  pointLookupTable (432 MB in the reference, map.hpp:24) is not materialised.
+// grid and the lookup table live on the B200; `world` is a host mirror refreshed by syncWorld() (the
+// reference's 27 MB array member, map.hpp:25).  pointLookupTable (432 MB in the reference, map.hpp:24) is kept on
+// the device as one int per voxel (index of the stored point, -1 = empty); mapCloud receives the same appends.
 #ifndef MAP_HPP
 #define MAP_HPP
 
@@ -48,7 +49,6 @@ public:
 private:
     icpb_map *dev_;
     void ensure();
-    void updatePoints(const point_list_t &pts, int rule, int delta);
 };
 } // namespace map
 

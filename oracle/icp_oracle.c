@@ -643,6 +643,36 @@ void orc_map_update_endpoints(uint8_t *grid, const int dims[3], float cell,
     }
 }
 
+int orc_map_update_tracked(uint8_t *grid, int32_t *table, const int dims[3], float cell, const orc_point *pts, int n,
+                           int variant, int delta, int max_conf, int map_cloud_size, int32_t *appended)
+{
+    int n_app = 0;
+    for (int i = 0; i < n; i++) {
+        float p[3] = {pts[i].x, pts[i].y, pts[i].z};
+        int v[3];
+        orc_voxel_coords(p, cell, dims, v);
+        size_t lin = ((size_t)v[0] * dims[1] + v[1]) * dims[2] + v[2];
+        uint8_t *c = &grid[lin];
+        int insert = 0;
+        if (variant == 0) {                       /* map.cpp:249-259 */
+            if (*c > 255 - delta) *c = 255;
+            else *c = (uint8_t)(*c + delta);
+            insert = (table[lin] < 0) && (*c >= max_conf);
+        } else if (variant == 1) {                /* map.cpp:104-113 */
+            if (*c > 255 - delta) { *c = 255; insert = table[lin] < 0; }
+            else *c = (uint8_t)(*c + delta);
+        } else {                                  /* map.cpp:139-149 */
+            if (*c >= max_conf - delta) { *c = 255; insert = table[lin] < 0; }
+            else *c = (uint8_t)(*c + delta);
+        }
+        if (insert) {
+            table[lin] = map_cloud_size + n_app;
+            appended[n_app++] = i;
+        }
+    }
+    return n_app;
+}
+
 /* Ray integration.  Origin of the semantics: Map::rayTrace, map.cpp:272-439
  * (Amanatides-Woo, dead and buggy in the reference: call sites commented at
  * :99,:231; "TODO - This is wrong" :363; unsigned wrap :424-427).  The

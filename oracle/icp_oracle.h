@@ -108,6 +108,12 @@ int orc_icp(orc_point *data /* in/out, n */, int n, const orc_point *target, int
 void orc_voxel_coords(const float p[3], float cell, const int dims[3], int v[3]);
 void orc_map_update_endpoints(uint8_t *grid, const int dims[3], float cell,
                               const orc_point *pts, int n, int rule, int delta, int max_conf);
+/* Map::update WITH the pointLookupTable / mapCloud bookkeeping, restated sequentially:
+ * variant 0 = update(PointCloud, delta, win) map.cpp:220-269; 1 = update(assoc, delta) map.cpp:88-119;
+ * 2 = update(assoc, errors, nonAssoc, delta) map.cpp:122-151.  `table` holds -1 (== empty, map.cpp:27) or the
+ * index the point received in the map cloud; appended[] lists the inserted points' indices in insertion order. */
+int orc_map_update_tracked(uint8_t *grid, int32_t *table, const int dims[3], float cell, const orc_point *pts, int n,
+                           int variant, int delta, int max_conf, int map_cloud_size, int32_t *appended);
 /* returns number of voxels visited (decrement candidates) */
 long long orc_map_integrate_rays(uint8_t *grid, const int dims[3], float cell,
                                  const orc_point *pts, int n, const float origin[3],

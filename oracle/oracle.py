@@ -233,6 +233,17 @@ def map_update_endpoints(grid, dims, cell, pts, rule=RULE_A, delta=25, max_conf=
     return grid
 
 
+def map_update_tracked(grid, table, dims, cell, pts, variant, delta=25, max_conf=180, map_cloud_size=0):
+    """Returns the indices (into pts) of the points appended to the map cloud, in insertion order."""
+    assert grid.dtype == np.uint8 and table.dtype == np.int32 and grid.flags.c_contiguous and table.flags.c_contiguous
+    d = (C.c_int * 3)(*dims)
+    pts = np.ascontiguousarray(pts)
+    app = np.zeros(max(len(pts), 1), dtype=np.int32)
+    k = lib().orc_map_update_tracked(_p(grid), _p(table), d, C.c_float(cell), _p(pts), len(pts), variant, delta, max_conf,
+                                     map_cloud_size, _p(app))
+    return app[:k].copy()
+
+
 def map_integrate_rays(grid, dims, cell, pts, origin, delta_dec=25, delta_inc=25, z_lo=0, z_hi=None):
     assert grid.dtype == np.uint8 and grid.flags.c_contiguous
     d = (C.c_int * 3)(*dims)

@@ -105,6 +105,13 @@ def map_update(pts, delta, kind):
     fn(_p(pts), len(pts), int(delta))
 
 
+def map_cloud(kind, capacity=1 << 20):
+    """mapCloud.keypoints (kind 0) / mapCloud.points (kind 1) of the reference's global map."""
+    out = np.zeros(capacity, dtype=POINT_DTYPE)
+    n = lib().ref_map_cloud(int(kind), _p(out), capacity)
+    return out[:n].copy()
+
+
 def map_world():
     out = np.zeros((300, 300, 300), dtype=np.uint8)
     lib().ref_map_world(_p(out))

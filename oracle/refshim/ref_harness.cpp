@@ -135,6 +135,14 @@ void ref_map_update_assoc(const ref_point *pts, int n, int delta)
 }
 void ref_map_world(unsigned char *out) { std::memcpy(out, icp::map.world, sizeof(icp::map.world)); }
 int ref_map_keypoints() { return (int)icp::map.mapCloud.keypoints.size(); }
+// mapCloud.keypoints (kind 0) or mapCloud.points (kind 1) as appended by the Map::update overloads
+int ref_map_cloud(int kind, ref_point *out, int capacity)
+{
+    const point_list_t &l = kind == 0 ? icp::map.mapCloud.keypoints : icp::map.mapCloud.points;
+    int n = (int)l.size();
+    for (int i = 0; i < n && i < capacity; ++i) out[i] = from_cp(l[i]);
+    return n;
+}
 
 // The while loop of icp.cpp:155-258 with the all-point association of :149/:253 swapped in for the
 // key-point one, every step being the reference's own function (the loop skeleton is restated

@@ -67,6 +67,17 @@ int main(int argc, char **argv)
     m.update(assoc, DELTA_CONFIDENCE);
     m.update(assoc, DELTA_CONFIDENCE);
     m.integrateRays(data, cv::Point3f(5, 5, 5), DELTA_CONFIDENCE, DELTA_CONFIDENCE);
+    {   // lookup-table / mapCloud bookkeeping through the reference's three update overloads
+        map::Map m2;
+        icp::PointCloud kp;
+        kp.keypoints.assign(data.points.begin(), data.points.begin() + 1500);
+        m2.update(kp, MAX_CONFIDENCE, win);                                   // map.cpp:220-269
+        point_list_t non(target.points.begin(), target.points.begin() + 1200);
+        for (int rep = 0; rep < 7; ++rep) m2.update(assoc, errors, non, DELTA_CONFIDENCE); // map.cpp:122-151
+        dump(out + "/mapcloud_kp.bin", m2.mapCloud.keypoints.data(), m2.mapCloud.keypoints.size() * sizeof(color_point_t));
+        m2.syncWorld();
+        dump(out + "/world2.bin", m2.world, (size_t)MAP_HEIGHT * MAP_HEIGHT * MAP_HEIGHT);
+    }
     m.syncWorld();
     dump(out + "/world.bin", m.world, (size_t)MAP_HEIGHT * MAP_HEIGHT * MAP_HEIGHT);
     cv::Point3i v = m.getVoxelCoordinates(data.points[0].point);

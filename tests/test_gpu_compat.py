@@ -92,6 +92,19 @@ def test_compat_program_matches_oracle(tmp_path, orc):
     orc.map_update_endpoints(grid, dims, cell, firsts, orc.RULE_A, 25, 180)
     orc.map_update_endpoints(grid, dims, cell, firsts, orc.RULE_A, 25, 180)
     orc.map_integrate_rays(grid, dims, cell, moved, (5.0, 5.0, 5.0), 25, 25)
+    # the three update overloads incl. mapCloud bookkeeping (second map of the C++ program)
+    g2 = np.zeros(dims, np.uint8)
+    tbl = np.full(dims, -1, np.int32)
+    kp_list = []
+    app = orc.map_update_tracked(g2, tbl, dims, cell, np.ascontiguousarray(moved[:1500]), 0, 180, 180, 0)
+    kp_list.extend(moved[:1500][app])
+    non = np.ascontiguousarray(tgt5[:1200])
+    for _ in range(7):
+        app = orc.map_update_tracked(g2, tbl, dims, cell, non, 2, 25, 180, len(kp_list))
+        kp_list.extend(non[app])
+    _same(_pts(o + "/mapcloud_kp.bin", orc), np.array(kp_list, dtype=orc.POINT_DTYPE))
+    assert len(kp_list) > 1500 - 200 and np.array_equal(np.fromfile(o + "/world2.bin", np.uint8).reshape(dims), g2)
+
     world = np.fromfile(o + "/world.bin", np.uint8).reshape(dims)
     assert np.array_equal(world, grid)
     vox = np.fromfile(o + "/voxel.bin", np.int32)

@@ -150,3 +150,30 @@ def test_slab_clipped_walks_random_rays(ctx, orc, origin_z):
     got = np.concatenate(parts, axis=2)
     assert np.array_equal(got, want), f"{(got != want).sum()} voxels differ"
     c.close()
+
+
+@pytest.mark.parametrize("variant,delta", [(0, 180), (0, 25), (1, 25), (2, 25), (2, 60)])
+def test_tracked_updates_match_oracle(ctx, orc, pair10k, variant, delta):
+    """M3 with the lookup-table / mapCloud bookkeeping on the device: grid, inserted points and their order."""
+    data, target = pair10k
+    dims, cell = REF_DIMS, float(REF_CELL)
+    m = ctx.map(dims, cell)
+    mc = ctx.cloud(200000)
+    grid = np.zeros(dims, np.uint8)
+    table = np.full(dims, -1, np.int32)
+    mine = []
+    for rep in range(12):
+        pts = np.ascontiguousarray((data if rep % 2 == 0 else target)[rep * 37: rep * 37 + 2500])
+        c = ctx.cloud_from_points(pts)
+        k = m.update_tracked(c, variant, delta, 180, mc)
+        app = orc.map_update_tracked(grid, table, dims, cell, pts, variant, delta, 180, len(mine))
+        assert k == len(app)
+        mine.extend(pts[app])
+        c.close()
+    assert np.array_equal(m.download(), grid)
+    got = mc.download()
+    assert len(got) == len(mine) and len(mine) > 0
+    assert np.array_equal(got.view(np.uint8), np.array(mine, dtype=orc.POINT_DTYPE).view(np.uint8))
+    probe = orc.xyz_of(np.array(mine[:1], dtype=orc.POINT_DTYPE))[0]
+    assert m.has_entry(tuple(float(x) for x in probe))
+    m.close(); mc.close()

@@ -121,3 +121,27 @@ def test_registration_loop_pose_within_tolerance(orc, pair10k):
     assert np.abs(r["cam_position"] - o["cam_position"]).max() < 1e-5
     assert abs(r["mse"] - o["mse"]) < 1e-7
     assert np.abs(orc.xyz_of(rout) - orc.xyz_of(oout)).max() < 1e-5
+
+
+@pytest.mark.parametrize("kind,variant,delta,which", [("cloud", 0, 180, 0), ("cloud", 0, 25, 0), ("nonassoc", 2, 25, 0),
+                                                      ("assoc", 1, 25, 1)])
+def test_map_cloud_bookkeeping_bit_exact(orc, pair10k, kind, variant, delta, which):
+    """pointLookupTable / mapCloud insertion of the Map::update overloads (map.cpp:104-110, 142-145, 256-259):
+    which points are appended, and in which order."""
+    data, target = pair10k
+    cell = float(np.float32(10.0) / np.float32(300.0))
+    dims = (300, 300, 300)
+    ref.map_reset()
+    grid = np.zeros(dims, np.uint8)
+    table = np.full(dims, -1, np.int32)
+    mine = []
+    for rep in range(12):
+        pts = np.ascontiguousarray((data if rep % 2 == 0 else target)[rep * 37: rep * 37 + 2500])
+        ref.map_update(pts, delta, kind)
+        app = orc.map_update_tracked(grid, table, dims, cell, pts, variant, delta, 180, len(mine))
+        mine.extend(pts[app])
+    got = ref.map_cloud(which)
+    assert len(got) == len(mine) and len(mine) > 0
+    assert np.array_equal(got.view(np.uint8), np.array(mine, dtype=orc.POINT_DTYPE).view(np.uint8))
+    assert np.array_equal(ref.map_world(), grid)
+    ref.map_reset()
