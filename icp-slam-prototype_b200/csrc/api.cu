@@ -786,19 +786,44 @@ int icpb_cloud_transform(icpb_cloud *cloud, const float R[9], const float t[3])
     icpb_ctx *ctx = cloud->ctx;
     if (cloud->n == 0 || (!R && !t)) return ICPB_OK;
     CU(ctx, cudaSetDevice(ctx->device));
-    float *d_rt;
-    int rc;
-    if ((rc = ws_get(ctx, WS_RT, 16 * sizeof(float), (void **)&d_rt))) return rc;
-    void *hp;
-    if ((rc = pinned_get(ctx, 16 * sizeof(float), &hp))) return rc;
-    float *h = (float *)hp;
-    for (int k = 0; k < 9; ++k) h[k] = R ? R[k] : 0.f;
-    for (int k = 0; k < 3; ++k) h[9 + k] = t ? t[k] : 0.f;
-    CU(ctx, cudaMemcpyAsync(d_rt, h, 12 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    launch_transform(cloud->d_pts, cloud->n, d_rt, d_rt + 9, R != nullptr, t != nullptr, ctx->stream);
+    launch_transform(cloud->d_pts, cloud->n, R, t, R != nullptr, t != nullptr, ctx->stream);
     ctx->launches += 1;
-    CU(ctx, cudaStreamSynchronize(ctx->stream)); // the pinned staging block is reused by later calls
     CU(ctx, cudaGetLastError());
+    return ICPB_OK;
+}
+
+int icpb_cloud_pack_band_device(icpb_cloud *cloud, void *device_dst, int band_capacity)
+{
+    if (!cloud || !device_dst) return ICPB_ERR_INVALID;
+    icpb_ctx *ctx = cloud->ctx;
+    if (cloud->n > band_capacity) return fail(ctx, ICPB_ERR_CAPACITY, "icpb_cloud_pack_band_device: band too small");
+    CU(ctx, cudaSetDevice(ctx->device));
+    launch_pack_band(cloud->d_pts, cloud->n, (float4 *)device_dst, ctx->stream);
+    ctx->launches += 1;
+    CU(ctx, cudaGetLastError());
+    return ICPB_OK;
+}
+
+int icpb_cloud_assemble_bands_device(icpb_cloud *cloud, const void *device_bands, int world, int band_capacity)
+{
+    if (!cloud || !device_bands || world <= 0 || band_capacity <= 0) return ICPB_ERR_INVALID;
+    icpb_ctx *ctx = cloud->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    void *misc;
+    int rc;
+    if ((rc = ws_get(ctx, WS_MISC, 64, &misc, true))) return rc;
+    int *d_total = (int *)((char *)misc + 56);
+    launch_assemble_bands((const float4 *)device_bands, world, band_capacity, cloud->d_pts, cloud->capacity, d_total, ctx->stream);
+    ctx->launches += 1;
+    int total = 0;
+    CU(ctx, cudaMemcpyAsync(&total, d_total, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaGetLastError());
+    if (total > cloud->capacity) {
+        cloud->n = cloud->capacity;
+        return fail(ctx, ICPB_ERR_CAPACITY, "icpb_cloud_assemble_bands_device: cloud capacity exceeded");
+    }
+    cloud->n = total;
     return ICPB_OK;
 }
 

@@ -107,6 +107,9 @@ void launch_nn_finalize(const RegDesc *descs, const IcpParamsDev *prm, int batch
                         int pass, cudaStream_t s);
 void launch_transform(float4 *pts, int n, const float *R, const float *t, int have_R, int have_t,
                       cudaStream_t s);
+void launch_pack_band(const float4 *pts, int n, float4 *dst, cudaStream_t s);
+void launch_assemble_bands(const float4 *bands, int world, int band_capacity, float4 *out, int out_capacity, int *total,
+                           cudaStream_t s);
 void launch_pending_translate(const RegDesc *descs, int batch, int max_n, cudaStream_t s);
 void launch_center(const float4 *pts, int n, double *chunk_sums, double *out3, unsigned int *counter,
                    cudaStream_t s);

@@ -776,26 +776,73 @@ void launch_nn_finalize(const RegDesc *descs, const IcpParamsDev *prm, int batch
 // --------------------------------------------------------------------------
 // stand-alone P2 transform, and the deferred translation of the <3 rule
 // --------------------------------------------------------------------------
-__global__ void transform_kernel(float4 *pts, int n, const float *__restrict__ Rp, const float *__restrict__ tp,
-                                 int have_R, int have_t)
+struct RtArgs {
+    float R[9];
+    float t[3];
+};
+
+// R and t travel as kernel arguments: no staging buffer, no host synchronisation
+__global__ void transform_kernel(float4 *pts, int n, RtArgs a, int have_R, int have_t)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 p = pts[i];
     if (have_R) {
-        float x = (Rp[0] * p.x + Rp[1] * p.y) + Rp[2] * p.z;
-        float y = (Rp[3] * p.x + Rp[4] * p.y) + Rp[5] * p.z;
-        float z = (Rp[6] * p.x + Rp[7] * p.y) + Rp[8] * p.z;
+        float x = (a.R[0] * p.x + a.R[1] * p.y) + a.R[2] * p.z;
+        float y = (a.R[3] * p.x + a.R[4] * p.y) + a.R[5] * p.z;
+        float z = (a.R[6] * p.x + a.R[7] * p.y) + a.R[8] * p.z;
         p.x = x; p.y = y; p.z = z;
     }
-    if (have_t) { p.x += tp[0]; p.y += tp[1]; p.z += tp[2]; }
+    if (have_t) { p.x += a.t[0]; p.y += a.t[1]; p.z += a.t[2]; }
     pts[i] = p;
 }
 
 void launch_transform(float4 *pts, int n, const float *R, const float *t, int have_R, int have_t, cudaStream_t s)
 {
     if (n <= 0) return;
-    transform_kernel<<<(n + 255) / 256, 256, 0, s>>>(pts, n, R, t, have_R, have_t);
+    RtArgs a;
+    for (int k = 0; k < 9; ++k) a.R[k] = have_R ? R[k] : 0.f;
+    for (int k = 0; k < 3; ++k) a.t[k] = have_t ? t[k] : 0.f;
+    transform_kernel<<<(n + 255) / 256, 256, 0, s>>>(pts, n, a, have_R, have_t);
+}
+
+// z-slab exchange helpers: a band = one 16-byte header row (point count) followed by band_capacity point rows
+__global__ void pack_band_kernel(const float4 *__restrict__ pts, int n, float4 *dst)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) dst[0] = make_float4(__int_as_float(n), 0.f, 0.f, 0.f);
+    if (i < n) dst[1 + i] = pts[i];
+}
+
+void launch_pack_band(const float4 *pts, int n, float4 *dst, cudaStream_t s)
+{
+    pack_band_kernel<<<(max(n, 1) + 255) / 256, 256, 0, s>>>(pts, n, dst);
+}
+
+// blockIdx.y = band; output offset = sum of the counts of the bands before it (rank order == raster order)
+__global__ void assemble_bands_kernel(const float4 *__restrict__ bands, int world, int band_capacity, float4 *out,
+                                      int out_capacity, int *total)
+{
+    const int r = blockIdx.y;
+    const float4 *band = bands + (size_t)r * (band_capacity + 1);
+    int base = 0, all = 0;
+    for (int q = 0; q < world; ++q) {
+        int c = __float_as_int(bands[(size_t)q * (band_capacity + 1)].x);
+        c = min(max(c, 0), band_capacity);
+        if (q < r) base += c;
+        all += c;
+    }
+    const int cnt = min(max(__float_as_int(band[0].x), 0), band_capacity);
+    if (r == 0 && blockIdx.x == 0 && threadIdx.x == 0) *total = all;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x)
+        if (base + i < out_capacity) out[base + i] = band[1 + i];
+}
+
+void launch_assemble_bands(const float4 *bands, int world, int band_capacity, float4 *out, int out_capacity, int *total,
+                           cudaStream_t s)
+{
+    dim3 grid((band_capacity + 1023) / 1024, world);
+    assemble_bands_kernel<<<grid, 256, 0, s>>>(bands, world, band_capacity, out, out_capacity, total);
 }
 
 __global__ void pending_translate_kernel(const RegDesc *__restrict__ descs)

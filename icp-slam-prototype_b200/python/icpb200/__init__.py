@@ -268,6 +268,13 @@ class Cloud:
     def download_device(self, ptr, capacity):
         self.ctx.check(self.ctx.lib.icpb_cloud_download_device(self.h, C.c_void_p(ptr), int(capacity)))
 
+    def pack_band_device(self, ptr, band_capacity):
+        self.ctx.check(self.ctx.lib.icpb_cloud_pack_band_device(self.h, C.c_void_p(ptr), int(band_capacity)))
+
+    def assemble_bands_device(self, ptr, world, band_capacity):
+        self.ctx.check(self.ctx.lib.icpb_cloud_assemble_bands_device(self.h, C.c_void_p(ptr), int(world), int(band_capacity)))
+        return self.n
+
     def device_ptr(self):
         return self.ctx.lib.icpb_cloud_device_ptr(self.h)
 

@@ -88,21 +88,28 @@ class SlabMap:
         r0, r1 = row_band(h, self.rank, self.world)
         self.local.from_depth(mask_rows(depth, r0, r1), None, K)
         self.local.transform(np.asarray(R_wc, np.float32), np.asarray(t_wc, np.float32))
-        n = self.local.n
-        dev = torch.device("cuda", self.ctx.device)
-        mine = torch.empty((max(n, 1), 4), dtype=torch.float32, device=dev)
-        self.local.download_device(mine.data_ptr(), max(n, 1))
-        self.ctx.sync()
-        if self.world > 1:
-            allp, _ = all_gather_points(mine[:n])
+        origin = tuple(float(x) for x in t_wc)
+        if self.world == 1:
+            v = self.map.integrate_rays(self.local, origin, delta_dec, delta_inc, count_visits)
+            return self.local.n, v
+        # fixed-capacity bands with the count in a header row: one all-gather, no count exchange, no host sync
+        cap = (-(-h // self.world)) * w
+        if getattr(self, "_send", None) is None or self._send.shape[0] != cap + 1:
+            dev = torch.device("cuda", self.ctx.device)
+            self._send = torch.zeros((cap + 1, 4), dtype=torch.float32, device=dev)
+            self._recv = torch.zeros((self.world * (cap + 1), 4), dtype=torch.float32, device=dev)
+        self.local.pack_band_device(self._send.data_ptr(), cap)
+        import torch.distributed as dist
+        # a context created on torch's current stream is ordered with the collective; otherwise fence both sides
+        shared = self.ctx.lib.icpb_ctx_stream(self.ctx.h) == torch.cuda.current_stream().cuda_stream
+        if not shared:
+            self.ctx.sync()
+        dist.all_gather_into_tensor(self._recv, self._send)
+        if not shared:
             torch.cuda.current_stream().synchronize()
-        else:
-            allp = mine[:n]
-        allp = allp.contiguous()
-        self.full.upload_device(allp.data_ptr(), allp.shape[0])
-        v = self.map.integrate_rays(self.full, tuple(float(x) for x in t_wc), delta_dec, delta_inc, count_visits)
-        self.ctx.sync()
-        return allp.shape[0], v
+        n = self.full.assemble_bands_device(self._recv.data_ptr(), self.world, cap)
+        v = self.map.integrate_rays(self.full, origin, delta_dec, delta_inc, count_visits)
+        return n, v
 
     def download(self):
         return self.map.download()

@@ -144,6 +144,11 @@ int icpb_cloud_copy(icpb_cloud *dst, const icpb_cloud *src);
 /* Adopt n points already in device memory (16 B each), e.g. after an all-gather. */
 int icpb_cloud_upload_device(icpb_cloud *cloud, const void *device_points, int n);
 const void *icpb_cloud_device_ptr(const icpb_cloud *cloud);
+/* z-slab exchange without host round trips: a "band" is one 16-byte header row (the point count) followed by
+ * band_capacity point rows.  pack writes this cloud as a band into device memory (e.g. the send buffer of an
+ * all-gather); assemble concatenates `world` bands (rank order) into this cloud. */
+int icpb_cloud_pack_band_device(icpb_cloud *cloud, void *device_dst, int band_capacity);
+int icpb_cloud_assemble_bands_device(icpb_cloud *cloud, const void *device_bands, int world, int band_capacity);
 /* Copy the cloud's points into caller-owned DEVICE memory (e.g. a torch tensor feeding an all-gather). */
 int icpb_cloud_download_device(icpb_cloud *cloud, void *device_dst, int capacity);
 /* PointCloud(cv::Mat& data, cv::Mat colorMat), pointcloud.cpp:109-165 (and :11-58):
