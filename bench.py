@@ -303,6 +303,7 @@ def run_b200(args, rank, world, local):
             "config": {"workload": wl["name"], "n_data": n, "n_target": m, "icp_iterations": ITERS,
                        "nn_passes": ITERS + 1, "solve_mode": "reference", "per_rank": "one frame pair per GPU",
                        "l2": "flushed between timed steps (256 MiB device write)",
+                       "nn_filter": "centred" if res["nn_filter_used"] == icpb200.FILTER_CENTRED else "direct",
                        "nn_qpt": res["nn_qpt"], "nn_splits": res["nn_splits"],
                        "exact_rescans_last_step": res["exact_rescans"]},
             "extra": {"nn_correspondences_per_s": world * n * (ITERS + 1) / (ms_per_step * 1e-3),
@@ -314,7 +315,10 @@ def run_b200(args, rank, world, local):
                                           "ms_per_step": float(np.mean(grid_ms)),
                                           "registrations_per_s": 1000.0 / float(np.mean(grid_ms)),
                                           "cell_m": res_g["grid_cell_used"], "pose_identical_to_brute_force": grid_same_pose}},
-            "roofline": {"bound": "fp32", "kernel": "nn_partial_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "fp32",
+                         "kernel": ("nn_partial_centred_kernel" if res["nn_filter_used"] == icpb200.FILTER_CENTRED
+                                    else "nn_partial_kernel") + f"<{res['nn_qpt']}>",
+                         "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one nn_partial launch at this workload, from the
                          # ncu --set full capture summarised in profiles/r01_ncu_nn_partial_fullres.txt (targets stay in L2)

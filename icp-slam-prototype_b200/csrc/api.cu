@@ -17,7 +17,7 @@ thread_local std::string g_create_error;
 enum WsId {
     WS_DESCS = 0, WS_STATES, WS_PARAMS, WS_TGT_SOA, WS_PM1, WS_PM2, WS_PG, WS_IDX, WS_DIST, WS_CHUNKS, WS_ALT,
     WS_IDX_TRACE, WS_DIST_TRACE, WS_MISC, WS_DEPTH, WS_BGR, WS_KEEP, WS_TILESTATE, WS_IMG_A, WS_IMG_B, WS_NORMALS,
-    WS_RT, WS_GRID_META, WS_GRID_COUNTS, WS_GRID_CURSOR, WS_GRID_SUMS, WS_GRID_SORTED, WS_GRID_BBOX, WS_GRID_HEAVY, WS_BATCHSTATE, WS_TRACK, WS_COUNT
+    WS_RT, WS_GRID_META, WS_GRID_COUNTS, WS_GRID_CURSOR, WS_GRID_SUMS, WS_GRID_SORTED, WS_GRID_BBOX, WS_GRID_HEAVY, WS_BATCHSTATE, WS_TRACK, WS_PA, WS_PM3, WS_PG2, WS_COUNT
 };
 
 int fail(icpb_ctx *ctx, int status, const char *what, cudaError_t ce = cudaSuccess)
@@ -79,14 +79,18 @@ int env_int(const char *name, int dflt)
 }
 
 // Work decomposition of nn_partial: QPT queries per thread, `splits` target ranges.
-void choose_nn_config(const icpb_ctx *ctx, int max_n, int max_m, int batch, int *qpt, int *splits)
+void choose_nn_config(const icpb_ctx *ctx, int max_n, int max_m, int batch, int filter, int *qpt, int *splits)
 {
-    int q = 8;
+    // Centred filter: the per-thread centring of the targets is amortised over the thread's queries, so large
+    // scans take 12 queries per thread (168 registers, 3 CTAs per SM); direct filter: 8.
+    int q = (filter == kFilterCentred && max_n >= 50000) ? 12 : 8;
     const long long slots = (long long)ctx->sm_count * 4; // ~4 resident 128-thread CTAs per SM
+    auto tiles_of = [&](int qq) { return (long long)((max_n + kNnThreads * qq - 1) / (kNnThreads * qq)) * batch; };
     // small problems: smaller query tiles give the grid more CTAs before the targets must be split
-    if ((long long)((max_n + kNnThreads * 8 - 1) / (kNnThreads * 8)) * batch < slots / 8) q = 4;
+    if (tiles_of(8) < slots / 8) q = 4;
     q = env_int("ICPB_QPT", q);
-    if (q != 2 && q != 4 && q != 8) q = 8;
+    if (filter == kFilterCentred) { if (q != 2 && q != 4 && q != 8 && q != 12 && q != 16) q = 8; }
+    else if (q != 2 && q != 4 && q != 8) q = 8;
     const int tiles = (max_n + kNnThreads * q - 1) / (kNnThreads * q);
     const int ngroups = (max_m + kGroup - 1) / kGroup;
     long long s = (slots + (long long)tiles * batch - 1) / ((long long)tiles * batch);
@@ -131,13 +135,14 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
     if (trace && count != 1) return fail(ctx, ICPB_ERR_INVALID, "traces are only supported for a single registration");
 
     int qpt, splits;
-    choose_nn_config(ctx, max_n, max_m, count, &qpt, &splits);
+    const int filter = env_int("ICPB_NN_FILTER", prm->nn_filter) == kFilterDirect ? kFilterDirect : kFilterCentred;
+    choose_nn_config(ctx, max_n, max_m, count, filter, &qpt, &splits);
 
     RegDesc *d_descs;
     IcpState *d_states;
     IcpParamsDev *d_prm;
-    float *d_soa, *d_pm1, *d_pm2, *d_dist;
-    int *d_pg, *d_idx;
+    float *d_soa, *d_pm1, *d_pm2, *d_pm3, *d_pa, *d_dist;
+    int *d_pg, *d_pg2, *d_idx;
     double *d_chunks;
     float4 *d_alt;
     int rc;
@@ -148,6 +153,9 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
     if ((rc = ws_get(ctx, WS_PM1, tot_n * splits * sizeof(float), (void **)&d_pm1))) return rc;
     if ((rc = ws_get(ctx, WS_PM2, tot_n * splits * sizeof(float), (void **)&d_pm2))) return rc;
     if ((rc = ws_get(ctx, WS_PG, tot_n * splits * sizeof(int), (void **)&d_pg))) return rc;
+    if ((rc = ws_get(ctx, WS_PA, tot_n * sizeof(float), (void **)&d_pa))) return rc;
+    if ((rc = ws_get(ctx, WS_PM3, tot_n * splits * sizeof(float), (void **)&d_pm3))) return rc;
+    if ((rc = ws_get(ctx, WS_PG2, tot_n * splits * sizeof(int), (void **)&d_pg2))) return rc;
     if ((rc = ws_get(ctx, WS_IDX, tot_n * sizeof(int), (void **)&d_idx))) return rc;
     if ((rc = ws_get(ctx, WS_DIST, tot_n * sizeof(float), (void **)&d_dist))) return rc;
     if ((rc = ws_get(ctx, WS_CHUNKS, tot_chunks * kTerms * sizeof(double), (void **)&d_chunks))) return rc;
@@ -253,6 +261,9 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         d.pm1 = d_pm1 + off_n * splits;
         d.pm2 = d_pm2 + off_n * splits;
         d.pg = d_pg + off_n * splits;
+        d.pa = d_pa + off_n;
+        d.pm3 = d_pm3 + off_n * splits;
+        d.pg2 = d_pg2 + off_n * splits;
         d.idx = d_idx + off_n;
         d.dist = d_dist + off_n;
         d.chunk_sums = d_chunks + off_c * kTerms;
@@ -308,9 +319,9 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
     for (int pass = 0; pass < passes; ++pass) {
         if (prof) CU(ctx, cudaEventRecord(ctx->prof_events[2 * pass], st));
         if (grid_mode) launch_nn_grid(d_descs, count, max_n, pass, ctx->sm_count, st);
-        else launch_nn_partial(d_descs, count, max_n, qpt, splits, pass, st);
+        else launch_nn_partial(d_descs, count, max_n, qpt, splits, pass, filter, st);
         if (prof) CU(ctx, cudaEventRecord(ctx->prof_events[2 * pass + 1], st));
-        launch_nn_finalize(d_descs, d_prm, count, max_n, grid_mode ? 0 : splits, pass, st);
+        launch_nn_finalize(d_descs, d_prm, count, max_n, grid_mode ? 0 : splits, pass, filter, st);
         launches += grid_mode ? 3 : 2;
     }
     launch_pending_translate(d_descs, count, max_n, st);
@@ -369,6 +380,7 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
             r.nn_splits = splits;
             r.nn_mode_used = grid_mode ? ICPB_NN_GRID : ICPB_NN_BRUTE;
             r.grid_cell_used = grid_mode ? gm.h : 0.f;
+            r.nn_filter_used = filter;
         }
     }
     if (trace) {

@@ -33,6 +33,13 @@ constexpr float kPadCoord = 1.0e18f; // padding targets: (a-b)^2 ~ 3e36, finite,
 // second-best group minimum within this relative band of the best => exact FP64 rescan
 constexpr float kBandRel = 1.0f + 1.9073486328125e-06f; // 1 + 2^-19
 constexpr float kBandAbs = 1.0e-30f;
+// the two filters of the brute-force scan (nn.cu)
+constexpr int kFilterCentred = ICPB_FILTER_CENTRED; // |t'|^2 - 2a'.t' about a per-thread centre: 3 per pair + 6 per target per thread
+constexpr int kFilterDirect = ICPB_FILTER_DIRECT;   // (a-t)^2 in packed FP32: 6 FMA-pipe lane-ops per pair
+// centred filter: the W-gap that proves "strictly farther" is kBandCentredA * A + kBandCentredX * max(W_best + A, 0);
+// the bound at nn_partial_centred_kernel needs 16u A + 103u X (u = 2^-24), used with ~10 % slack
+constexpr float kBandCentredA = 18.0f * 5.9604644775390625e-08f;
+constexpr float kBandCentredX = 115.0f * 5.9604644775390625e-08f;
 
 // Per-registration device state: iteration control and pose, kept on the
 // device for the whole loop (icp.cpp:22-25 globals + locals of :28-285).
@@ -85,6 +92,9 @@ struct RegDesc {
     int n, m, ngroups;
     int n_stride;            // row stride of the per-split partial arrays
     float *pm1, *pm2;        // [S][n_stride] best / second-best group minimum (approximate squared distance)
+    float *pm3;              // [S][n_stride] centred filter only: third-best group minimum
+    int *pg2;                // [S][n_stride] centred filter only: group holding pm2 (-1: none)
+    float *pa;               // [n_stride] centred filter only: |a - c|^2 of every query about its thread's centre
     int *pg;                 // [S][n_stride] group holding pm1
     int *idx;                // [n] nearest target index
     float *dist;             // [n] nearest distance (reference arithmetic)
@@ -101,10 +111,10 @@ struct RegDesc {
 
 // ---- launchers (defined in the .cu files) ---------------------------------
 void launch_target_prep(const float4 *tgt, int m, float *soa, int ngroups, cudaStream_t s);
-void launch_nn_partial(const RegDesc *descs, int batch, int max_n, int qpt, int splits, int pass,
+void launch_nn_partial(const RegDesc *descs, int batch, int max_n, int qpt, int splits, int pass, int filter,
                        cudaStream_t s);
 void launch_nn_finalize(const RegDesc *descs, const IcpParamsDev *prm, int batch, int max_n, int splits,
-                        int pass, cudaStream_t s);
+                        int pass, int filter, cudaStream_t s);
 void launch_transform(float4 *pts, int n, const float *R, const float *t, int have_R, int have_t,
                       cudaStream_t s);
 void launch_pack_band(const float4 *pts, int n, float4 *dst, cudaStream_t s);

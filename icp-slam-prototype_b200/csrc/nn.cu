@@ -301,18 +301,217 @@ __global__ void __launch_bounds__(kNnThreads) nn_partial_kernel(const RegDesc *_
     }
 }
 
-void launch_nn_partial(const RegDesc *descs, int batch, int max_n, int qpt, int splits, int pass, cudaStream_t s)
+// --------------------------------------------------------------------------
+// nn_partial_centred: the N x M scan with the expanded, locally centred filter
+// --------------------------------------------------------------------------
+//
+// Same contract as nn_partial_kernel (best / second-best GROUP minimum and the
+// best group's id per query and split), but the filter value is
+//     W(a,t) = |t'|^2 - 2 a'.t'  =  |a - t|^2 - |a'|^2,   a' = a - c,  t' = t - c
+// with c the centre of the QPT *consecutive* queries a thread owns.  Per
+// (query, target) pair the FMA pipe sees 3 FFMA (packed two targets at a time)
+// instead of 3 FADD + FMUL + 2 FFMA; centring the targets costs 6 packed-lane
+// ops per target per thread, amortised over the thread's QPT queries.
+// Centring is what keeps the expansion usable: its rounding error scales with
+// (|a'| + |t'|)^2, i.e. with the spread of one thread's queries (centimetres
+// for a raster-ordered cloud) instead of the 5-8 m world coordinates.
+//
+// Error bound used by nn_finalize (u = 2^-24, A = |a'|^2, D = |a - t|^2 exact):
+//     |W + A - D| <= 40 u A + 26 u D
+// (a' and t' carry one rounding each, |t'|^2 three, the FMA chain three, every
+// partial result is bounded by (|a'| + |t'|)^2 and |t'| <= |a'| + sqrt(D)).
+// A target whose W exceeds the best W by more than 2^-17 (A + max(W_best + A, 0))
+// is therefore strictly farther in the reference's own arithmetic (3 u on each
+// squared distance, 4 u for the float sqrt) than the best target: it can
+// neither win nor tie.  A is written to d.pa by split 0.
+template <int QPT>
+__global__ void __launch_bounds__(kNnThreads, (QPT >= 16 ? 2 : QPT >= 12 ? 3 : 4)) nn_partial_centred_kernel(const RegDesc *__restrict__ descs, int splits,
+                                                                        int pass)
+{
+    const RegDesc d = descs[blockIdx.z]; // by value: no pointer reloads after stores
+    IcpState *st = d.st;
+    if (st->done) return;
+    const int n = d.n;
+    const int q0 = blockIdx.x * (kNnThreads * QPT);
+    if (q0 >= n) return;
+    const int split = blockIdx.y;
+    const int tid = threadIdx.x;
+
+    const int gps = (d.ngroups + splits - 1) / splits;
+    const int g_begin = split * gps;
+    const int g_end = min(d.ngroups, g_begin + gps);
+    const int n_tiles = (g_end > g_begin) ? (g_end - g_begin + kStageGroups - 1) / kStageGroups : 0;
+
+    constexpr int kStageFloats = kStageGroups * kGroup * 3;
+    __shared__ __align__(128) float s_tile[kStages][kStageFloats];
+    __shared__ __align__(8) uint64_t s_full[kStages];
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&s_full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const float *soa = d.tgt_soa;
+    auto issue = [&](int tile) {
+        int gb = g_begin + tile * kStageGroups;
+        int ng = min(kStageGroups, g_end - gb);
+        uint32_t bytes = (uint32_t)ng * (kGroup * 3 * sizeof(float));
+        int s = tile % kStages;
+        mbar_expect_tx(&s_full[s], bytes);
+        tma_bulk_g2s(&s_tile[s][0], soa + (size_t)gb * (kGroup * 3), bytes, &s_full[s]);
+    };
+    if (tid == 0) {
+        for (int t = 0; t < kStages && t < n_tiles; ++t) issue(t);
+    }
+
+    // ---- queries: QPT consecutive points per thread; apply the pending rigid motion, hand on to the next buffer
+    const float4 *src = d.D[pass & 1];
+    float4 *dst = d.D[(pass + 1) & 1];
+    const int apply = st->apply;
+    float R[9], T[3];
+    if (apply) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[k] = st->Rf[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) T[k] = st->tf[k];
+    }
+    const int i0 = q0 + tid * QPT;
+    float ax[QPT], ay[QPT], az[QPT];
+    float lox = CUDART_INF_F, loy = CUDART_INF_F, loz = CUDART_INF_F;
+    float hix = -CUDART_INF_F, hiy = -CUDART_INF_F, hiz = -CUDART_INF_F;
+#pragma unroll
+    for (int q = 0; q < QPT; ++q) {
+        const int i = i0 + q;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n) {
+            p = src[i];
+            if (apply) p = apply_rt(p, R, T);
+            if (split == 0) dst[i] = p;
+            lox = fminf(lox, p.x); loy = fminf(loy, p.y); loz = fminf(loz, p.z);
+            hix = fmaxf(hix, p.x); hiy = fmaxf(hiy, p.y); hiz = fmaxf(hiz, p.z);
+        }
+        ax[q] = p.x; ay[q] = p.y; az[q] = p.z;
+    }
+    // centre of the thread's own queries (any value is valid; it only sets the size of the error bound)
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    if (i0 < n) { cx = 0.5f * lox + 0.5f * hix; cy = 0.5f * loy + 0.5f * hiy; cz = 0.5f * loz + 0.5f * hiz; }
+    // a' = a - c; the scan uses 2a' against the negated centred targets -(t - c)
+#pragma unroll
+    for (int q = 0; q < QPT; ++q) {
+        const bool v = (i0 + q) < n;
+        const float x = v ? ax[q] - cx : 0.f, y = v ? ay[q] - cy : 0.f, z = v ? az[q] - cz : 0.f;
+        if (v && split == 0) d.pa[i0 + q] = (x * x + y * y) + z * z;
+        ax[q] = 2.f * x; ay[q] = 2.f * y; az[q] = 2.f * z;
+    }
+    const u64 c2x = pack2(cx, cx), c2y = pack2(cy, cy), c2z = pack2(cz, cz);
+
+    // three best GROUP minima per query (ids for the best two): nn_finalize re-evaluates one or two groups exactly
+    float m1[QPT], m2[QPT], m3[QPT];
+    int g1[QPT], g2[QPT];
+#pragma unroll
+    for (int q = 0; q < QPT; ++q) {
+        m1[q] = CUDART_INF_F; m2[q] = CUDART_INF_F; m3[q] = CUDART_INF_F;
+        g1[q] = g_begin < d.ngroups ? g_begin : 0; g2[q] = -1;
+    }
+
+    for (int tile = 0; tile < n_tiles; ++tile) {
+        const int s = tile % kStages;
+        mbar_wait(&s_full[s], (uint32_t)((tile / kStages) & 1));
+        const int gb = g_begin + tile * kStageGroups;
+        const int ng = min(kStageGroups, g_end - gb);
+        for (int gi = 0; gi < ng; ++gi) {
+            const float4 *s4 = reinterpret_cast<const float4 *>(&s_tile[s][gi * (kGroup * 3)]);
+            float gm[QPT];
+#pragma unroll
+            for (int q = 0; q < QPT; ++q) gm[q] = CUDART_INF_F;
+#pragma unroll kUnrollJ
+            for (int j = 0; j < kGroup / 4; ++j) {
+                const float4 X = s4[j];
+                const float4 Y = s4[kGroup / 4 + j];
+                const float4 Z = s4[2 * (kGroup / 4) + j];
+                // -(t - c) for four targets, and |t - c|^2
+                const u64 x01 = add2(pack2(X.x, X.y), c2x), x23 = add2(pack2(X.z, X.w), c2x);
+                const u64 y01 = add2(pack2(Y.x, Y.y), c2y), y23 = add2(pack2(Y.z, Y.w), c2y);
+                const u64 z01 = add2(pack2(Z.x, Z.y), c2z), z23 = add2(pack2(Z.z, Z.w), c2z);
+                const u64 n01 = fma2(z01, z01, fma2(y01, y01, mul2(x01, x01)));
+                const u64 n23 = fma2(z23, z23, fma2(y23, y23, mul2(x23, x23)));
+#pragma unroll
+                for (int q = 0; q < QPT; ++q) {
+                    const u64 qx = pack2(ax[q], ax[q]);
+                    const u64 qy = pack2(ay[q], ay[q]);
+                    const u64 qz = pack2(az[q], az[q]);
+                    u64 sa = fma2(qx, x01, n01), sb = fma2(qx, x23, n23);
+                    sa = fma2(qy, y01, sa); sb = fma2(qy, y23, sb);
+                    sa = fma2(qz, z01, sa); sb = fma2(qz, z23, sb);
+                    float s0, s1, s2, s3;
+                    unpack2(sa, s0, s1);
+                    unpack2(sb, s2, s3);
+                    gm[q] = min3(gm[q], s0, s1);
+                    gm[q] = min3(gm[q], s2, s3);
+                }
+            }
+            const int g = gb + gi;
+            // most groups beat none of the thread's third-best minima: one compare per query, then skip
+            bool hit = false;
+#pragma unroll
+            for (int q = 0; q < QPT; ++q) hit |= gm[q] < m3[q];
+            if (hit) {
+#pragma unroll
+                for (int q = 0; q < QPT; ++q) {
+                    const float v = gm[q];
+                    const bool lt1 = v < m1[q], lt2 = v < m2[q];
+                    m3[q] = lt2 ? m2[q] : fminf(m3[q], v);
+                    g2[q] = lt1 ? g1[q] : (lt2 ? g : g2[q]);
+                    m2[q] = lt1 ? m1[q] : (lt2 ? v : m2[q]);
+                    g1[q] = lt1 ? g : g1[q];
+                    m1[q] = lt1 ? v : m1[q];
+                }
+            }
+        }
+        __syncthreads(); // every warp is done with stage s
+        if (tid == 0 && tile + kStages < n_tiles) issue(tile + kStages);
+    }
+
+    const size_t row = (size_t)split * d.n_stride;
+#pragma unroll
+    for (int q = 0; q < QPT; ++q) {
+        const int i = i0 + q;
+        if (i < n) {
+            d.pm1[row + i] = m1[q];
+            d.pm2[row + i] = m2[q];
+            d.pm3[row + i] = m3[q];
+            d.pg[row + i] = g1[q];
+            d.pg2[row + i] = g2[q];
+        }
+    }
+}
+
+template <int QPT>
+static void launch_centred(dim3 grid, const RegDesc *descs, int splits, int pass, cudaStream_t s)
+{
+    nn_partial_centred_kernel<QPT><<<grid, kNnThreads, 0, s>>>(descs, splits, pass);
+}
+
+void launch_nn_partial(const RegDesc *descs, int batch, int max_n, int qpt, int splits, int pass, int filter,
+                       cudaStream_t s)
 {
     dim3 block(kNnThreads);
-    if (qpt == 8) {
-        dim3 grid((max_n + kNnThreads * 8 - 1) / (kNnThreads * 8), splits, batch);
-        nn_partial_kernel<8><<<grid, block, 0, s>>>(descs, splits, pass);
-    } else if (qpt == 4) {
-        dim3 grid((max_n + kNnThreads * 4 - 1) / (kNnThreads * 4), splits, batch);
-        nn_partial_kernel<4><<<grid, block, 0, s>>>(descs, splits, pass);
+    dim3 grid((max_n + kNnThreads * qpt - 1) / (kNnThreads * qpt), splits, batch);
+    if (filter == kFilterCentred) {
+        switch (qpt) {
+        case 16: launch_centred<16>(grid, descs, splits, pass, s); break;
+        case 12: launch_centred<12>(grid, descs, splits, pass, s); break;
+        case 8: launch_centred<8>(grid, descs, splits, pass, s); break;
+        case 4: launch_centred<4>(grid, descs, splits, pass, s); break;
+        default: launch_centred<2>(grid, descs, splits, pass, s); break;
+        }
     } else {
-        dim3 grid((max_n + kNnThreads * 2 - 1) / (kNnThreads * 2), splits, batch);
-        nn_partial_kernel<2><<<grid, block, 0, s>>>(descs, splits, pass);
+        switch (qpt) {
+        case 8: nn_partial_kernel<8><<<grid, block, 0, s>>>(descs, splits, pass); break;
+        case 4: nn_partial_kernel<4><<<grid, block, 0, s>>>(descs, splits, pass); break;
+        default: nn_partial_kernel<2><<<grid, block, 0, s>>>(descs, splits, pass); break;
+        }
     }
 }
 
@@ -570,7 +769,7 @@ __device__ __forceinline__ void solve_step_local(IcpState *st, const IcpParamsDe
 // --------------------------------------------------------------------------
 __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__restrict__ descs,
                                                              const IcpParamsDev *__restrict__ prm, int splits,
-                                                             int pass)
+                                                             int pass, int filter)
 {
     const RegDesc d = descs[blockIdx.z]; // by value: no pointer reloads after stores
     IcpState *st = d.st;
@@ -605,34 +804,59 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
         // ICPB_NN_GRID: nn_grid_kernel already resolved (idx, dist) exactly
         if (valid) { best_i = d.idx[i]; best_d = d.dist[i]; }
     } else {
-        // ---- combine the per-split (best, second-best, group) records, ascending split order
-        float m1 = CUDART_INF_F, m2 = CUDART_INF_F;
-        int g = 0;
+        // ---- combine the per-split records (ascending split order) into the three best group minima;
+        //      id -1 = "some group other than the ones named" (a bound without an address)
+        float m1 = CUDART_INF_F, m2 = CUDART_INF_F, m3 = CUDART_INF_F;
+        int g = 0, g2 = -1;
+        auto insert = [&](float v, int id) {
+            if (v < m1) { m3 = m2; m2 = m1; g2 = g; m1 = v; g = id; }
+            else if (v < m2) { m3 = m2; m2 = v; g2 = id; }
+            else if (v < m3) m3 = v;
+        };
         if (valid) {
             // loads first (independent, batched), then the order-dependent combine on registers
             constexpr int kB = 8;
             for (int s0 = 0; s0 < splits; s0 += kB) {
-                float p1[kB], p2[kB];
-                int pgv[kB];
+                float p1[kB], p2[kB], p3[kB];
+                int pgv[kB], pgw[kB];
     #pragma unroll
                 for (int k = 0; k < kB; ++k) {
                     const int s = min(s0 + k, splits - 1);
                     const size_t o = (size_t)s * d.n_stride + i;
                     p1[k] = __ldcg(&d.pm1[o]); p2[k] = __ldcg(&d.pm2[o]); pgv[k] = __ldcg(&d.pg[o]);
+                    if (filter == kFilterCentred) { p3[k] = __ldcg(&d.pm3[o]); pgw[k] = __ldcg(&d.pg2[o]); }
+                    else { p3[k] = CUDART_INF_F; pgw[k] = -1; }
                 }
     #pragma unroll
                 for (int k = 0; k < kB; ++k) {
                     if (s0 + k < splits) {
-                        m2 = fminf(fminf(m2, p2[k]), fmaxf(m1, p1[k]));
-                        if (p1[k] < m1) { m1 = p1[k]; g = pgv[k]; }
+                        insert(p1[k], pgv[k]);
+                        insert(p2[k], pgw[k]);
+                        insert(p3[k], -1);
                     }
                 }
             }
         }
-        bool ambiguous = valid && !(m2 > m1 * kBandRel + kBandAbs);
+        // is every target outside the best group (or the best two) provably farther, in the reference's
+        // arithmetic, than the best target?
+        float band;
+        if (filter == kFilterCentred) {
+            // m1..m3 are W = |a-t|^2 - A; bound derived at nn_partial_centred_kernel
+            const float A = valid ? __ldcg(&d.pa[i]) * 1.000001f : 0.f;
+            const float X = fmaxf(m1 + A, 0.f);
+            band = (A * kBandCentredA + X * kBandCentredX) + kBandAbs;
+        } else {
+            band = m1 * (kBandRel - 1.0f) + kBandAbs;
+        }
+        const float lim = m1 + band;
+        const bool one = m2 > lim;                                  // the best group alone decides
+        const bool two = !one && g2 >= 0 && g >= 0 && m3 > lim;     // the best two groups decide
+        const bool ambiguous = valid && !(one || two);
         if (valid && !ambiguous) {
-            // exact re-evaluation of the winning group (reference arithmetic, ascending index, strict <)
-            const int t0 = g * kGroup;
+            // exact re-evaluation (reference arithmetic, ascending index, strict <) of the deciding group(s)
+            const int ga = two ? min(g, g2) : g;
+            const int gbb = two ? max(g, g2) : -1;
+            int t0 = ga * kGroup;
             float4 b = d.tgt[t0];
             best_d = exact_distance(a.x, a.y, a.z, b.x, b.y, b.z);
             best_i = t0;
@@ -642,6 +866,16 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
                 b = d.tgt[min(t, m - 1)];
                 float dd = exact_distance(a.x, a.y, a.z, b.x, b.y, b.z);
                 if (t < m && dd < best_d) { best_d = dd; best_i = t; }
+            }
+            if (gbb >= 0) {
+                t0 = gbb * kGroup;
+    #pragma unroll 8
+                for (int k = 0; k < kGroup; ++k) {
+                    const int t = t0 + k;
+                    b = d.tgt[min(t, m - 1)];
+                    float dd = exact_distance(a.x, a.y, a.z, b.x, b.y, b.z);
+                    if (t < m && dd < best_d) { best_d = dd; best_i = t; }
+                }
             }
         }
         if (ambiguous) {
@@ -767,10 +1001,10 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
 }
 
 void launch_nn_finalize(const RegDesc *descs, const IcpParamsDev *prm, int batch, int max_n, int splits, int pass,
-                        cudaStream_t s)
+                        int filter, cudaStream_t s)
 {
     dim3 grid((max_n + kChunk - 1) / kChunk, 1, batch);
-    nn_finalize_kernel<<<grid, kChunk, 0, s>>>(descs, prm, splits, pass);
+    nn_finalize_kernel<<<grid, kChunk, 0, s>>>(descs, prm, splits, pass, filter);
 }
 
 // --------------------------------------------------------------------------

@@ -397,6 +397,7 @@ cv::Mat getTransformation(cv::Mat &data, cv::Mat &previous, cv::Mat color, std::
     prm.dist_trace = nullptr;
     prm.nn_mode = ICPB_NN_BRUTE;
     prm.grid_cell = 0.f;
+    prm.nn_filter = ICPB_FILTER_CENTRED;
     icpb_icp_result res;
     cv::Mat rigid(4, 4, CV_32FC1);
     if (dataCloud.points.empty() || previousCloud.points.empty()) {

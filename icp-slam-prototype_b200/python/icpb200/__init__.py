@@ -24,6 +24,7 @@ SUB_NONE, SUB_STRIDE, SUB_HASH, SUB_STREAM = 0, 1, 2, 3
 SOLVE_REFERENCE, SOLVE_KABSCH = 0, 1
 RULE_A, RULE_C = 0, 1
 NN_BRUTE, NN_GRID, NN_AUTO = 0, 1, 2
+FILTER_CENTRED, FILTER_DIRECT = 0, 1
 TRACK_INIT, TRACK_ASSOC, TRACK_NONASSOC = 0, 1, 2
 
 
@@ -41,7 +42,8 @@ class Intrinsics(C.Structure):
 class IcpParams(C.Structure):
     _fields_ = [("max_iterations", C.c_int), ("threshold", C.c_float), ("max_nn_distance", C.c_float),
                 ("solve_mode", C.c_int), ("last_translation", C.c_float * 3),
-                ("idx_trace", C.c_void_p), ("dist_trace", C.c_void_p), ("nn_mode", C.c_int), ("grid_cell", C.c_float)]
+                ("idx_trace", C.c_void_p), ("dist_trace", C.c_void_p), ("nn_mode", C.c_int), ("grid_cell", C.c_float),
+                ("nn_filter", C.c_int)]
 
 
 class IcpResult(C.Structure):
@@ -50,7 +52,8 @@ class IcpResult(C.Structure):
                 ("offset", C.c_float * 3), ("pose_R", C.c_double * 9), ("pose_t", C.c_double * 3),
                 ("small_assoc_exit", C.c_int), ("exact_rescans", C.c_int), ("gpu_ms", C.c_float),
                 ("kernel_launches", C.c_int), ("nn_partial_ms", C.c_float), ("nn_partial_launches", C.c_int),
-                ("nn_qpt", C.c_int), ("nn_splits", C.c_int), ("nn_mode_used", C.c_int), ("grid_cell_used", C.c_float)]
+                ("nn_qpt", C.c_int), ("nn_splits", C.c_int), ("nn_mode_used", C.c_int), ("grid_cell_used", C.c_float),
+                ("nn_filter_used", C.c_int)]
 
     def to_dict(self):
         return {
@@ -64,7 +67,7 @@ class IcpResult(C.Structure):
             "gpu_ms": self.gpu_ms, "kernel_launches": self.kernel_launches,
             "nn_partial_ms": self.nn_partial_ms, "nn_partial_launches": self.nn_partial_launches,
             "nn_qpt": self.nn_qpt, "nn_splits": self.nn_splits, "nn_mode_used": self.nn_mode_used,
-            "grid_cell_used": self.grid_cell_used,
+            "grid_cell_used": self.grid_cell_used, "nn_filter_used": self.nn_filter_used,
         }
 
 
@@ -205,10 +208,10 @@ class Context:
 
     def icp_register(self, data, target, max_iterations=20, threshold=0.0, max_nn_distance=0.75,
                      solve_mode=SOLVE_REFERENCE, last_translation=(0, 0, 0), trace=False, nn_mode=NN_BRUTE,
-                     grid_cell=0.0):
+                     grid_cell=0.0, nn_filter=FILTER_CENTRED):
         it = dt = None
         prm = IcpParams(max_iterations, threshold, max_nn_distance, solve_mode, (C.c_float * 3)(*last_translation),
-                        None, None, nn_mode, grid_cell)
+                        None, None, nn_mode, grid_cell, nn_filter)
         if trace:
             it = np.full((max_iterations + 1, data.n), -1, dtype=np.int32)
             dt = np.zeros((max_iterations + 1, data.n), dtype=np.float32)
@@ -222,7 +225,7 @@ class Context:
                            solve_mode=SOLVE_REFERENCE):
         n = len(datas)
         prm = IcpParams(max_iterations, threshold, max_nn_distance, solve_mode, (C.c_float * 3)(0, 0, 0), None, None,
-                        NN_BRUTE, 0.0)
+                        NN_BRUTE, 0.0, FILTER_CENTRED)
         dh = (C.c_void_p * n)(*[d.h for d in datas])
         th = (C.c_void_p * n)(*[t.h for t in targets])
         res = (IcpResult * n)()

@@ -70,6 +70,11 @@ enum { ICPB_SOLVE_REFERENCE = 0, /* icp.cpp:199-246: uncentred SVD, offset = mea
 enum { ICPB_NN_BRUTE = 0, ICPB_NN_GRID = 1,
        ICPB_NN_AUTO = 2 }; /* GRID when n*m is large enough for the bucketing to pay off, else BRUTE */
 
+/* Approximate FP32 filter in front of the exact re-evaluation of the BRUTE scan (never visible in the results):
+ * CENTRED evaluates |t'|^2 - 2a'.t' about a per-thread centre (3 FMA per pair), DIRECT evaluates (a-t)^2 (6 FP32
+ * operations per pair; kept for A/B measurements). */
+enum { ICPB_FILTER_CENTRED = 0, ICPB_FILTER_DIRECT = 1 };
+
 enum { ICPB_RULE_A = 0,  /* map.cpp:249-253 / 104-113 */
        ICPB_RULE_C = 1 };/* map.cpp:139-149 */
 
@@ -83,6 +88,7 @@ typedef struct {
     float *dist_trace;         /* optional host buffer, same shape */
     int nn_mode;               /* ICPB_NN_BRUTE (default 0) or ICPB_NN_GRID */
     float grid_cell;           /* ICPB_NN_GRID: cell edge in metres (0 = chosen from the target's density) */
+    int nn_filter;             /* ICPB_FILTER_CENTRED (default 0) or ICPB_FILTER_DIRECT; env ICPB_NN_FILTER overrides */
 } icpb_icp_params;
 
 typedef struct {
@@ -105,6 +111,7 @@ typedef struct {
     int nn_qpt, nn_splits;  /* work decomposition chosen for nn_partial */
     int nn_mode_used;       /* ICPB_NN_BRUTE or ICPB_NN_GRID */
     float grid_cell_used;
+    int nn_filter_used;     /* ICPB_FILTER_* of the BRUTE scan */
 } icpb_icp_result;
 
 /* ---- library / context ------------------------------------------------- */

@@ -88,3 +88,38 @@ def test_nn_empty_cloud_is_an_error(ctx, orc):
     with pytest.raises(icpb200.IcpbError) as e:
         ctx.nn_search(dc, tc)
     assert e.value.status == icpb200.ERR_EMPTY
+
+
+def test_nn_spread_queries_with_near_ties(ctx, orc):
+    """Worst case for the centred filter: the queries one thread owns are metres apart (large |a - c|^2, hence a
+    wide error band) and every query sees many targets at radii that differ by a few float ulps.  The band must
+    flag those queries for exact evaluation; results stay bit-exact."""
+    rng = np.random.default_rng(10)
+    centres = np.array([[3.0, 3.5, 4.0], [8.0, 7.5, 3.0], [5.5, 2.5, 7.75]], np.float32)
+    n = 768
+    data = orc.make_points(centres[np.arange(n) % 3] + rng.normal(0, 1e-4, (n, 3)).astype(np.float32))
+    tg = []
+    for c in centres:
+        dirs = rng.standard_normal((1500, 3))
+        dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+        radius = 0.05 * (1.0 + rng.integers(0, 6, 1500) * 2.0 ** -23)
+        tg.append(c + dirs * radius[:, None])
+    target = orc.make_points(np.concatenate(tg).astype(np.float32)[rng.permutation(4500)])
+    _check(ctx, orc, data, target, expect_rescans=lambda r: r > 0)
+
+
+def test_nn_surface_like_clouds_rarely_rescan(ctx, orc, pair10k):
+    """On Kinect-shaped clouds the three-best-group records settle almost every query without the full exact scan."""
+    data, target = pair10k
+    resc = _check(ctx, orc, data, target)
+    assert resc < len(data) // 100, resc
+
+
+@pytest.mark.parametrize("flt", ["0", "1"])
+def test_nn_both_filters_are_exact(ctx, orc, monkeypatch, flt):
+    """ICPB_FILTER_CENTRED (default) and ICPB_FILTER_DIRECT feed the same exact resolution."""
+    monkeypatch.setenv("ICPB_NN_FILTER", flt)
+    rng = np.random.default_rng(11)
+    data = orc.make_points(rng.uniform(3, 8, (3001, 3)))
+    target = orc.make_points(rng.uniform(3, 8, (5003, 3)))
+    _check(ctx, orc, data, target)
