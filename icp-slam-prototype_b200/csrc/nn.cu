@@ -804,8 +804,9 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
         // ICPB_NN_GRID: nn_grid_kernel already resolved (idx, dist) exactly
         if (valid) { best_i = d.idx[i]; best_d = d.dist[i]; }
     } else {
-        // ---- combine the per-split records (ascending split order) into the three best group minima;
-        //      id -1 = "some group other than the ones named" (a bound without an address)
+        // ---- combine the per-split records into the three best group minima; id -1 = "some group other than
+        //      the ones named" (a bound without an address).  Only the three splits with the smallest best value
+        //      can contribute: the best split its three records, the second its first two, the third its first.
         float m1 = CUDART_INF_F, m2 = CUDART_INF_F, m3 = CUDART_INF_F;
         int g = 0, g2 = -1;
         auto insert = [&](float v, int id) {
@@ -814,28 +815,43 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
             else if (v < m3) m3 = v;
         };
         if (valid) {
-            // loads first (independent, batched), then the order-dependent combine on registers
+            float a1 = CUDART_INF_F, a2 = CUDART_INF_F, a3 = CUDART_INF_F;
+            int s1 = -1, s2 = -1, s3 = -1;
             constexpr int kB = 8;
             for (int s0 = 0; s0 < splits; s0 += kB) {
-                float p1[kB], p2[kB], p3[kB];
-                int pgv[kB], pgw[kB];
+                float p1[kB];
+    #pragma unroll
+                for (int k = 0; k < kB; ++k) // independent loads, issued together
+                    p1[k] = __ldcg(&d.pm1[(size_t)min(s0 + k, splits - 1) * d.n_stride + i]);
     #pragma unroll
                 for (int k = 0; k < kB; ++k) {
-                    const int s = min(s0 + k, splits - 1);
-                    const size_t o = (size_t)s * d.n_stride + i;
-                    p1[k] = __ldcg(&d.pm1[o]); p2[k] = __ldcg(&d.pm2[o]); pgv[k] = __ldcg(&d.pg[o]);
-                    if (filter == kFilterCentred) { p3[k] = __ldcg(&d.pm3[o]); pgw[k] = __ldcg(&d.pg2[o]); }
-                    else { p3[k] = CUDART_INF_F; pgw[k] = -1; }
-                }
-    #pragma unroll
-                for (int k = 0; k < kB; ++k) {
-                    if (s0 + k < splits) {
-                        insert(p1[k], pgv[k]);
-                        insert(p2[k], pgw[k]);
-                        insert(p3[k], -1);
+                    const float v = p1[k];
+                    const int sp = s0 + k;
+                    if (sp < splits) {
+                        if (v < a1 || s1 < 0) { a3 = a2; s3 = s2; a2 = a1; s2 = s1; a1 = v; s1 = sp; }
+                        else if (v < a2 || s2 < 0) { a3 = a2; s3 = s2; a2 = v; s2 = sp; }
+                        else if (v < a3 || s3 < 0) { a3 = v; s3 = sp; }
                     }
                 }
             }
+            const bool top3 = filter == kFilterCentred;
+            const size_t o1 = (size_t)s1 * d.n_stride + i;
+            const size_t o2 = (size_t)max(s2, 0) * d.n_stride + i;
+            const size_t o3 = (size_t)max(s3, 0) * d.n_stride + i;
+            const int ga = __ldcg(&d.pg[o1]);
+            const float p2a = __ldcg(&d.pm2[o1]);
+            const int g2a = top3 ? __ldcg(&d.pg2[o1]) : -1;
+            const float p3a = top3 ? __ldcg(&d.pm3[o1]) : CUDART_INF_F;
+            const int gb = __ldcg(&d.pg[o2]);
+            const float p2b = __ldcg(&d.pm2[o2]);
+            const int g2b = top3 ? __ldcg(&d.pg2[o2]) : -1;
+            const int gc = __ldcg(&d.pg[o3]);
+            insert(a1, ga);
+            insert(p2a, g2a);
+            insert(p3a, -1);
+            if (s2 >= 0) { insert(a2, gb); insert(p2b, g2b); }
+            if (s3 >= 0) insert(a3, gc);
+            if (m1 == CUDART_INF_F) g = ga; // nothing finite anywhere (NaN / overflow inputs): keep a valid address
         }
         // is every target outside the best group (or the best two) provably farther, in the reference's
         // arithmetic, than the best target?
