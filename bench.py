@@ -321,8 +321,8 @@ def run_b200(args, rank, world, local):
                          "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one nn_partial launch at this workload, from the
-                         # ncu --set full capture summarised in profiles/r01_ncu_nn_partial_fullres.txt (targets stay in L2)
-                         "traffic": 8211200 if not wl["points"] else None,
+                         # ncu --set full capture summarised in profiles/r01_ncu_nn_centred_fullres.txt (targets stay in L2; 8.2 MB read + 17.6 MB of per-split records written)
+                         "traffic": 25856768 if not wl["points"] else None,
                          "peak_source": "FFMA micro-benchmark measured in this run (MEASURED_PEAKS.json holds "
                                         "only HBM and bf16 tensor peaks; the NN scan is FP32 CUDA-core bound)",
                          "flop_per_launch": flop_per_launch, "avg_launch_ms": avg_launch_s * 1e3,
