@@ -1,6 +1,7 @@
 // C-ABI of libicpb200.so (include/icpb200.h): contexts, handles, host-side
 // orchestration of the kernels in nn.cu / cloud.cu / map.cu.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1144,6 +1145,82 @@ int icpb_map_upload(icpb_map *map, const uint8_t *in, long long size)
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaMemcpyAsync(map->dev.grid, in, (size_t)size, cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return ICPB_OK;
+}
+
+// ---- pose reporting (8f-4): scalar host arithmetic, as in the reference ------------------------------------
+// Separately rounded float operations throughout (host code of this file is built with -ffp-contract=off).
+namespace {
+inline float sign_of(float v) { return v >= 0.0f ? 1.0f : -1.0f; } // SIGN, quaternion.hpp:22
+constexpr float kPiF = 3.14159265358979f;                            // PI, icp.hpp:4
+} // namespace
+
+int icpb_pose_quat_from_rotation(const float R[9], float q[4]) // quaternion.cpp:23-79
+{
+    if (!R || !q) return ICPB_ERR_INVALID;
+    const float tr[4] = {(R[0] + R[4] + R[8] + 1.0f) / 4.0f, (R[0] - R[4] - R[8] + 1.0f) / 4.0f,
+                         (-R[0] + R[4] - R[8] + 1.0f) / 4.0f, (-R[0] - R[4] + R[8] + 1.0f) / 4.0f};
+    float c[4]; // magnitudes of w, x, y, z
+    for (int k = 0; k < 4; ++k) c[k] = sqrtf(tr[k] < 0.0f ? 0.0f : tr[k]);
+    // antisymmetric / symmetric off-diagonal combinations that carry the signs
+    const float a_x = R[7] - R[5], a_y = R[2] - R[6], a_z = R[3] - R[1];
+    const float s_xy = R[3] + R[1], s_xz = R[2] + R[6], s_yz = R[7] + R[5];
+    if (c[0] >= c[1] && c[0] >= c[2] && c[0] >= c[3]) {        // w largest: signs from the antisymmetric part
+        c[1] *= sign_of(a_x); c[2] *= sign_of(a_y); c[3] *= sign_of(a_z);
+    } else if (c[1] >= c[0] && c[1] >= c[2] && c[1] >= c[3]) { // x largest
+        c[0] *= sign_of(a_x); c[2] *= sign_of(s_xy); c[3] *= sign_of(s_xz);
+    } else if (c[2] >= c[0] && c[2] >= c[1] && c[2] >= c[3]) { // y largest
+        c[0] *= sign_of(a_y); c[1] *= sign_of(s_xy); c[3] *= sign_of(s_yz);
+    } else if (c[3] >= c[0] && c[3] >= c[1] && c[3] >= c[2]) { // z largest
+        c[0] *= sign_of(a_z); c[1] *= sign_of(s_xz); c[2] *= sign_of(s_yz);
+    }
+    const float len = sqrtf(c[0] * c[0] + c[1] * c[1] + c[2] * c[2] + c[3] * c[3]); // NORM, quaternion.hpp:23
+    for (int k = 0; k < 4; ++k) q[k] = c[k] / len;
+    return ICPB_OK;
+}
+
+int icpb_pose_quat_mul(const float a[4], const float b[4], float out[4]) // quaternion.cpp:184-192
+{
+    if (!a || !b || !out) return ICPB_ERR_INVALID;
+    const float t[4] = {a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3],
+                        a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                        a[0] * b[2] + a[2] * b[0] + a[3] * b[1] - a[1] * b[3],
+                        a[0] * b[3] + a[3] * b[0] + a[1] * b[2] - a[2] * b[1]};
+    for (int k = 0; k < 4; ++k) out[k] = t[k];
+    return ICPB_OK;
+}
+
+int icpb_pose_quat_inverse(const float q[4], float out[4]) // quaternion.cpp:325-328: conjugate scaled by 1 / squared norm
+{
+    if (!q || !out) return ICPB_ERR_INVALID;
+    const float inv = 1 / (q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    const float t[4] = {q[0] * inv, -q[1] * inv, -q[2] * inv, -q[3] * inv};
+    for (int k = 0; k < 4; ++k) out[k] = t[k];
+    return ICPB_OK;
+}
+
+int icpb_pose_quat_to_euler_deg(const float q[4], float e[3]) // SLAM.cpp:613-636
+{
+    if (!q || !e) return ICPB_ERR_INVALID;
+    const float w = q[0], x = q[1], y = q[2], z = q[3];
+    const float yy = y * y;
+    const float roll = atan2f(2.0f * (w * x + y * z), 1.0f - 2.0f * (x * x + yy));
+    float sp = 2.0f * (w * y - z * x);
+    sp = sp > 1.0f ? 1.0f : sp;
+    sp = sp < -1.0f ? -1.0f : sp;
+    const float pitch = asinf(sp);
+    const float yaw = atan2f(2.0f * (w * z + x * y), 1.0f - 2.0f * (yy + z * z));
+    e[0] = roll * 180.0f / kPiF; e[1] = pitch * 180.0f / kPiF; e[2] = yaw * 180.0f / kPiF;
+    return ICPB_OK;
+}
+
+int icpb_pose_matrix_to_euler_deg(const float R[9], float e[3]) // SLAM.cpp:638-648
+{
+    if (!R || !e) return ICPB_ERR_INVALID;
+    const float c2 = (float)sqrt((double)R[0] * (double)R[0] + (double)R[1] * (double)R[1]); // pow(float, 2): double
+    e[0] = atan2f(R[5], R[8]) * 180 / kPiF;
+    e[1] = atan2f(-R[2], c2) * 180 / kPiF;
+    e[2] = atan2f(R[1], R[0]) * 180 / kPiF;
     return ICPB_OK;
 }
 

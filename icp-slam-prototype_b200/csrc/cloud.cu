@@ -103,6 +103,9 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *s
 // ordinal among NON-ZERO pixels (consumed by the subsample rule exactly where
 // the reference consumes one rand(), pointcloud.cpp:22-28) and the output
 // position among KEPT pixels (raster order == push_back order, :54).
+// Specialised on the subsample rule and on the presence of a colour image: the per-pixel keep decision
+// compiles to nothing for ICPB_SUB_NONE, and no integer division is carried by rules that do not use one.
+template <int RULE, bool HAS_BGR>
 __global__ void __launch_bounds__(kBpThreads) backproject_kernel(BackprojectArgs a, uint32_t epoch)
 {
     // batched launch: frame = blockIdx.y, every per-frame pointer advances by its stride
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(kBpThreads) backproject_kernel(BackprojectArgs
     for (int k = 0; k < kBpPix; ++k) nvalid += (dpx[k] != 0);
 
     // the ordinal among non-zero pixels is only consumed by the STRIDE / STREAM rules: skip that scan otherwise
-    const bool need_ordinal = (a.rule == ICPB_SUB_STRIDE) || (a.rule == ICPB_SUB_STREAM);
+    constexpr bool need_ordinal = (RULE == ICPB_SUB_STRIDE) || (RULE == ICPB_SUB_STREAM);
     const unsigned long long tag = (unsigned long long)(epoch << 2) << 32;
     uint32_t v_base = 0;
     if (need_ordinal) {
@@ -177,13 +180,10 @@ __global__ void __launch_bounds__(kBpThreads) backproject_kernel(BackprojectArgs
 #pragma unroll
     for (int k = 0; k < kBpPix; ++k) {
         if (dpx[k] != 0) {
-            bool keep;
-            switch (a.rule) {
-            case ICPB_SUB_STRIDE: keep = (ord % rule_arg) == 0; break;
-            case ICPB_SUB_HASH: keep = (hash32(a.seed, (uint32_t)(p0 + k)) % rule_arg) == 0; break;
-            case ICPB_SUB_STREAM: keep = (ord < (uint32_t)a.keep_stream_len) && a.keep_stream[ord] != 0; break;
-            default: keep = true; break;
-            }
+            bool keep = true;
+            if (RULE == ICPB_SUB_STRIDE) keep = (ord % rule_arg) == 0;
+            else if (RULE == ICPB_SUB_HASH) keep = (hash32(a.seed, (uint32_t)(p0 + k)) % rule_arg) == 0;
+            else if (RULE == ICPB_SUB_STREAM) keep = (ord < (uint32_t)a.keep_stream_len) && a.keep_stream[ord] != 0;
             if (keep) keep_mask |= 1u << k;
             ++ord;
         }
@@ -210,18 +210,30 @@ __global__ void __launch_bounds__(kBpThreads) backproject_kernel(BackprojectArgs
     uint32_t lo = k_off;
     // pointcloud.cpp:37-39 (134-136): all float, left to right, true division
     {
+        // the thread's 8 BGR triples: 24 bytes, 8-byte aligned when the image base is -> three 8-byte loads
+        uint32_t cw[6] = {0, 0, 0, 0, 0, 0};
+        if (HAS_BGR && keep_mask) {
+            const uint8_t *c = a.bgr + (size_t)p0 * 3;
+            if (p0 + kBpPix <= npx && ((reinterpret_cast<uintptr_t>(c) & 7) == 0)) {
+                const uint2 *c2 = reinterpret_cast<const uint2 *>(c);
+                const uint2 w0 = c2[0], w1 = c2[1], w2 = c2[2];
+                cw[0] = w0.x; cw[1] = w0.y; cw[2] = w1.x; cw[3] = w1.y; cw[4] = w2.x; cw[5] = w2.y;
+            } else {
+                for (int b = 0; b < 3 * kBpPix; ++b)
+                    if (p0 * 3 + b < npx * 3) cw[b >> 2] |= (uint32_t)c[b] << (8 * (b & 3));
+            }
+        }
         int v = p0 / a.w, u = p0 - v * a.w;
 #pragma unroll
         for (int k = 0; k < kBpPix; ++k) {
             if (keep_mask & (1u << k)) {
-                const int p = p0 + k;
                 float pz = ((float)dpx[k]) / a.K.depth_scale;
                 float px = ((float)u - a.K.cx_u) * pz / a.K.fx_u;
                 float py = ((float)v - a.K.cx_v) * pz / a.K.fx_v;
                 uint32_t cbits = 0;
-                if (a.bgr) {
-                    const uint8_t *c = a.bgr + (size_t)p * 3;
-                    cbits = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16); // :47
+                if (HAS_BGR) { // bytes 3k .. 3k+2 of the 24-byte run (:47): a funnel shift across two words
+                    const int w = (3 * k) >> 2, sh = 8 * ((3 * k) & 3);
+                    cbits = __funnelshift_r(cw[w], w + 1 < 6 ? cw[w + 1] : 0u, sh) & 0x00ffffffu;
                 }
                 s_pts[lo++] = make_float4(px, py, pz, __uint_as_float(cbits));
             }
@@ -242,7 +254,18 @@ void launch_backproject(const BackprojectArgs &a, cudaStream_t s)
     epoch = (epoch + 1) & 0x3fffffffu;
     if (epoch == 0) epoch = 1;
     dim3 grid(a.n_tiles, a.frames > 0 ? a.frames : 1);
-    backproject_kernel<<<grid, kBpThreads, 0, s>>>(a, epoch);
+#define ICPB_BP_LAUNCH(R)                                                                           \
+    do {                                                                                            \
+        if (a.bgr) backproject_kernel<R, true><<<grid, kBpThreads, 0, s>>>(a, epoch);               \
+        else backproject_kernel<R, false><<<grid, kBpThreads, 0, s>>>(a, epoch);                    \
+    } while (0)
+    switch (a.rule) {
+    case ICPB_SUB_STRIDE: ICPB_BP_LAUNCH(ICPB_SUB_STRIDE); break;
+    case ICPB_SUB_HASH: ICPB_BP_LAUNCH(ICPB_SUB_HASH); break;
+    case ICPB_SUB_STREAM: ICPB_BP_LAUNCH(ICPB_SUB_STREAM); break;
+    default: ICPB_BP_LAUNCH(ICPB_SUB_NONE); break;
+    }
+#undef ICPB_BP_LAUNCH
 }
 
 // P3, SLAM.cpp:412-430.  Central differences on raw depth units; normalize as

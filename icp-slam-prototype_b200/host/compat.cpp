@@ -552,3 +552,52 @@ int Map::bound(int t, int ds) // map.cpp:209-217 (always 1/ds; unused by the ref
 }
 
 } // namespace map
+
+// ================================================================ quaternion.hpp / SLAM.hpp pose reporting (8f-4)
+#include "icpb200/quaternion.hpp"
+
+Quaternion::Quaternion(void) : x(0), y(0), z(0), w(0) {}                                          // quaternion.cpp:15-21
+Quaternion::Quaternion(float wi, float xi, float yi, float zi) : x(xi), y(yi), z(zi), w(wi) {}    // :87-93
+Quaternion::Quaternion(float v[4]) : x(v[1]), y(v[2]), z(v[3]), w(v[0]) {}                         // :100-106
+Quaternion::Quaternion(cv::Mat rotationMatrix)                                                   // :23-79
+{
+    float R[9], q[4];
+    for (int k = 0; k < 9; ++k) R[k] = rotationMatrix.at<float>(k / 3, k % 3);
+    icpb_pose_quat_from_rotation(R, q);
+    w = q[0]; x = q[1]; y = q[2]; z = q[3];
+}
+Quaternion Quaternion::operator*(const Quaternion &q) // :184-192
+{
+    const float a[4] = {w, x, y, z}, b[4] = {q.w, q.x, q.y, q.z};
+    float o[4];
+    icpb_pose_quat_mul(a, b, o);
+    return Quaternion(o[0], o[1], o[2], o[3]);
+}
+bool Quaternion::operator==(const Quaternion &q) { return w == q.w && x == q.x && y == q.y && z == q.z; } // :285-288
+float Quaternion::norm() { return (w * w + x * x + y * y + z * z); }                                       // :294-297 (squared)
+float Quaternion::magnitude() { return sqrtf(norm()); }                                                    // :304-307
+Quaternion Quaternion::scale(float s) { return Quaternion(w * s, x * s, y * s, z * s); }                   // :314-317
+Quaternion Quaternion::conjugate() { return Quaternion(w, -x, -y, -z); }                                   // :335-338
+Quaternion Quaternion::inverse()                                                                           // :325-328
+{
+    const float a[4] = {w, x, y, z};
+    float o[4];
+    icpb_pose_quat_inverse(a, o);
+    return Quaternion(o[0], o[1], o[2], o[3]);
+}
+
+void toEulerianAngle(Quaternion q, float &x, float &y, float &z) // SLAM.cpp:613-636
+{
+    const float a[4] = {q.w, q.x, q.y, q.z};
+    float e[3];
+    icpb_pose_quat_to_euler_deg(a, e);
+    x = e[0]; y = e[1]; z = e[2];
+}
+
+void transformationMatToEulerianAngle(cv::Mat t, float &x, float &y, float &z) // SLAM.cpp:638-648
+{
+    float R[9], e[3];
+    for (int k = 0; k < 9; ++k) R[k] = t.at<float>(k / 3, k % 3);
+    icpb_pose_matrix_to_euler_deg(R, e);
+    x = e[0]; y = e[1]; z = e[2];
+}

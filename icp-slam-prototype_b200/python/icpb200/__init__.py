@@ -383,3 +383,46 @@ class Map:
     def upload(self, grid):
         grid = np.ascontiguousarray(grid, dtype=np.uint8)
         self.ctx.check(self.ctx.lib.icpb_map_upload(self.h, _p(grid), grid.size))
+
+
+# ---- pose reporting: scalar host functions of the library; q = [w, x, y, z], degrees -----------
+def _f32(a, n):
+    a = np.ascontiguousarray(a, dtype=np.float32).reshape(-1)
+    if a.size != n:
+        raise ValueError(f"expected {n} floats")
+    return a
+
+
+def pose_quat_from_rotation(R):
+    R = _f32(R, 9); q = np.zeros(4, np.float32)
+    if load().icpb_pose_quat_from_rotation(_p(R), _p(q)):
+        raise IcpbError(ERR_INVALID, "icpb_pose_quat_from_rotation")
+    return q
+
+
+def pose_quat_mul(a, b):
+    a = _f32(a, 4); b = _f32(b, 4); o = np.zeros(4, np.float32)
+    if load().icpb_pose_quat_mul(_p(a), _p(b), _p(o)):
+        raise IcpbError(ERR_INVALID, "icpb_pose_quat_mul")
+    return o
+
+
+def pose_quat_inverse(q):
+    q = _f32(q, 4); o = np.zeros(4, np.float32)
+    if load().icpb_pose_quat_inverse(_p(q), _p(o)):
+        raise IcpbError(ERR_INVALID, "icpb_pose_quat_inverse")
+    return o
+
+
+def pose_quat_to_euler_deg(q):
+    q = _f32(q, 4); e = np.zeros(3, np.float32)
+    if load().icpb_pose_quat_to_euler_deg(_p(q), _p(e)):
+        raise IcpbError(ERR_INVALID, "icpb_pose_quat_to_euler_deg")
+    return e
+
+
+def pose_matrix_to_euler_deg(R):
+    R = _f32(R, 9); e = np.zeros(3, np.float32)
+    if load().icpb_pose_matrix_to_euler_deg(_p(R), _p(e)):
+        raise IcpbError(ERR_INVALID, "icpb_pose_matrix_to_euler_deg")
+    return e

@@ -241,6 +241,15 @@ int icpb_map_download(icpb_map *map, uint8_t *out, long long capacity);
 int icpb_map_upload(icpb_map *map, const uint8_t *in, long long size);
 int icpb_map_size_bytes(const icpb_map *map, long long *size);
 
+/* ---- pose reporting ------------------------------------
+ * Scalar per-frame host arithmetic in the reference (SLAM.cpp:284-293); it stays host code here: no context,
+ * no device.  Quaternions are {w, x, y, z}; rotation matrices are row-major 3x3 float; angles are degrees. */
+int icpb_pose_quat_from_rotation(const float R[9], float q[4]);           /* Quaternion(cv::Mat), quaternion.cpp:23-79 */
+int icpb_pose_quat_mul(const float a[4], const float b[4], float out[4]); /* operator*, quaternion.cpp:184-192 */
+int icpb_pose_quat_inverse(const float q[4], float out[4]);               /* inverse(), quaternion.cpp:325-328 */
+int icpb_pose_quat_to_euler_deg(const float q[4], float e[3]);            /* toEulerianAngle, SLAM.cpp:613-636 */
+int icpb_pose_matrix_to_euler_deg(const float R[9], float e[3]);          /* transformationMatToEulerianAngle, SLAM.cpp:638-648 */
+
 #ifdef __cplusplus
 }
 #endif

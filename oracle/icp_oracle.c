@@ -738,3 +738,85 @@ long long orc_map_integrate_rays(uint8_t *grid, const int dims[3], float cell,
     }
     return visited;
 }
+
+
+/* ======================================================================== */
+/* 8f-4 pose reporting (scalar host code in the reference)                   */
+/* ======================================================================== */
+#define ORC_PI 3.14159265358979f /* icp.hpp:4 */
+
+static float orc_sign(float x) { return (x >= 0.0f) ? +1.0f : -1.0f; } /* quaternion.hpp:22 */
+
+/* Quaternion::Quaternion(cv::Mat), quaternion.cpp:23-79.  q = {w, x, y, z}. */
+void orc_quat_from_rot(const float R[9], float q[4])
+{
+    float r11 = R[0], r12 = R[1], r13 = R[2], r21 = R[3], r22 = R[4], r23 = R[5], r31 = R[6], r32 = R[7], r33 = R[8];
+    float w = (r11 + r22 + r33 + 1.0f) / 4.0f; /* :35-38 */
+    float x = (r11 - r22 - r33 + 1.0f) / 4.0f;
+    float y = (-r11 + r22 - r33 + 1.0f) / 4.0f;
+    float z = (-r11 - r22 + r33 + 1.0f) / 4.0f;
+    if (w < 0.0f) w = 0.0f; /* :40-43 */
+    if (x < 0.0f) x = 0.0f;
+    if (y < 0.0f) y = 0.0f;
+    if (z < 0.0f) z = 0.0f;
+    w = sqrtf(w); x = sqrtf(x); y = sqrtf(y); z = sqrtf(z); /* :44-47 */
+    if (w >= x && w >= y && w >= z) { /* :49-69 */
+        x *= orc_sign(r32 - r23); y *= orc_sign(r13 - r31); z *= orc_sign(r21 - r12);
+    } else if (x >= w && x >= y && x >= z) {
+        w *= orc_sign(r32 - r23); y *= orc_sign(r21 + r12); z *= orc_sign(r13 + r31);
+    } else if (y >= w && y >= x && y >= z) {
+        w *= orc_sign(r13 - r31); x *= orc_sign(r21 + r12); z *= orc_sign(r32 + r23);
+    } else if (z >= w && z >= x && z >= y) {
+        w *= orc_sign(r21 - r12); x *= orc_sign(r31 + r13); y *= orc_sign(r32 + r23);
+    }
+    float r = sqrtf(w * w + x * x + y * y + z * z); /* NORM, quaternion.hpp:23; :73-77 */
+    q[0] = w / r; q[1] = x / r; q[2] = y / r; q[3] = z / r;
+}
+
+/* Quaternion::operator*, quaternion.cpp:184-192 */
+void orc_quat_mul(const float a[4], const float b[4], float out[4])
+{
+    float w = a[0], x = a[1], y = a[2], z = a[3], qw = b[0], qx = b[1], qy = b[2], qz = b[3];
+    float o0 = w * qw - x * qx - y * qy - z * qz;
+    float o1 = w * qx + x * qw + y * qz - z * qy;
+    float o2 = w * qy + y * qw + z * qx - x * qz;
+    float o3 = w * qz + z * qw + x * qy - y * qx;
+    out[0] = o0; out[1] = o1; out[2] = o2; out[3] = o3;
+}
+
+/* Quaternion::inverse = conjugate().scale(1/norm()), quaternion.cpp:294-341 (norm() is the SQUARED norm, :294-297) */
+void orc_quat_inverse(const float q[4], float out[4])
+{
+    float n = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    float s = 1 / n;
+    out[0] = q[0] * s; out[1] = -q[1] * s; out[2] = -q[2] * s; out[3] = -q[3] * s;
+}
+
+/* toEulerianAngle, SLAM.cpp:613-636: degrees */
+void orc_quat_to_euler_deg(const float q[4], float e[3])
+{
+    float qw = q[0], qx = q[1], qy = q[2], qz = q[3];
+    float ysqr = qy * qy;
+    float t0 = 2.0f * (qw * qx + qy * qz);
+    float t1 = 1.0f - 2.0f * (qx * qx + ysqr);
+    float x = atan2f(t0, t1);
+    float t2 = +2.0f * (qw * qy - qz * qx);
+    t2 = t2 > 1.0f ? 1.0f : t2;
+    t2 = t2 < -1.0f ? -1.0f : t2;
+    float y = asinf(t2);
+    float t3 = +2.0f * (qw * qz + qx * qy);
+    float t4 = +1.0f - 2.0f * (ysqr + qz * qz);
+    float z = atan2f(t3, t4);
+    e[0] = x * 180.0f / ORC_PI; e[1] = y * 180.0f / ORC_PI; e[2] = z * 180.0f / ORC_PI;
+}
+
+/* transformationMatToEulerianAngle, SLAM.cpp:638-648: pow(float,2) promotes to double, sqrt(double), stored to float;
+ * `x * 180 / PI` is float * int -> float */
+void orc_mat_to_euler_deg(const float R[9], float e[3])
+{
+    float c2 = (float)sqrt((double)R[0] * (double)R[0] + (double)R[1] * (double)R[1]);
+    float x = atan2f(R[5], R[8]);
+    float y = atan2f(-R[2], c2);
+    float z = atan2f(R[1], R[0]);
+    e[0] = x * 180 / ORC_PI; e[1] = y * 180 / ORC_PI; e[2] = z * 180 / ORC_PI;
+}

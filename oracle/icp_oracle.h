@@ -119,6 +119,13 @@ long long orc_map_integrate_rays(uint8_t *grid, const int dims[3], float cell,
                                  const orc_point *pts, int n, const float origin[3],
                                  int delta_dec, int delta_inc, int z_lo, int z_hi);
 
+/* ---- 8f-4 pose reporting: quaternion.cpp:23-79,184-192,294-341; SLAM.cpp:613-648 (q = {w, x, y, z}) ---- */
+void orc_quat_from_rot(const float R[9], float q[4]);
+void orc_quat_mul(const float a[4], const float b[4], float out[4]);
+void orc_quat_inverse(const float q[4], float out[4]);
+void orc_quat_to_euler_deg(const float q[4], float e[3]);
+void orc_mat_to_euler_deg(const float R[9], float e[3]);
+
 #ifdef __cplusplus
 }
 #endif

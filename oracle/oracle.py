@@ -253,3 +253,40 @@ def map_integrate_rays(grid, dims, cell, pts, origin, delta_dec=25, delta_inc=25
         z_hi = dims[2]
     return int(lib().orc_map_integrate_rays(_p(grid), d, C.c_float(cell), _p(pts), len(pts), o, delta_dec,
                                             delta_inc, z_lo, z_hi))
+
+
+# ---- 8f-4 pose reporting (q = [w, x, y, z]) ------------------------------------------------------------------
+def _f(a, n):
+    a = np.ascontiguousarray(a, dtype=np.float32).reshape(-1)
+    assert a.size == n
+    return a
+
+
+def quat_from_rot(R):
+    R = _f(R, 9); q = np.zeros(4, np.float32)
+    lib().orc_quat_from_rot(_p(R), _p(q))
+    return q
+
+
+def quat_mul(a, b):
+    a = _f(a, 4); b = _f(b, 4); o = np.zeros(4, np.float32)
+    lib().orc_quat_mul(_p(a), _p(b), _p(o))
+    return o
+
+
+def quat_inverse(q):
+    q = _f(q, 4); o = np.zeros(4, np.float32)
+    lib().orc_quat_inverse(_p(q), _p(o))
+    return o
+
+
+def quat_to_euler_deg(q):
+    q = _f(q, 4); e = np.zeros(3, np.float32)
+    lib().orc_quat_to_euler_deg(_p(q), _p(e))
+    return e
+
+
+def mat_to_euler_deg(R):
+    R = _f(R, 9); e = np.zeros(3, np.float32)
+    lib().orc_mat_to_euler_deg(_p(R), _p(e))
+    return e

@@ -126,3 +126,23 @@ def icp_allpoints(data, target, max_iterations, threshold):
                                  C.c_float(threshold), _p(rigid), _p(camR), _p(camP), C.byref(mse_), C.byref(na))
     return {"iterations": it, "rigid": rigid.reshape(4, 4), "cam_rotation": camR.reshape(3, 3),
             "cam_position": camP, "mse": mse_.value, "n_assoc": na.value}, data
+
+
+# ---- 8f-4: the reference's own Quaternion class; q = [w, x, y, z]
+def quat_from_rot(R):
+    R = np.ascontiguousarray(R, dtype=np.float32).reshape(9); q = np.zeros(4, np.float32)
+    lib().ref_quat_from_rot(_p(R), _p(q))
+    return q
+
+
+def quat_mul(a, b):
+    a = np.ascontiguousarray(a, dtype=np.float32); b = np.ascontiguousarray(b, dtype=np.float32)
+    o = np.zeros(4, np.float32)
+    lib().ref_quat_mul(_p(a), _p(b), _p(o))
+    return o
+
+
+def quat_inverse(a):
+    a = np.ascontiguousarray(a, dtype=np.float32); o = np.zeros(4, np.float32)
+    lib().ref_quat_inverse(_p(a), _p(o))
+    return o

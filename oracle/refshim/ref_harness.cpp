@@ -189,4 +189,25 @@ int ref_icp_allpoints(ref_point *data, int n, const ref_point *target, int m, in
     return i;
 }
 
+// ---- 8f-4: the reference's own Quaternion class (quaternion.cpp, compiled by path); q = {w, x, y, z}
+void ref_quat_from_rot(const float *R9, float *q4) // quaternion.cpp:23-79
+{
+    cv::Mat R(3, 3, CV_32FC1);
+    for (int i = 0; i < 9; ++i) R.at<float>(i / 3, i % 3) = R9[i];
+    Quaternion q(R);
+    q4[0] = q.w; q4[1] = q.x; q4[2] = q.y; q4[3] = q.z;
+}
+void ref_quat_mul(const float *a, const float *b, float *o) // quaternion.cpp:184-192
+{
+    Quaternion qa(a[0], a[1], a[2], a[3]), qb(b[0], b[1], b[2], b[3]);
+    Quaternion r = qa * qb;
+    o[0] = r.w; o[1] = r.x; o[2] = r.y; o[3] = r.z;
+}
+void ref_quat_inverse(const float *a, float *o) // quaternion.cpp:325-328
+{
+    Quaternion qa(a[0], a[1], a[2], a[3]);
+    Quaternion r = qa.inverse();
+    o[0] = r.w; o[1] = r.x; o[2] = r.y; o[3] = r.z;
+}
+
 } // extern "C"

@@ -9,6 +9,7 @@
 #include "icpb200/icp.hpp"
 #include "icpb200/map.hpp"
 #include "icpb200/pointcloud.hpp"
+#include "icpb200/quaternion.hpp"
 
 static void dump(const std::string &path, const void *p, size_t bytes)
 {
@@ -99,6 +100,16 @@ int main(int argc, char **argv)
     for (int k = 0; k < 9; ++k) pose[k] = cr.at<float>(k / 3, k % 3);
     pose[9] = cp.x; pose[10] = cp.y; pose[11] = cp.z;
     dump(out + "/pose.bin", pose, sizeof(pose));
+    // pose reporting exactly as the frame loop writes it (SLAM.cpp:284-293)
+    {
+        Quaternion rotationQ = Quaternion(cr);
+        float e[10];
+        toEulerianAngle(rotationQ, e[0], e[1], e[2]);
+        transformationMatToEulerianAngle(cr, e[3], e[4], e[5]);
+        Quaternion d = rotationQ * rotationQ.inverse();
+        e[6] = d.w; e[7] = d.x; e[8] = d.y; e[9] = d.z;
+        dump(out + "/euler.bin", e, sizeof(e));
+    }
     printf("\ncompat ok: n_data=%zu n_target=%zu assoc=%zu\n", data.points.size(), target.points.size(), assoc.size());
     return 0;
 }

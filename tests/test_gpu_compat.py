@@ -133,3 +133,9 @@ def test_compat_program_matches_oracle(tmp_path, orc):
     pose = np.fromfile(o + "/pose.bin", f32)
     assert np.array_equal(pose[:9].reshape(3, 3), orc.gemm33f(camR, r2["cam_rotation"]))
     assert np.array_equal(pose[9:], (camP + r2["cam_position"]).astype(f32))
+    # pose reporting through the drop-in Quaternion / toEulerianAngle (SLAM.cpp:284-293)
+    eu = np.fromfile(o + "/euler.bin", f32)
+    q = orc.quat_from_rot(pose[:9])
+    assert np.array_equal(eu[0:3], orc.quat_to_euler_deg(q))
+    assert np.array_equal(eu[3:6], orc.mat_to_euler_deg(pose[:9]))
+    assert np.array_equal(eu[6:10], orc.quat_mul(q, orc.quat_inverse(q)))
