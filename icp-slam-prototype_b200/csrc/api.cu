@@ -18,7 +18,7 @@ thread_local std::string g_create_error;
 enum WsId {
     WS_DESCS = 0, WS_STATES, WS_PARAMS, WS_TGT_SOA, WS_PM1, WS_PM2, WS_PG, WS_IDX, WS_DIST, WS_CHUNKS, WS_ALT,
     WS_IDX_TRACE, WS_DIST_TRACE, WS_MISC, WS_DEPTH, WS_BGR, WS_KEEP, WS_TILESTATE, WS_IMG_A, WS_IMG_B, WS_NORMALS,
-    WS_RT, WS_GRID_META, WS_GRID_COUNTS, WS_GRID_CURSOR, WS_GRID_SUMS, WS_GRID_SORTED, WS_GRID_BBOX, WS_GRID_HEAVY, WS_BATCHSTATE, WS_TRACK, WS_PA, WS_PM3, WS_PG2, WS_COUNT
+    WS_RT, WS_GRID_META, WS_GRID_COUNTS, WS_GRID_CURSOR, WS_GRID_SUMS, WS_GRID_SORTED, WS_GRID_BBOX, WS_GRID_HEAVY, WS_BATCHSTATE, WS_TRACK, WS_PA, WS_PM3, WS_PG2, WS_MLOG, WS_REJ_FLAG, WS_REJ_PTS, WS_COUNT
 };
 
 int fail(icpb_ctx *ctx, int status, const char *what, cudaError_t ce = cudaSuccess)
@@ -109,6 +109,8 @@ void choose_nn_config(const icpb_ctx *ctx, int max_n, int max_m, int batch, int 
 struct RegHost {
     icpb_cloud *data;
     const icpb_cloud *target;
+    icpb_cloud *carry = nullptr;    // key-point variant: points that follow the motion
+    icpb_cloud *nonassoc = nullptr; // key-point variant: receives the accumulated rejects
 };
 
 // The device-resident registration loop for `count` independent problems.
@@ -161,6 +163,20 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
     if ((rc = ws_get(ctx, WS_DIST, tot_n * sizeof(float), (void **)&d_dist))) return rc;
     if ((rc = ws_get(ctx, WS_CHUNKS, tot_chunks * kTerms * sizeof(double), (void **)&d_chunks))) return rc;
     if ((rc = ws_get(ctx, WS_ALT, tot_n * sizeof(float4), (void **)&d_alt))) return rc;
+    // key-point variant (single registration): motion log, per-pass reject records
+    const bool kp_mode = count == 1 && (regs[0].carry || regs[0].nonassoc);
+    float *d_mlog = nullptr;
+    int *d_rej_flag = nullptr;
+    float4 *d_rej_pts = nullptr;
+    if (kp_mode) {
+        if (regs[0].nonassoc && regs[0].nonassoc->capacity < passes * regs[0].data->n)
+            return fail(ctx, ICPB_ERR_CAPACITY, "non-association cloud needs capacity (max_iterations+1) * key-points");
+        if ((rc = ws_get(ctx, WS_MLOG, sizeof(float) * 12 * (size_t)std::max(passes, 1), (void **)&d_mlog))) return rc;
+        if (regs[0].nonassoc) {
+            if ((rc = ws_get(ctx, WS_REJ_FLAG, sizeof(int) * (size_t)passes * max_n, (void **)&d_rej_flag))) return rc;
+            if ((rc = ws_get(ctx, WS_REJ_PTS, sizeof(float4) * (size_t)passes * max_n, (void **)&d_rej_pts))) return rc;
+        }
+    }
     int *d_idx_trace = nullptr;
     float *d_dist_trace = nullptr;
     if (prm->idx_trace) {
@@ -276,6 +292,13 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         d.gstart = d_gcounts;
         d.gheavy = d_gheavy ? d_gheavy + passes + 8 : nullptr;
         d.gheavy_count = d_gheavy;
+        d.carry = (kp_mode && regs[b].carry) ? regs[b].carry->d_pts : nullptr;
+        d.n_carry = (kp_mode && regs[b].carry) ? regs[b].carry->n : 0;
+        d.mlog = d_mlog;
+        d.rej_flag = d_rej_flag;
+        d.rej_pts = d_rej_pts;
+        d.nonassoc = (kp_mode && regs[b].nonassoc) ? regs[b].nonassoc->d_pts : nullptr;
+        d.nonassoc_capacity = (kp_mode && regs[b].nonassoc) ? regs[b].nonassoc->capacity : 0;
         IcpState &s = h_states[b];
         memset(&s, 0, sizeof(s));
         const float I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -327,6 +350,10 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
     }
     launch_pending_translate(d_descs, count, max_n, st);
     ++launches;
+    if (kp_mode) {
+        launch_keypoint_epilogue(d_descs, count, h_descs[0].n_carry, st);
+        ++launches;
+    }
     CU(ctx, cudaEventRecord(ctx->ev1, st));
     CU(ctx, cudaGetLastError());
 
@@ -350,6 +377,7 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
 
     for (int b = 0; b < count; ++b) {
         const IcpState &s = h_states[b];
+        if (kp_mode && regs[b].nonassoc) regs[b].nonassoc->n = std::min(s.n_nonassoc, regs[b].nonassoc->capacity);
         if (keep_transformed && s.last_buf == 1) {
             CU(ctx, cudaMemcpyAsync(h_descs[b].D[0], h_descs[b].D[1], sizeof(float4) * h_descs[b].n,
                                     cudaMemcpyDeviceToDevice, st));
@@ -382,6 +410,7 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
             r.nn_mode_used = grid_mode ? ICPB_NN_GRID : ICPB_NN_BRUTE;
             r.grid_cell_used = grid_mode ? gm.h : 0.f;
             r.nn_filter_used = filter;
+            r.n_nonassoc = s.n_nonassoc;
         }
     }
     if (trace) {
@@ -961,6 +990,35 @@ int icpb_icp_register_batch(icpb_ctx *ctx, icpb_cloud *const *data, const icpb_c
     std::vector<RegHost> regs((size_t)count);
     for (int b = 0; b < count; ++b) regs[b] = RegHost{data[b], target[b]};
     return run_registrations(ctx, regs.data(), count, params, results, true);
+}
+
+// 8f-2: the loop as the reference runs it (icp.cpp:98,155-258) -- key-points against the map's key-points
+int icpb_icp_register_keypoints(icpb_ctx *ctx, icpb_cloud *keypoints, icpb_cloud *points, const icpb_cloud *map_keypoints,
+                                const icpb_icp_params *params, icpb_icp_result *result, icpb_cloud *non_associations)
+{
+    if (!ctx || !keypoints || !map_keypoints || !params) return ICPB_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if ((points && points->ctx != ctx) || (non_associations && non_associations->ctx != ctx))
+        return fail(ctx, ICPB_ERR_INVALID, "cloud belongs to another context");
+    if (non_associations) non_associations->n = 0;
+    if (keypoints->n <= 0 || map_keypoints->n <= 0) {
+        // icp.cpp:490-491 (empty map: nothing is touched) / no key-points to associate: zero passes, identity motion
+        if (result) {
+            memset(result, 0, sizeof(*result));
+            for (int k = 0; k < 3; ++k) {
+                result->rigid[5 * k] = 1.f; result->cam_rotation[4 * k] = 1.f; result->pose_R[4 * k] = 1.0;
+            }
+            result->rigid[15] = 1.f;
+        }
+        return ICPB_OK;
+    }
+    RegHost r{keypoints, map_keypoints};
+    r.carry = (points && points->n > 0) ? points : nullptr;
+    r.nonassoc = non_associations;
+    if (!r.carry && !r.nonassoc) return run_registrations(ctx, &r, 1, params, result, true);
+    icpb_icp_params p = *params;
+    p.nn_mode = ICPB_NN_BRUTE; // a few thousand key-points: the brute-force scan is the fast path
+    return run_registrations(ctx, &r, 1, &p, result, true);
 }
 
 // ---- certainty map ---------------------------------------------------------------------

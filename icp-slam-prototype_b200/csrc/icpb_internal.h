@@ -56,6 +56,8 @@ struct IcpState {
     int small_exit;
     int pending_translate; // <3 associations rule: apply tf as a plain translation after the loop
     int rescans;
+    int n_log;          // motions recorded in RegDesc::mlog (key-point variant: replayed on the carried cloud)
+    int n_nonassoc;     // key-point variant: length of the accumulated reject list
     unsigned int block_counter;
     float rigid[9];
     float camR[9];
@@ -102,6 +104,14 @@ struct RegDesc {
     IcpState *st;
     int *idx_trace;          // nullable [(max_it+1)][n]
     float *dist_trace;
+    // key-point variant (icp.cpp:98,255; 8f-2); all null / 0 otherwise
+    float4 *carry;           // points that only follow the motion (dataCloud.points while the key-points are associated)
+    int n_carry;
+    float *mlog;             // [max_iterations][12] the (R, t) applied by every iteration, in order
+    int *rej_flag;           // [passes][n] 1: the query was rejected by the acceptance test of that pass (icp.cpp:507-509)
+    float4 *rej_pts;         // [passes][n] its coordinates at that pass
+    float4 *nonassoc;        // out: the rejects of all passes, pass-major, query order
+    int nonassoc_capacity;
     const GridMeta *grid;    // ICPB_NN_GRID only
     const float4 *gsorted;   // targets sorted by cell, w = original index
     const int *gstart;       // [ncells+1] first sorted slot of every cell
@@ -121,6 +131,7 @@ void launch_pack_band(const float4 *pts, int n, float4 *dst, cudaStream_t s);
 void launch_assemble_bands(const float4 *bands, int world, int band_capacity, float4 *out, int out_capacity, int *total,
                            cudaStream_t s);
 void launch_pending_translate(const RegDesc *descs, int batch, int max_n, cudaStream_t s);
+void launch_keypoint_epilogue(const RegDesc *descs, int batch, int max_carry, cudaStream_t s);
 void launch_center(const float4 *pts, int n, double *chunk_sums, double *out3, unsigned int *counter,
                    cudaStream_t s);
 void launch_fp32_peak(float *out, int blocks, int threads, int iters, cudaStream_t s);

@@ -659,21 +659,22 @@ __device__ float mse_from_sums(const double *sums)
 
 // The body of the while loop of icp.cpp:155-258 for one iteration, minus the
 // association itself.  Runs in one thread.
-__device__ void solve_step_local(IcpState *st, const IcpParamsDev *prm, const double *sums, int pass);
+__device__ void solve_step_local(IcpState *st, const IcpParamsDev *prm, const double *sums, int pass, float *mlog);
 
 // Works on a register / local copy of the state: one global read and one global write of the block.
-__device__ __noinline__ void solve_step(IcpState *gst, const IcpParamsDev *gprm, const double *sums, int pass)
+__device__ __noinline__ void solve_step(IcpState *gst, const IcpParamsDev *gprm, const double *sums, int pass, float *mlog)
 {
     IcpState st = *gst;
     IcpParamsDev prm = *gprm;
     double lsums[kTerms];
 #pragma unroll
     for (int k = 0; k < kTerms; ++k) lsums[k] = sums[k];
-    solve_step_local(&st, &prm, lsums, pass);
+    solve_step_local(&st, &prm, lsums, pass, mlog);
     *gst = st;
 }
 
-__device__ __forceinline__ void solve_step_local(IcpState *st, const IcpParamsDev *prm, const double *sums, int pass)
+__device__ __forceinline__ void solve_step_local(IcpState *st, const IcpParamsDev *prm, const double *sums, int pass,
+                                                 float *mlog)
 {
     st->passes = pass + 1;
     st->last_buf = (pass + 1) & 1;
@@ -760,6 +761,11 @@ __device__ __forceinline__ void solve_step_local(IcpState *st, const IcpParamsDe
     }
     for (int k = 0; k < 9; ++k) { st->PR[k] = NR[k]; st->Rf[k] = Rf[k]; }
     for (int k = 0; k < 3; ++k) { st->Pt[k] = Nt[k]; st->tf[k] = tf[k]; }
+    if (mlog) { // key-point variant: the carried cloud replays every motion after the loop
+        for (int k = 0; k < 9; ++k) mlog[12 * i + k] = Rf[k];
+        for (int k = 0; k < 3; ++k) mlog[12 * i + 9 + k] = tf[k];
+        st->n_log = i + 1;
+    }
     st->apply = 1;
     st->iterations = i + 1;
 }
@@ -944,6 +950,11 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
         d.dist[i] = best_d;
         if (d.idx_trace) d.idx_trace[(size_t)pass * n + i] = best_i;
         if (d.dist_trace) d.dist_trace[(size_t)pass * n + i] = best_d;
+        if (d.rej_flag) { // icp.cpp:507-509: the rejects of every pass accumulate
+            const bool rejected = !(best_d < prm->max_nn_distance);
+            d.rej_flag[(size_t)pass * n + i] = rejected ? 1 : 0;
+            if (rejected) d.rej_pts[(size_t)pass * n + i] = a;
+        }
     }
 
     // ---- association sums (CANON-3 level 1)
@@ -1012,7 +1023,7 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
     __syncthreads();
     if (tid == 0) {
         st->block_counter = 0; // re-armed before solve_step copies the state
-        solve_step(st, prm, s_tot, pass);
+        solve_step(st, prm, s_tot, pass, d.mlog);
     }
 }
 
@@ -1106,6 +1117,55 @@ __global__ void pending_translate_kernel(const RegDesc *__restrict__ descs)
     float4 p = buf[i];
     p.x += st->tf[0]; p.y += st->tf[1]; p.z += st->tf[2];
     buf[i] = p;
+}
+
+// Key-point variant, after the loop.  blockIdx.y == 0 .. : the carried cloud replays the recorded motions, each as
+// rotate-then-translate in float exactly like the associated key-points experienced them (pointcloud.cpp:321-359),
+// then the deferred translation of the <3 rule.  The LAST y-slice (one CTA) compacts the reject flags of all executed
+// passes, pass-major and in query order, into the non-association list (icp.cpp:96,508).
+__global__ void __launch_bounds__(256) keypoint_epilogue_kernel(const RegDesc *__restrict__ descs)
+{
+    const RegDesc &d = descs[blockIdx.z];
+    const IcpState *st = d.st;
+    if (blockIdx.y + 1 < gridDim.y) {
+        const int i = (blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+        if (!d.carry || i >= d.n_carry) return;
+        float4 p = d.carry[i];
+        const int nl = st->n_log;
+        for (int k = 0; k < nl; ++k) p = apply_rt(p, d.mlog + 12 * k, d.mlog + 12 * k + 9);
+        if (st->pending_translate) { p.x += st->tf[0]; p.y += st->tf[1]; p.z += st->tf[2]; }
+        d.carry[i] = p;
+        return;
+    }
+    if (blockIdx.x != 0 || !d.rej_flag) return;
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    const long long total = (long long)st->passes * d.n;
+    for (long long c0 = 0; c0 < total; c0 += 256) {
+        const long long e = c0 + tid;
+        const int f = (e < total) ? d.rej_flag[e] : 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) s_warp[wid] = __popc(bal);
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < wid; ++w) before += s_warp[w];
+        const int pos = before + __popc(bal & ((1u << lane) - 1u));
+        if (f && pos < d.nonassoc_capacity) d.nonassoc[pos] = d.rej_pts[e];
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += s_warp[w]; s_base += t; }
+        __syncthreads();
+    }
+    if (tid == 0) d.st->n_nonassoc = s_base;
+}
+
+void launch_keypoint_epilogue(const RegDesc *descs, int batch, int max_carry, cudaStream_t s)
+{
+    const int blocks = (max_carry + 255) / 256;
+    dim3 grid(blocks > 0 ? blocks : 1, 2, batch); // y = 0: carried points; y = 1: reject compaction
+    keypoint_epilogue_kernel<<<grid, 256, 0, s>>>(descs);
 }
 
 void launch_pending_translate(const RegDesc *descs, int batch, int max_n, cudaStream_t s)

@@ -16,8 +16,8 @@ namespace {
 
 struct Host {
     icpb_ctx *ctx = nullptr;
-    icpb_cloud *slot[3] = {nullptr, nullptr, nullptr};
-    int cap[3] = {0, 0, 0};
+    icpb_cloud *slot[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int cap[5] = {0, 0, 0, 0, 0};
 };
 
 Host &H()
@@ -93,6 +93,7 @@ struct IcpGlobals {
     cv::Point3f cameraPosition;
     map::Map *map = nullptr;
     bool started = false;
+    int mode = 0; // icp::ASSOCIATE_ALL_POINTS
 };
 IcpGlobals &G()
 {
@@ -354,8 +355,72 @@ void resetState()
     g.map->clear();
     g.map->mapCloud = PointCloud();
 }
+void setAssociationMode(int mode) { G().mode = mode; }
+map::Map &mapState() { return *G().map; }
 cv::Mat cameraRotationState() { return mat33(G().cameraRotation); }
 cv::Point3f cameraPositionState() { return G().cameraPosition; }
+
+// icp.cpp:28-285 exactly as the reference runs it (ASSOCIATE_KEYPOINTS): the data cloud's key-points
+// against the growing map cloud's key-points (:98,:255), the whole cloud moved along, rule-C map update from the
+// accumulated rejects (:271).  The loop, the motion of all points and the reject list stay on the device
+// (icpb_icp_register_keypoints); the map update is icpb_map_update_tracked.
+static cv::Mat getTransformationKeyPoints(cv::Mat &data, cv::Mat &previous, cv::Mat color, std::vector<cv::KeyPoint> keypoints,
+                                          int maxIterations, float threshold, cv::viz::Viz3d &depthWindow)
+{
+    IcpGlobals &g = G();
+    map::Map &m = *g.map;
+    PointCloud dataCloud(data, color, keypoints);         // :38
+    PointCloud previousCloud(previous, color, keypoints); // :39
+    if (m.mapCloud.points.size() == 0) {                  // :47-68
+        const float I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        for (int k = 0; k < 9; ++k) g.cameraRotation[k] = I[k];
+        g.cameraPosition = cv::Point3f(5, 5, 5);
+        for (int k = 0; k < 3; ++k) g.lastTranslation[k] = 0.f;
+        cv::Mat R0 = mat33(g.cameraRotation);
+        previousCloud.rotate(R0);
+        previousCloud.translate(g.cameraPosition);
+        m.update(previousCloud, MAX_CONFIDENCE, depthWindow);
+        m.mapCloud.points = previousCloud.points;
+        g.started = true;
+    }
+    cv::Mat rigid(4, 4, CV_32FC1);
+    for (int k = 0; k < 16; ++k) rigid.at<float>(k / 4, k % 4) = (k % 5 == 0) ? 1.f : 0.f;
+    // :70-71 and the loop, on the device
+    const float cp[3] = {g.cameraPosition.x, g.cameraPosition.y, g.cameraPosition.z};
+    icpb_cloud *kc = upload(0, dataCloud.keypoints);
+    icpb_cloud *pc = upload(1, dataCloud.points);
+    icpb_cloud *mc = upload(3, m.mapCloud.keypoints);
+    icpb_cloud *nc = scratch(4, (maxIterations + 1) * (int)std::max<size_t>(dataCloud.keypoints.size(), 1));
+    if (!dataCloud.keypoints.empty()) check(icpb_cloud_transform(kc, g.cameraRotation, cp), "icpb_cloud_transform");
+    if (!dataCloud.points.empty()) check(icpb_cloud_transform(pc, g.cameraRotation, cp), "icpb_cloud_transform");
+    icpb_icp_params prm;
+    prm.max_iterations = maxIterations;
+    prm.threshold = threshold;
+    prm.max_nn_distance = MAX_NN_KEYPOINT_DISTANCE; // :503
+    prm.solve_mode = ICPB_SOLVE_REFERENCE;
+    for (int k = 0; k < 3; ++k) prm.last_translation[k] = g.lastTranslation[k];
+    prm.idx_trace = nullptr;
+    prm.dist_trace = nullptr;
+    prm.nn_mode = ICPB_NN_BRUTE;
+    prm.grid_cell = 0.f;
+    prm.nn_filter = ICPB_FILTER_CENTRED;
+    icpb_icp_result res;
+    check(icpb_icp_register_keypoints(H().ctx, kc, dataCloud.points.empty() ? nullptr : pc, mc, &prm, &res, nc),
+          "icpb_icp_register_keypoints");
+    mul33(g.cameraRotation, res.cam_rotation, g.cameraRotation);                                  // :237
+    g.cameraPosition += cv::Point3f(res.cam_position[0], res.cam_position[1], res.cam_position[2]); // :246
+    for (int k = 0; k < 3; ++k) g.lastTranslation[k] = -res.offset[k];                              // :260
+    std::cout << res.mse;                                                                           // :264
+    if (res.n_assoc > 0) { // map.cpp:124-126; rule C on the rejects of every pass (:271, map.cpp:130-151)
+        point_list_t non;
+        download(nc, non);
+        associations_t some(1);
+        m.update(some, std::vector<float>(), non, DELTA_CONFIDENCE);
+    }
+    std::cout << std::endl << m.mapCloud.points.size() << std::endl;                                // :279
+    for (int k = 0; k < 16; ++k) rigid.at<float>(k / 4, k % 4) = res.rigid[k];
+    return rigid;
+}
 
 // icp.cpp:28-285 with the all-point association (:149/:253) against the previous frame's cloud placed at the
 // current camera pose.  Depth -> XYZ, the 20-iteration loop and the pose update all stay on the device.
@@ -364,6 +429,8 @@ cv::Mat getTransformation(cv::Mat &data, cv::Mat &previous, cv::Mat color, std::
 {
     (void)rotation;
     IcpGlobals &g = G();
+    if (g.mode == ASSOCIATE_KEYPOINTS)
+        return getTransformationKeyPoints(data, previous, color, keypoints, maxIterations, threshold, depthWindow);
     PointCloud dataCloud(data, color, keypoints);       // :38
     PointCloud previousCloud(previous, color, keypoints); // :39 (previous depth with the CURRENT colour / key-points)
     if (!g.started) {                                   // :47-68

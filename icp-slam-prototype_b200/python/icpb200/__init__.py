@@ -53,7 +53,7 @@ class IcpResult(C.Structure):
                 ("small_assoc_exit", C.c_int), ("exact_rescans", C.c_int), ("gpu_ms", C.c_float),
                 ("kernel_launches", C.c_int), ("nn_partial_ms", C.c_float), ("nn_partial_launches", C.c_int),
                 ("nn_qpt", C.c_int), ("nn_splits", C.c_int), ("nn_mode_used", C.c_int), ("grid_cell_used", C.c_float),
-                ("nn_filter_used", C.c_int)]
+                ("nn_filter_used", C.c_int), ("n_nonassoc", C.c_int)]
 
     def to_dict(self):
         return {
@@ -68,6 +68,7 @@ class IcpResult(C.Structure):
             "nn_partial_ms": self.nn_partial_ms, "nn_partial_launches": self.nn_partial_launches,
             "nn_qpt": self.nn_qpt, "nn_splits": self.nn_splits, "nn_mode_used": self.nn_mode_used,
             "grid_cell_used": self.grid_cell_used, "nn_filter_used": self.nn_filter_used,
+            "n_nonassoc": self.n_nonassoc,
         }
 
 
@@ -220,6 +221,18 @@ class Context:
         res = IcpResult()
         self.check(self.lib.icpb_icp_register(self.h, data.h, target.h, C.byref(prm), C.byref(res)))
         return res.to_dict(), it, dt
+
+    def icp_register_keypoints(self, keypoints, points, map_keypoints, max_iterations=16, threshold=1e-4,
+                               max_nn_distance=0.1, solve_mode=SOLVE_REFERENCE, last_translation=(0, 0, 0),
+                               non_associations=None):
+        """8f-2: the reference's live loop (icp.cpp:98,155-258).  Clouds are moved in place."""
+        prm = IcpParams(max_iterations, threshold, max_nn_distance, solve_mode, (C.c_float * 3)(*last_translation),
+                        None, None, NN_BRUTE, 0.0, FILTER_CENTRED)
+        res = IcpResult()
+        self.check(self.lib.icpb_icp_register_keypoints(
+            self.h, keypoints.h, points.h if points is not None else None, map_keypoints.h, C.byref(prm), C.byref(res),
+            non_associations.h if non_associations is not None else None))
+        return res.to_dict()
 
     def icp_register_batch(self, datas, targets, max_iterations=20, threshold=0.0, max_nn_distance=0.75,
                            solve_mode=SOLVE_REFERENCE):

@@ -112,6 +112,7 @@ typedef struct {
     int nn_mode_used;       /* ICPB_NN_BRUTE or ICPB_NN_GRID */
     float grid_cell_used;
     int nn_filter_used;     /* ICPB_FILTER_* of the BRUTE scan */
+    int n_nonassoc;         /* icpb_icp_register_keypoints: length of the accumulated reject list */
 } icpb_icp_result;
 
 /* ---- library / context ------------------------------------------------- */
@@ -203,6 +204,16 @@ int icpb_icp_register(icpb_ctx *ctx, icpb_cloud *data, const icpb_cloud *target,
 /* `count` independent registrations (BASELINE config 4); results[i] for pair i. */
 int icpb_icp_register_batch(icpb_ctx *ctx, icpb_cloud *const *data, const icpb_cloud *const *target,
                             int count, const icpb_icp_params *params, icpb_icp_result *results);
+/* The loop as the reference runs it (icp.cpp:98,155-258): the data cloud's KEY-POINTS are
+ * associated with the map cloud's key-points (findGlobalKeyPointAssociations, icp.cpp:488-539; pass
+ * max_nn_distance = MAX_NN_KEYPOINT_DISTANCE 0.1, icp.hpp:10), `points` (nullable) follow every motion like
+ * dataCloud.points do (pointcloud.cpp:321-359), and the key-points rejected by ANY pass accumulate, in order, in
+ * `non_associations` (nullable; capacity >= (max_iterations+1) * key-points; icp.cpp:96,508) - the list
+ * Map::update(assoc, errors, nonAssoc, delta) consumes (icpb_map_update_tracked, ICPB_TRACK_NONASSOC).
+ * An empty map cloud (icp.cpp:490-491) or an empty key-point list: zero passes, nothing is touched. */
+int icpb_icp_register_keypoints(icpb_ctx *ctx, icpb_cloud *keypoints, icpb_cloud *points,
+                                const icpb_cloud *map_keypoints, const icpb_icp_params *params,
+                                icpb_icp_result *result, icpb_cloud *non_associations);
 
 /* ---- certainty map: class map::Map, map.hpp:20-37 ------------------------ */
 /* Map::Map map.cpp:17-31; world[x][y][z] z-fastest (map.hpp:25).  The reference

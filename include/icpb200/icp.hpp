@@ -18,6 +18,8 @@
 
 #include "pointcloud.hpp"
 
+namespace map { class Map; }
+
 typedef std::vector<std::pair<color_point_t, color_point_t>> associations_t;
 
 namespace icp {
@@ -39,7 +41,13 @@ float getNearestPoint(color_point_t point, color_point_t &nearest, PointCloud &c
 float getNearestKeyPoint(color_point_t point, color_point_t &nearest, PointCloud &cloud);
 
 // Additions over the reference (explicit state instead of icp.cpp:22-26's file-scope globals)
+// getTransformation's association: ALL_POINTS (default) is the all-point scan of icp.cpp:149/253 against the previous
+// frame (the north-star path); KEYPOINTS is the loop exactly as the reference runs it (icp.cpp:98/255/271): key-points
+// against the growing map cloud, rule-C map update from the rejects.
+enum { ASSOCIATE_ALL_POINTS = 0, ASSOCIATE_KEYPOINTS = 1 };
+void setAssociationMode(int mode);
 void resetState();
+map::Map &mapState(); // the process-global map of icp.cpp:26
 cv::Mat cameraRotationState();
 cv::Point3f cameraPositionState();
 } // namespace icp

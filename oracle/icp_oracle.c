@@ -465,11 +465,24 @@ static float mse_from_sums(const double sums[ORC_NTERMS])
     return (float)((double)e * (double)e);
 }
 
-int orc_icp(orc_point *data, int n, const orc_point *target, int m,
-            const orc_icp_params *prm, orc_icp_result *res, int32_t *idx_trace,
-            float *dist_trace)
+/* Rejected queries of one association pass, in query order (icp.cpp:507-509: nonAssociations.push_back, never
+ * cleared between the passes of one getTransformation call). */
+static void append_rejects(const orc_point *data, int n, const float *dist, float max_nn, orc_point *out, int *n_out)
+{
+    if (!out) return;
+    for (int q = 0; q < n; q++)
+        if (!(dist[q] < max_nn)) out[(*n_out)++] = data[q];
+}
+
+/* The loop of icp.cpp:98-258.  `data` are the associated points (all points: :149/:253; key-points: :98/:255);
+ * `carry` (nullable) are points that only follow the motion (dataCloud.rotate / translate move points AND
+ * key-points, pointcloud.cpp:321-359); `nonassoc` (nullable, capacity (max_iterations+1)*n) collects the rejects. */
+static int icp_core(orc_point *data, int n, orc_point *carry, int n_carry, const orc_point *target, int m,
+                    const orc_icp_params *prm, orc_icp_result *res, int32_t *idx_trace, float *dist_trace,
+                    orc_point *nonassoc, int *n_nonassoc)
 {
     if (n <= 0 || m <= 0) return -1;
+    if (n_nonassoc) *n_nonassoc = 0;
     int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
     float *dist = (float *)malloc(sizeof(float) * (size_t)n);
     double *terms = (double *)malloc(sizeof(double) * ORC_NTERMS * (size_t)n);
@@ -489,6 +502,7 @@ int orc_icp(orc_point *data, int n, const orc_point *target, int m,
     if (dist_trace) memcpy(dist_trace, dist, sizeof(float) * (size_t)n);
     passes++;
     assoc_sums(data, n, target, idx, dist, prm->max_nn_distance, terms, sums);
+    append_rejects(data, n, dist, prm->max_nn_distance, nonassoc, n_nonassoc);
 
     int i = 0;
     /* icp.cpp:155 */
@@ -502,6 +516,7 @@ int orc_icp(orc_point *data, int n, const orc_point *target, int m,
             offset[1] = -prm->last_translation[1];
             offset[2] = -prm->last_translation[2];
             orc_translate(data, n, prm->last_translation);
+            if (carry) orc_translate(carry, n_carry, prm->last_translation);
             for (int k = 0; k < 3; k++) Pt[k] += (double)prm->last_translation[k];
             res->small_assoc_exit = 1;
             break;
@@ -525,6 +540,7 @@ int orc_icp(orc_point *data, int n, const orc_point *target, int m,
             /* icp.cpp:235-237 */
             orc_inv33f(R, Rf);
             orc_rotate(data, n, Rf);
+            if (carry) orc_rotate(carry, n_carry, Rf);
             orc_gemm33f(camR, Rf, camR);
             /* icp.cpp:240 / 314-344: mean of (a - b) over the associations,
              * which hold pre-rotation copies of a */
@@ -532,6 +548,7 @@ int orc_icp(orc_point *data, int n, const orc_point *target, int m,
             /* icp.cpp:245-246 */
             tf[0] = -offset[0]; tf[1] = -offset[1]; tf[2] = -offset[2];
             orc_translate(data, n, tf);
+            if (carry) orc_translate(carry, n_carry, tf);
             camP[0] -= offset[0]; camP[1] -= offset[1]; camP[2] -= offset[2];
         } else {
             /* rigid_transform_3D.py:14-36 with A = data, B = matches */
@@ -560,6 +577,7 @@ int orc_icp(orc_point *data, int n, const orc_point *target, int m,
                 tf[r] = (float)(cB[r] - ((Rd[3 * r] * cA[0] + Rd[3 * r + 1] * cA[1]) + Rd[3 * r + 2] * cA[2]));
             orc_rotate(data, n, Rf);
             orc_translate(data, n, tf);
+            if (carry) { orc_rotate(carry, n_carry, Rf); orc_translate(carry, n_carry, tf); }
             offset[0] = -tf[0]; offset[1] = -tf[1]; offset[2] = -tf[2];
         }
         /* composed pose in double from the float R, t actually applied */
@@ -581,6 +599,7 @@ int orc_icp(orc_point *data, int n, const orc_point *target, int m,
         if (idx_trace) memcpy(idx_trace + (size_t)passes * n - n, idx, sizeof(int32_t) * (size_t)n);
         if (dist_trace) memcpy(dist_trace + (size_t)passes * n - n, dist, sizeof(float) * (size_t)n);
         assoc_sums(data, n, target, idx, dist, prm->max_nn_distance, terms, sums);
+        append_rejects(data, n, dist, prm->max_nn_distance, nonassoc, n_nonassoc);
         i++;
     }
 
@@ -601,6 +620,30 @@ int orc_icp(orc_point *data, int n, const orc_point *target, int m,
     memcpy(res->pose_t, Pt, sizeof(Pt));
     free(idx); free(dist); free(terms);
     return 0;
+}
+
+int orc_icp(orc_point *data, int n, const orc_point *target, int m,
+            const orc_icp_params *prm, orc_icp_result *res, int32_t *idx_trace,
+            float *dist_trace)
+{
+    return icp_core(data, n, NULL, 0, target, m, prm, res, idx_trace, dist_trace, NULL, NULL);
+}
+
+/* 8f-2, the loop as the reference runs it (icp.cpp:98,155-258): the data cloud's KEY-POINTS are associated with
+ * the map cloud's key-points (findGlobalKeyPointAssociations :488-515, prm->max_nn_distance = 0.1 m, icp.hpp:10);
+ * the cloud's points follow every motion; the rejected key-points of ALL passes accumulate in `nonassoc`
+ * (:508, :96).  An empty map (:490-491) or an empty key-point list leaves everything untouched. */
+int orc_icp_keypoints(orc_point *keypoints, int k, orc_point *points, int n, const orc_point *map_keypoints, int mk,
+                      const orc_icp_params *prm, orc_icp_result *res, orc_point *nonassoc, int *n_nonassoc)
+{
+    *n_nonassoc = 0;
+    if (k <= 0 || mk <= 0) {
+        memset(res, 0, sizeof(*res));
+        for (int d = 0; d < 3; d++) { res->rigid[5 * d] = 1.f; res->cam_rotation[4 * d] = 1.f; res->pose_R[4 * d] = 1.0; }
+        res->rigid[15] = 1.f;
+        return 0;
+    }
+    return icp_core(keypoints, k, points, n, map_keypoints, mk, prm, res, NULL, NULL, nonassoc, n_nonassoc);
 }
 
 /* ------------------------------------------------------------------------- */

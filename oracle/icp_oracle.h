@@ -104,6 +104,12 @@ int orc_icp(orc_point *data /* in/out, n */, int n, const orc_point *target, int
             int32_t *idx_trace /* nullable, (max_iterations+1)*n */,
             float *dist_trace /* nullable, same shape */);
 
+/* 8f-2: the same loop with the KEY-POINT association the reference runs (icp.cpp:98,255; :488-539): `keypoints`
+ * (in/out) are associated with `map_keypoints`, `points` (in/out, nullable) only follow the motion, the rejected
+ * key-points of every pass accumulate in `nonassoc` (capacity (max_iterations+1)*k, icp.cpp:508). */
+int orc_icp_keypoints(orc_point *keypoints, int k, orc_point *points, int n, const orc_point *map_keypoints, int mk,
+                      const orc_icp_params *prm, orc_icp_result *res, orc_point *nonassoc, int *n_nonassoc);
+
 /* ---- M1-M4: map.hpp:20-37, map.cpp:55-85, 88-151, 220-269, 272-439 ---- */
 void orc_voxel_coords(const float p[3], float cell, const int dims[3], int v[3]);
 void orc_map_update_endpoints(uint8_t *grid, const int dims[3], float cell,

@@ -217,6 +217,34 @@ def icp(data, target, max_iterations=20, threshold=0.0, max_nn_distance=0.75, so
     return out, data, it, dt
 
 
+def _res_dict(res):
+    return {
+        "iterations": res.iterations, "nn_passes": res.nn_passes, "n_assoc": res.n_assoc, "mse": res.mse,
+        "rigid": np.array(res.rigid[:], dtype=np.float32).reshape(4, 4),
+        "cam_rotation": np.array(res.cam_rotation[:], dtype=np.float32).reshape(3, 3),
+        "cam_position": np.array(res.cam_position[:], dtype=np.float32),
+        "offset": np.array(res.offset[:], dtype=np.float32),
+        "pose_R": np.array(res.pose_R[:]).reshape(3, 3), "pose_t": np.array(res.pose_t[:]),
+        "small_assoc_exit": res.small_assoc_exit,
+    }
+
+
+def icp_keypoints(keypoints, points, map_keypoints, max_iterations=16, threshold=1e-4, max_nn_distance=0.1,
+                  solve_mode=SOLVE_REFERENCE, last_translation=(0, 0, 0), n_threads=1):
+    """8f-2 (icp.cpp:98,155-258).  Returns (result dict, moved key-points, moved points, non-associations)."""
+    kp = np.ascontiguousarray(keypoints).copy()
+    pts = np.ascontiguousarray(points).copy()
+    mk = np.ascontiguousarray(map_keypoints)
+    prm = IcpParams(max_iterations, threshold, max_nn_distance, solve_mode, (C.c_float * 3)(*last_translation), n_threads)
+    res = IcpResult()
+    non = np.zeros(max(1, (max_iterations + 1) * len(kp)), dtype=POINT_DTYPE)
+    n_non = C.c_int(0)
+    rc = lib().orc_icp_keypoints(_p(kp), len(kp), _p(pts), len(pts), _p(mk), len(mk), C.byref(prm), C.byref(res),
+                                 _p(non), C.byref(n_non))
+    assert rc == 0
+    return _res_dict(res), kp, pts, non[:n_non.value].copy()
+
+
 def voxel_coords(p, cell, dims):
     p = np.ascontiguousarray(p, dtype=np.float32).reshape(3)
     d = (C.c_int * 3)(*dims)

@@ -146,3 +146,16 @@ def quat_inverse(a):
     a = np.ascontiguousarray(a, dtype=np.float32); o = np.zeros(4, np.float32)
     lib().ref_quat_inverse(_p(a), _p(o))
     return o
+
+
+def get_transformation(depth_cur, depth_prev, bgr, keypoints_xy, max_iterations=16, threshold=1e-4, seed=1):
+    """The reference's own icp::getTransformation (live key-point variant) on its process-global map / camera pose.
+    Returns (rigid 4x4, cameraRotation, cameraPosition) after the call."""
+    depth_cur = np.ascontiguousarray(depth_cur, dtype=np.uint16); depth_prev = np.ascontiguousarray(depth_prev, dtype=np.uint16)
+    bgr = np.ascontiguousarray(bgr, dtype=np.uint8)
+    kp = np.ascontiguousarray(keypoints_xy, dtype=np.float32).reshape(-1, 2)
+    h, w = depth_cur.shape
+    rigid = np.zeros(16, np.float32); camR = np.zeros(9, np.float32); camP = np.zeros(3, np.float32)
+    lib().ref_get_transformation(_p(depth_cur), _p(depth_prev), _p(bgr), w, h, _p(kp), len(kp), int(max_iterations),
+                                 C.c_float(threshold), C.c_uint(seed), _p(rigid), _p(camR), _p(camP))
+    return rigid.reshape(4, 4), camR.reshape(3, 3), camP

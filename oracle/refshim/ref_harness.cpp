@@ -16,7 +16,9 @@
 void logDeltaTime(int, int) {}
 
 namespace icp {
-extern map::Map map; // icp.cpp:26
+extern map::Map map;               // icp.cpp:26
+extern cv::Mat cameraRotation;     // icp.cpp:22
+extern cv::Point3f cameraPosition; // icp.cpp:24
 }
 
 struct ref_point { float x, y, z; unsigned char c0, c1, c2, pad; };
@@ -187,6 +189,26 @@ int ref_icp_allpoints(ref_point *data, int n, const ref_point *target, int m, in
     *n_assoc_out = (int)associations.size();
     for (int k = 0; k < n; ++k) data[k] = from_cp(dataCloud.points[k]);
     return i;
+}
+
+// The reference's OWN icp::getTransformation (icp.cpp:28-285), live key-point variant, called as SLAM.cpp:277 calls
+// it.  Key-points arrive as pixel coordinates (cv::FAST is out of scope).  srand(seed) first: the two PointCloud
+// constructors (:38-39) draw rand() per non-zero pixel (pointcloud.cpp:28), data cloud first.
+void ref_get_transformation(const uint16_t *depth_cur, const uint16_t *depth_prev, const uint8_t *bgr, int w, int h,
+                            const float *kp_xy, int n_kp, int maxIterations, float threshold, unsigned seed,
+                            float *rigid16, float *camR9, float *camP3)
+{
+    cv::Mat data(h, w, CV_16UC1, (void *)depth_cur), previous(h, w, CV_16UC1, (void *)depth_prev);
+    cv::Mat color(h, w, CV_8UC3, (void *)bgr);
+    std::vector<cv::KeyPoint> kps((size_t)n_kp);
+    for (int i = 0; i < n_kp; ++i) kps[(size_t)i].pt = cv::Point2f(kp_xy[2 * i], kp_xy[2 * i + 1]);
+    cv::Mat rotation;
+    cv::viz::Viz3d win("ref");
+    srand(seed);
+    cv::Mat T = icp::getTransformation(data, previous, color, kps, rotation, maxIterations, threshold, win);
+    for (int k = 0; k < 16; ++k) rigid16[k] = T.at<float>(k / 4, k % 4);
+    for (int k = 0; k < 9; ++k) camR9[k] = icp::cameraRotation.at<float>(k / 3, k % 3);
+    camP3[0] = icp::cameraPosition.x; camP3[1] = icp::cameraPosition.y; camP3[2] = icp::cameraPosition.z;
 }
 
 // ---- 8f-4: the reference's own Quaternion class (quaternion.cpp, compiled by path); q = {w, x, y, z}

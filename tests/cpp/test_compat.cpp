@@ -110,6 +110,36 @@ int main(int argc, char **argv)
         e[6] = d.w; e[7] = d.x; e[8] = d.y; e[9] = d.z;
         dump(out + "/euler.bin", e, sizeof(e));
     }
+    // the loop as the reference runs it (key-points against the growing map cloud), two frames from a fresh state
+    {
+        icp::resetState();
+        icp::setAssociationMode(icp::ASSOCIATE_KEYPOINTS);
+        std::vector<cv::KeyPoint> kp2;
+        for (int i = 0; i < 700; ++i) {
+            int x = 10 + (i * 97) % (w - 20), y = 10 + (i * 61) % (h - 20);
+            if (prev.at<uint16_t>(y, x) == 0 || cur.at<uint16_t>(y, x) == 0) continue;
+            cv::KeyPoint k; k.pt = cv::Point2f((float)x, (float)y); kp2.push_back(k);
+        }
+        srand(11);
+        cv::Mat L1 = icp::getTransformation(cur, prev, bgr, kp2, rot, 16, 1e-4f, win);
+        cv::Mat L2 = icp::getTransformation(prev, cur, bgr, kp2, rot, 16, 1e-4f, win);
+        dump(out + "/L1.bin", L1.data, 16 * sizeof(float));
+        dump(out + "/L2.bin", L2.data, 16 * sizeof(float));
+        cv::Mat lr = icp::cameraRotationState();
+        cv::Point3f lp = icp::cameraPositionState();
+        float lpose[12];
+        for (int k = 0; k < 9; ++k) lpose[k] = lr.at<float>(k / 3, k % 3);
+        lpose[9] = lp.x; lpose[10] = lp.y; lpose[11] = lp.z;
+        dump(out + "/live_pose.bin", lpose, sizeof(lpose));
+        std::vector<float> kxy;
+        for (const cv::KeyPoint &k : kp2) { kxy.push_back(k.pt.x); kxy.push_back(k.pt.y); }
+        dump(out + "/live_kxy.bin", kxy.data(), kxy.size() * sizeof(float));
+        map::Map &lm = icp::mapState();
+        dump(out + "/live_mapkp.bin", lm.mapCloud.keypoints.data(), lm.mapCloud.keypoints.size() * sizeof(color_point_t));
+        lm.syncWorld();
+        dump(out + "/live_world.bin", lm.world, (size_t)MAP_HEIGHT * MAP_HEIGHT * MAP_HEIGHT);
+        icp::setAssociationMode(icp::ASSOCIATE_ALL_POINTS);
+    }
     printf("\ncompat ok: n_data=%zu n_target=%zu assoc=%zu\n", data.points.size(), target.points.size(), assoc.size());
     return 0;
 }

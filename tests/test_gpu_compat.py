@@ -133,6 +133,24 @@ def test_compat_program_matches_oracle(tmp_path, orc):
     pose = np.fromfile(o + "/pose.bin", f32)
     assert np.array_equal(pose[:9].reshape(3, 3), orc.gemm33f(camR, r2["cam_rotation"]))
     assert np.array_equal(pose[9:], (camP + r2["cam_position"]).astype(f32))
+    # the loop as the reference runs it (icp::setAssociationMode(ASSOCIATE_KEYPOINTS)), two frames from a fresh state
+    from test_live_loop_vs_ref import OracleSlam
+    kxy = np.fromfile(o + "/live_kxy.bin", f32).reshape(-1, 2)
+    kps = [(int(x), int(y)) for x, y in kxy]
+    assert len(kps) > 300
+    libc.srand(11)
+    mine = OracleSlam(orc)
+    d_cur = _rand_stream(libc, int((cur != 0).sum())); d_prev = _rand_stream(libc, int((prev != 0).sum()))
+    l1 = mine.frame(cur, prev, col, kps, d_cur, d_prev)
+    d_cur = _rand_stream(libc, int((prev != 0).sum())); d_prev = _rand_stream(libc, int((cur != 0).sum()))
+    l2 = mine.frame(prev, cur, col, kps, d_cur, d_prev)
+    assert l1["iterations"] >= 1
+    assert np.array_equal(np.fromfile(o + "/L1.bin", f32).reshape(4, 4), l1["rigid"])
+    assert np.array_equal(np.fromfile(o + "/L2.bin", f32).reshape(4, 4), l2["rigid"])
+    lpose = np.fromfile(o + "/live_pose.bin", f32)
+    assert np.array_equal(lpose[:9].reshape(3, 3), mine.camR) and np.array_equal(lpose[9:], mine.camP)
+    _same(_pts(o + "/live_mapkp.bin", orc), mine.map_kp)
+    assert np.array_equal(np.fromfile(o + "/live_world.bin", np.uint8).reshape(300, 300, 300), mine.grid)
     # pose reporting through the drop-in Quaternion / toEulerianAngle (SLAM.cpp:284-293)
     eu = np.fromfile(o + "/euler.bin", f32)
     q = orc.quat_from_rot(pose[:9])
