@@ -7,6 +7,9 @@
 //   filterDepthImage                                        SLAM.cpp:553-573               (8f-1)
 //
 // Built with -fmad=false; float divisions are IEEE (nvcc default -prec-div=true).
+#include <cmath>
+#include <cstring>
+
 #include "icpb_internal.h"
 
 namespace icpb {
@@ -98,121 +101,115 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *s
     return wbase + inc - v;
 }
 
-// P1.  One CTA per 2048-pixel tile, tiles taken by ticket so that every
-// predecessor a tile waits for has already started.  Two chained scans: the
-// ordinal among NON-ZERO pixels (consumed by the subsample rule exactly where
-// the reference consumes one rand(), pointcloud.cpp:22-28) and the output
-// position among KEPT pixels (raster order == push_back order, :54).
-// Specialised on the subsample rule and on the presence of a colour image: the per-pixel keep decision
-// compiles to nothing for ICPB_SUB_NONE, and no integer division is carried by rules that do not use one.
-template <int RULE, bool HAS_BGR>
-__global__ void __launch_bounds__(kBpThreads) backproject_kernel(BackprojectArgs a, uint32_t epoch)
+// Correctly rounded a / c for a divisor known on the host: rc = RN(1/c) (computed in double), then the classical
+// FMA sequence -- quotient estimate, exact residual, correction, twice.  The first correction leaves a faithful
+// quotient, the second is then the correctly rounded one (Markstein's theorem; needs rc correctly rounded, which the
+// host guarantees, and no over/underflow, which the launcher checks).  Same result as the `/` of
+// pointcloud.cpp:37-39, five instructions instead of the ~ten of a general IEEE division.
+struct DivConst {
+    float c, rc;
+};
+template <bool FAST>
+__device__ __forceinline__ float div_by(float a, DivConst d)
+{
+    if (!FAST) return a / d.c;
+    float q = __fmul_rn(a, d.rc);
+    float r = __fmaf_rn(-d.c, q, a);
+    q = __fmaf_rn(r, d.rc, q);
+    r = __fmaf_rn(-d.c, q, a);
+    return __fmaf_rn(r, d.rc, q);
+}
+
+struct BackprojectDiv {
+    DivConst scale, fx_u, fx_v;
+};
+
+// P1.  One CTA per 2048-pixel tile (tile = blockIdx.x: predecessors are dispatched first).  Two chained scans: the
+// ordinal among NON-ZERO pixels (consumed by the subsample rule exactly where the reference consumes one rand(),
+// pointcloud.cpp:22-28; only the STRIDE / STREAM rules need it) and the output position among KEPT pixels (raster
+// order == push_back order, :54).  The look-back for the output position runs in warp 0 AFTER it has lifted its own
+// pixels, while the other warps lift theirs: its latency hides behind the arithmetic.  Specialised on the subsample
+// rule, on the presence of a colour image and on the division path.
+template <int RULE, bool HAS_BGR, bool FASTDIV>
+__global__ void __launch_bounds__(kBpThreads) backproject_kernel(BackprojectArgs a, BackprojectDiv dv, uint32_t epoch)
 {
     // batched launch: frame = blockIdx.y, every per-frame pointer advances by its stride
     {
         const long long f = blockIdx.y;
         a.depth += f * a.depth_stride;
-        if (a.bgr) a.bgr += f * a.bgr_stride;
+        if (HAS_BGR) a.bgr += f * a.bgr_stride;
         a.out += f * a.out_stride;
         a.tile_state += f * a.state_stride;
-        a.ticket = (unsigned int *)((unsigned long long *)a.ticket + f * a.state_stride);
         a.out_count = (int *)((unsigned long long *)a.out_count + f * a.state_stride);
     }
     __shared__ uint32_t s_warp[kBpThreads / 32];
     __shared__ uint32_t s_bcast[2];
-    __shared__ int s_tile;
+    __shared__ float4 s_pts[kBpTile];
     const int tid = threadIdx.x;
-    if (tid == 0) {
-        unsigned int t = atomicAdd(a.ticket, 1u);
-        if (t == (unsigned int)(a.n_tiles - 1)) *a.ticket = 0; // last ticket of this launch: re-arm
-        s_tile = (int)t;
-    }
-    __syncthreads();
-    const int tile = s_tile;
-    if (tile < 0 || tile >= a.n_tiles) { // corrupted ticket: report, never spin
-        if (tid == 0) *a.out_count = -1;
-        return;
-    }
+    const int tile = blockIdx.x;
     int failed = 0;
     unsigned long long *stateV = a.tile_state;
     unsigned long long *stateK = a.tile_state + a.n_tiles;
     const int npx = a.w * a.h;
     const int p0 = tile * kBpTile + tid * kBpPix;
 
-    uint16_t dpx[kBpPix];
+    uint32_t dw[4] = {0, 0, 0, 0}; // 8 u16 depths
     if (p0 + kBpPix <= npx) {
-        uint4 raw = *reinterpret_cast<const uint4 *>(a.depth + p0);
-        dpx[0] = raw.x & 0xffff; dpx[1] = raw.x >> 16; dpx[2] = raw.y & 0xffff; dpx[3] = raw.y >> 16;
-        dpx[4] = raw.z & 0xffff; dpx[5] = raw.z >> 16; dpx[6] = raw.w & 0xffff; dpx[7] = raw.w >> 16;
+        const uint4 raw = *reinterpret_cast<const uint4 *>(a.depth + p0);
+        dw[0] = raw.x; dw[1] = raw.y; dw[2] = raw.z; dw[3] = raw.w;
     } else {
 #pragma unroll
-        for (int k = 0; k < kBpPix; ++k) dpx[k] = (p0 + k < npx) ? a.depth[p0 + k] : (uint16_t)0;
+        for (int k = 0; k < kBpPix; ++k)
+            if (p0 + k < npx) dw[k >> 1] |= (uint32_t)a.depth[p0 + k] << (16 * (k & 1));
     }
-    uint32_t nvalid = 0;
+    uint32_t valid_mask = 0;
 #pragma unroll
-    for (int k = 0; k < kBpPix; ++k) nvalid += (dpx[k] != 0);
+    for (int k = 0; k < kBpPix; ++k)
+        if ((dw[k >> 1] >> (16 * (k & 1))) & 0xffffu) valid_mask |= 1u << k;
 
-    // the ordinal among non-zero pixels is only consumed by the STRIDE / STREAM rules: skip that scan otherwise
     constexpr bool need_ordinal = (RULE == ICPB_SUB_STRIDE) || (RULE == ICPB_SUB_STREAM);
     const unsigned long long tag = (unsigned long long)(epoch << 2) << 32;
-    uint32_t v_base = 0;
-    if (need_ordinal) {
-        uint32_t tile_valid;
-        uint32_t v_off = block_exclusive_scan(nvalid, s_warp, tile_valid);
-        if (tid == 0) {
-            unsigned long long fl = (tile == 0) ? 2ull : 1ull;
-            st_volatile_u64(&stateV[tile], tag | (fl << 32) | tile_valid);
+    uint32_t keep_mask = valid_mask;
+    if (RULE != ICPB_SUB_NONE) {
+        uint32_t v_base = 0;
+        if (need_ordinal) {
+            uint32_t tile_valid;
+            const uint32_t v_off = block_exclusive_scan(__popc(valid_mask), s_warp, tile_valid);
+            if (tid == 0) st_volatile_u64(&stateV[tile], tag | ((tile == 0 ? 2ull : 1ull) << 32) | tile_valid);
+            if (tid < 32) {
+                const uint32_t ex = (tile == 0) ? 0u : lookback(stateV, tile, epoch, &failed);
+                if (tid == 0) {
+                    if (tile != 0) st_volatile_u64(&stateV[tile], tag | (2ull << 32) | (ex + tile_valid));
+                    s_bcast[0] = ex;
+                }
+            }
+            __syncthreads();
+            v_base = s_bcast[0] + v_off;
         }
-        if (tid < 32) {
-            uint32_t ex = (tile == 0) ? 0u : lookback(stateV, tile, epoch, &failed);
-            if (tid == 0) {
-                if (tile != 0) st_volatile_u64(&stateV[tile], tag | (2ull << 32) | (ex + tile_valid));
-                s_bcast[0] = ex;
+        keep_mask = 0;
+        uint32_t ord = v_base;
+        const uint32_t rule_arg = a.rule_arg ? a.rule_arg : 1u;
+#pragma unroll
+        for (int k = 0; k < kBpPix; ++k) {
+            if (valid_mask & (1u << k)) {
+                bool keep = true;
+                if (RULE == ICPB_SUB_STRIDE) keep = (ord % rule_arg) == 0;
+                else if (RULE == ICPB_SUB_HASH) keep = (hash32(a.seed, (uint32_t)(p0 + k)) % rule_arg) == 0;
+                else if (RULE == ICPB_SUB_STREAM) keep = (ord < (uint32_t)a.keep_stream_len) && a.keep_stream[ord] != 0;
+                if (keep) keep_mask |= 1u << k;
+                ++ord;
             }
         }
-        __syncthreads();
-        v_base = s_bcast[0] + v_off;
     }
-
-    // keep decisions
-    uint32_t keep_mask = 0, ord = v_base;
-    const uint32_t rule_arg = a.rule_arg ? a.rule_arg : 1u;
-#pragma unroll
-    for (int k = 0; k < kBpPix; ++k) {
-        if (dpx[k] != 0) {
-            bool keep = true;
-            if (RULE == ICPB_SUB_STRIDE) keep = (ord % rule_arg) == 0;
-            else if (RULE == ICPB_SUB_HASH) keep = (hash32(a.seed, (uint32_t)(p0 + k)) % rule_arg) == 0;
-            else if (RULE == ICPB_SUB_STREAM) keep = (ord < (uint32_t)a.keep_stream_len) && a.keep_stream[ord] != 0;
-            if (keep) keep_mask |= 1u << k;
-            ++ord;
-        }
-    }
-    const uint32_t nkeep = __popc(keep_mask);
     uint32_t tile_keep;
-    uint32_t k_off = block_exclusive_scan(nkeep, s_warp, tile_keep);
-    if (tid == 0) {
-        unsigned long long fl = (tile == 0) ? 2ull : 1ull;
-        st_volatile_u64(&stateK[tile], tag | (fl << 32) | tile_keep);
-    }
-    if (tid < 32) {
-        uint32_t ex = (tile == 0) ? 0u : lookback(stateK, tile, epoch, &failed);
-        if (tid == 0) {
-            if (tile != 0) st_volatile_u64(&stateK[tile], tag | (2ull << 32) | (ex + tile_keep));
-            s_bcast[1] = ex;
-            if (failed) *a.out_count = -1;
-            else if (tile == a.n_tiles - 1) *a.out_count = (int)(ex + tile_keep);
-        }
-    }
-    __syncthreads();
-    // points go to shared memory at their tile-local position first, then leave with fully coalesced 16-byte stores
-    __shared__ float4 s_pts[kBpTile];
-    uint32_t lo = k_off;
-    // pointcloud.cpp:37-39 (134-136): all float, left to right, true division
-    {
-        // the thread's 8 BGR triples: 24 bytes, 8-byte aligned when the image base is -> three 8-byte loads
-        uint32_t cw[6] = {0, 0, 0, 0, 0, 0};
-        if (HAS_BGR && keep_mask) {
+    const uint32_t k_off = block_exclusive_scan(__popc(keep_mask), s_warp, tile_keep);
+    if (tid == 0) st_volatile_u64(&stateK[tile], tag | ((tile == 0 ? 2ull : 1ull) << 32) | tile_keep);
+
+    // ---- lift the kept pixels into shared memory at their tile-local position (pointcloud.cpp:37-39 / 134-136:
+    //      all float, left to right, true division)
+    if (keep_mask) {
+        uint32_t cw[6] = {0, 0, 0, 0, 0, 0}; // the thread's 8 BGR triples: 24 bytes, three 8-byte loads when aligned
+        if (HAS_BGR) {
             const uint8_t *c = a.bgr + (size_t)p0 * 3;
             if (p0 + kBpPix <= npx && ((reinterpret_cast<uintptr_t>(c) & 7) == 0)) {
                 const uint2 *c2 = reinterpret_cast<const uint2 *>(c);
@@ -223,13 +220,21 @@ __global__ void __launch_bounds__(kBpThreads) backproject_kernel(BackprojectArgs
                     if (p0 * 3 + b < npx * 3) cw[b >> 2] |= (uint32_t)c[b] << (8 * (b & 3));
             }
         }
-        int v = p0 / a.w, u = p0 - v * a.w;
+        const int v0 = p0 / a.w;
+        int u = p0 - v0 * a.w;
+        // (float)u and (float)v kept as floats and stepped by 1.0f: exact for image coordinates
+        float uf = (float)u, vf = (float)v0;
+        float yv = __fsub_rn(vf, a.K.cx_v); // (v - cx_v), constant along a row
+        uint32_t lo = k_off;
 #pragma unroll
         for (int k = 0; k < kBpPix; ++k) {
             if (keep_mask & (1u << k)) {
-                float pz = ((float)dpx[k]) / a.K.depth_scale;
-                float px = ((float)u - a.K.cx_u) * pz / a.K.fx_u;
-                float py = ((float)v - a.K.cx_v) * pz / a.K.fx_v;
+                const uint32_t d16 = (dw[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+                // (float)d for d < 2^23 without a conversion instruction: 0x4B000000 | d is 2^23 + d
+                const float df = __fsub_rn(__uint_as_float(0x4B000000u | d16), 8388608.0f);
+                const float pz = div_by<FASTDIV>(df, dv.scale);
+                const float px = div_by<FASTDIV>(__fmul_rn(__fsub_rn(uf, a.K.cx_u), pz), dv.fx_u);
+                const float py = div_by<FASTDIV>(__fmul_rn(yv, pz), dv.fx_v);
                 uint32_t cbits = 0;
                 if (HAS_BGR) { // bytes 3k .. 3k+2 of the 24-byte run (:47): a funnel shift across two words
                     const int w = (3 * k) >> 2, sh = 8 * ((3 * k) & 3);
@@ -237,15 +242,37 @@ __global__ void __launch_bounds__(kBpThreads) backproject_kernel(BackprojectArgs
                 }
                 s_pts[lo++] = make_float4(px, py, pz, __uint_as_float(cbits));
             }
-            if (++u == a.w) { u = 0; ++v; }
+            uf += 1.0f;
+            if (++u == a.w) { u = 0; uf = 0.0f; vf += 1.0f; yv = __fsub_rn(vf, a.K.cx_v); }
+        }
+    }
+    // ---- warp 0: exclusive prefix of this tile among the kept pixels (its own lifting is already done)
+    if (tid < 32) {
+        const uint32_t ex = (tile == 0) ? 0u : lookback(stateK, tile, epoch, &failed);
+        if (tid == 0) {
+            if (tile != 0) st_volatile_u64(&stateK[tile], tag | (2ull << 32) | (ex + tile_keep));
+            s_bcast[1] = ex;
+            if (failed) *a.out_count = -1;
+            else if (tile == a.n_tiles - 1) *a.out_count = (int)(ex + tile_keep);
         }
     }
     __syncthreads();
+    // ---- the tile leaves with fully coalesced 16-byte stores
     const uint32_t tile_base = s_bcast[1];
     for (uint32_t j = tid; j < tile_keep; j += kBpThreads) {
         const uint32_t o = tile_base + j;
         if ((int)o < a.capacity) a.out[o] = s_pts[j];
     }
+}
+
+static bool fast_div_ok(float c)
+{
+    // the FMA sequence needs a normal divisor well inside the exponent range; an all-ones significand is kept on the
+    // plain division path as well (the reciprocal's rounding is least favourable there)
+    uint32_t b;
+    memcpy(&b, &c, 4);
+    const uint32_t e = (b >> 23) & 0xffu, m = b & 0x7fffffu;
+    return e >= 127 - 60 && e <= 127 + 60 && m != 0x7fffffu;
 }
 
 void launch_backproject(const BackprojectArgs &a, cudaStream_t s)
@@ -254,10 +281,20 @@ void launch_backproject(const BackprojectArgs &a, cudaStream_t s)
     epoch = (epoch + 1) & 0x3fffffffu;
     if (epoch == 0) epoch = 1;
     dim3 grid(a.n_tiles, a.frames > 0 ? a.frames : 1);
-#define ICPB_BP_LAUNCH(R)                                                                           \
-    do {                                                                                            \
-        if (a.bgr) backproject_kernel<R, true><<<grid, kBpThreads, 0, s>>>(a, epoch);               \
-        else backproject_kernel<R, false><<<grid, kBpThreads, 0, s>>>(a, epoch);                    \
+    BackprojectDiv dv;
+    dv.scale = {a.K.depth_scale, (float)(1.0 / (double)a.K.depth_scale)};
+    dv.fx_u = {a.K.fx_u, (float)(1.0 / (double)a.K.fx_u)};
+    dv.fx_v = {a.K.fx_v, (float)(1.0 / (double)a.K.fx_v)};
+    // depths are 1..65535 and image coordinates a few thousand at most: with divisors inside 2^+-60 nothing can
+    // overflow or underflow in the FMA sequence
+    const bool fast = fast_div_ok(a.K.depth_scale) && fast_div_ok(a.K.fx_u) && fast_div_ok(a.K.fx_v) &&
+                      fabsf(a.K.cx_u) < 1.0e6f && fabsf(a.K.cx_v) < 1.0e6f;
+#define ICPB_BP_LAUNCH(R)                                                                                   \
+    do {                                                                                                    \
+        if (a.bgr && fast) backproject_kernel<R, true, true><<<grid, kBpThreads, 0, s>>>(a, dv, epoch);     \
+        else if (a.bgr) backproject_kernel<R, true, false><<<grid, kBpThreads, 0, s>>>(a, dv, epoch);       \
+        else if (fast) backproject_kernel<R, false, true><<<grid, kBpThreads, 0, s>>>(a, dv, epoch);        \
+        else backproject_kernel<R, false, false><<<grid, kBpThreads, 0, s>>>(a, dv, epoch);                 \
     } while (0)
     switch (a.rule) {
     case ICPB_SUB_STRIDE: ICPB_BP_LAUNCH(ICPB_SUB_STRIDE); break;

@@ -164,3 +164,54 @@ def test_backproject_batch_device(ctx, orc):
         assert cnt[f] == len(ref)
         got = np.ascontiguousarray(pts[f, : cnt[f]]).view(orc.POINT_DTYPE).reshape(-1)
         assert np.array_equal(got.view(np.uint8), ref.view(np.uint8))
+
+
+def _exhaustive_frames(w, h, along_rows):
+    """Frames whose depth is constant along a row (or a column) and runs through 1..65535 over the frames: together
+    with the other axis this pairs EVERY depth value with every image coordinate of that axis."""
+    n = h if along_rows else w
+    frames = []
+    d = 1
+    while d <= 65535:
+        vals = np.clip(np.arange(d, d + n), 0, 65535).astype(np.uint16)
+        vals[np.arange(d, d + n) > 65535] = 0
+        frames.append(np.repeat(vals[:, None], w, 1) if along_rows else np.repeat(vals[None, :], h, 0))
+        d += n
+    return frames
+
+
+@pytest.mark.parametrize("sensor", ["v1", "v2", "distinct_axes"])
+def test_backproject_exhaustive_depth_x_coordinate(ctx, orc, sensor):
+    """The kernel divides by the (host-known) intrinsics with a reciprocal + FMA-residual sequence instead of `/`.
+    Proof by exhaustion that it is the correctly rounded quotient of pointcloud.cpp:37-39: every depth value 1..65535
+    paired with every column (x) and with every row (y), bit-equal to the oracle's true divisions."""
+    import icpb200
+    if sensor == "v1":
+        K, Ko, (w, h) = icpb200.reference_intrinsics_v1(), orc.kinect_v1(), (640, 480)
+    elif sensor == "v2":
+        K, Ko, (w, h) = icpb200.reference_intrinsics_v2(), orc.kinect_v2(), (512, 424)
+    else:  # true per-axis intrinsics (pointcloud.hpp:7-10 has FY / CY; the reference never uses them)
+        K, Ko, (w, h) = icpb200.Intrinsics(468.60, 318.27, 468.61, 243.99, 5000.0), \
+            orc.Intrinsics(468.60, 318.27, 468.61, 243.99, 5000.0), (640, 480)
+    c = ctx.cloud(w * h)
+    for along_rows in (True, False):
+        for depth in _exhaustive_frames(w, h, along_rows):
+            c.from_depth(depth, None, K)
+            ref, _, _ = orc.backproject(depth, None, Ko)
+            _same_points(c.download(), ref)
+    c.close()
+
+
+def test_backproject_unfavourable_divisors_use_true_division(ctx, orc):
+    """Divisors outside the proven range of the FMA sequence (all-ones significand, extreme exponents) take the plain
+    IEEE division path: still bit-equal."""
+    import icpb200
+    depth, bgr = _frame(4)
+    ones = float(np.uint32(0x43FFFFFF).view(np.float32))   # 511.99997, significand all ones
+    for fx, scale in ((ones, 5000.0), (468.6, ones), (1.0e-25, 5000.0)):
+        K, Ko = icpb200.Intrinsics(fx, 318.27, fx, 318.27, scale), orc.Intrinsics(fx, 318.27, fx, 318.27, scale)
+        c = ctx.cloud(depth.size)
+        c.from_depth(depth, bgr, K)
+        ref, _, _ = orc.backproject(depth, bgr, Ko)
+        _same_points(c.download(), ref)
+        c.close()
