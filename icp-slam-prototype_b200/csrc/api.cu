@@ -735,7 +735,8 @@ int icpb_cloud_from_depth_device(icpb_cloud *cloud, const void *d_depth, const v
     int rc;
     // [ticket (u32) | pad][out_count (i32) | pad][2*n_tiles status words]: fixed positions, so a
     // different image size never reinterprets stale status words as the ticket
-    if ((rc = ws_get(ctx, WS_TILESTATE, sizeof(unsigned long long) * (2 * (size_t)a.n_tiles + 2), &ts, true))) return rc;
+    // (+ n_tiles words: the per-tile counts of the two-pass kernels, kept apart from the epoch-tagged status words)
+    if ((rc = ws_get(ctx, WS_TILESTATE, sizeof(unsigned long long) * (3 * (size_t)a.n_tiles + 2), &ts, true))) return rc;
     a.ticket = (unsigned int *)ts;
     a.out_count = (int *)((unsigned long long *)ts + 1);
     a.tile_state = (unsigned long long *)ts + 2;
@@ -747,6 +748,15 @@ int icpb_cloud_from_depth_device(icpb_cloud *cloud, const void *d_depth, const v
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaGetLastError());
     int n = *(int *)hp;
+    if (n < 0 && (rule == ICPB_SUB_NONE || rule == ICPB_SUB_HASH)) {
+        // a predecessor tile never published (CTAs not dispatched in tile order): redo with the kernels that never wait
+        launch_backproject(a, ctx->stream, true);
+        ctx->launches += 2;
+        CU(ctx, cudaMemcpyAsync(hp, a.out_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        CU(ctx, cudaGetLastError());
+        n = *(int *)hp;
+    }
     if (n < 0) {
         cloud->n = 0;
         CU(ctx, cudaMemsetAsync(ts, 0, sizeof(unsigned long long) * 2, ctx->stream));
@@ -781,7 +791,7 @@ int icpb_backproject_batch_device(icpb_ctx *ctx, const void *d_depth, const void
     a.depth_stride = (long long)w * h;
     a.bgr_stride = (long long)w * h * 3;
     a.out_stride = capacity_per_frame;
-    a.state_stride = 2LL * a.n_tiles + 2;
+    a.state_stride = 3LL * a.n_tiles + 2; // ticket, count, 2 n_tiles status words, n_tiles words of per-tile counts
     void *ts;
     int rc;
     if ((rc = ws_get(ctx, WS_BATCHSTATE, sizeof(unsigned long long) * (size_t)a.state_stride * frames, &ts, true))) return rc;

@@ -8,6 +8,7 @@
 //
 // Built with -fmad=false; float divisions are IEEE (nvcc default -prec-div=true).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "icpb_internal.h"
@@ -99,6 +100,25 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *s
     __syncthreads();
     total = tot;
     return wbase + inc - v;
+}
+
+// The staged tile leaves with fully coalesced 16-byte stores: all shared-memory reads first, then all the stores, so
+// the eight stores of a thread are in flight together instead of each waiting for its own LDS.
+__device__ __forceinline__ void store_tile(const float4 *s_pts, uint32_t tile_keep, uint32_t tile_base, float4 *out,
+                                           int capacity, int tid)
+{
+    float4 v[kBpPix];
+#pragma unroll
+    for (int k = 0; k < kBpPix; ++k) {
+        const uint32_t j = (uint32_t)tid + (uint32_t)k * kBpThreads;
+        if (j < tile_keep) v[k] = s_pts[j];
+    }
+#pragma unroll
+    for (int k = 0; k < kBpPix; ++k) {
+        const uint32_t j = (uint32_t)tid + (uint32_t)k * kBpThreads;
+        const uint32_t o = tile_base + j;
+        if (j < tile_keep && (int)o < capacity) out[o] = v[k];
+    }
 }
 
 // Correctly rounded a / c for a divisor known on the host: rc = RN(1/c) (computed in double), then the classical
@@ -221,29 +241,36 @@ __global__ void __launch_bounds__(kBpThreads) backproject_kernel(BackprojectArgs
             }
         }
         const int v0 = p0 / a.w;
-        int u = p0 - v0 * a.w;
-        // (float)u and (float)v kept as floats and stepped by 1.0f: exact for image coordinates
-        float uf = (float)u, vf = (float)v0;
-        float yv = __fsub_rn(vf, a.K.cx_v); // (v - cx_v), constant along a row
-        uint32_t lo = k_off;
+        const int u0 = p0 - v0 * a.w;
+        // Image widths are multiples of 8 in practice (640, 512): the thread's 8 pixels then share a row and the
+        // coordinates are u0 + k, exactly representable float sums; otherwise every pixel finds its own (u, v).
+        const bool same_row = (a.w % kBpPix) == 0;
+        const float uf0 = (float)u0, vf0 = (float)v0;
+        float4 *dst = &s_pts[k_off];
+        // branch-free: all 8 pixels are lifted (a zero depth just gives z = 0), only the kept ones are stored
 #pragma unroll
         for (int k = 0; k < kBpPix; ++k) {
-            if (keep_mask & (1u << k)) {
-                const uint32_t d16 = (dw[k >> 1] >> (16 * (k & 1))) & 0xffffu;
-                // (float)d for d < 2^23 without a conversion instruction: 0x4B000000 | d is 2^23 + d
-                const float df = __fsub_rn(__uint_as_float(0x4B000000u | d16), 8388608.0f);
-                const float pz = div_by<FASTDIV>(df, dv.scale);
-                const float px = div_by<FASTDIV>(__fmul_rn(__fsub_rn(uf, a.K.cx_u), pz), dv.fx_u);
-                const float py = div_by<FASTDIV>(__fmul_rn(yv, pz), dv.fx_v);
-                uint32_t cbits = 0;
-                if (HAS_BGR) { // bytes 3k .. 3k+2 of the 24-byte run (:47): a funnel shift across two words
-                    const int w = (3 * k) >> 2, sh = 8 * ((3 * k) & 3);
-                    cbits = __funnelshift_r(cw[w], w + 1 < 6 ? cw[w + 1] : 0u, sh) & 0x00ffffffu;
-                }
-                s_pts[lo++] = make_float4(px, py, pz, __uint_as_float(cbits));
+            float uf = uf0 + (float)k, vf = vf0;
+            if (!same_row) {
+                const int pk = p0 + k, vv = pk / a.w;
+                uf = (float)(pk - vv * a.w);
+                vf = (float)vv;
             }
-            uf += 1.0f;
-            if (++u == a.w) { u = 0; uf = 0.0f; vf += 1.0f; yv = __fsub_rn(vf, a.K.cx_v); }
+            const uint32_t d16 = (dw[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+            // (float)d for d < 2^23 without a conversion instruction: 0x4B000000 | d is 2^23 + d
+            const float df = __fsub_rn(__uint_as_float(0x4B000000u | d16), 8388608.0f);
+            const float pz = div_by<FASTDIV>(df, dv.scale);
+            const float px = div_by<FASTDIV>(__fmul_rn(__fsub_rn(uf, a.K.cx_u), pz), dv.fx_u);
+            const float py = div_by<FASTDIV>(__fmul_rn(__fsub_rn(vf, a.K.cx_v), pz), dv.fx_v);
+            uint32_t cbits = 0;
+            if (HAS_BGR) { // bytes 3k .. 3k+2 of the 24-byte run (:47): a funnel shift across two words
+                const int w = (3 * k) >> 2, sh = 8 * ((3 * k) & 3);
+                cbits = __funnelshift_r(cw[w], w + 1 < 6 ? cw[w + 1] : 0u, sh) & 0x00ffffffu;
+            }
+            if (keep_mask & (1u << k)) {
+                *dst = make_float4(px, py, pz, __uint_as_float(cbits));
+                ++dst;
+            }
         }
     }
     // ---- warp 0: exclusive prefix of this tile among the kept pixels (its own lifting is already done)
@@ -259,10 +286,161 @@ __global__ void __launch_bounds__(kBpThreads) backproject_kernel(BackprojectArgs
     __syncthreads();
     // ---- the tile leaves with fully coalesced 16-byte stores
     const uint32_t tile_base = s_bcast[1];
-    for (uint32_t j = tid; j < tile_keep; j += kBpThreads) {
+    for (uint32_t j = tid; j < tile_keep; j += kBpThreads) { // (batching the LDS / STG costs 11 registers and a CTA per SM)
         const uint32_t o = tile_base + j;
         if ((int)o < a.capacity) a.out[o] = s_pts[j];
     }
+}
+
+// ---- two-pass variant for the rules whose keep decision is local to the pixel (NONE, HASH) -------------------
+// Pass 1 counts the kept pixels of every tile; pass 2 lifts and writes, each CTA summing the counts of the tiles
+// before it in its frame (<= a few hundred L2-resident words, fetched before anything else).  No CTA ever waits for
+// another one, which is what bounded the chained-scan kernel (30 % of its stall samples sat behind the look-back).
+// Costs a second read of the depth image (2 of 18 bytes per pixel, mostly from L2).
+template <int RULE>
+__device__ __forceinline__ uint32_t local_keep_mask(const uint32_t (&dw)[4], const BackprojectArgs &a, int p0)
+{
+    uint32_t m = 0;
+    const uint32_t rule_arg = a.rule_arg ? a.rule_arg : 1u;
+#pragma unroll
+    for (int k = 0; k < kBpPix; ++k) {
+        bool keep = ((dw[k >> 1] >> (16 * (k & 1))) & 0xffffu) != 0;
+        if (RULE == ICPB_SUB_HASH) keep = keep && (hash32(a.seed, (uint32_t)(p0 + k)) % rule_arg) == 0;
+        if (keep) m |= 1u << k;
+    }
+    return m;
+}
+
+__device__ __forceinline__ void load_depth8(const BackprojectArgs &a, int p0, int npx, uint32_t (&dw)[4])
+{
+    dw[0] = dw[1] = dw[2] = dw[3] = 0;
+    if (p0 + kBpPix <= npx) {
+        const uint4 raw = *reinterpret_cast<const uint4 *>(a.depth + p0);
+        dw[0] = raw.x; dw[1] = raw.y; dw[2] = raw.z; dw[3] = raw.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < kBpPix; ++k)
+            if (p0 + k < npx) dw[k >> 1] |= (uint32_t)a.depth[p0 + k] << (16 * (k & 1));
+    }
+}
+
+template <int RULE>
+__global__ void __launch_bounds__(kBpThreads) backproject_count_kernel(BackprojectArgs a)
+{
+    a.depth += (long long)blockIdx.y * a.depth_stride;
+    int *counts = reinterpret_cast<int *>(a.tile_state + (long long)blockIdx.y * a.state_stride + 2 * a.n_tiles);
+    __shared__ uint32_t s_warp[kBpThreads / 32];
+    const int tid = threadIdx.x, tile = blockIdx.x;
+    const int p0 = tile * kBpTile + tid * kBpPix;
+    uint32_t dw[4];
+    load_depth8(a, p0, a.w * a.h, dw);
+    uint32_t c = __popc(local_keep_mask<RULE>(dw, a, p0));
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+    if ((tid & 31) == 0) s_warp[tid >> 5] = c;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int k = 0; k < kBpThreads / 32; ++k) t += s_warp[k];
+        counts[tile] = (int)t;
+    }
+}
+
+template <int RULE, bool HAS_BGR, bool FASTDIV>
+__global__ void __launch_bounds__(kBpThreads) backproject_write_kernel(BackprojectArgs a, BackprojectDiv dv)
+{
+    {
+        const long long f = blockIdx.y;
+        a.depth += f * a.depth_stride;
+        if (HAS_BGR) a.bgr += f * a.bgr_stride;
+        a.out += f * a.out_stride;
+        a.tile_state += f * a.state_stride;
+        a.out_count = (int *)((unsigned long long *)a.out_count + f * a.state_stride);
+    }
+    __shared__ uint32_t s_warp[kBpThreads / 32];
+    __shared__ uint32_t s_before[kBpThreads / 32];
+    __shared__ float4 s_pts[kBpTile];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tile = blockIdx.x;
+    const int npx = a.w * a.h;
+    const int p0 = tile * kBpTile + tid * kBpPix;
+
+    // points kept by the tiles before this one: independent loads, issued first
+    const int *counts = reinterpret_cast<const int *>(a.tile_state + 2 * a.n_tiles);
+    uint32_t before = 0;
+    for (int j = tid; j < tile; j += kBpThreads) before += (uint32_t)__ldcg(&counts[j]);
+
+    uint32_t dw[4];
+    load_depth8(a, p0, npx, dw);
+    const uint32_t keep_mask = local_keep_mask<RULE>(dw, a, p0);
+    const uint32_t nkeep = __popc(keep_mask);
+    uint32_t inc = nkeep;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += o;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) before += __shfl_xor_sync(0xffffffffu, before, off);
+    if (lane == 31) s_warp[wid] = inc;
+    if (lane == 0) s_before[wid] = before;
+    __syncthreads();
+    uint32_t wbase = 0, tile_keep = 0, tile_base = 0;
+#pragma unroll
+    for (int k = 0; k < kBpThreads / 32; ++k) {
+        const uint32_t c = s_warp[k];
+        if (k < wid) wbase += c;
+        tile_keep += c;
+        tile_base += s_before[k];
+    }
+    const uint32_t k_off = wbase + inc - nkeep;
+    if (tid == 0 && tile == a.n_tiles - 1) *a.out_count = (int)(tile_base + tile_keep);
+
+    if (keep_mask) {
+        uint32_t cw[6] = {0, 0, 0, 0, 0, 0}; // the thread's 8 BGR triples: 24 bytes, three 8-byte loads when aligned
+        if (HAS_BGR) {
+            const uint8_t *c = a.bgr + (size_t)p0 * 3;
+            if (p0 + kBpPix <= npx && ((reinterpret_cast<uintptr_t>(c) & 7) == 0)) {
+                const uint2 *c2 = reinterpret_cast<const uint2 *>(c);
+                const uint2 w0 = c2[0], w1 = c2[1], w2 = c2[2];
+                cw[0] = w0.x; cw[1] = w0.y; cw[2] = w1.x; cw[3] = w1.y; cw[4] = w2.x; cw[5] = w2.y;
+            } else {
+                for (int b = 0; b < 3 * kBpPix; ++b)
+                    if (p0 * 3 + b < npx * 3) cw[b >> 2] |= (uint32_t)c[b] << (8 * (b & 3));
+            }
+        }
+        const int v0 = p0 / a.w;
+        const int u0 = p0 - v0 * a.w;
+        const bool same_row = (a.w % kBpPix) == 0; // see backproject_kernel
+        const float uf0 = (float)u0, vf0 = (float)v0;
+        float4 *dst = &s_pts[k_off];
+#pragma unroll
+        for (int k = 0; k < kBpPix; ++k) {
+            float uf = uf0 + (float)k, vf = vf0;
+            if (!same_row) {
+                const int pk = p0 + k, vv = pk / a.w;
+                uf = (float)(pk - vv * a.w);
+                vf = (float)vv;
+            }
+            const uint32_t d16 = (dw[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+            const float df = __fsub_rn(__uint_as_float(0x4B000000u | d16), 8388608.0f);
+            const float pz = div_by<FASTDIV>(df, dv.scale);                                             // pointcloud.cpp:37
+            const float px = div_by<FASTDIV>(__fmul_rn(__fsub_rn(uf, a.K.cx_u), pz), dv.fx_u);          // :38
+            const float py = div_by<FASTDIV>(__fmul_rn(__fsub_rn(vf, a.K.cx_v), pz), dv.fx_v);          // :39
+            uint32_t cbits = 0;
+            if (HAS_BGR) {
+                const int w = (3 * k) >> 2, sh = 8 * ((3 * k) & 3);
+                cbits = __funnelshift_r(cw[w], w + 1 < 6 ? cw[w + 1] : 0u, sh) & 0x00ffffffu;        // :47
+            }
+            if (keep_mask & (1u << k)) {
+                *dst = make_float4(px, py, pz, __uint_as_float(cbits));
+                ++dst;
+            }
+        }
+    }
+    __syncthreads();
+    store_tile(s_pts, tile_keep, tile_base, a.out, a.capacity, tid);
 }
 
 static bool fast_div_ok(float c)
@@ -275,7 +453,7 @@ static bool fast_div_ok(float c)
     return e >= 127 - 60 && e <= 127 + 60 && m != 0x7fffffu;
 }
 
-void launch_backproject(const BackprojectArgs &a, cudaStream_t s)
+void launch_backproject(const BackprojectArgs &a, cudaStream_t s, bool force_two_pass)
 {
     static uint32_t epoch = 0; // per-process launch counter; stale tile words never match it
     epoch = (epoch + 1) & 0x3fffffffu;
@@ -296,13 +474,27 @@ void launch_backproject(const BackprojectArgs &a, cudaStream_t s)
         else if (fast) backproject_kernel<R, false, true><<<grid, kBpThreads, 0, s>>>(a, dv, epoch);        \
         else backproject_kernel<R, false, false><<<grid, kBpThreads, 0, s>>>(a, dv, epoch);                 \
     } while (0)
+#define ICPB_BP_TWO_PASS(R)                                                                                 \
+    do {                                                                                                    \
+        backproject_count_kernel<R><<<grid, kBpThreads, 0, s>>>(a);                                         \
+        if (a.bgr && fast) backproject_write_kernel<R, true, true><<<grid, kBpThreads, 0, s>>>(a, dv);      \
+        else if (a.bgr) backproject_write_kernel<R, true, false><<<grid, kBpThreads, 0, s>>>(a, dv);        \
+        else if (fast) backproject_write_kernel<R, false, true><<<grid, kBpThreads, 0, s>>>(a, dv);         \
+        else backproject_write_kernel<R, false, false><<<grid, kBpThreads, 0, s>>>(a, dv);                  \
+    } while (0)
+    // Default: the single-launch chained-scan kernel (0.349 vs 0.359 ms for 256 frames).  The two-pass kernels never
+    // wait on another CTA: they are the retry path when a chained launch reports that a predecessor never published
+    // (out_count < 0), and can be forced with ICPB_BP_TWOPASS=1.
+    static const bool env_two_pass = getenv("ICPB_BP_TWOPASS") && atoi(getenv("ICPB_BP_TWOPASS")) != 0;
+    const bool two_pass = env_two_pass || force_two_pass;
     switch (a.rule) {
-    case ICPB_SUB_STRIDE: ICPB_BP_LAUNCH(ICPB_SUB_STRIDE); break;
-    case ICPB_SUB_HASH: ICPB_BP_LAUNCH(ICPB_SUB_HASH); break;
+    case ICPB_SUB_STRIDE: ICPB_BP_LAUNCH(ICPB_SUB_STRIDE); break; // ordinal-dependent decisions: chained scans
     case ICPB_SUB_STREAM: ICPB_BP_LAUNCH(ICPB_SUB_STREAM); break;
-    default: ICPB_BP_LAUNCH(ICPB_SUB_NONE); break;
+    case ICPB_SUB_HASH: if (two_pass) ICPB_BP_TWO_PASS(ICPB_SUB_HASH); else ICPB_BP_LAUNCH(ICPB_SUB_HASH); break;
+    default: if (two_pass) ICPB_BP_TWO_PASS(ICPB_SUB_NONE); else ICPB_BP_LAUNCH(ICPB_SUB_NONE); break;
     }
 #undef ICPB_BP_LAUNCH
+#undef ICPB_BP_TWO_PASS
 }
 
 // P3, SLAM.cpp:412-430.  Central differences on raw depth units; normalize as
