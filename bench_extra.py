@@ -127,7 +127,19 @@ def run_map1cm(args, rank, world, local):
     frames = args.frames or 32
     poses = synth.trajectory(frames, step_deg=0.8, step_m=0.02)
     depths = [synth.render_depth(R, t, synth.KINECT_V1, seed=f) for f, (R, t) in enumerate(poses)]
-    sm = D.SlabMap(ctx, dims, cell, rank, world, 640 * 480)
+    # slab boundaries balanced on the ray work of three frames of the sequence (host-side, identical on every rank)
+    bounds = None
+    if world > 1:
+        probe = ctx.cloud(640 * 480)
+        oz, ez = [], []
+        for f in (0, frames // 2, frames - 1):
+            R, t = poses[f]
+            probe.from_depth(depths[f], None, K)
+            probe.transform(np.asarray(R, np.float32), np.asarray(t, np.float32))
+            ez.append(probe.download()["z"].astype(np.float64)); oz.append(float(t[2]))
+        bounds = D.balanced_slab_bounds(dims[2], world, cell, oz, ez)
+        probe.close()
+    sm = D.SlabMap(ctx, dims, cell, rank, world, 640 * 480, bounds)
 
     def step(count):
         npts = vis = 0
@@ -174,7 +186,8 @@ def run_map1cm(args, rank, world, local):
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": {"workload": f"configs[4]: {frames} full-res Kinect v1 frames into a 600x600x500 1 cm uint8 grid "
-                                       "(180 MB), z-slab sharded, one all-gather of lifted points per frame",
+                                       "(180 MB), z-slab sharded (boundaries balanced on ray work), one all-gather of "
+                                       "lifted points per frame",
                            "rays_per_pass": npts, "voxels_visited_per_pass": visited, "slabs": hs,
                            "slabs_equal_single_gpu_grid": unsharded_ok,
                            "l2": "grid (180 MB) exceeds L2 at 1 GPU"},

@@ -197,27 +197,53 @@ struct Best {
 
 // Visit shell r (cells at Chebyshev distance exactly r from c0).  LANES threads share the work: lane `lane`
 // takes candidates lane, lane+LANES, ... of every contiguous run.
+// Gap between coordinate q and the cell interval [lo, lo + h) along one axis, shrunk by the same slack the cube
+// bound uses for the float rounding of the cell assignment: a LOWER bound on |q - t| for every target t of the cell.
+__device__ __forceinline__ float axis_gap(float q, float lo, float h)
+{
+    return fmaxf(fmaxf(lo - q, q - (lo + h)), 0.f) - 1e-3f * h;
+}
+
 template <int LANES>
 __device__ __forceinline__ void visit_shell(const GridMeta &g, const float4 *__restrict__ sorted, const int *__restrict__ start,
                                             const float4 &p, int c0x, int c0y, int c0z, int r, int lane, Best &best)
 {
     const int nx = g.dim[0], ny = g.dim[1], nz = g.dim[2];
     const int xlo = max(c0x - r, 0), xhi = min(c0x + r, nx - 1);
+    // LANES > 1: the lanes split every run by position, so they must all prune the same rows and cells -- the reach
+    // is frozen at the (warp-uniform) best the shell starts with.  One thread per query uses its live best.
+    const float frozen_reach2 = best.d * best.d * 1.00001f + 1e-30f;
     for (int dz = -r; dz <= r; ++dz) {
         const int z = c0z + dz;
         if (z < 0 || z >= nz) continue;
+        const float gz = fmaxf(axis_gap(p.z, g.mn[2] + z * g.h, g.h), 0.f);
         for (int dy = -r; dy <= r; ++dy) {
             const int y = c0y + dy;
             if (y < 0 || y >= ny) continue;
+            // Ball pruning: a row of cells whose box is farther from the query than the current best distance
+            // cannot hold a better or an equal candidate.  best.d only shrinks, so the test stays valid.
+            const float gy = fmaxf(axis_gap(p.y, g.mn[1] + y * g.h, g.h), 0.f);
+            const float gyz2 = gy * gy + gz * gz;
+            const float reach2 = (LANES > 1) ? frozen_reach2 : best.d * best.d * 1.00001f + 1e-30f; // +inf: nothing found yet
+            if (gyz2 > reach2) continue;
             const int rowbase = (z * ny + y) * nx;
             const bool edge = (dz == -r) || (dz == r) || (dy == -r) || (dy == r);
             const int nseg = edge ? 1 : 2; // edge rows: the whole x-run; inner rows: the two end cells
             for (int sgm = 0; sgm < nseg; ++sgm) {
                 int a, b;
-                if (edge) { a = xlo; b = xhi; }
-                else {
+                if (edge) {
+                    a = xlo; b = xhi;
+                    if (reach2 < CUDART_INF_F) { // cells of the run the ball can reach
+                        const float rx = sqrtf(fmaxf(reach2 - gyz2, 0.f)) * 1.00001f + 2e-3f * g.h;
+                        a = max(a, cell_axis(p.x - rx, g.mn[0], g.h, nx));
+                        b = min(b, cell_axis(p.x + rx, g.mn[0], g.h, nx));
+                        if (a > b) continue;
+                    }
+                } else {
                     const int x = (sgm == 0) ? c0x - r : c0x + r;
                     if (x < 0 || x >= nx) continue;
+                    const float gx = fmaxf(axis_gap(p.x, g.mn[0] + x * g.h, g.h), 0.f);
+                    if (gx * gx + gyz2 > reach2) continue;
                     a = b = x;
                 }
                 const int t0 = __ldg(&start[rowbase + a]);

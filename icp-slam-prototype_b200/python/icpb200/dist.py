@@ -21,6 +21,31 @@ def slab_bounds(dim_z, rank, world):
     return shard_range(dim_z, rank, world)
 
 
+def balanced_slab_bounds(dim_z, world, cell, origins_z, endpoints_z):
+    """Slab boundaries [b_0 = 0, ..., b_world = dim_z] that equalise the RAY WORK per slab instead of the layer count.
+
+    A ray from the camera at height origin_z to an endpoint at height z crosses every z-layer between the two, and the
+    layers it crosses are where its walk spends its steps; a room seen from one side puts almost all of that in a few
+    slabs when the split is uniform (measured: 1,029 vs 1,506,688 occupied voxels for 2 uniform slabs).  Coverage per
+    layer is accumulated with a difference array over (origin, endpoint) layer pairs; boundaries sit at equal
+    quantiles of its running sum.  Pure function of its inputs: every rank computes the same boundaries from the same
+    frames, no communication.  origins_z: one height per frame; endpoints_z: list of arrays (world z of the frame's
+    points), same length."""
+    cover = np.zeros(dim_z + 1, dtype=np.float64)
+    for oz, ez in zip(origins_z, endpoints_z):
+        lo = np.clip(np.floor(np.minimum(ez, oz) / cell).astype(np.int64), 0, dim_z - 1)
+        hi = np.clip(np.floor(np.maximum(ez, oz) / cell).astype(np.int64), 0, dim_z - 1)
+        np.add.at(cover, lo, 1.0)
+        np.add.at(cover, hi + 1, -1.0)
+    work = np.cumsum(np.cumsum(cover)[:dim_z] + 1e-9)      # tiny floor: empty layers still get an owner
+    bounds = [0]
+    for g in range(1, world):
+        b = int(np.searchsorted(work, work[-1] * g / world)) + 1
+        bounds.append(min(max(b, bounds[-1] + 1), dim_z - (world - g)))
+    bounds.append(dim_z)
+    return bounds
+
+
 def row_band(height, rank, world):
     """Image rows [r0, r1) a rank back-projects before the exchange."""
     return shard_range(height, rank, world)
@@ -75,9 +100,10 @@ class SlabMap:
     integrate(depth, pose) lifts this rank's row band on its GPU, all-gathers the points over NCCL and walks
     every ray into the local slab (icpb_map_integrate_rays clips writes to [z_lo, z_hi))."""
 
-    def __init__(self, ctx, dims, cell, rank, world, capacity):
+    def __init__(self, ctx, dims, cell, rank, world, capacity, bounds=None):
         self.ctx, self.dims, self.cell, self.rank, self.world = ctx, tuple(dims), cell, rank, world
-        self.z_lo, self.z_hi = slab_bounds(dims[2], rank, world)
+        # bounds: optional list of world+1 slab boundaries (balanced_slab_bounds); default = equal layer counts
+        self.z_lo, self.z_hi = (bounds[rank], bounds[rank + 1]) if bounds is not None else slab_bounds(dims[2], rank, world)
         self.map = ctx.map(dims, cell, self.z_lo, self.z_hi)
         self.local = ctx.cloud(capacity)
         self.full = ctx.cloud(capacity)

@@ -88,3 +88,25 @@ def test_two_rank_slabs_and_gather(tmp_path, orc):
     want = np.array([[float(i), float(i) * 2] for i in range(11)])
     for r in range(2):
         assert np.array_equal(np.load(tmp_path / f"rows_rank{r}.npy"), want)
+
+
+def test_balanced_slab_bounds_equalise_ray_work():
+    """Boundaries are a partition of [0, Z), deterministic, and split the per-layer ray coverage evenly."""
+    import numpy as np
+    from icpb200 import dist as D
+    rng = np.random.default_rng(1)
+    ez = [rng.uniform(2.5, 4.9, 50000), rng.uniform(3.0, 4.5, 50000)]
+    oz = [1.0, 1.2]
+    for world in (2, 4, 8):
+        b = D.balanced_slab_bounds(500, world, 0.01, oz, ez)
+        assert b == D.balanced_slab_bounds(500, world, 0.01, oz, ez)
+        assert b[0] == 0 and b[-1] == 500 and all(b[i] < b[i + 1] for i in range(world))
+        cover = np.zeros(500)
+        for o, e in zip(oz, ez):
+            for z in e[::50]:
+                cover[int(o / 0.01): int(z / 0.01) + 1] += 1
+        work = [cover[b[i]: b[i + 1]].sum() for i in range(world)]
+        assert max(work) < 1.15 * (sum(work) / world), (b, work)
+    # degenerate input: every slab still owns at least one layer
+    b = D.balanced_slab_bounds(16, 8, 0.01, [0.05], [np.array([0.05])])
+    assert b[0] == 0 and b[-1] == 16 and all(b[i] < b[i + 1] for i in range(8))
