@@ -9,9 +9,11 @@ none exits early.  Default workload = BASELINE.json configs[1]: full-resolution
 640x480 (~292k valid points per cloud), one B200 per rank, weak scaling (every
 rank registers its own frame pair).  Prints ONE JSON line on rank 0.
 
---impl reference times the CPU restatement of the reference path (oracle/, all
-host threads) on a bounded sample of the same workload and extrapolates; it is
-the only place besides the cpu_baseline leg where bench.py executes oracle/.
+--impl reference times the reference's own CPU code for the path (oracle/_ref:
+icp.cpp compiled unmodified by path; the oracle port when that library is
+absent) with all host threads on a bounded sample of the same workload and
+extrapolates; it is the only place besides the cpu_baseline leg where bench.py
+executes oracle/.
 """
 import argparse
 import json
@@ -107,17 +109,29 @@ def dist_setup(n_gpus):
     return rank, world, local
 
 
+def cpu_kind():
+    """"reference": the reference's own icp.cpp compiled by path (oracle/_ref/libicpref.so, built where /root/reference
+    exists and shipped to the GPU box); "port": the oracle's restatement when that library is absent."""
+    from oracle import ref
+    return "reference" if ref.available() else "port"
+
+
 def cpu_sample_registration_rate(data, target, n_threads, sample_queries, seed=0):
-    """Times ONE association pass of the oracle on a seeded sample of the queries against the full
-    target and extrapolates linearly to N queries x (ITERS+1) passes."""
+    """Times ONE association pass on a seeded sample of the queries against the full target -- the reference's own
+    getNearestPoint (icp.cpp:566-593) when oracle/_ref is there, else the oracle port -- and extrapolates linearly to
+    N queries x (ITERS+1) passes."""
     from oracle import oracle as orc
+    from oracle import ref
     rng = np.random.default_rng(seed)
     n = len(data)
     k = min(sample_queries, n)
     sel = np.sort(rng.choice(n, size=k, replace=False))
     sample = np.ascontiguousarray(data[sel])
     t0 = time.perf_counter()
-    orc.nn(sample, target, n_threads=n_threads)
+    if ref.available():
+        ref.nearest_mt(sample, target, n_threads)
+    else:
+        orc.nn(sample, target, n_threads=n_threads)
     dt = time.perf_counter() - t0
     per_reg = dt * (n / k) * (ITERS + 1)
     return 1.0 / per_reg, dt, k
@@ -141,8 +155,10 @@ def run_reference(args, rank, world):
         data = synth.subsample_exact(data, wl["points"], 1)
         target = synth.subsample_exact(target, wl["points"], 2)
     threads = os.cpu_count() or 1
-    # bounded sample: ~1-2 s of wall time per step on a many-core host
-    sample_q = max(256, min(len(data), int(2.0e9 * threads / 8 / max(len(target), 1) / 6.5)))
+    # bounded sample: ~2-4 s of wall time per step on a many-core host (18 ns/pair/thread for the reference's own
+    # code, 5.4 for the port, measured)
+    ns_pair = 18.0 if cpu_kind() == "reference" else 5.4
+    sample_q = max(256, min(len(data), int(3.0e9 * threads / max(len(target), 1) / ns_pair)))
     vals = []
     for s in range(args.warmup + args.steps):
         v, dt, k = cpu_sample_registration_rate(data, target, threads, sample_q, seed=s)
@@ -156,7 +172,7 @@ def run_reference(args, rank, world):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "n_data": int(len(data)), "n_target": int(len(target)),
                    "nn_passes": ITERS + 1},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": cpu_kind(),
                          "sample": f"each step: one association pass of {k} seeded queries against the full "
                                    f"{len(target)}-point target with {threads} OpenMP threads, extrapolated "
                                    f"linearly to {len(data)} queries x {ITERS + 1} passes"},
@@ -294,7 +310,7 @@ def run_b200(args, rank, world, local):
         from oracle import oracle as orc
         orc.build()
         dpts, tpts = pristine.download(), target.download()
-        sample_q = max(64, min(n, int(12.0 / (m * 7.0e-9))))  # ~12 s of single-thread work
+        sample_q = max(64, min(n, int(12.0 / (m * (18.0e-9 if cpu_kind() == "reference" else 5.4e-9)))))  # ~12 s, 1 thread
         cpu_v, cpu_dt, cpu_k = cpu_sample_registration_rate(dpts, tpts, 1, sample_q)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -327,7 +343,7 @@ def run_b200(args, rank, world, local):
                                         "only HBM and bf16 tensor peaks; the NN scan is FP32 CUDA-core bound)",
                          "flop_per_launch": flop_per_launch, "avg_launch_ms": avg_launch_s * 1e3,
                          "launches_timed": nn_launches},
-            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port",
+            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": cpu_kind(),
                              "sample": f"one association pass of {cpu_k} seeded queries against the full "
                                        f"{m}-point target ({cpu_dt:.2f} s), extrapolated linearly to {n} queries "
                                        f"x {ITERS + 1} passes"},

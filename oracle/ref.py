@@ -159,3 +159,11 @@ def get_transformation(depth_cur, depth_prev, bgr, keypoints_xy, max_iterations=
     lib().ref_get_transformation(_p(depth_cur), _p(depth_prev), _p(bgr), w, h, _p(kp), len(kp), int(max_iterations),
                                  C.c_float(threshold), C.c_uint(seed), _p(rigid), _p(camR), _p(camP))
     return rigid.reshape(4, 4), camR.reshape(3, 3), camP
+
+
+def nearest_mt(data, target, threads=1):
+    """getNearestPoint for every query on `threads` OpenMP threads (bench.py's CPU baseline); returns the distances."""
+    data = np.ascontiguousarray(data); target = np.ascontiguousarray(target)
+    d = np.zeros(len(data), dtype=np.float32)
+    lib().ref_nearest_mt(_p(data), len(data), _p(target), len(target), _p(d), int(threads))
+    return d

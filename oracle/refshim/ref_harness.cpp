@@ -211,6 +211,15 @@ void ref_get_transformation(const uint16_t *depth_cur, const uint16_t *depth_pre
     camP3[0] = icp::cameraPosition.x; camP3[1] = icp::cameraPosition.y; camP3[2] = icp::cameraPosition.z;
 }
 
+// CPU baseline of bench.py: getNearestPoint (icp.cpp:566-593) for every query, the query loop spread over `threads`
+// OpenMP threads (the reference itself is single threaded; every call is its own unmodified function).
+void ref_nearest_mt(const ref_point *data, int n, const ref_point *target, int m, float *d_out, int threads)
+{
+    icp::PointCloud tc; fill(tc, target, m);
+#pragma omp parallel for schedule(dynamic, 16) num_threads(threads > 0 ? threads : 1)
+    for (int i = 0; i < n; ++i) { color_point_t nn; d_out[i] = icp::getNearestPoint(to_cp(data[i]), nn, tc); }
+}
+
 // ---- 8f-4: the reference's own Quaternion class (quaternion.cpp, compiled by path); q = {w, x, y, z}
 void ref_quat_from_rot(const float *R9, float *q4) // quaternion.cpp:23-79
 {
