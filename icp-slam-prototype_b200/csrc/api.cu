@@ -1155,14 +1155,15 @@ int icpb_map_integrate_rays(icpb_map *map, const icpb_cloud *points, const float
         return fail(ctx, ICPB_ERR_INVALID, "delta out of [0,255]");
     CU(ctx, cudaSetDevice(ctx->device));
     unsigned long long *d_vis = nullptr;
+    void *misc;
+    int rc;
+    if ((rc = ws_get(ctx, WS_MISC, 64, &misc, true))) return rc;
+    unsigned int *d_next = (unsigned int *)((char *)misc + 40); // ray counter of the persistent walk kernel
     if (voxels_visited) {
-        void *misc;
-        int rc;
-        if ((rc = ws_get(ctx, WS_MISC, 64, &misc, true))) return rc;
         d_vis = (unsigned long long *)((char *)misc + 48);
         CU(ctx, cudaMemsetAsync(d_vis, 0, sizeof(unsigned long long), ctx->stream));
     }
-    launch_map_rays(map->dev, points->d_pts, points->n, origin, delta_dec, d_vis, ctx->stream);        // phase 1
+    launch_map_rays(map->dev, points->d_pts, points->n, origin, delta_dec, d_vis, d_next, ctx->sm_count, ctx->stream); // phase 1
     launch_map_endpoints(map->dev, points->d_pts, points->n, ICPB_RULE_A, delta_inc, 0, ctx->stream);  // phase 2
     ctx->launches += 2 * (points->n > 0);
     CU(ctx, cudaGetLastError());

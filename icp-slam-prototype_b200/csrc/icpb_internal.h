@@ -176,7 +176,7 @@ void launch_map_endpoints(const MapDev &m, const float4 *pts, int n, int rule, i
 void launch_map_tracked(const MapDev &m, int *table, const float4 *pts, int n, int variant, int delta, int max_conf,
                         float4 *dst, int dst_n, int dst_capacity, int *d_appended, cudaStream_t s);
 void launch_map_rays(const MapDev &m, const float4 *pts, int n, const float origin[3], int delta_dec,
-                     unsigned long long *visited, cudaStream_t s);
+                     unsigned long long *visited, unsigned int *next_ray, int sm_count, cudaStream_t s);
 
 } // namespace icpb
 

@@ -190,88 +190,138 @@ void launch_map_tracked(const MapDev &m, int *table, const float4 *pts, int n, i
 // its walls carries e_k = (2 n_k + 1) P / n_k > 2 P, larger than every real wall time, and an axis with n_k = 0
 // starts at 3 P: neither is ever selected, so the loop needs no per-axis counters.  Every voxel entered except
 // the endpoint voxel is decremented with clamp at 0.  I = int when 3 * dims product < 2^31, else long long.
+//
+// Scheduling: persistent warps, one ray per LANE, rays handed out from a global counter.  Walk lengths differ by
+// 2-4x between near and far surfaces; with one thread per ray a warp ran at 21.8 of 32 lanes and the last wave left
+// half the SMs idle.  Here a lane that finishes its ray waits only until 8 lanes of its warp are idle, then the
+// warp draws new rays for all of them at once (the set-up, ~100 instructions, is amortised over >= 8 lanes).  The
+// certainty updates commute (g^k), so the order in which rays are walked does not matter.
+constexpr int kRayRefill = 8;  // idle lanes that trigger a refill
+constexpr int kRayBurst = 16;  // walk steps between two refill checks
+
+template <typename I>
+struct RayState {
+    I ex, ey, ez, dxs, dys, dzs;
+    long long lin, stx, sty;
+    int sz, zrel, rem; // rem: walk steps still to take
+};
+
+// Set-up of ray i (also performs the visit of the slab-entry voxel when the walk is entered by a jump).
+template <typename I>
+__device__ __forceinline__ void ray_setup(const MapDev &m, const float4 p, int ox, int oy, int oz, int delta_dec,
+                                          RayState<I> &r, unsigned long long &visits)
+{
+    const int ex_ = voxel_axis(p.x, m.cell, m.dims[0]);
+    const int ey_ = voxel_axis(p.y, m.cell, m.dims[1]);
+    const int ez_ = voxel_axis(p.z, m.cell, m.dims[2]);
+    const int nx = abs(ex_ - ox), ny = abs(ey_ - oy), nz = abs(ez_ - oz);
+    const int sx = (ex_ > ox) - (ex_ < ox), sy = (ey_ > oy) - (ey_ < oy), sz = (ez_ > oz) - (ez_ < oz);
+    const I mx = nx ? nx : 1, my = ny ? ny : 1, mz = nz ? nz : 1;
+    const I P3 = 3 * mx * my * mz;
+    r.ex = nx ? my * mz : P3; r.ey = ny ? mx * mz : P3; r.ez = nz ? mx * my : P3;
+    r.dxs = 2 * my * mz; r.dys = 2 * mx * mz; r.dzs = 2 * mx * my;
+    const int steps = nx + ny + nz;
+    visits += steps > 0 ? (unsigned long long)(steps - 1) : 0ull;
+    int z = oz;
+    int done_steps = 0;
+    bool live = true, entered_now = false;
+    long long lin0 = ((long long)ox * m.dims[1] + oy) * m.zs + (oz - m.z_lo);
+    // Slab clipping: z moves monotonically, so the part of the walk inside [z_lo, z_hi) is one contiguous
+    // range of steps.  If the origin is outside the slab, jump to the state right after the z-step that
+    // enters it: that is z-step number k; by then every x / y wall with time <= (2k-1)/(2 nz) has been
+    // crossed (x and y go first on ties), i.e. floor(((2k-1) n + nz) / (2 nz)) of them.
+    if (oz < m.z_lo || oz >= m.z_hi) {
+        long long k = 0;
+        if (sz > 0 && oz < m.z_lo) k = (long long)m.z_lo - oz;
+        else if (sz < 0 && oz >= m.z_hi) k = (long long)oz - (m.z_hi - 1);
+        if (k <= 0 || k > nz) live = false; // the ray never enters this slab
+        else {
+            const long long cz = k;
+            const long long cx = nx ? min((long long)nx, ((2 * k - 1) * nx + nz) / (2LL * nz)) : 0;
+            const long long cy = ny ? min((long long)ny, ((2 * k - 1) * ny + nz) / (2LL * nz)) : 0;
+            z = oz + sz * (int)cz;
+            lin0 = ((long long)(ox + sx * (int)cx) * m.dims[1] + (oy + sy * (int)cy)) * m.zs + (z - m.z_lo);
+            if (nx) r.ex = (I)(2 * cx + 1) * my * mz;
+            if (ny) r.ey = (I)(2 * cy + 1) * mx * mz;
+            r.ez = (I)(2 * cz + 1) * mx * my;
+            done_steps = (int)(cx + cy + cz);
+            entered_now = true;
+        }
+    }
+    r.lin = lin0;
+    r.stx = (long long)sx * m.dims[1] * m.zs; r.sty = (long long)sy * m.zs;
+    r.sz = sz;
+    r.zrel = z - m.z_lo;
+    r.rem = live ? max(steps - 1 - done_steps, 0) : 0;
+    // the voxel just entered by the jump is itself a visit unless it is the endpoint
+    if (live && entered_now && done_steps <= steps - 1 && m.grid[lin0] != 0)
+        byte_rmw(m.grid, (size_t)lin0, [&](uint32_t c) { return c > (uint32_t)delta_dec ? c - delta_dec : 0u; });
+}
+
 template <typename I>
 __global__ void __launch_bounds__(128) map_rays_kernel(MapDev m, const float4 *__restrict__ pts, int n, int ox, int oy,
-                                                      int oz, int delta_dec, unsigned long long *visited)
+                                                      int oz, int delta_dec, unsigned long long *visited,
+                                                      unsigned int *next_ray)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    RayState<I> r;
+    r.ex = r.ey = r.ez = r.dxs = r.dys = r.dzs = 0;
+    r.lin = r.stx = r.sty = 0;
+    r.sz = r.zrel = r.rem = 0;
     unsigned long long my_visits = 0;
-    if (i < n) {
-        float4 p = pts[i];
-        const int ex_ = voxel_axis(p.x, m.cell, m.dims[0]);
-        const int ey_ = voxel_axis(p.y, m.cell, m.dims[1]);
-        const int ez_ = voxel_axis(p.z, m.cell, m.dims[2]);
-        const int nx = abs(ex_ - ox), ny = abs(ey_ - oy), nz = abs(ez_ - oz);
-        const int sx = (ex_ > ox) - (ex_ < ox), sy = (ey_ > oy) - (ey_ < oy), sz = (ez_ > oz) - (ez_ < oz);
-        const I mx = nx ? nx : 1, my = ny ? ny : 1, mz = nz ? nz : 1;
-        const I P3 = 3 * mx * my * mz;
-        I ex = nx ? my * mz : P3, ey = ny ? mx * mz : P3, ez = nz ? mx * my : P3;
-        const I dxs = 2 * my * mz, dys = 2 * mx * mz, dzs = 2 * mx * my;
-        const int steps = nx + ny + nz;
-        my_visits = steps > 0 ? (unsigned long long)(steps - 1) : 0ull;
-        int z = oz;
-        int done_steps = 0;
-        bool live = true;
-        long long lin0 = ((long long)ox * m.dims[1] + oy) * m.zs + (oz - m.z_lo);
-        // Slab clipping: z moves monotonically, so the part of the walk inside [z_lo, z_hi) is one contiguous
-        // range of steps.  If the origin is outside the slab, jump to the state right after the z-step that
-        // enters it: that is z-step number k; by then every x / y wall with time <= (2k-1)/(2 nz) has been
-        // crossed (x and y go first on ties), i.e. floor(((2k-1) n + nz) / (2 nz)) of them.
-        bool entered_now = false;
-        if (oz < m.z_lo || oz >= m.z_hi) {
-            long long k = 0;
-            if (sz > 0 && oz < m.z_lo) k = (long long)m.z_lo - oz;
-            else if (sz < 0 && oz >= m.z_hi) k = (long long)oz - (m.z_hi - 1);
-            if (k <= 0 || k > nz) live = false; // the ray never enters this slab
-            else {
-                const long long cz = k;
-                const long long cx = nx ? min((long long)nx, ((2 * k - 1) * nx + nz) / (2LL * nz)) : 0;
-                const long long cy = ny ? min((long long)ny, ((2 * k - 1) * ny + nz) / (2LL * nz)) : 0;
-                z = oz + sz * (int)cz;
-                lin0 = ((long long)(ox + sx * (int)cx) * m.dims[1] + (oy + sy * (int)cy)) * m.zs + (z - m.z_lo);
-                if (nx) ex = (I)(2 * cx + 1) * my * mz;
-                if (ny) ey = (I)(2 * cy + 1) * mx * mz;
-                ez = (I)(2 * cz + 1) * mx * my;
-                done_steps = (int)(cx + cy + cz);
-                entered_now = true;
+    bool drained = false; // warp-uniform: the counter has passed n
+    uint8_t *g = m.grid;
+    const unsigned zs = (unsigned)m.zs;
+    while (true) {
+        const unsigned idle = __ballot_sync(0xffffffffu, r.rem <= 0);
+        if (!drained && __popc(idle) >= kRayRefill) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(next_ray, (unsigned)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (r.rem <= 0) {
+                const unsigned i = base + (unsigned)__popc(idle & lt);
+                if (i < (unsigned)n) ray_setup<I>(m, pts[i], ox, oy, oz, delta_dec, r, my_visits);
             }
+            drained = base + (unsigned)__popc(idle) >= (unsigned)n;
         }
-        if (live) {
-            uint8_t *g = m.grid;
-            long long lin = lin0;
-            const long long stx = (long long)sx * m.dims[1] * m.zs, sty = (long long)sy * m.zs, stz = sz;
-            // the voxel just entered by the jump is itself a visit unless it is the endpoint
-            if (entered_now && done_steps <= steps - 1 && g[lin] != 0)
-                byte_rmw(g, (size_t)lin, [&](uint32_t c) { return c > (uint32_t)delta_dec ? c - delta_dec : 0u; });
-            const unsigned zs = (unsigned)m.zs;
-            int zrel = z - m.z_lo;
-            for (int s = done_steps; s + 1 < steps; ++s) {
-                const bool px = (ex <= ey) && (ex <= ez);
-                const bool py = !px && (ey <= ez);
+        if (__ballot_sync(0xffffffffu, r.rem > 0) == 0u) {
+            if (drained) break;
+            continue; // every ray drawn this round was empty (never enters the slab): draw again
+        }
+#pragma unroll 4
+        for (int k = 0; k < kRayBurst; ++k) {
+            if (r.rem > 0) {
+                const bool px = (r.ex <= r.ey) && (r.ex <= r.ez);
+                const bool py = !px && (r.ey <= r.ez);
                 const bool pz = !px && !py;
-                lin += px ? stx : (py ? sty : stz);
-                ex += px ? dxs : (I)0;
-                ey += py ? dys : (I)0;
-                ez += pz ? dzs : (I)0;
-                zrel += pz ? sz : 0;
-                if ((unsigned)zrel >= zs) break; // left the slab for good
+                r.lin += px ? r.stx : (py ? r.sty : (long long)r.sz);
+                r.ex += px ? r.dxs : (I)0;
+                r.ey += py ? r.dys : (I)0;
+                r.ez += pz ? r.dzs : (I)0;
+                r.zrel += pz ? r.sz : 0;
+                --r.rem;
+                if ((unsigned)r.zrel >= zs) r.rem = 0; // left the slab for good
                 // phase 1 only lowers values, so a cached non-zero byte is at worst stale-high: the CAS re-reads it
-                if (g[lin] != 0)
-                    byte_rmw(g, (size_t)lin, [&](uint32_t c) { return c > (uint32_t)delta_dec ? c - delta_dec : 0u; });
+                else if (g[r.lin] != 0)
+                    byte_rmw(g, (size_t)r.lin, [&](uint32_t c) { return c > (uint32_t)delta_dec ? c - delta_dec : 0u; });
             }
         }
     }
     if (visited) {
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) my_visits += __shfl_xor_sync(0xffffffffu, my_visits, off);
-        if ((threadIdx.x & 31) == 0 && my_visits) atomicAdd(visited, my_visits);
+        if (lane == 0 && my_visits) atomicAdd(visited, my_visits);
     }
 }
 
 void launch_map_rays(const MapDev &m, const float4 *pts, int n, const float origin[3], int delta_dec,
-                     unsigned long long *visited, cudaStream_t s)
+                     unsigned long long *visited, unsigned int *next_ray, int sm_count, cudaStream_t s)
 {
     if (n <= 0) return;
+    cudaMemsetAsync(next_ray, 0, sizeof(unsigned int), s);
+    // persistent grid: every resident warp slot is filled once (40 registers -> 12 CTAs of 128 threads per SM)
+    const int blocks = min((n + 127) / 128, sm_count * 12);
     // origin voxel: same quantisation as any point (map.cpp:226 uses getVoxelCoordinates too)
     int o[3];
     for (int k = 0; k < 3; ++k) {
@@ -282,9 +332,9 @@ void launch_map_rays(const MapDev &m, const float4 *pts, int n, const float orig
     }
     const double prod = 3.0 * m.dims[0] * m.dims[1] * m.dims[2];
     if (prod < 2147483647.0)
-        map_rays_kernel<int><<<(n + 127) / 128, 128, 0, s>>>(m, pts, n, o[0], o[1], o[2], delta_dec, visited);
+        map_rays_kernel<int><<<blocks, 128, 0, s>>>(m, pts, n, o[0], o[1], o[2], delta_dec, visited, next_ray);
     else
-        map_rays_kernel<long long><<<(n + 127) / 128, 128, 0, s>>>(m, pts, n, o[0], o[1], o[2], delta_dec, visited);
+        map_rays_kernel<long long><<<blocks, 128, 0, s>>>(m, pts, n, o[0], o[1], o[2], delta_dec, visited, next_ray);
 }
 
 } // namespace icpb
