@@ -196,8 +196,18 @@ void launch_map_tracked(const MapDev &m, int *table, const float4 *pts, int n, i
 // half the SMs idle.  Here a lane that finishes its ray waits only until 8 lanes of its warp are idle, then the
 // warp draws new rays for all of them at once (the set-up, ~100 instructions, is amortised over >= 8 lanes).  The
 // certainty updates commute (g^k), so the order in which rays are walked does not matter.
-constexpr int kRayRefill = 8;  // idle lanes that trigger a refill
-constexpr int kRayBurst = 16;  // walk steps between two refill checks
+#ifndef ICPB_RAY_REFILL
+#define ICPB_RAY_REFILL 8
+#endif
+#ifndef ICPB_RAY_BURST
+#define ICPB_RAY_BURST 16
+#endif
+#ifndef ICPB_RAY_GROUP
+#define ICPB_RAY_GROUP 4
+#endif
+constexpr int kRayRefill = ICPB_RAY_REFILL; // idle lanes that trigger a refill
+constexpr int kRayBurst = ICPB_RAY_BURST;   // walk steps between two refill checks
+constexpr int kRayGroup = ICPB_RAY_GROUP;   // steps whose voxel reads are issued together
 
 template <typename I>
 struct RayState {
@@ -289,23 +299,38 @@ __global__ void __launch_bounds__(128) map_rays_kernel(MapDev m, const float4 *_
             if (drained) break;
             continue; // every ray drawn this round was empty (never enters the slab): draw again
         }
-#pragma unroll 4
-        for (int k = 0; k < kRayBurst; ++k) {
-            if (r.rem > 0) {
-                const bool px = (r.ex <= r.ey) && (r.ex <= r.ez);
-                const bool py = !px && (r.ey <= r.ez);
-                const bool pz = !px && !py;
-                r.lin += px ? r.stx : (py ? r.sty : (long long)r.sz);
-                r.ex += px ? r.dxs : (I)0;
-                r.ey += py ? r.dys : (I)0;
-                r.ez += pz ? r.dzs : (I)0;
-                r.zrel += pz ? r.sz : 0;
-                --r.rem;
-                if ((unsigned)r.zrel >= zs) r.rem = 0; // left the slab for good
-                // phase 1 only lowers values, so a cached non-zero byte is at worst stale-high: the CAS re-reads it
-                else if (g[r.lin] != 0)
-                    byte_rmw(g, (size_t)r.lin, [&](uint32_t c) { return c > (uint32_t)delta_dec ? c - delta_dec : 0u; });
+        // kRayGroup steps at a time: first all the DDA advances (pure integer state), then all the voxel reads --
+        // independent loads, in flight together -- then the rare decrements.  One step per load made the walk wait a
+        // full L2 / DRAM latency per voxel (65 % of the stall samples sat on the first use of the loaded byte).
+#pragma unroll 1
+        for (int k = 0; k < kRayBurst / kRayGroup; ++k) {
+            long long at[kRayGroup];
+            bool in[kRayGroup];
+#pragma unroll
+            for (int u = 0; u < kRayGroup; ++u) {
+                in[u] = r.rem > 0;
+                if (in[u]) {
+                    const bool px = (r.ex <= r.ey) && (r.ex <= r.ez);
+                    const bool py = !px && (r.ey <= r.ez);
+                    const bool pz = !px && !py;
+                    r.lin += px ? r.stx : (py ? r.sty : (long long)r.sz);
+                    r.ex += px ? r.dxs : (I)0;
+                    r.ey += py ? r.dys : (I)0;
+                    r.ez += pz ? r.dzs : (I)0;
+                    r.zrel += pz ? r.sz : 0;
+                    --r.rem;
+                    if ((unsigned)r.zrel >= zs) { r.rem = 0; in[u] = false; } // left the slab for good
+                }
+                at[u] = r.lin;
             }
+            uint8_t v[kRayGroup];
+#pragma unroll
+            for (int u = 0; u < kRayGroup; ++u) v[u] = in[u] ? g[at[u]] : (uint8_t)0;
+            // phase 1 only lowers values, so a cached non-zero byte is at worst stale-high: the CAS re-reads it
+#pragma unroll
+            for (int u = 0; u < kRayGroup; ++u)
+                if (v[u] != 0)
+                    byte_rmw(g, (size_t)at[u], [&](uint32_t c) { return c > (uint32_t)delta_dec ? c - delta_dec : 0u; });
         }
     }
     if (visited) {

@@ -1,6 +1,5 @@
-set -x
-python -m pytest tests/test_gpu_map.py tests/test_gpu_pipeline.py tests/test_golden.py tests/test_gpu_compat.py -m gpu -x -q 2>&1 | tail -4
-python bench.py --workload map1cm 2>&1 | cut -c1-1300
-python bench.py --workload trajectory 2>&1 | cut -c1-1300
-python tools/profile_case.py --iters 0 --map --cm 1 | tail -3
-python tools/profile_case.py --iters 0 --map --cm 2 | tail -3
+for v in default g8b16 g8b32 g4b32 g8b32r4 g8b32r16 g16b32; do
+  if [ $v = default ]; then unset ICPB_LIB; else export ICPB_LIB=$PWD/icp-slam-prototype_b200/variants/lib_$v.so; fi
+  echo "== $v"; python tools/profile_case.py --iters 0 --map --cm 1 | tail -2 | sed 's/.*visited//'
+  python bench.py --workload map1cm 2>/dev/null | sed 's/.*"ms_per_step": \([0-9.]*\).*/map1cm ms_per_step \1/'
+done
