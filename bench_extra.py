@@ -141,12 +141,20 @@ def run_map1cm(args, rank, world, local):
         probe.close()
     sm = D.SlabMap(ctx, dims, cell, rank, world, 640 * 480, bounds)
 
+    # depth frames resident in HBM before the timed region (the metric's definition); int16 view of the u16 bits
+    d_depths = torch.from_numpy(np.stack(depths).astype(np.uint16).view(np.int16)).to(torch.device("cuda", local))
+    frame_bytes = 640 * 480 * 2
+
     def step(count):
         npts = vis = 0
         ctx.timer_start()
-        for (R, t), dpt in zip(poses, depths):
-            n, v = sm.integrate(dpt, K, R, t, 25, 25, count)
-            npts += n; vis += v
+        if count:   # counted pass: the host-synchronising calls, which also report the voxel visits
+            for (R, t), dpt in zip(poses, depths):
+                n, v = sm.integrate(dpt, K, R, t, 25, 25, True)
+                npts += n; vis += v
+        else:       # timed passes: the sync-free frame path, nothing returns to the host until the end
+            for f, (R, t) in enumerate(poses):
+                sm.integrate_device(d_depths.data_ptr() + f * frame_bytes, 640, 480, K, R, t, 25, 25)
         return ctx.timer_stop(), npts, vis
 
     for _ in range(args.warmup):
@@ -187,7 +195,8 @@ def run_map1cm(args, rank, world, local):
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": {"workload": f"configs[4]: {frames} full-res Kinect v1 frames into a 600x600x500 1 cm uint8 grid "
                                        "(180 MB), z-slab sharded (boundaries balanced on ray work), one all-gather of "
-                                       "lifted points per frame",
+                                       "lifted points per frame; depth frames resident in HBM, no host synchronisation "
+                                       "inside the sequence",
                            "rays_per_pass": npts, "voxels_visited_per_pass": visited, "slabs": hs,
                            "slabs_equal_single_gpu_grid": unsharded_ok,
                            "l2": "grid (180 MB) exceeds L2 at 1 GPU"},

@@ -18,7 +18,7 @@ thread_local std::string g_create_error;
 enum WsId {
     WS_DESCS = 0, WS_STATES, WS_PARAMS, WS_TGT_SOA, WS_PM1, WS_PM2, WS_PG, WS_IDX, WS_DIST, WS_CHUNKS, WS_ALT,
     WS_IDX_TRACE, WS_DIST_TRACE, WS_MISC, WS_DEPTH, WS_BGR, WS_KEEP, WS_TILESTATE, WS_IMG_A, WS_IMG_B, WS_NORMALS,
-    WS_RT, WS_GRID_META, WS_GRID_COUNTS, WS_GRID_CURSOR, WS_GRID_SUMS, WS_GRID_SORTED, WS_GRID_BBOX, WS_GRID_HEAVY, WS_BATCHSTATE, WS_TRACK, WS_PA, WS_PM3, WS_PG2, WS_MLOG, WS_REJ_FLAG, WS_REJ_PTS, WS_COUNT
+    WS_RT, WS_GRID_META, WS_GRID_COUNTS, WS_GRID_CURSOR, WS_GRID_SUMS, WS_GRID_SORTED, WS_GRID_BBOX, WS_GRID_HEAVY, WS_BATCHSTATE, WS_TRACK, WS_PA, WS_PM3, WS_PG2, WS_MLOG, WS_REJ_FLAG, WS_REJ_PTS, WS_FRAME, WS_COUNT
 };
 
 int fail(icpb_ctx *ctx, int status, const char *what, cudaError_t ce = cudaSuccess)
@@ -730,6 +730,7 @@ int icpb_cloud_from_depth_device(icpb_cloud *cloud, const void *d_depth, const v
     a.capacity = cloud->capacity;
     a.n_tiles = backproject_tiles(w, h);
     a.frames = 1;
+    a.v_offset = 0;
     a.depth_stride = a.bgr_stride = a.out_stride = a.state_stride = 0;
     void *ts;
     int rc;
@@ -788,6 +789,7 @@ int icpb_backproject_batch_device(icpb_ctx *ctx, const void *d_depth, const void
     a.capacity = capacity_per_frame;
     a.n_tiles = backproject_tiles(w, h);
     a.frames = frames;
+    a.v_offset = 0;
     a.depth_stride = (long long)w * h;
     a.bgr_stride = (long long)w * h * 3;
     a.out_stride = capacity_per_frame;
@@ -1173,6 +1175,80 @@ int icpb_map_integrate_rays(icpb_map *map, const icpb_cloud *points, const float
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         *voxels_visited = (long long)v;
     }
+    return ICPB_OK;
+}
+
+// ---- sync-free frame path (multi-GPU z-slab map and the single-GPU sequence alike) --------------------------------
+// The point count of a lifted frame never visits the host: it travels in the band's header row and every consumer
+// kernel reads it from device memory, so a sequence of frames is enqueued without a single host synchronisation.
+
+int icpb_frame_lift_band_device(icpb_ctx *ctx, const void *d_depth, int w, int h, int row0, int row1,
+                                const icpb_intrinsics *K, const float R[9], const float t[3], void *d_band,
+                                int band_capacity)
+{
+    if (!ctx || !d_depth || !K || !d_band || w <= 0 || h <= 0) return ICPB_ERR_INVALID;
+    if (row0 < 0 || row1 <= row0 || row1 > h) return fail(ctx, ICPB_ERR_INVALID, "row band outside the image");
+    if ((long long)(row1 - row0) * w > band_capacity) return fail(ctx, ICPB_ERR_CAPACITY, "band smaller than its pixel count");
+    const uint16_t *band_depth = (const uint16_t *)d_depth + (size_t)row0 * w;
+    if (((uintptr_t)band_depth & 15) != 0) return fail(ctx, ICPB_ERR_INVALID, "band depth rows must start 16-byte aligned");
+    CU(ctx, cudaSetDevice(ctx->device));
+    BackprojectArgs a;
+    a.depth = band_depth;
+    a.bgr = nullptr;
+    a.w = w; a.h = row1 - row0; a.K = *K;
+    a.rule = ICPB_SUB_NONE; a.rule_arg = 1; a.seed = 0;
+    a.keep_stream = nullptr; a.keep_stream_len = 0;
+    a.out = (float4 *)d_band + 1;           // row 0 is the header: point count in its first word
+    a.capacity = band_capacity;
+    a.n_tiles = backproject_tiles(w, a.h);
+    a.frames = 1;
+    a.v_offset = row0;
+    a.depth_stride = a.bgr_stride = a.out_stride = a.state_stride = 0;
+    void *ts;
+    int rc;
+    if ((rc = ws_get(ctx, WS_TILESTATE, sizeof(unsigned long long) * (3 * (size_t)a.n_tiles + 2), &ts, true))) return rc;
+    a.ticket = (unsigned int *)ts;
+    a.out_count = (int *)d_band;
+    a.tile_state = (unsigned long long *)ts + 2;
+    CU(ctx, cudaMemsetAsync(d_band, 0, sizeof(float4), ctx->stream));
+    launch_backproject(a, ctx->stream);
+    if (R || t) launch_transform(a.out, band_capacity, R, t, R != nullptr, t != nullptr, ctx->stream, (const int *)d_band);
+    ctx->launches += 1 + ((R || t) ? 1 : 0);
+    CU(ctx, cudaGetLastError());
+    return ICPB_OK;
+}
+
+int icpb_map_integrate_bands_device(icpb_map *map, const void *d_bands, int world, int band_capacity, const float origin[3],
+                                    int delta_dec, int delta_inc)
+{
+    if (!map || !d_bands || !origin || world <= 0 || band_capacity <= 0) return ICPB_ERR_INVALID;
+    icpb_ctx *ctx = map->ctx;
+    if (delta_dec < 0 || delta_dec > 255 || delta_inc < 0 || delta_inc > 255)
+        return fail(ctx, ICPB_ERR_INVALID, "delta out of [0,255]");
+    CU(ctx, cudaSetDevice(ctx->device));
+    void *misc;
+    int rc;
+    if ((rc = ws_get(ctx, WS_MISC, 64, &misc, true))) return rc;
+    unsigned int *d_next = (unsigned int *)((char *)misc + 40);
+    const float4 *pts;
+    const int *d_n;
+    const int cap = world * band_capacity;
+    if (world == 1) { // a single band is already the frame
+        pts = (const float4 *)d_bands + 1;
+        d_n = (const int *)d_bands;
+    } else {
+        float4 *frame;
+        if ((rc = ws_get(ctx, WS_FRAME, sizeof(float4) * (size_t)cap, (void **)&frame))) return rc;
+        int *d_total = (int *)((char *)misc + 56);
+        launch_assemble_bands((const float4 *)d_bands, world, band_capacity, frame, cap, d_total, ctx->stream);
+        ctx->launches += 1;
+        pts = frame;
+        d_n = d_total;
+    }
+    launch_map_rays(map->dev, pts, cap, origin, delta_dec, nullptr, d_next, ctx->sm_count, ctx->stream, d_n); // phase 1
+    launch_map_endpoints(map->dev, pts, cap, ICPB_RULE_A, delta_inc, 0, ctx->stream, d_n);                   // phase 2
+    ctx->launches += 2;
+    CU(ctx, cudaGetLastError());
     return ICPB_OK;
 }
 

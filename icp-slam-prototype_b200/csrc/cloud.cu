@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kBpThreads) backproject_kernel(BackprojectArgs
         // Image widths are multiples of 8 in practice (640, 512): the thread's 8 pixels then share a row and the
         // coordinates are u0 + k, exactly representable float sums; otherwise every pixel finds its own (u, v).
         const bool same_row = (a.w % kBpPix) == 0;
-        const float uf0 = (float)u0, vf0 = (float)v0;
+        const float uf0 = (float)u0, vf0 = (float)(v0 + a.v_offset);
         float4 *dst = &s_pts[k_off];
         // branch-free: all 8 pixels are lifted (a zero depth just gives z = 0), only the kept ones are stored
 #pragma unroll
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(kBpThreads) backproject_kernel(BackprojectArgs
             if (!same_row) {
                 const int pk = p0 + k, vv = pk / a.w;
                 uf = (float)(pk - vv * a.w);
-                vf = (float)vv;
+                vf = (float)(vv + a.v_offset);
             }
             const uint32_t d16 = (dw[k >> 1] >> (16 * (k & 1))) & 0xffffu;
             // (float)d for d < 2^23 without a conversion instruction: 0x4B000000 | d is 2^23 + d
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(kBpThreads) backproject_write_kernel(Backproje
         const int v0 = p0 / a.w;
         const int u0 = p0 - v0 * a.w;
         const bool same_row = (a.w % kBpPix) == 0; // see backproject_kernel
-        const float uf0 = (float)u0, vf0 = (float)v0;
+        const float uf0 = (float)u0, vf0 = (float)(v0 + a.v_offset);
         float4 *dst = &s_pts[k_off];
 #pragma unroll
         for (int k = 0; k < kBpPix; ++k) {
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(kBpThreads) backproject_write_kernel(Backproje
             if (!same_row) {
                 const int pk = p0 + k, vv = pk / a.w;
                 uf = (float)(pk - vv * a.w);
-                vf = (float)vv;
+                vf = (float)(vv + a.v_offset);
             }
             const uint32_t d16 = (dw[k >> 1] >> (16 * (k & 1))) & 0xffffu;
             const float df = __fsub_rn(__uint_as_float(0x4B000000u | d16), 8388608.0f);

@@ -125,8 +125,9 @@ void launch_nn_partial(const RegDesc *descs, int batch, int max_n, int qpt, int 
                        cudaStream_t s);
 void launch_nn_finalize(const RegDesc *descs, const IcpParamsDev *prm, int batch, int max_n, int splits,
                         int pass, int filter, cudaStream_t s);
+// n_dev (nullable): the point count lives on the device (sync-free frame path); n is then the capacity
 void launch_transform(float4 *pts, int n, const float *R, const float *t, int have_R, int have_t,
-                      cudaStream_t s);
+                      cudaStream_t s, const int *n_dev = nullptr);
 void launch_pack_band(const float4 *pts, int n, float4 *dst, cudaStream_t s);
 void launch_assemble_bands(const float4 *bands, int world, int band_capacity, float4 *out, int out_capacity, int *total,
                            cudaStream_t s);
@@ -156,6 +157,7 @@ struct BackprojectArgs {
     unsigned int *ticket;
     int n_tiles;
     // batched launch (blockIdx.y = frame): strides between consecutive frames, in elements
+    int v_offset;            // image row of the first depth row handed in (a row band of a larger frame)
     int frames;
     long long depth_stride, bgr_stride, out_stride, state_stride; // pixels, bytes, points, u64 words
 };
@@ -172,11 +174,12 @@ struct MapDev {
     float cell;
 };
 void launch_map_endpoints(const MapDev &m, const float4 *pts, int n, int rule, int delta, int max_conf,
-                          cudaStream_t s);
+                          cudaStream_t s, const int *n_dev = nullptr);
 void launch_map_tracked(const MapDev &m, int *table, const float4 *pts, int n, int variant, int delta, int max_conf,
                         float4 *dst, int dst_n, int dst_capacity, int *d_appended, cudaStream_t s);
 void launch_map_rays(const MapDev &m, const float4 *pts, int n, const float origin[3], int delta_dec,
-                     unsigned long long *visited, unsigned int *next_ray, int sm_count, cudaStream_t s);
+                     unsigned long long *visited, unsigned int *next_ray, int sm_count, cudaStream_t s,
+                     const int *n_dev = nullptr);
 
 } // namespace icpb
 

@@ -47,9 +47,10 @@ __device__ __forceinline__ void byte_rmw(uint8_t *grid, size_t lin, F fn)
 }
 
 __global__ void map_endpoints_kernel(MapDev m, const float4 *__restrict__ pts, int n, int rule, int delta,
-                                     int max_conf)
+                                     int max_conf, const int *__restrict__ n_dev)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_dev) n = min(n, *n_dev);
     const int lane = threadIdx.x & 31;
     long long lin = -1;
     if (i < n) {
@@ -71,10 +72,10 @@ __global__ void map_endpoints_kernel(MapDev m, const float4 *__restrict__ pts, i
 }
 
 void launch_map_endpoints(const MapDev &m, const float4 *pts, int n, int rule, int delta, int max_conf,
-                          cudaStream_t s)
+                          cudaStream_t s, const int *n_dev)
 {
     if (n <= 0) return;
-    map_endpoints_kernel<<<(n + 255) / 256, 256, 0, s>>>(m, pts, n, rule, delta, max_conf);
+    map_endpoints_kernel<<<(n + 255) / 256, 256, 0, s>>>(m, pts, n, rule, delta, max_conf, n_dev);
 }
 
 // M3 with the reference's lookup-table / mapCloud bookkeeping (map.cpp:101-113, 136-149, 246-259).  One CTA,
@@ -271,8 +272,9 @@ __device__ __forceinline__ void ray_setup(const MapDev &m, const float4 p, int o
 template <typename I>
 __global__ void __launch_bounds__(128) map_rays_kernel(MapDev m, const float4 *__restrict__ pts, int n, int ox, int oy,
                                                       int oz, int delta_dec, unsigned long long *visited,
-                                                      unsigned int *next_ray)
+                                                      unsigned int *next_ray, const int *__restrict__ n_dev)
 {
+    if (n_dev) n = min(n, *n_dev);
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     RayState<I> r;
@@ -341,7 +343,7 @@ __global__ void __launch_bounds__(128) map_rays_kernel(MapDev m, const float4 *_
 }
 
 void launch_map_rays(const MapDev &m, const float4 *pts, int n, const float origin[3], int delta_dec,
-                     unsigned long long *visited, unsigned int *next_ray, int sm_count, cudaStream_t s)
+                     unsigned long long *visited, unsigned int *next_ray, int sm_count, cudaStream_t s, const int *n_dev)
 {
     if (n <= 0) return;
     cudaMemsetAsync(next_ray, 0, sizeof(unsigned int), s);
@@ -357,9 +359,9 @@ void launch_map_rays(const MapDev &m, const float4 *pts, int n, const float orig
     }
     const double prod = 3.0 * m.dims[0] * m.dims[1] * m.dims[2];
     if (prod < 2147483647.0)
-        map_rays_kernel<int><<<blocks, 128, 0, s>>>(m, pts, n, o[0], o[1], o[2], delta_dec, visited, next_ray);
+        map_rays_kernel<int><<<blocks, 128, 0, s>>>(m, pts, n, o[0], o[1], o[2], delta_dec, visited, next_ray, n_dev);
     else
-        map_rays_kernel<long long><<<blocks, 128, 0, s>>>(m, pts, n, o[0], o[1], o[2], delta_dec, visited, next_ray);
+        map_rays_kernel<long long><<<blocks, 128, 0, s>>>(m, pts, n, o[0], o[1], o[2], delta_dec, visited, next_ray, n_dev);
 }
 
 } // namespace icpb

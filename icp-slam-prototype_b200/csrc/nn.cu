@@ -1043,9 +1043,10 @@ struct RtArgs {
 };
 
 // R and t travel as kernel arguments: no staging buffer, no host synchronisation
-__global__ void transform_kernel(float4 *pts, int n, RtArgs a, int have_R, int have_t)
+__global__ void transform_kernel(float4 *pts, int n, RtArgs a, int have_R, int have_t, const int *__restrict__ n_dev)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_dev) n = min(n, *n_dev);
     if (i >= n) return;
     float4 p = pts[i];
     if (have_R) {
@@ -1058,13 +1059,14 @@ __global__ void transform_kernel(float4 *pts, int n, RtArgs a, int have_R, int h
     pts[i] = p;
 }
 
-void launch_transform(float4 *pts, int n, const float *R, const float *t, int have_R, int have_t, cudaStream_t s)
+void launch_transform(float4 *pts, int n, const float *R, const float *t, int have_R, int have_t, cudaStream_t s,
+                      const int *n_dev)
 {
     if (n <= 0) return;
     RtArgs a;
     for (int k = 0; k < 9; ++k) a.R[k] = have_R ? R[k] : 0.f;
     for (int k = 0; k < 3; ++k) a.t[k] = have_t ? t[k] : 0.f;
-    transform_kernel<<<(n + 255) / 256, 256, 0, s>>>(pts, n, a, have_R, have_t);
+    transform_kernel<<<(n + 255) / 256, 256, 0, s>>>(pts, n, a, have_R, have_t, n_dev);
 }
 
 // z-slab exchange helpers: a band = one 16-byte header row (point count) followed by band_capacity point rows

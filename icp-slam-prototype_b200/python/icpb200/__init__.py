@@ -185,6 +185,13 @@ class Context:
             C.c_void_p(d_points), int(capacity_per_frame), C.c_void_p(d_counts)))
 
     # ---- image stages
+    def frame_lift_band_device(self, d_depth, w, h, row0, row1, K, R, t, d_band, band_capacity):
+        """Sync-free: rows [row0, row1) of a device-resident depth frame -> world-space band (header row + points)."""
+        Rp = None if R is None else (C.c_float * 9)(*np.asarray(R, np.float32).reshape(9))
+        tp = None if t is None else (C.c_float * 3)(*np.asarray(t, np.float32).reshape(3))
+        self.check(self.lib.icpb_frame_lift_band_device(self.h, C.c_void_p(d_depth), int(w), int(h), int(row0), int(row1),
+                                                        C.byref(K), Rp, tp, C.c_void_p(d_band), int(band_capacity)))
+
     def normals(self, depth):
         depth = np.ascontiguousarray(depth, dtype=np.uint16)
         h, w = depth.shape
@@ -375,6 +382,12 @@ class Map:
         self.ctx.check(self.ctx.lib.icpb_map_integrate_rays(self.h, cloud.h, o, delta_dec, delta_inc,
                                                            C.byref(v) if count_visits else None))
         return v.value
+
+    def integrate_bands_device(self, d_bands, world, band_capacity, origin, delta_dec=25, delta_inc=25):
+        """Sync-free: `world` device-resident bands -> ray decrements + endpoint increments on this slab."""
+        o = (C.c_float * 3)(*origin)
+        self.ctx.check(self.ctx.lib.icpb_map_integrate_bands_device(self.h, C.c_void_p(d_bands), int(world),
+                                                                    int(band_capacity), o, delta_dec, delta_inc))
 
     def voxel_coords(self, p):
         pp = (C.c_float * 3)(*p)

@@ -127,7 +127,7 @@ class SlabMap:
         self.local.pack_band_device(self._send.data_ptr(), cap)
         import torch.distributed as dist
         # a context created on torch's current stream is ordered with the collective; otherwise fence both sides
-        shared = self.ctx.lib.icpb_ctx_stream(self.ctx.h) == torch.cuda.current_stream().cuda_stream
+        shared = (self.ctx.lib.icpb_ctx_stream(self.ctx.h) or 0) == torch.cuda.current_stream().cuda_stream
         if not shared:
             self.ctx.sync()
         dist.all_gather_into_tensor(self._recv, self._send)
@@ -136,6 +136,29 @@ class SlabMap:
         n = self.full.assemble_bands_device(self._recv.data_ptr(), self.world, cap)
         v = self.map.integrate_rays(self.full, origin, delta_dec, delta_inc, count_visits)
         return n, v
+
+    def integrate_device(self, d_depth, w, h, K, R_wc, t_wc, delta_dec=25, delta_inc=25):
+        """The same frame integration without a single host synchronisation: `d_depth` is the device address of the
+        (whole) u16 frame; this rank lifts its row band into a device band (count in the header row), the bands are
+        all-gathered on the context's stream, and every consumer kernel reads the point count from device memory.
+        Needs a context created on torch's current stream (the collective is ordered by the stream)."""
+        import torch
+        r0, r1 = row_band(h, self.rank, self.world)
+        cap = (-(-h // self.world)) * w
+        if getattr(self, "_send", None) is None or self._send.shape[0] != cap + 1:
+            dev = torch.device("cuda", self.ctx.device)
+            self._send = torch.zeros((cap + 1, 4), dtype=torch.float32, device=dev)
+            self._recv = torch.zeros((self.world * (cap + 1), 4), dtype=torch.float32, device=dev)
+        if (self.ctx.lib.icpb_ctx_stream(self.ctx.h) or 0) != torch.cuda.current_stream().cuda_stream:
+            raise RuntimeError("integrate_device needs a context created on torch's current stream")
+        origin = tuple(float(x) for x in t_wc)
+        self.ctx.frame_lift_band_device(d_depth, w, h, r0, r1, K, R_wc, t_wc, self._send.data_ptr(), cap)
+        if self.world == 1:
+            self.map.integrate_bands_device(self._send.data_ptr(), 1, cap, origin, delta_dec, delta_inc)
+            return
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(self._recv, self._send)
+        self.map.integrate_bands_device(self._recv.data_ptr(), self.world, cap, origin, delta_dec, delta_inc)
 
     def download(self):
         return self.map.download()

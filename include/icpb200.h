@@ -245,6 +245,18 @@ int icpb_map_has_entry(icpb_map *map, const float p[3], int *has_entry);
 int icpb_map_integrate_rays(icpb_map *map, const icpb_cloud *points, const float origin[3],
                             int delta_dec, int delta_inc, long long *voxels_visited);
 /* Map::getVoxelCoordinates map.cpp:55-85 (host-side scalar helper). */
+/* Sync-free frame path (the z-slab map of SURVEY.md 8e, and frame sequences on one GPU).  A "band" is one 16-byte
+ * header row (point count in its first word) followed by band_capacity point rows, in device memory.
+ * icpb_frame_lift_band_device: image rows [row0, row1) of a device-resident depth frame -> world-space points of the
+ * band (pointcloud.cpp:109-165 followed by rotate / translate :321-359), count into the header; nothing returns to
+ * the host.  icpb_map_integrate_bands_device: `world` bands laid out back to back (one all-gather of the ranks' bands;
+ * rank order = raster order) -> M4 ray decrements then rule-A endpoint increments on this handle's slab, every kernel
+ * reading the point count from device memory. */
+int icpb_frame_lift_band_device(icpb_ctx *ctx, const void *d_depth, int w, int h, int row0, int row1,
+                                const icpb_intrinsics *K, const float R[9], const float t[3], void *d_band,
+                                int band_capacity);
+int icpb_map_integrate_bands_device(icpb_map *map, const void *d_bands, int world, int band_capacity,
+                                    const float origin[3], int delta_dec, int delta_inc);
 int icpb_map_voxel_coords(const icpb_map *map, const float p[3], int v[3]);
 /* Slab download in the reference's linear order restricted to the slab:
  * out[(x*dimY + y)*(z_hi-z_lo) + (z - z_lo)]. */

@@ -177,3 +177,57 @@ def test_tracked_updates_match_oracle(ctx, orc, pair10k, variant, delta):
     probe = orc.xyz_of(np.array(mine[:1], dtype=orc.POINT_DTYPE))[0]
     assert m.has_entry(tuple(float(x) for x in probe))
     m.close(); mc.close()
+
+
+def test_sync_free_frame_path_equals_the_synchronising_calls(ctx, orc):
+    """icpb_frame_lift_band_device + icpb_map_integrate_bands_device (point count kept on the device) against
+    from_depth / transform / integrate_rays: the same grid, byte for byte -- as one band, and as two row bands feeding
+    two z-slabs (the world-size-2 layout emulated on one GPU: bands back to back, as an all-gather leaves them)."""
+    import torch
+    import icpb200
+    from icpb200 import synth
+    from icpb200 import dist as D
+    K = icpb200.reference_intrinsics_v1()
+    dims, cell = (300, 300, 250), 0.02
+    poses = synth.trajectory(3, step_deg=1.0, step_m=0.03)
+    depths = [synth.render_depth(R, t, synth.KINECT_V1, seed=f) for f, (R, t) in enumerate(poses)]
+    h, w = depths[0].shape
+    dev = torch.device("cuda", ctx.device)
+    d_depths = torch.from_numpy(np.stack(depths).view(np.int16)).to(dev)
+    torch.cuda.synchronize()   # the fixture's context runs on its own stream
+
+    ref_map = ctx.map(dims, cell)
+    cl = ctx.cloud(w * h)
+    for (R, t), d in zip(poses, depths):
+        cl.from_depth(d, None, K); cl.transform(R.astype(np.float32), t.astype(np.float32))
+        ref_map.integrate_rays(cl, tuple(float(x) for x in t), 25, 25, False)
+    want = ref_map.download()
+    assert (want > 0).sum() > 1000
+
+    # one band
+    m1 = ctx.map(dims, cell)
+    cap = w * h
+    band = torch.zeros((cap + 1, 4), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    for f, (R, t) in enumerate(poses):
+        ctx.frame_lift_band_device(d_depths.data_ptr() + f * w * h * 2, w, h, 0, h, K, R, t, band.data_ptr(), cap)
+        m1.integrate_bands_device(band.data_ptr(), 1, cap, tuple(float(x) for x in t))
+    assert np.array_equal(m1.download(), want)
+
+    # two row bands, two z-slabs
+    world = 2
+    bcap = (-(-h // world)) * w
+    bands = torch.zeros((world * (bcap + 1), 4), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    slabs = [ctx.map(dims, cell, *D.slab_bounds(dims[2], g, world)) for g in range(world)]
+    for f, (R, t) in enumerate(poses):
+        for g in range(world):
+            r0, r1 = D.row_band(h, g, world)
+            ctx.frame_lift_band_device(d_depths.data_ptr() + f * w * h * 2, w, h, r0, r1, K, R, t,
+                                       bands.data_ptr() + g * (bcap + 1) * 16, bcap)
+        for g in range(world):
+            slabs[g].integrate_bands_device(bands.data_ptr(), world, bcap, tuple(float(x) for x in t))
+    got = np.concatenate([s_.download() for s_ in slabs], axis=2)
+    assert np.array_equal(got, want)
+    for x in (ref_map, m1, cl, *slabs):
+        x.close()
