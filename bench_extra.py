@@ -312,3 +312,108 @@ def run_trajectory(args, rank, world, local):
                 "extra": {"stage_wall_s": stage, "render_s_untimed": render_s}}
         print(json.dumps(line), flush=True)
     ctx.close()
+
+
+def run_live(args, rank, world, local):
+    """the per-frame loop exactly as the reference runs it (icp.cpp:28-285, key-point association
+    against the growing map cloud, rule-C map update), frames/s through the C-ABI; beside it the reference's OWN
+    icp::getTransformation (oracle/_ref, single thread like the reference) on the same frames and key-points.
+    cv::FAST is out of scope: key-points are seeded pixels with depth in every frame."""
+    import icpb200
+    from icpb200 import synth
+    torch = _setup(local, world)
+    ctx = icpb200.Context(local)
+    K = icpb200.reference_intrinsics_v1()
+    frames = args.frames or 40
+    n_kp = 1500
+    poses = synth.trajectory(frames, step_deg=0.5, step_m=0.01)
+    depths = [synth.render_depth(R, t, synth.KINECT_V1, seed=f) for f, (R, t) in enumerate(poses)]
+    h, w = depths[0].shape
+    bgr = np.random.default_rng(3).integers(0, 255, (h, w, 3), dtype=np.uint8)
+    ok = np.ones((h, w), bool)
+    for d in depths:
+        ok &= d != 0
+    ys, xs = np.nonzero(ok[8:-8, 8:-8])
+    sel = np.random.default_rng(7).choice(len(xs), n_kp, replace=False)
+    kxy = np.stack([xs[sel] + 8, ys[sel] + 8], 1).astype(np.float32)
+    # the 1-in-40 subsample decisions (rand() % 40 in the reference, pointcloud.cpp:28), drawn before the timed region
+    decs = [(np.random.default_rng(100 + f).integers(0, 40, int((d != 0).sum())) == 0).astype(np.uint8)
+            for f, d in enumerate(depths)]
+    dims, cell = (300, 300, 300), float(np.float32(10.0) / np.float32(300.0))     # map.hpp:9-10,17
+    FX, CX = np.float32(468.60), np.float32(318.27)
+
+    def lift(depth):   # pointcloud.cpp:64-97, host scalar code in the reference as well
+        x, y = kxy[:, 0].astype(np.int64), kxy[:, 1].astype(np.int64)
+        pz = depth[y, x].astype(np.float32) / np.float32(5000.0)
+        out = np.zeros(len(x), icpb200.POINT_DTYPE)
+        out["x"] = (x.astype(np.float32) - CX) * pz / FX; out["y"] = (y.astype(np.float32) - CX) * pz / FX; out["z"] = pz
+        out["c0"], out["c1"], out["c2"] = bgr[y, x, 0], bgr[y, x, 1], bgr[y, x, 2]
+        return out
+
+    def run():
+        m = ctx.map(dims, cell)
+        map_kp = ctx.cloud(1 << 18)
+        pts, kps, non = ctx.cloud(w * h), ctx.cloud(n_kp), ctx.cloud(17 * n_kp)
+        camR, camP, last_t = np.eye(3, dtype=np.float32), np.zeros(3, np.float32), np.zeros(3, np.float32)
+        started = False
+        ctx.sync()
+        t0 = time.perf_counter()
+        for f in range(1, frames):
+            cur, prev = depths[f], depths[f - 1]
+            dec = decs[f]
+            if not started:                                                             # icp.cpp:47-68
+                camR, camP = np.eye(3, dtype=np.float32), np.array([5, 5, 5], np.float32)
+                pk = ctx.cloud_from_points(lift(prev))
+                pk.transform(camR, camP)
+                m.update_tracked(pk, icpb200.TRACK_INIT, 180, 180, map_kp)
+                pk.close()
+                started = True
+            pts.from_depth(cur, bgr, K, icpb200.SUB_STREAM, 40, 0, dec)
+            kps.upload(lift(cur))
+            pts.transform(camR, camP); kps.transform(camR, camP)                        # :70-71
+            res = ctx.icp_register_keypoints(kps, pts, map_kp, 16, 1e-4, 0.1, last_translation=tuple(last_t),
+                                             non_associations=non)
+            camR = (camR @ res["cam_rotation"]).astype(np.float32)
+            camP = (camP + res["cam_position"]).astype(np.float32)
+            last_t = (-res["offset"]).astype(np.float32)
+            if res["n_assoc"] > 0 and non.n > 0:
+                m.update_tracked(non, icpb200.TRACK_NONASSOC, 25, 180, map_kp)          # :271
+        ctx.sync()
+        dt = time.perf_counter() - t0
+        out = (dt, camR, camP, map_kp.n)
+        for c in (m, map_kp, pts, kps, non):
+            c.close()
+        return out
+
+    run()
+    _barrier(torch, world)
+    dt, camR, camP, n_map = run()
+    _barrier(torch, world)
+    tot = _max_over_ranks(torch, world, local, dt * 1e3)
+    if rank == 0:
+        cpu = None
+        try:
+            from oracle import ref
+            if ref.available():
+                ref.map_reset()
+                k = min(frames, 9)
+                t0 = time.perf_counter()
+                for f in range(1, k):
+                    _, rR, rP = ref.get_transformation(depths[f], depths[f - 1], bgr, kxy, 16, 1e-4, 1 if f == 1 else 12345 + f)
+                cdt = time.perf_counter() - t0
+                cpu = {"value": (k - 1) / cdt, "unit": "frames/s", "cores": 1, "kind": "reference",
+                       "sample": f"the reference's own icp::getTransformation (oracle/_ref) on the first {k - 1} frame pairs "
+                                 f"of the same sequence, {n_kp} key-points ({cdt:.2f} s)"}
+        except Exception as e:  # the library is test infrastructure; the GPU number stands without it
+            cpu = {"unavailable": str(e)}
+        line = {"metric": "live_loop_frames_per_s", "value": world * (frames - 1) / (tot * 1e-3), "unit": "frames/s",
+                "n_gpus": world, "steps": 1, "warmup": 1, "ms_per_step": tot, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"8f-2: {frames - 1} Kinect v1 frame pairs through the reference's live loop "
+                                       f"(1-in-40 subsampled cloud, {n_kp} key-points against the growing map cloud, "
+                                       "16 iterations max, threshold 1e-4, rule-C map update on the 300^3 grid); includes "
+                                       "host->device copies of every frame",
+                           "map_keypoints_at_end": int(n_map), "per_rank": "replica of the same sequence"},
+                "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    ctx.close()

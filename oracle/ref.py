@@ -148,6 +148,22 @@ def quat_inverse(a):
     return o
 
 
+class _quiet_stdout:
+    """The reference prints its MSE and map size to std::cout (icp.cpp:264,279): keep that out of the caller's stdout."""
+
+    def __enter__(self):
+        import sys
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        self._null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self._null, 1)
+
+    def __exit__(self, *exc):
+        lib().ref_flush_stdout()
+        os.dup2(self._saved, 1)
+        os.close(self._null); os.close(self._saved)
+
+
 def get_transformation(depth_cur, depth_prev, bgr, keypoints_xy, max_iterations=16, threshold=1e-4, seed=1):
     """The reference's own icp::getTransformation (live key-point variant) on its process-global map / camera pose.
     Returns (rigid 4x4, cameraRotation, cameraPosition) after the call."""
@@ -156,8 +172,9 @@ def get_transformation(depth_cur, depth_prev, bgr, keypoints_xy, max_iterations=
     kp = np.ascontiguousarray(keypoints_xy, dtype=np.float32).reshape(-1, 2)
     h, w = depth_cur.shape
     rigid = np.zeros(16, np.float32); camR = np.zeros(9, np.float32); camP = np.zeros(3, np.float32)
-    lib().ref_get_transformation(_p(depth_cur), _p(depth_prev), _p(bgr), w, h, _p(kp), len(kp), int(max_iterations),
-                                 C.c_float(threshold), C.c_uint(seed), _p(rigid), _p(camR), _p(camP))
+    with _quiet_stdout():
+        lib().ref_get_transformation(_p(depth_cur), _p(depth_prev), _p(bgr), w, h, _p(kp), len(kp), int(max_iterations),
+                                     C.c_float(threshold), C.c_uint(seed), _p(rigid), _p(camR), _p(camP))
     return rigid.reshape(4, 4), camR.reshape(3, 3), camP
 
 

@@ -3,7 +3,9 @@
 // extern "C" entry points around the reference's OWN functions, compiled unmodified and by path
 // from /root/reference against oracle/refshim/opencv2/cvshim.hpp.  Used only by tests/ (and the
 // golden-vector generator) to pin the hand-written oracle.  Nothing here is shipped or timed.
+#include <cstdio>
 #include <cstdlib>
+#include <iostream>
 #include <new>
 
 #include "opencv2/imgproc/imgproc.hpp"
@@ -219,6 +221,8 @@ void ref_nearest_mt(const ref_point *data, int n, const ref_point *target, int m
 #pragma omp parallel for schedule(dynamic, 16) num_threads(threads > 0 ? threads : 1)
     for (int i = 0; i < n; ++i) { color_point_t nn; d_out[i] = icp::getNearestPoint(to_cp(data[i]), nn, tc); }
 }
+
+void ref_flush_stdout() { std::cout.flush(); fflush(stdout); }
 
 // ---- 8f-4: the reference's own Quaternion class (quaternion.cpp, compiled by path); q = {w, x, y, z}
 void ref_quat_from_rot(const float *R9, float *q4) // quaternion.cpp:23-79
