@@ -97,9 +97,10 @@ void choose_nn_config(const icpb_ctx *ctx, int max_n, int max_m, int batch, int 
     long long s = (slots + (long long)tiles * batch - 1) / ((long long)tiles * batch);
     s = std::max<long long>(1, std::min<long long>(s, std::max(1, ngroups / 4)));
     // large scans: ~12 CTAs per SM so the tail (SMs running their last CTA alone) stays short,
-    // as long as every split still streams >= 128 groups (4096 targets)
+    // as long as every split still streams >= 64 groups (2048 targets; batches of 10k-point registrations: 3 splits,
+    // +11 % on bench.py --workload batch10k)
     const long long fine = ((long long)ctx->sm_count * 12 + (long long)tiles * batch - 1) / ((long long)tiles * batch);
-    if (fine > s && ngroups / fine >= 128) s = fine;
+    if (fine > s && ngroups / fine >= 64) s = fine;
     s = env_int("ICPB_SPLITS", (int)s);
     s = std::max<long long>(1, std::min<long long>(s, ngroups));
     *qpt = q;
