@@ -735,11 +735,9 @@ int icpb_cloud_from_depth_device(icpb_cloud *cloud, const void *d_depth, const v
     a.depth_stride = a.bgr_stride = a.out_stride = a.state_stride = 0;
     void *ts;
     int rc;
-    // [ticket (u32) | pad][out_count (i32) | pad][2*n_tiles status words]: fixed positions, so a
-    // different image size never reinterprets stale status words as the ticket
+    // [reserved word][out_count (i32) | pad][2*n_tiles epoch-tagged status words][n_tiles words of per-tile counts]
     // (+ n_tiles words: the per-tile counts of the two-pass kernels, kept apart from the epoch-tagged status words)
     if ((rc = ws_get(ctx, WS_TILESTATE, sizeof(unsigned long long) * (3 * (size_t)a.n_tiles + 2), &ts, true))) return rc;
-    a.ticket = (unsigned int *)ts;
     a.out_count = (int *)((unsigned long long *)ts + 1);
     a.tile_state = (unsigned long long *)ts + 2;
     launch_backproject(a, ctx->stream);
@@ -794,11 +792,10 @@ int icpb_backproject_batch_device(icpb_ctx *ctx, const void *d_depth, const void
     a.depth_stride = (long long)w * h;
     a.bgr_stride = (long long)w * h * 3;
     a.out_stride = capacity_per_frame;
-    a.state_stride = 3LL * a.n_tiles + 2; // ticket, count, 2 n_tiles status words, n_tiles words of per-tile counts
+    a.state_stride = 3LL * a.n_tiles + 2; // reserved, count, 2 n_tiles status words, n_tiles words of per-tile counts
     void *ts;
     int rc;
     if ((rc = ws_get(ctx, WS_BATCHSTATE, sizeof(unsigned long long) * (size_t)a.state_stride * frames, &ts, true))) return rc;
-    a.ticket = (unsigned int *)ts;
     a.out_count = (int *)((unsigned long long *)ts + 1);
     a.tile_state = (unsigned long long *)ts + 2;
     launch_backproject(a, ctx->stream);
@@ -1208,7 +1205,6 @@ int icpb_frame_lift_band_device(icpb_ctx *ctx, const void *d_depth, int w, int h
     void *ts;
     int rc;
     if ((rc = ws_get(ctx, WS_TILESTATE, sizeof(unsigned long long) * (3 * (size_t)a.n_tiles + 2), &ts, true))) return rc;
-    a.ticket = (unsigned int *)ts;
     a.out_count = (int *)d_band;
     a.tile_state = (unsigned long long *)ts + 2;
     CU(ctx, cudaMemsetAsync(d_band, 0, sizeof(float4), ctx->stream));

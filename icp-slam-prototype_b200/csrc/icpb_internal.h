@@ -154,7 +154,6 @@ struct BackprojectArgs {
     int capacity;
     int *out_count;          // device: number of points written
     unsigned long long *tile_state; // device scratch, zeroed by the launcher
-    unsigned int *ticket;
     int n_tiles;
     // batched launch (blockIdx.y = frame): strides between consecutive frames, in elements
     int v_offset;            // image row of the first depth row handed in (a row band of a larger frame)

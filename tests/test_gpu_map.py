@@ -231,3 +231,30 @@ def test_sync_free_frame_path_equals_the_synchronising_calls(ctx, orc):
     assert np.array_equal(got, want)
     for x in (ref_map, m1, cl, *slabs):
         x.close()
+
+
+def test_frame_band_argument_checks(ctx):
+    """The sync-free calls cannot report a capacity problem after the fact (the count never reaches the host), so
+    everything that can be checked is checked before anything is enqueued."""
+    import torch
+    import icpb200
+    K = icpb200.reference_intrinsics_v1()
+    dev = torch.device("cuda", ctx.device)
+    depth = torch.zeros((480, 640), dtype=torch.int16, device=dev)
+    band = torch.zeros((640 * 480 + 1, 4), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    with pytest.raises(icpb200.IcpbError) as e:      # band smaller than its pixel count
+        ctx.frame_lift_band_device(depth.data_ptr(), 640, 480, 0, 480, K, None, None, band.data_ptr(), 640 * 240)
+    assert e.value.status == icpb200.ERR_CAPACITY
+    for r0, r1 in ((-1, 10), (10, 10), (0, 481)):   # rows outside the image / empty band
+        with pytest.raises(icpb200.IcpbError) as e:
+            ctx.frame_lift_band_device(depth.data_ptr(), 640, 480, r0, r1, K, None, None, band.data_ptr(), 640 * 480)
+        assert e.value.status == icpb200.ERR_INVALID
+    # an all-zero band: count 0 in the header, integrating it changes nothing
+    ctx.frame_lift_band_device(depth.data_ptr(), 640, 480, 0, 480, K, None, None, band.data_ptr(), 640 * 480)
+    m = ctx.map((300, 300, 250), 0.02)
+    m.integrate_bands_device(band.data_ptr(), 1, 640 * 480, (3.0, 3.0, 1.0))
+    ctx.sync()
+    assert int(band[0, 0].view(torch.int32).item()) == 0
+    assert int(m.download().sum()) == 0
+    m.close()
