@@ -319,7 +319,8 @@ def run_b200(args, rank, world, local):
             "config": {"workload": wl["name"], "n_data": n, "n_target": m, "icp_iterations": ITERS,
                        "nn_passes": ITERS + 1, "solve_mode": "reference", "per_rank": "one frame pair per GPU",
                        "l2": "flushed between timed steps (256 MiB device write)",
-                       "nn_filter": "centred" if res["nn_filter_used"] == icpb200.FILTER_CENTRED else "direct",
+                       "nn_filter": {icpb200.FILTER_DIRECT: "direct", icpb200.FILTER_WARP: "warp-centred (Morton-ordered queries)",
+                                     icpb200.FILTER_CENTRED: "thread-centred"}[res["nn_filter_used"]],
                        "nn_qpt": res["nn_qpt"], "nn_splits": res["nn_splits"],
                        "exact_rescans_last_step": res["exact_rescans"]},
             "extra": {"nn_correspondences_per_s": world * n * (ITERS + 1) / (ms_per_step * 1e-3),
@@ -332,13 +333,14 @@ def run_b200(args, rank, world, local):
                                           "registrations_per_s": 1000.0 / float(np.mean(grid_ms)),
                                           "cell_m": res_g["grid_cell_used"], "pose_identical_to_brute_force": grid_same_pose}},
             "roofline": {"bound": "fp32",
-                         "kernel": ("nn_partial_centred_kernel" if res["nn_filter_used"] == icpb200.FILTER_CENTRED
-                                    else "nn_partial_kernel") + f"<{res['nn_qpt']}>",
+                         "kernel": {icpb200.FILTER_DIRECT: "nn_partial_kernel", icpb200.FILTER_WARP: "nn_partial_warp_kernel",
+                                    icpb200.FILTER_CENTRED: "nn_partial_centred_kernel"}[res["nn_filter_used"]]
+                                   + f"<{res['nn_qpt']}>",
                          "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one nn_partial launch at this workload, from the
-                         # ncu --set full capture summarised in profiles/r01_ncu_nn_centred_fullres.txt (targets stay in L2; 8.2 MB read + 17.6 MB of per-split records written)
-                         "traffic": 25856768 if not wl["points"] else None,
+                         # ncu --set full capture summarised in profiles/r01_ncu_nn_warp_fullres.txt (targets stay in L2; 9.6 MB read + 26.3 MB of per-split records written)
+                         "traffic": 35862784 if not wl["points"] else None,
                          "peak_source": "FFMA micro-benchmark measured in this run (MEASURED_PEAKS.json holds "
                                         "only HBM and bf16 tensor peaks; the NN scan is FP32 CUDA-core bound)",
                          "flop_per_launch": flop_per_launch, "avg_launch_ms": avg_launch_s * 1e3,

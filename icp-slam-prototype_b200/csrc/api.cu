@@ -18,7 +18,7 @@ thread_local std::string g_create_error;
 enum WsId {
     WS_DESCS = 0, WS_STATES, WS_PARAMS, WS_TGT_SOA, WS_PM1, WS_PM2, WS_PG, WS_IDX, WS_DIST, WS_CHUNKS, WS_ALT,
     WS_IDX_TRACE, WS_DIST_TRACE, WS_MISC, WS_DEPTH, WS_BGR, WS_KEEP, WS_TILESTATE, WS_IMG_A, WS_IMG_B, WS_NORMALS,
-    WS_RT, WS_GRID_META, WS_GRID_COUNTS, WS_GRID_CURSOR, WS_GRID_SUMS, WS_GRID_SORTED, WS_GRID_BBOX, WS_GRID_HEAVY, WS_BATCHSTATE, WS_TRACK, WS_PA, WS_PM3, WS_PG2, WS_MLOG, WS_REJ_FLAG, WS_REJ_PTS, WS_FRAME, WS_COUNT
+    WS_RT, WS_GRID_META, WS_GRID_COUNTS, WS_GRID_CURSOR, WS_GRID_SUMS, WS_GRID_SORTED, WS_GRID_BBOX, WS_GRID_HEAVY, WS_BATCHSTATE, WS_TRACK, WS_PA, WS_PM3, WS_PG2, WS_MLOG, WS_REJ_FLAG, WS_REJ_PTS, WS_FRAME, WS_PERM, WS_COUNT
 };
 
 int fail(icpb_ctx *ctx, int status, const char *what, cudaError_t ce = cudaSuccess)
@@ -84,13 +84,13 @@ void choose_nn_config(const icpb_ctx *ctx, int max_n, int max_m, int batch, int 
 {
     // Centred filter: the per-thread centring of the targets is amortised over the thread's queries, so large
     // scans take 12 queries per thread (168 registers, 3 CTAs per SM); direct filter: 8.
-    int q = (filter == kFilterCentred && max_n >= 50000) ? 12 : 8;
+    int q = (filter != kFilterDirect && max_n >= 50000) ? 12 : 8;
     const long long slots = (long long)ctx->sm_count * 4; // ~4 resident 128-thread CTAs per SM
     auto tiles_of = [&](int qq) { return (long long)((max_n + kNnThreads * qq - 1) / (kNnThreads * qq)) * batch; };
     // small problems: smaller query tiles give the grid more CTAs before the targets must be split
     if (tiles_of(8) < slots / 8) q = 4;
     q = env_int("ICPB_QPT", q);
-    if (filter == kFilterCentred) { if (q != 2 && q != 4 && q != 8 && q != 12 && q != 16) q = 8; }
+    if (filter != kFilterDirect) { if (q != 2 && q != 4 && q != 8 && q != 12 && q != 16) q = 8; }
     else if (q != 2 && q != 4 && q != 8) q = 8;
     const int tiles = (max_n + kNnThreads * q - 1) / (kNnThreads * q);
     const int ngroups = (max_m + kGroup - 1) / kGroup;
@@ -139,7 +139,10 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
     if (trace && count != 1) return fail(ctx, ICPB_ERR_INVALID, "traces are only supported for a single registration");
 
     int qpt, splits;
-    const int filter = env_int("ICPB_NN_FILTER", prm->nn_filter) == kFilterDirect ? kFilterDirect : kFilterCentred;
+    int filter = env_int("ICPB_NN_FILTER", prm->nn_filter);
+    if (filter != kFilterDirect && filter != kFilterWarp && filter != kFilterCentred)
+        filter = (count == 1 && max_n >= 50000) ? kFilterWarp : kFilterCentred; // ICPB_FILTER_AUTO
+    if (filter == kFilterWarp && count != 1) filter = kFilterCentred; // the spatial sort is built per single registration
     choose_nn_config(ctx, max_n, max_m, count, filter, &qpt, &splits);
 
     RegDesc *d_descs;
@@ -188,6 +191,11 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         if ((rc = ws_get(ctx, WS_DIST_TRACE, (size_t)passes * max_n * sizeof(float), (void **)&d_dist_trace)))
             return rc;
         CU(ctx, cudaMemsetAsync(d_dist_trace, 0, (size_t)passes * max_n * sizeof(float), ctx->stream));
+    }
+
+    int *d_perm = nullptr;
+    if (filter == kFilterWarp) {
+        if ((rc = ws_get(ctx, WS_PERM, sizeof(int) * (size_t)max_n, (void **)&d_perm))) return rc;
     }
 
     // ---- ICPB_NN_GRID: bucket the (fixed) target once per registration
@@ -280,6 +288,7 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         d.pm2 = d_pm2 + off_n * splits;
         d.pg = d_pg + off_n * splits;
         d.pa = d_pa + off_n;
+        d.perm = d_perm;
         d.pm3 = d_pm3 + off_n * splits;
         d.pg2 = d_pg2 + off_n * splits;
         d.idx = d_idx + off_n;
@@ -321,6 +330,14 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
 
     long long launches = 0;
     CU(ctx, cudaEventRecord(ctx->ev0, st));
+    if (filter == kFilterWarp && !grid_mode) {
+        // Morton order of the queries, once per registration (inside the timed region)
+        int *d_scnt, *d_ssum;
+        if ((rc = ws_get(ctx, WS_GRID_COUNTS, sizeof(int) * ((size_t)spatial_sort_cells() + 1), (void **)&d_scnt))) return rc;
+        if ((rc = ws_get(ctx, WS_GRID_SUMS, sizeof(int) * ((size_t)spatial_sort_cells() / 4096 + 8), (void **)&d_ssum))) return rc;
+        launch_spatial_sort(h_descs[0].D[0], h_descs[0].n, d_scnt, d_ssum, d_perm, st);
+        launches += 5;
+    }
     if (grid_mode) {
         CU(ctx, cudaMemcpyAsync(d_gmeta, &gm, sizeof(gm), cudaMemcpyHostToDevice, st));
         CU(ctx, cudaMemsetAsync(d_gcounts, 0, sizeof(int) * ((size_t)gm.ncells + 1), st));

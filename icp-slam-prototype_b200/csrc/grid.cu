@@ -177,6 +177,62 @@ void launch_grid_build(const float4 *tgt, int m, const GridMeta &g, int *counts,
     grid_scatter_kernel<<<(m + 255) / 256, 256, 0, s>>>(tgt, m, g, cursor, sorted);
 }
 
+// ---- spatial order of the QUERIES for the warp-centred brute-force filter (nn.cu) --------------------------------
+// Counting sort of the data cloud by the Morton code of a 64^3 grid of 12.5 cm cells around the cloud's first point
+// (clamped: a far-away point only lands in a border cell).  The order is a performance matter only -- it decides
+// which queries share a warp, never what any query's result is -- so neither the clamping nor the arbitrary order
+// inside a cell matters.  perm[slot] = original index.
+constexpr int kSortBits = 6;
+constexpr int kSortCells = 1 << (3 * kSortBits);
+constexpr float kSortCell = 0.125f;
+
+__device__ __forceinline__ unsigned int spread3(unsigned int v) // 6 bits -> every third bit
+{
+    v &= 0x3fu;
+    v = (v | (v << 8)) & 0x300fu;
+    v = (v | (v << 4)) & 0x30c3u;
+    v = (v | (v << 2)) & 0x9249u;
+    return v;
+}
+
+__device__ __forceinline__ int sort_key(const float4 p, const float4 ref)
+{
+    const int half = 1 << (kSortBits - 1);
+    const int cx = min(max((int)floorf((p.x - ref.x) / kSortCell) + half, 0), 2 * half - 1);
+    const int cy = min(max((int)floorf((p.y - ref.y) / kSortCell) + half, 0), 2 * half - 1);
+    const int cz = min(max((int)floorf((p.z - ref.z) / kSortCell) + half, 0), 2 * half - 1);
+    return (int)(spread3((unsigned)cx) | (spread3((unsigned)cy) << 1) | (spread3((unsigned)cz) << 2));
+}
+
+__global__ void sort_count_kernel(const float4 *__restrict__ pts, int n, int *counts)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    atomicAdd(&counts[sort_key(pts[i], pts[0])], 1);
+}
+
+__global__ void sort_scatter_kernel(const float4 *__restrict__ pts, int n, int *cursor, int *perm)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    perm[atomicAdd(&cursor[sort_key(pts[i], pts[0])], 1)] = i;
+}
+
+int spatial_sort_cells() { return kSortCells; }
+
+// counts: kSortCells + 1 ints (zeroed here); block_sums: kSortCells / 4096 + 8 ints; perm: n ints.
+void launch_spatial_sort(const float4 *pts, int n, int *counts, int *block_sums, int *perm, cudaStream_t s)
+{
+    const int nc = kSortCells + 1;
+    cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)nc, s);
+    sort_count_kernel<<<(n + 255) / 256, 256, 0, s>>>(pts, n, counts);
+    const int nblocks = (nc + kScanTile - 1) / kScanTile;
+    scan_reduce_kernel<<<nblocks, kScanThreads, 0, s>>>(counts, nc, block_sums);
+    scan_sums_kernel<<<1, kScanThreads, 0, s>>>(block_sums, nblocks);
+    scan_apply_kernel<<<nblocks, kScanThreads, 0, s>>>(counts, nc, block_sums);
+    sort_scatter_kernel<<<(n + 255) / 256, 256, 0, s>>>(pts, n, counts, perm); // counts doubles as the cursor: not reused
+}
+
 // ---- the search ------------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ float exact_distance_xyz(float ax, float ay, float az, float bx, float by, float bz, float &xyz)

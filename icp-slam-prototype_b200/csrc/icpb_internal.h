@@ -36,6 +36,7 @@ constexpr float kBandAbs = 1.0e-30f;
 // the two filters of the brute-force scan (nn.cu)
 constexpr int kFilterCentred = ICPB_FILTER_CENTRED; // |t'|^2 - 2a'.t' about a per-thread centre: 3 per pair + 6 per target per thread
 constexpr int kFilterDirect = ICPB_FILTER_DIRECT;   // (a-t)^2 in packed FP32: 6 FMA-pipe lane-ops per pair
+constexpr int kFilterWarp = ICPB_FILTER_WARP;       // the centred form about a per-WARP centre over spatially sorted queries
 // centred filter: the W-gap that proves "strictly farther" is kBandCentredA * A + kBandCentredX * max(W_best + A, 0);
 // the bound at nn_partial_centred_kernel needs 16u A + 103u X (u = 2^-24), used with ~10 % slack
 constexpr float kBandCentredA = 18.0f * 5.9604644775390625e-08f;
@@ -96,7 +97,8 @@ struct RegDesc {
     float *pm1, *pm2;        // [S][n_stride] best / second-best group minimum (approximate squared distance)
     float *pm3;              // [S][n_stride] centred filter only: third-best group minimum
     int *pg2;                // [S][n_stride] centred filter only: group holding pm2 (-1: none)
-    float *pa;               // [n_stride] centred filter only: |a - c|^2 of every query about its thread's centre
+    const int *perm;         // warp-centred filter only: [n] original index of the query in sorted slot k
+    float *pa;               // [n_stride] centred filters only: |a - c|^2 of every query about its thread's centre
     int *pg;                 // [S][n_stride] group holding pm1
     int *idx;                // [n] nearest target index
     float *dist;             // [n] nearest distance (reference arithmetic)
@@ -140,6 +142,8 @@ void launch_grid_bbox(const float4 *tgt, int m, unsigned int *bbox, cudaStream_t
 void launch_grid_build(const float4 *tgt, int m, const GridMeta &g, int *counts, int *cursor, int *block_sums,
                        float4 *sorted, cudaStream_t s);
 void launch_nn_grid(const RegDesc *descs, int batch, int max_n, int pass, int sm_count, cudaStream_t s);
+int spatial_sort_cells();
+void launch_spatial_sort(const float4 *pts, int n, int *counts, int *block_sums, int *perm, cudaStream_t s);
 
 struct BackprojectArgs {
     const uint16_t *depth;

@@ -487,6 +487,206 @@ __global__ void __launch_bounds__(kNnThreads, (QPT >= 16 ? 2 : QPT >= 12 ? 3 : 4
     }
 }
 
+// --------------------------------------------------------------------------
+// nn_partial_warp: the centred filter about ONE centre per warp
+// --------------------------------------------------------------------------
+//
+// Same filter value and the same error bound as nn_partial_centred_kernel, with c the centre of the WARP's queries:
+// the 32 targets of a group are centred once per warp -- lane l lifts target l into a warp-private shared-memory
+// buffer -- instead of once per thread, which removes the 12 packed operations per 4-target step that the
+// per-thread centring costs (7 - 9 % of the scan).  A warp's queries must then be spatial neighbours: threads take
+// their queries through d.perm, the Morton order built once per registration (grid.cu); a rigid motion keeps
+// neighbours neighbours, so the order is not rebuilt between passes.  A = |a - c|^2 is larger than with per-thread
+// centres (decimetres instead of centimetres), so a few more queries need the second group or the full rescan.
+template <int QPT>
+__global__ void __launch_bounds__(kNnThreads, (QPT >= 16 ? 2 : QPT >= 12 ? 3 : 4)) nn_partial_warp_kernel(
+    const RegDesc *__restrict__ descs, int splits, int pass)
+{
+    const RegDesc d = descs[blockIdx.z]; // by value: no pointer reloads after stores
+    IcpState *st = d.st;
+    if (st->done) return;
+    const int n = d.n;
+    const int q0 = blockIdx.x * (kNnThreads * QPT);
+    if (q0 >= n) return;
+    const int split = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    const int gps = (d.ngroups + splits - 1) / splits;
+    const int g_begin = split * gps;
+    const int g_end = min(d.ngroups, g_begin + gps);
+    const int n_tiles = (g_end > g_begin) ? (g_end - g_begin + kStageGroups - 1) / kStageGroups : 0;
+
+    constexpr int kStageFloats = kStageGroups * kGroup * 3;
+    __shared__ __align__(128) float s_tile[kStages][kStageFloats];
+    __shared__ __align__(16) float s_wb[kNnThreads / 32][2][4 * kGroup]; // per warp, double buffered: x32 y32 z32 n32
+    __shared__ __align__(8) uint64_t s_full[kStages];
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&s_full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const float *soa = d.tgt_soa;
+    auto issue = [&](int tile) {
+        int gb = g_begin + tile * kStageGroups;
+        int ng = min(kStageGroups, g_end - gb);
+        uint32_t bytes = (uint32_t)ng * (kGroup * 3 * sizeof(float));
+        int s = tile % kStages;
+        mbar_expect_tx(&s_full[s], bytes);
+        tma_bulk_g2s(&s_tile[s][0], soa + (size_t)gb * (kGroup * 3), bytes, &s_full[s]);
+    };
+    if (tid == 0) {
+        for (int t = 0; t < kStages && t < n_tiles; ++t) issue(t);
+    }
+
+    // ---- queries: QPT consecutive SORTED slots per thread; apply the pending rigid motion, hand on to the next buffer
+    const float4 *src = d.D[pass & 1];
+    float4 *dst = d.D[(pass + 1) & 1];
+    const int apply = st->apply;
+    float R[9], T[3];
+    if (apply) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[k] = st->Rf[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) T[k] = st->tf[k];
+    }
+    const int k0 = q0 + tid * QPT;
+    int qi[QPT];
+    float ax[QPT], ay[QPT], az[QPT];
+    float lox = CUDART_INF_F, loy = CUDART_INF_F, loz = CUDART_INF_F;
+    float hix = -CUDART_INF_F, hiy = -CUDART_INF_F, hiz = -CUDART_INF_F;
+#pragma unroll
+    for (int q = 0; q < QPT; ++q) {
+        const int k = k0 + q;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        qi[q] = -1;
+        if (k < n) {
+            const int i = d.perm[k];
+            qi[q] = i;
+            p = src[i];
+            if (apply) p = apply_rt(p, R, T);
+            if (split == 0) dst[i] = p;
+            lox = fminf(lox, p.x); loy = fminf(loy, p.y); loz = fminf(loz, p.z);
+            hix = fmaxf(hix, p.x); hiy = fmaxf(hiy, p.y); hiz = fmaxf(hiz, p.z);
+        }
+        ax[q] = p.x; ay[q] = p.y; az[q] = p.z;
+    }
+    // centre of the warp's queries (any value is valid; it only sets the size of the error bound)
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        lox = fminf(lox, __shfl_xor_sync(0xffffffffu, lox, off)); hix = fmaxf(hix, __shfl_xor_sync(0xffffffffu, hix, off));
+        loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, off)); hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, off));
+        loz = fminf(loz, __shfl_xor_sync(0xffffffffu, loz, off)); hiz = fmaxf(hiz, __shfl_xor_sync(0xffffffffu, hiz, off));
+    }
+    const bool any_query = lox <= hix; // false only for a warp past the end of the cloud
+    const float cx = any_query ? 0.5f * lox + 0.5f * hix : 0.f, cy = any_query ? 0.5f * loy + 0.5f * hiy : 0.f,
+                cz = any_query ? 0.5f * loz + 0.5f * hiz : 0.f;
+#pragma unroll
+    for (int q = 0; q < QPT; ++q) {
+        const bool v = qi[q] >= 0;
+        const float x = v ? ax[q] - cx : 0.f, y = v ? ay[q] - cy : 0.f, z = v ? az[q] - cz : 0.f;
+        if (v && split == 0) d.pa[qi[q]] = (x * x + y * y) + z * z;
+        ax[q] = 2.f * x; ay[q] = 2.f * y; az[q] = 2.f * z;
+    }
+
+    float m1[QPT], m2[QPT], m3[QPT];
+    int g1[QPT], g2[QPT];
+#pragma unroll
+    for (int q = 0; q < QPT; ++q) {
+        m1[q] = CUDART_INF_F; m2[q] = CUDART_INF_F; m3[q] = CUDART_INF_F;
+        g1[q] = g_begin < d.ngroups ? g_begin : 0; g2[q] = -1;
+    }
+
+    float *wb0 = &s_wb[wid][0][0], *wb1 = &s_wb[wid][1][0];
+    // lane l centres target l of a group: -(t - c) and |t - c|^2 into the warp's buffer
+    auto centre_group = [&](const float *grp, float *wb) {
+        const float tx = grp[lane] + cx, ty = grp[kGroup + lane] + cy, tz = grp[2 * kGroup + lane] + cz;
+        wb[lane] = tx; wb[kGroup + lane] = ty; wb[2 * kGroup + lane] = tz;
+        wb[3 * kGroup + lane] = __fmaf_rn(tz, tz, __fmaf_rn(ty, ty, tx * tx));
+    };
+
+    for (int tile = 0; tile < n_tiles; ++tile) {
+        const int s = tile % kStages;
+        mbar_wait(&s_full[s], (uint32_t)((tile / kStages) & 1));
+        const int gb = g_begin + tile * kStageGroups;
+        const int ng = min(kStageGroups, g_end - gb);
+        centre_group(&s_tile[s][0], wb0);
+        for (int gi = 0; gi < ng; ++gi) {
+            float *cur = (gi & 1) ? wb1 : wb0;
+            if (gi + 1 < ng) centre_group(&s_tile[s][(gi + 1) * (kGroup * 3)], (gi & 1) ? wb0 : wb1);
+            __syncwarp();
+            const float4 *w4 = reinterpret_cast<const float4 *>(cur);
+            float gm[QPT];
+#pragma unroll
+            for (int q = 0; q < QPT; ++q) gm[q] = CUDART_INF_F;
+#pragma unroll kUnrollJ
+            for (int j = 0; j < kGroup / 4; ++j) {
+                const float4 X = w4[j];
+                const float4 Y = w4[kGroup / 4 + j];
+                const float4 Z = w4[2 * (kGroup / 4) + j];
+                const float4 N = w4[3 * (kGroup / 4) + j];
+                const u64 x01 = pack2(X.x, X.y), x23 = pack2(X.z, X.w);
+                const u64 y01 = pack2(Y.x, Y.y), y23 = pack2(Y.z, Y.w);
+                const u64 z01 = pack2(Z.x, Z.y), z23 = pack2(Z.z, Z.w);
+                const u64 n01 = pack2(N.x, N.y), n23 = pack2(N.z, N.w);
+#pragma unroll
+                for (int q = 0; q < QPT; ++q) {
+                    const u64 qx = pack2(ax[q], ax[q]);
+                    const u64 qy = pack2(ay[q], ay[q]);
+                    const u64 qz = pack2(az[q], az[q]);
+                    u64 sa = fma2(qx, x01, n01), sb = fma2(qx, x23, n23);
+                    sa = fma2(qy, y01, sa); sb = fma2(qy, y23, sb);
+                    sa = fma2(qz, z01, sa); sb = fma2(qz, z23, sb);
+                    float s0, s1, s2, s3;
+                    unpack2(sa, s0, s1);
+                    unpack2(sb, s2, s3);
+                    gm[q] = min3(gm[q], s0, s1);
+                    gm[q] = min3(gm[q], s2, s3);
+                }
+            }
+            const int g = gb + gi;
+            bool hit = false;
+#pragma unroll
+            for (int q = 0; q < QPT; ++q) hit |= gm[q] < m3[q];
+            if (hit) {
+#pragma unroll
+                for (int q = 0; q < QPT; ++q) {
+                    const float v = gm[q];
+                    const bool lt1 = v < m1[q], lt2 = v < m2[q];
+                    m3[q] = lt2 ? m2[q] : fminf(m3[q], v);
+                    g2[q] = lt1 ? g1[q] : (lt2 ? g : g2[q]);
+                    m2[q] = lt1 ? m1[q] : (lt2 ? v : m2[q]);
+                    g1[q] = lt1 ? g : g1[q];
+                    m1[q] = lt1 ? v : m1[q];
+                }
+            }
+            __syncwarp(); // every lane is done with `cur` before it is refilled two groups later
+        }
+        __syncthreads(); // every warp is done with stage s
+        if (tid == 0 && tile + kStages < n_tiles) issue(tile + kStages);
+    }
+
+    const size_t row = (size_t)split * d.n_stride;
+#pragma unroll
+    for (int q = 0; q < QPT; ++q) {
+        const int i = qi[q];
+        if (i >= 0) {
+            d.pm1[row + i] = m1[q];
+            d.pm2[row + i] = m2[q];
+            d.pm3[row + i] = m3[q];
+            d.pg[row + i] = g1[q];
+            d.pg2[row + i] = g2[q];
+        }
+    }
+}
+
+template <int QPT>
+static void launch_warp(dim3 grid, const RegDesc *descs, int splits, int pass, cudaStream_t s)
+{
+    nn_partial_warp_kernel<QPT><<<grid, kNnThreads, 0, s>>>(descs, splits, pass);
+}
+
 template <int QPT>
 static void launch_centred(dim3 grid, const RegDesc *descs, int splits, int pass, cudaStream_t s)
 {
@@ -498,7 +698,15 @@ void launch_nn_partial(const RegDesc *descs, int batch, int max_n, int qpt, int 
 {
     dim3 block(kNnThreads);
     dim3 grid((max_n + kNnThreads * qpt - 1) / (kNnThreads * qpt), splits, batch);
-    if (filter == kFilterCentred) {
+    if (filter == kFilterWarp) {
+        switch (qpt) {
+        case 16: launch_warp<16>(grid, descs, splits, pass, s); break;
+        case 12: launch_warp<12>(grid, descs, splits, pass, s); break;
+        case 8: launch_warp<8>(grid, descs, splits, pass, s); break;
+        case 4: launch_warp<4>(grid, descs, splits, pass, s); break;
+        default: launch_warp<2>(grid, descs, splits, pass, s); break;
+        }
+    } else if (filter == kFilterCentred) {
         switch (qpt) {
         case 16: launch_centred<16>(grid, descs, splits, pass, s); break;
         case 12: launch_centred<12>(grid, descs, splits, pass, s); break;
@@ -840,7 +1048,7 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
                     }
                 }
             }
-            const bool top3 = filter == kFilterCentred;
+            const bool top3 = filter != kFilterDirect;
             const size_t o1 = (size_t)s1 * d.n_stride + i;
             const size_t o2 = (size_t)max(s2, 0) * d.n_stride + i;
             const size_t o3 = (size_t)max(s3, 0) * d.n_stride + i;
@@ -862,7 +1070,7 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
         // is every target outside the best group (or the best two) provably farther, in the reference's
         // arithmetic, than the best target?
         float band;
-        if (filter == kFilterCentred) {
+        if (filter != kFilterDirect) {
             // m1..m3 are W = |a-t|^2 - A; bound derived at nn_partial_centred_kernel
             const float A = valid ? __ldcg(&d.pa[i]) * 1.000001f : 0.f;
             const float X = fmaxf(m1 + A, 0.f);

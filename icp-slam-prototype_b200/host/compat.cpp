@@ -403,7 +403,7 @@ static cv::Mat getTransformationKeyPoints(cv::Mat &data, cv::Mat &previous, cv::
     prm.dist_trace = nullptr;
     prm.nn_mode = ICPB_NN_BRUTE;
     prm.grid_cell = 0.f;
-    prm.nn_filter = ICPB_FILTER_CENTRED;
+    prm.nn_filter = ICPB_FILTER_AUTO;
     icpb_icp_result res;
     check(icpb_icp_register_keypoints(H().ctx, kc, dataCloud.points.empty() ? nullptr : pc, mc, &prm, &res, nc),
           "icpb_icp_register_keypoints");
@@ -464,7 +464,7 @@ cv::Mat getTransformation(cv::Mat &data, cv::Mat &previous, cv::Mat color, std::
     prm.dist_trace = nullptr;
     prm.nn_mode = ICPB_NN_BRUTE;
     prm.grid_cell = 0.f;
-    prm.nn_filter = ICPB_FILTER_CENTRED;
+    prm.nn_filter = ICPB_FILTER_AUTO;
     icpb_icp_result res;
     cv::Mat rigid(4, 4, CV_32FC1);
     if (dataCloud.points.empty() || previousCloud.points.empty()) {

@@ -24,7 +24,7 @@ SUB_NONE, SUB_STRIDE, SUB_HASH, SUB_STREAM = 0, 1, 2, 3
 SOLVE_REFERENCE, SOLVE_KABSCH = 0, 1
 RULE_A, RULE_C = 0, 1
 NN_BRUTE, NN_GRID, NN_AUTO = 0, 1, 2
-FILTER_CENTRED, FILTER_DIRECT = 0, 1
+FILTER_AUTO, FILTER_DIRECT, FILTER_WARP, FILTER_CENTRED = 0, 1, 2, 3
 TRACK_INIT, TRACK_ASSOC, TRACK_NONASSOC = 0, 1, 2
 
 
@@ -216,7 +216,7 @@ class Context:
 
     def icp_register(self, data, target, max_iterations=20, threshold=0.0, max_nn_distance=0.75,
                      solve_mode=SOLVE_REFERENCE, last_translation=(0, 0, 0), trace=False, nn_mode=NN_BRUTE,
-                     grid_cell=0.0, nn_filter=FILTER_CENTRED):
+                     grid_cell=0.0, nn_filter=FILTER_AUTO):
         it = dt = None
         prm = IcpParams(max_iterations, threshold, max_nn_distance, solve_mode, (C.c_float * 3)(*last_translation),
                         None, None, nn_mode, grid_cell, nn_filter)
@@ -234,7 +234,7 @@ class Context:
                                non_associations=None):
         """8f-2: the reference's live loop (icp.cpp:98,155-258).  Clouds are moved in place."""
         prm = IcpParams(max_iterations, threshold, max_nn_distance, solve_mode, (C.c_float * 3)(*last_translation),
-                        None, None, NN_BRUTE, 0.0, FILTER_CENTRED)
+                        None, None, NN_BRUTE, 0.0, FILTER_AUTO)
         res = IcpResult()
         self.check(self.lib.icpb_icp_register_keypoints(
             self.h, keypoints.h, points.h if points is not None else None, map_keypoints.h, C.byref(prm), C.byref(res),
@@ -245,7 +245,7 @@ class Context:
                            solve_mode=SOLVE_REFERENCE):
         n = len(datas)
         prm = IcpParams(max_iterations, threshold, max_nn_distance, solve_mode, (C.c_float * 3)(0, 0, 0), None, None,
-                        NN_BRUTE, 0.0, FILTER_CENTRED)
+                        NN_BRUTE, 0.0, FILTER_AUTO)
         dh = (C.c_void_p * n)(*[d.h for d in datas])
         th = (C.c_void_p * n)(*[t.h for t in targets])
         res = (IcpResult * n)()

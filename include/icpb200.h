@@ -71,9 +71,12 @@ enum { ICPB_NN_BRUTE = 0, ICPB_NN_GRID = 1,
        ICPB_NN_AUTO = 2 }; /* GRID when n*m is large enough for the bucketing to pay off, else BRUTE */
 
 /* Approximate FP32 filter in front of the exact re-evaluation of the BRUTE scan (never visible in the results):
- * CENTRED evaluates |t'|^2 - 2a'.t' about a per-thread centre (3 FMA per pair), DIRECT evaluates (a-t)^2 (6 FP32
- * operations per pair; kept for A/B measurements). */
-enum { ICPB_FILTER_CENTRED = 0, ICPB_FILTER_DIRECT = 1 };
+ * CENTRED evaluates |t'|^2 - 2a'.t' about one centre per THREAD (3 FMA per pair + the centring of the targets per
+ * thread); WARP does the same about one centre per warp - the queries are first put into a spatial (Morton) order so
+ * that a warp's queries are neighbours, and the targets are centred once per warp in shared memory (single
+ * registrations only); DIRECT evaluates (a-t)^2 (6 FP32 operations per pair; kept for A/B measurements).
+ * AUTO = WARP for a single registration of >= 50,000 queries, CENTRED otherwise. */
+enum { ICPB_FILTER_AUTO = 0, ICPB_FILTER_DIRECT = 1, ICPB_FILTER_WARP = 2, ICPB_FILTER_CENTRED = 3 };
 
 enum { ICPB_RULE_A = 0,  /* map.cpp:249-253 / 104-113 */
        ICPB_RULE_C = 1 };/* map.cpp:139-149 */
@@ -88,7 +91,7 @@ typedef struct {
     float *dist_trace;         /* optional host buffer, same shape */
     int nn_mode;               /* ICPB_NN_BRUTE (default 0) or ICPB_NN_GRID */
     float grid_cell;           /* ICPB_NN_GRID: cell edge in metres (0 = chosen from the target's density) */
-    int nn_filter;             /* ICPB_FILTER_CENTRED (default 0) or ICPB_FILTER_DIRECT; env ICPB_NN_FILTER overrides */
+    int nn_filter;             /* ICPB_FILTER_* (default 0 = AUTO); env ICPB_NN_FILTER overrides */
 } icpb_icp_params;
 
 typedef struct {

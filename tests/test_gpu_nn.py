@@ -115,11 +115,24 @@ def test_nn_surface_like_clouds_rarely_rescan(ctx, orc, pair10k):
     assert resc < len(data) // 100, resc
 
 
-@pytest.mark.parametrize("flt", ["0", "1"])
-def test_nn_both_filters_are_exact(ctx, orc, monkeypatch, flt):
-    """ICPB_FILTER_CENTRED (default) and ICPB_FILTER_DIRECT feed the same exact resolution."""
+@pytest.mark.parametrize("flt", ["1", "2", "3"])
+def test_nn_every_filter_is_exact(ctx, orc, monkeypatch, flt):
+    """ICPB_FILTER_DIRECT, _WARP and _CENTRED feed the same exact resolution."""
     monkeypatch.setenv("ICPB_NN_FILTER", flt)
     rng = np.random.default_rng(11)
     data = orc.make_points(rng.uniform(3, 8, (3001, 3)))
     target = orc.make_points(rng.uniform(3, 8, (5003, 3)))
     _check(ctx, orc, data, target)
+
+
+@pytest.mark.parametrize("flt", ["2", "3"])
+def test_nn_centred_filters_on_tie_cases(ctx, orc, monkeypatch, flt):
+    """The lattice / duplicate / near-tie cases again with each centred filter forced (AUTO picks by size)."""
+    monkeypatch.setenv("ICPB_NN_FILTER", flt)
+    test_nn_lattice_ties(ctx, orc)
+    test_nn_duplicate_targets(ctx, orc)
+    test_nn_sqrt_collapsed_ties(ctx, orc)
+    test_nn_spread_queries_with_near_ties(ctx, orc)
+    test_nn_far_and_near_scales(ctx, orc)
+    for n, m in [(1, 1), (31, 32), (257, 1000), (1025, 4097)]:
+        test_nn_ragged_sizes(ctx, orc, n, m)

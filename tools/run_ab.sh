@@ -1,1 +1,9 @@
-for cfg in "8 3" "8 4" "16 2" "16 3" "12 4"; do set -- $cfg; ICPB_QPT=$1 ICPB_SPLITS=$2 python bench.py --workload batch10k 2>/dev/null | sed "s/.*\"value\": \([0-9.]*\).*\"ms_per_step\": \([0-9.]*\).*/q$1 s$2 reg\/s \1 ms \2/"; done
+set -x
+ICPB_NN_FILTER=2 python -m pytest tests/test_gpu_nn.py tests/test_gpu_icp.py tests/test_gpu_keypoints.py tests/test_gpu_pipeline.py -m gpu -x -q 2>&1 | tail -5
+echo "=== fullres"
+python tools/profile_case.py --iters 2 --repeat 2 | tail -1
+for q in 8 12 16; do ICPB_NN_FILTER=2 ICPB_QPT=$q python tools/profile_case.py --iters 2 --repeat 2 | tail -1; done
+ICPB_NN_FILTER=2 python tools/profile_case.py --iters 20 --repeat 1 | tail -1
+echo "=== 10k"
+python tools/profile_case.py --points 10000 --iters 20 --repeat 3 | tail -1
+for q in 2 4 8; do ICPB_NN_FILTER=2 ICPB_QPT=$q python tools/profile_case.py --points 10000 --iters 20 --repeat 3 | tail -1; done

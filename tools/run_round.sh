@@ -7,5 +7,5 @@ python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_r1c
 python bench.py --steps 2 --warmup 3 > gpurun_out/bench_short.json 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_bench_r1c.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_bench.log 2>&1
 python tools/profile_case.py --iters 0 > gpurun_out/ncu_nn_plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:nn_partial -c 1 -f -o gpurun_out/prof_nn_centred_q12 python tools/profile_case.py --iters 0 > gpurun_out/ncu_nn_q12.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:nn_partial -c 1 -f -o gpurun_out/prof_nn_warp_q12 python tools/profile_case.py --iters 0 > gpurun_out/ncu_nn_warp_q12.log 2>&1
 tail -1 gpurun_out/ncu_nn_plain.log
