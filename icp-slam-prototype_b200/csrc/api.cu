@@ -140,9 +140,8 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
 
     int qpt, splits;
     int filter = env_int("ICPB_NN_FILTER", prm->nn_filter);
-    if (filter != kFilterDirect && filter != kFilterWarp && filter != kFilterCentred)
-        filter = (count == 1 && max_n >= 50000) ? kFilterWarp : kFilterCentred; // ICPB_FILTER_AUTO
-    if (filter == kFilterWarp && count != 1) filter = kFilterCentred; // the spatial sort is built per single registration
+    if (filter != kFilterDirect && filter != kFilterWarp && filter != kFilterCentred) // ICPB_FILTER_AUTO
+        filter = ((count == 1 && max_n >= 50000) || (count > 1 && max_n >= 4096)) ? kFilterWarp : kFilterCentred;
     choose_nn_config(ctx, max_n, max_m, count, filter, &qpt, &splits);
 
     RegDesc *d_descs;
@@ -195,7 +194,7 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
 
     int *d_perm = nullptr;
     if (filter == kFilterWarp) {
-        if ((rc = ws_get(ctx, WS_PERM, sizeof(int) * (size_t)max_n, (void **)&d_perm))) return rc;
+        if ((rc = ws_get(ctx, WS_PERM, sizeof(int) * tot_n, (void **)&d_perm))) return rc;
     }
 
     // ---- ICPB_NN_GRID: bucket the (fixed) target once per registration
@@ -288,7 +287,7 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         d.pm2 = d_pm2 + off_n * splits;
         d.pg = d_pg + off_n * splits;
         d.pa = d_pa + off_n;
-        d.perm = d_perm;
+        d.perm = d_perm ? d_perm + off_n : nullptr;
         d.pm3 = d_pm3 + off_n * splits;
         d.pg2 = d_pg2 + off_n * splits;
         d.idx = d_idx + off_n;
@@ -331,11 +330,12 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
     long long launches = 0;
     CU(ctx, cudaEventRecord(ctx->ev0, st));
     if (filter == kFilterWarp && !grid_mode) {
-        // Morton order of the queries, once per registration (inside the timed region)
+        // Morton order of every data cloud, once per registration (inside the timed region)
+        const int bits = spatial_sort_bits(max_n);
         int *d_scnt, *d_ssum;
-        if ((rc = ws_get(ctx, WS_GRID_COUNTS, sizeof(int) * ((size_t)spatial_sort_cells() + 1), (void **)&d_scnt))) return rc;
-        if ((rc = ws_get(ctx, WS_GRID_SUMS, sizeof(int) * ((size_t)spatial_sort_cells() / 4096 + 8), (void **)&d_ssum))) return rc;
-        launch_spatial_sort(h_descs[0].D[0], h_descs[0].n, d_scnt, d_ssum, d_perm, st);
+        if ((rc = ws_get(ctx, WS_GRID_COUNTS, sizeof(int) * ((size_t)spatial_sort_cells(bits) + 1) * count, (void **)&d_scnt))) return rc;
+        if ((rc = ws_get(ctx, WS_GRID_SUMS, sizeof(int) * (size_t)spatial_sort_sum_slots(bits) * count, (void **)&d_ssum))) return rc;
+        launch_spatial_sort(d_descs, count, max_n, bits, d_scnt, d_ssum, st);
         launches += 5;
     }
     if (grid_mode) {

@@ -178,14 +178,10 @@ void launch_grid_build(const float4 *tgt, int m, const GridMeta &g, int *counts,
 }
 
 // ---- spatial order of the QUERIES for the warp-centred brute-force filter (nn.cu) --------------------------------
-// Counting sort of the data cloud by the Morton code of a 64^3 grid of 12.5 cm cells around the cloud's first point
-// (clamped: a far-away point only lands in a border cell).  The order is a performance matter only -- it decides
+// Counting sort of every data cloud of the batch by the Morton code of a 2^bits-cubed grid around the cloud's first
+// point (clamped: a far-away point only lands in a border cell).  The order is a performance matter only -- it decides
 // which queries share a warp, never what any query's result is -- so neither the clamping nor the arbitrary order
-// inside a cell matters.  perm[slot] = original index.
-constexpr int kSortBits = 6;
-constexpr int kSortCells = 1 << (3 * kSortBits);
-constexpr float kSortCell = 0.125f;
-
+// inside a cell matters.  d.perm[slot] = original index.  blockIdx.y / .z = registration.
 __device__ __forceinline__ unsigned int spread3(unsigned int v) // 6 bits -> every third bit
 {
     v &= 0x3fu;
@@ -195,42 +191,100 @@ __device__ __forceinline__ unsigned int spread3(unsigned int v) // 6 bits -> eve
     return v;
 }
 
-__device__ __forceinline__ int sort_key(const float4 p, const float4 ref)
+__device__ __forceinline__ int sort_key(const float4 p, const float4 ref, int bits, float cell)
 {
-    const int half = 1 << (kSortBits - 1);
-    const int cx = min(max((int)floorf((p.x - ref.x) / kSortCell) + half, 0), 2 * half - 1);
-    const int cy = min(max((int)floorf((p.y - ref.y) / kSortCell) + half, 0), 2 * half - 1);
-    const int cz = min(max((int)floorf((p.z - ref.z) / kSortCell) + half, 0), 2 * half - 1);
+    const int half = 1 << (bits - 1);
+    const int cx = min(max((int)floorf((p.x - ref.x) / cell) + half, 0), 2 * half - 1);
+    const int cy = min(max((int)floorf((p.y - ref.y) / cell) + half, 0), 2 * half - 1);
+    const int cz = min(max((int)floorf((p.z - ref.z) / cell) + half, 0), 2 * half - 1);
     return (int)(spread3((unsigned)cx) | (spread3((unsigned)cy) << 1) | (spread3((unsigned)cz) << 2));
 }
 
-__global__ void sort_count_kernel(const float4 *__restrict__ pts, int n, int *counts)
+__global__ void sort_count_kernel(const RegDesc *__restrict__ descs, int bits, float cell, int *counts, int stride)
 {
+    const RegDesc &d = descs[blockIdx.y];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    atomicAdd(&counts[sort_key(pts[i], pts[0])], 1);
+    if (i >= d.n) return;
+    const float4 *pts = d.D[0];
+    atomicAdd(&counts[(size_t)blockIdx.y * stride + sort_key(pts[i], pts[0], bits, cell)], 1);
 }
 
-__global__ void sort_scatter_kernel(const float4 *__restrict__ pts, int n, int *cursor, int *perm)
+__global__ void sort_scatter_kernel(const RegDesc *__restrict__ descs, int bits, float cell, int *cursor, int stride)
 {
+    const RegDesc &d = descs[blockIdx.y];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    perm[atomicAdd(&cursor[sort_key(pts[i], pts[0])], 1)] = i;
+    if (i >= d.n) return;
+    const float4 *pts = d.D[0];
+    const_cast<int *>(d.perm)[atomicAdd(&cursor[(size_t)blockIdx.y * stride + sort_key(pts[i], pts[0], bits, cell)], 1)] = i;
 }
 
-int spatial_sort_cells() { return kSortCells; }
-
-// counts: kSortCells + 1 ints (zeroed here); block_sums: kSortCells / 4096 + 8 ints; perm: n ints.
-void launch_spatial_sort(const float4 *pts, int n, int *counts, int *block_sums, int *perm, cudaStream_t s)
+// batched forms of the three scan kernels: blockIdx.y = registration, arrays `stride` / `sums_stride` apart
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_batch_kernel(const int *in, int n, int stride, int *block_sums,
+                                                                        int sums_stride)
 {
-    const int nc = kSortCells + 1;
-    cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)nc, s);
-    sort_count_kernel<<<(n + 255) / 256, 256, 0, s>>>(pts, n, counts);
+    __shared__ int s_warp[33];
+    in += (size_t)blockIdx.y * stride;
+    int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    int v = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) v += (base + k < n) ? in[base + k] : 0;
+    int total;
+    block_scan_excl(v, s_warp, total);
+    if (threadIdx.x == 0) block_sums[(size_t)blockIdx.y * sums_stride + blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_sums_batch_kernel(int *block_sums, int nblocks, int sums_stride)
+{
+    __shared__ int s_warp[33];
+    block_sums += (size_t)blockIdx.x * sums_stride;
+    int carry = 0;
+    for (int b0 = 0; b0 < nblocks; b0 += kScanThreads) {
+        int i = b0 + threadIdx.x;
+        int v = (i < nblocks) ? block_sums[i] : 0;
+        int total;
+        int ex = block_scan_excl(v, s_warp, total);
+        if (i < nblocks) block_sums[i] = carry + ex;
+        carry += total;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply_batch_kernel(int *data, int n, int stride, const int *block_sums,
+                                                                       int sums_stride)
+{
+    __shared__ int s_warp[33];
+    data += (size_t)blockIdx.y * stride;
+    int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    int x[kScanItems], v = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) { x[k] = (base + k < n) ? data[base + k] : 0; v += x[k]; }
+    int total;
+    int ex = block_scan_excl(v, s_warp, total) + block_sums[(size_t)blockIdx.y * sums_stride + blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (base + k < n) data[base + k] = ex;
+        ex += x[k];
+    }
+}
+
+// 12.5 cm cells (64^3) for dense clouds, 25 cm (32^3) for sparse ones: a warp's few hundred queries fill about a cell
+int spatial_sort_bits(int max_n) { return max_n >= 50000 ? 6 : 5; }
+int spatial_sort_cells(int bits) { return 1 << (3 * bits); }
+int spatial_sort_sum_slots(int bits) { return (spatial_sort_cells(bits) + 1 + kScanTile - 1) / kScanTile + 1; }
+
+// counts: batch x (cells + 1) ints (zeroed here); block_sums: batch x spatial_sort_sum_slots ints.
+void launch_spatial_sort(const RegDesc *descs, int batch, int max_n, int bits, int *counts, int *block_sums, cudaStream_t s)
+{
+    const int nc = spatial_sort_cells(bits) + 1;
+    const int ss = spatial_sort_sum_slots(bits);
+    const float cell = 8.0f / (float)(1 << bits);
+    cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)nc * batch, s);
+    dim3 pgrid((max_n + 255) / 256, batch);
+    sort_count_kernel<<<pgrid, 256, 0, s>>>(descs, bits, cell, counts, nc);
     const int nblocks = (nc + kScanTile - 1) / kScanTile;
-    scan_reduce_kernel<<<nblocks, kScanThreads, 0, s>>>(counts, nc, block_sums);
-    scan_sums_kernel<<<1, kScanThreads, 0, s>>>(block_sums, nblocks);
-    scan_apply_kernel<<<nblocks, kScanThreads, 0, s>>>(counts, nc, block_sums);
-    sort_scatter_kernel<<<(n + 255) / 256, 256, 0, s>>>(pts, n, counts, perm); // counts doubles as the cursor: not reused
+    scan_reduce_batch_kernel<<<dim3(nblocks, batch), kScanThreads, 0, s>>>(counts, nc, nc, block_sums, ss);
+    scan_sums_batch_kernel<<<batch, kScanThreads, 0, s>>>(block_sums, nblocks, ss);
+    scan_apply_batch_kernel<<<dim3(nblocks, batch), kScanThreads, 0, s>>>(counts, nc, nc, block_sums, ss);
+    sort_scatter_kernel<<<pgrid, 256, 0, s>>>(descs, bits, cell, counts, nc); // counts doubles as the cursor: not reused
 }
 
 // ---- the search ------------------------------------------------------------------------------------------------

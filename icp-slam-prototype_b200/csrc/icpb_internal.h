@@ -142,8 +142,10 @@ void launch_grid_bbox(const float4 *tgt, int m, unsigned int *bbox, cudaStream_t
 void launch_grid_build(const float4 *tgt, int m, const GridMeta &g, int *counts, int *cursor, int *block_sums,
                        float4 *sorted, cudaStream_t s);
 void launch_nn_grid(const RegDesc *descs, int batch, int max_n, int pass, int sm_count, cudaStream_t s);
-int spatial_sort_cells();
-void launch_spatial_sort(const float4 *pts, int n, int *counts, int *block_sums, int *perm, cudaStream_t s);
+int spatial_sort_bits(int max_n);
+int spatial_sort_cells(int bits);
+int spatial_sort_sum_slots(int bits);
+void launch_spatial_sort(const RegDesc *descs, int batch, int max_n, int bits, int *counts, int *block_sums, cudaStream_t s);
 
 struct BackprojectArgs {
     const uint16_t *depth;

@@ -73,9 +73,10 @@ enum { ICPB_NN_BRUTE = 0, ICPB_NN_GRID = 1,
 /* Approximate FP32 filter in front of the exact re-evaluation of the BRUTE scan (never visible in the results):
  * CENTRED evaluates |t'|^2 - 2a'.t' about one centre per THREAD (3 FMA per pair + the centring of the targets per
  * thread); WARP does the same about one centre per warp - the queries are first put into a spatial (Morton) order so
- * that a warp's queries are neighbours, and the targets are centred once per warp in shared memory (single
- * registrations only); DIRECT evaluates (a-t)^2 (6 FP32 operations per pair; kept for A/B measurements).
- * AUTO = WARP for a single registration of >= 50,000 queries, CENTRED otherwise. */
+ * that a warp's queries are neighbours, and the targets are centred once per warp in shared memory; DIRECT
+ * evaluates (a-t)^2 (6 FP32 operations per pair; kept for A/B measurements).
+ * AUTO = WARP for a single registration of >= 50,000 queries and for batches of >= 4,096-query registrations,
+ * CENTRED otherwise (small single registrations: the ordering would cost what it saves). */
 enum { ICPB_FILTER_AUTO = 0, ICPB_FILTER_DIRECT = 1, ICPB_FILTER_WARP = 2, ICPB_FILTER_CENTRED = 3 };
 
 enum { ICPB_RULE_A = 0,  /* map.cpp:249-253 / 104-113 */
