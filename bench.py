@@ -34,7 +34,7 @@ UNIT = "registrations/s"
 ITERS = 20
 FLOP_PER_PAIR = 8  # 3 sub + 3 mul + 2 add, icp.cpp:607-611
 
-EXTRA_WORKLOADS = ("batch10k", "map1cm", "trajectory", "backproject", "live")
+EXTRA_WORKLOADS = ("batch10k", "map1cm", "trajectory", "backproject", "live", "normals")
 
 WORKLOADS = {
     "fullres": dict(name="configs[1]: full-resolution Kinect v1 640x480 frame-pair ICP, 20 iterations", points=None),

@@ -31,6 +31,12 @@ def _setup(local, world):
     return torch
 
 
+def _hbm_peak():
+    """Measured copy bandwidth of this pool's B200s (driver-written MEASURED_PEAKS.json), else the recipe's fallback."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return json.load(open(path))["hbm_gbs"] if os.path.exists(path) else 6650.0
+
+
 def _barrier(torch, world):
     if world > 1:
         import torch.distributed as dist
@@ -415,5 +421,48 @@ def run_live(args, rank, world, local):
                                        "host->device copies of every frame",
                            "map_keypoints_at_end": int(n_map), "per_rank": "replica of the same sequence"},
                 "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+
+
+def run_normals(args, rank, world, local):
+    """P3 in isolation (SLAM.cpp:412-430): a batch of resident Kinect v1 frames -> per-pixel normals, one launch."""
+    import icpb200
+    from icpb200 import synth
+    torch = _setup(local, world)
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = icpb200.Context(local, stream=stream)
+    nf = args.frames or 256
+    base = [synth.render_depth(R, t, synth.KINECT_V1, seed=f) for f, (R, t) in enumerate(synth.trajectory(8, step_deg=1.0))]
+    w, h = synth.KINECT_V1["w"], synth.KINECT_V1["h"]
+    dev = torch.device("cuda", local)
+    d_depth = torch.from_numpy(np.stack([base[f % 8] for f in range(nf)]).astype(np.uint16).view(np.int16)).to(dev)
+    d_out = torch.empty((nf, h, w, 3), dtype=torch.float32, device=dev)
+
+    def step():
+        ctx.timer_start()
+        ctx.normals_batch_device(d_depth.data_ptr(), nf, w, h, d_out.data_ptr())
+        return ctx.timer_stop()
+
+    for _ in range(args.warmup):
+        step()
+    _barrier(torch, world)
+    ms_all = [step() for _ in range(args.steps)]
+    _barrier(torch, world)
+    tot = _max_over_ranks(torch, world, local, float(np.sum(ms_all)))
+    if rank == 0:
+        ms = tot / args.steps
+        bytes_per_launch = float(nf) * w * h * 14.0   # 2 B depth read + 12 B normal written per pixel (SURVEY.md 8d)
+        peak = _hbm_peak()
+        line = {"metric": "normal_maps_per_s", "value": world * nf / (ms * 1e-3), "unit": "frames/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{nf} resident Kinect v1 640x480 depth frames -> normals (SLAM.cpp:412-430), one launch",
+                           "l2": f"inputs+outputs ({bytes_per_launch / 1e6:.0f} MB) exceed L2"},
+                "roofline": {"bound": "hbm", "kernel": "normals4_kernel", "achieved": bytes_per_launch / (ms * 1e-3) / 1e9,
+                             "peak": peak, "unit": "GB/s", "frac": bytes_per_launch / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                             "bytes_per_launch": bytes_per_launch,
+                             "note": "the reference normalises in double (cv::normalize): one FP64 sqrt and one FP64 divide "
+                                     "per pixel bound the kernel before HBM does"}}
         print(json.dumps(line), flush=True)
     ctx.close()

@@ -939,6 +939,16 @@ int icpb_normals_from_depth(icpb_ctx *ctx, const uint16_t *depth, int w, int h, 
     return ICPB_OK;
 }
 
+int icpb_normals_batch_device(icpb_ctx *ctx, const void *d_depth, int frames, int w, int h, void *d_normals)
+{
+    if (!ctx || !d_depth || !d_normals || frames <= 0 || w <= 0 || h <= 0) return ICPB_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    launch_normals((const uint16_t *)d_depth, w, h, (float *)d_normals, ctx->stream, frames);
+    ctx->launches += 1;
+    CU(ctx, cudaGetLastError());
+    return ICPB_OK;
+}
+
 int icpb_depth_filter(icpb_ctx *ctx, const uint16_t *depth, int w, int h, int min_d, int max_d, uint16_t *out)
 {
     if (!ctx || !depth || !out || w <= 0 || h <= 0) return ICPB_ERR_INVALID;

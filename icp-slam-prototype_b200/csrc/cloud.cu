@@ -525,10 +525,70 @@ __global__ void normals_kernel(const uint16_t *__restrict__ depth, int w, int h,
     o[0] = n0; o[1] = n1; o[2] = n2;
 }
 
-void launch_normals(const uint16_t *depth, int w, int h, float *normals, cudaStream_t s)
+// The same stencil, four pixels of a row per thread (image widths that are multiples of 4): the rows above and below
+// arrive as one 8-byte load each, the centre row as one 8-byte load plus its two outer neighbours, and the 12 floats of
+// the four normals leave as three 16-byte stores.  blockIdx.z = frame of a batch.
+__device__ __forceinline__ void normal_of(float up, float dn, float lf, float rt, bool inside, float &n0, float &n1,
+                                          float &n2)
 {
-    dim3 grid((w + 127) / 128, h);
-    normals_kernel<<<grid, 128, 0, s>>>(depth, w, h, normals);
+    n0 = n1 = n2 = 0.f;
+    if (!inside) return;
+    const float dzdx = (dn - up) / 2.0f;
+    const float dzdy = (rt - lf) / 2.0f;
+    const float v0 = -dzdx, v1 = -dzdy, v2 = 1.0f;
+    const double nv = sqrt(((double)v0 * (double)v0 + (double)v1 * (double)v1) + (double)v2 * (double)v2);
+    const double inv = 1.0 / nv;
+    n0 = (float)((double)v0 * inv);
+    n1 = (float)((double)v1 * inv);
+    n2 = (float)((double)v2 * inv);
+}
+
+__global__ void __launch_bounds__(128) normals4_kernel(const uint16_t *__restrict__ depth, int w, int h,
+                                                       float *__restrict__ normals)
+{
+    const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int r = blockIdx.y;
+    if (c0 >= w) return;
+    depth += (size_t)blockIdx.z * w * h;
+    normals += (size_t)blockIdx.z * w * h * 3;
+    float out[12];
+    if (r >= 1 && r < h - 1) {
+        const uint2 upw = *reinterpret_cast<const uint2 *>(depth + (size_t)(r - 1) * w + c0);
+        const uint2 dnw = *reinterpret_cast<const uint2 *>(depth + (size_t)(r + 1) * w + c0);
+        const uint2 ctw = *reinterpret_cast<const uint2 *>(depth + (size_t)r * w + c0);
+        const float up[4] = {(float)(upw.x & 0xffffu), (float)(upw.x >> 16), (float)(upw.y & 0xffffu), (float)(upw.y >> 16)};
+        const float dn[4] = {(float)(dnw.x & 0xffffu), (float)(dnw.x >> 16), (float)(dnw.y & 0xffffu), (float)(dnw.y >> 16)};
+        float ct[6];
+        ct[0] = (c0 > 0) ? (float)depth[(size_t)r * w + c0 - 1] : 0.f;
+        ct[1] = (float)(ctw.x & 0xffffu); ct[2] = (float)(ctw.x >> 16);
+        ct[3] = (float)(ctw.y & 0xffffu); ct[4] = (float)(ctw.y >> 16);
+        ct[5] = (c0 + 4 < w) ? (float)depth[(size_t)r * w + c0 + 4] : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = c0 + k;
+            normal_of(up[k], dn[k], ct[k], ct[k + 2], c >= 1 && c < w - 1, out[3 * k], out[3 * k + 1], out[3 * k + 2]);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) out[k] = 0.f;
+    }
+    float4 *o = reinterpret_cast<float4 *>(normals + ((size_t)r * w + c0) * 3);
+    o[0] = make_float4(out[0], out[1], out[2], out[3]);
+    o[1] = make_float4(out[4], out[5], out[6], out[7]);
+    o[2] = make_float4(out[8], out[9], out[10], out[11]);
+}
+
+void launch_normals(const uint16_t *depth, int w, int h, float *normals, cudaStream_t s, int frames)
+{
+    if ((w & 3) == 0 && ((uintptr_t)depth & 7) == 0 && ((uintptr_t)normals & 15) == 0) {
+        dim3 grid((w / 4 + 127) / 128, h, frames);
+        normals4_kernel<<<grid, 128, 0, s>>>(depth, w, h, normals);
+        return;
+    }
+    for (int f = 0; f < frames; ++f) { // odd widths: one pixel per thread
+        dim3 grid((w + 127) / 128, h);
+        normals_kernel<<<grid, 128, 0, s>>>(depth + (size_t)f * w * h, w, h, normals + (size_t)f * w * h * 3);
+    }
 }
 
 // 8f-1, SLAM.cpp:553-573: range threshold (:559-565), then 5x5 rect dilate and

@@ -168,7 +168,7 @@ struct BackprojectArgs {
 };
 int backproject_tiles(int w, int h);
 void launch_backproject(const BackprojectArgs &a, cudaStream_t s, bool force_two_pass = false);
-void launch_normals(const uint16_t *depth, int w, int h, float *normals, cudaStream_t s);
+void launch_normals(const uint16_t *depth, int w, int h, float *normals, cudaStream_t s, int frames = 1);
 void launch_depth_filter(const uint16_t *in, uint16_t *tmp_a, uint16_t *tmp_b, uint16_t *out, int w, int h,
                          int min_d, int max_d, cudaStream_t s);
 

@@ -192,6 +192,10 @@ class Context:
         self.check(self.lib.icpb_frame_lift_band_device(self.h, C.c_void_p(d_depth), int(w), int(h), int(row0), int(row1),
                                                         C.byref(K), Rp, tp, C.c_void_p(d_band), int(band_capacity)))
 
+    def normals_batch_device(self, d_depth, frames, w, h, d_normals):
+        self.check(self.lib.icpb_normals_batch_device(self.h, C.c_void_p(d_depth), int(frames), int(w), int(h),
+                                                      C.c_void_p(d_normals)))
+
     def normals(self, depth):
         depth = np.ascontiguousarray(depth, dtype=np.uint16)
         h, w = depth.shape

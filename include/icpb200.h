@@ -187,6 +187,9 @@ void icpb_intrinsics_reference_v2(icpb_intrinsics *K); /* SLAM.cpp:26-29 */
 /* ---- image-space stages ------------------------------------------------- */
 /* getNormalMap, SLAM.cpp:412-430: host u16 depth -> host float h*w*3. */
 int icpb_normals_from_depth(icpb_ctx *ctx, const uint16_t *depth, int w, int h, float *normals);
+/* The same for `frames` device-resident frames laid out back to back (u16 in, 3 floats per pixel out); no host
+ * synchronisation. */
+int icpb_normals_batch_device(icpb_ctx *ctx, const void *d_depth, int frames, int w, int h, void *d_normals);
 /* filterDepthImage, SLAM.cpp:553-573 (range threshold + 5x5 close, anchor (3,3)). */
 int icpb_depth_filter(icpb_ctx *ctx, const uint16_t *depth, int w, int h, int min_d, int max_d,
                       uint16_t *out);

@@ -130,6 +130,32 @@ def test_normals(ctx, orc):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
+@pytest.mark.parametrize("w,h", [(640, 480), (512, 424), (8, 3), (4, 1), (12, 2), (33, 5), (7, 7)])
+def test_normals_sizes(ctx, orc, w, h):
+    """Widths that are multiples of 4 take the four-pixels-per-thread kernel, the others the scalar one; borders are
+    zeros either way (SLAM.cpp:412-430 never writes row / column 0 and reads past the last ones)."""
+    rng = np.random.default_rng(w * 100 + h)
+    depth = rng.integers(0, 65536, (h, w)).astype(np.uint16)
+    got = ctx.normals(depth)
+    want = orc.normals(depth)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_normals_batch_device(ctx, orc):
+    import torch
+    rng = np.random.default_rng(12)
+    depth = rng.integers(0, 65536, (5, 424, 512)).astype(np.uint16)
+    dev = torch.device("cuda", ctx.device)
+    d_in = torch.from_numpy(depth.view(np.int16)).to(dev)
+    d_out = torch.empty((5, 424, 512, 3), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    ctx.normals_batch_device(d_in.data_ptr(), 5, 512, 424, d_out.data_ptr())
+    ctx.sync()
+    got = d_out.cpu().numpy()
+    for f in range(5):
+        assert np.array_equal(got[f].view(np.uint32), orc.normals(depth[f]).view(np.uint32))
+
+
 def test_depth_filter(ctx, orc):
     from icpb200 import synth
     R, t = synth.trajectory(1)[0]
