@@ -168,3 +168,23 @@ def test_icp_grid_mode_partial_overlap_and_ties(ctx, orc):
     assert np.array_equal(out.view(np.uint8), rout.view(np.uint8))
     assert np.array_equal(res["pose_R"], ref["pose_R"])
     dc.close(); tc.close()
+
+
+def test_icp_ragged_batch_with_the_warp_filter(ctx, orc, pair10k):
+    """Batches whose largest registration has >= 4096 queries take the warp-centred filter (batched Morton sort, one
+    permutation per registration): ragged sizes, every registration checked against the oracle."""
+    data, target = pair10k
+    sizes = [(9000, 10000), (4096, 5000), (10000, 3000), (33, 7000), (5001, 4097)]
+    datas, targets, want = [], [], []
+    for k, (n, m) in enumerate(sizes):
+        d = np.ascontiguousarray(data[k * 37: k * 37 + n]); t = np.ascontiguousarray(target[k * 11: k * 11 + m])
+        datas.append(ctx.cloud_from_points(d)); targets.append(ctx.cloud_from_points(t))
+        want.append(orc.icp(d, t, 4, 0.0, 0.75, orc.SOLVE_REFERENCE, n_threads=8))
+    res = ctx.icp_register_batch(datas, targets, 4, 0.0, 0.75, 0)
+    for k in range(len(sizes)):
+        assert res[k]["nn_filter_used"] == 2          # ICPB_FILTER_WARP
+        assert np.array_equal(res[k]["pose_R"], want[k][0]["pose_R"]) and np.array_equal(res[k]["pose_t"], want[k][0]["pose_t"])
+        assert res[k]["n_assoc"] == want[k][0]["n_assoc"]
+        assert np.array_equal(datas[k].download().view(np.uint8), want[k][1].view(np.uint8))
+    for c in datas + targets:
+        c.close()

@@ -136,3 +136,17 @@ def test_nn_centred_filters_on_tie_cases(ctx, orc, monkeypatch, flt):
     test_nn_far_and_near_scales(ctx, orc)
     for n, m in [(1, 1), (31, 32), (257, 1000), (1025, 4097)]:
         test_nn_ragged_sizes(ctx, orc, n, m)
+
+
+def test_nn_large_cloud_takes_the_warp_filter(ctx, orc):
+    """>= 50,000 queries: ICPB_FILTER_AUTO orders the queries along a Morton curve and centres per warp.  Surface-like
+    clouds (two noisy sheets) and a shuffled query order -- the ordering is rebuilt from the coordinates."""
+    rng = np.random.default_rng(21)
+    n, m = 60000, 24000
+    uv = rng.uniform(0, 3, (n, 2))
+    q = np.stack([3 + uv[:, 0], 4 + uv[:, 1], 5 + 0.3 * np.sin(uv[:, 0] * 3) + rng.normal(0, 2e-3, n)], 1)
+    uv = rng.uniform(0, 3, (m, 2))
+    t = np.stack([3.01 + uv[:, 0], 4.02 + uv[:, 1], 5.01 + 0.3 * np.sin(uv[:, 0] * 3) + rng.normal(0, 2e-3, m)], 1)
+    data, target = orc.make_points(q[rng.permutation(n)]), orc.make_points(t)
+    resc = _check(ctx, orc, data, target)
+    assert resc < n // 200, resc
