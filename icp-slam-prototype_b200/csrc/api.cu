@@ -18,7 +18,7 @@ thread_local std::string g_create_error;
 enum WsId {
     WS_DESCS = 0, WS_STATES, WS_PARAMS, WS_TGT_SOA, WS_PM1, WS_PM2, WS_PG, WS_IDX, WS_DIST, WS_CHUNKS, WS_ALT,
     WS_IDX_TRACE, WS_DIST_TRACE, WS_MISC, WS_DEPTH, WS_BGR, WS_KEEP, WS_TILESTATE, WS_IMG_A, WS_IMG_B, WS_NORMALS,
-    WS_RT, WS_GRID_META, WS_GRID_COUNTS, WS_GRID_CURSOR, WS_GRID_SUMS, WS_GRID_SORTED, WS_GRID_BBOX, WS_GRID_HEAVY, WS_BATCHSTATE, WS_TRACK, WS_PA, WS_PM3, WS_PG2, WS_MLOG, WS_REJ_FLAG, WS_REJ_PTS, WS_FRAME, WS_PERM, WS_COUNT
+    WS_RT, WS_GRID_META, WS_GRID_COUNTS, WS_GRID_CURSOR, WS_GRID_SUMS, WS_GRID_SORTED, WS_GRID_BBOX, WS_GRID_HEAVY, WS_BATCHSTATE, WS_TRACK, WS_PA, WS_PM3, WS_PG2, WS_MLOG, WS_REJ_FLAG, WS_REJ_PTS, WS_FRAME, WS_PERM, WS_SORT_COUNTS, WS_SORT_SUMS, WS_COUNT
 };
 
 int fail(icpb_ctx *ctx, int status, const char *what, cudaError_t ce = cudaSuccess)
@@ -193,7 +193,8 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
     }
 
     int *d_perm = nullptr;
-    if (filter == kFilterWarp) {
+    const bool grid_sorted = env_int("ICPB_GRID_SORT", 1) != 0;
+    if (filter == kFilterWarp || grid_sorted) {
         if ((rc = ws_get(ctx, WS_PERM, sizeof(int) * tot_n, (void **)&d_perm))) return rc;
     }
 
@@ -228,13 +229,13 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
             memcpy(&f, &u, 4);
             (k < 3 ? lo[k] : hi[k - 3]) = f;
         }
-        // default cell: ~32 points per occupied cell (at most 0.2 m), taking a third of the bounding box's surface as the area
+        // default cell: ~50 points per occupied cell (at most 0.2 m), taking a third of the bounding box's surface as the area
         // the (surface-sampled) cloud covers; sweeps on full-resolution and 10k-point Kinect clouds sit near this
         float h = prm->grid_cell;
         if (!(h > 0.f)) {
             const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
             const float area = 2.f * (ex * ey + ey * ez + ez * ex) / 3.f;
-            h = sqrtf(32.f * std::max(area, 1e-6f) / (float)m);
+            h = sqrtf(50.f * std::max(area, 1e-6f) / (float)m);
             h = std::min(std::max(h, 0.01f), 0.2f);
         }
         for (;;) {
@@ -287,7 +288,8 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         d.pm2 = d_pm2 + off_n * splits;
         d.pg = d_pg + off_n * splits;
         d.pa = d_pa + off_n;
-        d.perm = d_perm ? d_perm + off_n : nullptr;
+        // only handed to the kernels when the sort below fills it
+        d.perm = (d_perm && ((filter == kFilterWarp && !grid_mode) || (grid_mode && grid_sorted))) ? d_perm + off_n : nullptr;
         d.pm3 = d_pm3 + off_n * splits;
         d.pg2 = d_pg2 + off_n * splits;
         d.idx = d_idx + off_n;
@@ -329,12 +331,12 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
 
     long long launches = 0;
     CU(ctx, cudaEventRecord(ctx->ev0, st));
-    if (filter == kFilterWarp && !grid_mode) {
+    if ((filter == kFilterWarp && !grid_mode) || (grid_mode && grid_sorted)) {
         // Morton order of every data cloud, once per registration (inside the timed region)
         const int bits = spatial_sort_bits(max_n);
         int *d_scnt, *d_ssum;
-        if ((rc = ws_get(ctx, WS_GRID_COUNTS, sizeof(int) * ((size_t)spatial_sort_cells(bits) + 1) * count, (void **)&d_scnt))) return rc;
-        if ((rc = ws_get(ctx, WS_GRID_SUMS, sizeof(int) * (size_t)spatial_sort_sum_slots(bits) * count, (void **)&d_ssum))) return rc;
+        if ((rc = ws_get(ctx, WS_SORT_COUNTS, sizeof(int) * ((size_t)spatial_sort_cells(bits) + 1) * count, (void **)&d_scnt))) return rc;
+        if ((rc = ws_get(ctx, WS_SORT_SUMS, sizeof(int) * (size_t)spatial_sort_sum_slots(bits) * count, (void **)&d_ssum))) return rc;
         launch_spatial_sort(d_descs, count, max_n, bits, d_scnt, d_ssum, st);
         launches += 5;
     }

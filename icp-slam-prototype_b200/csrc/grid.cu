@@ -415,8 +415,11 @@ __global__ void __launch_bounds__(128) nn_grid_kernel(const RegDesc *__restrict_
     const RegDesc d = descs[blockIdx.z];
     IcpState *st = d.st;
     if (st->done) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= d.n) return;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= d.n) return;
+    // queries in Morton order when the permutation is there: the lanes of a warp then walk (almost) the same cells,
+    // so their candidate loads hit the same lines and they leave the shell loops together
+    const int i = d.perm ? d.perm[k] : k;
 
     // P2 fused into the query load, as in nn_partial (pointcloud.cpp:321-359)
     float4 p = d.D[pass & 1][i];
