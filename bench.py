@@ -370,6 +370,12 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="registrations for the batch10k workload (whole job)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    # ONE JSON line on stdout: Python's prints keep the real stdout, anything native code writes to file descriptor 1
+    # (NCCL prints its version banner there) is sent to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     rank, world, local = dist_setup(args.gpus)
     if args.impl == "reference":
         run_reference(args, rank, world)
