@@ -385,6 +385,10 @@ def main():
         if args.workload in EXTRA_WORKLOADS:
             import bench_extra
             getattr(bench_extra, "run_" + args.workload)(args, rank, world, local)
+            if world > 1:
+                import torch.distributed as dist
+                if dist.is_initialized():
+                    dist.destroy_process_group()
         else:
             run_b200(args, rank, world, local)
 
