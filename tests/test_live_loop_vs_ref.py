@@ -121,3 +121,34 @@ def test_live_keypoint_loop_matches_the_references_getTransformation(orc):
     diff = int((world != mine.grid).sum())
     assert diff <= 4, diff   # a reject within float noise of a voxel wall may land next door
     assert int((mine.grid > 0).sum()) > 500
+
+
+def test_live_loop_fewer_than_three_associations_matches_the_reference(orc):
+    """icp.cpp:163-182 inside the real loop: a frame that brings only two key-points replays the last translation on
+    the data cloud, leaves the camera pose alone and reports -lastTranslation as the offset -- checked against the
+    reference's own getTransformation, frame after a normal frame."""
+    from icpb200 import synth
+    poses = synth.trajectory(4, step_deg=0.6, step_m=0.012)
+    frames = [synth.render_depth(R, t, synth.KINECT_V1, seed=f) for f, (R, t) in enumerate(poses)]
+    bgr = np.random.default_rng(5).integers(0, 255, frames[0].shape + (3,), dtype=np.uint8)
+    kps_all = _keypoint_pixels(frames, 400, 9)
+    per_frame = {1: kps_all, 2: kps_all[:2], 3: kps_all}
+
+    ref.map_reset()
+    libc = ctypes.CDLL("libc.so.6")
+    mine = OracleSlam(orc)
+    seen_small = False
+    for f in range(1, len(frames)):
+        cur, prev, kps = frames[f], frames[f - 1], per_frame[f]
+        seed = 300 + f
+        T_ref, camR_ref, camP_ref = ref.get_transformation(cur, prev, bgr, np.array(kps, np.float32), 16, 1e-4, seed)
+        libc.srand(seed)
+        dec_cur = _rand_stream(libc, int((cur != 0).sum()))
+        dec_prev = _rand_stream(libc, int((prev != 0).sum()))
+        r = mine.frame(cur, prev, bgr, kps, dec_cur, dec_prev)
+        seen_small |= bool(r["small_assoc_exit"])
+        assert np.abs(mine.camR - camR_ref).max() < 1e-5 and np.abs(mine.camP - camP_ref).max() < 1e-5, f
+        assert np.abs(r["rigid"][:3, 3] - T_ref[:3, 3]).max() < 1e-5, f          # offset column (icp.cpp:266-268)
+    assert seen_small
+    assert len(ref.map_cloud(0)) == len(mine.map_kp)
+    assert int((ref.map_world() != mine.grid).sum()) <= 4
