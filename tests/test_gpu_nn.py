@@ -150,3 +150,36 @@ def test_nn_large_cloud_takes_the_warp_filter(ctx, orc):
     data, target = orc.make_points(q[rng.permutation(n)]), orc.make_points(t)
     resc = _check(ctx, orc, data, target)
     assert resc < n // 200, resc
+
+
+def _random_case(rng, orc):
+    """One random association problem: sizes, coordinate scale, geometry and ordering all drawn from the seed."""
+    n = int(rng.integers(1, 3000)); m = int(rng.integers(1, 4000))
+    scale = float(10.0 ** rng.uniform(-2, 1.5)); origin = rng.uniform(-20, 20, 3)
+    kind = int(rng.integers(0, 5))
+    if kind == 0:      # uniform boxes
+        q = rng.uniform(0, 1, (n, 3)); t = rng.uniform(0, 1, (m, 3))
+    elif kind == 1:    # two noisy sheets (surface-like)
+        uv = rng.uniform(0, 1, (n, 2)); q = np.stack([uv[:, 0], uv[:, 1], 0.1 * np.sin(6 * uv[:, 0]) + rng.normal(0, 1e-3, n)], 1)
+        uv = rng.uniform(0, 1, (m, 2)); t = np.stack([uv[:, 0], uv[:, 1], 0.1 * np.sin(6 * uv[:, 0]) + rng.normal(0, 1e-3, m)], 1)
+    elif kind == 2:    # clusters with duplicates among the targets
+        c = rng.uniform(0, 1, (8, 3))
+        q = c[rng.integers(0, 8, n)] + rng.normal(0, 0.01, (n, 3))
+        t = c[rng.integers(0, 8, m)] + rng.normal(0, 0.01, (m, 3))
+        t[rng.integers(0, m, m // 3 + 1)] = t[rng.integers(0, m, m // 3 + 1)]
+    elif kind == 3:    # integer lattice: masses of exact ties
+        q = rng.integers(0, 6, (n, 3)) / 4.0 + 0.125; t = rng.integers(0, 6, (m, 3)) / 4.0
+    else:              # queries are copies of targets (distance 0) mixed with far outliers
+        t = rng.uniform(0, 1, (m, 3)); q = t[rng.integers(0, m, n)].copy()
+        far = rng.random(n) < 0.2; q[far] += rng.uniform(2, 5, (int(far.sum()), 3))
+    return orc.make_points(q * scale + origin), orc.make_points(t * scale + origin)
+
+
+@pytest.mark.parametrize("flt", ["0", "1", "2", "3"])
+def test_nn_randomized_differential(ctx, orc, monkeypatch, flt):
+    """40 random problems per filter (AUTO, DIRECT, WARP, CENTRED) against the oracle: indices and distances bit-equal."""
+    monkeypatch.setenv("ICPB_NN_FILTER", flt)
+    rng = np.random.default_rng(1000 + int(flt))
+    for _ in range(40):
+        data, target = _random_case(rng, orc)
+        _check(ctx, orc, data, target)
