@@ -363,9 +363,9 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
     for (int pass = 0; pass < passes; ++pass) {
         if (prof) CU(ctx, cudaEventRecord(ctx->prof_events[2 * pass], st));
         if (grid_mode) launch_nn_grid(d_descs, count, max_n, pass, ctx->sm_count, st);
-        else launch_nn_partial(d_descs, count, max_n, qpt, splits, pass, filter, st);
+        else launch_nn_partial(d_descs, d_states, count, max_n, qpt, splits, pass, filter, st);
         if (prof) CU(ctx, cudaEventRecord(ctx->prof_events[2 * pass + 1], st));
-        launch_nn_finalize(d_descs, d_prm, count, max_n, grid_mode ? 0 : splits, pass, filter, st);
+        launch_nn_finalize(d_descs, d_states, d_prm, count, max_n, grid_mode ? 0 : splits, pass, filter, st);
         launches += grid_mode ? 3 : 2;
     }
     launch_pending_translate(d_descs, count, max_n, st);

@@ -171,11 +171,13 @@ void launch_target_prep(const float4 *tgt, int m, float *soa, int ngroups, cudaS
 // second-best GROUP minimum and the best group's id; nn_finalize re-evaluates
 // the best group in the reference's exact arithmetic.
 template <int QPT>
-__global__ void __launch_bounds__(kNnThreads) nn_partial_kernel(const RegDesc *__restrict__ descs, int splits,
-                                                                int pass)
+__global__ void __launch_bounds__(kNnThreads) nn_partial_kernel(const RegDesc *__restrict__ descs, IcpState *states,
+                                                                int splits, int pass)
 {
+    // the loop state sits at states[blockIdx.z] (== d.st): addressed from the kernel argument, its load does not wait
+    // for the descriptor's
+    IcpState *st = states + blockIdx.z;
     const RegDesc d = descs[blockIdx.z]; // by value: no pointer reloads after stores
-    IcpState *st = d.st;
     if (st->done) return;
     const int n = d.n;
     const int q0 = blockIdx.x * (kNnThreads * QPT);
@@ -325,11 +327,13 @@ __global__ void __launch_bounds__(kNnThreads) nn_partial_kernel(const RegDesc *_
 // squared distance, 4 u for the float sqrt) than the best target: it can
 // neither win nor tie.  A is written to d.pa by split 0.
 template <int QPT>
-__global__ void __launch_bounds__(kNnThreads, (QPT >= 16 ? 2 : QPT >= 12 ? 3 : 4)) nn_partial_centred_kernel(const RegDesc *__restrict__ descs, int splits,
-                                                                        int pass)
+__global__ void __launch_bounds__(kNnThreads, (QPT >= 16 ? 2 : QPT >= 12 ? 3 : 4)) nn_partial_centred_kernel(const RegDesc *__restrict__ descs,
+                                                                        IcpState *states, int splits, int pass)
 {
+    // the loop state sits at states[blockIdx.z] (== d.st): addressed from the kernel argument, its load does not wait
+    // for the descriptor's
+    IcpState *st = states + blockIdx.z;
     const RegDesc d = descs[blockIdx.z]; // by value: no pointer reloads after stores
-    IcpState *st = d.st;
     if (st->done) return;
     const int n = d.n;
     const int q0 = blockIdx.x * (kNnThreads * QPT);
@@ -500,10 +504,12 @@ __global__ void __launch_bounds__(kNnThreads, (QPT >= 16 ? 2 : QPT >= 12 ? 3 : 4
 // centres (decimetres instead of centimetres), so a few more queries need the second group or the full rescan.
 template <int QPT>
 __global__ void __launch_bounds__(kNnThreads, (QPT >= 16 ? 2 : QPT >= 12 ? 3 : 4)) nn_partial_warp_kernel(
-    const RegDesc *__restrict__ descs, int splits, int pass)
+    const RegDesc *__restrict__ descs, IcpState *states, int splits, int pass)
 {
+    // the loop state sits at states[blockIdx.z] (== d.st): addressed from the kernel argument, its load does not wait
+    // for the descriptor's
+    IcpState *st = states + blockIdx.z;
     const RegDesc d = descs[blockIdx.z]; // by value: no pointer reloads after stores
-    IcpState *st = d.st;
     if (st->done) return;
     const int n = d.n;
     const int q0 = blockIdx.x * (kNnThreads * QPT);
@@ -682,43 +688,43 @@ __global__ void __launch_bounds__(kNnThreads, (QPT >= 16 ? 2 : QPT >= 12 ? 3 : 4
 }
 
 template <int QPT>
-static void launch_warp(dim3 grid, const RegDesc *descs, int splits, int pass, cudaStream_t s)
+static void launch_warp(dim3 grid, const RegDesc *descs, IcpState *states, int splits, int pass, cudaStream_t s)
 {
-    nn_partial_warp_kernel<QPT><<<grid, kNnThreads, 0, s>>>(descs, splits, pass);
+    nn_partial_warp_kernel<QPT><<<grid, kNnThreads, 0, s>>>(descs, states, splits, pass);
 }
 
 template <int QPT>
-static void launch_centred(dim3 grid, const RegDesc *descs, int splits, int pass, cudaStream_t s)
+static void launch_centred(dim3 grid, const RegDesc *descs, IcpState *states, int splits, int pass, cudaStream_t s)
 {
-    nn_partial_centred_kernel<QPT><<<grid, kNnThreads, 0, s>>>(descs, splits, pass);
+    nn_partial_centred_kernel<QPT><<<grid, kNnThreads, 0, s>>>(descs, states, splits, pass);
 }
 
-void launch_nn_partial(const RegDesc *descs, int batch, int max_n, int qpt, int splits, int pass, int filter,
-                       cudaStream_t s)
+void launch_nn_partial(const RegDesc *descs, IcpState *states, int batch, int max_n, int qpt, int splits, int pass,
+                       int filter, cudaStream_t s)
 {
     dim3 block(kNnThreads);
     dim3 grid((max_n + kNnThreads * qpt - 1) / (kNnThreads * qpt), splits, batch);
     if (filter == kFilterWarp) {
         switch (qpt) {
-        case 16: launch_warp<16>(grid, descs, splits, pass, s); break;
-        case 12: launch_warp<12>(grid, descs, splits, pass, s); break;
-        case 8: launch_warp<8>(grid, descs, splits, pass, s); break;
-        case 4: launch_warp<4>(grid, descs, splits, pass, s); break;
-        default: launch_warp<2>(grid, descs, splits, pass, s); break;
+        case 16: launch_warp<16>(grid, descs, states, splits, pass, s); break;
+        case 12: launch_warp<12>(grid, descs, states, splits, pass, s); break;
+        case 8: launch_warp<8>(grid, descs, states, splits, pass, s); break;
+        case 4: launch_warp<4>(grid, descs, states, splits, pass, s); break;
+        default: launch_warp<2>(grid, descs, states, splits, pass, s); break;
         }
     } else if (filter == kFilterCentred) {
         switch (qpt) {
-        case 16: launch_centred<16>(grid, descs, splits, pass, s); break;
-        case 12: launch_centred<12>(grid, descs, splits, pass, s); break;
-        case 8: launch_centred<8>(grid, descs, splits, pass, s); break;
-        case 4: launch_centred<4>(grid, descs, splits, pass, s); break;
-        default: launch_centred<2>(grid, descs, splits, pass, s); break;
+        case 16: launch_centred<16>(grid, descs, states, splits, pass, s); break;
+        case 12: launch_centred<12>(grid, descs, states, splits, pass, s); break;
+        case 8: launch_centred<8>(grid, descs, states, splits, pass, s); break;
+        case 4: launch_centred<4>(grid, descs, states, splits, pass, s); break;
+        default: launch_centred<2>(grid, descs, states, splits, pass, s); break;
         }
     } else {
         switch (qpt) {
-        case 8: nn_partial_kernel<8><<<grid, block, 0, s>>>(descs, splits, pass); break;
-        case 4: nn_partial_kernel<4><<<grid, block, 0, s>>>(descs, splits, pass); break;
-        default: nn_partial_kernel<2><<<grid, block, 0, s>>>(descs, splits, pass); break;
+        case 8: nn_partial_kernel<8><<<grid, block, 0, s>>>(descs, states, splits, pass); break;
+        case 4: nn_partial_kernel<4><<<grid, block, 0, s>>>(descs, states, splits, pass); break;
+        default: nn_partial_kernel<2><<<grid, block, 0, s>>>(descs, states, splits, pass); break;
         }
     }
 }
@@ -981,12 +987,12 @@ __device__ __forceinline__ void solve_step_local(IcpState *st, const IcpParamsDe
 // --------------------------------------------------------------------------
 // nn_finalize: exact resolution, association sums, solve
 // --------------------------------------------------------------------------
-__global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__restrict__ descs,
+__global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__restrict__ descs, IcpState *states,
                                                              const IcpParamsDev *__restrict__ prm, int splits,
                                                              int pass, int filter)
 {
+    IcpState *st = states + blockIdx.z;  // == d.st; see nn_partial*
     const RegDesc d = descs[blockIdx.z]; // by value: no pointer reloads after stores
-    IcpState *st = d.st;
     if (st->done) return;
     const int n = d.n, m = d.m;
     const int chunk = blockIdx.x;
@@ -1013,6 +1019,8 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
 
     int best_i = 0;
     float best_d = 0.f;
+    float4 best_b = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool have_b = false;
     int n_amb = 0;
     if (splits == 0) {
         // ICPB_NN_GRID: nn_grid_kernel already resolved (idx, dist) exactly
@@ -1031,7 +1039,7 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
         if (valid) {
             float a1 = CUDART_INF_F, a2 = CUDART_INF_F, a3 = CUDART_INF_F;
             int s1 = -1, s2 = -1, s3 = -1;
-            constexpr int kB = 8;
+            constexpr int kB = 16; // 30 splits at 10k points: two rounds of independent loads
             for (int s0 = 0; s0 < splits; s0 += kB) {
                 float p1[kB];
     #pragma unroll
@@ -1090,21 +1098,22 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
             float4 b = d.tgt[t0];
             best_d = exact_distance(a.x, a.y, a.z, b.x, b.y, b.z);
             best_i = t0;
-    #pragma unroll 8
+            best_b = b; have_b = true; // the winner's coordinates feed the sums below: no second gather
+    #pragma unroll 16
             for (int k = 1; k < kGroup; ++k) {
                 const int t = t0 + k;
                 b = d.tgt[min(t, m - 1)];
                 float dd = exact_distance(a.x, a.y, a.z, b.x, b.y, b.z);
-                if (t < m && dd < best_d) { best_d = dd; best_i = t; }
+                if (t < m && dd < best_d) { best_d = dd; best_i = t; best_b = b; }
             }
             if (gbb >= 0) {
                 t0 = gbb * kGroup;
-    #pragma unroll 8
+    #pragma unroll 16
                 for (int k = 0; k < kGroup; ++k) {
                     const int t = t0 + k;
                     b = d.tgt[min(t, m - 1)];
                     float dd = exact_distance(a.x, a.y, a.z, b.x, b.y, b.z);
-                    if (t < m && dd < best_d) { best_d = dd; best_i = t; }
+                    if (t < m && dd < best_d) { best_d = dd; best_i = t; best_b = b; }
                 }
             }
         }
@@ -1147,6 +1156,7 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
                     bd = exact_distance(q.x, q.y, q.z, b.x, b.y, b.z);
                 }
                 best_d = bd; best_i = bi;
+                have_b = false;
             }
             __syncthreads();
         }
@@ -1169,7 +1179,7 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
     double t[kTerms];
     const bool accepted = valid && (best_d < prm->max_nn_distance); // icp.cpp:553
     if (accepted) {
-        float4 b = d.tgt[best_i];
+        const float4 b = have_b ? best_b : d.tgt[best_i];
         t[0] = a.x; t[1] = a.y; t[2] = a.z;
         t[3] = b.x; t[4] = b.y; t[5] = b.z;
         t[6] = (double)b.x * (double)a.x; t[7] = (double)b.x * (double)a.y; t[8] = (double)b.x * (double)a.z;
@@ -1235,11 +1245,11 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
     }
 }
 
-void launch_nn_finalize(const RegDesc *descs, const IcpParamsDev *prm, int batch, int max_n, int splits, int pass,
-                        int filter, cudaStream_t s)
+void launch_nn_finalize(const RegDesc *descs, IcpState *states, const IcpParamsDev *prm, int batch, int max_n, int splits,
+                        int pass, int filter, cudaStream_t s)
 {
     dim3 grid((max_n + kChunk - 1) / kChunk, 1, batch);
-    nn_finalize_kernel<<<grid, kChunk, 0, s>>>(descs, prm, splits, pass, filter);
+    nn_finalize_kernel<<<grid, kChunk, 0, s>>>(descs, states, prm, splits, pass, filter);
 }
 
 // --------------------------------------------------------------------------

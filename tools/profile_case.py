@@ -15,6 +15,7 @@ ap.add_argument("--points", type=int, default=0, help="0 = full resolution")
 ap.add_argument("--iters", type=int, default=1)
 ap.add_argument("--repeat", type=int, default=1)
 ap.add_argument("--grid", type=float, default=-1.0, help="use ICPB_NN_GRID with this cell size (0 = default)")
+ap.add_argument("--noprof", action="store_true", help="leave the per-launch event timing off")
 ap.add_argument("--map", action="store_true", help="also run back-projection + map integration")
 ap.add_argument("--cm", type=float, default=2.0, help="map cell in cm (2 -> 300x300x250, 1 -> 600x600x500)")
 a = ap.parse_args()
@@ -30,7 +31,7 @@ dat.from_depth(d1, col, K); dat.transform(None, cam)
 if a.points:
     tgt.upload(synth.subsample_exact(tgt.download(), a.points, 2))
     dat.upload(synth.subsample_exact(dat.download(), a.points, 1))
-ctx.set_profiling(True)
+ctx.set_profiling(not a.noprof)
 for r in range(a.repeat):
     work.copy_from(dat)
     res, _, _ = ctx.icp_register(work, tgt, a.iters, 0.0, 0.75, 0, nn_mode=1 if a.grid >= 0 else 0, grid_cell=max(a.grid, 0.0))
