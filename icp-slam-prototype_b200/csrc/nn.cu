@@ -987,9 +987,13 @@ __device__ __forceinline__ void solve_step_local(IcpState *st, const IcpParamsDe
 // --------------------------------------------------------------------------
 // nn_finalize: exact resolution, association sums, solve
 // --------------------------------------------------------------------------
-__global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__restrict__ descs, IcpState *states,
-                                                             const IcpParamsDev *__restrict__ prm, int splits,
-                                                             int pass, int filter)
+// Launched with kChunk threads (grid mode) or 2 * kChunk (brute-force modes): in the latter the group selection and
+// the exact re-evaluation of a query are shared by a PAIR of adjacent threads (each takes every second split and one
+// half of each candidate group; shuffles merge the halves), which halves the stage's serial length on the few CTAs a
+// small cloud gives (40 for 10k points).  From the sums on, threads 0 .. kChunk-1 own one query each, as before.
+__global__ void __launch_bounds__(2 * kChunk) nn_finalize_kernel(const RegDesc *__restrict__ descs, IcpState *states,
+                                                                 const IcpParamsDev *__restrict__ prm, int splits,
+                                                                 int pass, int filter)
 {
     IcpState *st = states + blockIdx.z;  // == d.st; see nn_partial*
     const RegDesc d = descs[blockIdx.z]; // by value: no pointer reloads after stores
@@ -999,14 +1003,22 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
     if (chunk * kChunk >= n) return;
     const int nchunks = (n + kChunk - 1) / kChunk;
     const int tid = threadIdx.x;
-    const int i = chunk * kChunk + tid;
-    const bool valid = i < n;
+    const int nthr = blockDim.x;
+    const bool paired = nthr == 2 * kChunk;
+    // exact stage: query slot and half; later stages: slot = tid for the first kChunk threads
+    const int slot = paired ? (tid >> 1) : tid;
+    const int half = paired ? (tid & 1) : 0;
+    int i = chunk * kChunk + slot;
+    bool valid = i < n;
 
     __shared__ float4 s_pts[kChunk];
+    __shared__ float4 s_bb[kChunk];
+    __shared__ float s_bd[kChunk];
+    __shared__ int s_bi[kChunk];
     __shared__ int s_list[kChunk];
     __shared__ int s_cnt;
-    __shared__ float s_rd[kChunk / 32];
-    __shared__ int s_ri[kChunk / 32];
+    __shared__ float s_rd[2 * kChunk / 32];
+    __shared__ int s_ri[2 * kChunk / 32];
     __shared__ double s_w[kChunk / 32][kTerms];
     __shared__ double s_tot[kTerms];
     __shared__ int s_last;
@@ -1014,7 +1026,7 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
     if (tid == 0) s_cnt = 0;
     const float4 *cur = d.D[(pass + 1) & 1];
     float4 a = valid ? cur[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    s_pts[tid] = a;
+    if (half == 0) s_pts[slot] = a;
     __syncthreads();
 
     int best_i = 0;
@@ -1039,16 +1051,17 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
         if (valid) {
             float a1 = CUDART_INF_F, a2 = CUDART_INF_F, a3 = CUDART_INF_F;
             int s1 = -1, s2 = -1, s3 = -1;
-            constexpr int kB = 16; // 30 splits at 10k points: two rounds of independent loads
-            for (int s0 = 0; s0 < splits; s0 += kB) {
+            constexpr int kB = 16; // 30 splits at 10k points: one round of independent loads per half
+            const int sstep = paired ? 2 : 1;
+            for (int s0 = half; s0 < splits; s0 += kB * sstep) {
                 float p1[kB];
     #pragma unroll
                 for (int k = 0; k < kB; ++k) // independent loads, issued together
-                    p1[k] = __ldcg(&d.pm1[(size_t)min(s0 + k, splits - 1) * d.n_stride + i]);
+                    p1[k] = __ldcg(&d.pm1[(size_t)min(s0 + k * sstep, splits - 1) * d.n_stride + i]);
     #pragma unroll
                 for (int k = 0; k < kB; ++k) {
                     const float v = p1[k];
-                    const int sp = s0 + k;
+                    const int sp = s0 + k * sstep;
                     if (sp < splits) {
                         if (v < a1 || s1 < 0) { a3 = a2; s3 = s2; a2 = a1; s2 = s1; a1 = v; s1 = sp; }
                         else if (v < a2 || s2 < 0) { a3 = a2; s3 = s2; a2 = v; s2 = sp; }
@@ -1056,8 +1069,26 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
                     }
                 }
             }
+            if (paired) {
+                // the partner scanned the other splits: fold its three records in, then both halves adopt half 0's
+                // list so that the pair takes identical decisions (ties between splits may be ordered either way; the
+                // exact stage settles them)
+                const unsigned pm = __activemask();
+                const float b1 = __shfl_xor_sync(pm, a1, 1), b2 = __shfl_xor_sync(pm, a2, 1), b3 = __shfl_xor_sync(pm, a3, 1);
+                const int t1 = __shfl_xor_sync(pm, s1, 1), t2 = __shfl_xor_sync(pm, s2, 1), t3 = __shfl_xor_sync(pm, s3, 1);
+                auto take = [&](float v, int sp) {
+                    if (sp < 0) return;
+                    if (v < a1 || s1 < 0) { a3 = a2; s3 = s2; a2 = a1; s2 = s1; a1 = v; s1 = sp; }
+                    else if (v < a2 || s2 < 0) { a3 = a2; s3 = s2; a2 = v; s2 = sp; }
+                    else if (v < a3 || s3 < 0) { a3 = v; s3 = sp; }
+                };
+                take(b1, t1); take(b2, t2); take(b3, t3);
+                const int src = (threadIdx.x & 31) & ~1;
+                a1 = __shfl_sync(pm, a1, src); a2 = __shfl_sync(pm, a2, src); a3 = __shfl_sync(pm, a3, src);
+                s1 = __shfl_sync(pm, s1, src); s2 = __shfl_sync(pm, s2, src); s3 = __shfl_sync(pm, s3, src);
+            }
             const bool top3 = filter != kFilterDirect;
-            const size_t o1 = (size_t)s1 * d.n_stride + i;
+            const size_t o1 = (size_t)max(s1, 0) * d.n_stride + i;
             const size_t o2 = (size_t)max(s2, 0) * d.n_stride + i;
             const size_t o3 = (size_t)max(s3, 0) * d.n_stride + i;
             const int ga = __ldcg(&d.pg[o1]);
@@ -1091,46 +1122,56 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
         const bool two = !one && g2 >= 0 && g >= 0 && m3 > lim;     // the best two groups decide
         const bool ambiguous = valid && !(one || two);
         if (valid && !ambiguous) {
-            // exact re-evaluation (reference arithmetic, ascending index, strict <) of the deciding group(s)
+            // exact re-evaluation (reference arithmetic, ascending index, strict <) of the deciding group(s); a pair
+            // splits every group into its lower and upper half and merges on (distance, index)
             const int ga = two ? min(g, g2) : g;
             const int gbb = two ? max(g, g2) : -1;
-            int t0 = ga * kGroup;
-            float4 b = d.tgt[t0];
-            best_d = exact_distance(a.x, a.y, a.z, b.x, b.y, b.z);
-            best_i = t0;
-            best_b = b; have_b = true; // the winner's coordinates feed the sums below: no second gather
+            const int span = paired ? kGroup / 2 : kGroup;
+            float bd = CUDART_INF_F;
+            int bi = 0x7fffffff;
+            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int grp = 0; grp < 2; ++grp) {
+                const int gsel = grp == 0 ? ga : gbb;
+                if (gsel < 0) break;
+                const int t0 = gsel * kGroup + half * span;
     #pragma unroll 16
-            for (int k = 1; k < kGroup; ++k) {
-                const int t = t0 + k;
-                b = d.tgt[min(t, m - 1)];
-                float dd = exact_distance(a.x, a.y, a.z, b.x, b.y, b.z);
-                if (t < m && dd < best_d) { best_d = dd; best_i = t; best_b = b; }
-            }
-            if (gbb >= 0) {
-                t0 = gbb * kGroup;
-    #pragma unroll 16
-                for (int k = 0; k < kGroup; ++k) {
+                for (int k = 0; k < span; ++k) {
                     const int t = t0 + k;
-                    b = d.tgt[min(t, m - 1)];
-                    float dd = exact_distance(a.x, a.y, a.z, b.x, b.y, b.z);
-                    if (t < m && dd < best_d) { best_d = dd; best_i = t; best_b = b; }
+                    const float4 b = d.tgt[min(t, m - 1)];
+                    const float dd = exact_distance(a.x, a.y, a.z, b.x, b.y, b.z);
+                    if (t < m && dd < bd) { bd = dd; bi = t; bb = b; }
                 }
             }
+            if (paired) {
+                const unsigned pm = __activemask();
+                const float od = __shfl_xor_sync(pm, bd, 1);
+                const int oi = __shfl_xor_sync(pm, bi, 1);
+                const float ox = __shfl_xor_sync(pm, bb.x, 1), oy = __shfl_xor_sync(pm, bb.y, 1);
+                const float oz = __shfl_xor_sync(pm, bb.z, 1), ow = __shfl_xor_sync(pm, bb.w, 1);
+                if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; bb = make_float4(ox, oy, oz, ow); }
+            }
+            if (bi == 0x7fffffff) { // no finite distance in the group (NaN inputs): keep its first target, like a strict-< scan
+                bi = ga * kGroup;
+                bb = d.tgt[min(bi, m - 1)];
+                bd = exact_distance(a.x, a.y, a.z, bb.x, bb.y, bb.z);
+            }
+            best_d = bd; best_i = bi; best_b = bb; have_b = true; // the winner's coordinates feed the sums: no second gather
         }
-        if (ambiguous) {
-            int slot = atomicAdd(&s_cnt, 1);
-            s_list[slot] = tid;
+        if (ambiguous && half == 0) {
+            const int e = atomicAdd(&s_cnt, 1);
+            s_list[e] = slot;
         }
+        if (half == 0) { s_bd[slot] = best_d; s_bi[slot] = have_b ? best_i : -1 - best_i; s_bb[slot] = best_b; }
         __syncthreads();
 
-        // ---- near-tie queries: CTA-cooperative full scan in exact arithmetic
+        // ---- near-tie queries: CTA-cooperative full scan in exact arithmetic (all threads of the CTA)
         n_amb = s_cnt;
         for (int e = 0; e < n_amb; ++e) {
             const int owner = s_list[e];
             const float4 q = s_pts[owner];
             float bd = CUDART_INF_F;
             int bi = 0x7fffffff;
-            for (int t = tid; t < m; t += kChunk) {
+            for (int t = tid; t < m; t += nthr) {
                 float4 b = d.tgt[t];
                 float dd = exact_distance(q.x, q.y, q.z, b.x, b.y, b.z);
                 if (dd < bd) { bd = dd; bi = t; }
@@ -1143,9 +1184,9 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
             }
             if ((tid & 31) == 0) { s_rd[tid >> 5] = bd; s_ri[tid >> 5] = bi; }
             __syncthreads();
-            if (tid == owner) {
+            if (tid == 0) {
                 bd = s_rd[0]; bi = s_ri[0];
-                for (int wv = 1; wv < kChunk / 32; ++wv) {
+                for (int wv = 1; wv < nthr / 32; ++wv) {
                     float od = s_rd[wv];
                     int oi = s_ri[wv];
                     if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
@@ -1155,12 +1196,23 @@ __global__ void __launch_bounds__(kChunk) nn_finalize_kernel(const RegDesc *__re
                     bi = 0;
                     bd = exact_distance(q.x, q.y, q.z, b.x, b.y, b.z);
                 }
-                best_d = bd; best_i = bi;
-                have_b = false;
+                s_bd[owner] = bd;
+                s_bi[owner] = -1 - bi; // negative: coordinates not staged, gathered later
             }
             __syncthreads();
         }
-
+        // ---- from here on one thread per query
+        if (tid >= kChunk) return;
+        i = chunk * kChunk + tid;
+        valid = i < n;
+        a = s_pts[tid];
+        best_d = s_bd[tid];
+        {
+            const int enc = s_bi[tid];
+            have_b = enc >= 0;
+            best_i = have_b ? enc : -1 - enc;
+            best_b = s_bb[tid];
+        }
     }
 
     if (valid) {
@@ -1249,7 +1301,11 @@ void launch_nn_finalize(const RegDesc *descs, IcpState *states, const IcpParamsD
                         int pass, int filter, cudaStream_t s)
 {
     dim3 grid((max_n + kChunk - 1) / kChunk, 1, batch);
-    nn_finalize_kernel<<<grid, kChunk, 0, s>>>(descs, states, prm, splits, pass, filter);
+    // brute-force modes on few CTAs (a small cloud; latency-bound: 10k points are 40 CTAs on 148 SMs): a pair of
+    // threads per query for the group selection and the exact stage.  Many CTAs (full resolution, batches) are
+    // throughput-bound and keep one thread per query (measured: pairs -6 % on the 1024-registration batch).
+    const bool paired = splits > 0 && (long long)grid.x * batch <= 2 * 148;
+    nn_finalize_kernel<<<grid, paired ? 2 * kChunk : kChunk, 0, s>>>(descs, states, prm, splits, pass, filter);
 }
 
 // --------------------------------------------------------------------------
