@@ -188,3 +188,31 @@ def test_icp_ragged_batch_with_the_warp_filter(ctx, orc, pair10k):
         assert np.array_equal(datas[k].download().view(np.uint8), want[k][1].view(np.uint8))
     for c in datas + targets:
         c.close()
+
+
+@pytest.mark.parametrize("flt", ["1", "2", "3"])
+def test_icp_randomized_differential(ctx, orc, monkeypatch, flt):
+    """Random registration problems (sizes, overlap, noise, solve mode) under each filter: iterations, association
+    count, composed pose and the transformed cloud are bit-equal to the oracle's."""
+    from scipy.spatial.transform import Rotation
+    monkeypatch.setenv("ICPB_NN_FILTER", flt)
+    rng = np.random.default_rng(500 + int(flt))
+    for case in range(8):
+        n = int(rng.integers(3, 5000)); m = int(rng.integers(3, 6000))
+        uv = rng.uniform(0, 2, (m, 2))
+        t = np.stack([4 + uv[:, 0], 4 + uv[:, 1], 5 + 0.2 * np.sin(3 * uv[:, 0]) * np.cos(2 * uv[:, 1])], 1)
+        sel = rng.integers(0, m, n)
+        R = Rotation.from_euler("xyz", rng.uniform(-3, 3, 3), degrees=True).as_matrix()
+        q = (t[sel] - 5) @ R.T + 5 + rng.uniform(-0.03, 0.03, 3) + rng.normal(0, 2e-3, (n, 3))
+        far = rng.random(n) < 0.1
+        q[far] += rng.uniform(1.0, 2.0, (int(far.sum()), 3))          # some queries beyond the acceptance radius
+        data, target = orc.make_points(q), orc.make_points(t)
+        mode = int(rng.integers(0, 2)); iters = int(rng.integers(1, 6)); thr = float(rng.choice([0.0, 1e-4]))
+        dc, tc = ctx.cloud_from_points(data), ctx.cloud_from_points(target)
+        res, _, _ = ctx.icp_register(dc, tc, iters, thr, 0.75, mode)
+        want, wout, _, _ = orc.icp(data, target, iters, thr, 0.75, mode, n_threads=8)
+        for k in ("iterations", "nn_passes", "n_assoc", "small_assoc_exit"):
+            assert res[k] == want[k], (case, k)
+        assert np.array_equal(res["pose_R"], want["pose_R"]) and np.array_equal(res["pose_t"], want["pose_t"]), case
+        assert np.array_equal(dc.download().view(np.uint8), wout.view(np.uint8)), case
+        dc.close(); tc.close()
