@@ -37,6 +37,19 @@ def _hbm_peak():
     return json.load(open(path))["hbm_gbs"] if os.path.exists(path) else 6650.0
 
 
+def _cpu_port_rate(fn, units, what):
+    """cpu_baseline for a secondary workload: the oracle port (oracle/, one thread) on a bounded sample, units / s."""
+    try:
+        from oracle import oracle as orc
+        orc.build()
+        t0 = time.perf_counter()
+        fn(orc)
+        dt = time.perf_counter() - t0
+        return {"value": units / dt, "cores": 1, "kind": "port", "sample": f"{what} ({dt:.2f} s)"}
+    except Exception as e:  # test infrastructure: the GPU number stands without it
+        return {"unavailable": str(e)}
+
+
 def _barrier(torch, world):
     if world > 1:
         import torch.distributed as dist
@@ -208,6 +221,18 @@ def run_map1cm(args, rank, world, local):
                            "l2": "grid (180 MB) exceeds L2 at 1 GPU"},
                 "extra": {"frames_per_s": frames / (ms_per_step * 1e-3),
                           "algorithmic_GBps": alg_bytes / (ms_per_step * 1e-3) / 1e9}}
+
+        def _one_frame(orc):
+            R, t = poses[0]
+            pts, _, _ = orc.backproject(depths[0], None, orc.kinect_v1())
+            pts = orc.translate(orc.rotate(pts, np.asarray(R, np.float32)), np.asarray(t, np.float32))
+            grid = np.zeros(dims, np.uint8)
+            orc.map_integrate_rays(grid, dims, np.float32(cell), pts, tuple(float(x) for x in t), 25, 25)
+
+        cb = _cpu_port_rate(_one_frame, visited / frames,
+                            "oracle lift + ray integration of the first frame into the 1 cm grid, one thread")
+        cb["unit"] = "voxel updates/s"
+        line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     ctx.close()
 
@@ -253,6 +278,10 @@ def run_backproject(args, rank, world, local):
                            "points": npts, "l2": f"inputs+outputs ({alg / 1e6:.0f} MB) exceed L2"},
                 "roofline": {"bound": "hbm", "kernel": "backproject_kernel", "achieved": gbs, "peak": peak, "unit": "GB/s",
                              "frac": gbs / peak, "traffic": None, "bytes_per_launch": alg}}
+        cb = _cpu_port_rate(lambda orc: [orc.backproject(base[f], None, orc.kinect_v1()) for f in range(8)], 8,
+                            "oracle back-projection of 8 of the frames, one thread")
+        cb["unit"] = "frames/s"
+        line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     ctx.close()
 
@@ -477,5 +506,9 @@ def run_normals(args, rank, world, local):
                              "bytes_per_launch": bytes_per_launch,
                              "note": "the reference normalises in double (cv::normalize): one FP64 sqrt and one FP64 divide "
                                      "per pixel bound the kernel before HBM does"}}
+        cb = _cpu_port_rate(lambda orc: [orc.normals(base[f]) for f in range(8)], 8,
+                            "oracle normals of 8 of the frames, one thread")
+        cb["unit"] = "frames/s"
+        line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     ctx.close()
