@@ -142,7 +142,15 @@ __device__ __forceinline__ float div_by(float a, DivConst d)
 
 struct BackprojectDiv {
     DivConst scale, fx_u, fx_v;
+    unsigned long long row_magic; // floor(2^40 / w) + 1, or 0 when the image is too large for the multiply-shift form
 };
+
+// p / w for 0 <= p < 2^24 and p * w < 2^40: (p * magic) >> 40 is the exact floor (the estimate is high by less than
+// p / 2^40 < 1 / w) -- three instructions instead of the ~25 of a general integer division
+__device__ __forceinline__ int row_of(int p, int w, unsigned long long magic)
+{
+    return magic ? (int)(((unsigned long long)(uint32_t)p * magic) >> 40) : p / w;
+}
 
 // P1.  One CTA per 2048-pixel tile (tile = blockIdx.x: predecessors are dispatched first).  Two chained scans: the
 // ordinal among NON-ZERO pixels (consumed by the subsample rule exactly where the reference consumes one rand(),
@@ -240,7 +248,7 @@ __global__ void __launch_bounds__(kBpThreads) backproject_kernel(BackprojectArgs
                     if (p0 * 3 + b < npx * 3) cw[b >> 2] |= (uint32_t)c[b] << (8 * (b & 3));
             }
         }
-        const int v0 = p0 / a.w;
+        const int v0 = row_of(p0, a.w, dv.row_magic);
         const int u0 = p0 - v0 * a.w;
         // Image widths are multiples of 8 in practice (640, 512): the thread's 8 pixels then share a row and the
         // coordinates are u0 + k, exactly representable float sums; otherwise every pixel finds its own (u, v).
@@ -283,12 +291,24 @@ __global__ void __launch_bounds__(kBpThreads) backproject_kernel(BackprojectArgs
             else if (tile == a.n_tiles - 1) *a.out_count = (int)(ex + tile_keep);
         }
     }
+    // ---- the tile leaves as ONE bulk copy shared -> global (1-D TMA, UBLKCP): the staged points are contiguous in
+    //      shared memory and in the output, 16-byte aligned at both ends, so no thread has to read them back and store
+    //      them (that loop was a quarter of the kernel's instructions and half of its stall samples).  The writers
+    //      make their generic-proxy stores visible to the async proxy, the barrier orders them before the copy, and
+    //      the issuing thread keeps the CTA's shared memory alive until the copy has read it.
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    // ---- the tile leaves with fully coalesced 16-byte stores
-    const uint32_t tile_base = s_bcast[1];
-    for (uint32_t j = tid; j < tile_keep; j += kBpThreads) { // (batching the LDS / STG costs 11 registers and a CTA per SM)
-        const uint32_t o = tile_base + j;
-        if ((int)o < a.capacity) a.out[o] = s_pts[j];
+    if (tid == 0) {
+        const uint32_t tile_base = s_bcast[1];
+        const long long room = (long long)a.capacity - (long long)tile_base;
+        const uint32_t n_out = (uint32_t)max(0ll, min((long long)tile_keep, room));
+        if (n_out) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.out + tile_base),
+                         "r"((uint32_t)__cvta_generic_to_shared(s_pts)), "r"(n_out * 16u)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
     }
 }
 
@@ -410,7 +430,7 @@ __global__ void __launch_bounds__(kBpThreads) backproject_write_kernel(Backproje
                     if (p0 * 3 + b < npx * 3) cw[b >> 2] |= (uint32_t)c[b] << (8 * (b & 3));
             }
         }
-        const int v0 = p0 / a.w;
+        const int v0 = row_of(p0, a.w, dv.row_magic);
         const int u0 = p0 - v0 * a.w;
         const bool same_row = (a.w % kBpPix) == 0; // see backproject_kernel
         const float uf0 = (float)u0, vf0 = (float)(v0 + a.v_offset);
@@ -463,6 +483,11 @@ void launch_backproject(const BackprojectArgs &a, cudaStream_t s, bool force_two
     dv.scale = {a.K.depth_scale, (float)(1.0 / (double)a.K.depth_scale)};
     dv.fx_u = {a.K.fx_u, (float)(1.0 / (double)a.K.fx_u)};
     dv.fx_v = {a.K.fx_v, (float)(1.0 / (double)a.K.fx_v)};
+    {
+        const unsigned long long reach = (unsigned long long)a.w * a.h + kBpTile; // one past the largest p0
+        dv.row_magic = (a.w >= 2 && reach < (1ull << 24) && reach * (unsigned long long)a.w < (1ull << 40))
+                           ? (1ull << 40) / (unsigned long long)a.w + 1ull : 0ull;
+    }
     // depths are 1..65535 and image coordinates a few thousand at most: with divisors inside 2^+-60 nothing can
     // overflow or underflow in the FMA sequence
     const bool fast = fast_div_ok(a.K.depth_scale) && fast_div_ok(a.K.fx_u) && fast_div_ok(a.K.fx_v) &&
