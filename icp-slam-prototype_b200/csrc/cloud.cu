@@ -17,7 +17,8 @@ namespace icpb {
 
 constexpr int kBpThreads = 256;
 constexpr int kBpPix = 8;                         // pixels per thread: one 16-byte load of u16
-constexpr int kBpTile = kBpThreads * kBpPix;      // 2048 pixels per CTA
+constexpr int kBpTile = kBpThreads * kBpPix;      // 2048 pixels: one staging buffer
+constexpr int kBpSubMax = 4;                      // most tiles a CTA of the chained kernel walks through its buffer
 
 int backproject_tiles(int w, int h) { return (w * h + kBpTile - 1) / kBpTile; }
 
@@ -152,15 +153,87 @@ __device__ __forceinline__ int row_of(int p, int w, unsigned long long magic)
     return magic ? (int)(((unsigned long long)(uint32_t)p * magic) >> 40) : p / w;
 }
 
-// P1.  One CTA per 2048-pixel tile (tile = blockIdx.x: predecessors are dispatched first).  Two chained scans: the
-// ordinal among NON-ZERO pixels (consumed by the subsample rule exactly where the reference consumes one rand(),
-// pointcloud.cpp:22-28; only the STRIDE / STREAM rules need it) and the output position among KEPT pixels (raster
-// order == push_back order, :54).  The look-back for the output position runs in warp 0 AFTER it has lifted its own
-// pixels, while the other warps lift theirs: its latency hides behind the arithmetic.  Specialised on the subsample
-// rule, on the presence of a colour image and on the division path.
-template <int RULE, bool HAS_BGR, bool FASTDIV>
+__device__ __forceinline__ void load_depth8(const BackprojectArgs &a, int p0, int npx, uint32_t (&dw)[4])
+{
+    dw[0] = dw[1] = dw[2] = dw[3] = 0;
+    if (p0 + kBpPix <= npx) {
+        const uint4 raw = *reinterpret_cast<const uint4 *>(a.depth + p0);
+        dw[0] = raw.x; dw[1] = raw.y; dw[2] = raw.z; dw[3] = raw.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < kBpPix; ++k)
+            if (p0 + k < npx) dw[k >> 1] |= (uint32_t)a.depth[p0 + k] << (16 * (k & 1));
+    }
+}
+
+// Lift a thread's 8 pixels and store the kept ones from `dst` on (pointcloud.cpp:37-39 / 134-136: all float, left to
+// right, true division).
+template <bool HAS_BGR, bool FASTDIV>
+__device__ __forceinline__ void lift8(const BackprojectArgs &a, const BackprojectDiv &dv, int p0, int npx,
+                                      const uint32_t (&dw)[4], uint32_t keep_mask, float4 *dst)
+{
+    if (!keep_mask) return;
+    uint32_t cw[6] = {0, 0, 0, 0, 0, 0}; // the thread's 8 BGR triples: 24 bytes, three 8-byte loads when aligned
+    if (HAS_BGR) {
+        const uint8_t *c = a.bgr + (size_t)p0 * 3;
+        if (p0 + kBpPix <= npx && ((reinterpret_cast<uintptr_t>(c) & 7) == 0)) {
+            const uint2 *c2 = reinterpret_cast<const uint2 *>(c);
+            const uint2 w0 = c2[0], w1 = c2[1], w2 = c2[2];
+            cw[0] = w0.x; cw[1] = w0.y; cw[2] = w1.x; cw[3] = w1.y; cw[4] = w2.x; cw[5] = w2.y;
+        } else {
+            for (int b = 0; b < 3 * kBpPix; ++b)
+                if (p0 * 3 + b < npx * 3) cw[b >> 2] |= (uint32_t)c[b] << (8 * (b & 3));
+        }
+    }
+    const int v0 = row_of(p0, a.w, dv.row_magic);
+    const int u0 = p0 - v0 * a.w;
+    // Image widths are multiples of 8 in practice (640, 512): the thread's 8 pixels then share a row and the
+    // coordinates are u0 + k, exactly representable float sums; otherwise every pixel finds its own (u, v).
+    const bool same_row = (a.w % kBpPix) == 0;
+    const float uf0 = (float)u0, vf0 = (float)(v0 + a.v_offset);
+    // branch-free: all 8 pixels are lifted (a zero depth just gives z = 0), only the kept ones are stored
+#pragma unroll
+    for (int k = 0; k < kBpPix; ++k) {
+        float uf = uf0 + (float)k, vf = vf0;
+        if (!same_row) {
+            const int pk = p0 + k, vv = pk / a.w;
+            uf = (float)(pk - vv * a.w);
+            vf = (float)(vv + a.v_offset);
+        }
+        const uint32_t d16 = (dw[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+        // (float)d for d < 2^23 without a conversion instruction: 0x4B000000 | d is 2^23 + d
+        const float df = __fsub_rn(__uint_as_float(0x4B000000u | d16), 8388608.0f);
+        const float pz = div_by<FASTDIV>(df, dv.scale);
+        const float px = div_by<FASTDIV>(__fmul_rn(__fsub_rn(uf, a.K.cx_u), pz), dv.fx_u);
+        const float py = div_by<FASTDIV>(__fmul_rn(__fsub_rn(vf, a.K.cx_v), pz), dv.fx_v);
+        uint32_t cbits = 0;
+        if (HAS_BGR) { // bytes 3k .. 3k+2 of the 24-byte run (:47): a funnel shift across two words
+            const int w = (3 * k) >> 2, sh = 8 * ((3 * k) & 3);
+            cbits = __funnelshift_r(cw[w], w + 1 < 6 ? cw[w + 1] : 0u, sh) & 0x00ffffffu;
+        }
+        if (keep_mask & (1u << k)) {
+            *dst = make_float4(px, py, pz, __uint_as_float(cbits));
+            ++dst;
+        }
+    }
+}
+
+// P1.  One CTA per run of kBpSub consecutive 2048-pixel tiles (run = blockIdx.x: predecessors are dispatched first).
+// Two chained scans: the ordinal among NON-ZERO pixels (consumed by the subsample rule exactly where the reference
+// consumes one rand(), pointcloud.cpp:22-28; only the STRIDE / STREAM rules need it) and the output position among KEPT
+// pixels (raster order == push_back order, :54).  The look-back for the output position runs in warp 0 AFTER it has
+// lifted its first pixels, while the other warps lift theirs: its latency hides behind the arithmetic.
+// Why several tiles per CTA: under a saturated memory system every dependent round trip costs a microsecond or two, and
+// the staging buffer (what bounds the CTAs per SM) is held for the whole chain depth-load -> scan -> look-back -> copy.
+// A CTA loads the depth of all its tiles at once and looks back once, then walks the tiles through the same 32 KB
+// buffer: one load round trip and one look-back per kBpSub tiles instead of per tile.  Measured on 256 resident frames:
+// 4,227 GB/s with one tile per CTA, 4,978 with two, 5,113 with four (59 registers, 4 CTAs per SM); launches with few
+// tiles (a single frame is 150) take two so that more SMs take part.
+// Specialised on the subsample rule, on the presence of a colour image and on the division path.
+template <int RULE, bool HAS_BGR, bool FASTDIV, int kBpSub>
 __global__ void __launch_bounds__(kBpThreads) backproject_kernel(BackprojectArgs a, BackprojectDiv dv, uint32_t epoch)
 {
+    constexpr int kBpSuper = kBpTile * kBpSub;
     // batched launch: frame = blockIdx.y, every per-frame pointer advances by its stride
     {
         const long long f = blockIdx.y;
@@ -174,141 +247,115 @@ __global__ void __launch_bounds__(kBpThreads) backproject_kernel(BackprojectArgs
     __shared__ uint32_t s_bcast[2];
     __shared__ float4 s_pts[kBpTile];
     const int tid = threadIdx.x;
-    const int tile = blockIdx.x;
+    const int tile = blockIdx.x; // index of the run: the unit of both chained scans
     int failed = 0;
     unsigned long long *stateV = a.tile_state;
     unsigned long long *stateK = a.tile_state + a.n_tiles;
     const int npx = a.w * a.h;
-    const int p0 = tile * kBpTile + tid * kBpPix;
+    const int p_first = tile * kBpSuper + tid * kBpPix;
 
-    uint32_t dw[4] = {0, 0, 0, 0}; // 8 u16 depths
-    if (p0 + kBpPix <= npx) {
-        const uint4 raw = *reinterpret_cast<const uint4 *>(a.depth + p0);
-        dw[0] = raw.x; dw[1] = raw.y; dw[2] = raw.z; dw[3] = raw.w;
-    } else {
+    uint32_t dw[kBpSub][4]; // 8 u16 depths per tile of the run
+    uint32_t valid_mask[kBpSub], keep_mask[kBpSub];
+#pragma unroll
+    for (int j = 0; j < kBpSub; ++j) load_depth8(a, p_first + j * kBpTile, npx, dw[j]);
+#pragma unroll
+    for (int j = 0; j < kBpSub; ++j) {
+        valid_mask[j] = 0;
 #pragma unroll
         for (int k = 0; k < kBpPix; ++k)
-            if (p0 + k < npx) dw[k >> 1] |= (uint32_t)a.depth[p0 + k] << (16 * (k & 1));
+            if ((dw[j][k >> 1] >> (16 * (k & 1))) & 0xffffu) valid_mask[j] |= 1u << k;
+        keep_mask[j] = valid_mask[j];
     }
-    uint32_t valid_mask = 0;
-#pragma unroll
-    for (int k = 0; k < kBpPix; ++k)
-        if ((dw[k >> 1] >> (16 * (k & 1))) & 0xffffu) valid_mask |= 1u << k;
 
     constexpr bool need_ordinal = (RULE == ICPB_SUB_STRIDE) || (RULE == ICPB_SUB_STREAM);
     const unsigned long long tag = (unsigned long long)(epoch << 2) << 32;
-    uint32_t keep_mask = valid_mask;
     if (RULE != ICPB_SUB_NONE) {
+        uint32_t v_off[kBpSub];
+#pragma unroll
+        for (int j = 0; j < kBpSub; ++j) v_off[j] = 0;
         uint32_t v_base = 0;
         if (need_ordinal) {
-            uint32_t tile_valid;
-            const uint32_t v_off = block_exclusive_scan(__popc(valid_mask), s_warp, tile_valid);
-            if (tid == 0) st_volatile_u64(&stateV[tile], tag | ((tile == 0 ? 2ull : 1ull) << 32) | tile_valid);
+            uint32_t run_valid = 0;
+#pragma unroll
+            for (int j = 0; j < kBpSub; ++j) {
+                uint32_t t;
+                v_off[j] = run_valid + block_exclusive_scan(__popc(valid_mask[j]), s_warp, t);
+                run_valid += t;
+            }
+            if (tid == 0) st_volatile_u64(&stateV[tile], tag | ((tile == 0 ? 2ull : 1ull) << 32) | run_valid);
             if (tid < 32) {
                 const uint32_t ex = (tile == 0) ? 0u : lookback(stateV, tile, epoch, &failed);
                 if (tid == 0) {
-                    if (tile != 0) st_volatile_u64(&stateV[tile], tag | (2ull << 32) | (ex + tile_valid));
+                    if (tile != 0) st_volatile_u64(&stateV[tile], tag | (2ull << 32) | (ex + run_valid));
                     s_bcast[0] = ex;
                 }
             }
             __syncthreads();
-            v_base = s_bcast[0] + v_off;
+            v_base = s_bcast[0];
         }
-        keep_mask = 0;
-        uint32_t ord = v_base;
         const uint32_t rule_arg = a.rule_arg ? a.rule_arg : 1u;
 #pragma unroll
-        for (int k = 0; k < kBpPix; ++k) {
-            if (valid_mask & (1u << k)) {
-                bool keep = true;
-                if (RULE == ICPB_SUB_STRIDE) keep = (ord % rule_arg) == 0;
-                else if (RULE == ICPB_SUB_HASH) keep = (hash32(a.seed, (uint32_t)(p0 + k)) % rule_arg) == 0;
-                else if (RULE == ICPB_SUB_STREAM) keep = (ord < (uint32_t)a.keep_stream_len) && a.keep_stream[ord] != 0;
-                if (keep) keep_mask |= 1u << k;
-                ++ord;
-            }
-        }
-    }
-    uint32_t tile_keep;
-    const uint32_t k_off = block_exclusive_scan(__popc(keep_mask), s_warp, tile_keep);
-    if (tid == 0) st_volatile_u64(&stateK[tile], tag | ((tile == 0 ? 2ull : 1ull) << 32) | tile_keep);
-
-    // ---- lift the kept pixels into shared memory at their tile-local position (pointcloud.cpp:37-39 / 134-136:
-    //      all float, left to right, true division)
-    if (keep_mask) {
-        uint32_t cw[6] = {0, 0, 0, 0, 0, 0}; // the thread's 8 BGR triples: 24 bytes, three 8-byte loads when aligned
-        if (HAS_BGR) {
-            const uint8_t *c = a.bgr + (size_t)p0 * 3;
-            if (p0 + kBpPix <= npx && ((reinterpret_cast<uintptr_t>(c) & 7) == 0)) {
-                const uint2 *c2 = reinterpret_cast<const uint2 *>(c);
-                const uint2 w0 = c2[0], w1 = c2[1], w2 = c2[2];
-                cw[0] = w0.x; cw[1] = w0.y; cw[2] = w1.x; cw[3] = w1.y; cw[4] = w2.x; cw[5] = w2.y;
-            } else {
-                for (int b = 0; b < 3 * kBpPix; ++b)
-                    if (p0 * 3 + b < npx * 3) cw[b >> 2] |= (uint32_t)c[b] << (8 * (b & 3));
-            }
-        }
-        const int v0 = row_of(p0, a.w, dv.row_magic);
-        const int u0 = p0 - v0 * a.w;
-        // Image widths are multiples of 8 in practice (640, 512): the thread's 8 pixels then share a row and the
-        // coordinates are u0 + k, exactly representable float sums; otherwise every pixel finds its own (u, v).
-        const bool same_row = (a.w % kBpPix) == 0;
-        const float uf0 = (float)u0, vf0 = (float)(v0 + a.v_offset);
-        float4 *dst = &s_pts[k_off];
-        // branch-free: all 8 pixels are lifted (a zero depth just gives z = 0), only the kept ones are stored
+        for (int j = 0; j < kBpSub; ++j) {
+            keep_mask[j] = 0;
+            uint32_t ord = v_base + v_off[j];
 #pragma unroll
-        for (int k = 0; k < kBpPix; ++k) {
-            float uf = uf0 + (float)k, vf = vf0;
-            if (!same_row) {
-                const int pk = p0 + k, vv = pk / a.w;
-                uf = (float)(pk - vv * a.w);
-                vf = (float)(vv + a.v_offset);
-            }
-            const uint32_t d16 = (dw[k >> 1] >> (16 * (k & 1))) & 0xffffu;
-            // (float)d for d < 2^23 without a conversion instruction: 0x4B000000 | d is 2^23 + d
-            const float df = __fsub_rn(__uint_as_float(0x4B000000u | d16), 8388608.0f);
-            const float pz = div_by<FASTDIV>(df, dv.scale);
-            const float px = div_by<FASTDIV>(__fmul_rn(__fsub_rn(uf, a.K.cx_u), pz), dv.fx_u);
-            const float py = div_by<FASTDIV>(__fmul_rn(__fsub_rn(vf, a.K.cx_v), pz), dv.fx_v);
-            uint32_t cbits = 0;
-            if (HAS_BGR) { // bytes 3k .. 3k+2 of the 24-byte run (:47): a funnel shift across two words
-                const int w = (3 * k) >> 2, sh = 8 * ((3 * k) & 3);
-                cbits = __funnelshift_r(cw[w], w + 1 < 6 ? cw[w + 1] : 0u, sh) & 0x00ffffffu;
-            }
-            if (keep_mask & (1u << k)) {
-                *dst = make_float4(px, py, pz, __uint_as_float(cbits));
-                ++dst;
+            for (int k = 0; k < kBpPix; ++k) {
+                if (valid_mask[j] & (1u << k)) {
+                    bool keep = true;
+                    if (RULE == ICPB_SUB_STRIDE) keep = (ord % rule_arg) == 0;
+                    else if (RULE == ICPB_SUB_HASH) keep = (hash32(a.seed, (uint32_t)(p_first + j * kBpTile + k)) % rule_arg) == 0;
+                    else if (RULE == ICPB_SUB_STREAM) keep = (ord < (uint32_t)a.keep_stream_len) && a.keep_stream[ord] != 0;
+                    if (keep) keep_mask[j] |= 1u << k;
+                    ++ord;
+                }
             }
         }
     }
-    // ---- warp 0: exclusive prefix of this tile among the kept pixels (its own lifting is already done)
+    uint32_t k_off[kBpSub], sub_keep[kBpSub], run_keep = 0;
+#pragma unroll
+    for (int j = 0; j < kBpSub; ++j) {
+        k_off[j] = block_exclusive_scan(__popc(keep_mask[j]), s_warp, sub_keep[j]);
+        run_keep += sub_keep[j];
+    }
+    if (tid == 0) st_volatile_u64(&stateK[tile], tag | ((tile == 0 ? 2ull : 1ull) << 32) | run_keep);
+
+    // ---- the first tile of the run goes into the staging buffer at its tile-local positions
+    lift8<HAS_BGR, FASTDIV>(a, dv, p_first, npx, dw[0], keep_mask[0], &s_pts[k_off[0]]);
+    // ---- warp 0: exclusive prefix of this run among the kept pixels (its own lifting is already done)
     if (tid < 32) {
         const uint32_t ex = (tile == 0) ? 0u : lookback(stateK, tile, epoch, &failed);
         if (tid == 0) {
-            if (tile != 0) st_volatile_u64(&stateK[tile], tag | (2ull << 32) | (ex + tile_keep));
+            if (tile != 0) st_volatile_u64(&stateK[tile], tag | (2ull << 32) | (ex + run_keep));
             s_bcast[1] = ex;
             if (failed) *a.out_count = -1;
-            else if (tile == a.n_tiles - 1) *a.out_count = (int)(ex + tile_keep);
+            else if (tile == (int)gridDim.x - 1) *a.out_count = (int)(ex + run_keep);
         }
     }
-    // ---- the tile leaves as ONE bulk copy shared -> global (1-D TMA, UBLKCP): the staged points are contiguous in
+    // ---- every tile leaves as ONE bulk copy shared -> global (1-D TMA, UBLKCP): the staged points are contiguous in
     //      shared memory and in the output, 16-byte aligned at both ends, so no thread has to read them back and store
     //      them (that loop was a quarter of the kernel's instructions and half of its stall samples).  The writers
     //      make their generic-proxy stores visible to the async proxy, the barrier orders them before the copy, and
-    //      the issuing thread keeps the CTA's shared memory alive until the copy has read it.
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
-        const uint32_t tile_base = s_bcast[1];
-        const long long room = (long long)a.capacity - (long long)tile_base;
-        const uint32_t n_out = (uint32_t)max(0ll, min((long long)tile_keep, room));
-        if (n_out) {
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.out + tile_base),
-                         "r"((uint32_t)__cvta_generic_to_shared(s_pts)), "r"(n_out * 16u)
-                         : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    //      the issuing thread holds the buffer (and at the end the CTA's shared memory) until the copy has read it.
+    uint32_t done = 0; // points of the run already copied out (thread 0)
+#pragma unroll
+    for (int j = 0; j < kBpSub; ++j) {
+        if (j > 0) lift8<HAS_BGR, FASTDIV>(a, dv, p_first + j * kBpTile, npx, dw[j], keep_mask[j], &s_pts[k_off[j]]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t base = s_bcast[1] + done;
+            const long long room = (long long)a.capacity - (long long)base;
+            const uint32_t n_out = (uint32_t)max(0ll, min((long long)sub_keep[j], room));
+            if (n_out) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.out + base),
+                             "r"((uint32_t)__cvta_generic_to_shared(s_pts)), "r"(n_out * 16u)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            done += sub_keep[j];
         }
+        if (j + 1 < kBpSub) __syncthreads(); // the buffer is free for the next tile
     }
 }
 
@@ -329,19 +376,6 @@ __device__ __forceinline__ uint32_t local_keep_mask(const uint32_t (&dw)[4], con
         if (keep) m |= 1u << k;
     }
     return m;
-}
-
-__device__ __forceinline__ void load_depth8(const BackprojectArgs &a, int p0, int npx, uint32_t (&dw)[4])
-{
-    dw[0] = dw[1] = dw[2] = dw[3] = 0;
-    if (p0 + kBpPix <= npx) {
-        const uint4 raw = *reinterpret_cast<const uint4 *>(a.depth + p0);
-        dw[0] = raw.x; dw[1] = raw.y; dw[2] = raw.z; dw[3] = raw.w;
-    } else {
-#pragma unroll
-        for (int k = 0; k < kBpPix; ++k)
-            if (p0 + k < npx) dw[k >> 1] |= (uint32_t)a.depth[p0 + k] << (16 * (k & 1));
-    }
 }
 
 template <int RULE>
@@ -479,12 +513,17 @@ void launch_backproject(const BackprojectArgs &a, cudaStream_t s, bool force_two
     epoch = (epoch + 1) & 0x3fffffffu;
     if (epoch == 0) epoch = 1;
     dim3 grid(a.n_tiles, a.frames > 0 ? a.frames : 1);
+    // chained kernel: one CTA per run of 2 or 4 tiles (4 once the launch has tiles for several waves of CTAs)
+    bool sub4 = (long long)a.n_tiles * grid.y >= 8192;
+    if (const char *e = getenv("ICPB_BP_SUB")) sub4 = atoi(e) == 4; // tests pin either run length
+    const int sub = sub4 ? 4 : 2;
+    dim3 cgrid((a.n_tiles + sub - 1) / sub, grid.y);
     BackprojectDiv dv;
     dv.scale = {a.K.depth_scale, (float)(1.0 / (double)a.K.depth_scale)};
     dv.fx_u = {a.K.fx_u, (float)(1.0 / (double)a.K.fx_u)};
     dv.fx_v = {a.K.fx_v, (float)(1.0 / (double)a.K.fx_v)};
     {
-        const unsigned long long reach = (unsigned long long)a.w * a.h + kBpTile; // one past the largest p0
+        const unsigned long long reach = (unsigned long long)a.w * a.h + kBpTile * kBpSubMax; // one past the largest p0
         dv.row_magic = (a.w >= 2 && reach < (1ull << 24) && reach * (unsigned long long)a.w < (1ull << 40))
                            ? (1ull << 40) / (unsigned long long)a.w + 1ull : 0ull;
     }
@@ -492,12 +531,17 @@ void launch_backproject(const BackprojectArgs &a, cudaStream_t s, bool force_two
     // overflow or underflow in the FMA sequence
     const bool fast = fast_div_ok(a.K.depth_scale) && fast_div_ok(a.K.fx_u) && fast_div_ok(a.K.fx_v) &&
                       fabsf(a.K.cx_u) < 1.0e6f && fabsf(a.K.cx_v) < 1.0e6f;
+#define ICPB_BP_LAUNCH_SUB(R, S)                                                                             \
+    do {                                                                                                    \
+        if (a.bgr && fast) backproject_kernel<R, true, true, S><<<cgrid, kBpThreads, 0, s>>>(a, dv, epoch); \
+        else if (a.bgr) backproject_kernel<R, true, false, S><<<cgrid, kBpThreads, 0, s>>>(a, dv, epoch);   \
+        else if (fast) backproject_kernel<R, false, true, S><<<cgrid, kBpThreads, 0, s>>>(a, dv, epoch);    \
+        else backproject_kernel<R, false, false, S><<<cgrid, kBpThreads, 0, s>>>(a, dv, epoch);             \
+    } while (0)
 #define ICPB_BP_LAUNCH(R)                                                                                   \
     do {                                                                                                    \
-        if (a.bgr && fast) backproject_kernel<R, true, true><<<grid, kBpThreads, 0, s>>>(a, dv, epoch);     \
-        else if (a.bgr) backproject_kernel<R, true, false><<<grid, kBpThreads, 0, s>>>(a, dv, epoch);       \
-        else if (fast) backproject_kernel<R, false, true><<<grid, kBpThreads, 0, s>>>(a, dv, epoch);        \
-        else backproject_kernel<R, false, false><<<grid, kBpThreads, 0, s>>>(a, dv, epoch);                 \
+        if (sub4) ICPB_BP_LAUNCH_SUB(R, 4);                                                                 \
+        else ICPB_BP_LAUNCH_SUB(R, 2);                                                                      \
     } while (0)
 #define ICPB_BP_TWO_PASS(R)                                                                                 \
     do {                                                                                                    \
@@ -519,6 +563,7 @@ void launch_backproject(const BackprojectArgs &a, cudaStream_t s, bool force_two
     default: if (two_pass) ICPB_BP_TWO_PASS(ICPB_SUB_NONE); else ICPB_BP_LAUNCH(ICPB_SUB_NONE); break;
     }
 #undef ICPB_BP_LAUNCH
+#undef ICPB_BP_LAUNCH_SUB
 #undef ICPB_BP_TWO_PASS
 }
 

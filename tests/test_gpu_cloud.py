@@ -31,6 +31,24 @@ def test_backproject_rules_v1(ctx, orc, rule, arg):
     c.close()
 
 
+@pytest.mark.parametrize("sub", ["2", "4"])
+@pytest.mark.parametrize("rule,arg", [(0, 1), (1, 7), (2, 3)])
+def test_backproject_tiles_per_cta(ctx, orc, monkeypatch, sub, rule, arg):
+    """The chained kernel walks 2 or 4 tiles per CTA through one staging buffer (4 for launches with thousands of
+    tiles): both run lengths, every subsample rule, on a frame and on sizes that end inside a run."""
+    import icpb200
+    monkeypatch.setenv("ICPB_BP_SUB", sub)
+    depth, bgr = _frame(4)
+    for rows in (480, 13, 7, 3):      # 150 tiles, and frames whose last run is partial or a single short tile
+        d = np.ascontiguousarray(depth[:rows]); b = np.ascontiguousarray(bgr[:rows])
+        c = ctx.cloud(d.size)
+        n = c.from_depth(d, b, icpb200.reference_intrinsics_v1(), rule, arg, seed=99)
+        ref, _, _ = orc.backproject(d, b, orc.kinect_v1(), rule, arg, seed=99)
+        assert n == len(ref)
+        _same_points(c.download(), ref)
+        c.close()
+
+
 def test_backproject_v2_no_color(ctx, orc):
     import icpb200
     from icpb200 import synth
