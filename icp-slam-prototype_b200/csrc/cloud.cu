@@ -7,6 +7,7 @@
 //   filterDepthImage                                        SLAM.cpp:553-573               (8f-1)
 //
 // Built with -fmad=false; float divisions are IEEE (nvcc default -prec-div=true).
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -613,46 +614,74 @@ __device__ __forceinline__ void normal_of(float up, float dn, float lf, float rt
     n2 = (float)((double)v2 * inv);
 }
 
-__global__ void __launch_bounds__(128) normals4_kernel(const uint16_t *__restrict__ depth, int w, int h,
+// kNormRows rows per thread: the kNormRows + 2 depth rows a thread needs are all requested before the first normal is
+// computed (one round trip for the lot, and a row that serves as "below", "centre" and "above" is fetched once instead
+// of three times), and a CTA spans a whole image row when the width allows, so a launch is a few thousand CTAs rather
+// than a quarter of a million 128-thread ones.
+constexpr int kNormRows = 4;
+
+__global__ void __launch_bounds__(256) normals4_kernel(const uint16_t *__restrict__ depth, int w, int h,
                                                        float *__restrict__ normals)
 {
     const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int r = blockIdx.y;
+    const int r0 = blockIdx.y * kNormRows;
     if (c0 >= w) return;
     depth += (size_t)blockIdx.z * w * h;
     normals += (size_t)blockIdx.z * w * h * 3;
-    float out[12];
-    if (r >= 1 && r < h - 1) {
-        const uint2 upw = *reinterpret_cast<const uint2 *>(depth + (size_t)(r - 1) * w + c0);
-        const uint2 dnw = *reinterpret_cast<const uint2 *>(depth + (size_t)(r + 1) * w + c0);
-        const uint2 ctw = *reinterpret_cast<const uint2 *>(depth + (size_t)r * w + c0);
-        const float up[4] = {(float)(upw.x & 0xffffu), (float)(upw.x >> 16), (float)(upw.y & 0xffffu), (float)(upw.y >> 16)};
-        const float dn[4] = {(float)(dnw.x & 0xffffu), (float)(dnw.x >> 16), (float)(dnw.y & 0xffffu), (float)(dnw.y >> 16)};
-        float ct[6];
-        ct[0] = (c0 > 0) ? (float)depth[(size_t)r * w + c0 - 1] : 0.f;
-        ct[1] = (float)(ctw.x & 0xffffu); ct[2] = (float)(ctw.x >> 16);
-        ct[3] = (float)(ctw.y & 0xffffu); ct[4] = (float)(ctw.y >> 16);
-        ct[5] = (c0 + 4 < w) ? (float)depth[(size_t)r * w + c0 + 4] : 0.f;
+    // rows r0 - 1 .. r0 + kNormRows (those inside the image): four pixels each, plus the two outer neighbours
+    uint2 row[kNormRows + 2];
+    uint32_t lf[kNormRows + 2], rt[kNormRows + 2];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int c = c0 + k;
-            normal_of(up[k], dn[k], ct[k], ct[k + 2], c >= 1 && c < w - 1, out[3 * k], out[3 * k + 1], out[3 * k + 2]);
+    for (int j = 0; j < kNormRows + 2; ++j) {
+        const int r = r0 - 1 + j;
+        row[j] = make_uint2(0u, 0u);
+        lf[j] = rt[j] = 0u;
+        if (r >= 0 && r < h) {
+            const uint16_t *p = depth + (size_t)r * w + c0;
+            row[j] = *reinterpret_cast<const uint2 *>(p);
+            if (j >= 1 && j <= kNormRows) { // only centre rows look sideways
+                if (c0 > 0) lf[j] = p[-1];
+                if (c0 + 4 < w) rt[j] = p[4];
+            }
         }
-    } else {
-#pragma unroll
-        for (int k = 0; k < 12; ++k) out[k] = 0.f;
     }
-    float4 *o = reinterpret_cast<float4 *>(normals + ((size_t)r * w + c0) * 3);
-    o[0] = make_float4(out[0], out[1], out[2], out[3]);
-    o[1] = make_float4(out[4], out[5], out[6], out[7]);
-    o[2] = make_float4(out[8], out[9], out[10], out[11]);
+#pragma unroll
+    for (int j = 1; j <= kNormRows; ++j) {
+        const int r = r0 - 1 + j;
+        if (r >= h) break;
+        float out[12];
+        if (r >= 1 && r < h - 1) {
+            const uint2 upw = row[j - 1], dnw = row[j + 1], ctw = row[j];
+            const float up[4] = {(float)(upw.x & 0xffffu), (float)(upw.x >> 16), (float)(upw.y & 0xffffu), (float)(upw.y >> 16)};
+            const float dn[4] = {(float)(dnw.x & 0xffffu), (float)(dnw.x >> 16), (float)(dnw.y & 0xffffu), (float)(dnw.y >> 16)};
+            float ct[6];
+            ct[0] = (float)lf[j];
+            ct[1] = (float)(ctw.x & 0xffffu); ct[2] = (float)(ctw.x >> 16);
+            ct[3] = (float)(ctw.y & 0xffffu); ct[4] = (float)(ctw.y >> 16);
+            ct[5] = (float)rt[j];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c = c0 + k;
+                normal_of(up[k], dn[k], ct[k], ct[k + 2], c >= 1 && c < w - 1, out[3 * k], out[3 * k + 1], out[3 * k + 2]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) out[k] = 0.f;
+        }
+        float4 *o = reinterpret_cast<float4 *>(normals + ((size_t)r * w + c0) * 3);
+        o[0] = make_float4(out[0], out[1], out[2], out[3]);
+        o[1] = make_float4(out[4], out[5], out[6], out[7]);
+        o[2] = make_float4(out[8], out[9], out[10], out[11]);
+    }
 }
 
 void launch_normals(const uint16_t *depth, int w, int h, float *normals, cudaStream_t s, int frames)
 {
     if ((w & 3) == 0 && ((uintptr_t)depth & 7) == 0 && ((uintptr_t)normals & 15) == 0) {
-        dim3 grid((w / 4 + 127) / 128, h, frames);
-        normals4_kernel<<<grid, 128, 0, s>>>(depth, w, h, normals);
+        const int quads = w / 4;
+        const int threads = std::min(256, (quads + 31) / 32 * 32); // 640 -> 160, 512 -> 128: one CTA per row strip
+        dim3 grid((quads + threads - 1) / threads, (h + kNormRows - 1) / kNormRows, frames);
+        normals4_kernel<<<grid, threads, 0, s>>>(depth, w, h, normals);
         return;
     }
     for (int f = 0; f < frames; ++f) { // odd widths: one pixel per thread
