@@ -228,11 +228,15 @@ __device__ __forceinline__ void lift8(const BackprojectArgs &a, const Backprojec
 // the staging buffer (what bounds the CTAs per SM) is held for the whole chain depth-load -> scan -> look-back -> copy.
 // A CTA loads the depth of all its tiles at once and looks back once, then walks the tiles through the same 32 KB
 // buffer: one load round trip and one look-back per kBpSub tiles instead of per tile.  Measured on 256 resident frames:
-// 4,227 GB/s with one tile per CTA, 4,978 with two, 5,113 with four (59 registers, 4 CTAs per SM); launches with few
-// tiles (a single frame is 150) take two so that more SMs take part.
+// 4,227 GB/s with one tile per CTA, 4,978 with two, 5,113 with four at 59 registers (4 CTAs per SM) and 5,450 with
+// four at 40 registers (6 CTAs per SM); launches with few tiles (a single frame is 150) take two so that more SMs
+// take part.
 // Specialised on the subsample rule, on the presence of a colour image and on the division path.
 template <int RULE, bool HAS_BGR, bool FASTDIV, int kBpSub>
-__global__ void __launch_bounds__(kBpThreads) backproject_kernel(BackprojectArgs a, BackprojectDiv dv, uint32_t epoch)
+// (six CTAs per SM is what the 32 KB staging buffer allows: hold the four-tile variant to 40 registers for it -- a
+//  dozen bytes of spill -- 5,113 -> 5,450 GB/s)
+__global__ void __launch_bounds__(kBpThreads, 6)
+backproject_kernel(BackprojectArgs a, BackprojectDiv dv, uint32_t epoch)
 {
     constexpr int kBpSuper = kBpTile * kBpSub;
     // batched launch: frame = blockIdx.y, every per-frame pointer advances by its stride
