@@ -229,3 +229,22 @@ def test_backproject_reference_quirk_and_rules(orc):
     assert np.array_equal(s.view(np.uint8), pts[::2].copy().view(np.uint8))
     st, _, _ = orc.backproject(depth, rule=orc.SUB_STREAM, keep_stream=np.array([0, 1, 1, 0], np.uint8))
     assert np.array_equal(st.view(np.uint8), pts[1:3].copy().view(np.uint8))
+
+
+def test_row_index_multiply_shift_is_the_exact_floor():
+    """cloud.cu `row_of`: p / w as (p * (2^40 // w + 1)) >> 40.  The launcher enables it when w >= 2, the largest p it
+    can see is below 2^24 and p * w < 2^40; inside that envelope it must be the exact floor for every p."""
+    rng = np.random.default_rng(5)
+    widths = [2, 3, 7, 8, 100, 512, 640, 641, 1920, 4095, 4096, 65535]
+    for w in widths:
+        magic = (1 << 40) // w + 1
+        reach = min(1 << 24, (1 << 40) // w)
+        p = np.unique(np.concatenate([
+            np.arange(0, min(reach, 70000), dtype=np.uint64),
+            rng.integers(0, reach, 200000, dtype=np.uint64),
+            np.arange(max(reach - 70000, 0), reach, dtype=np.uint64),
+            (np.arange(1, min(reach // w, 60000) + 1, dtype=np.uint64) * np.uint64(w)) - np.uint64(1),  # last pixel of a row
+        ]))
+        p = p[p < reach]
+        got = (p * np.uint64(magic)) >> np.uint64(40)      # p < 2^24, magic <= 2^39 + 1: no overflow in 64 bits
+        assert np.array_equal(got, p // np.uint64(w)), w
