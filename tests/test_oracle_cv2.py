@@ -133,3 +133,21 @@ def test_normals_match_float64_formula(orc):
     v /= np.linalg.norm(v, axis=-1, keepdims=True)
     assert np.abs(n[1:-1, 1:-1] - v).max() < 1e-7
     assert not n[0].any() and not n[-1].any() and not n[:, 0].any() and not n[:, -1].any()
+
+
+def test_normals_bit_exact_against_the_cv_normalize_formula(orc):
+    """cv::normalize(Vec3f) as OpenCV 3.2 defines it (matx.hpp: `double nv = norm(v); return v * (nv ? 1./nv : 0.)`,
+    norm = sqrt of the squares summed left to right in double, the product rounded to float per component), written out
+    in IEEE double with numpy: the oracle's normals must equal it bit for bit, not just to 1e-7 (SLAM.cpp:412-430)."""
+    rng = np.random.default_rng(11)
+    for (h, w) in [(30, 40), (64, 48), (5, 4)]:
+        d = rng.integers(0, 65536, (h, w)).astype(np.uint16)
+        d[rng.random((h, w)) < 0.2] = 0
+        n = orc.normals(d)
+        f = d.astype(np.float32)
+        dzdx = (f[2:, 1:-1] - f[:-2, 1:-1]) / np.float32(2)          # float arithmetic, :421-422
+        dzdy = (f[1:-1, 2:] - f[1:-1, :-2]) / np.float32(2)
+        v = np.stack([-dzdx, -dzdy, np.ones_like(dzdx)], -1).astype(np.float64)
+        nv = np.sqrt((v[..., 0] * v[..., 0] + v[..., 1] * v[..., 1]) + v[..., 2] * v[..., 2])
+        want = (v * (1.0 / nv)[..., None]).astype(np.float32)
+        assert np.array_equal(n[1:-1, 1:-1].view(np.uint32), want.view(np.uint32))
