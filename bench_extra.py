@@ -504,8 +504,9 @@ def run_normals(args, rank, world, local):
                 "roofline": {"bound": "hbm", "kernel": "normals4_kernel", "achieved": bytes_per_launch / (ms * 1e-3) / 1e9,
                              "peak": peak, "unit": "GB/s", "frac": bytes_per_launch / (ms * 1e-3) / 1e9 / peak, "traffic": None,
                              "bytes_per_launch": bytes_per_launch,
-                             "note": "the reference normalises in double (cv::normalize): one FP64 sqrt and one FP64 divide "
-                                     "per pixel bound the kernel before HBM does"}}
+                             "note": "issue-bound before HBM binds (71 % issue utilisation, profiles/r01_ncu_normals_batch.txt): "
+                                     "the reference normalises in double (cv::normalize), one IEEE FP64 sqrt and one FP64 "
+                                     "reciprocal per pixel"}}
         cb = _cpu_port_rate(lambda orc: [orc.normals(base[f]) for f in range(8)], 8,
                             "oracle normals of 8 of the frames, one thread")
         cb["unit"] = "frames/s"
