@@ -341,6 +341,35 @@ static float nearest_one(const color_point_t &point, color_point_t &nearest, con
     nearest = targets[(size_t)idx];
     return d;
 }
+// icp.cpp:476-486.  The reference reads pointLookupTable[x][y][z]; here the table lives on the device as an index into
+// the map cloud, and a voxel's entry is the single map-cloud point recorded in it -- found on the host by its voxel.
+void processVoxel(color_point_t point, color_point_t &nearest, float &shortestDistance, int x, int y, int z)
+{
+    map::Map &m = *G().map;
+    for (const color_point_t &p : m.mapCloud.points) {
+        const cv::Point3i v = m.getVoxelCoordinates(p.point);
+        if (v.x != x || v.y != y || v.z != z) continue;
+        const float d = distance(point, p);
+        if (d < shortestDistance) {
+            shortestDistance = d;
+            nearest = p;
+        }
+        return; // one entry per voxel
+    }
+}
+
+// icp.cpp:371-474 made exact: the expanding-cube walk is replaced by the exact scan of the map cloud on the device.
+float getNearestMappedPoint(color_point_t point, color_point_t &nearest)
+{
+    map::Map &m = *G().map;
+    if (m.mapCloud.points.empty()) return MAX_NN_COLOR_DISTANCE;
+    color_point_t best;
+    const float d = nearest_one(point, best, m.mapCloud.points);
+    if (!(d < MAX_NN_COLOR_DISTANCE)) return MAX_NN_COLOR_DISTANCE;
+    nearest = best;
+    return d;
+}
+
 float getNearestPoint(color_point_t point, color_point_t &nearest, PointCloud &cloud) { return nearest_one(point, nearest, cloud.points); }       // :566-593
 float getNearestKeyPoint(color_point_t point, color_point_t &nearest, PointCloud &cloud) { return nearest_one(point, nearest, cloud.keypoints); } // :517-539
 

@@ -37,6 +37,12 @@ void findGlobalNearestNeighborAssociations(PointCloud &data, PointCloud &previou
 void findGlobalKeyPointAssociations(PointCloud &data, std::vector<float> &errors, associations_t &associations,
                                     point_list_t &nonAssociations);
 void findMappedNearestNeighborAssociations(PointCloud &data, std::vector<float> &errors, associations_t &associations);
+// icp.cpp:476-486 and :371-474, the helpers of the (dead, out-of-bounds-reading) expanding-cube search.  processVoxel
+// keeps its meaning -- the lookup-table entry of voxel (x, y, z), if any, against the running best -- as a host scalar
+// helper over the map cloud (each voxel's entry is the one map-cloud point recorded in it); getNearestMappedPoint is
+// made exact: the nearest point of the map cloud, MAX_NN_COLOR_DISTANCE when nothing is closer (what :379,:474 return).
+void processVoxel(color_point_t point, color_point_t &nearest, float &shortestDistance, int x, int y, int z);
+float getNearestMappedPoint(color_point_t point, color_point_t &nearest);
 float getNearestPoint(color_point_t point, color_point_t &nearest, PointCloud &cloud);
 float getNearestKeyPoint(color_point_t point, color_point_t &nearest, PointCloud &cloud);
 

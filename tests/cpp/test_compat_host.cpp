@@ -1,0 +1,76 @@
+// Host-only part of the C++ drop-in layer: the scalar helpers that never touch the device (they stay
+// host-side restatements).  Runs without a GPU; prints "ok" or the first failed check.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+#include "icpb200/icp.hpp"
+#include "icpb200/map.hpp"
+#include "icpb200/pointcloud.hpp"
+#include "icpb200/quaternion.hpp"
+
+#define CHECK(c) do { if (!(c)) { std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); return 1; } } while (0)
+
+static color_point_t cp(float x, float y, float z)
+{
+    color_point_t p;
+    p.point = cv::Point3f(x, y, z);
+    p.color = cv::Vec3b(1, 2, 3);
+    return p;
+}
+
+int main()
+{
+    // distance (icp.cpp:595-620), meanSquareError (:622-638), calculateOffset (:314-344)
+    CHECK(icp::distance(cv::Point3f(0, 0, 0), cv::Point3f(3, 4, 0)) == 5.0f);
+    CHECK(icp::distance(cp(1, 1, 1), cp(1, 1, 3)) == 2.0f);
+    std::vector<float> errs = {1.f, 3.f};
+    CHECK(icp::meanSquareError(errs) == 4.0f);
+    CHECK(icp::meanSquareError(std::vector<float>()) == 0.0f);
+    associations_t as;
+    as.push_back(std::make_pair(cp(1, 2, 3), cp(0, 0, 0)));
+    as.push_back(std::make_pair(cp(3, 2, 1), cp(0, 0, 0)));
+    const cv::Point3f off = icp::calculateOffset(as);
+    CHECK(off.x == 2.f && off.y == 2.f && off.z == 2.f);
+
+    // makeRotationMatrix (:640-653): degrees, Rx * Ry * Rz with the reference's sign layout
+    cv::Mat r = icp::makeRotationMatrix(90.f, 0.f, 0.f);
+    CHECK(std::fabs(r.at<float>(1, 2) - 1.f) < 1e-6f && std::fabs(r.at<float>(2, 1) + 1.f) < 1e-6f);
+    CHECK(r.at<float>(0, 0) == 1.f);
+
+    // getVoxelCoordinates (map.cpp:55-85): truncation and clamping
+    map::Map &m = icp::mapState();
+    const float c = float(CELL_PHYSICAL_HEIGHT);
+    cv::Point3i v = m.getVoxelCoordinates(cv::Point3f(5.f, 5.f, 5.f));
+    CHECK(v.x == int(5.f / c) && v.y == v.x && v.z == v.x);
+    v = m.getVoxelCoordinates(cv::Point3f(-1.f, 100.f, 0.f));
+    CHECK(v.x == 0 && v.y == MAP_HEIGHT - 1 && v.z == 0);
+
+    // processVoxel (icp.cpp:476-486): the entry of a voxel against the running best
+    m.mapCloud.points.clear();
+    m.mapCloud.points.push_back(cp(5.01f, 5.01f, 5.01f));
+    m.mapCloud.points.push_back(cp(6.0f, 6.0f, 6.0f));
+    const cv::Point3i v0 = m.getVoxelCoordinates(m.mapCloud.points[0].point);
+    const cv::Point3i v1 = m.getVoxelCoordinates(m.mapCloud.points[1].point);
+    color_point_t nearest = cp(0, 0, 0);
+    float best = MAX_NN_COLOR_DISTANCE;
+    icp::processVoxel(cp(5.0f, 5.0f, 5.0f), nearest, best, v0.x, v0.y, v0.z);
+    CHECK(best == icp::distance(cp(5.0f, 5.0f, 5.0f), m.mapCloud.points[0]));
+    CHECK(nearest == m.mapCloud.points[0]);
+    const float kept = best;
+    icp::processVoxel(cp(5.0f, 5.0f, 5.0f), nearest, best, v1.x, v1.y, v1.z); // farther: the best stays
+    CHECK(best == kept && nearest == m.mapCloud.points[0]);
+    icp::processVoxel(cp(5.0f, 5.0f, 5.0f), nearest, best, 1, 2, 3);          // empty voxel: nothing happens
+    CHECK(best == kept);
+    m.mapCloud.points.clear();
+    // with an empty map cloud nothing is closer than the acceptance radius (icp.cpp:379,474) -- and no device is touched
+    CHECK(icp::getNearestMappedPoint(cp(5, 5, 5), nearest) == MAX_NN_COLOR_DISTANCE);
+
+    // pose reporting (quaternion.cpp:23-79, SLAM.cpp:613-648): identity
+    float eye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    Quaternion q(cv::Mat(3, 3, CV_32FC1, eye));
+    CHECK(std::fabs(q.w - 1.f) < 1e-6f && std::fabs(q.x) < 1e-6f);
+
+    std::printf("ok\n");
+    return 0;
+}
