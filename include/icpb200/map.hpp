@@ -35,6 +35,9 @@ public:
     void update(associations_t associations, int delta_confidencec);                                        // map.cpp:88-119
     void update(associations_t keyPointAssociations, std::vector<float> errors, point_list_t nonAssociations,
                 int delta_confidence);                                                                      // map.cpp:122-151
+    // map.hpp:31 declares a fourth overload that map.cpp never defines (using it does not link in the reference
+    // either); declared here for header parity and left undefined in the same way
+    void update(associations_t keyPointAssociations, std::vector<float> errors, icp::PointCloud &dataCloud, int delta_confidence);
     void rayTrace(cv::Point3i point, cv::Point3i origin, cv::viz::Viz3d &depthWindow);                      // map.cpp:272-439
     void drawCertaintyMap(cv::viz::Viz3d &depthWindow);
     cv::Point3i getVoxelCoordinates(cv::Point3f);                                                           // map.cpp:55-85
