@@ -8,6 +8,7 @@
 //
 // Built with -fmad=false; float divisions are IEEE (nvcc default -prec-div=true).
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -514,9 +515,10 @@ static bool fast_div_ok(float c)
 
 void launch_backproject(const BackprojectArgs &a, cudaStream_t s, bool force_two_pass)
 {
-    static uint32_t epoch = 0; // per-process launch counter; stale tile words never match it
-    epoch = (epoch + 1) & 0x3fffffffu;
-    if (epoch == 0) epoch = 1;
+    // per-process launch counter (atomic: contexts may be driven from different host threads); stale tile words never
+    // match it.  1 .. 2^30 - 1, never 0.
+    static std::atomic<uint32_t> launches{0};
+    const uint32_t epoch = launches.fetch_add(1, std::memory_order_relaxed) % 0x3fffffffu + 1u;
     dim3 grid(a.n_tiles, a.frames > 0 ? a.frames : 1);
     // chained kernel: one CTA per run of 2 or 4 tiles (4 once the launch has tiles for several waves of CTAs)
     bool sub4 = (long long)a.n_tiles * grid.y >= 8192;
