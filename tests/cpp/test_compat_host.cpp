@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 
 #include "icpb200/icp.hpp"
 #include "icpb200/map.hpp"
@@ -19,8 +20,41 @@ static color_point_t cp(float x, float y, float z)
     return p;
 }
 
-int main()
+// "dump" mode: the helpers on a seeded sweep, one value per line, for the comparison against the reference's own
+// compiled functions (tests/test_compat_host.py, Route B)
+static int dump()
 {
+    unsigned int st = 12345u;
+    auto rnd = [&st]() { st = st * 1664525u + 1013904223u; return (float)(st >> 8) / 16777216.0f; };
+    for (int k = 0; k < 64; ++k) {
+        const float ax = rnd() * 360.f - 180.f, ay = rnd() * 360.f - 180.f, az = rnd() * 360.f - 180.f;
+        cv::Mat r = icp::makeRotationMatrix(ax, ay, az);
+        std::printf("R %.9g %.9g %.9g", ax, ay, az);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) std::printf(" %.9g", r.at<float>(i, j));
+        std::printf("\n");
+    }
+    map::Map &m = icp::mapState();
+    for (int k = 0; k < 256; ++k) {
+        const cv::Point3f a(rnd() * 12.f - 1.f, rnd() * 12.f - 1.f, rnd() * 12.f - 1.f), b(rnd() * 10.f, rnd() * 10.f, rnd() * 10.f);
+        const cv::Point3i v = m.getVoxelCoordinates(a);
+        color_point_t ca = cp(a.x, a.y, a.z), cb = cp(b.x, b.y, b.z);
+        std::printf("P %.9g %.9g %.9g %.9g %.9g %.9g %d %d %d %.9g\n", a.x, a.y, a.z, b.x, b.y, b.z, v.x, v.y, v.z,
+                    icp::distance(ca, cb));
+    }
+    for (int n = 0; n < 6; ++n) {
+        std::vector<float> e;
+        for (int i = 0; i < n * 37; ++i) e.push_back(rnd() * 0.75f);
+        std::printf("E %d %.9g", (int)e.size(), icp::meanSquareError(e));
+        for (float x : e) std::printf(" %.9g", x);
+        std::printf("\n");
+    }
+    return 0;
+}
+
+int main(int argc, char **argv)
+{
+    if (argc > 1 && std::string(argv[1]) == "dump") return dump();
     // distance (icp.cpp:595-620), meanSquareError (:622-638), calculateOffset (:314-344)
     CHECK(icp::distance(cv::Point3f(0, 0, 0), cv::Point3f(3, 4, 0)) == 5.0f);
     CHECK(icp::distance(cp(1, 1, 1), cp(1, 1, 3)) == 2.0f);

@@ -28,3 +28,41 @@ def test_drop_in_headers_declare_every_reference_entry_point():
              "points", "keypoints"]
     missing = [n for n in names if not re.search(r"\b%s\b" % n, text)]
     assert not missing, missing
+
+
+def test_host_helpers_equal_the_reference_build():
+    """The same helpers against the reference's OWN functions compiled by path (Route B, oracle/_ref): makeRotationMatrix
+    (icp.cpp:640-653), getVoxelCoordinates (map.cpp:55-85), distance (icp.cpp:606-620), meanSquareError (:622-638) --
+    bit for bit on a seeded sweep."""
+    import numpy as np
+    import pytest
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built (no reference checkout)")
+    r = subprocess.run([BIN, "dump"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0
+    seen = {"R": 0, "P": 0, "E": 0}
+    for line in r.stdout.splitlines():
+        kind, *vals = line.split()
+        seen[kind] += 1
+        if kind == "R":
+            f = np.array(vals, dtype=np.float32)
+            want = ref.make_rotation(float(f[0]), float(f[1]), float(f[2]))
+            assert np.array_equal(f[3:].reshape(3, 3).view(np.uint32), want.view(np.uint32)), line
+        elif kind == "P":
+            a = np.array(vals[0:3], dtype=np.float32); b = np.array(vals[3:6], dtype=np.float32)
+            assert tuple(int(x) for x in vals[6:9]) == ref.voxel(a), line
+            pa = np.zeros(1, dtype=_point_dtype()); pb = np.zeros(1, dtype=_point_dtype())
+            for k, n in enumerate("xyz"):
+                pa[n] = a[k]; pb[n] = b[k]
+            assert np.float32(vals[9]) == np.float32(ref.distance(pa, pb)), line
+        else:
+            n = int(vals[0]); e = np.array(vals[2:], dtype=np.float32)
+            assert len(e) == n
+            assert np.float32(vals[1]) == np.float32(ref.mse(e)), line
+    assert seen == {"R": 64, "P": 256, "E": 6}
+
+
+def _point_dtype():
+    from oracle import oracle as orc
+    return orc.POINT_DTYPE
