@@ -81,6 +81,14 @@ def mse(errors):
     return float(lib().ref_mse(_p(errors), len(errors)))
 
 
+def calculate_offset(a, b):
+    """icp::calculateOffset (icp.cpp:314-344) over the pairs (a[i], b[i])."""
+    a = np.ascontiguousarray(a); b = np.ascontiguousarray(b)
+    out = np.zeros(3, dtype=np.float32)
+    lib().ref_calculate_offset(_p(a), _p(b), len(a), _p(out))
+    return out
+
+
 def make_rotation(x, y, z):
     out = np.zeros(9, dtype=np.float32)
     lib().ref_make_rotation(C.c_float(x), C.c_float(y), C.c_float(z), _p(out))

@@ -103,6 +103,14 @@ void ref_nearest(const ref_point *data, int n, const ref_point *target, int m, r
 
 float ref_mse(const float *errors, int n) { return icp::meanSquareError(std::vector<float>(errors, errors + n)); } // icp.cpp:622
 
+void ref_calculate_offset(const ref_point *a, const ref_point *b, int n, float *out3) // icp.cpp:314-344
+{
+    associations_t as;
+    for (int i = 0; i < n; ++i) as.push_back(std::make_pair(to_cp(a[i]), to_cp(b[i])));
+    cv::Point3f o = icp::calculateOffset(as);
+    out3[0] = o.x; out3[1] = o.y; out3[2] = o.z;
+}
+
 void ref_make_rotation(float x, float y, float z, float *out9) // icp.cpp:640
 {
     cv::Mat R = icp::makeRotationMatrix(x, y, z);

@@ -42,6 +42,17 @@ static int dump()
         std::printf("P %.9g %.9g %.9g %.9g %.9g %.9g %d %d %d %.9g\n", a.x, a.y, a.z, b.x, b.y, b.z, v.x, v.y, v.z,
                     icp::distance(ca, cb));
     }
+    for (int n = 1; n < 5; ++n) { // calculateOffset (icp.cpp:314-344): the sequential float sums of the reference
+        associations_t as;
+        std::printf("O %d", n * 53);
+        for (int i = 0; i < n * 53; ++i) {
+            const color_point_t a = cp(rnd() * 10.f, rnd() * 10.f, rnd() * 10.f), b = cp(rnd() * 10.f, rnd() * 10.f, rnd() * 10.f);
+            as.push_back(std::make_pair(a, b));
+            std::printf(" %.9g %.9g %.9g %.9g %.9g %.9g", a.point.x, a.point.y, a.point.z, b.point.x, b.point.y, b.point.z);
+        }
+        const cv::Point3f o = icp::calculateOffset(as);
+        std::printf(" %.9g %.9g %.9g\n", o.x, o.y, o.z);
+    }
     for (int n = 0; n < 6; ++n) {
         std::vector<float> e;
         for (int i = 0; i < n * 37; ++i) e.push_back(rnd() * 0.75f);

@@ -32,7 +32,7 @@ def test_drop_in_headers_declare_every_reference_entry_point():
 
 def test_host_helpers_equal_the_reference_build():
     """The same helpers against the reference's OWN functions compiled by path (Route B, oracle/_ref): makeRotationMatrix
-    (icp.cpp:640-653), getVoxelCoordinates (map.cpp:55-85), distance (icp.cpp:606-620), meanSquareError (:622-638) --
+    (icp.cpp:640-653), getVoxelCoordinates (map.cpp:55-85), distance (icp.cpp:606-620), meanSquareError (:622-638), calculateOffset (:314-344) --
     bit for bit on a seeded sweep."""
     import numpy as np
     import pytest
@@ -41,7 +41,7 @@ def test_host_helpers_equal_the_reference_build():
         pytest.skip("oracle/_ref not built (no reference checkout)")
     r = subprocess.run([BIN, "dump"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0
-    seen = {"R": 0, "P": 0, "E": 0}
+    seen = {"R": 0, "P": 0, "E": 0, "O": 0}
     for line in r.stdout.splitlines():
         kind, *vals = line.split()
         seen[kind] += 1
@@ -56,11 +56,18 @@ def test_host_helpers_equal_the_reference_build():
             for k, n in enumerate("xyz"):
                 pa[n] = a[k]; pb[n] = b[k]
             assert np.float32(vals[9]) == np.float32(ref.distance(pa, pb)), line
+        elif kind == "O":
+            n = int(vals[0]); f = np.array(vals[1:], dtype=np.float32)
+            pairs = f[:6 * n].reshape(n, 6)
+            pa = np.zeros(n, dtype=_point_dtype()); pb = np.zeros(n, dtype=_point_dtype())
+            for k, name in enumerate("xyz"):
+                pa[name] = pairs[:, k]; pb[name] = pairs[:, 3 + k]
+            assert np.array_equal(f[6 * n:].view(np.uint32), ref.calculate_offset(pa, pb).view(np.uint32)), line[:80]
         else:
             n = int(vals[0]); e = np.array(vals[2:], dtype=np.float32)
             assert len(e) == n
             assert np.float32(vals[1]) == np.float32(ref.mse(e)), line
-    assert seen == {"R": 64, "P": 256, "E": 6}
+    assert seen == {"R": 64, "P": 256, "E": 6, "O": 4}
 
 
 def _point_dtype():
