@@ -137,6 +137,17 @@ def cpu_sample_registration_rate(data, target, n_threads, sample_queries, seed=0
     return 1.0 / per_reg, dt, k
 
 
+def calibrated_sample_queries(data, target, n_threads, seconds, floor):
+    """Number of sample queries that makes one association pass last about `seconds` on THIS host: a short pilot pass
+    gives the cost per pair (the reference's code ran at 18 ns/pair/thread in the authoring container and at 5.7 on the
+    GPU box's host -- a fixed figure misses the 10-30 s window of the bench contract on one of them)."""
+    cpu_sample_registration_rate(data, target, n_threads, min(len(data), 8 * n_threads), seed=12344)  # library load, first touch
+    pilot = min(len(data), 96 * n_threads)
+    _, dt, k = cpu_sample_registration_rate(data, target, n_threads, pilot, seed=12345)
+    per_query = max(dt / k, 1e-9)
+    return int(max(floor, min(len(data), seconds / per_query)))
+
+
 def run_reference(args, rank, world):
     """CPU reference arm: rank 0 alone runs; other ranks exit 0 without work."""
     if rank != 0:
@@ -155,10 +166,8 @@ def run_reference(args, rank, world):
         data = synth.subsample_exact(data, wl["points"], 1)
         target = synth.subsample_exact(target, wl["points"], 2)
     threads = os.cpu_count() or 1
-    # bounded sample: ~2-4 s of wall time per step on a many-core host (18 ns/pair/thread for the reference's own
-    # code, 5.4 for the port, measured)
-    ns_pair = 18.0 if cpu_kind() == "reference" else 5.4
-    sample_q = max(256, min(len(data), int(3.0e9 * threads / max(len(target), 1) / ns_pair)))
+    # bounded sample: ~3 s of wall time per step on all host threads, sized by a pilot pass on this host
+    sample_q = calibrated_sample_queries(data, target, threads, 3.0, 256)
     vals = []
     for s in range(args.warmup + args.steps):
         v, dt, k = cpu_sample_registration_rate(data, target, threads, sample_q, seed=s)
@@ -320,7 +329,7 @@ def run_b200(args, rank, world, local):
         from oracle import oracle as orc
         orc.build()
         dpts, tpts = pristine.download(), target.download()
-        sample_q = max(64, min(n, int(12.0 / (m * (18.0e-9 if cpu_kind() == "reference" else 5.4e-9)))))  # ~12 s, 1 thread
+        sample_q = calibrated_sample_queries(dpts, tpts, 1, 12.0, 64)  # ~12 s of CPU work on one thread
         cpu_v, cpu_dt, cpu_k = cpu_sample_registration_rate(dpts, tpts, 1, sample_q)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
