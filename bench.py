@@ -316,6 +316,41 @@ def run_b200(args, rank, world, local):
     else:
         e2e_total = float(np.sum(e2e_ms))
 
+    # ---- parity at the benchmarked shape (rank 0): the association pass of the timed workload on a seeded sample of
+    #      queries against the oracle's scan (icp.cpp:541-593), indices and distances bit for bit
+    oracle_check = None
+    dpts = tpts = None
+    if rank == 0:
+        from oracle import oracle as orc
+        orc.build()
+        dpts, tpts = pristine.download(), target.download()
+        g_idx, g_dist, _ = ctx.nn_search(pristine, target)
+        sel = np.sort(np.random.default_rng(20261018).choice(n, size=min(2048, n), replace=False))
+        o_idx, o_dist = orc.nn(np.ascontiguousarray(dpts[sel]), tpts, n_threads=os.cpu_count() or 1)
+        oracle_check = {"queries": int(len(sel)), "against": "oracle scan of the full target (icp.cpp:541-593)",
+                        "indices_equal": bool(np.array_equal(g_idx[sel], o_idx)),
+                        "distances_bit_equal": bool(np.array_equal(g_dist[sel].view(np.uint32), o_dist.view(np.uint32)))}
+        assert oracle_check["indices_equal"] and oracle_check["distances_bit_equal"], "GPU association differs from the oracle"
+
+    # ---- the configs that SHARD (BASELINE configs[3] and configs[4]), measured at this N inside the same run so that the
+    #      driver's 1/2/4/8 scaling record holds them: strong scaling, every rank takes part
+    for c in (target, pristine, work, c_prev, c_cur):
+        c.close()
+    ctx.close()
+    del flush
+    torch.cuda.empty_cache()
+    sharded = None
+    if not wl["points"] and not args.no_sharded:
+        import bench_extra
+        import types
+        sub = types.SimpleNamespace(steps=3, warmup=3, batch=args.batch, frames=args.frames, batch_chunk=0)
+        sharded = {"note": "strong scaling at this run's N; each entry is the line `bench.py --workload <name>` prints",
+                   "batch10k": bench_extra.run_batch10k(sub, rank, world, local, emit=False),
+                   "map1cm": bench_extra.run_map1cm(sub, rank, world, local, emit=False)}
+        if world == 1:   # the HBM-bound stages in isolation (north star: GB/s against the copy peak)
+            sharded["hbm_stages"] = {"backproject": bench_extra.run_backproject(sub, rank, world, local, emit=False),
+                                     "normals": bench_extra.run_normals(sub, rank, world, local, emit=False)}
+
     if rank == 0:
         ms_per_step = total_ms / args.steps
         value = world * 1000.0 / ms_per_step
@@ -326,9 +361,6 @@ def run_b200(args, rank, world, local):
         nominal = 148 * 128 * 2 * (clocks["sm_max_mhz"] if clocks else 1965.0) * 1e6 / 1e12
         peak = max(fp32_tf, 1e-9)
         # CPU baseline: oracle port, 1 thread (the reference is single threaded), bounded sample
-        from oracle import oracle as orc
-        orc.build()
-        dpts, tpts = pristine.download(), target.download()
         sample_q = calibrated_sample_queries(dpts, tpts, 1, 12.0, 64)  # ~12 s of CPU work on one thread
         cpu_v, cpu_dt, cpu_k = cpu_sample_registration_rate(dpts, tpts, 1, sample_q)
         line = {
@@ -341,7 +373,7 @@ def run_b200(args, rank, world, local):
                        "nn_filter": {icpb200.FILTER_DIRECT: "direct", icpb200.FILTER_WARP: "warp-centred (Morton-ordered queries)",
                                      icpb200.FILTER_CENTRED: "thread-centred"}[res["nn_filter_used"]],
                        "nn_qpt": res["nn_qpt"], "nn_splits": res["nn_splits"],
-                       "exact_rescans_last_step": res["exact_rescans"]},
+                       "exact_rescans_last_step": res["exact_rescans"], "oracle_check": oracle_check},
             "extra": {"nn_correspondences_per_s": world * n * (ITERS + 1) / (ms_per_step * 1e-3),
                       "nn_pairs_per_s": world * float(n) * m * (ITERS + 1) / (ms_per_step * 1e-3),
                       "nn_partial_share_of_step": (nn_ms / total_ms if events_in_timed else None) if world == 1 else None,
@@ -372,8 +404,9 @@ def run_b200(args, rank, world, local):
             "gpu_launches": int(l1 - l0),
             "clocks": clocks,
         }
+        if sharded is not None:
+            line["extra"]["sharded"] = sharded
         print(json.dumps(line), flush=True)
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -387,6 +420,8 @@ def main():
     ap.add_argument("--workload", default="fullres", choices=sorted(WORKLOADS) + list(EXTRA_WORKLOADS))
     ap.add_argument("--frames", type=int, default=0, help="frames for the map1cm / trajectory workloads")
     ap.add_argument("--batch", type=int, default=1024, help="registrations for the batch10k workload (whole job)")
+    ap.add_argument("--batch-chunk", type=int, default=0, help="registrations per icpb_icp_register_batch call (0 = default)")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the extra.sharded block (configs[3] / configs[4])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     # ONE JSON line on stdout: Python's prints keep the real stdout, anything native code writes to file descriptor 1

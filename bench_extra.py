@@ -66,7 +66,13 @@ def _max_over_ranks(torch, world, local, value):
     return float(t.item())
 
 
-def run_batch10k(args, rank, world, local):
+def _fp32_nominal():
+    return 148 * 128 * 2 * 1.965e9 / 1e12
+
+
+def run_batch10k(args, rank, world, local, emit=True):
+    """configs[3]: args.batch independent 10k-point registrations, contiguous blocks of the batch per rank, no
+    data-path collective; the poses are gathered at the end.  Strong scaling.  Returns the JSON line on rank 0."""
     import icpb200
     from icpb200 import dist as D
     from icpb200 import synth
@@ -84,13 +90,15 @@ def run_batch10k(args, rank, world, local):
         full.from_depth(d0, col, K); full.transform(None, cam); t = full.download()
         full.from_depth(d1, col, K); full.transform(None, cam); d = full.download()
         pairs.append((d, t))
-    datas, targets, pristine = [], [], []
+    full.close()
+    datas, targets, pristine, host = [], [], [], []
     for i in range(lo, hi):
         d, t = pairs[i % 8]
         dp = synth.subsample_exact(d, 10000, 1000 + i)
         tp = synth.subsample_exact(t, 10000, 5000 + i)
+        host.append((dp, tp))
         datas.append(ctx.cloud_from_points(dp)); targets.append(ctx.cloud_from_points(tp)); pristine.append(ctx.cloud_from_points(dp))
-    chunk = 64
+    chunk = args.batch_chunk if getattr(args, "batch_chunk", 0) else 128
 
     def step():
         ctx.timer_start()
@@ -112,29 +120,82 @@ def run_batch10k(args, rank, world, local):
     l1 = ctx.launch_count()
     _barrier(torch, world)
     tot = _max_over_ranks(torch, world, local, float(np.sum(ms_all)))
-    # every pose must equal the single-registration result (spot check on this rank)
-    if datas:
-        datas[0].copy_from(pristine[0])
-        single, _, _ = ctx.icp_register(datas[0], targets[0], ITERS, 0.0, 0.75, icpb200.SOLVE_REFERENCE)
-        assert np.array_equal(single["pose_R"], res[0]["pose_R"]) and np.array_equal(single["pose_t"], res[0]["pose_t"])
+    # roofline of the scan kernel: the same steps again with CUDA events around every nn_partial launch
+    ctx.set_profiling(True)
+    nn_ms, nn_launches, qpt, splits, filt = 0.0, 0, 0, 0, 0
+    for _ in range(max(1, min(args.steps, 2))):
+        _, rp = step()
+        # one set of events per batch call: every registration of a call reports the call's figures
+        for b in range(0, len(rp), chunk):
+            nn_ms += rp[b]["nn_partial_ms"]; nn_launches += rp[b]["nn_partial_launches"]
+        qpt, splits, filt = rp[0]["nn_qpt"], rp[0]["nn_splits"], rp[0]["nn_filter_used"]
+    ctx.set_profiling(False)
+    # e2e: host point lists in, poses out -- uploads and the result blocks inside the timed region
+    e2e_ms = []
+    for s in range(2):
+        ctx.sync()
+        t0 = time.perf_counter()
+        for b in range(0, len(datas), chunk):
+            for (dp, tp), dcl, tcl in zip(host[b:b + chunk], datas[b:b + chunk], targets[b:b + chunk]):
+                dcl.upload(dp); tcl.upload(tp)
+            ctx.icp_register_batch(datas[b:b + chunk], targets[b:b + chunk], ITERS, 0.0, 0.75, icpb200.SOLVE_REFERENCE)
+        ctx.sync()
+        e2e_ms.append((time.perf_counter() - t0) * 1e3)
+    e2e_tot = _max_over_ranks(torch, world, local, float(e2e_ms[-1]))
     rows = torch.tensor(np.array([np.concatenate([r["pose_R"].ravel(), r["pose_t"]]) for r in res]).reshape(-1, 12),
                         dtype=torch.float64, device=f"cuda:{local}")
     allrows = D.gather_results(rows) if world > 1 else rows
+    line = None
     if rank == 0:
         ms_per_step = tot / args.steps
         digest = hashlib.sha256(allrows.cpu().numpy().tobytes()).hexdigest()
+        # oracle check + CPU baseline in one: registration 0 of the batch through the oracle port on one thread
+        cpu, oracle_ok = None, None
+        try:
+            from oracle import oracle as orc
+            orc.build()
+            dp, tp = host[0]
+            t0 = time.perf_counter()
+            ref, rout, _, _ = orc.icp(dp, tp, ITERS, 0.0, 0.75, orc.SOLVE_REFERENCE, n_threads=1)
+            cdt = time.perf_counter() - t0
+            oracle_ok = bool(np.array_equal(ref["pose_R"], res[0]["pose_R"]) and np.array_equal(ref["pose_t"], res[0]["pose_t"])
+                             and ref["n_assoc"] == res[0]["n_assoc"])
+            cpu = {"value": 1.0 / cdt, "unit": "registrations/s", "cores": 1, "kind": "port",
+                   "sample": f"registration 0 of the batch (10k x 10k, {ITERS + 1} passes) through the oracle port, one thread ({cdt:.2f} s)"}
+        except ImportError as e:
+            cpu = {"unavailable": str(e)}
+        assert oracle_ok is not False, "batch registration 0 differs from the oracle"
+        n_loc = len(datas)
+        flop_per_launch = 8.0 * 1e4 * 1e4 * min(chunk, n_loc)
+        avg_s = nn_ms / max(nn_launches, 1) * 1e-3
+        ach = flop_per_launch / max(avg_s, 1e-12) / 1e12
         line = {"metric": "icp_registrations_per_s", "value": total * 1000.0 / ms_per_step, "unit": "registrations/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"configs[3]: batch of {total} independent Kinect v1 10k-point registrations, "
                                        "20 iterations, sharded by index", "per_call_batch": chunk,
-                           "pose_sha256": digest, "l2": "working set (batch clouds + partials) exceeds L2"},
+                           "pose_sha256": digest, "registration_0_equals_oracle": oracle_ok,
+                           "l2": "working set (batch clouds + partials) exceeds L2"},
+                "roofline": {"bound": "fp32", "kernel": f"nn_partial ({'warp' if filt == icpb200.FILTER_WARP else 'centred'}-filter)<{qpt}>, {splits} splits",
+                             "achieved": ach, "peak": _fp32_nominal(), "unit": "TFLOP/s", "frac": ach / _fp32_nominal(),
+                             "traffic": None, "flop_per_launch": flop_per_launch, "avg_launch_ms": avg_s * 1e3,
+                             "launches_timed": nn_launches,
+                             "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (rank 0's launches)"},
+                "cpu_baseline": cpu,
+                "e2e": {"value": total * 1000.0 / e2e_tot, "unit": "registrations/s",
+                        "h2d_bytes_per_step": int(total * 2 * 10000 * 16), "d2h_bytes_per_step": int(total * 304)},
                 "gpu_launches": int(l1 - l0)}
-        print(json.dumps(line), flush=True)
+        if emit:
+            print(json.dumps(line), flush=True)
+    for c in datas + targets + pristine:
+        c.close()
     ctx.close()
+    return line
 
 
-def run_map1cm(args, rank, world, local):
+def run_map1cm(args, rank, world, local, emit=True):
+    """configs[4]: full-resolution Kinect v1 frames into the 600x600x500 1 cm grid, z-slab sharded.  Strong scaling.
+    The concatenated slabs are compared with the ORACLE's grid of the same sequence (and with the unsharded GPU grid)."""
     import icpb200
     from icpb200 import dist as D
     from icpb200 import synth
@@ -161,10 +222,11 @@ def run_map1cm(args, rank, world, local):
     sm = D.SlabMap(ctx, dims, cell, rank, world, 640 * 480, bounds)
 
     # depth frames resident in HBM before the timed region (the metric's definition); int16 view of the u16 bits
-    d_depths = torch.from_numpy(np.stack(depths).astype(np.uint16).view(np.int16)).to(torch.device("cuda", local))
+    host_depths = torch.from_numpy(np.stack(depths).astype(np.uint16).view(np.int16)).pin_memory()
+    d_depths = host_depths.to(torch.device("cuda", local))
     frame_bytes = 640 * 480 * 2
 
-    def step(count):
+    def step(count, h2d=False):
         npts = vis = 0
         ctx.timer_start()
         if count:   # counted pass: the host-synchronising calls, which also report the voxel visits
@@ -173,6 +235,8 @@ def run_map1cm(args, rank, world, local):
                 npts += n; vis += v
         else:       # timed passes: the sync-free frame path, nothing returns to the host until the end
             for f, (R, t) in enumerate(poses):
+                if h2d:  # e2e leg: the frame comes from pinned host memory on the same stream
+                    d_depths[f].copy_(host_depths[f], non_blocking=True)
                 sm.integrate_device(d_depths.data_ptr() + f * frame_bytes, 640, 480, K, R, t, 25, 25)
         return ctx.timer_stop(), npts, vis
 
@@ -188,6 +252,20 @@ def run_map1cm(args, rank, world, local):
         ms_all.append(ms)
     _barrier(torch, world)
     tot = _max_over_ranks(torch, world, local, float(np.sum(ms_all)))
+    # the ray-walk kernel's own time (roofline), same sequence with CUDA events around every launch
+    ctx.set_profiling(True)
+    step(False)
+    rays_ms, rays_launches = ctx.profile_read(icpb200.PROF_MAP_RAYS)
+    ends_ms, _ = ctx.profile_read(icpb200.PROF_MAP_ENDPOINTS)
+    lift_ms, _ = ctx.profile_read(icpb200.PROF_LIFT)
+    ctx.set_profiling(False)
+    rays_ms = _max_over_ranks(torch, world, local, rays_ms)
+    # e2e: every depth frame copied from pinned host memory inside the timed region, point count read back at the end
+    e2e = []
+    for _ in range(2):
+        ms, _, _ = step(False, h2d=True)
+        e2e.append(ms)
+    e2e_tot = _max_over_ranks(torch, world, local, float(e2e[-1]))
     h = hashlib.sha256(slab.tobytes()).hexdigest()
     if world > 1:
         import torch.distributed as dist
@@ -204,11 +282,38 @@ def run_map1cm(args, rank, world, local):
         g1 = one.download()
         unsharded_ok = all(hashlib.sha256(np.ascontiguousarray(g1[:, :, lo:hi]).tobytes()).hexdigest() == hh
                            for (lo, hi, hh, _) in hs)
+        one.map.close()
+        del g1
         assert unsharded_ok, "z-slab result differs from the single-GPU grid"
+    line = None
     if rank == 0:
         ms_per_step = tot / args.steps
         updates = visited + npts  # voxels visited by rays + endpoint updates, per pass over the sequence
         alg_bytes = 2.0 * visited + 12.0 * npts + 14.0 * npts
+        rays_bytes = 2.0 * visited + 12.0 * npts        # 2 B per visited voxel + 12 B per ray
+        peak = _hbm_peak()
+        rays_gbs = rays_bytes / max(rays_ms * 1e-3, 1e-12) / 1e9
+        # the whole sequence through the oracle: every slab of the counted pass must equal the oracle grid's slab
+        cb, oracle_ok = None, None
+        try:
+            from oracle import oracle as orc
+            orc.build()
+            grid = np.zeros(dims, np.uint8)
+            t0 = time.perf_counter()
+            ov = 0
+            for (R, t), dpt in zip(poses, depths):
+                pts, _, _ = orc.backproject(dpt, None, orc.kinect_v1())
+                pts = orc.translate(orc.rotate(pts, np.asarray(R, np.float32)), np.asarray(t, np.float32))
+                ov += orc.map_integrate_rays(grid, dims, np.float32(cell), pts, tuple(float(x) for x in t), 25, 25)
+            cdt = time.perf_counter() - t0
+            oracle_ok = bool(ov == visited and all(
+                hashlib.sha256(np.ascontiguousarray(grid[:, :, lo:hi]).tobytes()).hexdigest() == hh for (lo, hi, hh, _) in hs))
+            cb = {"value": (ov + npts) / cdt, "unit": "voxel updates/s", "cores": 1, "kind": "port",
+                  "sample": f"the whole {frames}-frame sequence (lift + ray integration) through the oracle port, one thread ({cdt:.1f} s)"}
+            del grid
+        except ImportError as e:
+            cb = {"unavailable": str(e)}
+        assert oracle_ok is not False, "z-slab result differs from the oracle's grid"
         line = {"metric": "voxel_updates_per_s", "value": updates / (ms_per_step * 1e-3), "unit": "voxel updates/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -217,27 +322,29 @@ def run_map1cm(args, rank, world, local):
                                        "lifted points per frame; depth frames resident in HBM, no host synchronisation "
                                        "inside the sequence",
                            "rays_per_pass": npts, "voxels_visited_per_pass": visited, "slabs": hs,
-                           "slabs_equal_single_gpu_grid": unsharded_ok,
+                           "slabs_equal_single_gpu_grid": unsharded_ok, "slabs_equal_oracle_grid": oracle_ok,
                            "l2": "grid (180 MB) exceeds L2 at 1 GPU"},
                 "extra": {"frames_per_s": frames / (ms_per_step * 1e-3),
-                          "algorithmic_GBps": alg_bytes / (ms_per_step * 1e-3) / 1e9}}
-
-        def _one_frame(orc):
-            R, t = poses[0]
-            pts, _, _ = orc.backproject(depths[0], None, orc.kinect_v1())
-            pts = orc.translate(orc.rotate(pts, np.asarray(R, np.float32)), np.asarray(t, np.float32))
-            grid = np.zeros(dims, np.uint8)
-            orc.map_integrate_rays(grid, dims, np.float32(cell), pts, tuple(float(x) for x in t), 25, 25)
-
-        cb = _cpu_port_rate(_one_frame, visited / frames,
-                            "oracle lift + ray integration of the first frame into the 1 cm grid, one thread")
-        cb["unit"] = "voxel updates/s"
-        line["cpu_baseline"] = cb
-        print(json.dumps(line), flush=True)
+                          "algorithmic_GBps": alg_bytes / (ms_per_step * 1e-3) / 1e9,
+                          "stage_ms_per_pass_rank0": {"lift": lift_ms, "map_rays_max_over_ranks": rays_ms, "map_endpoints": ends_ms}},
+                "roofline": {"bound": "hbm", "kernel": "map_rays_brick_kernel", "achieved": rays_gbs, "peak": peak,
+                             "unit": "GB/s", "frac": rays_gbs / peak, "traffic": None,
+                             "bytes_per_launch": rays_bytes / max(rays_launches, 1),
+                             "avg_launch_ms": rays_ms / max(rays_launches, 1), "launches_timed": rays_launches,
+                             "note": "algorithmic bytes = 2 B per voxel the walk passes + 12 B per ray (SURVEY.md 8d); the "
+                                     "brick-skipping walk does not touch the voxels of empty bricks, so the figure can "
+                                     "exceed what the memory system moves"},
+                "cpu_baseline": cb,
+                "e2e": {"value": updates / (e2e_tot * 1e-3), "unit": "voxel updates/s",
+                        "h2d_bytes_per_step": int(frames * frame_bytes), "d2h_bytes_per_step": 4}}
+        if emit:
+            print(json.dumps(line), flush=True)
+    sm.map.close()
     ctx.close()
+    return line
 
 
-def run_backproject(args, rank, world, local):
+def run_backproject(args, rank, world, local, emit=True):
     """HBM-bound stage in isolation: a batch of resident Kinect v1 frames -> XYZ clouds in one sync-free launch."""
     import icpb200
     from icpb200 import synth
@@ -282,11 +389,13 @@ def run_backproject(args, rank, world, local):
                             "oracle back-projection of 8 of the frames, one thread")
         cb["unit"] = "frames/s"
         line["cpu_baseline"] = cb
-        print(json.dumps(line), flush=True)
+        if emit:
+            print(json.dumps(line), flush=True)
     ctx.close()
+    return line if rank == 0 else None
 
 
-def run_trajectory(args, rank, world, local):
+def run_trajectory(args, rank, world, local, emit=True):
     """configs[2]: every rank runs the same trajectory (replicas; a single sequence does not shard)."""
     import icpb200
     from icpb200 import synth
@@ -357,12 +466,14 @@ def run_trajectory(args, rank, world, local):
                 "extra": {"stage_host_wall_s": stage, "render_s_untimed": render_s,
                           "note": "the map stage is enqueued without a host synchronisation (sync-free frame path): its "
                                   "host wall time is launch cost only, the device work overlaps the next frame"}}
-        print(json.dumps(line), flush=True)
+        if emit:
+            print(json.dumps(line), flush=True)
     ctx_map.close()
     ctx.close()
+    return line if rank == 0 else None
 
 
-def run_live(args, rank, world, local):
+def run_live(args, rank, world, local, emit=True):
     """the per-frame loop exactly as the reference runs it (icp.cpp:28-285, key-point association
     against the growing map cloud, rule-C map update), frames/s through the C-ABI; beside it the reference's OWN
     icp::getTransformation (oracle/_ref, single thread like the reference) on the same frames and key-points.
@@ -463,11 +574,13 @@ def run_live(args, rank, world, local):
                                        "host->device copies of every frame",
                            "map_keypoints_at_end": int(n_map), "per_rank": "replica of the same sequence"},
                 "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        if emit:
+            print(json.dumps(line), flush=True)
     ctx.close()
+    return line if rank == 0 else None
 
 
-def run_normals(args, rank, world, local):
+def run_normals(args, rank, world, local, emit=True):
     """P3 in isolation (SLAM.cpp:412-430): a batch of resident Kinect v1 frames -> per-pixel normals, one launch."""
     import icpb200
     from icpb200 import synth
@@ -511,5 +624,7 @@ def run_normals(args, rank, world, local):
                             "oracle normals of 8 of the frames, one thread")
         cb["unit"] = "frames/s"
         line["cpu_baseline"] = cb
-        print(json.dumps(line), flush=True)
+        if emit:
+            print(json.dumps(line), flush=True)
     ctx.close()
+    return line if rank == 0 else None

@@ -72,6 +72,27 @@ int pinned_get(icpb_ctx *ctx, size_t bytes, void **out)
     return ICPB_OK;
 }
 
+// profiling spans (icpb_ctx_profile_read): no-ops unless the context is in profiling mode
+int span_begin(icpb_ctx *ctx, int kernel)
+{
+    if (!ctx->profiling) return -1;
+    icpb_ctx::Span sp;
+    cudaEvent_t *ev[2] = {&sp.a, &sp.b};
+    for (auto e : ev) {
+        if (!ctx->ev_pool.empty()) { *e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); }
+        else if (cudaEventCreate(e) != cudaSuccess) return -1;
+    }
+    sp.kernel = kernel;
+    cudaEventRecord(sp.a, ctx->stream);
+    ctx->spans.push_back(sp);
+    return (int)ctx->spans.size() - 1;
+}
+
+void span_end(icpb_ctx *ctx, int id)
+{
+    if (id >= 0) cudaEventRecord(ctx->spans[id].b, ctx->stream);
+}
+
 int env_int(const char *name, int dflt)
 {
     const char *v = getenv(name);
@@ -362,10 +383,15 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
     }
     for (int pass = 0; pass < passes; ++pass) {
         if (prof) CU(ctx, cudaEventRecord(ctx->prof_events[2 * pass], st));
-        if (grid_mode) launch_nn_grid(d_descs, count, max_n, pass, ctx->sm_count, st);
-        else launch_nn_partial(d_descs, d_states, count, max_n, qpt, splits, pass, filter, st);
+        if (grid_mode) {
+            const int sp = span_begin(ctx, ICPB_PROF_NN_GRID);
+            launch_nn_grid(d_descs, count, max_n, pass, ctx->sm_count, st);
+            span_end(ctx, sp);
+        } else launch_nn_partial(d_descs, d_states, count, max_n, qpt, splits, pass, filter, st);
         if (prof) CU(ctx, cudaEventRecord(ctx->prof_events[2 * pass + 1], st));
+        const int spf = span_begin(ctx, ICPB_PROF_NN_FINALIZE);
         launch_nn_finalize(d_descs, d_states, d_prm, count, max_n, grid_mode ? 0 : splits, pass, filter, st);
+        span_end(ctx, spf);
         launches += grid_mode ? 3 : 2;
     }
     launch_pending_translate(d_descs, count, max_n, st);
@@ -534,6 +560,8 @@ int icpb_ctx_destroy(icpb_ctx *ctx)
     cudaEventDestroy(ctx->evt0);
     cudaEventDestroy(ctx->evt1);
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+    for (const icpb_ctx::Span &sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return ICPB_OK;
@@ -568,6 +596,26 @@ int icpb_ctx_set_profiling(icpb_ctx *ctx, int enabled)
 {
     if (!ctx) return ICPB_ERR_INVALID;
     ctx->profiling = enabled != 0;
+    return ICPB_OK;
+}
+
+int icpb_ctx_profile_read(icpb_ctx *ctx, int kernel, float *ms, int *launches)
+{
+    if (!ctx || kernel < 0 || kernel >= ICPB_PROF_COUNT) return ICPB_ERR_INVALID;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    float total = 0.f;
+    int count = 0;
+    std::vector<icpb_ctx::Span> keep;
+    for (const icpb_ctx::Span &sp : ctx->spans) {
+        if (sp.kernel != kernel) { keep.push_back(sp); continue; }
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) { total += t; ++count; }
+        ctx->ev_pool.push_back(sp.a);
+        ctx->ev_pool.push_back(sp.b);
+    }
+    ctx->spans.swap(keep);
+    if (ms) *ms = total;
+    if (launches) *launches = count;
     return ICPB_OK;
 }
 
@@ -1082,6 +1130,19 @@ int icpb_map_create(icpb_ctx *ctx, const int dims[3], float cell, int z_lo, int 
     if (ce != cudaSuccess) { delete m; return fail(ctx, ICPB_ERR_CUDA, "cudaMalloc(map)", ce); }
     ce = cudaMemsetAsync(m->dev.grid, 0, alloc, ctx->stream); // map.cpp:23-30
     if (ce != cudaSuccess) { cudaFree(m->dev.grid); delete m; return fail(ctx, ICPB_ERR_CUDA, "cudaMemset(map)", ce); }
+    // brick occupancy bits (icpb_internal.h), all clear = "every voxel is zero"
+    const long long nbx = (dims[0] + kBrick - 1) / kBrick;
+    m->dev.nby = (dims[1] + kBrick - 1) / kBrick;
+    m->dev.nbz = (m->dev.zs + kBrick - 1) / kBrick;
+    m->brick_words = (nbx * m->dev.nby * m->dev.nbz + 31) / 32;
+    ce = cudaMalloc((void **)&m->dev.bricks, sizeof(uint32_t) * (size_t)m->brick_words);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(m->dev.bricks, 0, sizeof(uint32_t) * (size_t)m->brick_words, ctx->stream);
+    if (ce != cudaSuccess) {
+        cudaFree(m->dev.grid);
+        if (m->dev.bricks) cudaFree(m->dev.bricks);
+        delete m;
+        return fail(ctx, ICPB_ERR_CUDA, "cudaMalloc(map occupancy)", ce);
+    }
     *out = m;
     return ICPB_OK;
 }
@@ -1092,6 +1153,7 @@ int icpb_map_destroy(icpb_map *map)
     cudaSetDevice(map->ctx->device);
     cudaStreamSynchronize(map->ctx->stream);
     cudaFree(map->dev.grid);
+    cudaFree(map->dev.bricks);
     if (map->table) cudaFree(map->table);
     delete map;
     return ICPB_OK;
@@ -1103,6 +1165,7 @@ int icpb_map_clear(icpb_map *map)
     icpb_ctx *ctx = map->ctx;
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaMemsetAsync(map->dev.grid, 0, ((size_t)map->bytes + 3) / 4 * 4, ctx->stream));
+    CU(ctx, cudaMemsetAsync(map->dev.bricks, 0, sizeof(uint32_t) * (size_t)map->brick_words, ctx->stream));
     if (map->table) CU(ctx, cudaMemsetAsync(map->table, 0xff, sizeof(int) * (size_t)map->bytes, ctx->stream));
     return ICPB_OK;
 }
@@ -1192,8 +1255,12 @@ int icpb_map_integrate_rays(icpb_map *map, const icpb_cloud *points, const float
         d_vis = (unsigned long long *)((char *)misc + 48);
         CU(ctx, cudaMemsetAsync(d_vis, 0, sizeof(unsigned long long), ctx->stream));
     }
+    int sp = span_begin(ctx, ICPB_PROF_MAP_RAYS);
     launch_map_rays(map->dev, points->d_pts, points->n, origin, delta_dec, d_vis, d_next, ctx->sm_count, ctx->stream); // phase 1
+    span_end(ctx, sp);
+    sp = span_begin(ctx, ICPB_PROF_MAP_ENDPOINTS);
     launch_map_endpoints(map->dev, points->d_pts, points->n, ICPB_RULE_A, delta_inc, 0, ctx->stream);  // phase 2
+    span_end(ctx, sp);
     ctx->launches += 2 * (points->n > 0);
     CU(ctx, cudaGetLastError());
     if (voxels_visited) {
@@ -1237,8 +1304,10 @@ int icpb_frame_lift_band_device(icpb_ctx *ctx, const void *d_depth, int w, int h
     a.out_count = (int *)d_band;
     a.tile_state = (unsigned long long *)ts + 2;
     CU(ctx, cudaMemsetAsync(d_band, 0, sizeof(float4), ctx->stream));
+    const int sp = span_begin(ctx, ICPB_PROF_LIFT);
     launch_backproject(a, ctx->stream);
     if (R || t) launch_transform(a.out, band_capacity, R, t, R != nullptr, t != nullptr, ctx->stream, (const int *)d_band);
+    span_end(ctx, sp);
     ctx->launches += 1 + ((R || t) ? 1 : 0);
     CU(ctx, cudaGetLastError());
     return ICPB_OK;
@@ -1271,8 +1340,12 @@ int icpb_map_integrate_bands_device(icpb_map *map, const void *d_bands, int worl
         pts = frame;
         d_n = d_total;
     }
+    int sp = span_begin(ctx, ICPB_PROF_MAP_RAYS);
     launch_map_rays(map->dev, pts, cap, origin, delta_dec, nullptr, d_next, ctx->sm_count, ctx->stream, d_n); // phase 1
+    span_end(ctx, sp);
+    sp = span_begin(ctx, ICPB_PROF_MAP_ENDPOINTS);
     launch_map_endpoints(map->dev, pts, cap, ICPB_RULE_A, delta_inc, 0, ctx->stream, d_n);                   // phase 2
+    span_end(ctx, sp);
     ctx->launches += 2;
     CU(ctx, cudaGetLastError());
     return ICPB_OK;
@@ -1315,7 +1388,10 @@ int icpb_map_upload(icpb_map *map, const uint8_t *in, long long size)
     if (size != map->bytes) return fail(ctx, ICPB_ERR_INVALID, "icpb_map_upload: size mismatch");
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaMemcpyAsync(map->dev.grid, in, (size_t)size, cudaMemcpyHostToDevice, ctx->stream));
+    launch_map_rebuild_bricks(map->dev, map->brick_words, ctx->stream);
+    ctx->launches += 1;
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaGetLastError());
     return ICPB_OK;
 }
 

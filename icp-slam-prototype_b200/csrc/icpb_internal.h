@@ -172,12 +172,22 @@ void launch_normals(const uint16_t *depth, int w, int h, float *normals, cudaStr
 void launch_depth_filter(const uint16_t *in, uint16_t *tmp_a, uint16_t *tmp_b, uint16_t *out, int w, int h,
                          int min_d, int max_d, cudaStream_t s);
 
+// Coarse occupancy of the certainty grid: one bit per brick of kBrick^3 voxels (slab-relative z), set whenever a voxel
+// of the brick is written non-zero and only cleared by icpb_map_clear / rebuilt by icpb_map_upload.  A clear bit proves
+// that every voxel of the brick is zero, so the ray walk (whose decrement of a zero voxel is a no-op, map.cpp:423) may
+// cross the brick without reading it.  600x600x500 at 1 cm: 75x75x63 bits = 44 KB, L1-resident.
+constexpr int kBrickLog = 3;
+constexpr int kBrick = 1 << kBrickLog;
+
 struct MapDev {
-    uint8_t *grid;    // slab storage: [(x*dimY + y)*zs + (z - z_lo)], zs = z_hi - z_lo padded to 4
+    uint8_t *grid;    // slab storage: [(x*dimY + y)*zs + (z - z_lo)], zs = z_hi - z_lo; the allocation is padded to 4 bytes
     int dims[3];
     int z_lo, z_hi, zs;
     float cell;
+    uint32_t *bricks; // occupancy bits, index (bx*nby + by)*nbz + bz
+    int nby, nbz;     // bricks along y and along the slab's z
 };
+void launch_map_rebuild_bricks(const MapDev &m, long long brick_words, cudaStream_t s);
 void launch_map_endpoints(const MapDev &m, const float4 *pts, int n, int rule, int delta, int max_conf,
                           cudaStream_t s, const int *n_dev = nullptr);
 void launch_map_tracked(const MapDev &m, int *table, const float4 *pts, int n, int variant, int delta, int max_conf,
@@ -207,6 +217,13 @@ struct icpb_ctx {
     size_t pinned_bytes = 0;
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;
+    // profiling mode: CUDA-event spans around individual kernels other than nn_partial (icpb_ctx_profile_read)
+    struct Span {
+        cudaEvent_t a, b;
+        int kernel;
+    };
+    std::vector<Span> spans;          // recorded, not yet read
+    std::vector<cudaEvent_t> ev_pool; // recycled events
 };
 
 struct icpb_cloud {
@@ -221,4 +238,5 @@ struct icpb_map {
     icpb::MapDev dev{};
     long long bytes = 0;
     int *table = nullptr; // lazily allocated lookup table: index into the map cloud, -1 = empty (map.hpp:24)
+    long long brick_words = 0; // 32-bit words of dev.bricks
 };

@@ -9,6 +9,8 @@
 // voxel give f^k(c) in any order: the kernels apply them with 32-bit CAS on
 // the word holding four packed voxels and the grid is bit-exact regardless
 // of scheduling.
+#include <cstdlib>
+
 #include "icpb_internal.h"
 
 namespace icpb {
@@ -46,18 +48,59 @@ __device__ __forceinline__ void byte_rmw(uint8_t *grid, size_t lin, F fn)
     }
 }
 
+// ---- brick occupancy (icpb_internal.h): bit (bx*nby + by)*nbz + bz covers voxels [8bx, 8bx+8) x [8by, ..) x [8bz, ..)
+__device__ __forceinline__ unsigned brick_bit(const MapDev &m, int x, int y, int zr)
+{
+    return (unsigned)(((x >> kBrickLog) * m.nby + (y >> kBrickLog)) * m.nbz + (zr >> kBrickLog));
+}
+
+// a voxel of the brick became (or stays) non-zero; the read keeps the common case free of atomics
+__device__ __forceinline__ void brick_mark(const MapDev &m, int x, int y, int zr)
+{
+    const unsigned b = brick_bit(m, x, y, zr);
+    uint32_t *w = m.bricks + (b >> 5);
+    const uint32_t mask = 1u << (b & 31);
+    if (!(*reinterpret_cast<volatile uint32_t *>(w) & mask)) atomicOr(w, mask);
+}
+
+// icpb_map_upload: recompute every bit from the grid.  One thread per brick column segment would be unbalanced for
+// thin slabs; one thread per brick, 8x8 rows of up to 8 bytes each, is plenty for a call that follows a host copy.
+__global__ void map_rebuild_bricks_kernel(MapDev m, int nbx)
+{
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nb = (long long)nbx * m.nby * m.nbz;
+    if (b >= nb) return;
+    const int bz = (int)(b % m.nbz), by = (int)((b / m.nbz) % m.nby), bx = (int)(b / ((long long)m.nbz * m.nby));
+    bool any = false;
+    for (int x = bx * kBrick; x < min((bx + 1) * kBrick, m.dims[0]) && !any; ++x)
+        for (int y = by * kBrick; y < min((by + 1) * kBrick, m.dims[1]) && !any; ++y) {
+            const uint8_t *row = m.grid + ((long long)x * m.dims[1] + y) * m.zs;
+            for (int z = bz * kBrick; z < min((bz + 1) * kBrick, m.zs); ++z) any |= row[z] != 0;
+        }
+    if (any) atomicOr(m.bricks + (b >> 5), 1u << (b & 31));
+}
+
+void launch_map_rebuild_bricks(const MapDev &m, long long brick_words, cudaStream_t s)
+{
+    cudaMemsetAsync(m.bricks, 0, sizeof(uint32_t) * (size_t)brick_words, s);
+    const int nbx = (m.dims[0] + kBrick - 1) / kBrick;
+    const long long nb = (long long)nbx * m.nby * m.nbz;
+    map_rebuild_bricks_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, s>>>(m, nbx);
+}
+
 __global__ void map_endpoints_kernel(MapDev m, const float4 *__restrict__ pts, int n, int rule, int delta,
                                      int max_conf, const int *__restrict__ n_dev)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n_dev) n = min(n, *n_dev);
+    if (n_dev) n = max(0, min(n, *n_dev)); // a negative header (-1: the lift's look-back timed out) means "no points"
     const int lane = threadIdx.x & 31;
     long long lin = -1;
+    int vx = 0, vy = 0, vz = 0;
     if (i < n) {
         float4 p = pts[i];
-        int vx = voxel_axis(p.x, m.cell, m.dims[0]);
-        int vy = voxel_axis(p.y, m.cell, m.dims[1]);
-        int vz = voxel_axis(p.z, m.cell, m.dims[2]);
+        vx = voxel_axis(p.x, m.cell, m.dims[0]);
+        vy = voxel_axis(p.y, m.cell, m.dims[1]);
+        vz = voxel_axis(p.z, m.cell, m.dims[2]);
         if (vz >= m.z_lo && vz < m.z_hi) lin = ((long long)vx * m.dims[1] + vy) * m.zs + (vz - m.z_lo);
     }
     // neighbouring pixels land in the same voxel: one CAS per distinct voxel per warp
@@ -65,6 +108,9 @@ __global__ void map_endpoints_kernel(MapDev m, const float4 *__restrict__ pts, i
     if (lin < 0) return;
     if ((__ffs(peers) - 1) != lane) return;
     const int k = __popc(peers);
+    // a positive delta leaves the voxel non-zero whatever it held: the brick is occupied from now on.  Marked BEFORE the
+    // voxel write; the ray walk of the same frame has finished (phase 1 precedes phase 2 on the stream).
+    if (delta > 0) brick_mark(m, vx, vy, vz - m.z_lo);
     byte_rmw(m.grid, (size_t)lin, [&](uint32_t c) {
         for (int r = 0; r < k && c != 255u; ++r) c = rule_apply(c, rule, delta, max_conf);
         return c;
@@ -149,7 +195,11 @@ __global__ void __launch_bounds__(kTrackThreads) map_tracked_kernel(MapDev m, in
         const int i = c0 + tid;
         const int fl = (i < n) ? flags[i] : 0;
         const int insert = fl & 1;
-        if (fl & 2) m.grid[vox_scratch[i]] = (uint8_t)(fl >> 8);
+        if (fl & 2) {
+            const long long v = vox_scratch[i];
+            m.grid[v] = (uint8_t)(fl >> 8);
+            if ((fl >> 8) & 0xff) brick_mark(m, (int)(v / ((long long)m.zs * m.dims[1])), (int)((v / m.zs) % m.dims[1]), (int)(v % m.zs));
+        }
         const int lane = tid & 31, wid = tid >> 5;
         int inc = insert;
 #pragma unroll
@@ -166,8 +216,8 @@ __global__ void __launch_bounds__(kTrackThreads) map_tracked_kernel(MapDev m, in
         __syncthreads();
         const int total = s_warp[32];
         const int pos = s_base + s_warp[wid] + inc - insert;
-        if (insert) {
-            if (pos < dst_capacity) dst[pos] = pts[i];
+        if (insert && pos < dst_capacity) { // past the capacity nothing is recorded: the call fails with ICPB_ERR_CAPACITY
+            dst[pos] = pts[i];
             table[vox_scratch[i]] = pos;
         }
         __syncthreads();
@@ -274,7 +324,7 @@ __global__ void __launch_bounds__(128) map_rays_kernel(MapDev m, const float4 *_
                                                       int oz, int delta_dec, unsigned long long *visited,
                                                       unsigned int *next_ray, const int *__restrict__ n_dev)
 {
-    if (n_dev) n = min(n, *n_dev);
+    if (n_dev) n = max(0, min(n, *n_dev));
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     RayState<I> r;
@@ -342,6 +392,208 @@ __global__ void __launch_bounds__(128) map_rays_kernel(MapDev m, const float4 *_
     }
 }
 
+// ---- M4 phase 1 with brick skipping --------------------------------------------------------------------------
+// The same walk, but a brick whose occupancy bit is clear holds only zero voxels, and decrementing a zero voxel is a
+// no-op (map.cpp:423): the walk crosses such a brick in ONE jump instead of one dependent byte load per voxel (the
+// byte-at-a-time kernel above spent 9.6 of every 10 issue slots waiting on those loads, profiles/r01_ncu_map_rays_*).
+// The jump is computed from the walk's own integer state, so the voxels entered afterwards are exactly the ones the
+// step-by-step walk enters: with k_a = steps along axis a that leave the brick (capped by the walls the ray still has
+// to cross), the exit wall is the earliest of the three T_a = e_a + (k_a - 1) d_a in the walk's order (ties x < y < z);
+// before it the other axes cross c_a = #{ j : e_a + j d_a precedes T } walls (<= for an axis that goes first on ties,
+// < otherwise) -- two integer divisions.  The jump stops on the LAST voxel inside the brick; the ordinary step that
+// follows enters the next brick and looks its bit up (only steps that cross a brick boundary do).  In occupied bricks
+// the walk steps voxel by voxel as before, the byte reads of up to kRayGroup steps in flight together.
+template <typename I>
+struct RayBrick {
+    I ex, ey, ez, dxs, dys, dzs;
+    int x, y, zr;     // current voxel, z relative to the slab
+    int rx, ry, rz;   // walls still to cross per axis
+    int sgn;          // step signs + 1, two bits per axis
+    int rem;          // visits still to make
+    bool empty;       // occupancy bit of the current voxel's brick is clear
+};
+
+__device__ __forceinline__ bool brick_is_empty(const MapDev &m, int x, int y, int zr)
+{
+    const unsigned b = brick_bit(m, x, y, zr);
+    return ((__ldg(m.bricks + (b >> 5)) >> (b & 31)) & 1u) == 0u;
+}
+
+template <typename I>
+__device__ __forceinline__ void ray_setup_brick(const MapDev &m, const float4 p, int ox, int oy, int oz, int delta_dec,
+                                                RayBrick<I> &r, unsigned long long &visits)
+{
+    const int ex_ = voxel_axis(p.x, m.cell, m.dims[0]);
+    const int ey_ = voxel_axis(p.y, m.cell, m.dims[1]);
+    const int ez_ = voxel_axis(p.z, m.cell, m.dims[2]);
+    const int nx = abs(ex_ - ox), ny = abs(ey_ - oy), nz = abs(ez_ - oz);
+    const int sx = (ex_ > ox) - (ex_ < ox), sy = (ey_ > oy) - (ey_ < oy), sz = (ez_ > oz) - (ez_ < oz);
+    const I mx = nx ? nx : 1, my = ny ? ny : 1, mz = nz ? nz : 1;
+    const I P3 = 3 * mx * my * mz;
+    r.ex = nx ? my * mz : P3; r.ey = ny ? mx * mz : P3; r.ez = nz ? mx * my : P3;
+    r.dxs = 2 * my * mz; r.dys = 2 * mx * mz; r.dzs = 2 * mx * my;
+    const int steps = nx + ny + nz;
+    visits += steps > 0 ? (unsigned long long)(steps - 1) : 0ull;
+    int cx = 0, cy = 0, cz = 0;
+    bool live = true, entered_now = false;
+    // slab clipping: see ray_setup above
+    if (oz < m.z_lo || oz >= m.z_hi) {
+        long long k = 0;
+        if (sz > 0 && oz < m.z_lo) k = (long long)m.z_lo - oz;
+        else if (sz < 0 && oz >= m.z_hi) k = (long long)oz - (m.z_hi - 1);
+        if (k <= 0 || k > nz) live = false;
+        else {
+            cz = (int)k;
+            cx = nx ? (int)min((long long)nx, ((2 * k - 1) * nx + nz) / (2LL * nz)) : 0;
+            cy = ny ? (int)min((long long)ny, ((2 * k - 1) * ny + nz) / (2LL * nz)) : 0;
+            if (nx) r.ex = (I)(2 * cx + 1) * my * mz;
+            if (ny) r.ey = (I)(2 * cy + 1) * mx * mz;
+            r.ez = (I)(2 * cz + 1) * mx * my;
+            entered_now = true;
+        }
+    }
+    r.x = ox + sx * cx; r.y = oy + sy * cy; r.zr = oz + sz * cz - m.z_lo;
+    r.rx = nx - cx; r.ry = ny - cy; r.rz = nz - cz;
+    r.sgn = (sx + 1) | ((sy + 1) << 2) | ((sz + 1) << 4);
+    const int done_steps = cx + cy + cz;
+    r.rem = live ? max(steps - 1 - done_steps, 0) : 0;
+    r.empty = false;
+    if (live) {
+        r.empty = brick_is_empty(m, r.x, r.y, r.zr);
+        // the voxel just entered by the jump is itself a visit unless it is the endpoint
+        if (entered_now && done_steps <= steps - 1 && !r.empty) {
+            const long long lin0 = ((long long)r.x * m.dims[1] + r.y) * m.zs + r.zr;
+            if (m.grid[lin0] != 0)
+                byte_rmw(m.grid, (size_t)lin0, [&](uint32_t c) { return c > (uint32_t)delta_dec ? c - delta_dec : 0u; });
+        }
+    }
+}
+
+// walls j in [0, r) of an axis with e + j d before time T: "<= T" when the axis goes first on ties, "< T" otherwise
+template <typename I>
+__device__ __forceinline__ int walls_before(I e, I d, int r, I T, bool first_on_ties)
+{
+    const I lim = T - e - (first_on_ties ? (I)0 : (I)1);
+    const int c = lim < 0 ? 0 : (int)(lim / d) + 1;
+    return min(c, r);
+}
+
+template <typename I>
+__device__ __forceinline__ void ray_jump(const MapDev &m, RayBrick<I> &r)
+{
+    const int sx = (r.sgn & 3) - 1, sy = ((r.sgn >> 2) & 3) - 1, sz = ((r.sgn >> 4) & 3) - 1;
+    const int lx = r.x & (kBrick - 1), ly = r.y & (kBrick - 1), lz = r.zr & (kBrick - 1);
+    // steps along each axis that leave the brick (the slab's upper face also ends the z-run)
+    const int kx = sx > 0 ? kBrick - lx : lx + 1;
+    const int ky = sy > 0 ? kBrick - ly : ly + 1;
+    const int kz = sz > 0 ? min(kBrick - lz, m.zs - r.zr) : lz + 1;
+    const bool vx = kx <= r.rx, vy = ky <= r.ry, vz = kz <= r.rz; // r_a = 0 for an axis that does not move
+    const I big = sizeof(I) == 4 ? (I)0x7fffffff : (I)0x7fffffffffffffffLL;
+    const I Tx = vx ? r.ex + (I)(kx - 1) * r.dxs : big;
+    const I Ty = vy ? r.ey + (I)(ky - 1) * r.dys : big;
+    const I Tz = vz ? r.ez + (I)(kz - 1) * r.dzs : big;
+    if (!(vx || vy || vz)) { r.rem = 0; return; } // the ray ends inside this (empty) brick
+    const bool bx = (Tx <= Ty) && (Tx <= Tz);
+    const bool by = !bx && (Ty <= Tz);
+    const I T = bx ? Tx : (by ? Ty : Tz);
+    // walls crossed inside the brick: all but the last of the exit axis, and whatever the others cross before T
+    const int cx = bx ? kx - 1 : walls_before<I>(r.ex, r.dxs, r.rx, T, true);
+    const int cy = by ? ky - 1 : walls_before<I>(r.ey, r.dys, r.ry, T, !bx);
+    const int cz = (!bx && !by) ? kz - 1 : walls_before<I>(r.ez, r.dzs, r.rz, T, false);
+    const int skip = cx + cy + cz;
+    if (skip >= r.rem) { r.rem = 0; return; } // every remaining visit lies in the empty brick
+    r.rem -= skip;
+    r.x += sx * cx; r.y += sy * cy; r.zr += sz * cz;
+    r.rx -= cx; r.ry -= cy; r.rz -= cz;
+    r.ex += (I)cx * r.dxs; r.ey += (I)cy * r.dys; r.ez += (I)cz * r.dzs;
+}
+
+template <typename I>
+__global__ void __launch_bounds__(128) map_rays_brick_kernel(MapDev m, const float4 *__restrict__ pts, int n, int ox, int oy,
+                                                            int oz, int delta_dec, unsigned long long *visited,
+                                                            unsigned int *next_ray, const int *__restrict__ n_dev)
+{
+    if (n_dev) n = max(0, min(n, *n_dev));
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    RayBrick<I> r;
+    r.ex = r.ey = r.ez = r.dxs = r.dys = r.dzs = 0;
+    r.x = r.y = r.zr = r.rx = r.ry = r.rz = 0;
+    r.sgn = 0x15;
+    r.rem = 0;
+    r.empty = false;
+    unsigned long long my_visits = 0;
+    bool drained = false; // warp-uniform: the counter has passed n
+    uint8_t *g = m.grid;
+    const unsigned zs = (unsigned)m.zs;
+    const long long ystride = m.zs, xstride = (long long)m.dims[1] * m.zs;
+    while (true) {
+        const unsigned idle = __ballot_sync(0xffffffffu, r.rem <= 0);
+        if (!drained && __popc(idle) >= kRayRefill) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(next_ray, (unsigned)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (r.rem <= 0) {
+                const unsigned i = base + (unsigned)__popc(idle & lt);
+                if (i < (unsigned)n) ray_setup_brick<I>(m, pts[i], ox, oy, oz, delta_dec, r, my_visits);
+            }
+            drained = base + (unsigned)__popc(idle) >= (unsigned)n;
+        }
+        if (__ballot_sync(0xffffffffu, r.rem > 0) == 0u) {
+            if (drained) break;
+            continue;
+        }
+#pragma unroll 1
+        for (int k = 0; k < kRayBurst / kRayGroup; ++k) {
+            if (r.rem > 0 && r.empty) ray_jump<I>(m, r);
+            const int sx = (r.sgn & 3) - 1, sy = ((r.sgn >> 2) & 3) - 1, sz = ((r.sgn >> 4) & 3) - 1;
+            long long at[kRayGroup];
+            bool in[kRayGroup];
+            bool halt = false; // the walk has just entered an empty brick: the next round jumps across it
+#pragma unroll
+            for (int u = 0; u < kRayGroup; ++u) {
+                in[u] = false;
+                at[u] = 0;
+                if (r.rem > 0 && !halt) {
+                    const bool px = (r.ex <= r.ey) && (r.ex <= r.ez);
+                    const bool py = !px && (r.ey <= r.ez);
+                    const bool pz = !px && !py;
+                    r.x += px ? sx : 0; r.y += py ? sy : 0; r.zr += pz ? sz : 0;
+                    r.rx -= px; r.ry -= py; r.rz -= pz;
+                    r.ex += px ? r.dxs : (I)0;
+                    r.ey += py ? r.dys : (I)0;
+                    r.ez += pz ? r.dzs : (I)0;
+                    --r.rem;
+                    if ((unsigned)r.zr >= zs) { r.rem = 0; halt = true; } // left the slab for good
+                    else {
+                        // the coordinate that moved tells whether a brick boundary was crossed
+                        const int c = px ? r.x : (py ? r.y : r.zr);
+                        const int s = px ? sx : (py ? sy : sz);
+                        const bool crossed = ((c & (kBrick - 1)) == (s > 0 ? 0 : kBrick - 1));
+                        if (crossed) r.empty = brick_is_empty(m, r.x, r.y, r.zr);
+                        in[u] = !r.empty;
+                        halt = r.empty;
+                        at[u] = (long long)r.x * xstride + (long long)r.y * ystride + r.zr;
+                    }
+                }
+            }
+            uint8_t v[kRayGroup];
+#pragma unroll
+            for (int u = 0; u < kRayGroup; ++u) v[u] = in[u] ? g[at[u]] : (uint8_t)0;
+            // phase 1 only lowers values, so a cached non-zero byte is at worst stale-high: the CAS re-reads it
+#pragma unroll
+            for (int u = 0; u < kRayGroup; ++u)
+                if (v[u] != 0)
+                    byte_rmw(g, (size_t)at[u], [&](uint32_t c) { return c > (uint32_t)delta_dec ? c - delta_dec : 0u; });
+        }
+    }
+    if (visited) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) my_visits += __shfl_xor_sync(0xffffffffu, my_visits, off);
+        if (lane == 0 && my_visits) atomicAdd(visited, my_visits);
+    }
+}
+
 void launch_map_rays(const MapDev &m, const float4 *pts, int n, const float origin[3], int delta_dec,
                      unsigned long long *visited, unsigned int *next_ray, int sm_count, cudaStream_t s, const int *n_dev)
 {
@@ -358,6 +610,15 @@ void launch_map_rays(const MapDev &m, const float4 *pts, int n, const float orig
         o[k] = q;
     }
     const double prod = 3.0 * m.dims[0] * m.dims[1] * m.dims[2];
+    static const bool bricks = []() { const char *e = getenv("ICPB_RAY_BRICKS"); return !(e && *e == '0'); }();
+    if (bricks) { // default: cross empty bricks in one jump
+        if (prod < 2147483647.0)
+            map_rays_brick_kernel<int><<<blocks, 128, 0, s>>>(m, pts, n, o[0], o[1], o[2], delta_dec, visited, next_ray, n_dev);
+        else
+            map_rays_brick_kernel<long long><<<blocks, 128, 0, s>>>(m, pts, n, o[0], o[1], o[2], delta_dec, visited, next_ray, n_dev);
+        return;
+    }
+    // ICPB_RAY_BRICKS=0: the byte-at-a-time walk (kept for A/B measurements)
     if (prod < 2147483647.0)
         map_rays_kernel<int><<<blocks, 128, 0, s>>>(m, pts, n, o[0], o[1], o[2], delta_dec, visited, next_ray, n_dev);
     else

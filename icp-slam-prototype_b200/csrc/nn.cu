@@ -1320,7 +1320,7 @@ struct RtArgs {
 __global__ void transform_kernel(float4 *pts, int n, RtArgs a, int have_R, int have_t, const int *__restrict__ n_dev)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n_dev) n = min(n, *n_dev);
+    if (n_dev) n = max(0, min(n, *n_dev)); // -1 in a band header: the lift failed, no points
     if (i >= n) return;
     float4 p = pts[i];
     if (have_R) {

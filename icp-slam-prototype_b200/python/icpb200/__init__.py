@@ -26,6 +26,7 @@ RULE_A, RULE_C = 0, 1
 NN_BRUTE, NN_GRID, NN_AUTO = 0, 1, 2
 FILTER_AUTO, FILTER_DIRECT, FILTER_WARP, FILTER_CENTRED = 0, 1, 2, 3
 TRACK_INIT, TRACK_ASSOC, TRACK_NONASSOC = 0, 1, 2
+PROF_MAP_RAYS, PROF_MAP_ENDPOINTS, PROF_NN_GRID, PROF_NN_FINALIZE, PROF_LIFT = 0, 1, 2, 3, 4
 
 
 class IcpbError(RuntimeError):
@@ -158,6 +159,13 @@ class Context:
 
     def set_profiling(self, enabled=True):
         self.check(self.lib.icpb_ctx_set_profiling(self.h, int(bool(enabled))))
+
+    def profile_read(self, kernel):
+        """(summed ms, launches) of `kernel` (PROF_*) since the last read; profiling mode only."""
+        ms = C.c_float(0)
+        k = C.c_int(0)
+        self.check(self.lib.icpb_ctx_profile_read(self.h, int(kernel), C.byref(ms), C.byref(k)))
+        return ms.value, k.value
 
     def launch_count(self):
         n = C.c_longlong(0)

@@ -138,6 +138,17 @@ int icpb_timer_stop(icpb_ctx *ctx, float *elapsed_ms);
 /* Profiling mode: bracket every nn_partial launch with CUDA events on the context
  * stream and report their summed duration in icpb_icp_result (roofline evidence). */
 int icpb_ctx_set_profiling(icpb_ctx *ctx, int enabled);
+/* Profiling mode also brackets every launch of the kernels below with CUDA events on the context stream;
+ * icpb_ctx_profile_read synchronises the stream, returns the summed duration and the number of launches of `kernel`
+ * since the last read, and forgets them (the per-kernel times behind bench.py's roofline figures; the stage names
+ * follow the reference's logDeltaTime keys, SLAM.hpp:4-13, where one exists). */
+enum { ICPB_PROF_MAP_RAYS = 0,     /* Map::rayTrace, map.cpp:272-439 */
+       ICPB_PROF_MAP_ENDPOINTS = 1, /* Map::update, map.cpp:220-269 */
+       ICPB_PROF_NN_GRID = 2,      /* LOG_NEAREST_NEIGHBOR: the cell-grid search kernels of one pass */
+       ICPB_PROF_NN_FINALIZE = 3,  /* LOG_SVD / LOG_ROTATE / LOG_TRANSLATE: sums + solve */
+       ICPB_PROF_LIFT = 4,         /* LOG_GEN_POINT_CLOUD: back-projection (+ transform) of one frame */
+       ICPB_PROF_COUNT = 5 };
+int icpb_ctx_profile_read(icpb_ctx *ctx, int kernel, float *ms, int *launches);
 /* Kernels launched on this context since creation. */
 int icpb_ctx_launch_count(icpb_ctx *ctx, long long *count);
 /* Dense FP32 FMA micro-benchmark: the measured roofline denominator for the

@@ -258,3 +258,88 @@ def test_frame_band_argument_checks(ctx):
     assert int(band[0, 0].view(torch.int32).item()) == 0
     assert int(m.download().sum()) == 0
     m.close()
+
+
+# ---- brick occupancy (round 2): the walk crosses bricks whose bit is clear in one jump -----------------------------
+
+def _sparse_start(rng, dims, p_brick, brick=8):
+    """A grid that is zero except inside a random subset of 8^3 bricks (there: random bytes, many of them zero)."""
+    nb = [-(-d // brick) for d in dims]
+    occ = rng.random(nb) < p_brick
+    mask = np.repeat(np.repeat(np.repeat(occ, brick, 0), brick, 1), brick, 2)[: dims[0], : dims[1], : dims[2]]
+    vals = rng.integers(0, 120, dims).astype(np.uint8) * (rng.random(dims) < 0.4)
+    return (vals * mask).astype(np.uint8)
+
+
+@pytest.mark.parametrize("p_brick", [0.0, 0.05, 0.3, 1.0])
+@pytest.mark.parametrize("dims,bounds", [((64, 48, 72), [0, 72]), ((61, 43, 70), [0, 7, 8, 30, 55, 70]),
+                                         ((9, 200, 17), [0, 3, 17])])
+def test_brick_skipping_walk_sparse_grids(ctx, orc, p_brick, dims, bounds):
+    """Random rays through grids whose occupied voxels sit in a random subset of bricks, whole map and ragged z-slabs
+    (slab heights that are not multiples of the brick, dims that are not either): every slab byte-equal to the oracle,
+    over two frames so that the second walk crosses the bricks the first frame's endpoints occupied."""
+    cell = 0.05
+    rng = np.random.default_rng(int(p_brick * 100) + dims[0])
+    start = _sparse_start(rng, dims, p_brick)
+    want = start.copy()
+    hi = np.array(dims) * cell
+    frames = []
+    for f in range(2):
+        xyz = rng.uniform([0, 0, 0], hi, (12000, 3)).astype(np.float32)
+        origin = tuple(float(v) for v in rng.uniform([0, 0, 0], hi))
+        frames.append((orc.make_points(xyz), origin))
+        orc.map_integrate_rays(want, dims, cell, frames[-1][0], origin, 25, 25)
+    parts = []
+    for lo, hi_z in zip(bounds[:-1], bounds[1:]):
+        s = ctx.map(dims, cell, lo, hi_z)
+        s.upload(np.ascontiguousarray(start[:, :, lo:hi_z]))
+        for pts, origin in frames:
+            c = ctx.cloud_from_points(pts)
+            s.integrate_rays(c, origin, 25, 25)
+            c.close()
+        parts.append(s.download())
+        s.close()
+    got = np.concatenate(parts, axis=2)
+    assert np.array_equal(got, want), f"{(got != want).sum()} voxels differ"
+
+
+def test_brick_bits_follow_clear_upload_and_endpoint_updates(ctx, orc):
+    """The occupancy bits must never claim "empty" for a brick that holds a non-zero voxel, whichever call wrote it:
+    endpoint updates (rule A and C), tracked updates, upload; clear resets them.  Checked through the walk's result."""
+    import icpb200
+    dims, cell = (48, 48, 48), 0.05
+    rng = np.random.default_rng(5)
+    hi = np.array(dims) * cell
+    m = ctx.map(dims, cell)
+    want = np.zeros(dims, np.uint8)
+
+    def rays(seed):
+        r = np.random.default_rng(seed)
+        pts = orc.make_points(r.uniform([0, 0, 0], hi, (6000, 3)).astype(np.float32))
+        origin = tuple(float(v) for v in r.uniform([0, 0, 0], hi))
+        c = ctx.cloud_from_points(pts)
+        m.integrate_rays(c, origin, 40, 25)
+        orc.map_integrate_rays(want, dims, cell, pts, origin, 40, 25)
+        c.close()
+        assert np.array_equal(m.download(), want)
+
+    for rule in (0, 1):
+        pts = orc.make_points(rng.uniform([0, 0, 0], hi, (3000, 3)).astype(np.float32))
+        c = ctx.cloud_from_points(pts)
+        m.update_endpoints(c, rule, 60, 180)
+        orc.map_update_endpoints(want, dims, cell, pts, rule, 60, 180)
+        c.close()
+        rays(10 + rule)
+    kp = orc.make_points(rng.uniform([0, 0, 0], hi, (2000, 3)).astype(np.float32))
+    c = ctx.cloud_from_points(kp)
+    mc = ctx.cloud(4096)
+    m.update_tracked(c, icpb200.TRACK_INIT, 180, 180, mc)
+    orc.map_update_endpoints(want, dims, cell, kp, 0, 180, 180)
+    c.close(); mc.close()
+    rays(20)
+    m.clear(); want[:] = 0
+    rays(30)
+    start = _sparse_start(rng, dims, 0.2)
+    m.upload(start); want[:] = start
+    rays(40)
+    m.close()
