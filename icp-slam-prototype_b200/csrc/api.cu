@@ -373,6 +373,8 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
             ++launches;
         }
     }
+    // ICPB_GRID_COOP_CM: widest ball (cm) the warp-cooperative search handles itself (0 = the per-thread shell walk)
+    const float coop_r = 0.01f * (float)env_int("ICPB_GRID_COOP_CM", 40);
     const bool prof = ctx->profiling;
     if (prof) {
         while ((int)ctx->prof_events.size() < 2 * passes) {
@@ -385,7 +387,7 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         if (prof) CU(ctx, cudaEventRecord(ctx->prof_events[2 * pass], st));
         if (grid_mode) {
             const int sp = span_begin(ctx, ICPB_PROF_NN_GRID);
-            launch_nn_grid(d_descs, count, max_n, pass, ctx->sm_count, st);
+            launch_nn_grid(d_descs, count, max_n, pass, ctx->sm_count, st, coop_r);
             span_end(ctx, sp);
         } else launch_nn_partial(d_descs, d_states, count, max_n, qpt, splits, pass, filter, st);
         if (prof) CU(ctx, cudaEventRecord(ctx->prof_events[2 * pass + 1], st));
@@ -1134,8 +1136,13 @@ int icpb_map_create(icpb_ctx *ctx, const int dims[3], float cell, int z_lo, int 
     const long long nbx = (dims[0] + kBrick - 1) / kBrick;
     m->dev.nby = (dims[1] + kBrick - 1) / kBrick;
     m->dev.nbz = (m->dev.zs + kBrick - 1) / kBrick;
-    m->brick_words = (nbx * m->dev.nby * m->dev.nbz + 31) / 32;
+    const long long words1 = (nbx * m->dev.nby * m->dev.nbz + 31) / 32;
+    const long long nbx2 = (dims[0] + kBrick2 - 1) / kBrick2;
+    m->dev.nby2 = (dims[1] + kBrick2 - 1) / kBrick2;
+    m->dev.nbz2 = (m->dev.zs + kBrick2 - 1) / kBrick2;
+    m->brick_words = words1 + (nbx2 * m->dev.nby2 * m->dev.nbz2 + 31) / 32; // both levels in one allocation
     ce = cudaMalloc((void **)&m->dev.bricks, sizeof(uint32_t) * (size_t)m->brick_words);
+    m->dev.bricks2 = m->dev.bricks + words1;
     if (ce == cudaSuccess) ce = cudaMemsetAsync(m->dev.bricks, 0, sizeof(uint32_t) * (size_t)m->brick_words, ctx->stream);
     if (ce != cudaSuccess) {
         cudaFree(m->dev.grid);

@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(128) nn_grid_kernel(const RegDesc *__restrict_
 
 // Phase 2: one warp per heavy query, continuing from shell light_r+1 with the candidates of every run split
 // over the 32 lanes; the warp's lexicographic (distance, index) minimum is exchanged after every shell.
-__global__ void __launch_bounds__(128) nn_grid_heavy_kernel(const RegDesc *__restrict__ descs, int pass)
+__global__ void __launch_bounds__(128) nn_grid_heavy_kernel(const RegDesc *__restrict__ descs, int pass, int first_shell)
 {
     const RegDesc d = descs[blockIdx.z];
     IcpState *st = d.st;
@@ -481,7 +481,9 @@ __global__ void __launch_bounds__(128) nn_grid_heavy_kernel(const RegDesc *__res
             const float dd = best.d;
             best.thr = (dd == CUDART_INF_F) ? CUDART_INF_F : (dd * dd) * (kBandRel + 4.8e-7f) + kBandAbs;
         }
-        for (int r = g.light_r + 1; r <= g.max_r; ++r) {
+        // first_shell < 0: continue after the per-thread shells; 0: a query handed over by the cooperative kernel, whose
+        // partial best (a real candidate, or none) says nothing about which shells were covered
+        for (int r = first_shell < 0 ? g.light_r + 1 : first_shell; r <= g.max_r; ++r) {
             visit_shell<32>(g, d.gsorted, d.gstart, p, c0x, c0y, c0z, r, lane, best);
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) {
@@ -501,12 +503,286 @@ __global__ void __launch_bounds__(128) nn_grid_heavy_kernel(const RegDesc *__res
     }
 }
 
-void launch_nn_grid(const RegDesc *descs, int batch, int max_n, int pass, int sm_count, cudaStream_t s)
+// ---- warp-cooperative search -------------------------------------------------------------------------------------
+// The per-thread walk above spends its time on private, divergent 16-byte candidate loads (13.9 of 32 lanes active,
+// long_scoreboard the top stall, profiles/r01_ncu_nn_grid_fullres_v2.txt).  Here the 32 Morton-neighbour queries of a
+// warp search TOGETHER, the way the brute-force scan of nn.cu does, but over a few hundred candidates instead of all M:
+//
+//   1. every query owns a search ball that is known to hold its nearest neighbour: radius = the reference-arithmetic
+//      distance to the neighbour the PREVIOUS pass found (a rigid motion of a few millimetres later that target is
+//      still close: temporal coherence of the ICP loop, icp.cpp:155-258); on the first pass a guess of one cell edge
+//      that is corrected by a second round;
+//   2. lane r takes row r (fixed y, z; a contiguous run of cells along x) of the box of cells around the warp's balls
+//      and intersects it with all 32 balls: the union of the needed x-ranges is ONE contiguous run of sorted targets;
+//   3. the runs are copied -- coalesced, once per warp -- into a warp-private shared-memory batch, centred on the
+//      warp's centre (x', y', z', |t'|^2 in SoA);
+//   4. every lane evaluates every staged candidate with the centred expansion filter of nn_partial_warp_kernel
+//      (3 packed FFMA per pair from four broadcast LDS.128 per four candidates); only a candidate whose filter value is
+//      within the proven error band of the lane's best EXACT squared distance is evaluated in the reference's
+//      arithmetic (icp.cpp:606-620) -- a handful per query;
+//   5. a lane is finished when its best distance is inside the ball it searched: every target at that distance or
+//      closer was staged, so the lexicographic (distance, index) minimum over the staged set is the brute-force
+//      scan's answer.  Otherwise its ball becomes its best distance and the warp goes round again.
+//
+// Lanes whose ball is wider than coop_r (no overlap with the target: the rim of the frame) are handed to the
+// warp-per-query kernel with their partial best, like the open queries of the per-thread kernel.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 gpack2(float lo, float hi)
 {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void gunpack2(u64 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 gfma2(u64 a, u64 b, u64 c)
+{
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ float gmin3(float a, float b, float c)
+{
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+#ifndef ICPB_COOP_CAP
+#define ICPB_COOP_CAP 512
+#endif
+constexpr int kCoopCap = ICPB_COOP_CAP;   // candidates per warp batch (20 B each in shared memory)
+constexpr int kCoopWarps = 4;
+
+struct CoopBuf {
+    float xs[kCoopCap], ys[kCoopCap], zs[kCoopCap], ns[kCoopCap]; // centred candidates, SoA
+    int gp[kCoopCap];                                              // their slot in the sorted target array
+};
+
+// all lanes: filter every staged candidate of the batch [0, fill) (fill padded to a multiple of 4 by the caller)
+__device__ __forceinline__ void coop_evaluate(const CoopBuf &b, int fill, const float4 *__restrict__ sorted, const float4 &p,
+                                              float qx, float qy, float qz, float A, Best &best, float &thrW)
+{
+    const u64 q2x = gpack2(qx, qx), q2y = gpack2(qy, qy), q2z = gpack2(qz, qz);
+    const float4 *X4 = reinterpret_cast<const float4 *>(b.xs);
+    const float4 *Y4 = reinterpret_cast<const float4 *>(b.ys);
+    const float4 *Z4 = reinterpret_cast<const float4 *>(b.zs);
+    const float4 *N4 = reinterpret_cast<const float4 *>(b.ns);
+#pragma unroll 2
+    for (int j = 0; j < fill / 4; ++j) {
+        const float4 X = X4[j], Y = Y4[j], Z = Z4[j], N = N4[j];
+        u64 sa = gfma2(q2x, gpack2(X.x, X.y), gpack2(N.x, N.y)), sb = gfma2(q2x, gpack2(X.z, X.w), gpack2(N.z, N.w));
+        sa = gfma2(q2y, gpack2(Y.x, Y.y), sa); sb = gfma2(q2y, gpack2(Y.z, Y.w), sb);
+        sa = gfma2(q2z, gpack2(Z.x, Z.y), sa); sb = gfma2(q2z, gpack2(Z.z, Z.w), sb);
+        float w0, w1, w2, w3;
+        gunpack2(sa, w0, w1);
+        gunpack2(sb, w2, w3);
+        const float m = fminf(gmin3(w0, w1, w2), w3);
+        if (m <= thrW) { // rare: some candidate of the four may be as close as the best
+            const float w[4] = {w0, w1, w2, w3};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (w[k] <= thrW) {
+                    const float4 t = __ldg(&sorted[b.gp[4 * j + k]]);
+                    float xyz;
+                    const float dd = exact_distance_xyz(p.x, p.y, p.z, t.x, t.y, t.z, xyz);
+                    const int oi = __float_as_int(t.w);
+                    if (dd < best.d || (dd == best.d && oi < best.i)) {
+                        best.d = dd; best.i = oi;
+                        // W = |a - t|^2 - A up to the filter error; everything above this is strictly farther (see nn.cu)
+                        thrW = (xyz - A) + ((A * kBandCentredA + xyz * kBandCentredX) + kBandAbs);
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32 * kCoopWarps) nn_grid_coop_kernel(const RegDesc *__restrict__ descs, int pass, float coop_r)
+{
+    const RegDesc d = descs[blockIdx.z];
+    IcpState *st = d.st;
+    if (st->done) return;
+    __shared__ __align__(16) CoopBuf s_buf[kCoopWarps];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    CoopBuf &buf = s_buf[wid];
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k - lane >= d.n) return; // whole warp past the end
+    const bool valid = k < d.n;
+    const int i = valid ? (d.perm ? d.perm[k] : k) : 0;
+    const GridMeta g = *d.grid;
+
+    // P2 fused into the query load (pointcloud.cpp:321-359), as in nn_grid_kernel
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+        p = d.D[pass & 1][i];
+        if (st->apply) {
+            const float *R = st->Rf, *T = st->tf;
+            const float x = ((R[0] * p.x + R[1] * p.y) + R[2] * p.z) + T[0];
+            const float y = ((R[3] * p.x + R[4] * p.y) + R[5] * p.z) + T[1];
+            const float z = ((R[6] * p.x + R[7] * p.y) + R[8] * p.z) + T[2];
+            p.x = x; p.y = y; p.z = z;
+        }
+        d.D[(pass + 1) & 1][i] = p;
+    }
+
+    // ---- the lane's ball: seeded by the previous pass's neighbour, else one cell edge
+    Best best = {CUDART_INF_F, CUDART_INF_F, 0x7fffffff};
+    float seed_xyz = CUDART_INF_F;
+    bool done = !valid || beyond_reach(g, p);
+    float rad = g.h;
+    if (!done && pass > 0) {
+        const int j = d.idx[i];
+        if (j >= 0) {
+            const float4 t = d.tgt[j];
+            best.d = exact_distance_xyz(p.x, p.y, p.z, t.x, t.y, t.z, seed_xyz);
+            best.i = j;
+            rad = best.d;
+        }
+    }
+    const float max_reach = g.max_nn * 1.00002f + 1e-6f; // nothing beyond the acceptance radius is ever needed (icp.cpp:553)
+
+    // ---- warp centre of the centred filter
+    const unsigned full = 0xffffffffu;
+    float lox = valid ? p.x : CUDART_INF_F, hix = valid ? p.x : -CUDART_INF_F;
+    float loy = valid ? p.y : CUDART_INF_F, hiy = valid ? p.y : -CUDART_INF_F;
+    float loz = valid ? p.z : CUDART_INF_F, hiz = valid ? p.z : -CUDART_INF_F;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        lox = fminf(lox, __shfl_xor_sync(full, lox, off)); hix = fmaxf(hix, __shfl_xor_sync(full, hix, off));
+        loy = fminf(loy, __shfl_xor_sync(full, loy, off)); hiy = fmaxf(hiy, __shfl_xor_sync(full, hiy, off));
+        loz = fminf(loz, __shfl_xor_sync(full, loz, off)); hiz = fmaxf(hiz, __shfl_xor_sync(full, hiz, off));
+    }
+    const float cx = 0.5f * lox + 0.5f * hix, cy = 0.5f * loy + 0.5f * hiy, cz = 0.5f * loz + 0.5f * hiz;
+    const float ax = valid ? p.x - cx : 0.f, ay = valid ? p.y - cy : 0.f, az = valid ? p.z - cz : 0.f;
+    const float A = ((ax * ax + ay * ay) + az * az) * 1.000001f;
+    const float qx = -2.f * ax, qy = -2.f * ay, qz = -2.f * az; // W = |t'|^2 - 2 a'.t'
+    float thrW = CUDART_INF_F;
+    if (best.d < CUDART_INF_F) thrW = (seed_xyz - A) + ((A * kBandCentredA + seed_xyz * kBandCentredX) + kBandAbs);
+
+    const float inv_h = 1.0f / g.h;
+    const int nx = g.dim[0], ny = g.dim[1], nz = g.dim[2];
+    bool deferred = false;
+
+    for (int round = 0; round < 8; ++round) {
+        // lanes whose ball outgrew the cooperative phase go to the warp-per-query kernel with their partial best
+        float rr = fminf(rad, max_reach);
+        if (!done && rr > coop_r) { deferred = true; done = true; }
+        const unsigned active = __ballot_sync(full, !done);
+        if (active == 0u) break;
+        const float reach2 = rr * rr * 1.00001f + 1e-30f;
+        // box of cells around the active balls
+        const float ext = rr * 1.00001f + 2e-3f * g.h;
+        int bx0 = done ? 0x7fffffff : cell_axis(p.x - ext, g.mn[0], g.h, nx), bx1 = done ? -1 : cell_axis(p.x + ext, g.mn[0], g.h, nx);
+        int by0 = done ? 0x7fffffff : cell_axis(p.y - ext, g.mn[1], g.h, ny), by1 = done ? -1 : cell_axis(p.y + ext, g.mn[1], g.h, ny);
+        int bz0 = done ? 0x7fffffff : cell_axis(p.z - ext, g.mn[2], g.h, nz), bz1 = done ? -1 : cell_axis(p.z + ext, g.mn[2], g.h, nz);
+        bx0 = __reduce_min_sync(full, bx0); bx1 = __reduce_max_sync(full, bx1);
+        by0 = __reduce_min_sync(full, by0); by1 = __reduce_max_sync(full, by1);
+        bz0 = __reduce_min_sync(full, bz0); bz1 = __reduce_max_sync(full, bz1);
+        const int nyb = by1 - by0 + 1, nzb = bz1 - bz0 + 1;
+        const int nrows = nyb * nzb;
+        // a lane that is done must not pick anything up any more
+        const float thr_eval = done ? -CUDART_INF_F : thrW;
+        float thr_live = thr_eval;
+        int fill = 0;
+        for (int rbase = 0; rbase < nrows; rbase += 32) {
+            // ---- lane <-> row: union over the active balls of the cells this row must contribute
+            const int row = rbase + lane;
+            const bool rv = row < nrows;
+            const int yy = by0 + (rv ? row % nyb : 0), zz = bz0 + (rv ? row / nyb : 0);
+            const float ylo = g.mn[1] + yy * g.h, zlo = g.mn[2] + zz * g.h;
+            int amin = 0x7fffffff, bmax = -1;
+            for (unsigned rest = active; rest; rest &= rest - 1) {
+                const int j = __ffs(rest) - 1;
+                const float jx = __shfl_sync(full, p.x, j), jy = __shfl_sync(full, p.y, j), jz = __shfl_sync(full, p.z, j);
+                const float jr2 = __shfl_sync(full, reach2, j);
+                const float gy = fmaxf(axis_gap(jy, ylo, g.h), 0.f), gz = fmaxf(axis_gap(jz, zlo, g.h), 0.f);
+                const float gyz2 = gy * gy + gz * gz;
+                if (gyz2 <= jr2) {
+                    const float rx = sqrt_approx(jr2 - gyz2) * 1.0001f + 2e-3f * g.h;
+                    const int a = (int)floorf((jx - rx - g.mn[0]) * inv_h), b = (int)floorf((jx + rx - g.mn[0]) * inv_h);
+                    amin = min(amin, a); bmax = max(bmax, b);
+                }
+            }
+            amin = max(amin, 0); bmax = min(bmax, nx - 1);
+            int t0 = 0, len = 0;
+            if (rv && amin <= bmax) {
+                const int rowbase = (zz * ny + yy) * nx;
+                t0 = __ldg(&d.gstart[rowbase + amin]);
+                len = __ldg(&d.gstart[rowbase + bmax + 1]) - t0;
+            }
+            // ---- copy the runs into the batch, centred; a full batch is evaluated at once
+            for (unsigned rows = __ballot_sync(full, len > 0); rows; rows &= rows - 1) {
+                const int r = __ffs(rows) - 1;
+                int pos = __shfl_sync(full, t0, r), remaining = __shfl_sync(full, len, r);
+                while (remaining > 0) {
+                    const int take = min(remaining, kCoopCap - fill);
+                    for (int e = lane; e < take; e += 32) {
+                        const float4 t = __ldg(&d.gsorted[pos + e]);
+                        const float tx = t.x - cx, ty = t.y - cy, tz = t.z - cz;
+                        buf.xs[fill + e] = tx; buf.ys[fill + e] = ty; buf.zs[fill + e] = tz;
+                        buf.ns[fill + e] = __fmaf_rn(tz, tz, __fmaf_rn(ty, ty, tx * tx));
+                        buf.gp[fill + e] = pos + e;
+                    }
+                    fill += take; pos += take; remaining -= take;
+                    if (fill == kCoopCap) {
+                        __syncwarp();
+                        coop_evaluate(buf, fill, d.gsorted, p, qx, qy, qz, A, best, thr_live);
+                        __syncwarp();
+                        fill = 0;
+                    }
+                }
+            }
+        }
+        if (fill > 0) {
+            // pad to a multiple of four with candidates that can never pass the filter
+            if (lane < 4 && (fill & 3) != 0 && fill + lane < ((fill + 3) & ~3)) {
+                buf.xs[fill + lane] = 0.f; buf.ys[fill + lane] = 0.f; buf.zs[fill + lane] = 0.f;
+                buf.ns[fill + lane] = CUDART_INF_F; buf.gp[fill + lane] = 0;
+            }
+            __syncwarp();
+            coop_evaluate(buf, (fill + 3) & ~3, d.gsorted, p, qx, qy, qz, A, best, thr_live);
+            __syncwarp();
+        }
+        if (!done) {
+            thrW = thr_live;
+            // finished: the best lies inside the searched ball (or the whole acceptance ball was searched)
+            if (best.d <= rr || rr >= max_reach) done = true;
+            else rad = (best.d < CUDART_INF_F) ? best.d : 4.f * rad;
+        }
+    }
+    if (!valid) return;
+    if (!done) deferred = true; // round limit (not reachable with radii that quadruple up to the acceptance radius)
+    if (deferred) {
+        const int slot = atomicAdd(&d.gheavy_count[pass], 1);
+        d.gheavy[slot] = i;
+    } else if (!(best.d < g.max_nn)) {
+        best.i = -1; best.d = CUDART_INF_F;
+    }
+    d.idx[i] = best.i;
+    d.dist[i] = best.d;
+}
+
+void launch_nn_grid(const RegDesc *descs, int batch, int max_n, int pass, int sm_count, cudaStream_t s, float coop_r)
+{
+    dim3 hgrid(sm_count * 8, 1, batch);
+    if (coop_r > 0.f) { // warp-cooperative search (default), open queries finished from shell 0
+        dim3 grid((max_n + 32 * kCoopWarps - 1) / (32 * kCoopWarps), 1, batch);
+        nn_grid_coop_kernel<<<grid, 32 * kCoopWarps, 0, s>>>(descs, pass, coop_r);
+        nn_grid_heavy_kernel<<<hgrid, 128, 0, s>>>(descs, pass, 0);
+        return;
+    }
     dim3 grid((max_n + 127) / 128, 1, batch);
     nn_grid_kernel<<<grid, 128, 0, s>>>(descs, pass);
-    dim3 hgrid(sm_count * 8, 1, batch);
-    nn_grid_heavy_kernel<<<hgrid, 128, 0, s>>>(descs, pass);
+    nn_grid_heavy_kernel<<<hgrid, 128, 0, s>>>(descs, pass, -1);
 }
 
 } // namespace icpb

@@ -141,7 +141,8 @@ void launch_fp32_peak(float *out, int blocks, int threads, int iters, cudaStream
 void launch_grid_bbox(const float4 *tgt, int m, unsigned int *bbox, cudaStream_t s);
 void launch_grid_build(const float4 *tgt, int m, const GridMeta &g, int *counts, int *cursor, int *block_sums,
                        float4 *sorted, cudaStream_t s);
-void launch_nn_grid(const RegDesc *descs, int batch, int max_n, int pass, int sm_count, cudaStream_t s);
+// coop_r > 0: warp-cooperative search for balls up to coop_r metres (grid.cu); 0: the per-thread shell walk
+void launch_nn_grid(const RegDesc *descs, int batch, int max_n, int pass, int sm_count, cudaStream_t s, float coop_r);
 int spatial_sort_bits(int max_n);
 int spatial_sort_cells(int bits);
 int spatial_sort_sum_slots(int bits);
@@ -176,8 +177,12 @@ void launch_depth_filter(const uint16_t *in, uint16_t *tmp_a, uint16_t *tmp_b, u
 // of the brick is written non-zero and only cleared by icpb_map_clear / rebuilt by icpb_map_upload.  A clear bit proves
 // that every voxel of the brick is zero, so the ray walk (whose decrement of a zero voxel is a no-op, map.cpp:423) may
 // cross the brick without reading it.  600x600x500 at 1 cm: 75x75x63 bits = 44 KB, L1-resident.
+// A second, coarser level (kBrick2^3 voxels, 722 bytes for the same grid) lets the walk cross the empty interior of a room
+// in a dozen jumps.
 constexpr int kBrickLog = 3;
 constexpr int kBrick = 1 << kBrickLog;
+constexpr int kBrick2Log = 5;
+constexpr int kBrick2 = 1 << kBrick2Log;
 
 struct MapDev {
     uint8_t *grid;    // slab storage: [(x*dimY + y)*zs + (z - z_lo)], zs = z_hi - z_lo; the allocation is padded to 4 bytes
@@ -186,6 +191,8 @@ struct MapDev {
     float cell;
     uint32_t *bricks; // occupancy bits, index (bx*nby + by)*nbz + bz
     int nby, nbz;     // bricks along y and along the slab's z
+    uint32_t *bricks2; // the coarse level, same layout with nby2 / nbz2 (stored behind the fine level)
+    int nby2, nbz2;
 };
 void launch_map_rebuild_bricks(const MapDev &m, long long brick_words, cudaStream_t s);
 void launch_map_endpoints(const MapDev &m, const float4 *pts, int n, int rule, int delta, int max_conf,

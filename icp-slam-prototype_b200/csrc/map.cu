@@ -54,13 +54,24 @@ __device__ __forceinline__ unsigned brick_bit(const MapDev &m, int x, int y, int
     return (unsigned)(((x >> kBrickLog) * m.nby + (y >> kBrickLog)) * m.nbz + (zr >> kBrickLog));
 }
 
+__device__ __forceinline__ unsigned brick2_bit(const MapDev &m, int x, int y, int zr)
+{
+    return (unsigned)(((x >> kBrick2Log) * m.nby2 + (y >> kBrick2Log)) * m.nbz2 + (zr >> kBrick2Log));
+}
+
 // a voxel of the brick became (or stays) non-zero; the read keeps the common case free of atomics
 __device__ __forceinline__ void brick_mark(const MapDev &m, int x, int y, int zr)
 {
     const unsigned b = brick_bit(m, x, y, zr);
     uint32_t *w = m.bricks + (b >> 5);
     const uint32_t mask = 1u << (b & 31);
-    if (!(*reinterpret_cast<volatile uint32_t *>(w) & mask)) atomicOr(w, mask);
+    if (!(*reinterpret_cast<volatile uint32_t *>(w) & mask)) {
+        atomicOr(w, mask);
+        const unsigned b2 = brick2_bit(m, x, y, zr);
+        uint32_t *w2 = m.bricks2 + (b2 >> 5);
+        const uint32_t mask2 = 1u << (b2 & 31);
+        if (!(*reinterpret_cast<volatile uint32_t *>(w2) & mask2)) atomicOr(w2, mask2);
+    }
 }
 
 // icpb_map_upload: recompute every bit from the grid.  One thread per brick column segment would be unbalanced for
@@ -77,7 +88,11 @@ __global__ void map_rebuild_bricks_kernel(MapDev m, int nbx)
             const uint8_t *row = m.grid + ((long long)x * m.dims[1] + y) * m.zs;
             for (int z = bz * kBrick; z < min((bz + 1) * kBrick, m.zs); ++z) any |= row[z] != 0;
         }
-    if (any) atomicOr(m.bricks + (b >> 5), 1u << (b & 31));
+    if (any) {
+        atomicOr(m.bricks + (b >> 5), 1u << (b & 31));
+        const unsigned b2 = brick2_bit(m, bx * kBrick, by * kBrick, bz * kBrick);
+        atomicOr(m.bricks2 + (b2 >> 5), 1u << (b2 & 31));
+    }
 }
 
 void launch_map_rebuild_bricks(const MapDev &m, long long brick_words, cudaStream_t s)
@@ -406,17 +421,32 @@ __global__ void __launch_bounds__(128) map_rays_kernel(MapDev m, const float4 *_
 template <typename I>
 struct RayBrick {
     I ex, ey, ez, dxs, dys, dzs;
+    float rdx, rdy, rdz; // 1 / dxs ... : quotient estimates of the jump
     int x, y, zr;     // current voxel, z relative to the slab
     int rx, ry, rz;   // walls still to cross per axis
     int sgn;          // step signs + 1, two bits per axis
     int rem;          // visits still to make
-    bool empty;       // occupancy bit of the current voxel's brick is clear
+    bool empty;       // the current voxel's brick (8^3) holds only zeros
+    bool empty2;      // so does its coarse brick (32^3)
 };
 
 __device__ __forceinline__ bool brick_is_empty(const MapDev &m, int x, int y, int zr)
 {
     const unsigned b = brick_bit(m, x, y, zr);
     return ((__ldg(m.bricks + (b >> 5)) >> (b & 31)) & 1u) == 0u;
+}
+
+__device__ __forceinline__ bool brick2_is_empty(const MapDev &m, int x, int y, int zr)
+{
+    const unsigned b = brick2_bit(m, x, y, zr);
+    return ((__ldg(m.bricks2 + (b >> 5)) >> (b & 31)) & 1u) == 0u;
+}
+
+template <typename I>
+__device__ __forceinline__ void ray_lookup(const MapDev &m, RayBrick<I> &r, bool coarse_too)
+{
+    if (coarse_too) r.empty2 = brick2_is_empty(m, r.x, r.y, r.zr);
+    r.empty = r.empty2 || brick_is_empty(m, r.x, r.y, r.zr); // a clear coarse bit covers all its fine bricks
 }
 
 template <typename I>
@@ -432,6 +462,7 @@ __device__ __forceinline__ void ray_setup_brick(const MapDev &m, const float4 p,
     const I P3 = 3 * mx * my * mz;
     r.ex = nx ? my * mz : P3; r.ey = ny ? mx * mz : P3; r.ez = nz ? mx * my : P3;
     r.dxs = 2 * my * mz; r.dys = 2 * mx * mz; r.dzs = 2 * mx * my;
+    r.rdx = 1.0f / (float)r.dxs; r.rdy = 1.0f / (float)r.dys; r.rdz = 1.0f / (float)r.dzs;
     const int steps = nx + ny + nz;
     visits += steps > 0 ? (unsigned long long)(steps - 1) : 0ull;
     int cx = 0, cy = 0, cz = 0;
@@ -457,9 +488,9 @@ __device__ __forceinline__ void ray_setup_brick(const MapDev &m, const float4 p,
     r.sgn = (sx + 1) | ((sy + 1) << 2) | ((sz + 1) << 4);
     const int done_steps = cx + cy + cz;
     r.rem = live ? max(steps - 1 - done_steps, 0) : 0;
-    r.empty = false;
+    r.empty = r.empty2 = false;
     if (live) {
-        r.empty = brick_is_empty(m, r.x, r.y, r.zr);
+        ray_lookup<I>(m, r, true);
         // the voxel just entered by the jump is itself a visit unless it is the endpoint
         if (entered_now && done_steps <= steps - 1 && !r.empty) {
             const long long lin0 = ((long long)r.x * m.dims[1] + r.y) * m.zs + r.zr;
@@ -469,24 +500,31 @@ __device__ __forceinline__ void ray_setup_brick(const MapDev &m, const float4 p,
     }
 }
 
-// walls j in [0, r) of an axis with e + j d before time T: "<= T" when the axis goes first on ties, "< T" otherwise
+// walls j in [0, r) of an axis with e + j d before time T: "<= T" when the axis goes first on ties, "< T" otherwise.
+// floor(lim / d) from a float estimate settled by the exact remainder: the quotient is below the axis' wall count
+// (<= a grid dimension), far inside the range where the estimate is within one of it.
 template <typename I>
-__device__ __forceinline__ int walls_before(I e, I d, int r, I T, bool first_on_ties)
+__device__ __forceinline__ int walls_before(I e, I d, float rcp_d, int r, I T, bool first_on_ties)
 {
     const I lim = T - e - (first_on_ties ? (I)0 : (I)1);
-    const int c = lim < 0 ? 0 : (int)(lim / d) + 1;
-    return min(c, r);
+    if (lim < 0) return 0;
+    int c = (int)((float)lim * rcp_d);
+    const I rmd = lim - (I)c * d;
+    c += (rmd >= d) - (rmd < 0);
+    return min(c + 1, r);
 }
 
-template <typename I>
+// LOG = log2 of the brick edge: kBrickLog for the fine level, kBrick2Log for the coarse one
+template <typename I, int LOG>
 __device__ __forceinline__ void ray_jump(const MapDev &m, RayBrick<I> &r)
 {
+    constexpr int B = 1 << LOG;
     const int sx = (r.sgn & 3) - 1, sy = ((r.sgn >> 2) & 3) - 1, sz = ((r.sgn >> 4) & 3) - 1;
-    const int lx = r.x & (kBrick - 1), ly = r.y & (kBrick - 1), lz = r.zr & (kBrick - 1);
+    const int lx = r.x & (B - 1), ly = r.y & (B - 1), lz = r.zr & (B - 1);
     // steps along each axis that leave the brick (the slab's upper face also ends the z-run)
-    const int kx = sx > 0 ? kBrick - lx : lx + 1;
-    const int ky = sy > 0 ? kBrick - ly : ly + 1;
-    const int kz = sz > 0 ? min(kBrick - lz, m.zs - r.zr) : lz + 1;
+    const int kx = sx > 0 ? B - lx : lx + 1;
+    const int ky = sy > 0 ? B - ly : ly + 1;
+    const int kz = sz > 0 ? min(B - lz, m.zs - r.zr) : lz + 1;
     const bool vx = kx <= r.rx, vy = ky <= r.ry, vz = kz <= r.rz; // r_a = 0 for an axis that does not move
     const I big = sizeof(I) == 4 ? (I)0x7fffffff : (I)0x7fffffffffffffffLL;
     const I Tx = vx ? r.ex + (I)(kx - 1) * r.dxs : big;
@@ -497,9 +535,9 @@ __device__ __forceinline__ void ray_jump(const MapDev &m, RayBrick<I> &r)
     const bool by = !bx && (Ty <= Tz);
     const I T = bx ? Tx : (by ? Ty : Tz);
     // walls crossed inside the brick: all but the last of the exit axis, and whatever the others cross before T
-    const int cx = bx ? kx - 1 : walls_before<I>(r.ex, r.dxs, r.rx, T, true);
-    const int cy = by ? ky - 1 : walls_before<I>(r.ey, r.dys, r.ry, T, !bx);
-    const int cz = (!bx && !by) ? kz - 1 : walls_before<I>(r.ez, r.dzs, r.rz, T, false);
+    const int cx = bx ? kx - 1 : walls_before<I>(r.ex, r.dxs, r.rdx, r.rx, T, true);
+    const int cy = by ? ky - 1 : walls_before<I>(r.ey, r.dys, r.rdy, r.ry, T, !bx);
+    const int cz = (!bx && !by) ? kz - 1 : walls_before<I>(r.ez, r.dzs, r.rdz, r.rz, T, false);
     const int skip = cx + cy + cz;
     if (skip >= r.rem) { r.rem = 0; return; } // every remaining visit lies in the empty brick
     r.rem -= skip;
@@ -518,10 +556,11 @@ __global__ void __launch_bounds__(128) map_rays_brick_kernel(MapDev m, const flo
     const unsigned lt = (1u << lane) - 1u;
     RayBrick<I> r;
     r.ex = r.ey = r.ez = r.dxs = r.dys = r.dzs = 0;
+    r.rdx = r.rdy = r.rdz = 0.f;
     r.x = r.y = r.zr = r.rx = r.ry = r.rz = 0;
     r.sgn = 0x15;
     r.rem = 0;
-    r.empty = false;
+    r.empty = r.empty2 = false;
     unsigned long long my_visits = 0;
     bool drained = false; // warp-uniform: the counter has passed n
     uint8_t *g = m.grid;
@@ -545,7 +584,10 @@ __global__ void __launch_bounds__(128) map_rays_brick_kernel(MapDev m, const flo
         }
 #pragma unroll 1
         for (int k = 0; k < kRayBurst / kRayGroup; ++k) {
-            if (r.rem > 0 && r.empty) ray_jump<I>(m, r);
+            if (r.rem > 0 && r.empty) {
+                if (r.empty2) ray_jump<I, kBrick2Log>(m, r);
+                else ray_jump<I, kBrickLog>(m, r);
+            }
             const int sx = (r.sgn & 3) - 1, sy = ((r.sgn >> 2) & 3) - 1, sz = ((r.sgn >> 4) & 3) - 1;
             long long at[kRayGroup];
             bool in[kRayGroup];
@@ -566,11 +608,11 @@ __global__ void __launch_bounds__(128) map_rays_brick_kernel(MapDev m, const flo
                     --r.rem;
                     if ((unsigned)r.zr >= zs) { r.rem = 0; halt = true; } // left the slab for good
                     else {
-                        // the coordinate that moved tells whether a brick boundary was crossed
+                        // the coordinate that moved tells whether a brick boundary (fine, coarse) was crossed
                         const int c = px ? r.x : (py ? r.y : r.zr);
                         const int s = px ? sx : (py ? sy : sz);
-                        const bool crossed = ((c & (kBrick - 1)) == (s > 0 ? 0 : kBrick - 1));
-                        if (crossed) r.empty = brick_is_empty(m, r.x, r.y, r.zr);
+                        if ((c & (kBrick - 1)) == (s > 0 ? 0 : kBrick - 1))
+                            ray_lookup<I>(m, r, (c & (kBrick2 - 1)) == (s > 0 ? 0 : kBrick2 - 1));
                         in[u] = !r.empty;
                         halt = r.empty;
                         at[u] = (long long)r.x * xstride + (long long)r.y * ystride + r.zr;

@@ -7,7 +7,10 @@ occupancy and random z-slabs.  Pure integers; run on the CPU before spending GPU
 import random
 import sys
 
-B = 8
+import numpy as np
+
+B = 8     # fine bricks (kBrick)
+B2 = 32   # coarse bricks (kBrick2)
 
 
 def plain_visits(o, e, z_lo, z_hi):
@@ -68,22 +71,38 @@ def brick_visits(o, e, z_lo, z_hi, occupied):
     out = []
     if not live:
         return out
-    empty = (x // B, y // B, zr // B) not in occupied
-    if entered and done <= steps - 1 and not empty:
-        out.append((x, y, zr + z_lo))
+    empty = empty2 = False
 
     def walls_before(e_, d_, r_, T, first):
+        # the kernel's float estimate of the quotient settled by the exact remainder
         lim = T - e_ - (0 if first else 1)
-        c = 0 if lim < 0 else lim // d_ + 1
-        return min(c, r_)
+        if lim < 0:
+            return 0
+        c = int(np.float32(lim) * (np.float32(1.0) / np.float32(d_)))
+        rmd = lim - c * d_
+        c += (1 if rmd >= d_ else 0) - (1 if rmd < 0 else 0)
+        assert c == lim // d_, (lim, d_, c)
+        return min(c + 1, r_)
 
+    occupied2 = {(i * B // B2, j * B // B2, k * B // B2) for (i, j, k) in occupied}
+
+    def lookup(coarse_too):
+        nonlocal empty, empty2
+        if coarse_too:
+            empty2 = (x // B2, y // B2, zr // B2) not in occupied2
+        empty = empty2 or (x // B, y // B, zr // B) not in occupied
+
+    lookup(True)
+    if entered and done <= steps - 1 and not empty:
+        out.append((x, y, zr + z_lo))
     BIG = 1 << 62
     while rem > 0:
         if empty:
-            lx, ly, lz = x % B, y % B, zr % B
-            kx = B - lx if sx > 0 else lx + 1
-            ky = B - ly if sy > 0 else ly + 1
-            kz = min(B - lz, zs - zr) if sz > 0 else lz + 1
+            BB = B2 if empty2 else B
+            lx, ly, lz = x % BB, y % BB, zr % BB
+            kx = BB - lx if sx > 0 else lx + 1
+            ky = BB - ly if sy > 0 else ly + 1
+            kz = min(BB - lz, zs - zr) if sz > 0 else lz + 1
             vx, vy, vz = kx <= rx, ky <= ry, kz <= rz
             Tx = ex + (kx - 1) * dx if vx else BIG
             Ty = ey + (ky - 1) * dy if vy else BIG
@@ -118,7 +137,7 @@ def brick_visits(o, e, z_lo, z_hi, occupied):
             break
         c, s = (x, sx) if px else ((y, sy) if py else (zr, sz))
         if (c % B) == (0 if s > 0 else B - 1):
-            empty = (x // B, y // B, zr // B) not in occupied
+            lookup((c % B2) == (0 if s > 0 else B2 - 1))
         if not empty:
             out.append((x, y, zr + z_lo))
     return out
@@ -129,7 +148,7 @@ def main():
     rng = random.Random(1234)
     bad = 0
     for case in range(n_cases):
-        dims = (rng.randint(1, 40), rng.randint(1, 40), rng.randint(1, 40))
+        dims = (rng.randint(1, 100), rng.randint(1, 100), rng.randint(1, 100))
         z_lo = rng.randint(0, dims[2] - 1)
         z_hi = rng.randint(z_lo + 1, dims[2])
         if rng.random() < 0.5:
@@ -143,7 +162,7 @@ def main():
             dlt = rng.randint(-min(dims), min(dims))
             e = tuple(min(max(o[j] + dlt * rng.choice((-1, 1)), 0), dims[j] - 1) for j in range(3))
         nb = [(d + B - 1) // B for d in (dims[0], dims[1], z_hi - z_lo)]
-        p_occ = rng.choice((0.0, 0.1, 0.5, 1.0))
+        p_occ = rng.choice((0.0, 0.01, 0.1, 0.5, 1.0))
         occupied = {(i, j, k) for i in range(nb[0]) for j in range(nb[1]) for k in range(nb[2]) if rng.random() < p_occ}
         want = [v for v in plain_visits(o, e, z_lo, z_hi) if (v[0] // B, v[1] // B, (v[2] - z_lo) // B) in occupied]
         got = brick_visits(o, e, z_lo, z_hi, occupied)
