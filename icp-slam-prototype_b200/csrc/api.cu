@@ -18,7 +18,7 @@ thread_local std::string g_create_error;
 enum WsId {
     WS_DESCS = 0, WS_STATES, WS_PARAMS, WS_TGT_SOA, WS_PM1, WS_PM2, WS_PG, WS_IDX, WS_DIST, WS_CHUNKS, WS_ALT,
     WS_IDX_TRACE, WS_DIST_TRACE, WS_MISC, WS_DEPTH, WS_BGR, WS_KEEP, WS_TILESTATE, WS_IMG_A, WS_IMG_B, WS_NORMALS,
-    WS_RT, WS_GRID_META, WS_GRID_COUNTS, WS_GRID_CURSOR, WS_GRID_SUMS, WS_GRID_SORTED, WS_GRID_BBOX, WS_GRID_HEAVY, WS_BATCHSTATE, WS_TRACK, WS_PA, WS_PM3, WS_PG2, WS_MLOG, WS_REJ_FLAG, WS_REJ_PTS, WS_FRAME, WS_PERM, WS_SORT_COUNTS, WS_SORT_SUMS, WS_COUNT
+    WS_RT, WS_GRID_META, WS_GRID_COUNTS, WS_GRID_CURSOR, WS_GRID_SUMS, WS_GRID_SORTED, WS_GRID_BBOX, WS_GRID_HEAVY, WS_BATCHSTATE, WS_TRACK, WS_PA, WS_PM3, WS_PG2, WS_MLOG, WS_REJ_FLAG, WS_REJ_PTS, WS_FRAME, WS_PERM, WS_SORT_COUNTS, WS_SORT_SUMS, WS_GRID_NB, WS_GRID_SEED, WS_COUNT
 };
 
 int fail(icpb_ctx *ctx, int status, const char *what, cudaError_t ce = cudaSuccess)
@@ -229,6 +229,7 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
     int *d_gcounts = nullptr, *d_gcursor = nullptr, *d_gsums = nullptr;
     float4 *d_gsorted = nullptr;
     int *d_gheavy = nullptr;
+    float4 *d_gnb = nullptr, *d_gseed = nullptr;
     long long grid_launches = 0;
     if (grid_mode) {
         const int m = regs[0].target->n;
@@ -283,6 +284,8 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         if ((rc = ws_get(ctx, WS_GRID_SUMS, sizeof(int) * ((size_t)gm.ncells / 4096 + 8), (void **)&d_gsums))) return rc;
         if ((rc = ws_get(ctx, WS_GRID_SORTED, sizeof(float4) * (size_t)m, (void **)&d_gsorted))) return rc;
         if ((rc = ws_get(ctx, WS_GRID_HEAVY, sizeof(int) * ((size_t)regs[0].data->n + passes + 8), (void **)&d_gheavy))) return rc;
+        if ((rc = ws_get(ctx, WS_GRID_NB, sizeof(float4) * (size_t)regs[0].data->n, (void **)&d_gnb))) return rc;
+        if ((rc = ws_get(ctx, WS_GRID_SEED, sizeof(float4) * ((size_t)regs[0].data->n + 32), (void **)&d_gseed))) return rc;
         grid_launches = 7;
     }
 
@@ -322,6 +325,8 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         d.grid = d_gmeta;
         d.gsorted = d_gsorted;
         d.gstart = d_gcounts;
+        d.gnb = d_gnb;
+        d.gseed = d_gseed;
         d.gheavy = d_gheavy ? d_gheavy + passes + 8 : nullptr;
         d.gheavy_count = d_gheavy;
         d.carry = (kp_mode && regs[b].carry) ? regs[b].carry->d_pts : nullptr;
@@ -374,7 +379,7 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         }
     }
     // ICPB_GRID_COOP_CM: widest ball (cm) the warp-cooperative search handles itself (0 = the per-thread shell walk)
-    const float coop_r = 0.01f * (float)env_int("ICPB_GRID_COOP_CM", 40);
+    const float coop_r = 0.01f * (float)env_int("ICPB_GRID_COOP_CM", 1000);
     const bool prof = ctx->profiling;
     if (prof) {
         while ((int)ctx->prof_events.size() < 2 * passes) {
@@ -392,7 +397,7 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         } else launch_nn_partial(d_descs, d_states, count, max_n, qpt, splits, pass, filter, st);
         if (prof) CU(ctx, cudaEventRecord(ctx->prof_events[2 * pass + 1], st));
         const int spf = span_begin(ctx, ICPB_PROF_NN_FINALIZE);
-        launch_nn_finalize(d_descs, d_states, d_prm, count, max_n, grid_mode ? 0 : splits, pass, filter, st);
+        launch_nn_finalize(d_descs, d_states, d_prm, count, max_n, grid_mode ? (coop_r > 0.f ? -1 : 0) : splits, pass, filter, st);
         span_end(ctx, spf);
         launches += grid_mode ? 3 : 2;
     }
@@ -1068,6 +1073,17 @@ int icpb_icp_register(icpb_ctx *ctx, icpb_cloud *data, const icpb_cloud *target,
     if (!ctx || !data || !target || !params) return ICPB_ERR_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));
     RegHost r{data, target};
+    return run_registrations(ctx, &r, 1, params, result, true);
+}
+
+int icpb_icp_register_carry(icpb_ctx *ctx, icpb_cloud *data, const icpb_cloud *target, icpb_cloud *carry,
+                            const icpb_icp_params *params, icpb_icp_result *result)
+{
+    if (!ctx || !data || !target || !params) return ICPB_ERR_INVALID;
+    if (carry && carry->ctx != ctx) return fail(ctx, ICPB_ERR_INVALID, "cloud belongs to another context");
+    CU(ctx, cudaSetDevice(ctx->device));
+    RegHost r{data, target};
+    r.carry = (carry && carry->n > 0) ? carry : nullptr;
     return run_registrations(ctx, &r, 1, params, result, true);
 }
 

@@ -499,6 +499,11 @@ __global__ void __launch_bounds__(128) nn_grid_heavy_kernel(const RegDesc *__res
             if (!(best.d < g.max_nn)) { best.i = -1; best.d = CUDART_INF_F; }
             d.idx[i] = best.i;
             d.dist[i] = best.d;
+            if (first_shell >= 0) { // cooperative mode: nn_finalize reads the neighbour's coordinates from gnb
+                float4 rec = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+                if (best.i >= 0) { const float4 t = d.tgt[best.i]; rec = make_float4(t.x, t.y, t.z, __int_as_float(best.i)); }
+                d.gnb[i] = rec;
+            }
         }
     }
 }
@@ -567,16 +572,18 @@ struct CoopBuf {
     int gp[kCoopCap];                                              // their slot in the sorted target array
 };
 
-// all lanes: filter every staged candidate of the batch [0, fill) (fill padded to a multiple of 4 by the caller)
-__device__ __forceinline__ void coop_evaluate(const CoopBuf &b, int fill, const float4 *__restrict__ sorted, const float4 &p,
-                                              float qx, float qy, float qz, float A, Best &best, float &thrW)
+// Phase A, all lanes: the centred filter value of every staged candidate of the batch [0, fill) (fill a multiple of 4),
+// reduced to the best and second-best minimum over GROUPS of four consecutive slots and the best group's number.
+// No branches: a lane's running minimum improves at a different slot than its neighbours', and any per-improvement
+// work would be executed by one lane at a time (the first version of this kernel spent 60 % of its instructions so).
+__device__ __forceinline__ void coop_scan(const CoopBuf &b, int fill, float qx, float qy, float qz, float &m1, float &m2, int &g1)
 {
     const u64 q2x = gpack2(qx, qx), q2y = gpack2(qy, qy), q2z = gpack2(qz, qz);
     const float4 *X4 = reinterpret_cast<const float4 *>(b.xs);
     const float4 *Y4 = reinterpret_cast<const float4 *>(b.ys);
     const float4 *Z4 = reinterpret_cast<const float4 *>(b.zs);
     const float4 *N4 = reinterpret_cast<const float4 *>(b.ns);
-#pragma unroll 2
+#pragma unroll 4
     for (int j = 0; j < fill / 4; ++j) {
         const float4 X = X4[j], Y = Y4[j], Z = Z4[j], N = N4[j];
         u64 sa = gfma2(q2x, gpack2(X.x, X.y), gpack2(N.x, N.y)), sb = gfma2(q2x, gpack2(X.z, X.w), gpack2(N.z, N.w));
@@ -586,39 +593,91 @@ __device__ __forceinline__ void coop_evaluate(const CoopBuf &b, int fill, const 
         gunpack2(sa, w0, w1);
         gunpack2(sb, w2, w3);
         const float m = fminf(gmin3(w0, w1, w2), w3);
-        if (m <= thrW) { // rare: some candidate of the four may be as close as the best
-            const float w[4] = {w0, w1, w2, w3};
+        const bool lt = m < m1;
+        m2 = lt ? m1 : fminf(m2, m);
+        g1 = lt ? j : g1;
+        m1 = fminf(m1, m);
+    }
+}
+
+struct BestB {
+    float x, y, z; // coordinates of the best target so far
+};
+
+__device__ __forceinline__ void coop_take(const float4 &p, const float4 &t, Best &best, BestB &bb)
+{
+    float xyz;
+    const float dd = exact_distance_xyz(p.x, p.y, p.z, t.x, t.y, t.z, xyz);
+    const int oi = __float_as_int(t.w);
+    if (dd < best.d || (dd == best.d && oi < best.i)) {
+        best.d = dd; best.i = oi;
+        bb.x = t.x; bb.y = t.y; bb.z = t.z;
+    }
+}
+
+// Fallback for lanes whose second-best group is within the error band of the best (near-ties across groups): every
+// candidate of the batch whose filter value is within the band is evaluated in the reference's arithmetic.
+__device__ __forceinline__ void coop_rescan(const CoopBuf &b, int fill, const float4 *__restrict__ sorted, const float4 &p,
+                                            float qx, float qy, float qz, float lim, Best &best, BestB &bb)
+{
+    const u64 q2x = gpack2(qx, qx), q2y = gpack2(qy, qy), q2z = gpack2(qz, qz);
+    const float4 *X4 = reinterpret_cast<const float4 *>(b.xs);
+    const float4 *Y4 = reinterpret_cast<const float4 *>(b.ys);
+    const float4 *Z4 = reinterpret_cast<const float4 *>(b.zs);
+    const float4 *N4 = reinterpret_cast<const float4 *>(b.ns);
+    for (int j = 0; j < fill / 4; ++j) {
+        const float4 X = X4[j], Y = Y4[j], Z = Z4[j], N = N4[j];
+        u64 sa = gfma2(q2x, gpack2(X.x, X.y), gpack2(N.x, N.y)), sb = gfma2(q2x, gpack2(X.z, X.w), gpack2(N.z, N.w));
+        sa = gfma2(q2y, gpack2(Y.x, Y.y), sa); sb = gfma2(q2y, gpack2(Y.z, Y.w), sb);
+        sa = gfma2(q2z, gpack2(Z.x, Z.y), sa); sb = gfma2(q2z, gpack2(Z.z, Z.w), sb);
+        float w[4];
+        gunpack2(sa, w[0], w[1]);
+        gunpack2(sb, w[2], w[3]);
+        if (fminf(gmin3(w[0], w[1], w[2]), w[3]) <= lim) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (w[k] <= thrW) {
-                    const float4 t = __ldg(&sorted[b.gp[4 * j + k]]);
-                    float xyz;
-                    const float dd = exact_distance_xyz(p.x, p.y, p.z, t.x, t.y, t.z, xyz);
-                    const int oi = __float_as_int(t.w);
-                    if (dd < best.d || (dd == best.d && oi < best.i)) {
-                        best.d = dd; best.i = oi;
-                        // W = |a - t|^2 - A up to the filter error; everything above this is strictly farther (see nn.cu)
-                        thrW = (xyz - A) + ((A * kBandCentredA + xyz * kBandCentredX) + kBandAbs);
-                    }
-                }
-            }
+            for (int k = 0; k < 4; ++k)
+                if (w[k] <= lim) coop_take(p, __ldg(&sorted[b.gp[4 * j + k]]), best, bb);
         }
     }
 }
 
+// One batch: phase A for all lanes, then the exact stage.  A lane whose second-best group minimum exceeds the best by
+// more than the filter's error band (the bound of nn_partial_centred_kernel, as applied by nn_finalize) needs only the
+// four candidates of its best group: everything outside is strictly farther, in the reference's arithmetic, than the
+// candidate that produced the minimum.  Other lanes take the fallback.
+__device__ __forceinline__ void coop_batch(const CoopBuf &b, int fill, const float4 *__restrict__ sorted, const float4 &p,
+                                           float qx, float qy, float qz, float A, bool live, Best &best, BestB &bb)
+{
+    float m1 = CUDART_INF_F, m2 = CUDART_INF_F;
+    int g1 = 0;
+    coop_scan(b, fill, qx, qy, qz, m1, m2, g1);
+    const bool have = live && m1 < CUDART_INF_F;
+    const float lim = m1 + ((A * kBandCentredA + fmaxf(m1 + A, 0.f) * kBandCentredX) + kBandAbs);
+    if (have) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) coop_take(p, __ldg(&sorted[b.gp[4 * g1 + k]]), best, bb);
+    }
+    const bool amb = have && !(m2 > lim);
+    if (__any_sync(0xffffffffu, amb)) coop_rescan(b, fill, sorted, p, qx, qy, qz, amb ? lim : -CUDART_INF_F, best, bb);
+}
+
 __global__ void __launch_bounds__(32 * kCoopWarps) nn_grid_coop_kernel(const RegDesc *__restrict__ descs, int pass, float coop_r)
 {
-    const RegDesc d = descs[blockIdx.z];
+    const RegDesc &d = descs[blockIdx.z];
     IcpState *st = d.st;
     if (st->done) return;
     __shared__ __align__(16) CoopBuf s_buf[kCoopWarps];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     CoopBuf &buf = s_buf[wid];
+    const int n = d.n;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k - lane >= d.n) return; // whole warp past the end
-    const bool valid = k < d.n;
-    const int i = valid ? (d.perm ? d.perm[k] : k) : 0;
+    if (k - lane >= n) return; // whole warp past the end
+    const bool valid = k < n;
+    const int *perm = d.perm;
+    const int i = valid ? (perm ? perm[k] : k) : 0;
     const GridMeta g = *d.grid;
+    const float4 *__restrict__ sorted = d.gsorted;
+    const int *__restrict__ gstart = d.gstart;
 
     // P2 fused into the query load (pointcloud.cpp:321-359), as in nn_grid_kernel
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -634,18 +693,24 @@ __global__ void __launch_bounds__(32 * kCoopWarps) nn_grid_coop_kernel(const Reg
         d.D[(pass + 1) & 1][i] = p;
     }
 
-    // ---- the lane's ball: seeded by the previous pass's neighbour, else one cell edge
+    // ---- the lane's ball: seeded by the previous pass's neighbour (kept per SORTED slot: a coalesced read, and the
+    //      coordinates come with it), else one cell edge
     Best best = {CUDART_INF_F, CUDART_INF_F, 0x7fffffff};
-    float seed_xyz = CUDART_INF_F;
+    BestB bb = {0.f, 0.f, 0.f};
     bool done = !valid || beyond_reach(g, p);
+    bool deferred = false;
     float rad = g.h;
     if (!done && pass > 0) {
-        const int j = d.idx[i];
+        const float4 sd = d.gseed[k];
+        const int j = __float_as_int(sd.w);
         if (j >= 0) {
-            const float4 t = d.tgt[j];
-            best.d = exact_distance_xyz(p.x, p.y, p.z, t.x, t.y, t.z, seed_xyz);
+            float xyz;
+            best.d = exact_distance_xyz(p.x, p.y, p.z, sd.x, sd.y, sd.z, xyz);
             best.i = j;
+            bb.x = sd.x; bb.y = sd.y; bb.z = sd.z;
             rad = best.d;
+        } else if (j == -2) { // nothing inside the acceptance radius last time: not worth widening the warp's search for
+            deferred = true; done = true;
         }
     }
     const float max_reach = g.max_nn * 1.00002f + 1e-6f; // nothing beyond the acceptance radius is ever needed (icp.cpp:553)
@@ -665,16 +730,13 @@ __global__ void __launch_bounds__(32 * kCoopWarps) nn_grid_coop_kernel(const Reg
     const float ax = valid ? p.x - cx : 0.f, ay = valid ? p.y - cy : 0.f, az = valid ? p.z - cz : 0.f;
     const float A = ((ax * ax + ay * ay) + az * az) * 1.000001f;
     const float qx = -2.f * ax, qy = -2.f * ay, qz = -2.f * az; // W = |t'|^2 - 2 a'.t'
-    float thrW = CUDART_INF_F;
-    if (best.d < CUDART_INF_F) thrW = (seed_xyz - A) + ((A * kBandCentredA + seed_xyz * kBandCentredX) + kBandAbs);
 
     const float inv_h = 1.0f / g.h;
     const int nx = g.dim[0], ny = g.dim[1], nz = g.dim[2];
-    bool deferred = false;
 
     for (int round = 0; round < 8; ++round) {
         // lanes whose ball outgrew the cooperative phase go to the warp-per-query kernel with their partial best
-        float rr = fminf(rad, max_reach);
+        const float rr = fminf(rad, max_reach);
         if (!done && rr > coop_r) { deferred = true; done = true; }
         const unsigned active = __ballot_sync(full, !done);
         if (active == 0u) break;
@@ -689,9 +751,7 @@ __global__ void __launch_bounds__(32 * kCoopWarps) nn_grid_coop_kernel(const Reg
         bz0 = __reduce_min_sync(full, bz0); bz1 = __reduce_max_sync(full, bz1);
         const int nyb = by1 - by0 + 1, nzb = bz1 - bz0 + 1;
         const int nrows = nyb * nzb;
-        // a lane that is done must not pick anything up any more
-        const float thr_eval = done ? -CUDART_INF_F : thrW;
-        float thr_live = thr_eval;
+        const bool live = !done; // a lane that is done must not pick anything up any more
         int fill = 0;
         for (int rbase = 0; rbase < nrows; rbase += 32) {
             // ---- lane <-> row: union over the active balls of the cells this row must contribute
@@ -716,8 +776,8 @@ __global__ void __launch_bounds__(32 * kCoopWarps) nn_grid_coop_kernel(const Reg
             int t0 = 0, len = 0;
             if (rv && amin <= bmax) {
                 const int rowbase = (zz * ny + yy) * nx;
-                t0 = __ldg(&d.gstart[rowbase + amin]);
-                len = __ldg(&d.gstart[rowbase + bmax + 1]) - t0;
+                t0 = __ldg(&gstart[rowbase + amin]);
+                len = __ldg(&gstart[rowbase + bmax + 1]) - t0;
             }
             // ---- copy the runs into the batch, centred; a full batch is evaluated at once
             for (unsigned rows = __ballot_sync(full, len > 0); rows; rows &= rows - 1) {
@@ -726,7 +786,7 @@ __global__ void __launch_bounds__(32 * kCoopWarps) nn_grid_coop_kernel(const Reg
                 while (remaining > 0) {
                     const int take = min(remaining, kCoopCap - fill);
                     for (int e = lane; e < take; e += 32) {
-                        const float4 t = __ldg(&d.gsorted[pos + e]);
+                        const float4 t = __ldg(&sorted[pos + e]);
                         const float tx = t.x - cx, ty = t.y - cy, tz = t.z - cz;
                         buf.xs[fill + e] = tx; buf.ys[fill + e] = ty; buf.zs[fill + e] = tz;
                         buf.ns[fill + e] = __fmaf_rn(tz, tz, __fmaf_rn(ty, ty, tx * tx));
@@ -735,7 +795,7 @@ __global__ void __launch_bounds__(32 * kCoopWarps) nn_grid_coop_kernel(const Reg
                     fill += take; pos += take; remaining -= take;
                     if (fill == kCoopCap) {
                         __syncwarp();
-                        coop_evaluate(buf, fill, d.gsorted, p, qx, qy, qz, A, best, thr_live);
+                        coop_batch(buf, fill, sorted, p, qx, qy, qz, A, live, best, bb);
                         __syncwarp();
                         fill = 0;
                     }
@@ -743,17 +803,16 @@ __global__ void __launch_bounds__(32 * kCoopWarps) nn_grid_coop_kernel(const Reg
             }
         }
         if (fill > 0) {
-            // pad to a multiple of four with candidates that can never pass the filter
+            // pad to a multiple of four with candidates that can never be the minimum
             if (lane < 4 && (fill & 3) != 0 && fill + lane < ((fill + 3) & ~3)) {
                 buf.xs[fill + lane] = 0.f; buf.ys[fill + lane] = 0.f; buf.zs[fill + lane] = 0.f;
                 buf.ns[fill + lane] = CUDART_INF_F; buf.gp[fill + lane] = 0;
             }
             __syncwarp();
-            coop_evaluate(buf, (fill + 3) & ~3, d.gsorted, p, qx, qy, qz, A, best, thr_live);
+            coop_batch(buf, (fill + 3) & ~3, sorted, p, qx, qy, qz, A, live, best, bb);
             __syncwarp();
         }
         if (!done) {
-            thrW = thr_live;
             // finished: the best lies inside the searched ball (or the whole acceptance ball was searched)
             if (best.d <= rr || rr >= max_reach) done = true;
             else rad = (best.d < CUDART_INF_F) ? best.d : 4.f * rad;
@@ -762,13 +821,18 @@ __global__ void __launch_bounds__(32 * kCoopWarps) nn_grid_coop_kernel(const Reg
     if (!valid) return;
     if (!done) deferred = true; // round limit (not reachable with radii that quadruple up to the acceptance radius)
     if (deferred) {
+        // the warp-per-query kernel finishes it (and writes gnb); its partial best, a real candidate or none, goes along
         const int slot = atomicAdd(&d.gheavy_count[pass], 1);
         d.gheavy[slot] = i;
-    } else if (!(best.d < g.max_nn)) {
-        best.i = -1; best.d = CUDART_INF_F;
+        d.idx[i] = best.i;
+        d.dist[i] = best.d;
+        d.gseed[k] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)); // no seed next pass: the search starts over
+        return;
     }
-    d.idx[i] = best.i;
-    d.dist[i] = best.d;
+    const bool accepted = best.d < g.max_nn;
+    const float4 rec = make_float4(bb.x, bb.y, bb.z, __int_as_float(accepted ? best.i : -1));
+    d.gnb[i] = rec;                                                                      // nn_finalize: sums, idx, dist
+    d.gseed[k] = accepted ? rec : make_float4(0.f, 0.f, 0.f, __int_as_float(beyond_reach(g, p) ? -1 : -2));
 }
 
 void launch_nn_grid(const RegDesc *descs, int batch, int max_n, int pass, int sm_count, cudaStream_t s, float coop_r)

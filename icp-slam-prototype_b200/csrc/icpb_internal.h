@@ -117,6 +117,8 @@ struct RegDesc {
     const GridMeta *grid;    // ICPB_NN_GRID only
     const float4 *gsorted;   // targets sorted by cell, w = original index
     const int *gstart;       // [ncells+1] first sorted slot of every cell
+    float4 *gnb;             // [n] cooperative search: the nearest target's coordinates, w = its distance (original query order)
+    float4 *gseed;           // [n] the same in SORTED slot order, w = its index bits: the next pass's search ball
     int *gheavy;             // [n] queries still open after the per-thread shells
     int *gheavy_count;       // [passes] length of that list per pass (zeroed once per registration)
 };

@@ -1034,7 +1034,19 @@ __global__ void __launch_bounds__(2 * kChunk) nn_finalize_kernel(const RegDesc *
     float4 best_b = make_float4(0.f, 0.f, 0.f, 0.f);
     bool have_b = false;
     int n_amb = 0;
-    if (splits == 0) {
+    if (splits < 0) {
+        // ICPB_NN_GRID, cooperative search: the neighbour's coordinates and index arrive in one coalesced 16-byte
+        // record per query; the distance is re-evaluated from them (same inputs, same arithmetic: same bits)
+        if (valid) {
+            const float4 nb = __ldcg(&d.gnb[i]);
+            best_i = __float_as_int(nb.w);
+            best_d = CUDART_INF_F;
+            if (best_i >= 0) {
+                best_b = nb; have_b = true;
+                best_d = exact_distance(a.x, a.y, a.z, nb.x, nb.y, nb.z);
+            }
+        }
+    } else if (splits == 0) {
         // ICPB_NN_GRID: nn_grid_kernel already resolved (idx, dist) exactly
         if (valid) { best_i = d.idx[i]; best_d = d.dist[i]; }
     } else {

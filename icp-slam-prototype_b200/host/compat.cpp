@@ -500,7 +500,14 @@ cv::Mat getTransformation(cv::Mat &data, cv::Mat &previous, cv::Mat color, std::
         for (int k = 0; k < 16; ++k) rigid.at<float>(k / 4, k % 4) = (k % 5 == 0) ? 1.f : 0.f;
         return rigid;
     }
-    check(icpb_icp_register(H().ctx, dc, tc, &prm, &res), "icpb_icp_register");
+    // the key-points ride along: dataCloud.rotate / translate move points and key-points together (pointcloud.cpp:321-359),
+    // so they receive (cameraRotation, cameraPosition) of :70-71 and then every motion of the loop, in order
+    icpb_cloud *kc = nullptr;
+    if (!dataCloud.keypoints.empty()) {
+        kc = upload(2, dataCloud.keypoints);
+        check(icpb_cloud_transform(kc, g.cameraRotation, cp), "icpb_cloud_transform");
+    }
+    check(icpb_icp_register_carry(H().ctx, dc, tc, kc, &prm, &res), "icpb_icp_register_carry");
     // cameraRotation *= R (:237) and cameraPosition -= offset (:246), accumulated over the iterations
     mul33(g.cameraRotation, res.cam_rotation, g.cameraRotation);
     g.cameraPosition += cv::Point3f(res.cam_position[0], res.cam_position[1], res.cam_position[2]);
@@ -508,11 +515,7 @@ cv::Mat getTransformation(cv::Mat &data, cv::Mat &previous, cv::Mat color, std::
     std::cout << res.mse;                                               // :264
     // :270 (the all-point twin of :271): certainty update from the registered key-points
     download(dc, dataCloud.points);
-    if (!dataCloud.keypoints.empty()) {
-        icpb_cloud *kc = upload(2, dataCloud.keypoints);
-        check(icpb_cloud_transform(kc, g.cameraRotation, nullptr), "icpb_cloud_transform");
-        const float np[3] = {g.cameraPosition.x, g.cameraPosition.y, g.cameraPosition.z};
-        check(icpb_cloud_transform(kc, nullptr, np), "icpb_cloud_transform");
+    if (kc) {
         download(kc, dataCloud.keypoints);
         g.map->update(dataCloud, DELTA_CONFIDENCE, depthWindow);
     }

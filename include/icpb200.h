@@ -219,6 +219,11 @@ int icpb_nn_search_device(icpb_ctx *ctx, const icpb_cloud *data, const icpb_clou
  * the data cloud is transformed in place; the whole loop runs on the device. */
 int icpb_icp_register(icpb_ctx *ctx, icpb_cloud *data, const icpb_cloud *target,
                       const icpb_icp_params *params, icpb_icp_result *result);
+/* The same loop with a second cloud in tow: `carry` (e.g. the data cloud's key-points) receives every motion the data
+ * cloud receives, in the same order and arithmetic -- what dataCloud.rotate / translate do to points AND key-points
+ * (pointcloud.cpp:321-359) while only the points are associated (icp.cpp:149/253). */
+int icpb_icp_register_carry(icpb_ctx *ctx, icpb_cloud *data, const icpb_cloud *target, icpb_cloud *carry,
+                            const icpb_icp_params *params, icpb_icp_result *result);
 /* `count` independent registrations (BASELINE config 4); results[i] for pair i. */
 int icpb_icp_register_batch(icpb_ctx *ctx, icpb_cloud *const *data, const icpb_cloud *const *target,
                             int count, const icpb_icp_params *params, icpb_icp_result *results);

@@ -629,6 +629,14 @@ int orc_icp(orc_point *data, int n, const orc_point *target, int m,
     return icp_core(data, n, NULL, 0, target, m, prm, res, idx_trace, dist_trace, NULL, NULL);
 }
 
+/* The all-point loop with a second cloud in tow: `carry` follows every motion of `data` (dataCloud.rotate /
+ * translate move points and key-points alike, pointcloud.cpp:321-359). */
+int orc_icp_carry(orc_point *data, int n, orc_point *carry, int n_carry, const orc_point *target, int m,
+                  const orc_icp_params *prm, orc_icp_result *res)
+{
+    return icp_core(data, n, n_carry > 0 ? carry : NULL, n_carry, target, m, prm, res, NULL, NULL, NULL, NULL);
+}
+
 /* 8f-2, the loop as the reference runs it (icp.cpp:98,155-258): the data cloud's KEY-POINTS are associated with
  * the map cloud's key-points (findGlobalKeyPointAssociations :488-515, prm->max_nn_distance = 0.1 m, icp.hpp:10);
  * the cloud's points follow every motion; the rejected key-points of ALL passes accumulate in `nonassoc`

@@ -107,6 +107,8 @@ int orc_icp(orc_point *data /* in/out, n */, int n, const orc_point *target, int
 /* 8f-2: the same loop with the KEY-POINT association the reference runs (icp.cpp:98,255; :488-539): `keypoints`
  * (in/out) are associated with `map_keypoints`, `points` (in/out, nullable) only follow the motion, the rejected
  * key-points of every pass accumulate in `nonassoc` (capacity (max_iterations+1)*k, icp.cpp:508). */
+int orc_icp_carry(orc_point *data, int n, orc_point *carry, int n_carry, const orc_point *target, int m,
+                  const orc_icp_params *prm, orc_icp_result *res);
 int orc_icp_keypoints(orc_point *keypoints, int k, orc_point *points, int n, const orc_point *map_keypoints, int mk,
                       const orc_icp_params *prm, orc_icp_result *res, orc_point *nonassoc, int *n_nonassoc);
 

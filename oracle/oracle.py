@@ -229,6 +229,19 @@ def _res_dict(res):
     }
 
 
+def icp_carry(data, carry, target, max_iterations=20, threshold=0.0, max_nn_distance=0.75, solve_mode=SOLVE_REFERENCE,
+              last_translation=(0, 0, 0), n_threads=1):
+    """All-point loop; `carry` follows every motion of `data`.  Returns (result dict, moved data, moved carry)."""
+    data = np.ascontiguousarray(data).copy()
+    carry = np.ascontiguousarray(carry).copy()
+    target = np.ascontiguousarray(target)
+    prm = IcpParams(max_iterations, threshold, max_nn_distance, solve_mode, (C.c_float * 3)(*last_translation), n_threads)
+    res = IcpResult()
+    rc = lib().orc_icp_carry(_p(data), len(data), _p(carry), len(carry), _p(target), len(target), C.byref(prm), C.byref(res))
+    assert rc == 0
+    return _res_dict(res), data, carry
+
+
 def icp_keypoints(keypoints, points, map_keypoints, max_iterations=16, threshold=1e-4, max_nn_distance=0.1,
                   solve_mode=SOLVE_REFERENCE, last_translation=(0, 0, 0), n_threads=1):
     """8f-2 (icp.cpp:98,155-258).  Returns (result dict, moved key-points, moved points, non-associations)."""

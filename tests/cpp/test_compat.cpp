@@ -100,6 +100,12 @@ int main(int argc, char **argv)
     for (int k = 0; k < 9; ++k) pose[k] = cr.at<float>(k / 3, k % 3);
     pose[9] = cp.x; pose[10] = cp.y; pose[11] = cp.z;
     dump(out + "/pose.bin", pose, sizeof(pose));
+    {   // the map after two all-point frames: the registered key-points must land where the points went
+        map::Map &am = icp::mapState();
+        dump(out + "/ap_mapkp.bin", am.mapCloud.keypoints.data(), am.mapCloud.keypoints.size() * sizeof(color_point_t));
+        am.syncWorld();
+        dump(out + "/ap_world.bin", am.world, (size_t)MAP_HEIGHT * MAP_HEIGHT * MAP_HEIGHT);
+    }
     // pose reporting exactly as the frame loop writes it (SLAM.cpp:284-293)
     {
         Quaternion rotationQ = Quaternion(cr);

@@ -119,7 +119,19 @@ def test_compat_program_matches_oracle(tmp_path, orc):
     I = np.eye(3, dtype=f32)
     tg = orc.translate(orc.rotate(pc1, I), cam)
     da = orc.translate(orc.rotate(dc1, I), cam)
-    r1, _, _, _ = orc.icp(da, tg, 3, 0.0, 0.75, orc.SOLVE_REFERENCE, n_threads=8)
+    # the 50 key-points of the C++ program ride along with the points (pointcloud.cpp:321-359) and feed the map (:62, :270)
+    from test_live_loop_vs_ref import lift_keypoints
+    kps50 = [(20 + (i * 37) % (w - 40), 20 + (i * 53) % (h - 40)) for i in range(50)]
+    ap_grid = np.zeros(dims, np.uint8)
+    ap_tbl = np.full(dims, -1, np.int32)
+    ap_kp = []
+    pk1 = orc.translate(orc.rotate(lift_keypoints(orc, prev, col, kps50), I), cam)
+    app = orc.map_update_tracked(ap_grid, ap_tbl, dims, cell, pk1, 0, 180, 180, 0)          # icp.cpp:62, map.cpp:220-269
+    ap_kp.extend(pk1[app])
+    dk1 = orc.translate(orc.rotate(lift_keypoints(orc, cur, col, kps50), I), cam)
+    r1, _, dk1m = orc.icp_carry(da, dk1, tg, 3, 0.0, 0.75, orc.SOLVE_REFERENCE, n_threads=8)
+    app = orc.map_update_tracked(ap_grid, ap_tbl, dims, cell, dk1m, 0, 25, 180, len(ap_kp))
+    ap_kp.extend(dk1m[app])
     assert np.array_equal(np.fromfile(o + "/T1.bin", f32).reshape(4, 4), r1["rigid"])
     camR = orc.gemm33f(I, r1["cam_rotation"])
     camP = (cam + r1["cam_position"]).astype(f32)
@@ -128,8 +140,14 @@ def test_compat_program_matches_oracle(tmp_path, orc):
     pc2 = orc.backproject(cur, col, orc.kinect_v1(), orc.SUB_STREAM, 40, 0, p2)[0]
     tg2 = orc.translate(orc.rotate(pc2, camR), camP)
     da2 = orc.translate(orc.rotate(dc2, camR), camP)
-    r2, _, _, _ = orc.icp(da2, tg2, 3, 0.0, 0.75, orc.SOLVE_REFERENCE, last_translation=tuple(-r1["offset"]), n_threads=8)
+    dk2 = orc.translate(orc.rotate(lift_keypoints(orc, prev, col, kps50), camR), camP)
+    r2, _, dk2m = orc.icp_carry(da2, dk2, tg2, 3, 0.0, 0.75, orc.SOLVE_REFERENCE, last_translation=tuple(-r1["offset"]), n_threads=8)
+    app = orc.map_update_tracked(ap_grid, ap_tbl, dims, cell, dk2m, 0, 25, 180, len(ap_kp))
+    ap_kp.extend(dk2m[app])
     assert np.array_equal(np.fromfile(o + "/T2.bin", f32).reshape(4, 4), r2["rigid"])
+    _same(_pts(o + "/ap_mapkp.bin", orc), np.array(ap_kp, dtype=orc.POINT_DTYPE))
+    assert np.array_equal(np.fromfile(o + "/ap_world.bin", np.uint8).reshape(dims), ap_grid)
+    assert (ap_grid > 0).sum() > 40
     pose = np.fromfile(o + "/pose.bin", f32)
     assert np.array_equal(pose[:9].reshape(3, 3), orc.gemm33f(camR, r2["cam_rotation"]))
     assert np.array_equal(pose[9:], (camP + r2["cam_position"]).astype(f32))
