@@ -1200,7 +1200,7 @@ int icpb_map_update_endpoints(icpb_map *map, const icpb_cloud *points, int rule,
     if (rule != ICPB_RULE_A && rule != ICPB_RULE_C) return fail(ctx, ICPB_ERR_INVALID, "unknown update rule");
     if (delta < 0 || delta > 255) return fail(ctx, ICPB_ERR_INVALID, "delta out of [0,255]");
     CU(ctx, cudaSetDevice(ctx->device));
-    launch_map_endpoints(map->dev, points->d_pts, points->n, rule, delta, max_conf, ctx->stream);
+    launch_map_endpoints(map->dev, flat_src(points->d_pts, points->n), rule, delta, max_conf, ctx->stream);
     ctx->launches += points->n > 0;
     CU(ctx, cudaGetLastError());
     return ICPB_OK;
@@ -1279,10 +1279,10 @@ int icpb_map_integrate_rays(icpb_map *map, const icpb_cloud *points, const float
         CU(ctx, cudaMemsetAsync(d_vis, 0, sizeof(unsigned long long), ctx->stream));
     }
     int sp = span_begin(ctx, ICPB_PROF_MAP_RAYS);
-    launch_map_rays(map->dev, points->d_pts, points->n, origin, delta_dec, d_vis, d_next, ctx->sm_count, ctx->stream); // phase 1
+    launch_map_rays(map->dev, flat_src(points->d_pts, points->n), origin, delta_dec, d_vis, d_next, ctx->sm_count, ctx->stream); // phase 1
     span_end(ctx, sp);
     sp = span_begin(ctx, ICPB_PROF_MAP_ENDPOINTS);
-    launch_map_endpoints(map->dev, points->d_pts, points->n, ICPB_RULE_A, delta_inc, 0, ctx->stream);  // phase 2
+    launch_map_endpoints(map->dev, flat_src(points->d_pts, points->n), ICPB_RULE_A, delta_inc, 0, ctx->stream);  // phase 2
     span_end(ctx, sp);
     ctx->launches += 2 * (points->n > 0);
     CU(ctx, cudaGetLastError());
@@ -1348,26 +1348,14 @@ int icpb_map_integrate_bands_device(icpb_map *map, const void *d_bands, int worl
     int rc;
     if ((rc = ws_get(ctx, WS_MISC, 64, &misc, true))) return rc;
     unsigned int *d_next = (unsigned int *)((char *)misc + 40);
-    const float4 *pts;
-    const int *d_n;
-    const int cap = world * band_capacity;
-    if (world == 1) { // a single band is already the frame
-        pts = (const float4 *)d_bands + 1;
-        d_n = (const int *)d_bands;
-    } else {
-        float4 *frame;
-        if ((rc = ws_get(ctx, WS_FRAME, sizeof(float4) * (size_t)cap, (void **)&frame))) return rc;
-        int *d_total = (int *)((char *)misc + 56);
-        launch_assemble_bands((const float4 *)d_bands, world, band_capacity, frame, cap, d_total, ctx->stream);
-        ctx->launches += 1;
-        pts = frame;
-        d_n = d_total;
-    }
+    if (world > kMaxBands) return fail(ctx, ICPB_ERR_INVALID, "more bands than kMaxBands");
+    // the kernels read the bands where they lie (header row + points, band_capacity + 1 rows apart): no assembly pass
+    const PointSrc src = band_src((const float4 *)d_bands, world, band_capacity, (long long)band_capacity + 1);
     int sp = span_begin(ctx, ICPB_PROF_MAP_RAYS);
-    launch_map_rays(map->dev, pts, cap, origin, delta_dec, nullptr, d_next, ctx->sm_count, ctx->stream, d_n); // phase 1
+    launch_map_rays(map->dev, src, origin, delta_dec, nullptr, d_next, ctx->sm_count, ctx->stream); // phase 1
     span_end(ctx, sp);
     sp = span_begin(ctx, ICPB_PROF_MAP_ENDPOINTS);
-    launch_map_endpoints(map->dev, pts, cap, ICPB_RULE_A, delta_inc, 0, ctx->stream, d_n);                   // phase 2
+    launch_map_endpoints(map->dev, src, ICPB_RULE_A, delta_inc, 0, ctx->stream);                   // phase 2
     span_end(ctx, sp);
     ctx->launches += 2;
     CU(ctx, cudaGetLastError());

@@ -197,13 +197,28 @@ struct MapDev {
     int nby2, nbz2;
 };
 void launch_map_rebuild_bricks(const MapDev &m, long long brick_words, cudaStream_t s);
-void launch_map_endpoints(const MapDev &m, const float4 *pts, int n, int rule, int delta, int max_conf,
-                          cudaStream_t s, const int *n_dev = nullptr);
+// Where a map kernel finds its points.  Flat: `n` points at pts (n_dev, nullable: the live count in device memory, n
+// then being the capacity).  Banded (bands > 0): `bands` bands `band_stride` rows apart, each one 16-byte header row
+// (its point count in the first word; negative = none) followed by up to band_cap points -- the receive buffer of an
+// all-gather as it is, no assembly pass.
+constexpr int kMaxBands = 16;
+struct PointSrc {
+    const float4 *pts;
+    const int *n_dev;
+    int n;
+    int bands, band_cap;
+    long long band_stride;
+};
+inline PointSrc flat_src(const float4 *pts, int n, const int *n_dev = nullptr) { return PointSrc{pts, n_dev, n, 0, 0, 0}; }
+inline PointSrc band_src(const float4 *first_header, int bands, int band_cap, long long band_stride)
+{
+    return PointSrc{first_header, nullptr, bands * band_cap, bands, band_cap, band_stride};
+}
+void launch_map_endpoints(const MapDev &m, const PointSrc &src, int rule, int delta, int max_conf, cudaStream_t s);
 void launch_map_tracked(const MapDev &m, int *table, const float4 *pts, int n, int variant, int delta, int max_conf,
                         float4 *dst, int dst_n, int dst_capacity, int *d_appended, cudaStream_t s);
-void launch_map_rays(const MapDev &m, const float4 *pts, int n, const float origin[3], int delta_dec,
-                     unsigned long long *visited, unsigned int *next_ray, int sm_count, cudaStream_t s,
-                     const int *n_dev = nullptr);
+void launch_map_rays(const MapDev &m, const PointSrc &src, const float origin[3], int delta_dec,
+                     unsigned long long *visited, unsigned int *next_ray, int sm_count, cudaStream_t s);
 
 } // namespace icpb
 

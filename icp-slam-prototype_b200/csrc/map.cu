@@ -103,16 +103,53 @@ void launch_map_rebuild_bricks(const MapDev &m, long long brick_words, cudaStrea
     map_rebuild_bricks_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, s>>>(m, nbx);
 }
 
-__global__ void map_endpoints_kernel(MapDev m, const float4 *__restrict__ pts, int n, int rule, int delta,
-                                     int max_conf, const int *__restrict__ n_dev)
+// ---- PointSrc (icpb_internal.h): per-thread view of where point i lives --------------------------------------------
+struct SrcView {
+    int total;
+};
+
+__device__ __forceinline__ int band_count(const PointSrc &s, int b)
+{
+    return max(0, min(s.band_cap, __ldg(reinterpret_cast<const int *>(s.pts + (long long)b * s.band_stride))));
+}
+
+__device__ __forceinline__ void src_open(const PointSrc &s, SrcView &v)
+{
+    if (s.bands == 0) {
+        // a negative live count (-1: the lift's look-back timed out) means "no points"
+        v.total = s.n_dev ? max(0, min(s.n, *s.n_dev)) : s.n;
+        return;
+    }
+    int acc = 0;
+    for (int b = 0; b < s.bands; ++b) acc += band_count(s, b);
+    v.total = acc;
+}
+
+// banded: the headers are a few L1-resident words; walking them per fetched point keeps them out of the registers of
+// the long-running ray kernel (a prefix array held for the kernel's lifetime cost it two resident CTAs per SM)
+__device__ __forceinline__ float4 src_point(const PointSrc &s, const SrcView &, int i)
+{
+    if (s.bands == 0) return s.pts[i];
+    int b = 0;
+    for (; b < s.bands - 1; ++b) {
+        const int c = band_count(s, b);
+        if (i < c) break;
+        i -= c;
+    }
+    return s.pts[(long long)b * s.band_stride + 1 + i];
+}
+
+__global__ void map_endpoints_kernel(MapDev m, PointSrc src, int rule, int delta, int max_conf)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n_dev) n = max(0, min(n, *n_dev)); // a negative header (-1: the lift's look-back timed out) means "no points"
+    SrcView sv;
+    src_open(src, sv);
+    const int n = sv.total;
     const int lane = threadIdx.x & 31;
     long long lin = -1;
     int vx = 0, vy = 0, vz = 0;
     if (i < n) {
-        float4 p = pts[i];
+        float4 p = src_point(src, sv, i);
         vx = voxel_axis(p.x, m.cell, m.dims[0]);
         vy = voxel_axis(p.y, m.cell, m.dims[1]);
         vz = voxel_axis(p.z, m.cell, m.dims[2]);
@@ -132,11 +169,10 @@ __global__ void map_endpoints_kernel(MapDev m, const float4 *__restrict__ pts, i
     });
 }
 
-void launch_map_endpoints(const MapDev &m, const float4 *pts, int n, int rule, int delta, int max_conf,
-                          cudaStream_t s, const int *n_dev)
+void launch_map_endpoints(const MapDev &m, const PointSrc &src, int rule, int delta, int max_conf, cudaStream_t s)
 {
-    if (n <= 0) return;
-    map_endpoints_kernel<<<(n + 255) / 256, 256, 0, s>>>(m, pts, n, rule, delta, max_conf, n_dev);
+    if (src.n <= 0) return;
+    map_endpoints_kernel<<<(src.n + 255) / 256, 256, 0, s>>>(m, src, rule, delta, max_conf);
 }
 
 // M3 with the reference's lookup-table / mapCloud bookkeeping (map.cpp:101-113, 136-149, 246-259).  One CTA,
@@ -335,11 +371,13 @@ __device__ __forceinline__ void ray_setup(const MapDev &m, const float4 p, int o
 }
 
 template <typename I>
-__global__ void __launch_bounds__(128) map_rays_kernel(MapDev m, const float4 *__restrict__ pts, int n, int ox, int oy,
+__global__ void __launch_bounds__(128) map_rays_kernel(MapDev m, PointSrc src, int ox, int oy,
                                                       int oz, int delta_dec, unsigned long long *visited,
-                                                      unsigned int *next_ray, const int *__restrict__ n_dev)
+                                                      unsigned int *next_ray)
 {
-    if (n_dev) n = max(0, min(n, *n_dev));
+    SrcView sv;
+    src_open(src, sv);
+    const int n = sv.total;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     RayState<I> r;
@@ -358,7 +396,7 @@ __global__ void __launch_bounds__(128) map_rays_kernel(MapDev m, const float4 *_
             base = __shfl_sync(0xffffffffu, base, 0);
             if (r.rem <= 0) {
                 const unsigned i = base + (unsigned)__popc(idle & lt);
-                if (i < (unsigned)n) ray_setup<I>(m, pts[i], ox, oy, oz, delta_dec, r, my_visits);
+                if (i < (unsigned)n) ray_setup<I>(m, src_point(src, sv, (int)i), ox, oy, oz, delta_dec, r, my_visits);
             }
             drained = base + (unsigned)__popc(idle) >= (unsigned)n;
         }
@@ -547,11 +585,13 @@ __device__ __forceinline__ void ray_jump(const MapDev &m, RayBrick<I> &r)
 }
 
 template <typename I>
-__global__ void __launch_bounds__(128) map_rays_brick_kernel(MapDev m, const float4 *__restrict__ pts, int n, int ox, int oy,
+__global__ void __launch_bounds__(128) map_rays_brick_kernel(MapDev m, PointSrc src, int ox, int oy,
                                                             int oz, int delta_dec, unsigned long long *visited,
-                                                            unsigned int *next_ray, const int *__restrict__ n_dev)
+                                                            unsigned int *next_ray)
 {
-    if (n_dev) n = max(0, min(n, *n_dev));
+    SrcView sv;
+    src_open(src, sv);
+    const int n = sv.total;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     RayBrick<I> r;
@@ -574,7 +614,7 @@ __global__ void __launch_bounds__(128) map_rays_brick_kernel(MapDev m, const flo
             base = __shfl_sync(0xffffffffu, base, 0);
             if (r.rem <= 0) {
                 const unsigned i = base + (unsigned)__popc(idle & lt);
-                if (i < (unsigned)n) ray_setup_brick<I>(m, pts[i], ox, oy, oz, delta_dec, r, my_visits);
+                if (i < (unsigned)n) ray_setup_brick<I>(m, src_point(src, sv, (int)i), ox, oy, oz, delta_dec, r, my_visits);
             }
             drained = base + (unsigned)__popc(idle) >= (unsigned)n;
         }
@@ -636,9 +676,10 @@ __global__ void __launch_bounds__(128) map_rays_brick_kernel(MapDev m, const flo
     }
 }
 
-void launch_map_rays(const MapDev &m, const float4 *pts, int n, const float origin[3], int delta_dec,
-                     unsigned long long *visited, unsigned int *next_ray, int sm_count, cudaStream_t s, const int *n_dev)
+void launch_map_rays(const MapDev &m, const PointSrc &src, const float origin[3], int delta_dec,
+                     unsigned long long *visited, unsigned int *next_ray, int sm_count, cudaStream_t s)
 {
+    const int n = src.n;
     if (n <= 0) return;
     cudaMemsetAsync(next_ray, 0, sizeof(unsigned int), s);
     // persistent grid: every resident warp slot is filled once (40 registers -> 12 CTAs of 128 threads per SM)
@@ -655,16 +696,16 @@ void launch_map_rays(const MapDev &m, const float4 *pts, int n, const float orig
     static const bool bricks = []() { const char *e = getenv("ICPB_RAY_BRICKS"); return !(e && *e == '0'); }();
     if (bricks) { // default: cross empty bricks in one jump
         if (prod < 2147483647.0)
-            map_rays_brick_kernel<int><<<blocks, 128, 0, s>>>(m, pts, n, o[0], o[1], o[2], delta_dec, visited, next_ray, n_dev);
+            map_rays_brick_kernel<int><<<blocks, 128, 0, s>>>(m, src, o[0], o[1], o[2], delta_dec, visited, next_ray);
         else
-            map_rays_brick_kernel<long long><<<blocks, 128, 0, s>>>(m, pts, n, o[0], o[1], o[2], delta_dec, visited, next_ray, n_dev);
+            map_rays_brick_kernel<long long><<<blocks, 128, 0, s>>>(m, src, o[0], o[1], o[2], delta_dec, visited, next_ray);
         return;
     }
     // ICPB_RAY_BRICKS=0: the byte-at-a-time walk (kept for A/B measurements)
     if (prod < 2147483647.0)
-        map_rays_kernel<int><<<blocks, 128, 0, s>>>(m, pts, n, o[0], o[1], o[2], delta_dec, visited, next_ray, n_dev);
+        map_rays_kernel<int><<<blocks, 128, 0, s>>>(m, src, o[0], o[1], o[2], delta_dec, visited, next_ray);
     else
-        map_rays_kernel<long long><<<blocks, 128, 0, s>>>(m, pts, n, o[0], o[1], o[2], delta_dec, visited, next_ray, n_dev);
+        map_rays_kernel<long long><<<blocks, 128, 0, s>>>(m, src, o[0], o[1], o[2], delta_dec, visited, next_ray);
 }
 
 } // namespace icpb

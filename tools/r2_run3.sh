@@ -1,7 +1,7 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_icp.py tests/test_gpu_fullshape.py tests/test_gpu_compat.py tests/test_gpu_keypoints.py tests/test_gpu_pipeline.py -m gpu -x -q > gpurun_out/r2_tests3.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_tests3.log
+timeout 900 python -m pytest tests/test_gpu_map.py tests/test_gpu_icp.py tests/test_gpu_fullshape.py tests/test_gpu_compat.py tests/test_gpu_keypoints.py tests/test_gpu_pipeline.py -m gpu -x -q > gpurun_out/r2_tests3.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_tests3.log
 tail -15 gpurun_out/r2_tests3.log
 (
 for cell in 0 0.1 0.125 0.15; do echo "# cell=$cell"; python tools/profile_case.py --grid $cell --iters 20 --repeat 3 --noprof | tail -1; done
