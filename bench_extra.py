@@ -195,18 +195,22 @@ def run_batch10k(args, rank, world, local, emit=True):
 
 def run_map1cm(args, rank, world, local, emit=True):
     """configs[4]: full-resolution Kinect v1 frames into the 600x600x500 1 cm grid, z-slab sharded.  Strong scaling.
-    The concatenated slabs are compared with the ORACLE's grid of the same sequence (and with the unsharded GPU grid)."""
+    Everything multi-GPU happens inside libicpb200 (icpb_comm / icpb_slabmap: NCCL all-gather of the lifted row bands,
+    several frames per exchange, double buffered); torch.distributed only carries the 128-byte NCCL id and the hashes.
+    The concatenated slabs are compared with the ORACLE's grid of the same sequence and with the unsharded GPU grid."""
     import icpb200
     from icpb200 import dist as D
     from icpb200 import synth
     torch = _setup(local, world)
-    stream = torch.cuda.current_stream().cuda_stream
-    ctx = icpb200.Context(local, stream=stream)
+    ctx = icpb200.Context(local)
     K = icpb200.reference_intrinsics_v1()
     dims, cell = (600, 600, 500), 0.01
     frames = args.frames or 32
+    fpe = int(os.environ.get("ICPB_FRAMES_PER_EXCHANGE", "8"))
     poses = synth.trajectory(frames, step_deg=0.8, step_m=0.02)
     depths = [synth.render_depth(R, t, synth.KINECT_V1, seed=f) for f, (R, t) in enumerate(poses)]
+    Rs = np.stack([np.asarray(R, np.float32) for R, _ in poses])
+    ts = np.stack([np.asarray(t, np.float32) for _, t in poses])
     # slab boundaries balanced on the ray work of three frames of the sequence (host-side, identical on every rank)
     bounds = None
     if world > 1:
@@ -219,52 +223,41 @@ def run_map1cm(args, rank, world, local, emit=True):
             ez.append(probe.download()["z"].astype(np.float64)); oz.append(float(t[2]))
         bounds = D.balanced_slab_bounds(dims[2], world, cell, oz, ez)
         probe.close()
-    sm = D.SlabMap(ctx, dims, cell, rank, world, 640 * 480, bounds)
+    comm = icpb200.Comm.from_torch(ctx) if world > 1 else None
+    sm = icpb200.SlabMapC(ctx, comm, dims, cell, 640, 480, bounds)
 
     # depth frames resident in HBM before the timed region (the metric's definition); int16 view of the u16 bits
     host_depths = torch.from_numpy(np.stack(depths).astype(np.uint16).view(np.int16)).pin_memory()
     d_depths = host_depths.to(torch.device("cuda", local))
+    torch.cuda.synchronize()
     frame_bytes = 640 * 480 * 2
+    ctx_stream = torch.cuda.ExternalStream(ctx.lib.icpb_ctx_stream(ctx.h))
 
-    def step(count, h2d=False):
-        npts = vis = 0
+    def step(h2d=False):
         ctx.timer_start()
-        if count:   # counted pass: the host-synchronising calls, which also report the voxel visits
-            for (R, t), dpt in zip(poses, depths):
-                n, v = sm.integrate(dpt, K, R, t, 25, 25, True)
-                npts += n; vis += v
-        else:       # timed passes: the sync-free frame path, nothing returns to the host until the end
-            for f, (R, t) in enumerate(poses):
-                if h2d:  # e2e leg: the frame comes from pinned host memory on the same stream
-                    d_depths[f].copy_(host_depths[f], non_blocking=True)
-                sm.integrate_device(d_depths.data_ptr() + f * frame_bytes, 640, 480, K, R, t, 25, 25)
-        return ctx.timer_stop(), npts, vis
+        if h2d:   # e2e leg: every frame comes from pinned host memory on the context's stream
+            with torch.cuda.stream(ctx_stream):
+                d_depths.copy_(host_depths, non_blocking=True)
+        sm.integrate_sequence_device(d_depths.data_ptr(), frames, K, Rs, ts, 25, 25, fpe)
+        return ctx.timer_stop()
 
     for _ in range(args.warmup):
-        step(False)
+        step()
     sm.map.clear()
-    _, npts, visited = step(True)           # counted pass (also the grid that is hashed)
+    step()                                  # the grid that is hashed: one pass over the sequence from an empty map
     slab = sm.download()
     _barrier(torch, world)
-    ms_all = []
-    for _ in range(args.steps):
-        ms, _, _ = step(False)
-        ms_all.append(ms)
+    ms_all = [step() for _ in range(args.steps)]
     _barrier(torch, world)
     tot = _max_over_ranks(torch, world, local, float(np.sum(ms_all)))
     # the ray-walk kernel's own time (roofline), same sequence with CUDA events around every launch
     ctx.set_profiling(True)
-    step(False)
+    step()
     rays_ms, rays_launches = ctx.profile_read(icpb200.PROF_MAP_RAYS)
     ends_ms, _ = ctx.profile_read(icpb200.PROF_MAP_ENDPOINTS)
-    lift_ms, _ = ctx.profile_read(icpb200.PROF_LIFT)
     ctx.set_profiling(False)
     rays_ms = _max_over_ranks(torch, world, local, rays_ms)
-    # e2e: every depth frame copied from pinned host memory inside the timed region, point count read back at the end
-    e2e = []
-    for _ in range(2):
-        ms, _, _ = step(False, h2d=True)
-        e2e.append(ms)
+    e2e = [step(h2d=True) for _ in range(2)]
     e2e_tot = _max_over_ranks(torch, world, local, float(e2e[-1]))
     h = hashlib.sha256(slab.tobytes()).hexdigest()
     if world > 1:
@@ -273,27 +266,32 @@ def run_map1cm(args, rank, world, local, emit=True):
         dist.all_gather_object(hs, (sm.z_lo, sm.z_hi, h, int((slab > 0).sum())))
     else:
         hs = [(sm.z_lo, sm.z_hi, h, int((slab > 0).sum()))]
-    unsharded_ok = None
-    if world > 1 and rank == 0:
-        # T7: the slabs must be the single-GPU grid, byte for byte - recompute it unsharded here and compare digests
-        one = D.SlabMap(ctx, dims, cell, 0, 1, 640 * 480)
+    del slab
+    line = None
+    if rank == 0:
+        # T7: the slabs must be the single-GPU grid, byte for byte -- integrated here unsharded through the
+        # host-synchronising calls, which also count the rays and the voxels their walks pass
+        one = ctx.map(dims, cell)
+        cl = ctx.cloud(640 * 480)
+        npts = visited = 0
         for (R, t), dpt in zip(poses, depths):
-            one.integrate(dpt, K, R, t, 25, 25, False)
+            cl.from_depth(dpt, None, K)
+            cl.transform(np.asarray(R, np.float32), np.asarray(t, np.float32))
+            npts += cl.n
+            visited += one.integrate_rays(cl, tuple(float(x) for x in t), 25, 25, True)
         g1 = one.download()
         unsharded_ok = all(hashlib.sha256(np.ascontiguousarray(g1[:, :, lo:hi]).tobytes()).hexdigest() == hh
                            for (lo, hi, hh, _) in hs)
-        one.map.close()
+        one.close(); cl.close()
         del g1
         assert unsharded_ok, "z-slab result differs from the single-GPU grid"
-    line = None
-    if rank == 0:
         ms_per_step = tot / args.steps
         updates = visited + npts  # voxels visited by rays + endpoint updates, per pass over the sequence
         alg_bytes = 2.0 * visited + 12.0 * npts + 14.0 * npts
         rays_bytes = 2.0 * visited + 12.0 * npts        # 2 B per visited voxel + 12 B per ray
         peak = _hbm_peak()
         rays_gbs = rays_bytes / max(rays_ms * 1e-3, 1e-12) / 1e9
-        # the whole sequence through the oracle: every slab of the counted pass must equal the oracle grid's slab
+        # the whole sequence through the oracle: every slab must equal the oracle grid's slab
         cb, oracle_ok = None, None
         try:
             from oracle import oracle as orc
@@ -318,28 +316,34 @@ def run_map1cm(args, rank, world, local, emit=True):
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": {"workload": f"configs[4]: {frames} full-res Kinect v1 frames into a 600x600x500 1 cm uint8 grid "
-                                       "(180 MB), z-slab sharded (boundaries balanced on ray work), one all-gather of "
-                                       "lifted points per frame; depth frames resident in HBM, no host synchronisation "
-                                       "inside the sequence",
+                                       "(180 MB), z-slab sharded (boundaries balanced on ray work); every rank lifts its row "
+                                       f"band, one NCCL all-gather per {fpe} frames inside libicpb200 (double buffered, three "
+                                       "streams), bands walked in place; depth frames resident in HBM, no host "
+                                       "synchronisation inside the sequence",
+                           "frames_per_exchange": fpe,
                            "rays_per_pass": npts, "voxels_visited_per_pass": visited, "slabs": hs,
                            "slabs_equal_single_gpu_grid": unsharded_ok, "slabs_equal_oracle_grid": oracle_ok,
                            "l2": "grid (180 MB) exceeds L2 at 1 GPU"},
                 "extra": {"frames_per_s": frames / (ms_per_step * 1e-3),
                           "algorithmic_GBps": alg_bytes / (ms_per_step * 1e-3) / 1e9,
-                          "stage_ms_per_pass_rank0": {"lift": lift_ms, "map_rays_max_over_ranks": rays_ms, "map_endpoints": ends_ms}},
+                          "stage_ms_per_pass": {"map_rays_max_over_ranks": rays_ms, "map_endpoints_rank0": ends_ms}},
                 "roofline": {"bound": "hbm", "kernel": "map_rays_brick_kernel", "achieved": rays_gbs, "peak": peak,
                              "unit": "GB/s", "frac": rays_gbs / peak, "traffic": None,
                              "bytes_per_launch": rays_bytes / max(rays_launches, 1),
                              "avg_launch_ms": rays_ms / max(rays_launches, 1), "launches_timed": rays_launches,
-                             "note": "algorithmic bytes = 2 B per voxel the walk passes + 12 B per ray (SURVEY.md 8d); the "
-                                     "brick-skipping walk does not touch the voxels of empty bricks, so the figure can "
-                                     "exceed what the memory system moves"},
+                             "note": "algorithmic bytes = 2 B per voxel the walk passes + 12 B per ray (SURVEY.md 8d), whole "
+                                     "job; time = the slowest rank's summed launches.  The brick-skipping walk does not touch "
+                                     "the voxels of empty bricks, so the figure can exceed what the memory system moves"},
                 "cpu_baseline": cb,
                 "e2e": {"value": updates / (e2e_tot * 1e-3), "unit": "voxel updates/s",
-                        "h2d_bytes_per_step": int(frames * frame_bytes), "d2h_bytes_per_step": 4}}
+                        "h2d_bytes_per_step": int(frames * frame_bytes), "d2h_bytes_per_step": 0}}
         if emit:
             print(json.dumps(line), flush=True)
-    sm.map.close()
+    if world > 1:
+        _barrier(torch, world)
+    sm.close()
+    if comm is not None:
+        comm.close()
     ctx.close()
     return line
 

@@ -482,6 +482,49 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
 
 } // namespace
 
+namespace icpb {
+
+int api_fail(icpb_ctx *ctx, int status, const char *what, cudaError_t ce) { return fail(ctx, status, what, ce); }
+
+int api_ws_get(icpb_ctx *ctx, int id, size_t bytes, void **out, bool zero_new) { return ws_get(ctx, id, bytes, out, zero_new); }
+
+int api_span_begin(icpb_ctx *ctx, int kernel) { return span_begin(ctx, kernel); }
+
+void api_span_end(icpb_ctx *ctx, int id) { span_end(ctx, id); }
+
+// Rows [row0, row1) of a device-resident depth frame -> world-space band (header row + points) on `stream`;
+// tile_state: 8 * (3 * tiles + 2) bytes of scratch, zeroed once by its owner.
+int api_lift_band(icpb_ctx *ctx, cudaStream_t stream, void *tile_state, const void *d_depth, int w, int h, int row0,
+                  int row1, const icpb_intrinsics *K, const float *R, const float *t, void *d_band, int band_capacity)
+{
+    if (row0 < 0 || row1 <= row0 || row1 > h) return fail(ctx, ICPB_ERR_INVALID, "row band outside the image");
+    if ((long long)(row1 - row0) * w > band_capacity) return fail(ctx, ICPB_ERR_CAPACITY, "band smaller than its pixel count");
+    const uint16_t *band_depth = (const uint16_t *)d_depth + (size_t)row0 * w;
+    if (((uintptr_t)band_depth & 15) != 0) return fail(ctx, ICPB_ERR_INVALID, "band depth rows must start 16-byte aligned");
+    BackprojectArgs a;
+    a.depth = band_depth;
+    a.bgr = nullptr;
+    a.w = w; a.h = row1 - row0; a.K = *K;
+    a.rule = ICPB_SUB_NONE; a.rule_arg = 1; a.seed = 0;
+    a.keep_stream = nullptr; a.keep_stream_len = 0;
+    a.out = (float4 *)d_band + 1;           // row 0 is the header: point count in its first word
+    a.capacity = band_capacity;
+    a.n_tiles = backproject_tiles(w, a.h);
+    a.frames = 1;
+    a.v_offset = row0;
+    a.depth_stride = a.bgr_stride = a.out_stride = a.state_stride = 0;
+    a.out_count = (int *)d_band;
+    a.tile_state = (unsigned long long *)tile_state + 2;
+    CU(ctx, cudaMemsetAsync(d_band, 0, sizeof(float4), stream));
+    launch_backproject(a, stream);
+    if (R || t) launch_transform(a.out, band_capacity, R, t, R != nullptr, t != nullptr, stream, (const int *)d_band);
+    ctx->launches += 1 + ((R || t) ? 1 : 0);
+    CU(ctx, cudaGetLastError());
+    return ICPB_OK;
+}
+
+} // namespace icpb
+
 extern "C" {
 
 int icpb_version(void) { return ICPB_VERSION; }
@@ -494,6 +537,7 @@ const char *icpb_status_string(int status)
     case ICPB_ERR_EMPTY: return "empty cloud";
     case ICPB_ERR_CUDA: return "CUDA error";
     case ICPB_ERR_CAPACITY: return "capacity exceeded";
+    case ICPB_ERR_NCCL: return "NCCL error";
     default: return "unknown status";
     }
 }
@@ -1304,36 +1348,15 @@ int icpb_frame_lift_band_device(icpb_ctx *ctx, const void *d_depth, int w, int h
                                 int band_capacity)
 {
     if (!ctx || !d_depth || !K || !d_band || w <= 0 || h <= 0) return ICPB_ERR_INVALID;
-    if (row0 < 0 || row1 <= row0 || row1 > h) return fail(ctx, ICPB_ERR_INVALID, "row band outside the image");
-    if ((long long)(row1 - row0) * w > band_capacity) return fail(ctx, ICPB_ERR_CAPACITY, "band smaller than its pixel count");
-    const uint16_t *band_depth = (const uint16_t *)d_depth + (size_t)row0 * w;
-    if (((uintptr_t)band_depth & 15) != 0) return fail(ctx, ICPB_ERR_INVALID, "band depth rows must start 16-byte aligned");
     CU(ctx, cudaSetDevice(ctx->device));
-    BackprojectArgs a;
-    a.depth = band_depth;
-    a.bgr = nullptr;
-    a.w = w; a.h = row1 - row0; a.K = *K;
-    a.rule = ICPB_SUB_NONE; a.rule_arg = 1; a.seed = 0;
-    a.keep_stream = nullptr; a.keep_stream_len = 0;
-    a.out = (float4 *)d_band + 1;           // row 0 is the header: point count in its first word
-    a.capacity = band_capacity;
-    a.n_tiles = backproject_tiles(w, a.h);
-    a.frames = 1;
-    a.v_offset = row0;
-    a.depth_stride = a.bgr_stride = a.out_stride = a.state_stride = 0;
     void *ts;
     int rc;
-    if ((rc = ws_get(ctx, WS_TILESTATE, sizeof(unsigned long long) * (3 * (size_t)a.n_tiles + 2), &ts, true))) return rc;
-    a.out_count = (int *)d_band;
-    a.tile_state = (unsigned long long *)ts + 2;
-    CU(ctx, cudaMemsetAsync(d_band, 0, sizeof(float4), ctx->stream));
+    const int tiles = backproject_tiles(w, row1 > row0 ? row1 - row0 : 1);
+    if ((rc = ws_get(ctx, WS_TILESTATE, sizeof(unsigned long long) * (3 * (size_t)tiles + 2), &ts, true))) return rc;
     const int sp = span_begin(ctx, ICPB_PROF_LIFT);
-    launch_backproject(a, ctx->stream);
-    if (R || t) launch_transform(a.out, band_capacity, R, t, R != nullptr, t != nullptr, ctx->stream, (const int *)d_band);
+    rc = icpb::api_lift_band(ctx, ctx->stream, ts, d_depth, w, h, row0, row1, K, R, t, d_band, band_capacity);
     span_end(ctx, sp);
-    ctx->launches += 1 + ((R || t) ? 1 : 0);
-    CU(ctx, cudaGetLastError());
-    return ICPB_OK;
+    return rc;
 }
 
 int icpb_map_integrate_bands_device(icpb_map *map, const void *d_bands, int world, int band_capacity, const float origin[3],

@@ -513,6 +513,18 @@ static bool fast_div_ok(float c)
     return e >= 127 - 60 && e <= 127 + 60 && m != 0x7fffffu;
 }
 
+// The two-pass kernels keep plain per-tile counts behind the status words.  A later chained launch over a LARGER image
+// reads those bytes as epoch-tagged status words, and a small count can spell a small epoch: zero them once the write
+// kernel is done (epoch 0 is never used, so a zero word reads as "not ready").
+static void clear_two_pass_counts(const BackprojectArgs &a, cudaStream_t s)
+{
+    unsigned long long *counts = a.tile_state + 2 * (long long)a.n_tiles;
+    const size_t bytes = sizeof(unsigned long long) * (size_t)a.n_tiles;
+    if (a.frames > 1 && a.state_stride > 0)
+        cudaMemset2DAsync(counts, sizeof(unsigned long long) * (size_t)a.state_stride, 0, bytes, (size_t)a.frames, s);
+    else cudaMemsetAsync(counts, 0, bytes, s);
+}
+
 void launch_backproject(const BackprojectArgs &a, cudaStream_t s, bool force_two_pass)
 {
     // per-process launch counter (atomic: contexts may be driven from different host threads); stale tile words never
@@ -557,6 +569,7 @@ void launch_backproject(const BackprojectArgs &a, cudaStream_t s, bool force_two
         else if (a.bgr) backproject_write_kernel<R, true, false><<<grid, kBpThreads, 0, s>>>(a, dv);        \
         else if (fast) backproject_write_kernel<R, false, true><<<grid, kBpThreads, 0, s>>>(a, dv);         \
         else backproject_write_kernel<R, false, false><<<grid, kBpThreads, 0, s>>>(a, dv);                  \
+        clear_two_pass_counts(a, s);                                                                        \
     } while (0)
     // Default: the single-launch chained-scan kernel (0.349 vs 0.359 ms for 256 frames).  The two-pass kernels never
     // wait on another CTA: they are the retry path when a chained launch reports that a predecessor never published

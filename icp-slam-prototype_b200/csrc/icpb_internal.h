@@ -220,6 +220,14 @@ void launch_map_tracked(const MapDev &m, int *table, const float4 *pts, int n, i
 void launch_map_rays(const MapDev &m, const PointSrc &src, const float origin[3], int delta_dec,
                      unsigned long long *visited, unsigned int *next_ray, int sm_count, cudaStream_t s);
 
+// ---- helpers of api.cu used by comm.cu ------------------------------------------------------------------------
+int api_fail(icpb_ctx *ctx, int status, const char *what, cudaError_t ce = cudaSuccess);
+int api_ws_get(icpb_ctx *ctx, int id, size_t bytes, void **out, bool zero_new = false);
+int api_span_begin(icpb_ctx *ctx, int kernel); // profiling spans on the context stream (icpb_ctx_profile_read)
+void api_span_end(icpb_ctx *ctx, int id);
+int api_lift_band(icpb_ctx *ctx, cudaStream_t stream, void *tile_state, const void *d_depth, int w, int h, int row0,
+                  int row1, const icpb_intrinsics *K, const float *R, const float *t, void *d_band, int band_capacity);
+
 } // namespace icpb
 
 // ---- handle definitions -----------------------------------------------------

@@ -19,7 +19,8 @@ POINT_DTYPE = np.dtype(
     [("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("c0", "u1"), ("c1", "u1"), ("c2", "u1"), ("pad", "u1")]
 )
 
-OK, ERR_INVALID, ERR_EMPTY, ERR_CUDA, ERR_CAPACITY = 0, 1, 2, 3, 4
+OK, ERR_INVALID, ERR_EMPTY, ERR_CUDA, ERR_CAPACITY, ERR_NCCL = 0, 1, 2, 3, 4, 5
+COMM_ID_BYTES = 128
 SUB_NONE, SUB_STRIDE, SUB_HASH, SUB_STREAM = 0, 1, 2, 3
 SOLVE_REFERENCE, SOLVE_KABSCH = 0, 1
 RULE_A, RULE_C = 0, 1
@@ -421,6 +422,86 @@ class Map:
     def upload(self, grid):
         grid = np.ascontiguousarray(grid, dtype=np.uint8)
         self.ctx.check(self.ctx.lib.icpb_map_upload(self.h, _p(grid), grid.size))
+
+
+# ---- multi-GPU (include/icpb200.h "multi-GPU"): NCCL communicator + z-slab map, all inside the library ---------------
+def comm_unique_id():
+    """128 bytes from ncclGetUniqueId (call on rank 0, hand to every rank by any transport)."""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    rc = load().icpb_comm_unique_id(buf)
+    if rc != OK:
+        raise IcpbError(rc, load().icpb_last_error(None).decode())
+    return bytes(buf)
+
+
+class Comm:
+    def __init__(self, ctx, world, rank, unique_id):
+        self.ctx, self.world, self.rank = ctx, int(world), int(rank)
+        h = C.c_void_p()
+        idb = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(unique_id)
+        ctx.check(ctx.lib.icpb_comm_create(ctx.h, self.world, self.rank, idb, C.byref(h)))
+        self.h = h
+
+    @staticmethod
+    def from_torch(ctx):
+        """Bootstrap over an initialised torch.distributed group: rank 0's unique id is broadcast as an object."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        box = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return Comm(ctx, world, rank, box[0])
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.icpb_comm_destroy(self.h)
+            self.h = None
+
+    def shard_range(self, n_items):
+        lo, hi = C.c_longlong(0), C.c_longlong(0)
+        self.ctx.check(self.ctx.lib.icpb_comm_shard_range(self.h, C.c_longlong(n_items), C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def allgather_host(self, arr):
+        """arr: contiguous numpy array, same shape on every rank -> [world, *arr.shape]."""
+        arr = np.ascontiguousarray(arr)
+        out = np.zeros((self.world,) + arr.shape, dtype=arr.dtype)
+        self.ctx.check(self.ctx.lib.icpb_comm_allgather_host(self.h, _p(arr), _p(out), C.c_longlong(arr.nbytes)))
+        return out
+
+
+class SlabMapC:
+    """icpb_slabmap: the rank's z-slab of a shared certainty map; comm=None for a single rank."""
+
+    def __init__(self, ctx, comm, dims, cell, w, h, bounds=None):
+        self.ctx, self.comm = ctx, comm
+        self.dims = tuple(int(d) for d in dims)
+        hnd = C.c_void_p()
+        d = (C.c_int * 3)(*self.dims)
+        b = None if bounds is None else (C.c_int * len(bounds))(*[int(x) for x in bounds])
+        ctx.check(ctx.lib.icpb_slabmap_create(ctx.h, comm.h if comm is not None else None, d, C.c_float(cell), b, int(w),
+                                              int(h), C.byref(hnd)))
+        self.h = hnd
+        mh, lo, hi = C.c_void_p(), C.c_int(0), C.c_int(0)
+        ctx.check(ctx.lib.icpb_slabmap_local(self.h, C.byref(mh), C.byref(lo), C.byref(hi)))
+        self.z_lo, self.z_hi = lo.value, hi.value
+        self.map = Map.__new__(Map)   # a view of the slab's map handle (owned by the slab map)
+        self.map.ctx, self.map.dims, self.map.z_lo, self.map.z_hi, self.map.h = ctx, self.dims, lo.value, hi.value, mh
+
+    def integrate_sequence_device(self, d_depths, frames, K, Rs, ts, delta_dec=25, delta_inc=25, frames_per_exchange=8):
+        Rs = np.ascontiguousarray(Rs, dtype=np.float32).reshape(frames, 9)
+        ts = np.ascontiguousarray(ts, dtype=np.float32).reshape(frames, 3)
+        self.ctx.check(self.ctx.lib.icpb_slabmap_integrate_sequence_device(
+            self.h, C.c_void_p(d_depths), int(frames), C.byref(K), _p(Rs), _p(ts), int(delta_dec), int(delta_inc),
+            int(frames_per_exchange)))
+
+    def download(self):
+        return self.map.download()
+
+    def close(self):
+        if self.h:
+            self.map.h = None
+            self.ctx.lib.icpb_slabmap_destroy(self.h)
+            self.h = None
 
 
 # ---- pose reporting (SURVEY.md 8f-4): scalar host functions of the library; q = [w, x, y, z], degrees -----------

@@ -32,12 +32,15 @@ enum {
     ICPB_ERR_INVALID = 1,   /* bad argument */
     ICPB_ERR_EMPTY = 2,     /* empty cloud where the reference would dereference begin() (icp.cpp:572) */
     ICPB_ERR_CUDA = 3,      /* CUDA runtime / no device */
-    ICPB_ERR_CAPACITY = 4   /* output does not fit the handle's capacity */
+    ICPB_ERR_CAPACITY = 4,  /* output does not fit the handle's capacity */
+    ICPB_ERR_NCCL = 5       /* NCCL missing (libnccl.so.2 could not be loaded) or a collective failed */
 };
 
 typedef struct icpb_ctx icpb_ctx;
 typedef struct icpb_cloud icpb_cloud;
 typedef struct icpb_map icpb_map;
+typedef struct icpb_comm icpb_comm;       /* one rank of a multi-GPU job: an NCCL communicator bound to a context */
+typedef struct icpb_slabmap icpb_slabmap; /* the rank's z-slab of a certainty map shared by the job */
 
 /* color_point_t, pointcloud.hpp:13-19 (cv::Point3f + cv::Vec3b + 1 pad = 16 B). */
 typedef struct {
@@ -286,6 +289,42 @@ int icpb_map_voxel_coords(const icpb_map *map, const float p[3], int v[3]);
 int icpb_map_download(icpb_map *map, uint8_t *out, long long capacity);
 int icpb_map_upload(icpb_map *map, const uint8_t *in, long long size);
 int icpb_map_size_bytes(const icpb_map *map, long long *size);
+
+/* ---- multi-GPU: one process (or host thread) per GPU, NCCL over NVLink ----------------------------
+ * The reference is single-process (its map is a file-scope global, icp.cpp:26); these entry points are what a host
+ * written against map.hpp needs to shard that map by z-slab, and to gather the results of registrations it has split
+ * over the ranks.  NCCL is loaded at run time (dlopen of libnccl.so.2): single-GPU users need no NCCL.
+ *
+ * Bootstrap: rank 0 calls icpb_comm_unique_id and hands the 128 bytes to every rank by any means (a file, MPI, a
+ * socket, torch.distributed); every rank then calls icpb_comm_create with the same bytes. */
+#define ICPB_COMM_ID_BYTES 128
+int icpb_comm_unique_id(uint8_t id[ICPB_COMM_ID_BYTES]);
+int icpb_comm_create(icpb_ctx *ctx, int world, int rank, const uint8_t id[ICPB_COMM_ID_BYTES], icpb_comm **out);
+int icpb_comm_destroy(icpb_comm *comm);
+int icpb_comm_rank(const icpb_comm *comm, int *world, int *rank);
+/* [lo, hi) of n_items owned by this rank: contiguous blocks, sizes differ by at most one (batches of registrations). */
+int icpb_comm_shard_range(const icpb_comm *comm, long long n_items, long long *lo, long long *hi);
+/* All-gather of `bytes` host bytes per rank (e.g. the poses of the rank's share of a batch), rank order.  Blocking. */
+int icpb_comm_allgather_host(icpb_comm *comm, const void *send, void *recv, long long bytes);
+
+/* The certainty map of map.hpp:20-37 sharded by z: rank g owns layers [bounds[g], bounds[g+1]) (bounds == NULL:
+ * equal layer counts) of a dims / cell grid.  Every rank lifts its band of image rows, the bands are all-gathered
+ * (the only exchange: <= 16 bytes per valid pixel per frame), and every rank walks every ray clipped to its slab
+ * (Map::rayTrace, map.cpp:272-439, semantics of DESIGN.md M4) and applies the endpoints it owns.  comm == NULL: a
+ * single rank owning the whole map, same code path without the collective. */
+int icpb_slabmap_create(icpb_ctx *ctx, icpb_comm *comm, const int dims[3], float cell, const int *bounds, int w, int h,
+                        icpb_slabmap **out);
+int icpb_slabmap_destroy(icpb_slabmap *sm);
+/* The rank's slab as an ordinary map handle (download / upload / clear); owned by the slab map. */
+int icpb_slabmap_local(icpb_slabmap *sm, icpb_map **map, int *z_lo, int *z_hi);
+/* `frames` device-resident w x h depth frames (u16, back to back) with their camera poses (R: frames x 9, t: frames x 3,
+ * camera-to-world, host arrays) -> ray decrements + endpoint increments of every frame, in order.  Nothing returns to
+ * the host: the call enqueues `frames_per_exchange` frames per all-gather, double buffered on three streams, so that
+ * the lift and the exchange of group g+1 overlap the walks of group g; it returns when everything is enqueued.
+ * Synchronise with icpb_ctx_sync (the slab map's streams are joined to the context stream at the end of the call). */
+int icpb_slabmap_integrate_sequence_device(icpb_slabmap *sm, const void *d_depths, int frames, const icpb_intrinsics *K,
+                                           const float *R, const float *t, int delta_dec, int delta_inc,
+                                           int frames_per_exchange);
 
 /* ---- pose reporting ------------------------------------
  * Scalar per-frame host arithmetic in the reference (SLAM.cpp:284-293); it stays host code here: no context,
