@@ -18,7 +18,7 @@ thread_local std::string g_create_error;
 enum WsId {
     WS_DESCS = 0, WS_STATES, WS_PARAMS, WS_TGT_SOA, WS_PM1, WS_PM2, WS_PG, WS_IDX, WS_DIST, WS_CHUNKS, WS_ALT,
     WS_IDX_TRACE, WS_DIST_TRACE, WS_MISC, WS_DEPTH, WS_BGR, WS_KEEP, WS_TILESTATE, WS_IMG_A, WS_IMG_B, WS_NORMALS,
-    WS_RT, WS_GRID_META, WS_GRID_COUNTS, WS_GRID_CURSOR, WS_GRID_SUMS, WS_GRID_SORTED, WS_GRID_BBOX, WS_GRID_HEAVY, WS_BATCHSTATE, WS_TRACK, WS_PA, WS_PM3, WS_PG2, WS_MLOG, WS_REJ_FLAG, WS_REJ_PTS, WS_FRAME, WS_PERM, WS_SORT_COUNTS, WS_SORT_SUMS, WS_GRID_NB, WS_GRID_SEED, WS_COUNT
+    WS_RT, WS_GRID_META, WS_GRID_COUNTS, WS_GRID_CURSOR, WS_GRID_SUMS, WS_GRID_SORTED, WS_GRID_BBOX, WS_GRID_HEAVY, WS_BATCHSTATE, WS_TRACK, WS_PA, WS_PM3, WS_PG2, WS_MLOG, WS_REJ_FLAG, WS_REJ_PTS, WS_FRAME, WS_PERM, WS_SORT_COUNTS, WS_SORT_SUMS, WS_GRID_NB, WS_GRID_SEED, WS_GRID_BOX, WS_COUNT
 };
 
 int fail(icpb_ctx *ctx, int status, const char *what, cudaError_t ce = cudaSuccess)
@@ -229,7 +229,7 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
     int *d_gcounts = nullptr, *d_gcursor = nullptr, *d_gsums = nullptr;
     float4 *d_gsorted = nullptr;
     int *d_gheavy = nullptr;
-    float4 *d_gnb = nullptr, *d_gseed = nullptr;
+    float4 *d_gnb = nullptr, *d_gseed = nullptr, *d_gbox = nullptr;
     long long grid_launches = 0;
     if (grid_mode) {
         const int m = regs[0].target->n;
@@ -285,8 +285,9 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         if ((rc = ws_get(ctx, WS_GRID_SORTED, sizeof(float4) * (size_t)m, (void **)&d_gsorted))) return rc;
         if ((rc = ws_get(ctx, WS_GRID_HEAVY, sizeof(int) * ((size_t)regs[0].data->n + passes + 8), (void **)&d_gheavy))) return rc;
         if ((rc = ws_get(ctx, WS_GRID_NB, sizeof(float4) * (size_t)regs[0].data->n, (void **)&d_gnb))) return rc;
+        if ((rc = ws_get(ctx, WS_GRID_BOX, sizeof(float4) * 2 * (size_t)gm.ncells, (void **)&d_gbox))) return rc;
         if ((rc = ws_get(ctx, WS_GRID_SEED, sizeof(float4) * ((size_t)regs[0].data->n + 32), (void **)&d_gseed))) return rc;
-        grid_launches = 7;
+        grid_launches = 8;
     }
 
     // host staging: descs | states | params in one pinned block
@@ -325,6 +326,7 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         d.grid = d_gmeta;
         d.gsorted = d_gsorted;
         d.gstart = d_gcounts;
+        d.gbox = d_gbox;
         d.gnb = d_gnb;
         d.gseed = d_gseed;
         d.gheavy = d_gheavy ? d_gheavy + passes + 8 : nullptr;
@@ -359,18 +361,16 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
     CU(ctx, cudaEventRecord(ctx->ev0, st));
     if ((filter == kFilterWarp && !grid_mode) || (grid_mode && grid_sorted)) {
         // Morton order of every data cloud, once per registration (inside the timed region)
-        const int bits = spatial_sort_bits(max_n);
-        int *d_scnt, *d_ssum;
-        if ((rc = ws_get(ctx, WS_SORT_COUNTS, sizeof(int) * ((size_t)spatial_sort_cells(bits) + 1) * count, (void **)&d_scnt))) return rc;
-        if ((rc = ws_get(ctx, WS_SORT_SUMS, sizeof(int) * (size_t)spatial_sort_sum_slots(bits) * count, (void **)&d_ssum))) return rc;
-        launch_spatial_sort(d_descs, count, max_n, bits, d_scnt, d_ssum, st);
-        launches += 5;
+        int *d_swork;
+        if ((rc = ws_get(ctx, WS_SORT_COUNTS, sizeof(int) * spatial_sort_work_ints(max_n, count), (void **)&d_swork))) return rc;
+        launch_spatial_sort(d_descs, count, max_n, d_swork, st);
+        launches += 15;
     }
     if (grid_mode) {
         CU(ctx, cudaMemcpyAsync(d_gmeta, &gm, sizeof(gm), cudaMemcpyHostToDevice, st));
         CU(ctx, cudaMemsetAsync(d_gcounts, 0, sizeof(int) * ((size_t)gm.ncells + 1), st));
         CU(ctx, cudaMemsetAsync(d_gheavy, 0, sizeof(int) * ((size_t)passes + 8), st));
-        launch_grid_build(h_descs[0].tgt, h_descs[0].m, gm, d_gcounts, d_gcursor, d_gsums, d_gsorted, st);
+        launch_grid_build(h_descs[0].tgt, h_descs[0].m, gm, d_gcounts, d_gcursor, d_gsums, d_gsorted, d_gbox, st);
         launches += grid_launches;
     } else {
         for (int b = 0; b < count; ++b) {

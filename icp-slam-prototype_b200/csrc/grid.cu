@@ -164,8 +164,26 @@ void launch_grid_bbox(const float4 *tgt, int m, unsigned int *bbox, cudaStream_t
 }
 
 // counts: ncells+1 ints, zeroed by the caller; on return counts[c] = start of cell c, counts[ncells] = m.
+// Tight bounding box of the targets of every cell (min / max of their coordinates, exact): the cooperative search
+// prunes a cell by the distance to this box, not to the cell's cube -- a surface patch fills a sliver of its cell.
+// One warp per group of 32 cells, lane = cell; empty cells get an inverted box.
+__global__ void grid_boxes_kernel(const float4 *__restrict__ sorted, const int *__restrict__ start, int ncells, float4 *boxes)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    const int t0 = start[c], t1 = start[c + 1];
+    float lx = CUDART_INF_F, ly = CUDART_INF_F, lz = CUDART_INF_F, hx = -CUDART_INF_F, hy = -CUDART_INF_F, hz = -CUDART_INF_F;
+    for (int t = t0; t < t1; ++t) {
+        const float4 p = __ldg(&sorted[t]);
+        lx = fminf(lx, p.x); ly = fminf(ly, p.y); lz = fminf(lz, p.z);
+        hx = fmaxf(hx, p.x); hy = fmaxf(hy, p.y); hz = fmaxf(hz, p.z);
+    }
+    boxes[2 * (size_t)c] = make_float4(lx, ly, lz, 0.f);
+    boxes[2 * (size_t)c + 1] = make_float4(hx, hy, hz, 0.f);
+}
+
 void launch_grid_build(const float4 *tgt, int m, const GridMeta &g, int *counts, int *cursor, int *block_sums,
-                       float4 *sorted, cudaStream_t s)
+                       float4 *sorted, float4 *boxes, cudaStream_t s)
 {
     const int n = g.ncells + 1;
     grid_count_kernel<<<(m + 255) / 256, 256, 0, s>>>(tgt, m, g, counts);
@@ -175,48 +193,12 @@ void launch_grid_build(const float4 *tgt, int m, const GridMeta &g, int *counts,
     scan_apply_kernel<<<nblocks, kScanThreads, 0, s>>>(counts, n, block_sums);
     cudaMemcpyAsync(cursor, counts, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, s);
     grid_scatter_kernel<<<(m + 255) / 256, 256, 0, s>>>(tgt, m, g, cursor, sorted);
+    if (boxes) grid_boxes_kernel<<<(g.ncells + 255) / 256, 256, 0, s>>>(sorted, counts, g.ncells, boxes);
 }
 
-// ---- spatial order of the QUERIES for the warp-centred brute-force filter (nn.cu) --------------------------------
-// Counting sort of every data cloud of the batch by the Morton code of a 2^bits-cubed grid around the cloud's first
-// point (clamped: a far-away point only lands in a border cell).  The order is a performance matter only -- it decides
-// which queries share a warp, never what any query's result is -- so neither the clamping nor the arbitrary order
-// inside a cell matters.  d.perm[slot] = original index.  blockIdx.y / .z = registration.
-__device__ __forceinline__ unsigned int spread3(unsigned int v) // 6 bits -> every third bit
-{
-    v &= 0x3fu;
-    v = (v | (v << 8)) & 0x300fu;
-    v = (v | (v << 4)) & 0x30c3u;
-    v = (v | (v << 2)) & 0x9249u;
-    return v;
-}
-
-__device__ __forceinline__ int sort_key(const float4 p, const float4 ref, int bits, float cell)
-{
-    const int half = 1 << (bits - 1);
-    const int cx = min(max((int)floorf((p.x - ref.x) / cell) + half, 0), 2 * half - 1);
-    const int cy = min(max((int)floorf((p.y - ref.y) / cell) + half, 0), 2 * half - 1);
-    const int cz = min(max((int)floorf((p.z - ref.z) / cell) + half, 0), 2 * half - 1);
-    return (int)(spread3((unsigned)cx) | (spread3((unsigned)cy) << 1) | (spread3((unsigned)cz) << 2));
-}
-
-__global__ void sort_count_kernel(const RegDesc *__restrict__ descs, int bits, float cell, int *counts, int stride)
-{
-    const RegDesc &d = descs[blockIdx.y];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= d.n) return;
-    const float4 *pts = d.D[0];
-    atomicAdd(&counts[(size_t)blockIdx.y * stride + sort_key(pts[i], pts[0], bits, cell)], 1);
-}
-
-__global__ void sort_scatter_kernel(const RegDesc *__restrict__ descs, int bits, float cell, int *cursor, int stride)
-{
-    const RegDesc &d = descs[blockIdx.y];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= d.n) return;
-    const float4 *pts = d.D[0];
-    const_cast<int *>(d.perm)[atomicAdd(&cursor[(size_t)blockIdx.y * stride + sort_key(pts[i], pts[0], bits, cell)], 1)] = i;
-}
+// ---- spatial order of the QUERIES (warp-centred brute-force filter of nn.cu, cooperative grid search) ---------------
+// The order is a performance matter only -- it decides which queries share a warp, never what any query's result is.
+// d.perm[slot] = original index.  blockIdx.y = registration.
 
 // batched forms of the three scan kernels: blockIdx.y = registration, arrays `stride` / `sums_stride` apart
 __global__ void __launch_bounds__(kScanThreads) scan_reduce_batch_kernel(const int *in, int n, int stride, int *block_sums,
@@ -266,25 +248,137 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_batch_kernel(int *dat
     }
 }
 
-// 12.5 cm cells (64^3) for dense clouds, 25 cm (32^3) for sparse ones: a warp's few hundred queries fill about a cell
-int spatial_sort_bits(int max_n) { return max_n >= 50000 ? 6 : 5; }
-int spatial_sort_cells(int bits) { return 1 << (3 * bits); }
-int spatial_sort_sum_slots(int bits) { return (spatial_sort_cells(bits) + 1 + kScanTile - 1) / kScanTile + 1; }
+// ---- stable LSD radix sort of the queries by a 24-bit Morton key ----------------------------------------------------
+// Three passes of 8 bits.  Every pass is a per-block digit histogram (block = 256 consecutive elements), an exclusive
+// scan over (digit, block) and a scatter that ranks equal digits inside the block in element order (__match_any +
+// per-warp counts): stable, hence DETERMINISTIC -- slot k of d.perm holds the same query in every run (the counting
+// sort with an atomic cursor that this replaces ordered the queries of a cell by arrival).  8 bits per axis over 8 m
+// around the cloud's first point: 3.1 cm cells, ties in original (raster) order, so the eight queries of a search
+// group and the 32 of a warp are close neighbours.
+constexpr int kRsBlock = 256;
 
-// counts: batch x (cells + 1) ints (zeroed here); block_sums: batch x spatial_sort_sum_slots ints.
-void launch_spatial_sort(const RegDesc *descs, int batch, int max_n, int bits, int *counts, int *block_sums, cudaStream_t s)
+__device__ __forceinline__ unsigned int spread3_8(unsigned int v) // 8 bits -> every third bit
 {
-    const int nc = spatial_sort_cells(bits) + 1;
-    const int ss = spatial_sort_sum_slots(bits);
-    const float cell = 8.0f / (float)(1 << bits);
-    cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)nc * batch, s);
-    dim3 pgrid((max_n + 255) / 256, batch);
-    sort_count_kernel<<<pgrid, 256, 0, s>>>(descs, bits, cell, counts, nc);
-    const int nblocks = (nc + kScanTile - 1) / kScanTile;
-    scan_reduce_batch_kernel<<<dim3(nblocks, batch), kScanThreads, 0, s>>>(counts, nc, nc, block_sums, ss);
-    scan_sums_batch_kernel<<<batch, kScanThreads, 0, s>>>(block_sums, nblocks, ss);
-    scan_apply_batch_kernel<<<dim3(nblocks, batch), kScanThreads, 0, s>>>(counts, nc, nc, block_sums, ss);
-    sort_scatter_kernel<<<pgrid, 256, 0, s>>>(descs, bits, cell, counts, nc); // counts doubles as the cursor: not reused
+    v &= 0xffu;
+    v = (v | (v << 8)) & 0x0000f00fu;
+    v = (v | (v << 4)) & 0x000c30c3u;
+    v = (v | (v << 2)) & 0x00249249u;
+    return v;
+}
+
+__device__ __forceinline__ unsigned int morton24(const float4 p, const float4 ref)
+{
+    const float cell = 8.0f / 256.0f;
+    const int cx = min(max((int)floorf((p.x - ref.x) / cell) + 128, 0), 255);
+    const int cy = min(max((int)floorf((p.y - ref.y) / cell) + 128, 0), 255);
+    const int cz = min(max((int)floorf((p.z - ref.z) / cell) + 128, 0), 255);
+    return spread3_8((unsigned)cx) | (spread3_8((unsigned)cy) << 1) | (spread3_8((unsigned)cz) << 2);
+}
+
+// keys + identity values, and the digit histogram of pass 0
+__global__ void __launch_bounds__(kRsBlock) rsort_keys_kernel(const RegDesc *__restrict__ descs, unsigned int *keys, int *vals,
+                                                              int stride, int *hist, int nblk)
+{
+    __shared__ int s_h[256];
+    const RegDesc &d = descs[blockIdx.y];
+    const int i = blockIdx.x * kRsBlock + threadIdx.x;
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    if (i < d.n) {
+        const float4 *pts = d.D[0];
+        const unsigned int key = morton24(pts[i], pts[0]);
+        keys[(size_t)blockIdx.y * stride + i] = key;
+        vals[(size_t)blockIdx.y * stride + i] = i;
+        atomicAdd(&s_h[key & 255u], 1);
+    }
+    __syncthreads();
+    hist[((size_t)blockIdx.y * 256 + threadIdx.x) * nblk + blockIdx.x] = s_h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kRsBlock) rsort_hist_kernel(const RegDesc *__restrict__ descs, const unsigned int *keys, int stride,
+                                                              int shift, int *hist, int nblk)
+{
+    __shared__ int s_h[256];
+    const int n = descs[blockIdx.y].n;
+    const int i = blockIdx.x * kRsBlock + threadIdx.x;
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    if (i < n) atomicAdd(&s_h[(keys[(size_t)blockIdx.y * stride + i] >> shift) & 255u], 1);
+    __syncthreads();
+    hist[((size_t)blockIdx.y * 256 + threadIdx.x) * nblk + blockIdx.x] = s_h[threadIdx.x];
+}
+
+// hist holds the exclusive scan over (digit, block).  out_vals == nullptr on the last pass: the values go to d.perm.
+__global__ void __launch_bounds__(kRsBlock) rsort_scatter_kernel(const RegDesc *__restrict__ descs, const unsigned int *keys,
+                                                                 const int *vals, unsigned int *out_keys, int *out_vals,
+                                                                 int stride, int shift, const int *hist, int nblk)
+{
+    __shared__ int s_cnt[kRsBlock / 32][256];
+    const RegDesc &d = descs[blockIdx.y];
+    const int n = d.n;
+    const int i = blockIdx.x * kRsBlock + threadIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < kRsBlock / 32; ++k) s_cnt[k][threadIdx.x] = 0;
+    __syncthreads();
+    const bool valid = i < n;
+    unsigned int key = 0;
+    int val = 0;
+    if (valid) { key = keys[(size_t)blockIdx.y * stride + i]; val = vals[(size_t)blockIdx.y * stride + i]; }
+    const unsigned int digit = valid ? ((key >> shift) & 255u) : 256u; // invalid lanes match only each other
+    const unsigned peers = __match_any_sync(0xffffffffu, digit);
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    if (valid && rank == 0) s_cnt[w][digit] = __popc(peers);
+    __syncthreads();
+    { // exclusive prefix over the block's warps, one thread per digit
+        int run = 0;
+#pragma unroll
+        for (int k = 0; k < kRsBlock / 32; ++k) { const int c = s_cnt[k][threadIdx.x]; s_cnt[k][threadIdx.x] = run; run += c; }
+    }
+    __syncthreads();
+    if (!valid) return;
+    const int pos = hist[((size_t)blockIdx.y * 256 + digit) * nblk + blockIdx.x] + s_cnt[w][digit] + rank;
+    if (out_vals) {
+        out_keys[(size_t)blockIdx.y * stride + pos] = key;
+        out_vals[(size_t)blockIdx.y * stride + pos] = val;
+    } else {
+        const_cast<int *>(d.perm)[pos] = val;
+    }
+}
+
+// work: batch * (4 * stride + 256 * nblk + sums) ints, laid out by spatial_sort_layout()
+int spatial_sort_stride(int max_n) { return (max_n + kRsBlock - 1) / kRsBlock * kRsBlock; }
+int spatial_sort_blocks(int max_n) { return (max_n + kRsBlock - 1) / kRsBlock; }
+int spatial_sort_sum_slots(int max_n) { return (256 * spatial_sort_blocks(max_n) + kScanTile - 1) / kScanTile + 1; }
+size_t spatial_sort_work_ints(int max_n, int batch)
+{
+    return (size_t)batch * (4 * (size_t)spatial_sort_stride(max_n) + 256 * (size_t)spatial_sort_blocks(max_n) +
+                            (size_t)spatial_sort_sum_slots(max_n));
+}
+
+void launch_spatial_sort(const RegDesc *descs, int batch, int max_n, int *work, cudaStream_t s)
+{
+    const int stride = spatial_sort_stride(max_n), nblk = spatial_sort_blocks(max_n), ss = spatial_sort_sum_slots(max_n);
+    unsigned int *keysA = (unsigned int *)work, *keysB = keysA + (size_t)batch * stride;
+    int *valsA = (int *)(keysB + (size_t)batch * stride), *valsB = valsA + (size_t)batch * stride;
+    int *hist = valsB + (size_t)batch * stride, *sums = hist + (size_t)batch * 256 * nblk;
+    const int nscan = 256 * nblk;
+    const int sblocks = (nscan + kScanTile - 1) / kScanTile;
+    dim3 grid(nblk, batch);
+    auto scan = [&]() {
+        scan_reduce_batch_kernel<<<dim3(sblocks, batch), kScanThreads, 0, s>>>(hist, nscan, nscan, sums, ss);
+        scan_sums_batch_kernel<<<batch, kScanThreads, 0, s>>>(sums, sblocks, ss);
+        scan_apply_batch_kernel<<<dim3(sblocks, batch), kScanThreads, 0, s>>>(hist, nscan, nscan, sums, ss);
+    };
+    rsort_keys_kernel<<<grid, kRsBlock, 0, s>>>(descs, keysA, valsA, stride, hist, nblk);
+    scan();
+    rsort_scatter_kernel<<<grid, kRsBlock, 0, s>>>(descs, keysA, valsA, keysB, valsB, stride, 0, hist, nblk);
+    rsort_hist_kernel<<<grid, kRsBlock, 0, s>>>(descs, keysB, stride, 8, hist, nblk);
+    scan();
+    rsort_scatter_kernel<<<grid, kRsBlock, 0, s>>>(descs, keysB, valsB, keysA, valsA, stride, 8, hist, nblk);
+    rsort_hist_kernel<<<grid, kRsBlock, 0, s>>>(descs, keysA, stride, 16, hist, nblk);
+    scan();
+    rsort_scatter_kernel<<<grid, kRsBlock, 0, s>>>(descs, keysA, valsA, nullptr, nullptr, stride, 16, hist, nblk);
 }
 
 // ---- the search ------------------------------------------------------------------------------------------------
@@ -566,6 +660,10 @@ __device__ __forceinline__ float sqrt_approx(float x)
 #endif
 constexpr int kCoopCap = ICPB_COOP_CAP;   // candidates per warp batch (20 B each in shared memory)
 constexpr int kCoopWarps = 4;
+#ifndef ICPB_COOP_GROUP
+#define ICPB_COOP_GROUP 8
+#endif
+constexpr int kCoopGroup = ICPB_COOP_GROUP; // lanes per bounding sphere of the region test (1 = every query's own ball)
 
 struct CoopBuf {
     float xs[kCoopCap], ys[kCoopCap], zs[kCoopCap], ns[kCoopCap]; // centred candidates, SoA
@@ -678,6 +776,7 @@ __global__ void __launch_bounds__(32 * kCoopWarps) nn_grid_coop_kernel(const Reg
     const GridMeta g = *d.grid;
     const float4 *__restrict__ sorted = d.gsorted;
     const int *__restrict__ gstart = d.gstart;
+    const float4 *__restrict__ gbox = d.gbox;
 
     // P2 fused into the query load (pointcloud.cpp:321-359), as in nn_grid_kernel
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -731,7 +830,6 @@ __global__ void __launch_bounds__(32 * kCoopWarps) nn_grid_coop_kernel(const Reg
     const float A = ((ax * ax + ay * ay) + az * az) * 1.000001f;
     const float qx = -2.f * ax, qy = -2.f * ay, qz = -2.f * az; // W = |t'|^2 - 2 a'.t'
 
-    const float inv_h = 1.0f / g.h;
     const int nx = g.dim[0], ny = g.dim[1], nz = g.dim[2];
 
     for (int round = 0; round < 8; ++round) {
@@ -740,7 +838,26 @@ __global__ void __launch_bounds__(32 * kCoopWarps) nn_grid_coop_kernel(const Reg
         if (!done && rr > coop_r) { deferred = true; done = true; }
         const unsigned active = __ballot_sync(full, !done);
         if (active == 0u) break;
-        const float reach2 = rr * rr * 1.00001f + 1e-30f;
+        // ---- the union of the active balls, over-approximated by one sphere per group of kCoopGroup consecutive lanes
+        //      (Morton neighbours): centre = middle of the group's queries, radius = the farthest reach of a member
+        float glx = done ? CUDART_INF_F : p.x, ghx = done ? -CUDART_INF_F : p.x;
+        float gly = done ? CUDART_INF_F : p.y, ghy = done ? -CUDART_INF_F : p.y;
+        float glz = done ? CUDART_INF_F : p.z, ghz = done ? -CUDART_INF_F : p.z;
+#pragma unroll
+        for (int off = 1; off < kCoopGroup; off <<= 1) {
+            glx = fminf(glx, __shfl_xor_sync(full, glx, off)); ghx = fmaxf(ghx, __shfl_xor_sync(full, ghx, off));
+            gly = fminf(gly, __shfl_xor_sync(full, gly, off)); ghy = fmaxf(ghy, __shfl_xor_sync(full, ghy, off));
+            glz = fminf(glz, __shfl_xor_sync(full, glz, off)); ghz = fmaxf(ghz, __shfl_xor_sync(full, ghz, off));
+        }
+        const float scx = 0.5f * glx + 0.5f * ghx, scy = 0.5f * gly + 0.5f * ghy, scz = 0.5f * glz + 0.5f * ghz;
+        float sr = -1.f; // no active member: the sphere needs nothing
+        if (!done) {
+            const float ex = p.x - scx, ey = p.y - scy, ez = p.z - scz;
+            sr = sqrtf((ex * ex + ey * ey) + ez * ez) * 1.00001f + rr;
+        }
+#pragma unroll
+        for (int off = 1; off < kCoopGroup; off <<= 1) sr = fmaxf(sr, __shfl_xor_sync(full, sr, off));
+        const float sr2 = sr < 0.f ? -1.f : (sr * sr) * 1.0001f + 1e-12f;
         // box of cells around the active balls
         const float ext = rr * 1.00001f + 2e-3f * g.h;
         int bx0 = done ? 0x7fffffff : cell_axis(p.x - ext, g.mn[0], g.h, nx), bx1 = done ? -1 : cell_axis(p.x + ext, g.mn[0], g.h, nx);
@@ -749,39 +866,35 @@ __global__ void __launch_bounds__(32 * kCoopWarps) nn_grid_coop_kernel(const Reg
         bx0 = __reduce_min_sync(full, bx0); bx1 = __reduce_max_sync(full, bx1);
         by0 = __reduce_min_sync(full, by0); by1 = __reduce_max_sync(full, by1);
         bz0 = __reduce_min_sync(full, bz0); bz1 = __reduce_max_sync(full, bz1);
-        const int nyb = by1 - by0 + 1, nzb = bz1 - bz0 + 1;
-        const int nrows = nyb * nzb;
+        const int nxb = bx1 - bx0 + 1, nyb = by1 - by0 + 1, nzb = bz1 - bz0 + 1;
+        const int nbox = nxb * nyb * nzb;
         const bool live = !done; // a lane that is done must not pick anything up any more
         int fill = 0;
-        for (int rbase = 0; rbase < nrows; rbase += 32) {
-            // ---- lane <-> row: union over the active balls of the cells this row must contribute
-            const int row = rbase + lane;
-            const bool rv = row < nrows;
-            const int yy = by0 + (rv ? row % nyb : 0), zz = bz0 + (rv ? row / nyb : 0);
-            const float ylo = g.mn[1] + yy * g.h, zlo = g.mn[2] + zz * g.h;
-            int amin = 0x7fffffff, bmax = -1;
-            for (unsigned rest = active; rest; rest &= rest - 1) {
-                const int j = __ffs(rest) - 1;
-                const float jx = __shfl_sync(full, p.x, j), jy = __shfl_sync(full, p.y, j), jz = __shfl_sync(full, p.z, j);
-                const float jr2 = __shfl_sync(full, reach2, j);
-                const float gy = fmaxf(axis_gap(jy, ylo, g.h), 0.f), gz = fmaxf(axis_gap(jz, zlo, g.h), 0.f);
-                const float gyz2 = gy * gy + gz * gz;
-                if (gyz2 <= jr2) {
-                    const float rx = sqrt_approx(jr2 - gyz2) * 1.0001f + 2e-3f * g.h;
-                    const int a = (int)floorf((jx - rx - g.mn[0]) * inv_h), b = (int)floorf((jx + rx - g.mn[0]) * inv_h);
-                    amin = min(amin, a); bmax = max(bmax, b);
-                }
-            }
-            amin = max(amin, 0); bmax = min(bmax, nx - 1);
+        for (int cbase = 0; cbase < nbox; cbase += 32) {
+            // ---- lane <-> cell of the box: needed when the tight box of its targets reaches into one of the spheres
+            const int ci = cbase + lane;
             int t0 = 0, len = 0;
-            if (rv && amin <= bmax) {
-                const int rowbase = (zz * ny + yy) * nx;
-                t0 = __ldg(&gstart[rowbase + amin]);
-                len = __ldg(&gstart[rowbase + bmax + 1]) - t0;
+            float4 blo = make_float4(0.f, 0.f, 0.f, 0.f), bhi = blo;
+            if (ci < nbox) {
+                const int xx = bx0 + ci % nxb, yz = ci / nxb;
+                const int cell = ((bz0 + yz / nyb) * ny + (by0 + yz % nyb)) * nx + xx;
+                t0 = __ldg(&gstart[cell]);
+                len = __ldg(&gstart[cell + 1]) - t0;
+                if (len > 0) { blo = __ldg(&gbox[2 * (size_t)cell]); bhi = __ldg(&gbox[2 * (size_t)cell + 1]); }
             }
-            // ---- copy the runs into the batch, centred; a full batch is evaluated at once
-            for (unsigned rows = __ballot_sync(full, len > 0); rows; rows &= rows - 1) {
-                const int r = __ffs(rows) - 1;
+            bool need = false;
+#pragma unroll
+            for (int s0 = 0; s0 < 32; s0 += kCoopGroup) {
+                const float sx = __shfl_sync(full, scx, s0), sy = __shfl_sync(full, scy, s0), sz = __shfl_sync(full, scz, s0);
+                const float s2 = __shfl_sync(full, sr2, s0);
+                const float dx = fmaxf(fmaxf(blo.x - sx, sx - bhi.x), 0.f), dy = fmaxf(fmaxf(blo.y - sy, sy - bhi.y), 0.f);
+                const float dz = fmaxf(fmaxf(blo.z - sz, sz - bhi.z), 0.f);
+                need |= ((dx * dx + dy * dy) + dz * dz) <= s2;
+            }
+            if (len <= 0) need = false;
+            // ---- copy the needed cells into the batch, centred; a full batch is evaluated at once
+            for (unsigned cells = __ballot_sync(full, need); cells; cells &= cells - 1) {
+                const int r = __ffs(cells) - 1;
                 int pos = __shfl_sync(full, t0, r), remaining = __shfl_sync(full, len, r);
                 while (remaining > 0) {
                     const int take = min(remaining, kCoopCap - fill);

@@ -117,6 +117,7 @@ struct RegDesc {
     const GridMeta *grid;    // ICPB_NN_GRID only
     const float4 *gsorted;   // targets sorted by cell, w = original index
     const int *gstart;       // [ncells+1] first sorted slot of every cell
+    const float4 *gbox;      // [2 * ncells] tight bounding box of every cell's targets: (lo.xyz, -), (hi.xyz, -)
     float4 *gnb;             // [n] cooperative search: the nearest target's coordinates, w = its distance (original query order)
     float4 *gseed;           // [n] the same in SORTED slot order, w = its index bits: the next pass's search ball
     int *gheavy;             // [n] queries still open after the per-thread shells
@@ -142,13 +143,11 @@ void launch_center(const float4 *pts, int n, double *chunk_sums, double *out3, u
 void launch_fp32_peak(float *out, int blocks, int threads, int iters, cudaStream_t s);
 void launch_grid_bbox(const float4 *tgt, int m, unsigned int *bbox, cudaStream_t s);
 void launch_grid_build(const float4 *tgt, int m, const GridMeta &g, int *counts, int *cursor, int *block_sums,
-                       float4 *sorted, cudaStream_t s);
+                       float4 *sorted, float4 *boxes, cudaStream_t s);
 // coop_r > 0: warp-cooperative search for balls up to coop_r metres (grid.cu); 0: the per-thread shell walk
 void launch_nn_grid(const RegDesc *descs, int batch, int max_n, int pass, int sm_count, cudaStream_t s, float coop_r);
-int spatial_sort_bits(int max_n);
-int spatial_sort_cells(int bits);
-int spatial_sort_sum_slots(int bits);
-void launch_spatial_sort(const RegDesc *descs, int batch, int max_n, int bits, int *counts, int *block_sums, cudaStream_t s);
+size_t spatial_sort_work_ints(int max_n, int batch); // ints of scratch launch_spatial_sort needs
+void launch_spatial_sort(const RegDesc *descs, int batch, int max_n, int *work, cudaStream_t s); // 15 launches
 
 struct BackprojectArgs {
     const uint16_t *depth;

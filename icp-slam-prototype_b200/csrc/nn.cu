@@ -984,6 +984,105 @@ __device__ __forceinline__ void solve_step_local(IcpState *st, const IcpParamsDe
     st->iterations = i + 1;
 }
 
+// Everything after the association of a chunk is known: per-query outputs, CANON-3 sums, and in the last CTA of the
+// registration the second summation level and the solve.  Shared by nn_finalize_kernel and nn_finalize_coop_kernel.
+struct FinalizeShared {
+    double w[kChunk / 32][kTerms];
+    double tot[kTerms];
+    int last;
+};
+
+__device__ __forceinline__ void finalize_tail(const RegDesc &d, IcpState *st, const IcpParamsDev *__restrict__ prm, int pass,
+                                              int chunk, int nchunks, int tid, bool valid, int i, int n, const float4 a,
+                                              int best_i, float best_d, const float4 best_b, bool have_b, int n_amb,
+                                              FinalizeShared &sh)
+{
+    double (&s_w)[kChunk / 32][kTerms] = sh.w;
+    double (&s_tot)[kTerms] = sh.tot;
+    int &s_last = sh.last;
+    if (valid) {
+        d.idx[i] = best_i;
+        d.dist[i] = best_d;
+        if (d.idx_trace) d.idx_trace[(size_t)pass * n + i] = best_i;
+        if (d.dist_trace) d.dist_trace[(size_t)pass * n + i] = best_d;
+        if (d.rej_flag) { // icp.cpp:507-509: the rejects of every pass accumulate
+            const bool rejected = !(best_d < prm->max_nn_distance);
+            d.rej_flag[(size_t)pass * n + i] = rejected ? 1 : 0;
+            if (rejected) d.rej_pts[(size_t)pass * n + i] = a;
+        }
+    }
+
+    // ---- association sums (CANON-3 level 1)
+    // one term at a time (value -> fold -> shared memory): twenty live doubles would cost forty registers per thread
+    const bool accepted = valid && (best_d < prm->max_nn_distance); // icp.cpp:553
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (accepted) b = have_b ? best_b : d.tgt[best_i];
+    auto term = [&](int k) -> double {
+        if (!accepted) return 0.0;
+        switch (k) {
+        case 0: return a.x; case 1: return a.y; case 2: return a.z;
+        case 3: return b.x; case 4: return b.y; case 5: return b.z;
+        case 6: return (double)b.x * (double)a.x; case 7: return (double)b.x * (double)a.y; case 8: return (double)b.x * (double)a.z;
+        case 9: return (double)b.y * (double)a.x; case 10: return (double)b.y * (double)a.y; case 11: return (double)b.y * (double)a.z;
+        case 12: return (double)b.z * (double)a.x; case 13: return (double)b.z * (double)a.y; case 14: return (double)b.z * (double)a.z;
+        case 15: return best_d;
+        case 16: return (double)(a.x - b.x); case 17: return (double)(a.y - b.y); case 18: return (double)(a.z - b.z);
+        default: return 1.0;
+        }
+    };
+#pragma unroll
+    for (int k = 0; k < kTerms; ++k) {
+        const double v = warp_fold(term(k));
+        if ((tid & 31) == 0) s_w[tid >> 5][k] = v;
+    }
+    __syncthreads();
+    if (tid < kTerms) {
+        double s = s_w[0][tid];
+        for (int wv = 1; wv < kChunk / 32; ++wv) s = s + s_w[wv][tid];
+        d.chunk_sums[(size_t)chunk * kTerms + tid] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        if (n_amb) atomicAdd(&st->rescans, n_amb);
+        unsigned int ticket = atomicAdd(&st->block_counter, 1u);
+        s_last = (ticket == (unsigned int)(nchunks - 1));
+    }
+    __syncthreads();
+    if (!s_last) return;
+
+    // ---- last CTA of this registration: CANON-3 level 2, then the solve
+    __threadfence();
+    {
+        double acc[kTerms];
+#pragma unroll
+        for (int k = 0; k < kTerms; ++k) acc[k] = 0.0;
+        for (int c = tid; c < nchunks; c += kChunk) {
+            double v[kTerms];
+#pragma unroll
+            for (int k = 0; k < kTerms; ++k) v[k] = __ldcg(&d.chunk_sums[(size_t)c * kTerms + k]); // issued together
+#pragma unroll
+            for (int k = 0; k < kTerms; ++k) acc[k] = acc[k] + v[k];
+        }
+#pragma unroll
+        for (int k = 0; k < kTerms; ++k) {
+            double v = warp_fold(acc[k]);
+            if ((tid & 31) == 0) s_w[tid >> 5][k] = v;
+        }
+    }
+    __syncthreads();
+    if (tid < kTerms) {
+        double s = s_w[0][tid];
+        for (int wv = 1; wv < kChunk / 32; ++wv) s = s + s_w[wv][tid];
+        s_tot[tid] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        st->block_counter = 0; // re-armed before solve_step copies the state
+        solve_step(st, prm, s_tot, pass, d.mlog);
+    }
+}
+
 // --------------------------------------------------------------------------
 // nn_finalize: exact resolution, association sums, solve
 // --------------------------------------------------------------------------
@@ -1019,9 +1118,7 @@ __global__ void __launch_bounds__(2 * kChunk) nn_finalize_kernel(const RegDesc *
     __shared__ int s_cnt;
     __shared__ float s_rd[2 * kChunk / 32];
     __shared__ int s_ri[2 * kChunk / 32];
-    __shared__ double s_w[kChunk / 32][kTerms];
-    __shared__ double s_tot[kTerms];
-    __shared__ int s_last;
+    __shared__ FinalizeShared s_fin;
 
     if (tid == 0) s_cnt = 0;
     const float4 *cur = d.D[(pass + 1) & 1];
@@ -1227,92 +1324,50 @@ __global__ void __launch_bounds__(2 * kChunk) nn_finalize_kernel(const RegDesc *
         }
     }
 
+    finalize_tail(d, st, prm, pass, chunk, nchunks, tid, valid, i, n, a, best_i, best_d, best_b, have_b, n_amb, s_fin);
+}
+
+// ICPB_NN_GRID with the cooperative search: the association arrives as one 16-byte record per query (the neighbour's
+// coordinates and index, grid.cu); nothing to resolve, so the kernel is the tail alone -- 256 threads, few registers,
+// eight CTAs per SM instead of the two of the general kernel (whose 59 us per pass were a third of a registration).
+__global__ void __launch_bounds__(kChunk, 6) nn_finalize_coop_kernel(const RegDesc *__restrict__ descs, IcpState *states,
+                                                                  const IcpParamsDev *__restrict__ prm, int pass)
+{
+    IcpState *st = states + blockIdx.z;
+    if (st->done) return;
+    const RegDesc &d = descs[blockIdx.z];
+    const int n = d.n;
+    const int chunk = blockIdx.x;
+    if (chunk * kChunk >= n) return;
+    const int nchunks = (n + kChunk - 1) / kChunk;
+    const int tid = threadIdx.x;
+    const int i = chunk * kChunk + tid;
+    const bool valid = i < n;
+    __shared__ FinalizeShared s_fin;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), best_b = a;
+    int best_i = -1;
+    float best_d = CUDART_INF_F;
+    bool have_b = false;
     if (valid) {
-        d.idx[i] = best_i;
-        d.dist[i] = best_d;
-        if (d.idx_trace) d.idx_trace[(size_t)pass * n + i] = best_i;
-        if (d.dist_trace) d.dist_trace[(size_t)pass * n + i] = best_d;
-        if (d.rej_flag) { // icp.cpp:507-509: the rejects of every pass accumulate
-            const bool rejected = !(best_d < prm->max_nn_distance);
-            d.rej_flag[(size_t)pass * n + i] = rejected ? 1 : 0;
-            if (rejected) d.rej_pts[(size_t)pass * n + i] = a;
+        a = d.D[(pass + 1) & 1][i];
+        const float4 nb = __ldcg(&d.gnb[i]);
+        best_i = __float_as_int(nb.w);
+        if (best_i >= 0) {
+            best_b = nb; have_b = true;
+            best_d = exact_distance(a.x, a.y, a.z, nb.x, nb.y, nb.z); // same inputs, same arithmetic: the search's own bits
         }
     }
-
-    // ---- association sums (CANON-3 level 1)
-    double t[kTerms];
-    const bool accepted = valid && (best_d < prm->max_nn_distance); // icp.cpp:553
-    if (accepted) {
-        const float4 b = have_b ? best_b : d.tgt[best_i];
-        t[0] = a.x; t[1] = a.y; t[2] = a.z;
-        t[3] = b.x; t[4] = b.y; t[5] = b.z;
-        t[6] = (double)b.x * (double)a.x; t[7] = (double)b.x * (double)a.y; t[8] = (double)b.x * (double)a.z;
-        t[9] = (double)b.y * (double)a.x; t[10] = (double)b.y * (double)a.y; t[11] = (double)b.y * (double)a.z;
-        t[12] = (double)b.z * (double)a.x; t[13] = (double)b.z * (double)a.y; t[14] = (double)b.z * (double)a.z;
-        t[15] = best_d;
-        t[16] = (double)(a.x - b.x); t[17] = (double)(a.y - b.y); t[18] = (double)(a.z - b.z);
-        t[19] = 1.0;
-    } else {
-#pragma unroll
-        for (int k = 0; k < kTerms; ++k) t[k] = 0.0;
-    }
-#pragma unroll
-    for (int k = 0; k < kTerms; ++k) {
-        double v = warp_fold(t[k]);
-        if ((tid & 31) == 0) s_w[tid >> 5][k] = v;
-    }
-    __syncthreads();
-    if (tid < kTerms) {
-        double s = s_w[0][tid];
-        for (int wv = 1; wv < kChunk / 32; ++wv) s = s + s_w[wv][tid];
-        d.chunk_sums[(size_t)chunk * kTerms + tid] = s;
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        if (n_amb) atomicAdd(&st->rescans, n_amb);
-        unsigned int ticket = atomicAdd(&st->block_counter, 1u);
-        s_last = (ticket == (unsigned int)(nchunks - 1));
-    }
-    __syncthreads();
-    if (!s_last) return;
-
-    // ---- last CTA of this registration: CANON-3 level 2, then the solve
-    __threadfence();
-    {
-        double acc[kTerms];
-#pragma unroll
-        for (int k = 0; k < kTerms; ++k) acc[k] = 0.0;
-        for (int c = tid; c < nchunks; c += kChunk) {
-            double v[kTerms];
-#pragma unroll
-            for (int k = 0; k < kTerms; ++k) v[k] = __ldcg(&d.chunk_sums[(size_t)c * kTerms + k]); // issued together
-#pragma unroll
-            for (int k = 0; k < kTerms; ++k) acc[k] = acc[k] + v[k];
-        }
-#pragma unroll
-        for (int k = 0; k < kTerms; ++k) {
-            double v = warp_fold(acc[k]);
-            if ((tid & 31) == 0) s_w[tid >> 5][k] = v;
-        }
-    }
-    __syncthreads();
-    if (tid < kTerms) {
-        double s = s_w[0][tid];
-        for (int wv = 1; wv < kChunk / 32; ++wv) s = s + s_w[wv][tid];
-        s_tot[tid] = s;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        st->block_counter = 0; // re-armed before solve_step copies the state
-        solve_step(st, prm, s_tot, pass, d.mlog);
-    }
+    finalize_tail(d, st, prm, pass, chunk, nchunks, tid, valid, i, n, a, best_i, best_d, best_b, have_b, 0, s_fin);
 }
 
 void launch_nn_finalize(const RegDesc *descs, IcpState *states, const IcpParamsDev *prm, int batch, int max_n, int splits,
                         int pass, int filter, cudaStream_t s)
 {
     dim3 grid((max_n + kChunk - 1) / kChunk, 1, batch);
+    if (splits < 0) { // cooperative cell-grid search
+        nn_finalize_coop_kernel<<<grid, kChunk, 0, s>>>(descs, states, prm, pass);
+        return;
+    }
     // brute-force modes on few CTAs (a small cloud; latency-bound: 10k points are 40 CTAs on 148 SMs): a pair of
     // threads per query for the group selection and the exact stage.  Many CTAs (full resolution, batches) are
     // throughput-bound and keep one thread per query (measured: pairs -6 % on the 1024-registration batch).

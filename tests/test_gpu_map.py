@@ -343,3 +343,41 @@ def test_brick_bits_follow_clear_upload_and_endpoint_updates(ctx, orc):
     m.upload(start); want[:] = start
     rays(40)
     m.close()
+
+
+@pytest.mark.parametrize("fpe", [1, 3, 8])
+def test_slabmap_sequence_single_rank_matches_oracle(ctx, orc, fpe):
+    """icpb_slabmap (the C-ABI z-slab map) with one rank: a sequence of device-resident frames, k frames per lift /
+    walk group on three streams, must give the oracle's grid -- the multi-rank path differs only by the all-gather."""
+    import ctypes
+    import icpb200
+    from icpb200 import synth
+    import torch
+    frames, dims, cell = 7, (300, 300, 250), 0.02
+    poses = synth.trajectory(frames, step_deg=0.8, step_m=0.02)
+    depths = [synth.render_depth(R, t, synth.KINECT_V2, seed=f) for f, (R, t) in enumerate(poses)]
+    K = icpb200.reference_intrinsics_v2()
+    want = np.zeros(dims, np.uint8)
+    for (R, t), dpt in zip(poses, depths):
+        pts, _, _ = orc.backproject(dpt, None, orc.kinect_v2())
+        pts = orc.translate(orc.rotate(pts, np.asarray(R, np.float32)), np.asarray(t, np.float32))
+        orc.map_integrate_rays(want, dims, cell, pts, tuple(float(x) for x in t), 25, 25)
+    h, w = depths[0].shape
+    sm = icpb200.SlabMapC(ctx, None, dims, cell, w, h)
+    d_depths = torch.from_numpy(np.stack(depths).astype(np.uint16).view(np.int16)).cuda()
+    torch.cuda.synchronize()
+    Rs = np.stack([np.asarray(R, np.float32) for R, _ in poses])
+    ts = np.stack([np.asarray(t, np.float32) for _, t in poses])
+    sm.integrate_sequence_device(d_depths.data_ptr(), frames, K, Rs, ts, 25, 25, fpe)
+    ctx.sync()
+    got = sm.download()
+    assert np.array_equal(got, want), f"{(got != want).sum()} voxels differ"
+    # a second pass over the same frames (occupied bricks everywhere the first pass put endpoints)
+    sm.integrate_sequence_device(d_depths.data_ptr(), frames, K, Rs, ts, 25, 25, fpe)
+    ctx.sync()
+    for (R, t), dpt in zip(poses, depths):
+        pts, _, _ = orc.backproject(dpt, None, orc.kinect_v2())
+        pts = orc.translate(orc.rotate(pts, np.asarray(R, np.float32)), np.asarray(t, np.float32))
+        orc.map_integrate_rays(want, dims, cell, pts, tuple(float(x) for x in t), 25, 25)
+    assert np.array_equal(sm.download(), want)
+    sm.close()
