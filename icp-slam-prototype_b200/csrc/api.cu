@@ -1253,6 +1253,29 @@ int icpb_map_update_endpoints(icpb_map *map, const icpb_cloud *points, int rule,
 int icpb_map_update_tracked(icpb_map *map, const icpb_cloud *points, int variant, int delta, int max_conf,
                             icpb_cloud *map_cloud, int *n_appended)
 {
+    if (!map_cloud) return ICPB_ERR_INVALID;
+    return icpb_map_update_tracked_base(map, points, variant, delta, max_conf, map_cloud, map_cloud->n, n_appended);
+}
+
+int icpb_map_table_entry(icpb_map *map, const int v[3], int *entry)
+{
+    if (!map || !v || !entry) return ICPB_ERR_INVALID;
+    icpb_ctx *ctx = map->ctx;
+    *entry = -1;
+    for (int k = 0; k < 3; ++k)
+        if (v[k] < 0 || v[k] >= map->dev.dims[k]) return fail(ctx, ICPB_ERR_INVALID, "icpb_map_table_entry: voxel outside the grid");
+    if (v[2] < map->dev.z_lo || v[2] >= map->dev.z_hi) return fail(ctx, ICPB_ERR_INVALID, "icpb_map_table_entry: voxel outside the slab");
+    if (!map->table) return ICPB_OK;
+    const size_t lin = ((size_t)v[0] * map->dev.dims[1] + v[1]) * map->dev.zs + (v[2] - map->dev.z_lo);
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(entry, map->table + lin, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return ICPB_OK;
+}
+
+int icpb_map_update_tracked_base(icpb_map *map, const icpb_cloud *points, int variant, int delta, int max_conf,
+                                 icpb_cloud *map_cloud, int table_base, int *n_appended)
+{
     if (!map || !points || !map_cloud) return ICPB_ERR_INVALID;
     icpb_ctx *ctx = map->ctx;
     if (variant < ICPB_TRACK_INIT || variant > ICPB_TRACK_NONASSOC) return fail(ctx, ICPB_ERR_INVALID, "unknown variant");
@@ -1273,7 +1296,7 @@ int icpb_map_update_tracked(icpb_map *map, const icpb_cloud *points, int variant
     if ((rc = ws_get(ctx, WS_TRACK, 16 + (sizeof(long long) + sizeof(int)) * 65536, &wsp))) return rc;
     int *d_app = (int *)wsp;
     launch_map_tracked(map->dev, map->table, points->d_pts, points->n, variant, delta, max_conf, map_cloud->d_pts,
-                       map_cloud->n, map_cloud->capacity, d_app, ctx->stream);
+                       map_cloud->n, map_cloud->capacity, d_app, table_base, ctx->stream);
     ctx->launches += 1;
     int app = 0;
     CU(ctx, cudaMemcpyAsync(&app, d_app, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

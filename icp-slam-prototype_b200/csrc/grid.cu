@@ -24,9 +24,11 @@ __device__ __forceinline__ unsigned int f2ord(float f)
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-// bbox[0..2] = ordered-uint min, bbox[3..5] = ordered-uint max (initialised by the host to ~0u / 0u)
-__global__ void grid_bbox_kernel(const float4 *__restrict__ pts, int m, unsigned int *bbox)
+// bbox[0..2] = ordered-uint min, bbox[3..5] = ordered-uint max (initialised by the host to ~0u / 0u).  One set of six
+// atomics per CTA (the first version issued them per warp: 49,000 atomics on six words, 35 us for 292k points).
+__global__ void __launch_bounds__(256) grid_bbox_kernel(const float4 *__restrict__ pts, int m, unsigned int *bbox)
 {
+    __shared__ unsigned int s_lo[3][8], s_hi[3][8];
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned int lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
     for (; i < m; i += gridDim.x * blockDim.x) {
@@ -37,15 +39,17 @@ __global__ void grid_bbox_kernel(const float4 *__restrict__ pts, int m, unsigned
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            lo[k] = min(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], off));
-            hi[k] = max(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], off));
-        }
+        lo[k] = __reduce_min_sync(0xffffffffu, lo[k]);
+        hi[k] = __reduce_max_sync(0xffffffffu, hi[k]);
+        if ((threadIdx.x & 31) == 0) { s_lo[k][threadIdx.x >> 5] = lo[k]; s_hi[k][threadIdx.x >> 5] = hi[k]; }
     }
-    if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { atomicMin(&bbox[k], lo[k]); atomicMax(&bbox[3 + k], hi[k]); }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int k = threadIdx.x;
+        unsigned int a = s_lo[k][0], b = s_hi[k][0];
+        for (int w = 1; w < 8; ++w) { a = min(a, s_lo[k][w]); b = max(b, s_hi[k][w]); }
+        atomicMin(&bbox[k], a);
+        atomicMax(&bbox[3 + k], b);
     }
 }
 
@@ -159,7 +163,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(int *data, int
 
 void launch_grid_bbox(const float4 *tgt, int m, unsigned int *bbox, cudaStream_t s)
 {
-    int blocks = min((m + 255) / 256, 1024);
+    int blocks = min((m + 255) / 256, 296);
     grid_bbox_kernel<<<blocks, 256, 0, s>>>(tgt, m, bbox);
 }
 

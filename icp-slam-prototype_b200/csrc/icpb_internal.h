@@ -215,7 +215,7 @@ inline PointSrc band_src(const float4 *first_header, int bands, int band_cap, lo
 }
 void launch_map_endpoints(const MapDev &m, const PointSrc &src, int rule, int delta, int max_conf, cudaStream_t s);
 void launch_map_tracked(const MapDev &m, int *table, const float4 *pts, int n, int variant, int delta, int max_conf,
-                        float4 *dst, int dst_n, int dst_capacity, int *d_appended, cudaStream_t s);
+                        float4 *dst, int dst_n, int dst_capacity, int *d_appended, int table_base, cudaStream_t s);
 void launch_map_rays(const MapDev &m, const PointSrc &src, const float origin[3], int delta_dec,
                      unsigned long long *visited, unsigned int *next_ray, int sm_count, cudaStream_t s);
 

@@ -191,7 +191,7 @@ __device__ __forceinline__ uint32_t track_apply(uint32_t c, int variant, int del
 __global__ void __launch_bounds__(kTrackThreads) map_tracked_kernel(MapDev m, int *table, const float4 *__restrict__ pts,
                                                                     int n, int variant, int delta, int max_conf,
                                                                     float4 *dst, int dst_n, int dst_capacity,
-                                                                    int *d_appended, long long *vox_scratch)
+                                                                    int *d_appended, long long *vox_scratch, int table_base)
 {
     __shared__ long long s_vox[kTrackThreads];
     __shared__ int s_warp[33];
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(kTrackThreads) map_tracked_kernel(MapDev m, in
         const int pos = s_base + s_warp[wid] + inc - insert;
         if (insert && pos < dst_capacity) { // past the capacity nothing is recorded: the call fails with ICPB_ERR_CAPACITY
             dst[pos] = pts[i];
-            table[vox_scratch[i]] = pos;
+            table[vox_scratch[i]] = table_base + (pos - dst_n); // the caller's numbering of the stored points
         }
         __syncthreads();
         if (tid == 0) s_base += total;
@@ -279,11 +279,11 @@ __global__ void __launch_bounds__(kTrackThreads) map_tracked_kernel(MapDev m, in
 }
 
 void launch_map_tracked(const MapDev &m, int *table, const float4 *pts, int n, int variant, int delta, int max_conf,
-                        float4 *dst, int dst_n, int dst_capacity, int *d_appended, cudaStream_t s)
+                        float4 *dst, int dst_n, int dst_capacity, int *d_appended, int table_base, cudaStream_t s)
 {
     long long *scratch = reinterpret_cast<long long *>(d_appended + 2);
     map_tracked_kernel<<<1, kTrackThreads, 0, s>>>(m, table, pts, n, variant, delta, max_conf, dst, dst_n, dst_capacity,
-                                                   d_appended, scratch);
+                                                   d_appended, scratch, table_base);
 }
 
 // M4 phase 1: exact integer Amanatides-Woo walk from the origin voxel centre to the endpoint voxel centre.

@@ -529,7 +529,7 @@ cv::Mat getTransformation(cv::Mat &data, cv::Mat &previous, cv::Mat color, std::
 // ================================================================ map.hpp
 namespace map {
 
-Map::Map() : world(nullptr), dev_(nullptr) {}
+Map::Map() : pointLookupTable{this}, world(nullptr), dev_(nullptr) {}
 
 Map::~Map()
 {
@@ -574,6 +574,9 @@ cv::Point3i Map::getVoxelCoordinates(cv::Point3f point) // map.cpp:55-85
 
 // The three Map::update overloads, certainty grid AND pointLookupTable / mapCloud bookkeeping, on the device
 // (icpb_map_update_tracked); the points it appends come back in point order and join the host-side list.
+// Table entries number the stored points of mapCloud.keypoints from 0 and those of mapCloud.points from kPointsList.
+static const int kPointsList = 1 << 30;
+
 static void tracked_update(icpb_map *dev, const point_list_t &pts, int variant, int delta, point_list_t &append_to)
 {
     const size_t kMax = 65536;
@@ -583,7 +586,8 @@ static void tracked_update(icpb_map *dev, const point_list_t &pts, int variant, 
         icpb_cloud *dst = scratch(1, (int)part.size());
         check(icpb_cloud_upload(dst, nullptr, 0), "icpb_cloud_upload");
         int appended = 0;
-        check(icpb_map_update_tracked(dev, src, variant, delta, MAX_CONFIDENCE, dst, &appended), "icpb_map_update_tracked");
+        const int base = (int)append_to.size() + (variant == ICPB_TRACK_ASSOC ? kPointsList : 0);
+        check(icpb_map_update_tracked_base(dev, src, variant, delta, MAX_CONFIDENCE, dst, base, &appended), "icpb_map_update_tracked");
         if (appended) {
             point_list_t got;
             download(dst, got);
@@ -635,6 +639,20 @@ void Map::integrateRays(icp::PointCloud &cloud, cv::Point3f origin, int delta_de
 }
 
 void Map::drawCertaintyMap(cv::viz::Viz3d &) {}
+
+color_point_t Map::lookup(int x, int y, int z) const // pointLookupTable[x][y][z], map.hpp:24
+{
+    if (!dev_) return empty;
+    const int v[3] = {x, y, z};
+    int e = -1;
+    check(icpb_map_table_entry(dev_, v, &e), "icpb_map_table_entry");
+    if (e < 0) return empty;
+    const point_list_t &list = (e >= kPointsList) ? mapCloud.points : mapCloud.keypoints;
+    const size_t k = (size_t)(e >= kPointsList ? e - kPointsList : e);
+    return k < list.size() ? list[k] : empty;
+}
+
+color_point_t LookupZ::operator[](int z) const { return m->lookup(x, y, z); }
 
 bool Map::isOccupied(cv::Point3f p) // map.cpp:441-444
 {

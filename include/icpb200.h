@@ -264,6 +264,13 @@ int icpb_map_update_endpoints(icpb_map *map, const icpb_cloud *points, int rule,
 enum { ICPB_TRACK_INIT = 0, ICPB_TRACK_ASSOC = 1, ICPB_TRACK_NONASSOC = 2 };
 int icpb_map_update_tracked(icpb_map *map, const icpb_cloud *points, int variant, int delta, int max_conf,
                             icpb_cloud *map_cloud, int *n_appended);
+/* The same with the caller's numbering: the lookup-table entries written by this call are table_base, table_base + 1,
+ * ... in append order (e.g. table_base = the length of the caller's own copy of the map cloud before the call), so
+ * that icpb_map_table_entry leads back to the stored point (pointLookupTable, map.hpp:24). */
+int icpb_map_update_tracked_base(icpb_map *map, const icpb_cloud *points, int variant, int delta, int max_conf,
+                                 icpb_cloud *map_cloud, int table_base, int *n_appended);
+/* Lookup-table entry of voxel v (-1 = empty, map.cpp:27). */
+int icpb_map_table_entry(icpb_map *map, const int v[3], int *entry);
 /* 1 when the voxel of p holds a lookup-table entry (pointLookupTable[..] != empty, map.hpp:24). */
 int icpb_map_has_entry(icpb_map *map, const float p[3], int *has_entry);
 /* Map::rayTrace map.cpp:272-439 (semantics in DESIGN.md "M4"): integer ray walk from the

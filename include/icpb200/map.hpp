@@ -21,10 +21,27 @@
 struct icpb_map;
 
 namespace map {
+class Map;
+// pointLookupTable[x][y][z] (map.hpp:24) as a read-only view: the reference's 432 MB array of stored points is an
+// int-per-voxel table on the device here; the view fetches the entry and returns the stored point (or `empty`).
+struct LookupZ {
+    const Map *m; int x, y;
+    color_point_t operator[](int z) const;
+};
+struct LookupY {
+    const Map *m; int x;
+    LookupZ operator[](int y) const { return LookupZ{m, x, y}; }
+};
+struct LookupTable {
+    const Map *m;
+    LookupY operator[](int x) const { return LookupY{m, x}; }
+};
+
 class Map { // map.hpp:20-37
 public:
     color_point_t empty;
     icp::PointCloud mapCloud;
+    LookupTable pointLookupTable;                   // map.hpp:24 (read-only view, see above)
     unsigned char (*world)[MAP_HEIGHT][MAP_HEIGHT]; // world[x][y][z], host mirror of the device grid
 
     Map();
@@ -48,6 +65,7 @@ public:
     void integrateRays(icp::PointCloud &cloud, cv::Point3f origin, int delta_dec, int delta_inc); // whole-cloud M4
     void syncWorld();                                                                             // device -> world
     void clear();
+    color_point_t lookup(int x, int y, int z) const;                                              // pointLookupTable[x][y][z]
 
 private:
     icpb_map *dev_;

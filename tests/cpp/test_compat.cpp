@@ -76,6 +76,18 @@ int main(int argc, char **argv)
         point_list_t non(target.points.begin(), target.points.begin() + 1200);
         for (int rep = 0; rep < 7; ++rep) m2.update(assoc, errors, non, DELTA_CONFIDENCE); // map.cpp:122-151
         dump(out + "/mapcloud_kp.bin", m2.mapCloud.keypoints.data(), m2.mapCloud.keypoints.size() * sizeof(color_point_t));
+        {   // pointLookupTable (map.hpp:24): the voxel of every stored key-point leads back to a stored point of that voxel
+            int bad = 0;
+            for (const color_point_t &kp : m2.mapCloud.keypoints) {
+                cv::Point3i v = m2.getVoxelCoordinates(kp.point);
+                color_point_t got = m2.pointLookupTable[v.x][v.y][v.z];
+                cv::Point3i gv = m2.getVoxelCoordinates(got.point);
+                if (got == m2.empty || gv.x != v.x || gv.y != v.y || gv.z != v.z) ++bad;
+            }
+            color_point_t none = m2.pointLookupTable[0][0][0];
+            int look[2] = {bad, (none == m2.empty) ? 1 : 0};
+            dump(out + "/lookup.bin", look, sizeof(look));
+        }
         m2.syncWorld();
         dump(out + "/world2.bin", m2.world, (size_t)MAP_HEIGHT * MAP_HEIGHT * MAP_HEIGHT);
     }

@@ -105,6 +105,8 @@ def test_compat_program_matches_oracle(tmp_path, orc):
     _same(_pts(o + "/mapcloud_kp.bin", orc), np.array(kp_list, dtype=orc.POINT_DTYPE))
     assert len(kp_list) > 1500 - 200 and np.array_equal(np.fromfile(o + "/world2.bin", np.uint8).reshape(dims), g2)
 
+    look = np.fromfile(o + "/lookup.bin", np.int32)
+    assert look[0] == 0 and look[1] == 1, "pointLookupTable view (map.hpp:24) does not lead back to the stored points"
     world = np.fromfile(o + "/world.bin", np.uint8).reshape(dims)
     assert np.array_equal(world, grid)
     vox = np.fromfile(o + "/voxel.bin", np.int32)
