@@ -81,7 +81,11 @@ def run_batch10k(args, rank, world, local, emit=True):
     K = icpb200.reference_intrinsics_v1()
     cam = np.array([5, 5, 5], np.float32)
     total = args.batch
-    lo, hi = D.shard_range(total, rank, world)
+    # the job's plumbing lives in libicpb200 (icpb_comm: NCCL): block ownership and the final gather of the poses;
+    # torch.distributed only carries the 128-byte NCCL id
+    comm = icpb200.Comm.from_torch(ctx) if world > 1 else None
+    lo, hi = comm.shard_range(total) if comm is not None else (0, total)
+    assert (lo, hi) == D.shard_range(total, rank, world)
     # 8 distinct rendered frame pairs; registration i uses pair i % 8 with its own seeded 10k subsample
     pairs = []
     full = ctx.cloud(640 * 480)
@@ -142,13 +146,20 @@ def run_batch10k(args, rank, world, local, emit=True):
         ctx.sync()
         e2e_ms.append((time.perf_counter() - t0) * 1e3)
     e2e_tot = _max_over_ranks(torch, world, local, float(e2e_ms[-1]))
-    rows = torch.tensor(np.array([np.concatenate([r["pose_R"].ravel(), r["pose_t"]]) for r in res]).reshape(-1, 12),
-                        dtype=torch.float64, device=f"cuda:{local}")
-    allrows = D.gather_results(rows) if world > 1 else rows
+    rows = np.array([np.concatenate([r["pose_R"].ravel(), r["pose_t"]]) for r in res], dtype=np.float64).reshape(-1, 12)
+    if comm is not None:   # equal-sized blocks for the all-gather: pad to the largest share, strip after
+        cap = -(-total // world)
+        padded = np.zeros((cap, 12), np.float64)
+        padded[: len(rows)] = rows
+        gathered = comm.allgather_host(padded)
+        allrows = np.concatenate([gathered[r][: D.shard_range(total, r, world)[1] - D.shard_range(total, r, world)[0]]
+                                  for r in range(world)])
+    else:
+        allrows = rows
     line = None
     if rank == 0:
         ms_per_step = tot / args.steps
-        digest = hashlib.sha256(allrows.cpu().numpy().tobytes()).hexdigest()
+        digest = hashlib.sha256(np.ascontiguousarray(allrows).tobytes()).hexdigest()
         # oracle check + CPU baseline in one: registration 0 of the batch through the oracle port on one thread
         cpu, oracle_ok = None, None
         try:
@@ -189,6 +200,9 @@ def run_batch10k(args, rank, world, local, emit=True):
             print(json.dumps(line), flush=True)
     for c in datas + targets + pristine:
         c.close()
+    if comm is not None:
+        _barrier(torch, world)
+        comm.close()
     ctx.close()
     return line
 
@@ -231,13 +245,12 @@ def run_map1cm(args, rank, world, local, emit=True):
     d_depths = host_depths.to(torch.device("cuda", local))
     torch.cuda.synchronize()
     frame_bytes = 640 * 480 * 2
-    ctx_stream = torch.cuda.ExternalStream(ctx.lib.icpb_ctx_stream(ctx.h))
 
     def step(h2d=False):
         ctx.timer_start()
-        if h2d:   # e2e leg: every frame comes from pinned host memory on the context's stream
-            with torch.cuda.stream(ctx_stream):
-                d_depths.copy_(host_depths, non_blocking=True)
+        if h2d:   # e2e leg: every frame comes from pinned host memory (torch's stream; the host waits for the copy)
+            d_depths.copy_(host_depths, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
         sm.integrate_sequence_device(d_depths.data_ptr(), frames, K, Rs, ts, 25, 25, fpe)
         return ctx.timer_stop()
 
@@ -256,6 +269,7 @@ def run_map1cm(args, rank, world, local, emit=True):
     rays_ms, rays_launches = ctx.profile_read(icpb200.PROF_MAP_RAYS)
     ends_ms, _ = ctx.profile_read(icpb200.PROF_MAP_ENDPOINTS)
     ctx.set_profiling(False)
+    rays_ms_rank = rays_ms
     rays_ms = _max_over_ranks(torch, world, local, rays_ms)
     e2e = [step(h2d=True) for _ in range(2)]
     e2e_tot = _max_over_ranks(torch, world, local, float(e2e[-1]))
@@ -264,8 +278,11 @@ def run_map1cm(args, rank, world, local, emit=True):
         import torch.distributed as dist
         hs = [None] * world
         dist.all_gather_object(hs, (sm.z_lo, sm.z_hi, h, int((slab > 0).sum())))
+        per_rank_rays = [None] * world
+        dist.all_gather_object(per_rank_rays, round(float(rays_ms_rank), 3))
     else:
         hs = [(sm.z_lo, sm.z_hi, h, int((slab > 0).sum()))]
+        per_rank_rays = [round(float(rays_ms_rank), 3)]
     del slab
     line = None
     if rank == 0:
@@ -326,7 +343,8 @@ def run_map1cm(args, rank, world, local, emit=True):
                            "l2": "grid (180 MB) exceeds L2 at 1 GPU"},
                 "extra": {"frames_per_s": frames / (ms_per_step * 1e-3),
                           "algorithmic_GBps": alg_bytes / (ms_per_step * 1e-3) / 1e9,
-                          "stage_ms_per_pass": {"map_rays_max_over_ranks": rays_ms, "map_endpoints_rank0": ends_ms}},
+                          "stage_ms_per_pass": {"map_rays_max_over_ranks": rays_ms, "map_rays_per_rank": per_rank_rays,
+                                                "map_endpoints_rank0": ends_ms}},
                 "roofline": {"bound": "hbm", "kernel": "map_rays_brick_kernel", "achieved": rays_gbs, "peak": peak,
                              "unit": "GB/s", "frac": rays_gbs / peak, "traffic": None,
                              "bytes_per_launch": rays_bytes / max(rays_launches, 1),

@@ -842,8 +842,10 @@ __global__ void __launch_bounds__(32 * kCoopWarps) nn_grid_coop_kernel(const Reg
         if (!done && rr > coop_r) { deferred = true; done = true; }
         const unsigned active = __ballot_sync(full, !done);
         if (active == 0u) break;
-        // ---- the union of the active balls, over-approximated by one sphere per group of kCoopGroup consecutive lanes
-        //      (Morton neighbours): centre = middle of the group's queries, radius = the farthest reach of a member
+        // ---- the union of the active balls.  A group of kCoopGroup consecutive lanes (Morton neighbours) is normally
+        //      covered by ONE sphere: centre = middle of the group's queries, radius = the farthest reach of a member.
+        //      A group that straddles a jump of the Morton curve would get a sphere metres wide: it is "loose" and its
+        //      members are tested ball by ball instead.
         float glx = done ? CUDART_INF_F : p.x, ghx = done ? -CUDART_INF_F : p.x;
         float gly = done ? CUDART_INF_F : p.y, ghy = done ? -CUDART_INF_F : p.y;
         float glz = done ? CUDART_INF_F : p.z, ghz = done ? -CUDART_INF_F : p.z;
@@ -854,14 +856,42 @@ __global__ void __launch_bounds__(32 * kCoopWarps) nn_grid_coop_kernel(const Reg
             glz = fminf(glz, __shfl_xor_sync(full, glz, off)); ghz = fmaxf(ghz, __shfl_xor_sync(full, ghz, off));
         }
         const float scx = 0.5f * glx + 0.5f * ghx, scy = 0.5f * gly + 0.5f * ghy, scz = 0.5f * glz + 0.5f * ghz;
-        float sr = -1.f; // no active member: the sphere needs nothing
+        float sr = -1.f, far = 0.f; // no active member: the sphere needs nothing
         if (!done) {
             const float ex = p.x - scx, ey = p.y - scy, ez = p.z - scz;
-            sr = sqrtf((ex * ex + ey * ey) + ez * ez) * 1.00001f + rr;
+            far = sqrtf((ex * ex + ey * ey) + ez * ez) * 1.00001f;
+            sr = far + rr;
         }
 #pragma unroll
-        for (int off = 1; off < kCoopGroup; off <<= 1) sr = fmaxf(sr, __shfl_xor_sync(full, sr, off));
-        const float sr2 = sr < 0.f ? -1.f : (sr * sr) * 1.0001f + 1e-12f;
+        for (int off = 1; off < kCoopGroup; off <<= 1) {
+            sr = fmaxf(sr, __shfl_xor_sync(full, sr, off));
+            far = fmaxf(far, __shfl_xor_sync(full, far, off));
+        }
+        const bool loose = far > 0.5f * g.h;                              // uniform within the group
+        const float sr2 = (sr < 0.f || loose) ? -1.f : (sr * sr) * 1.0001f + 1e-12f;
+        const float br2 = (!done && loose) ? (rr * rr) * 1.0001f + 1e-12f : -1.f; // the lane's own ball, loose groups only
+        const unsigned loose_lanes = __ballot_sync(full, br2 >= 0.f);
+        // needed(box): does the box [lo, hi] reach into one of the group spheres or one of the loose lanes' balls?
+        auto reaches = [&](float lx, float ly, float lz, float hx, float hy, float hz) -> bool {
+            bool hit = false;
+#pragma unroll
+            for (int s0 = 0; s0 < 32; s0 += kCoopGroup) {
+                const float sx = __shfl_sync(full, scx, s0), sy = __shfl_sync(full, scy, s0), sz = __shfl_sync(full, scz, s0);
+                const float s2 = __shfl_sync(full, sr2, s0);
+                const float dx = fmaxf(fmaxf(lx - sx, sx - hx), 0.f), dy = fmaxf(fmaxf(ly - sy, sy - hy), 0.f);
+                const float dz = fmaxf(fmaxf(lz - sz, sz - hz), 0.f);
+                hit |= ((dx * dx + dy * dy) + dz * dz) <= s2;
+            }
+            for (unsigned rest = loose_lanes; rest; rest &= rest - 1) {
+                const int j = __ffs(rest) - 1;
+                const float sx = __shfl_sync(full, p.x, j), sy = __shfl_sync(full, p.y, j), sz = __shfl_sync(full, p.z, j);
+                const float s2 = __shfl_sync(full, br2, j);
+                const float dx = fmaxf(fmaxf(lx - sx, sx - hx), 0.f), dy = fmaxf(fmaxf(ly - sy, sy - hy), 0.f);
+                const float dz = fmaxf(fmaxf(lz - sz, sz - hz), 0.f);
+                hit |= ((dx * dx + dy * dy) + dz * dz) <= s2;
+            }
+            return hit;
+        };
         // box of cells around the active balls
         const float ext = rr * 1.00001f + 2e-3f * g.h;
         int bx0 = done ? 0x7fffffff : cell_axis(p.x - ext, g.mn[0], g.h, nx), bx1 = done ? -1 : cell_axis(p.x + ext, g.mn[0], g.h, nx);
@@ -870,51 +900,70 @@ __global__ void __launch_bounds__(32 * kCoopWarps) nn_grid_coop_kernel(const Reg
         bx0 = __reduce_min_sync(full, bx0); bx1 = __reduce_max_sync(full, bx1);
         by0 = __reduce_min_sync(full, by0); by1 = __reduce_max_sync(full, by1);
         bz0 = __reduce_min_sync(full, bz0); bz1 = __reduce_max_sync(full, bz1);
-        const int nxb = bx1 - bx0 + 1, nyb = by1 - by0 + 1, nzb = bz1 - bz0 + 1;
-        const int nbox = nxb * nyb * nzb;
+        const int nyb = by1 - by0 + 1, nzb = bz1 - bz0 + 1;
+        const int nrows = nyb * nzb;
+        const float xlo = g.mn[0] + bx0 * g.h, xhi = g.mn[0] + (bx1 + 1) * g.h;
+        const float slack = 1e-3f * g.h; // float rounding of the cell assignment (as in axis_gap)
         const bool live = !done; // a lane that is done must not pick anything up any more
         int fill = 0;
-        for (int cbase = 0; cbase < nbox; cbase += 32) {
-            // ---- lane <-> cell of the box: needed when the tight box of its targets reaches into one of the spheres
-            const int ci = cbase + lane;
-            int t0 = 0, len = 0;
-            float4 blo = make_float4(0.f, 0.f, 0.f, 0.f), bhi = blo;
-            if (ci < nbox) {
-                const int xx = bx0 + ci % nxb, yz = ci / nxb;
-                const int cell = ((bz0 + yz / nyb) * ny + (by0 + yz % nyb)) * nx + xx;
-                t0 = __ldg(&gstart[cell]);
-                len = __ldg(&gstart[cell + 1]) - t0;
-                if (len > 0) { blo = __ldg(&gbox[2 * (size_t)cell]); bhi = __ldg(&gbox[2 * (size_t)cell + 1]); }
-            }
-            bool need = false;
+        for (int rbase = 0; rbase < nrows; rbase += 32) {
+            // ---- step 1, lane <-> row of cells (fixed y, z), arithmetic only: rows whose slab of space [x-range of the
+            //      warp's box] x [the row's y, z interval] no sphere reaches are dropped before anything is loaded (a
+            //      warp that straddles a Morton jump has a box of thousands of mostly irrelevant rows)
+            const int row = rbase + lane;
+            const bool rv = row < nrows;
+            const int yy = by0 + (rv ? row % nyb : 0), zz = bz0 + (rv ? row / nyb : 0);
+            const float ylo = g.mn[1] + yy * g.h, zlo = g.mn[2] + zz * g.h;
+            const bool row_need = reaches(xlo - slack, ylo - slack, zlo - slack, xhi + slack, ylo + g.h + slack, zlo + g.h + slack) && rv;
+            const int cnt = row_need ? bx1 - bx0 + 1 : 0;
+            // ---- step 2: the cells of the surviving rows, flattened over the lanes: lane <-> cell, tight-box test
+            int incl = cnt;
 #pragma unroll
-            for (int s0 = 0; s0 < 32; s0 += kCoopGroup) {
-                const float sx = __shfl_sync(full, scx, s0), sy = __shfl_sync(full, scy, s0), sz = __shfl_sync(full, scz, s0);
-                const float s2 = __shfl_sync(full, sr2, s0);
-                const float dx = fmaxf(fmaxf(blo.x - sx, sx - bhi.x), 0.f), dy = fmaxf(fmaxf(blo.y - sy, sy - bhi.y), 0.f);
-                const float dz = fmaxf(fmaxf(blo.z - sz, sz - bhi.z), 0.f);
-                need |= ((dx * dx + dy * dy) + dz * dz) <= s2;
+            for (int off = 1; off < 32; off <<= 1) {
+                const int o = __shfl_up_sync(full, incl, off);
+                if (lane >= off) incl += o;
             }
-            if (len <= 0) need = false;
-            // ---- copy the needed cells into the batch, centred; a full batch is evaluated at once
-            for (unsigned cells = __ballot_sync(full, need); cells; cells &= cells - 1) {
-                const int r = __ffs(cells) - 1;
-                int pos = __shfl_sync(full, t0, r), remaining = __shfl_sync(full, len, r);
-                while (remaining > 0) {
-                    const int take = min(remaining, kCoopCap - fill);
-                    for (int e = lane; e < take; e += 32) {
-                        const float4 t = __ldg(&sorted[pos + e]);
-                        const float tx = t.x - cx, ty = t.y - cy, tz = t.z - cz;
-                        buf.xs[fill + e] = tx; buf.ys[fill + e] = ty; buf.zs[fill + e] = tz;
-                        buf.ns[fill + e] = __fmaf_rn(tz, tz, __fmaf_rn(ty, ty, tx * tx));
-                        buf.gp[fill + e] = pos + e;
-                    }
-                    fill += take; pos += take; remaining -= take;
-                    if (fill == kCoopCap) {
-                        __syncwarp();
-                        coop_batch(buf, fill, sorted, p, qx, qy, qz, A, live, best, bb);
-                        __syncwarp();
-                        fill = 0;
+            const int total = __shfl_sync(full, incl, 31);
+            const int excl = incl - cnt;
+            const int rowbase_l = (zz * ny + yy) * nx + bx0;
+            for (int cb = 0; cb < total; cb += 32) {
+                const int ci = cb + lane;
+                int r = 0; // the last lane whose first flattened cell is <= ci
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1) {
+                    const int e = __shfl_sync(full, excl, (r + step) & 31);
+                    if (r + step < 32 && e <= ci) r += step;
+                }
+                const int r_excl = __shfl_sync(full, excl, r), r_base = __shfl_sync(full, rowbase_l, r);
+                int t0 = 0, len = 0;
+                float4 blo = make_float4(0.f, 0.f, 0.f, 0.f), bhi = blo;
+                if (ci < total) {
+                    const int cell = r_base + (ci - r_excl);
+                    t0 = __ldg(&gstart[cell]);
+                    len = __ldg(&gstart[cell + 1]) - t0;
+                    if (len > 0) { blo = __ldg(&gbox[2 * (size_t)cell]); bhi = __ldg(&gbox[2 * (size_t)cell + 1]); }
+                }
+                const bool need = reaches(blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z) && len > 0;
+                // ---- copy the needed cells into the batch, centred; a full batch is evaluated at once
+                for (unsigned cells = __ballot_sync(full, need); cells; cells &= cells - 1) {
+                    const int rc = __ffs(cells) - 1;
+                    int pos = __shfl_sync(full, t0, rc), remaining = __shfl_sync(full, len, rc);
+                    while (remaining > 0) {
+                        const int take = min(remaining, kCoopCap - fill);
+                        for (int e = lane; e < take; e += 32) {
+                            const float4 t = __ldg(&sorted[pos + e]);
+                            const float tx = t.x - cx, ty = t.y - cy, tz = t.z - cz;
+                            buf.xs[fill + e] = tx; buf.ys[fill + e] = ty; buf.zs[fill + e] = tz;
+                            buf.ns[fill + e] = __fmaf_rn(tz, tz, __fmaf_rn(ty, ty, tx * tx));
+                            buf.gp[fill + e] = pos + e;
+                        }
+                        fill += take; pos += take; remaining -= take;
+                        if (fill == kCoopCap) {
+                            __syncwarp();
+                            coop_batch(buf, fill, sorted, p, qx, qy, qz, A, live, best, bb);
+                            __syncwarp();
+                            fill = 0;
+                        }
                     }
                 }
             }

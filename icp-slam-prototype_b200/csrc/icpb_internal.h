@@ -37,10 +37,12 @@ constexpr float kBandAbs = 1.0e-30f;
 constexpr int kFilterCentred = ICPB_FILTER_CENTRED; // |t'|^2 - 2a'.t' about a per-thread centre: 3 per pair + 6 per target per thread
 constexpr int kFilterDirect = ICPB_FILTER_DIRECT;   // (a-t)^2 in packed FP32: 6 FMA-pipe lane-ops per pair
 constexpr int kFilterWarp = ICPB_FILTER_WARP;       // the centred form about a per-WARP centre over spatially sorted queries
-// centred filter: the W-gap that proves "strictly farther" is kBandCentredA * A + kBandCentredX * max(W_best + A, 0);
-// the bound at nn_partial_centred_kernel needs 16u A + 103u X (u = 2^-24), used with ~10 % slack
-constexpr float kBandCentredA = 18.0f * 5.9604644775390625e-08f;
-constexpr float kBandCentredX = 115.0f * 5.9604644775390625e-08f;
+// centred filters (nn_partial_centred / nn_partial_warp / nn_grid_coop): a target whose filter value W exceeds the best
+// W by more than kBandCentredA * A + kBandCentredX * max(W_best + A, 0) is strictly farther, in the reference's own
+// arithmetic, than the best target -- it can neither win nor tie.  The single derivation is DESIGN.md section 4
+// ("error band of the centred filter"): it needs 18 u A + 106 u D (u = 2^-24); the constants carry a third more.
+constexpr float kBandCentredA = 24.0f * 5.9604644775390625e-08f;
+constexpr float kBandCentredX = 128.0f * 5.9604644775390625e-08f;
 
 // Per-registration device state: iteration control and pose, kept on the
 // device for the whole loop (icp.cpp:22-25 globals + locals of :28-285).

@@ -318,14 +318,8 @@ __global__ void __launch_bounds__(kNnThreads) nn_partial_kernel(const RegDesc *_
 // (|a'| + |t'|)^2, i.e. with the spread of one thread's queries (centimetres
 // for a raster-ordered cloud) instead of the 5-8 m world coordinates.
 //
-// Error bound used by nn_finalize (u = 2^-24, A = |a'|^2, D = |a - t|^2 exact):
-//     |W + A - D| <= 40 u A + 26 u D
-// (a' and t' carry one rounding each, |t'|^2 three, the FMA chain three, every
-// partial result is bounded by (|a'| + |t'|)^2 and |t'| <= |a'| + sqrt(D)).
-// A target whose W exceeds the best W by more than 2^-17 (A + max(W_best + A, 0))
-// is therefore strictly farther in the reference's own arithmetic (3 u on each
-// squared distance, 4 u for the float sqrt) than the best target: it can
-// neither win nor tie.  A is written to d.pa by split 0.
+// Error bound and the band nn_finalize applies (kBandCentredA / kBandCentredX, icpb_internal.h): ONE derivation, in
+// DESIGN.md section 4, "error band of the centred filter".  A = |a'|^2 is written to d.pa by split 0.
 template <int QPT>
 __global__ void __launch_bounds__(kNnThreads, (QPT >= 16 ? 2 : QPT >= 12 ? 3 : 4)) nn_partial_centred_kernel(const RegDesc *__restrict__ descs,
                                                                         IcpState *states, int splits, int pass)
@@ -984,6 +978,11 @@ __device__ __forceinline__ void solve_step_local(IcpState *st, const IcpParamsDe
     st->iterations = i + 1;
 }
 
+struct FinalizeShared;
+__device__ __noinline__ void finalize_last_cta(const double *chunk_sums, float *mlog, IcpState *st,
+                                               const IcpParamsDev *__restrict__ prm, int pass, int nchunks, int tid,
+                                               FinalizeShared &sh);
+
 // Everything after the association of a chunk is known: per-query outputs, CANON-3 sums, and in the last CTA of the
 // registration the second summation level and the solve.  Shared by nn_finalize_kernel and nn_finalize_coop_kernel.
 struct FinalizeShared {
@@ -998,7 +997,6 @@ __device__ __forceinline__ void finalize_tail(const RegDesc &d, IcpState *st, co
                                               FinalizeShared &sh)
 {
     double (&s_w)[kChunk / 32][kTerms] = sh.w;
-    double (&s_tot)[kTerms] = sh.tot;
     int &s_last = sh.last;
     if (valid) {
         d.idx[i] = best_i;
@@ -1051,7 +1049,17 @@ __device__ __forceinline__ void finalize_tail(const RegDesc &d, IcpState *st, co
     __syncthreads();
     if (!s_last) return;
 
-    // ---- last CTA of this registration: CANON-3 level 2, then the solve
+    // ---- last CTA of this registration: CANON-3 level 2, then the solve (out of line: its forty accumulator registers
+    //      and the solve's must not set the register count of the 1,100 CTAs that never get here)
+    finalize_last_cta(d.chunk_sums, d.mlog, st, prm, pass, nchunks, tid, sh);
+}
+
+__device__ __noinline__ void finalize_last_cta(const double *chunk_sums, float *mlog, IcpState *st,
+                                               const IcpParamsDev *__restrict__ prm, int pass, int nchunks, int tid,
+                                               FinalizeShared &sh)
+{
+    double (&s_w)[kChunk / 32][kTerms] = sh.w;
+    double (&s_tot)[kTerms] = sh.tot;
     __threadfence();
     {
         double acc[kTerms];
@@ -1060,7 +1068,7 @@ __device__ __forceinline__ void finalize_tail(const RegDesc &d, IcpState *st, co
         for (int c = tid; c < nchunks; c += kChunk) {
             double v[kTerms];
 #pragma unroll
-            for (int k = 0; k < kTerms; ++k) v[k] = __ldcg(&d.chunk_sums[(size_t)c * kTerms + k]); // issued together
+            for (int k = 0; k < kTerms; ++k) v[k] = __ldcg(&chunk_sums[(size_t)c * kTerms + k]); // issued together
 #pragma unroll
             for (int k = 0; k < kTerms; ++k) acc[k] = acc[k] + v[k];
         }
@@ -1079,7 +1087,7 @@ __device__ __forceinline__ void finalize_tail(const RegDesc &d, IcpState *st, co
     __syncthreads();
     if (tid == 0) {
         st->block_counter = 0; // re-armed before solve_step copies the state
-        solve_step(st, prm, s_tot, pass, d.mlog);
+        solve_step(st, prm, s_tot, pass, mlog);
     }
 }
 

@@ -183,3 +183,61 @@ def test_nn_randomized_differential(ctx, orc, monkeypatch, flt):
     for _ in range(40):
         data, target = _random_case(rng, orc)
         _check(ctx, orc, data, target)
+
+
+# ---- the error band of the FP32 filter, stressed from both sides --------------------------
+
+def _band_sweep_clouds(orc, offset):
+    """4,096 queries next to the bisector plane of two targets that sit in DIFFERENT 32-target groups: the relative
+    difference of their two squared distances sweeps -1.3e-5 .. +1.3e-5 in steps of ~6e-9 -- through zero, through the
+    filter's own rounding noise and through the band |W2 - W1| = 18uA + 115uD (~7e-6 D) on either side, so that
+    "the best group alone decides", "the best two groups decide" and "full exact rescan" are all taken, each within an ulp
+    of its threshold.  Fillers are metres away.  `offset` moves everything to large coordinates (coarser ulps)."""
+    rng = np.random.default_rng(11)
+    n = 4096
+    k = np.arange(n, dtype=np.float64) - n / 2
+    q = np.stack([k * 5e-10, rng.uniform(-0.2, 0.2, n), rng.uniform(-0.2, 0.2, n)], 1)
+    t = rng.uniform(2.0, 3.0, (96, 3)) * rng.choice([-1.0, 1.0], (96, 3))
+    t[3] = (0.3, 0.0, 0.0)        # group 0
+    t[70] = (-0.3, 0.0, 0.0)      # group 2
+    off = np.asarray(offset, np.float64)
+    return orc.make_points((q + off).astype(np.float32)), orc.make_points((t + off).astype(np.float32))
+
+
+@pytest.mark.parametrize("offset", [(0, 0, 0), (0.001, -0.002, 0.0005), (5, 5, 5)])
+@pytest.mark.parametrize("mode", ["direct", "warp", "centred", "grid"])
+def test_nn_band_is_right_on_both_sides(ctx, orc, mode, offset):
+    import icpb200
+    data, target = _band_sweep_clouds(orc, offset)
+    ridx, rdist = orc.nn(data, target, n_threads=8)
+    assert 0.3 < (ridx == 3).mean() < 0.7 and set(np.unique(ridx)) == {3, 70}   # the sweep really crosses the bisector
+    dc, tc = ctx.cloud_from_points(data), ctx.cloud_from_points(target)
+    kw = dict(nn_mode=icpb200.NN_GRID) if mode == "grid" else dict(
+        nn_filter={"direct": icpb200.FILTER_DIRECT, "warp": icpb200.FILTER_WARP, "centred": icpb200.FILTER_CENTRED}[mode])
+    res, it, dt = ctx.icp_register(dc, tc, 0, 0.0, 0.75, icpb200.SOLVE_REFERENCE, trace=True, **kw)
+    assert np.array_equal(it[0], ridx), f"{(it[0] != ridx).sum()} index mismatches"
+    assert np.array_equal(dt[0].view(np.uint32), rdist.view(np.uint32))
+    dc.close(); tc.close()
+
+
+def test_nn_warp_filter_is_deterministic(ctx, orc):
+    """The query order behind the warp-centred filter is a stable radix sort: 20 runs of a 60k-query search give the
+    same indices, distances AND the same number of exact rescans (round 1 used an atomic cursor: 11..17 rescans)."""
+    import icpb200
+    rng = np.random.default_rng(3)
+    base = rng.uniform(4, 6, (60000, 3)).astype(np.float32)
+    data = orc.make_points(base + rng.normal(0, 0.02, base.shape).astype(np.float32))
+    target = orc.make_points(np.concatenate([base[::2], base[::2] + np.float32(1e-4)]))
+    dc0, tc = ctx.cloud_from_points(data), ctx.cloud_from_points(target)
+    dc = ctx.cloud(len(data))
+    first = None
+    for run in range(20):
+        dc.copy_from(dc0)
+        res, it, dt = ctx.icp_register(dc, tc, 0, 0.0, 0.75, icpb200.SOLVE_REFERENCE, trace=True, nn_filter=icpb200.FILTER_WARP)
+        sig = (it[0].tobytes(), dt[0].tobytes(), res["exact_rescans"])
+        if first is None:
+            first = sig
+            ridx, rdist = orc.nn(data[:3000], target, n_threads=8)
+            assert np.array_equal(it[0][:3000], ridx) and np.array_equal(dt[0][:3000].view(np.uint32), rdist.view(np.uint32))
+        assert sig == first, f"run {run} differs from run 0 (rescans {res['exact_rescans']} vs {first[2]})"
+    dc.close(); dc0.close(); tc.close()
