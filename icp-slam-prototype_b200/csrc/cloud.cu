@@ -618,23 +618,6 @@ __global__ void normals_kernel(const uint16_t *__restrict__ depth, int w, int h,
 // The same stencil, four pixels of a row per thread (image widths that are multiples of 4): the rows above and below
 // arrive as one 8-byte load each, the centre row as one 8-byte load plus its two outer neighbours, and the 12 floats of
 // the four normals leave as three 16-byte stores.  blockIdx.z = frame of a batch.
-#ifdef ICPB_NORMALS_FAST
-__device__ __forceinline__ bool near_float_midpoint(double p)
-{
-    const int lo = __double2loint(p) & 0x1fffffff;
-    return (unsigned)(lo - 0x10000000 + 64) <= 128u;
-}
-
-__device__ __noinline__ void normalize_exact(double d0, double d1, double s, float &n0, float &n1, float &n2)
-{
-    const double nv = sqrt(s);
-    const double inv = 1.0 / nv;
-    n0 = (float)(d0 * inv);
-    n1 = (float)(d1 * inv);
-    n2 = (float)(1.0 * inv);
-}
-#endif
-
 __device__ __forceinline__ void normal_of(float up, float dn, float lf, float rt, bool inside, float &n0, float &n1,
                                           float &n2)
 {
@@ -642,37 +625,12 @@ __device__ __forceinline__ void normal_of(float up, float dn, float lf, float rt
     if (!inside) return;
     const float dzdx = (dn - up) / 2.0f;
     const float dzdy = (rt - lf) / 2.0f;
-#ifdef ICPB_NORMALS_FAST
-    // Same bits with 16 instead of 26 FP64 instructions per pixel: cv::normalize's double sqrt + reciprocal replaced by a
-    // float rsqrt refined by two Newton steps in fma form; a product within 64 ulps of a float rounding boundary takes
-    // the exact sequence, kept out of line.  Host proof over all (dzdx, dzdy): tools/checks/normalize_fastpath_check.c.
-    const float v0 = -dzdx, v1 = -dzdy;
-    const double d0 = (double)v0, d1 = (double)v1;
-    const double s = (d0 * d0 + d1 * d1) + 1.0;
-    double y = (double)rsqrtf((float)s);
-    const double h = 0.5 * s;
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        const double hy = __dmul_rn(h, y);
-        const double e = __fma_rn(-hy, y, 0.5);
-        y = __fma_rn(y, e, y);
-    }
-    const double p0 = __dmul_rn(d0, y), p1 = __dmul_rn(d1, y);
-    if (near_float_midpoint(p0) || near_float_midpoint(p1) || near_float_midpoint(y)) {
-        normalize_exact(d0, d1, s, n0, n1, n2);
-        return;
-    }
-    n0 = (float)p0;
-    n1 = (float)p1;
-    n2 = (float)y;
-#else
     const float v0 = -dzdx, v1 = -dzdy, v2 = 1.0f;
     const double nv = sqrt(((double)v0 * (double)v0 + (double)v1 * (double)v1) + (double)v2 * (double)v2);
     const double inv = 1.0 / nv;
     n0 = (float)((double)v0 * inv);
     n1 = (float)((double)v1 * inv);
     n2 = (float)((double)v2 * inv);
-#endif
 }
 
 // kNormRows rows per thread: the kNormRows + 2 depth rows a thread needs are all requested before the first normal is

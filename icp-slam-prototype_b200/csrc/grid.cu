@@ -867,7 +867,11 @@ __global__ void __launch_bounds__(32 * kCoopWarps) nn_grid_coop_kernel(const Reg
             sr = fmaxf(sr, __shfl_xor_sync(full, sr, off));
             far = fmaxf(far, __shfl_xor_sync(full, far, off));
         }
-        const bool loose = far > 0.5f * g.h;                              // uniform within the group
+        // loose: the sphere would cover much more than its members' balls do (uniform within the group)
+        float rmax = done ? 0.f : rr;
+#pragma unroll
+        for (int off = 1; off < kCoopGroup; off <<= 1) rmax = fmaxf(rmax, __shfl_xor_sync(full, rmax, off));
+        const bool loose = far > 0.5f * rmax + 0.01f;
         const float sr2 = (sr < 0.f || loose) ? -1.f : (sr * sr) * 1.0001f + 1e-12f;
         const float br2 = (!done && loose) ? (rr * rr) * 1.0001f + 1e-12f : -1.f; // the lane's own ball, loose groups only
         const unsigned loose_lanes = __ballot_sync(full, br2 >= 0.f);
@@ -977,6 +981,17 @@ __global__ void __launch_bounds__(32 * kCoopWarps) nn_grid_coop_kernel(const Reg
             __syncwarp();
             coop_batch(buf, (fill + 3) & ~3, sorted, p, qx, qy, qz, A, live, best, bb);
             __syncwarp();
+        }
+        // a lane that found nothing borrows its neighbours' finds: their best targets are real candidates a few
+        // centimetres further away, which bounds the lane's next ball far better than quadrupling the radius
+        const bool empty_handed = !done && !(best.d < CUDART_INF_F);
+        if (__any_sync(full, empty_handed)) {
+            for (unsigned src = __ballot_sync(full, best.d < CUDART_INF_F); src; src &= src - 1) {
+                const int j = __ffs(src) - 1;
+                const float4 t = make_float4(__shfl_sync(full, bb.x, j), __shfl_sync(full, bb.y, j), __shfl_sync(full, bb.z, j),
+                                             __int_as_float(__shfl_sync(full, best.i, j)));
+                if (empty_handed) coop_take(p, t, best, bb);
+            }
         }
         if (!done) {
             // finished: the best lies inside the searched ball (or the whole acceptance ball was searched)
