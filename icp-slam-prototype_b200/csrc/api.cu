@@ -257,7 +257,10 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         if (!(h > 0.f)) {
             const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
             const float area = 2.f * (ex * ey + ey * ez + ez * ex) / 3.f;
-            h = sqrtf(50.f * std::max(area, 1e-6f) / (float)m);
+            // ~90 points per occupied cell for the cooperative search (its cost per cell is a fixed few dozen
+            // instructions per warp; measured optimum 0.10 m on the full-resolution pair), ~50 for the per-thread walk
+            const float per_cell = env_int("ICPB_GRID_COOP_CM", 1000) > 0 ? (float)env_int("ICPB_GRID_CELL_PTS", 90) : 50.f;
+            h = sqrtf(per_cell * std::max(area, 1e-6f) / (float)m);
             h = std::min(std::max(h, 0.01f), 0.2f);
         }
         for (;;) {

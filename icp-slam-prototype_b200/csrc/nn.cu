@@ -733,6 +733,17 @@ __device__ __forceinline__ double warp_fold(double v)
     return v;
 }
 
+// The value warp_fold leaves in lane 0, computed by ONE thread from the 32 inputs x[0..31].  The shuffle steps give
+// v16[l] = x[l] + x[l+16], v8[l] = v16[l] + v16[l+8], ..., v1[0] = v2[0] + v2[1]; with F<l, 32> = x[l] and
+// F<l, s> = F<l, 2s> + F<l+s, 2s> that is F<0, 1>: the same additions in the same association, evaluated depth first
+// (five live partial sums).
+template <int L, int S>
+__device__ __forceinline__ double fold_tree(const double *x)
+{
+    if constexpr (S == 32) return x[L];
+    else return fold_tree<L, 2 * S>(x) + fold_tree<L + S, 2 * S>(x);
+}
+
 // --------------------------------------------------------------------------
 // 3x3 SVD (one-sided Jacobi, double) -- stands in for cv::SVD, icp.cpp:215.
 // Same operation sequence as the host-side oracle so results are bit equal.
@@ -994,7 +1005,7 @@ struct FinalizeShared {
 __device__ __forceinline__ void finalize_tail(const RegDesc &d, IcpState *st, const IcpParamsDev *__restrict__ prm, int pass,
                                               int chunk, int nchunks, int tid, bool valid, int i, int n, const float4 a,
                                               int best_i, float best_d, const float4 best_b, bool have_b, int n_amb,
-                                              FinalizeShared &sh)
+                                              FinalizeShared &sh, double *fold_buf = nullptr)
 {
     double (&s_w)[kChunk / 32][kTerms] = sh.w;
     int &s_last = sh.last;
@@ -1028,10 +1039,26 @@ __device__ __forceinline__ void finalize_tail(const RegDesc &d, IcpState *st, co
         default: return 1.0;
         }
     };
+    if (fold_buf) {
+        // The same fold tree (v[l] += v[l + off], off = 16, 8, 4, 2, 1) evaluated from shared memory: every thread
+        // stores its twenty terms, then one thread per (group of 32, term) adds the 32 values depth first in exactly the
+        // shuffle tree's association -- 320 warp-level shared-memory operations per chunk instead of 1,600 shuffles
+        // (the shuffle version kept the LSU pipe 60 % busy and cost 46 us per pass at full resolution).
+        // layout [term][group][33]: stores run along the lanes, loads see a two-way bank conflict at worst
 #pragma unroll
-    for (int k = 0; k < kTerms; ++k) {
-        const double v = warp_fold(term(k));
-        if ((tid & 31) == 0) s_w[tid >> 5][k] = v;
+        for (int k = 0; k < kTerms; ++k) fold_buf[(k * (kChunk / 32) + (tid >> 5)) * 33 + (tid & 31)] = term(k);
+        __syncthreads();
+        if (tid < kTerms * (kChunk / 32)) {
+            const int g = tid % (kChunk / 32), k = tid / (kChunk / 32);
+            const double *x = fold_buf + (k * (kChunk / 32) + g) * 33;
+            s_w[g][k] = fold_tree<0, 1>(x);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kTerms; ++k) {
+            const double v = warp_fold(term(k));
+            if ((tid & 31) == 0) s_w[tid >> 5][k] = v;
+        }
     }
     __syncthreads();
     if (tid < kTerms) {
@@ -1338,7 +1365,7 @@ __global__ void __launch_bounds__(2 * kChunk) nn_finalize_kernel(const RegDesc *
 // ICPB_NN_GRID with the cooperative search: the association arrives as one 16-byte record per query (the neighbour's
 // coordinates and index, grid.cu); nothing to resolve, so the kernel is the tail alone -- 256 threads, few registers,
 // eight CTAs per SM instead of the two of the general kernel (whose 59 us per pass were a third of a registration).
-__global__ void __launch_bounds__(kChunk, 6) nn_finalize_coop_kernel(const RegDesc *__restrict__ descs, IcpState *states,
+__global__ void __launch_bounds__(kChunk, 5) nn_finalize_coop_kernel(const RegDesc *__restrict__ descs, IcpState *states,
                                                                   const IcpParamsDev *__restrict__ prm, int pass)
 {
     IcpState *st = states + blockIdx.z;
@@ -1352,6 +1379,7 @@ __global__ void __launch_bounds__(kChunk, 6) nn_finalize_coop_kernel(const RegDe
     const int i = chunk * kChunk + tid;
     const bool valid = i < n;
     __shared__ FinalizeShared s_fin;
+    __shared__ double s_fold[kTerms * (kChunk / 32) * 33];
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), best_b = a;
     int best_i = -1;
     float best_d = CUDART_INF_F;
@@ -1365,7 +1393,7 @@ __global__ void __launch_bounds__(kChunk, 6) nn_finalize_coop_kernel(const RegDe
             best_d = exact_distance(a.x, a.y, a.z, nb.x, nb.y, nb.z); // same inputs, same arithmetic: the search's own bits
         }
     }
-    finalize_tail(d, st, prm, pass, chunk, nchunks, tid, valid, i, n, a, best_i, best_d, best_b, have_b, 0, s_fin);
+    finalize_tail(d, st, prm, pass, chunk, nchunks, tid, valid, i, n, a, best_i, best_d, best_b, have_b, 0, s_fin, s_fold);
 }
 
 void launch_nn_finalize(const RegDesc *descs, IcpState *states, const IcpParamsDev *prm, int batch, int max_n, int splits,
