@@ -225,18 +225,25 @@ def run_map1cm(args, rank, world, local, emit=True):
     depths = [synth.render_depth(R, t, synth.KINECT_V1, seed=f) for f, (R, t) in enumerate(poses)]
     Rs = np.stack([np.asarray(R, np.float32) for R, _ in poses])
     ts = np.stack([np.asarray(t, np.float32) for _, t in poses])
-    # slab boundaries balanced on the ray work of three frames of the sequence (host-side, identical on every rank)
+    # slab boundaries balanced on the MEASURED work of the ray walk: three frames of the sequence go through a scratch
+    # whole map twice (the second time the bricks their endpoints occupy are there) with the per-layer work histogram
+    # switched on; equal shares of it are equal shares of the walk.  Every rank computes the same integers: no exchange.
     bounds = None
     if world > 1:
         probe = ctx.cloud(640 * 480)
-        oz, ez = [], []
-        for f in (0, frames // 2, frames - 1):
-            R, t = poses[f]
-            probe.from_depth(depths[f], None, K)
-            probe.transform(np.asarray(R, np.float32), np.asarray(t, np.float32))
-            ez.append(probe.download()["z"].astype(np.float64)); oz.append(float(t[2]))
-        bounds = D.balanced_slab_bounds(dims[2], world, cell, oz, ez)
-        probe.close()
+        scratch = ctx.map(dims, cell)
+        work = np.zeros(dims[2], np.uint64)
+        for rep in range(2):
+            for f in (0, frames // 2, frames - 1):
+                R, t = poses[f]
+                probe.from_depth(depths[f], None, K)
+                probe.transform(np.asarray(R, np.float32), np.asarray(t, np.float32))
+                if rep == 0:
+                    scratch.integrate_rays(probe, tuple(float(x) for x in t), 25, 25, False)
+                else:
+                    scratch.integrate_rays_profiled(probe, tuple(float(x) for x in t), work, 25, 25)
+        bounds = icpb200.slab_bounds_from_work(work, world)
+        probe.close(); scratch.close()
     comm = icpb200.Comm.from_torch(ctx) if world > 1 else None
     sm = icpb200.SlabMapC(ctx, comm, dims, cell, 640, 480, bounds)
 
@@ -333,7 +340,7 @@ def run_map1cm(args, rank, world, local, emit=True):
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": {"workload": f"configs[4]: {frames} full-res Kinect v1 frames into a 600x600x500 1 cm uint8 grid "
-                                       "(180 MB), z-slab sharded (boundaries balanced on ray work); every rank lifts its row "
+                                       "(180 MB), z-slab sharded (boundaries at equal shares of the measured per-layer walk work); every rank lifts its row "
                                        f"band, one NCCL all-gather per {fpe} frames inside libicpb200 (double buffered, three "
                                        "streams), bands walked in place; depth frames resident in HBM, no host "
                                        "synchronisation inside the sequence",

@@ -1365,6 +1365,58 @@ int icpb_map_integrate_rays(icpb_map *map, const icpb_cloud *points, const float
     return ICPB_OK;
 }
 
+int icpb_map_integrate_rays_profiled(icpb_map *map, const icpb_cloud *points, const float origin[3], int delta_dec,
+                                     int delta_inc, unsigned long long *layer_work)
+{
+    if (!map || !points || !origin || !layer_work) return ICPB_ERR_INVALID;
+    icpb_ctx *ctx = map->ctx;
+    if (delta_dec < 0 || delta_dec > 255 || delta_inc < 0 || delta_inc > 255)
+        return fail(ctx, ICPB_ERR_INVALID, "delta out of [0,255]");
+    if (map->dev.z_lo != 0 || map->dev.z_hi != map->dev.dims[2])
+        return fail(ctx, ICPB_ERR_INVALID, "icpb_map_integrate_rays_profiled needs a whole-map handle");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int layers = map->dev.dims[2];
+    void *misc, *hist;
+    int rc;
+    if ((rc = ws_get(ctx, WS_MISC, 64, &misc, true))) return rc;
+    if ((rc = ws_get(ctx, WS_FRAME, sizeof(unsigned int) * (size_t)layers, &hist))) return rc;
+    unsigned int *d_next = (unsigned int *)((char *)misc + 40);
+    CU(ctx, cudaMemsetAsync(hist, 0, sizeof(unsigned int) * (size_t)layers, ctx->stream));
+    launch_map_rays(map->dev, flat_src(points->d_pts, points->n), origin, delta_dec, nullptr, d_next, ctx->sm_count, ctx->stream,
+                    (unsigned int *)hist);
+    launch_map_endpoints(map->dev, flat_src(points->d_pts, points->n), ICPB_RULE_A, delta_inc, 0, ctx->stream);
+    ctx->launches += 2 * (points->n > 0);
+    std::vector<unsigned int> h((size_t)layers);
+    CU(ctx, cudaMemcpyAsync(h.data(), hist, sizeof(unsigned int) * (size_t)layers, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaGetLastError());
+    for (int z = 0; z < layers; ++z) layer_work[z] += h[(size_t)z];
+    return ICPB_OK;
+}
+
+int icpb_slab_bounds_from_work(const unsigned long long *work, int layers, int world, int *bounds)
+{
+    if (!work || !bounds || layers <= 0 || world <= 0 || world > layers) return ICPB_ERR_INVALID;
+    long double total = 0;
+    for (int z = 0; z < layers; ++z) total += (long double)work[z] + 1e-3L; // tiny floor: empty layers still get an owner
+    bounds[0] = 0;
+    long double acc = 0;
+    int z = 0;
+    for (int g = 1; g < world; ++g) {
+        const long double want = total * g / world;
+        while (z < layers && acc + (long double)work[z] + 1e-3L <= want) { acc += (long double)work[z] + 1e-3L; ++z; }
+        // the boundary sits where the running sum is closest to the quantile, leaving room for the slabs still to come
+        int b = z;
+        if (z < layers && (want - acc) > ((long double)work[z] + 1e-3L) / 2) b = z + 1;
+        b = std::max(b, bounds[g - 1] + 1);
+        b = std::min(b, layers - (world - g));
+        bounds[g] = b;
+        while (z < b) { acc += (long double)work[z] + 1e-3L; ++z; }
+    }
+    bounds[world] = layers;
+    return ICPB_OK;
+}
+
 // ---- sync-free frame path (multi-GPU z-slab map and the single-GPU sequence alike) --------------------------------
 // The point count of a lifted frame never visits the host: it travels in the band's header row and every consumer
 // kernel reads it from device memory, so a sequence of frames is enqueued without a single host synchronisation.

@@ -219,7 +219,8 @@ void launch_map_endpoints(const MapDev &m, const PointSrc &src, int rule, int de
 void launch_map_tracked(const MapDev &m, int *table, const float4 *pts, int n, int variant, int delta, int max_conf,
                         float4 *dst, int dst_n, int dst_capacity, int *d_appended, int table_base, cudaStream_t s);
 void launch_map_rays(const MapDev &m, const PointSrc &src, const float origin[3], int delta_dec,
-                     unsigned long long *visited, unsigned int *next_ray, int sm_count, cudaStream_t s);
+                     unsigned long long *visited, unsigned int *next_ray, int sm_count, cudaStream_t s,
+                     unsigned int *layer_work = nullptr);
 
 // ---- helpers of api.cu used by comm.cu ------------------------------------------------------------------------
 int api_fail(icpb_ctx *ctx, int status, const char *what, cudaError_t ce = cudaSuccess);

@@ -584,10 +584,13 @@ __device__ __forceinline__ void ray_jump(const MapDev &m, RayBrick<I> &r)
     r.ex += (I)cx * r.dxs; r.ey += (I)cy * r.dys; r.ez += (I)cz * r.dzs;
 }
 
+// layer_work (nullable, dims[2] words): calibration of the z-slab boundaries -- every step adds 1 and every jump 4 (their
+// relative instruction cost) to the z-layer it happens in, so that equal shares of the histogram are equal shares of
+// this kernel's work (icpb_map_integrate_rays_profiled).
 template <typename I>
 __global__ void __launch_bounds__(128) map_rays_brick_kernel(MapDev m, PointSrc src, int ox, int oy,
                                                             int oz, int delta_dec, unsigned long long *visited,
-                                                            unsigned int *next_ray)
+                                                            unsigned int *next_ray, unsigned int *layer_work)
 {
     SrcView sv;
     src_open(src, sv);
@@ -614,7 +617,10 @@ __global__ void __launch_bounds__(128) map_rays_brick_kernel(MapDev m, PointSrc 
             base = __shfl_sync(0xffffffffu, base, 0);
             if (r.rem <= 0) {
                 const unsigned i = base + (unsigned)__popc(idle & lt);
-                if (i < (unsigned)n) ray_setup_brick<I>(m, src_point(src, sv, (int)i), ox, oy, oz, delta_dec, r, my_visits);
+                if (i < (unsigned)n) {
+                    ray_setup_brick<I>(m, src_point(src, sv, (int)i), ox, oy, oz, delta_dec, r, my_visits);
+                    if (layer_work && r.rem > 0) atomicAdd(&layer_work[r.zr + m.z_lo], 6u);
+                }
             }
             drained = base + (unsigned)__popc(idle) >= (unsigned)n;
         }
@@ -625,6 +631,7 @@ __global__ void __launch_bounds__(128) map_rays_brick_kernel(MapDev m, PointSrc 
 #pragma unroll 1
         for (int k = 0; k < kRayBurst / kRayGroup; ++k) {
             if (r.rem > 0 && r.empty) {
+                if (layer_work) atomicAdd(&layer_work[r.zr + m.z_lo], 4u);
                 if (r.empty2) ray_jump<I, kBrick2Log>(m, r);
                 else ray_jump<I, kBrickLog>(m, r);
             }
@@ -648,6 +655,7 @@ __global__ void __launch_bounds__(128) map_rays_brick_kernel(MapDev m, PointSrc 
                     --r.rem;
                     if ((unsigned)r.zr >= zs) { r.rem = 0; halt = true; } // left the slab for good
                     else {
+                        if (layer_work) atomicAdd(&layer_work[r.zr + m.z_lo], 1u);
                         // the coordinate that moved tells whether a brick boundary (fine, coarse) was crossed
                         const int c = px ? r.x : (py ? r.y : r.zr);
                         const int s = px ? sx : (py ? sy : sz);
@@ -677,7 +685,7 @@ __global__ void __launch_bounds__(128) map_rays_brick_kernel(MapDev m, PointSrc 
 }
 
 void launch_map_rays(const MapDev &m, const PointSrc &src, const float origin[3], int delta_dec,
-                     unsigned long long *visited, unsigned int *next_ray, int sm_count, cudaStream_t s)
+                     unsigned long long *visited, unsigned int *next_ray, int sm_count, cudaStream_t s, unsigned int *layer_work)
 {
     const int n = src.n;
     if (n <= 0) return;
@@ -696,9 +704,9 @@ void launch_map_rays(const MapDev &m, const PointSrc &src, const float origin[3]
     static const bool bricks = []() { const char *e = getenv("ICPB_RAY_BRICKS"); return !(e && *e == '0'); }();
     if (bricks) { // default: cross empty bricks in one jump
         if (prod < 2147483647.0)
-            map_rays_brick_kernel<int><<<blocks, 128, 0, s>>>(m, src, o[0], o[1], o[2], delta_dec, visited, next_ray);
+            map_rays_brick_kernel<int><<<blocks, 128, 0, s>>>(m, src, o[0], o[1], o[2], delta_dec, visited, next_ray, layer_work);
         else
-            map_rays_brick_kernel<long long><<<blocks, 128, 0, s>>>(m, src, o[0], o[1], o[2], delta_dec, visited, next_ray);
+            map_rays_brick_kernel<long long><<<blocks, 128, 0, s>>>(m, src, o[0], o[1], o[2], delta_dec, visited, next_ray, layer_work);
         return;
     }
     // ICPB_RAY_BRICKS=0: the byte-at-a-time walk (kept for A/B measurements)

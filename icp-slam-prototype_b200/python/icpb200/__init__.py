@@ -396,6 +396,12 @@ class Map:
                                                            C.byref(v) if count_visits else None))
         return v.value
 
+    def integrate_rays_profiled(self, cloud, origin, layer_work, delta_dec=25, delta_inc=25):
+        """Integration + per-z-layer work histogram of the ray walk, accumulated into layer_work (uint64[dims[2]])."""
+        o = (C.c_float * 3)(*origin)
+        assert layer_work.dtype == np.uint64 and len(layer_work) == self.dims[2]
+        self.ctx.check(self.ctx.lib.icpb_map_integrate_rays_profiled(self.h, cloud.h, o, delta_dec, delta_inc, _p(layer_work)))
+
     def integrate_bands_device(self, d_bands, world, band_capacity, origin, delta_dec=25, delta_inc=25):
         """Sync-free: `world` device-resident bands -> ray decrements + endpoint increments on this slab."""
         o = (C.c_float * 3)(*origin)
@@ -432,6 +438,16 @@ def comm_unique_id():
     if rc != OK:
         raise IcpbError(rc, load().icpb_last_error(None).decode())
     return bytes(buf)
+
+
+def slab_bounds_from_work(work, world):
+    """z-slab boundaries [0, ..., layers] with equal shares of the per-layer work histogram."""
+    work = np.ascontiguousarray(work, dtype=np.uint64)
+    b = (C.c_int * (world + 1))()
+    rc = load().icpb_slab_bounds_from_work(_p(work), len(work), int(world), b)
+    if rc != OK:
+        raise IcpbError(rc, "icpb_slab_bounds_from_work")
+    return list(b)
 
 
 class Comm:

@@ -277,6 +277,14 @@ int icpb_map_has_entry(icpb_map *map, const float p[3], int *has_entry);
  * origin voxel, decrements with clamp at 0, then rule-A endpoint increments. */
 int icpb_map_integrate_rays(icpb_map *map, const icpb_cloud *points, const float origin[3],
                             int delta_dec, int delta_inc, long long *voxels_visited);
+/* The same integration, and in addition the WORK the ray walk spends per z-layer is accumulated into layer_work (host,
+ * dims[2] entries, added to): 1 per voxel step, 4 per brick jump, 6 per ray set-up -- their relative cost.  Equal shares of
+ * the histogram are equal shares of the walk: icpb_slab_bounds_from_work turns it into z-slab boundaries.  Calibration
+ * call (it synchronises and uses atomics per step); whole-map handles only. */
+int icpb_map_integrate_rays_profiled(icpb_map *map, const icpb_cloud *points, const float origin[3], int delta_dec,
+                                     int delta_inc, unsigned long long *layer_work);
+/* bounds[0..world]: bounds[0] = 0, bounds[world] = layers, every slab at least one layer, equal shares of `work`. */
+int icpb_slab_bounds_from_work(const unsigned long long *work, int layers, int world, int *bounds);
 /* Map::getVoxelCoordinates map.cpp:55-85 (host-side scalar helper). */
 /* Sync-free frame path (the z-slab map of SURVEY.md 8e, and frame sequences on one GPU).  A "band" is one 16-byte
  * header row (point count in its first word) followed by band_capacity point rows, in device memory.

@@ -381,3 +381,24 @@ def test_slabmap_sequence_single_rank_matches_oracle(ctx, orc, fpe):
         orc.map_integrate_rays(want, dims, cell, pts, tuple(float(x) for x in t), 25, 25)
     assert np.array_equal(sm.download(), want)
     sm.close()
+
+
+def test_profiled_integration_same_grid_and_a_work_histogram(ctx, orc):
+    """icpb_map_integrate_rays_profiled: the calibration call behind the z-slab boundaries changes nothing in the grid."""
+    import icpb200
+    dims, cell = (150, 150, 125), 0.04
+    m = ctx.map(dims, cell)
+    grid = np.zeros(dims, np.uint8)
+    work = np.zeros(dims[2], np.uint64)
+    for f in range(2):
+        pts, origin = _world_cloud(orc, f, stride=3)
+        c = ctx.cloud_from_points(pts)
+        m.integrate_rays_profiled(c, origin, work, 25, 25)
+        v = orc.map_integrate_rays(grid, dims, cell, pts, origin, 25, 25)
+        c.close()
+        assert 0 < int(work.sum()) <= 6 * len(pts) * (f + 1) + 4 * 2 * v * (f + 1)
+    assert np.array_equal(m.download(), grid)
+    b = icpb200.slab_bounds_from_work(work, 4)
+    shares = [int(work[b[g]:b[g + 1]].sum()) for g in range(4)]
+    assert max(shares) <= work.sum() / 4 + work.max() + 1
+    m.close()
