@@ -400,7 +400,8 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         } else launch_nn_partial(d_descs, d_states, count, max_n, qpt, splits, pass, filter, st);
         if (prof) CU(ctx, cudaEventRecord(ctx->prof_events[2 * pass + 1], st));
         const int spf = span_begin(ctx, ICPB_PROF_NN_FINALIZE);
-        launch_nn_finalize(d_descs, d_states, d_prm, count, max_n, grid_mode ? (coop_r > 0.f ? -1 : 0) : splits, pass, filter, st);
+        launch_nn_finalize(d_descs, d_states, d_prm, count, max_n, grid_mode ? (coop_r > 0.f ? -1 : 0) : splits, pass, filter, st,
+                           grid_mode ? h_descs[0].D[(pass + 1) & 1] : nullptr, d_gnb);
         span_end(ctx, spf);
         launches += grid_mode ? 3 : 2;
     }

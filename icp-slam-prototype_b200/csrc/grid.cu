@@ -671,9 +671,12 @@ __device__ __forceinline__ float sqrt_approx(float x)
 constexpr int kCoopCap = ICPB_COOP_CAP;   // candidates per warp batch (20 B each in shared memory)
 constexpr int kCoopWarps = 4;
 #ifndef ICPB_COOP_GROUP
-#define ICPB_COOP_GROUP 8
+#define ICPB_COOP_GROUP 4
 #endif
 constexpr int kCoopGroup = ICPB_COOP_GROUP; // lanes per bounding sphere of the region test (1 = every query's own ball)
+#ifndef ICPB_COOP_MINB
+#define ICPB_COOP_MINB 5
+#endif
 
 struct CoopBuf {
     float xs[kCoopCap], ys[kCoopCap], zs[kCoopCap], ns[kCoopCap]; // centred candidates, SoA
@@ -769,7 +772,7 @@ __device__ __forceinline__ void coop_batch(const CoopBuf &b, int fill, const flo
     if (__any_sync(0xffffffffu, amb)) coop_rescan(b, fill, sorted, p, qx, qy, qz, amb ? lim : -CUDART_INF_F, best, bb);
 }
 
-__global__ void __launch_bounds__(32 * kCoopWarps) nn_grid_coop_kernel(const RegDesc *__restrict__ descs, int pass, float coop_r)
+__global__ void __launch_bounds__(32 * kCoopWarps, ICPB_COOP_MINB) nn_grid_coop_kernel(const RegDesc *__restrict__ descs, int pass, float coop_r)
 {
     const RegDesc &d = descs[blockIdx.z];
     IcpState *st = d.st;

@@ -131,7 +131,8 @@ void launch_target_prep(const float4 *tgt, int m, float *soa, int ngroups, cudaS
 void launch_nn_partial(const RegDesc *descs, IcpState *states, int batch, int max_n, int qpt, int splits, int pass,
                        int filter, cudaStream_t s);
 void launch_nn_finalize(const RegDesc *descs, IcpState *states, const IcpParamsDev *prm, int batch, int max_n,
-                        int splits, int pass, int filter, cudaStream_t s);
+                        int splits, int pass, int filter, cudaStream_t s, const float4 *q_cur = nullptr,
+                        const float4 *q_nb = nullptr);
 // n_dev (nullable): the point count lives on the device (sync-free frame path); n is then the capacity
 void launch_transform(float4 *pts, int n, const float *R, const float *t, int have_R, int have_t,
                       cudaStream_t s, const int *n_dev = nullptr);

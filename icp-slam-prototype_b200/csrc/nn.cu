@@ -1066,9 +1066,11 @@ __device__ __forceinline__ void finalize_tail(const RegDesc &d, IcpState *st, co
         for (int wv = 1; wv < kChunk / 32; ++wv) s = s + s_w[wv][tid];
         d.chunk_sums[(size_t)chunk * kTerms + tid] = s;
     }
-    __threadfence();
+    // the barrier orders the chunk sums written by threads 0..19 before thread 0's fence, and the fence (cumulative)
+    // before its ticket: one thread waits for the memory system instead of 256
     __syncthreads();
     if (tid == 0) {
+        __threadfence();
         if (n_amb) atomicAdd(&st->rescans, n_amb);
         unsigned int ticket = atomicAdd(&st->block_counter, 1u);
         s_last = (ticket == (unsigned int)(nchunks - 1));
@@ -1365,14 +1367,23 @@ __global__ void __launch_bounds__(2 * kChunk) nn_finalize_kernel(const RegDesc *
 // ICPB_NN_GRID with the cooperative search: the association arrives as one 16-byte record per query (the neighbour's
 // coordinates and index, grid.cu); nothing to resolve, so the kernel is the tail alone -- 256 threads, few registers,
 // eight CTAs per SM instead of the two of the general kernel (whose 59 us per pass were a third of a registration).
+// q_cur / q_nb / q_n (count == 1: known to the host): the kernel's first loads go out at once instead of behind two
+// dependent reads of the descriptor -- the kernel is a chain of memory round trips, not work.
 __global__ void __launch_bounds__(kChunk, 5) nn_finalize_coop_kernel(const RegDesc *__restrict__ descs, IcpState *states,
-                                                                  const IcpParamsDev *__restrict__ prm, int pass)
+                                                                  const IcpParamsDev *__restrict__ prm, int pass,
+                                                                  const float4 *__restrict__ q_cur,
+                                                                  const float4 *__restrict__ q_nb, int q_n)
 {
     IcpState *st = states + blockIdx.z;
+    const int chunk = blockIdx.x;
+    float4 a_early = make_float4(0.f, 0.f, 0.f, 0.f), nb_early = a_early;
+    if (q_cur && chunk * kChunk + (int)threadIdx.x < q_n) {
+        a_early = q_cur[chunk * kChunk + threadIdx.x];
+        nb_early = __ldcg(&q_nb[chunk * kChunk + threadIdx.x]);
+    }
     if (st->done) return;
     const RegDesc &d = descs[blockIdx.z];
-    const int n = d.n;
-    const int chunk = blockIdx.x;
+    const int n = q_cur ? q_n : d.n;
     if (chunk * kChunk >= n) return;
     const int nchunks = (n + kChunk - 1) / kChunk;
     const int tid = threadIdx.x;
@@ -1385,8 +1396,8 @@ __global__ void __launch_bounds__(kChunk, 5) nn_finalize_coop_kernel(const RegDe
     float best_d = CUDART_INF_F;
     bool have_b = false;
     if (valid) {
-        a = d.D[(pass + 1) & 1][i];
-        const float4 nb = __ldcg(&d.gnb[i]);
+        a = q_cur ? a_early : d.D[(pass + 1) & 1][i];
+        const float4 nb = q_cur ? nb_early : __ldcg(&d.gnb[i]);
         best_i = __float_as_int(nb.w);
         if (best_i >= 0) {
             best_b = nb; have_b = true;
@@ -1397,11 +1408,11 @@ __global__ void __launch_bounds__(kChunk, 5) nn_finalize_coop_kernel(const RegDe
 }
 
 void launch_nn_finalize(const RegDesc *descs, IcpState *states, const IcpParamsDev *prm, int batch, int max_n, int splits,
-                        int pass, int filter, cudaStream_t s)
+                        int pass, int filter, cudaStream_t s, const float4 *q_cur, const float4 *q_nb)
 {
     dim3 grid((max_n + kChunk - 1) / kChunk, 1, batch);
     if (splits < 0) { // cooperative cell-grid search
-        nn_finalize_coop_kernel<<<grid, kChunk, 0, s>>>(descs, states, prm, pass);
+        nn_finalize_coop_kernel<<<grid, kChunk, 0, s>>>(descs, states, prm, pass, batch == 1 ? q_cur : nullptr, q_nb, max_n);
         return;
     }
     // brute-force modes on few CTAs (a small cloud; latency-bound: 10k points are 40 CTAs on 148 SMs): a pair of

@@ -38,6 +38,11 @@ for r in range(a.repeat):
     print(f"n={dat.n} m={tgt.n} passes={res['nn_passes']} gpu_ms={res['gpu_ms']:.3f} "
           f"nn_partial_ms={res['nn_partial_ms']:.3f} qpt={res['nn_qpt']} splits={res['nn_splits']} cell={res['grid_cell_used']:.3f} "
           f"rescans={res['exact_rescans']}")
+    if not a.noprof and a.grid >= 0:
+        g_ms, g_k = ctx.profile_read(icpb200.PROF_NN_GRID)
+        f_ms, f_k = ctx.profile_read(icpb200.PROF_NN_FINALIZE)
+        print(f"  spans: nn_grid {g_ms:.3f} ms / {g_k} passes = {1e3 * g_ms / max(g_k, 1):.1f} us, "
+              f"nn_finalize {f_ms:.3f} ms / {f_k} = {1e3 * f_ms / max(f_k, 1):.1f} us, rest {res['gpu_ms'] - g_ms - f_ms:.3f} ms")
 if a.map:
     from icpb200 import synth as _s
     cell = a.cm / 100.0
