@@ -69,6 +69,8 @@ struct icpb_comm {
     size_t stage_bytes = 0;
 };
 
+constexpr int kSeqCounters = 4096; // ray counters of a sequence call: one per frame, zeroed by one memset
+
 struct icpb_slabmap {
     icpb_ctx *ctx = nullptr;
     icpb_comm *comm = nullptr;
@@ -212,7 +214,7 @@ int icpb_slabmap_create(icpb_ctx *ctx, icpb_comm *comm, const int dims[3], float
     const size_t ts_bytes = sizeof(unsigned long long) * (3 * (size_t)tiles + 2);
     if (ce == cudaSuccess) ce = cudaMalloc(&sm->tile_state, ts_bytes);
     if (ce == cudaSuccess) ce = cudaMemsetAsync(sm->tile_state, 0, ts_bytes, ctx->stream);
-    if (ce == cudaSuccess) ce = cudaMalloc((void **)&sm->next_ray, 64);
+    if (ce == cudaSuccess) ce = cudaMalloc((void **)&sm->next_ray, sizeof(unsigned int) * kSeqCounters);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
     if (ce != cudaSuccess) { icpb_slabmap_destroy(sm); return api_fail(ctx, ICPB_ERR_CUDA, "icpb_slabmap_create", ce); }
     *out = sm;
@@ -282,6 +284,8 @@ int icpb_slabmap_integrate_sequence_device(icpb_slabmap *sm, const void *d_depth
     if (s_comm) CUC(ctx, cudaStreamWaitEvent(s_comm, sm->ev_join, 0));
     const size_t frame_px = (size_t)sm->w * sm->h;
     const int groups = (frames + k - 1) / k;
+    const bool fresh_counters = frames <= kSeqCounters;
+    if (fresh_counters) CUC(ctx, cudaMemsetAsync(sm->next_ray, 0, sizeof(unsigned int) * (size_t)frames, s_main));
     for (int g = 0; g < groups; ++g) {
         const int b = g & 1;
         const int f0 = g * k, kk = std::min(k, frames - f0);
@@ -320,7 +324,8 @@ int icpb_slabmap_integrate_sequence_device(icpb_slabmap *sm, const void *d_depth
             const int f = f0 + j;
             const PointSrc src = band_src(src_base + band_rows * j, sm->world, sm->band_cap, stride);
             int sp = api_span_begin(ctx, ICPB_PROF_MAP_RAYS);
-            launch_map_rays(sm->map->dev, src, t + 3 * f, delta_dec, nullptr, sm->next_ray, ctx->sm_count, s_main);
+            launch_map_rays(sm->map->dev, src, t + 3 * f, delta_dec, nullptr, fresh_counters ? sm->next_ray + f : sm->next_ray,
+                            ctx->sm_count, s_main, fresh_counters ? kCounterIsZero : nullptr);
             api_span_end(ctx, sp);
             sp = api_span_begin(ctx, ICPB_PROF_MAP_ENDPOINTS);
             launch_map_endpoints(sm->map->dev, src, ICPB_RULE_A, delta_inc, 0, s_main);

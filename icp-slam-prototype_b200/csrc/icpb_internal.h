@@ -222,6 +222,7 @@ void launch_map_tracked(const MapDev &m, int *table, const float4 *pts, int n, i
 void launch_map_rays(const MapDev &m, const PointSrc &src, const float origin[3], int delta_dec,
                      unsigned long long *visited, unsigned int *next_ray, int sm_count, cudaStream_t s,
                      unsigned int *layer_work = nullptr);
+extern unsigned int *const kCounterIsZero; // pass as layer_work: next_ray is already zero, skip the memset
 
 // ---- helpers of api.cu used by comm.cu ------------------------------------------------------------------------
 int api_fail(icpb_ctx *ctx, int status, const char *what, cudaError_t ce = cudaSuccess);

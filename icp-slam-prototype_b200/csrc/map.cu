@@ -507,14 +507,20 @@ __device__ __forceinline__ void ray_setup_brick(const MapDev &m, const float4 p,
     bool live = true, entered_now = false;
     // slab clipping: see ray_setup above
     if (oz < m.z_lo || oz >= m.z_hi) {
-        long long k = 0;
-        if (sz > 0 && oz < m.z_lo) k = (long long)m.z_lo - oz;
-        else if (sz < 0 && oz >= m.z_hi) k = (long long)oz - (m.z_hi - 1);
+        int k = 0;
+        if (sz > 0 && oz < m.z_lo) k = m.z_lo - oz;
+        else if (sz < 0 && oz >= m.z_hi) k = oz - (m.z_hi - 1);
         if (k <= 0 || k > nz) live = false;
         else {
-            cz = (int)k;
-            cx = nx ? (int)min((long long)nx, ((2 * k - 1) * nx + nz) / (2LL * nz)) : 0;
-            cy = ny ? (int)min((long long)ny, ((2 * k - 1) * ny + nz) / (2LL * nz)) : 0;
+            cz = k;
+            // (2k - 1) n + nz < 2 dims^2: 32-bit for every grid the int walk serves, 64-bit otherwise
+            if (sizeof(I) == 4) {
+                cx = nx ? min(nx, (int)(((unsigned)(2 * k - 1) * (unsigned)nx + (unsigned)nz) / (2u * (unsigned)nz))) : 0;
+                cy = ny ? min(ny, (int)(((unsigned)(2 * k - 1) * (unsigned)ny + (unsigned)nz) / (2u * (unsigned)nz))) : 0;
+            } else {
+                cx = nx ? (int)min((long long)nx, ((2LL * k - 1) * nx + nz) / (2LL * nz)) : 0;
+                cy = ny ? (int)min((long long)ny, ((2LL * k - 1) * ny + nz) / (2LL * nz)) : 0;
+            }
             if (nx) r.ex = (I)(2 * cx + 1) * my * mz;
             if (ny) r.ey = (I)(2 * cy + 1) * mx * mz;
             r.ez = (I)(2 * cz + 1) * mx * my;
@@ -684,12 +690,17 @@ __global__ void __launch_bounds__(128) map_rays_brick_kernel(MapDev m, PointSrc 
     }
 }
 
+// layer_work == kCounterIsZero: no histogram, and next_ray already is zero (a fresh counter per frame of a sequence:
+// one memset per sequence instead of one per frame)
+unsigned int *const kCounterIsZero = reinterpret_cast<unsigned int *>(1);
+
 void launch_map_rays(const MapDev &m, const PointSrc &src, const float origin[3], int delta_dec,
                      unsigned long long *visited, unsigned int *next_ray, int sm_count, cudaStream_t s, unsigned int *layer_work)
 {
     const int n = src.n;
     if (n <= 0) return;
-    cudaMemsetAsync(next_ray, 0, sizeof(unsigned int), s);
+    if (!layer_work || layer_work != kCounterIsZero) cudaMemsetAsync(next_ray, 0, sizeof(unsigned int), s);
+    if (layer_work == kCounterIsZero) layer_work = nullptr;
     // persistent grid: every resident warp slot is filled once (40 registers -> 12 CTAs of 128 threads per SM)
     const int blocks = min((n + 127) / 128, sm_count * 12);
     // origin voxel: same quantisation as any point (map.cpp:226 uses getVoxelCoordinates too)
