@@ -403,7 +403,7 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         launch_nn_finalize(d_descs, d_states, d_prm, count, max_n, grid_mode ? (coop_r > 0.f ? -1 : 0) : splits, pass, filter, st,
                            grid_mode ? h_descs[0].D[(pass + 1) & 1] : nullptr, d_gnb);
         span_end(ctx, spf);
-        launches += grid_mode ? 3 : 2;
+        launches += grid_mode ? (coop_r > 0.f ? 4 : 3) : 2;
     }
     launch_pending_translate(d_descs, count, max_n, st);
     ++launches;

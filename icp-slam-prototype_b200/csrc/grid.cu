@@ -825,6 +825,23 @@ __global__ void __launch_bounds__(32 * kCoopWarps, ICPB_COOP_MINB) nn_grid_coop_
             deferred = true; done = true;
         }
     }
+    const int nx = g.dim[0], ny = g.dim[1], nz = g.dim[2];
+    if (!done && pass == 0) {
+        // no previous pass to seed from: the first target of the query's own cell (or of a face neighbour) is a real
+        // candidate a cell edge or so away -- a ball that is searched ONCE, instead of a guess of one cell edge that is
+        // corrected by a second round for every query whose neighbour is farther than that
+        const int c0x = cell_axis(p.x, g.mn[0], g.h, nx), c0y = cell_axis(p.y, g.mn[1], g.h, ny), c0z = cell_axis(p.z, g.mn[2], g.h, nz);
+        const int ox[7] = {0, -1, 1, 0, 0, 0, 0}, oy[7] = {0, 0, 0, -1, 1, 0, 0}, oz[7] = {0, 0, 0, 0, 0, -1, 1};
+#pragma unroll 1
+        for (int k = 0; k < 7 && !(best.d < CUDART_INF_F); ++k) {
+            const int x = c0x + ox[k], y = c0y + oy[k], z = c0z + oz[k];
+            if (x < 0 || y < 0 || z < 0 || x >= nx || y >= ny || z >= nz) continue;
+            const int cell = (z * ny + y) * nx + x;
+            const int t0 = __ldg(&gstart[cell]);
+            if (__ldg(&gstart[cell + 1]) > t0) coop_take(p, __ldg(&sorted[t0]), best, bb);
+        }
+        if (best.d < CUDART_INF_F) rad = best.d;
+    }
     const float max_reach = g.max_nn * 1.00002f + 1e-6f; // nothing beyond the acceptance radius is ever needed (icp.cpp:553)
 
     // ---- warp centre of the centred filter
@@ -842,8 +859,6 @@ __global__ void __launch_bounds__(32 * kCoopWarps, ICPB_COOP_MINB) nn_grid_coop_
     const float ax = valid ? p.x - cx : 0.f, ay = valid ? p.y - cy : 0.f, az = valid ? p.z - cz : 0.f;
     const float A = ((ax * ax + ay * ay) + az * az) * 1.000001f;
     const float qx = -2.f * ax, qy = -2.f * ay, qz = -2.f * az; // W = |t'|^2 - 2 a'.t'
-
-    const int nx = g.dim[0], ny = g.dim[1], nz = g.dim[2];
 
     for (int round = 0; round < 8; ++round) {
         // lanes whose ball outgrew the cooperative phase go to the warp-per-query kernel with their partial best

@@ -1002,6 +1002,7 @@ struct FinalizeShared {
     int last;
 };
 
+template <bool kTicket = true>
 __device__ __forceinline__ void finalize_tail(const RegDesc &d, IcpState *st, const IcpParamsDev *__restrict__ prm, int pass,
                                               int chunk, int nchunks, int tid, bool valid, int i, int n, const float4 a,
                                               int best_i, float best_d, const float4 best_b, bool have_b, int n_amb,
@@ -1066,6 +1067,7 @@ __device__ __forceinline__ void finalize_tail(const RegDesc &d, IcpState *st, co
         for (int wv = 1; wv < kChunk / 32; ++wv) s = s + s_w[wv][tid];
         d.chunk_sums[(size_t)chunk * kTerms + tid] = s;
     }
+    if (!kTicket) return; // the second level and the solve run as their own one-CTA kernel (nn_solve_kernel)
     // the barrier orders the chunk sums written by threads 0..19 before thread 0's fence, and the fence (cumulative)
     // before its ticket: one thread waits for the memory system instead of 256
     __syncthreads();
@@ -1083,9 +1085,9 @@ __device__ __forceinline__ void finalize_tail(const RegDesc &d, IcpState *st, co
     finalize_last_cta(d.chunk_sums, d.mlog, st, prm, pass, nchunks, tid, sh);
 }
 
-__device__ __noinline__ void finalize_last_cta(const double *chunk_sums, float *mlog, IcpState *st,
-                                               const IcpParamsDev *__restrict__ prm, int pass, int nchunks, int tid,
-                                               FinalizeShared &sh)
+__device__ __forceinline__ void finalize_last_cta_body(const double *chunk_sums, float *mlog, IcpState *st,
+                                                       const IcpParamsDev *__restrict__ prm, int pass, int nchunks, int tid,
+                                                       FinalizeShared &sh, bool rearm_ticket)
 {
     double (&s_w)[kChunk / 32][kTerms] = sh.w;
     double (&s_tot)[kTerms] = sh.tot;
@@ -1115,9 +1117,16 @@ __device__ __noinline__ void finalize_last_cta(const double *chunk_sums, float *
     }
     __syncthreads();
     if (tid == 0) {
-        st->block_counter = 0; // re-armed before solve_step copies the state
+        if (rearm_ticket) st->block_counter = 0; // re-armed before solve_step copies the state
         solve_step(st, prm, s_tot, pass, mlog);
     }
+}
+
+__device__ __noinline__ void finalize_last_cta(const double *chunk_sums, float *mlog, IcpState *st,
+                                               const IcpParamsDev *__restrict__ prm, int pass, int nchunks, int tid,
+                                               FinalizeShared &sh)
+{
+    finalize_last_cta_body(chunk_sums, mlog, st, prm, pass, nchunks, tid, sh, true);
 }
 
 // --------------------------------------------------------------------------
@@ -1404,7 +1413,21 @@ __global__ void __launch_bounds__(kChunk, 5) nn_finalize_coop_kernel(const RegDe
             best_d = exact_distance(a.x, a.y, a.z, nb.x, nb.y, nb.z); // same inputs, same arithmetic: the search's own bits
         }
     }
-    finalize_tail(d, st, prm, pass, chunk, nchunks, tid, valid, i, n, a, best_i, best_d, best_b, have_b, 0, s_fin, s_fold);
+    finalize_tail<false>(d, st, prm, pass, chunk, nchunks, tid, valid, i, n, a, best_i, best_d, best_b, have_b, 0, s_fin, s_fold);
+}
+
+// CANON-3 level 2 + the solve for the cooperative search, one CTA per registration with all the registers it wants.
+// Inside nn_finalize_coop_kernel (48 registers for occupancy) the same code ran out of spilled local memory: 43 us of
+// a 49 us kernel were this tail on one SM while 147 idled (profiles/r02_ncu_nn_finalize_coop_tail.txt).
+__global__ void __launch_bounds__(kChunk, 1) nn_solve_kernel(const RegDesc *__restrict__ descs, IcpState *states,
+                                                             const IcpParamsDev *__restrict__ prm, int pass)
+{
+    IcpState *st = states + blockIdx.z;
+    if (st->done) return;
+    const RegDesc &d = descs[blockIdx.z];
+    __shared__ FinalizeShared s_fin;
+    const int nchunks = (d.n + kChunk - 1) / kChunk;
+    finalize_last_cta_body(d.chunk_sums, d.mlog, st, prm, pass, nchunks, threadIdx.x, s_fin, false);
 }
 
 void launch_nn_finalize(const RegDesc *descs, IcpState *states, const IcpParamsDev *prm, int batch, int max_n, int splits,
@@ -1413,6 +1436,7 @@ void launch_nn_finalize(const RegDesc *descs, IcpState *states, const IcpParamsD
     dim3 grid((max_n + kChunk - 1) / kChunk, 1, batch);
     if (splits < 0) { // cooperative cell-grid search
         nn_finalize_coop_kernel<<<grid, kChunk, 0, s>>>(descs, states, prm, pass, batch == 1 ? q_cur : nullptr, q_nb, max_n);
+        nn_solve_kernel<<<dim3(1, 1, batch), kChunk, 0, s>>>(descs, states, prm, pass);
         return;
     }
     // brute-force modes on few CTAs (a small cloud; latency-bound: 10k points are 40 CTAs on 148 SMs): a pair of
