@@ -1043,7 +1043,8 @@ __global__ void __launch_bounds__(32 * kCoopWarps, ICPB_COOP_MINB) nn_grid_coop_
 void launch_nn_grid(const RegDesc *descs, int batch, int max_n, int pass, int sm_count, cudaStream_t s, float coop_r)
 {
     dim3 hgrid(sm_count * 8, 1, batch);
-    if (coop_r > 0.f) { // warp-cooperative search (default), open queries finished from shell 0
+    if (coop_r > 0.f) {
+        hgrid.x = sm_count * 2; // a handful of queries at most reach the fall-back (it strides over its list) // warp-cooperative search (default), open queries finished from shell 0
         dim3 grid((max_n + 32 * kCoopWarps - 1) / (32 * kCoopWarps), 1, batch);
         nn_grid_coop_kernel<<<grid, 32 * kCoopWarps, 0, s>>>(descs, pass, coop_r);
         nn_grid_heavy_kernel<<<hgrid, 128, 0, s>>>(descs, pass, 0);

@@ -72,6 +72,8 @@ enum { ICPB_SOLVE_REFERENCE = 0, /* icp.cpp:199-246: uncentred SVD, offset = mea
  * max_nn_distance - those are rejected by icp.cpp:553 in either mode. */
 enum { ICPB_NN_BRUTE = 0, ICPB_NN_GRID = 1,
        ICPB_NN_AUTO = 2 }; /* GRID when n*m is large enough for the bucketing to pay off, else BRUTE */
+/* The cell build is per registration: icpb_icp_register_batch with count > 1 runs the BRUTE scan whatever nn_mode
+ * says, and says so in icpb_icp_result.nn_mode_used (same associations either way). */
 
 /* Approximate FP32 filter in front of the exact re-evaluation of the BRUTE scan (never visible in the results):
  * CENTRED evaluates |t'|^2 - 2a'.t' about one centre per THREAD (3 FMA per pair + the centring of the targets per
