@@ -18,7 +18,7 @@ thread_local std::string g_create_error;
 enum WsId {
     WS_DESCS = 0, WS_STATES, WS_PARAMS, WS_TGT_SOA, WS_PM1, WS_PM2, WS_PG, WS_IDX, WS_DIST, WS_CHUNKS, WS_ALT,
     WS_IDX_TRACE, WS_DIST_TRACE, WS_MISC, WS_DEPTH, WS_BGR, WS_KEEP, WS_TILESTATE, WS_IMG_A, WS_IMG_B, WS_NORMALS,
-    WS_RT, WS_GRID_META, WS_GRID_COUNTS, WS_GRID_CURSOR, WS_GRID_SUMS, WS_GRID_SORTED, WS_GRID_BBOX, WS_GRID_HEAVY, WS_BATCHSTATE, WS_TRACK, WS_PA, WS_PM3, WS_PG2, WS_MLOG, WS_REJ_FLAG, WS_REJ_PTS, WS_FRAME, WS_PERM, WS_SORT_COUNTS, WS_SORT_SUMS, WS_GRID_NB, WS_GRID_SEED, WS_GRID_BOX, WS_COUNT
+    WS_RT, WS_GRID_META, WS_GRID_COUNTS, WS_GRID_CURSOR, WS_GRID_SUMS, WS_GRID_SORTED, WS_GRID_BBOX, WS_GRID_HEAVY, WS_BATCHSTATE, WS_TRACK, WS_PA, WS_PM3, WS_PG2, WS_MLOG, WS_REJ_FLAG, WS_REJ_PTS, WS_FRAME, WS_PERM, WS_SORT_COUNTS, WS_SORT_SUMS, WS_GRID_NB, WS_GRID_SEED, WS_GRID_BOX, WS_GRID_BOXC, WS_COUNT
 };
 
 int fail(icpb_ctx *ctx, int status, const char *what, cudaError_t ce = cudaSuccess)
@@ -229,7 +229,7 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
     int *d_gcounts = nullptr, *d_gcursor = nullptr, *d_gsums = nullptr;
     float4 *d_gsorted = nullptr;
     int *d_gheavy = nullptr;
-    float4 *d_gnb = nullptr, *d_gseed = nullptr, *d_gbox = nullptr;
+    float4 *d_gnb = nullptr, *d_gseed = nullptr, *d_gbox = nullptr, *d_gboxc = nullptr;
     long long grid_launches = 0;
     if (grid_mode) {
         const int m = regs[0].target->n;
@@ -263,14 +263,18 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
             h = sqrtf(per_cell * std::max(area, 1e-6f) / (float)m);
             h = std::min(std::max(h, 0.01f), 0.2f);
         }
+        // the cooperative search splits every cell into 2 x 2 x 2 children (ICPB_GRID_SUB=1: no children)
+        const bool coop_mode = env_int("ICPB_GRID_COOP_CM", 1000) > 0;
+        gm.sub = (coop_mode && env_int("ICPB_GRID_SUB", 8) == 8) ? 8 : 1;
+        const double cell_cap = gm.sub == 8 ? 4.0e6 : 48.0e6; // counters + boxes stay below ~1.3 GB / ~200 MB
         for (;;) {
             double cells = 1.0;
             for (int k = 0; k < 3; ++k) {
                 gm.dim[k] = std::max(1, (int)floorf((hi[k] - lo[k]) / h) + 1);
                 cells *= gm.dim[k];
             }
-            if (cells <= 48.0e6) break;
-            h *= 1.26f; // coarser cells until the table fits (~192 MB of int counters at most)
+            if (cells <= cell_cap) break;
+            h *= 1.26f; // coarser cells until the tables fit
         }
         for (int k = 0; k < 3; ++k) gm.mn[k] = lo[k];
         gm.h = h;
@@ -280,17 +284,19 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         // per-thread shells out to ~ICPB_GRID_LIGHT_CM (default 45 cm): typical ICP residuals resolve there;
         // the few queries still open (no overlap, far from the target) are finished by one warp each
         gm.light_r = std::max(2, (int)ceilf(0.01f * env_int("ICPB_GRID_LIGHT_CM", 45) / h));
-        const size_t cbytes = sizeof(int) * ((size_t)gm.ncells + 1);
+        const size_t slots = (size_t)gm.ncells * gm.sub; // sorted-array cells (children included)
+        const size_t cbytes = sizeof(int) * (slots + 1);
         if ((rc = ws_get(ctx, WS_GRID_META, sizeof(GridMeta), (void **)&d_gmeta))) return rc;
         if ((rc = ws_get(ctx, WS_GRID_COUNTS, cbytes, (void **)&d_gcounts))) return rc;
         if ((rc = ws_get(ctx, WS_GRID_CURSOR, cbytes, (void **)&d_gcursor))) return rc;
-        if ((rc = ws_get(ctx, WS_GRID_SUMS, sizeof(int) * ((size_t)gm.ncells / 4096 + 8), (void **)&d_gsums))) return rc;
+        if ((rc = ws_get(ctx, WS_GRID_SUMS, sizeof(int) * (slots / 4096 + 8), (void **)&d_gsums))) return rc;
         if ((rc = ws_get(ctx, WS_GRID_SORTED, sizeof(float4) * (size_t)m, (void **)&d_gsorted))) return rc;
         if ((rc = ws_get(ctx, WS_GRID_HEAVY, sizeof(int) * ((size_t)regs[0].data->n + passes + 8), (void **)&d_gheavy))) return rc;
         if ((rc = ws_get(ctx, WS_GRID_NB, sizeof(float4) * (size_t)regs[0].data->n, (void **)&d_gnb))) return rc;
-        if ((rc = ws_get(ctx, WS_GRID_BOX, sizeof(float4) * 2 * (size_t)gm.ncells, (void **)&d_gbox))) return rc;
+        if ((rc = ws_get(ctx, WS_GRID_BOX, sizeof(float4) * 2 * slots, (void **)&d_gbox))) return rc;
+        if (gm.sub == 8 && (rc = ws_get(ctx, WS_GRID_BOXC, sizeof(float4) * 2 * (size_t)gm.ncells, (void **)&d_gboxc))) return rc;
         if ((rc = ws_get(ctx, WS_GRID_SEED, sizeof(float4) * ((size_t)regs[0].data->n + 32), (void **)&d_gseed))) return rc;
-        grid_launches = 8;
+        grid_launches = gm.sub == 8 ? 9 : 8;
     }
 
     // host staging: descs | states | params in one pinned block
@@ -330,6 +336,7 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         d.gsorted = d_gsorted;
         d.gstart = d_gcounts;
         d.gbox = d_gbox;
+        d.gboxc = d_gboxc;
         d.gnb = d_gnb;
         d.gseed = d_gseed;
         d.gheavy = d_gheavy ? d_gheavy + passes + 8 : nullptr;
@@ -371,9 +378,9 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
     }
     if (grid_mode) {
         CU(ctx, cudaMemcpyAsync(d_gmeta, &gm, sizeof(gm), cudaMemcpyHostToDevice, st));
-        CU(ctx, cudaMemsetAsync(d_gcounts, 0, sizeof(int) * ((size_t)gm.ncells + 1), st));
+        CU(ctx, cudaMemsetAsync(d_gcounts, 0, sizeof(int) * ((size_t)gm.ncells * gm.sub + 1), st));
         CU(ctx, cudaMemsetAsync(d_gheavy, 0, sizeof(int) * ((size_t)passes + 8), st));
-        launch_grid_build(h_descs[0].tgt, h_descs[0].m, gm, d_gcounts, d_gcursor, d_gsums, d_gsorted, d_gbox, st);
+        launch_grid_build(h_descs[0].tgt, h_descs[0].m, gm, d_gcounts, d_gcursor, d_gsums, d_gsorted, d_gbox, d_gboxc, st);
         launches += grid_launches;
     } else {
         for (int b = 0; b < count; ++b) {

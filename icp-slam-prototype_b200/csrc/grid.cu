@@ -64,7 +64,13 @@ __device__ __forceinline__ int cell_of(const GridMeta &g, float x, float y, floa
     int cx = cell_axis(x, g.mn[0], g.h, g.dim[0]);
     int cy = cell_axis(y, g.mn[1], g.h, g.dim[1]);
     int cz = cell_axis(z, g.mn[2], g.h, g.dim[2]);
-    return (cz * g.dim[1] + cy) * g.dim[0] + cx; // x fastest
+    const int coarse = (cz * g.dim[1] + cy) * g.dim[0] + cx; // x fastest
+    if (g.sub == 1) return coarse;
+    // 2 x 2 x 2 children: which half of the cell along every axis (any consistent rule will do: the search prunes by the
+    // tight boxes of the points actually assigned, not by the children's nominal cubes)
+    const int sx = (x - (g.mn[0] + cx * g.h)) >= 0.5f * g.h, sy = (y - (g.mn[1] + cy * g.h)) >= 0.5f * g.h;
+    const int sz = (z - (g.mn[2] + cz * g.h)) >= 0.5f * g.h;
+    return coarse * 8 + (sz * 4 + sy * 2 + sx);
 }
 
 __global__ void grid_count_kernel(const float4 *__restrict__ pts, int m, GridMeta g, int *counts)
@@ -192,10 +198,26 @@ __global__ void grid_boxes_kernel(const float4 *__restrict__ sorted, const int *
     boxes[2 * (size_t)c + 1] = make_float4(hx, hy, hz, 0.f);
 }
 
-void launch_grid_build(const float4 *tgt, int m, const GridMeta &g, int *counts, int *cursor, int *block_sums,
-                       float4 *sorted, float4 *boxes, cudaStream_t s)
+// coarse box = union of the eight children's
+__global__ void grid_coarse_boxes_kernel(const float4 *__restrict__ boxes, int ncells, float4 *coarse)
 {
-    const int n = g.ncells + 1;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    float4 lo = boxes[16 * (size_t)c], hi = boxes[16 * (size_t)c + 1];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+        const float4 l = boxes[16 * (size_t)c + 2 * k], h = boxes[16 * (size_t)c + 2 * k + 1];
+        lo.x = fminf(lo.x, l.x); lo.y = fminf(lo.y, l.y); lo.z = fminf(lo.z, l.z);
+        hi.x = fmaxf(hi.x, h.x); hi.y = fmaxf(hi.y, h.y); hi.z = fmaxf(hi.z, h.z);
+    }
+    coarse[2 * (size_t)c] = lo;
+    coarse[2 * (size_t)c + 1] = hi;
+}
+
+void launch_grid_build(const float4 *tgt, int m, const GridMeta &g, int *counts, int *cursor, int *block_sums,
+                       float4 *sorted, float4 *boxes, float4 *coarse_boxes, cudaStream_t s)
+{
+    const int n = g.ncells * g.sub + 1;
     grid_count_kernel<<<(m + 255) / 256, 256, 0, s>>>(tgt, m, g, counts);
     const int nblocks = (n + kScanTile - 1) / kScanTile;
     scan_reduce_kernel<<<nblocks, kScanThreads, 0, s>>>(counts, n, block_sums);
@@ -203,7 +225,9 @@ void launch_grid_build(const float4 *tgt, int m, const GridMeta &g, int *counts,
     scan_apply_kernel<<<nblocks, kScanThreads, 0, s>>>(counts, n, block_sums);
     cudaMemcpyAsync(cursor, counts, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, s);
     grid_scatter_kernel<<<(m + 255) / 256, 256, 0, s>>>(tgt, m, g, cursor, sorted);
-    if (boxes) grid_boxes_kernel<<<(g.ncells + 255) / 256, 256, 0, s>>>(sorted, counts, g.ncells, boxes);
+    if (boxes) grid_boxes_kernel<<<(g.ncells * g.sub + 255) / 256, 256, 0, s>>>(sorted, counts, g.ncells * g.sub, boxes);
+    if (boxes && coarse_boxes && g.sub == 8)
+        grid_coarse_boxes_kernel<<<(g.ncells + 255) / 256, 256, 0, s>>>(boxes, g.ncells, coarse_boxes);
 }
 
 // ---- spatial order of the QUERIES (warp-centred brute-force filter of nn.cu, cooperative grid search) ---------------
@@ -460,8 +484,8 @@ __device__ __forceinline__ void visit_shell(const GridMeta &g, const float4 *__r
                     if (gx * gx + gyz2 > reach2) continue;
                     a = b = x;
                 }
-                const int t0 = __ldg(&start[rowbase + a]);
-                const int t1 = __ldg(&start[rowbase + b + 1]);
+                const int t0 = __ldg(&start[(rowbase + a) * g.sub]);
+                const int t1 = __ldg(&start[(rowbase + b + 1) * g.sub]);
                 for (int t = t0 + lane; t < t1; t += LANES) {
                     const float4 q = __ldg(&sorted[t]);
                     const float ex = p.x - q.x, ey = p.y - q.y, ez = p.z - q.z;
@@ -790,6 +814,7 @@ __global__ void __launch_bounds__(32 * kCoopWarps, ICPB_COOP_MINB) nn_grid_coop_
     const float4 *__restrict__ sorted = d.gsorted;
     const int *__restrict__ gstart = d.gstart;
     const float4 *__restrict__ gbox = d.gbox;
+    const float4 *__restrict__ gboxc = d.gboxc;
 
     // P2 fused into the query load (pointcloud.cpp:321-359), as in nn_grid_kernel
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -837,8 +862,8 @@ __global__ void __launch_bounds__(32 * kCoopWarps, ICPB_COOP_MINB) nn_grid_coop_
             const int x = c0x + ox[k], y = c0y + oy[k], z = c0z + oz[k];
             if (x < 0 || y < 0 || z < 0 || x >= nx || y >= ny || z >= nz) continue;
             const int cell = (z * ny + y) * nx + x;
-            const int t0 = __ldg(&gstart[cell]);
-            if (__ldg(&gstart[cell + 1]) > t0) coop_take(p, __ldg(&sorted[t0]), best, bb);
+            const int t0 = __ldg(&gstart[cell * g.sub]);
+            if (__ldg(&gstart[(cell + 1) * g.sub]) > t0) coop_take(p, __ldg(&sorted[t0]), best, bb);
         }
         if (best.d < CUDART_INF_F) rad = best.d;
     }
@@ -963,35 +988,81 @@ __global__ void __launch_bounds__(32 * kCoopWarps, ICPB_COOP_MINB) nn_grid_coop_
                     if (r + step < 32 && e <= ci) r += step;
                 }
                 const int r_excl = __shfl_sync(full, excl, r), r_base = __shfl_sync(full, rowbase_l, r);
-                int t0 = 0, len = 0;
+                int cell = -1, t0 = 0, len = 0;
                 float4 blo = make_float4(0.f, 0.f, 0.f, 0.f), bhi = blo;
                 if (ci < total) {
-                    const int cell = r_base + (ci - r_excl);
-                    t0 = __ldg(&gstart[cell]);
-                    len = __ldg(&gstart[cell + 1]) - t0;
-                    if (len > 0) { blo = __ldg(&gbox[2 * (size_t)cell]); bhi = __ldg(&gbox[2 * (size_t)cell + 1]); }
+                    cell = r_base + (ci - r_excl);
+                    t0 = __ldg(&gstart[cell * g.sub]);
+                    len = __ldg(&gstart[(cell + 1) * g.sub]) - t0;
+                    const float4 *bx = g.sub == 8 ? gboxc : gbox;
+                    if (len > 0) { blo = __ldg(&bx[2 * (size_t)cell]); bhi = __ldg(&bx[2 * (size_t)cell + 1]); }
                 }
                 const bool need = reaches(blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z) && len > 0;
-                // ---- copy the needed cells into the batch, centred; a full batch is evaluated at once
-                for (unsigned cells = __ballot_sync(full, need); cells; cells &= cells - 1) {
-                    const int rc = __ffs(cells) - 1;
-                    int pos = __shfl_sync(full, t0, rc), remaining = __shfl_sync(full, len, rc);
-                    while (remaining > 0) {
-                        const int take = min(remaining, kCoopCap - fill);
-                        for (int e = lane; e < take; e += 32) {
-                            const float4 t = __ldg(&sorted[pos + e]);
-                            const float tx = t.x - cx, ty = t.y - cy, tz = t.z - cz;
-                            buf.xs[fill + e] = tx; buf.ys[fill + e] = ty; buf.zs[fill + e] = tz;
-                            buf.ns[fill + e] = __fmaf_rn(tz, tz, __fmaf_rn(ty, ty, tx * tx));
-                            buf.gp[fill + e] = pos + e;
+                // stage: the runs of the lanes that hold a needed cell (my_pos, my_len; 0 = none), FLATTENED over the warp
+                // -- element j of their concatenation goes to lane j mod 32, found by a five-step search over the runs'
+                // prefix sums -- so that every load instruction carries 32 targets and consecutive ones are independent
+                // (copying run after run left most lanes idle on the short runs of child cells and exposed one L2
+                // latency per run).  Centred into the batch; a full batch is evaluated at once.
+                auto stage_runs = [&](int my_pos, int my_len) {
+                    int incl2 = my_len;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const int o = __shfl_up_sync(full, incl2, off);
+                        if (lane >= off) incl2 += o;
+                    }
+                    const int all = __shfl_sync(full, incl2, 31);
+                    const int excl2 = incl2 - my_len;
+                    for (int base = 0; base < all;) {
+                        const int take = min(all - base, kCoopCap - fill);
+#pragma unroll 2
+                        for (int e0 = 0; e0 < take; e0 += 32) { // warp-uniform trip count: the search shuffles need every lane
+                            const int e = e0 + lane;
+                            const int j = base + e;
+                            int r = 0; // the last lane whose run starts at or before element j
+#pragma unroll
+                            for (int step = 16; step >= 1; step >>= 1) {
+                                const int x2 = __shfl_sync(full, excl2, (r + step) & 31);
+                                if (r + step < 32 && x2 <= j) r += step;
+                            }
+                            const int src = __shfl_sync(full, my_pos, r) + (j - __shfl_sync(full, excl2, r));
+                            if (e < take) {
+                                const float4 t = __ldg(&sorted[src]);
+                                const float tx = t.x - cx, ty = t.y - cy, tz = t.z - cz;
+                                buf.xs[fill + e] = tx; buf.ys[fill + e] = ty; buf.zs[fill + e] = tz;
+                                buf.ns[fill + e] = __fmaf_rn(tz, tz, __fmaf_rn(ty, ty, tx * tx));
+                                buf.gp[fill + e] = src;
+                            }
                         }
-                        fill += take; pos += take; remaining -= take;
+                        fill += take; base += take;
                         if (fill == kCoopCap) {
                             __syncwarp();
                             coop_batch(buf, fill, sorted, p, qx, qy, qz, A, live, best, bb);
                             __syncwarp();
                             fill = 0;
                         }
+                    }
+                };
+                const unsigned needed = __ballot_sync(full, need);
+                if (g.sub == 1) {
+                    if (needed) stage_runs(t0, need ? len : 0);
+                } else {
+                    // ---- step 3: the eight children of the needed cells, flattened over the lanes again: their own tight
+                    //      boxes decide (half the edge: a quarter of the points a cell would bring along for its rim)
+                    const int kids = 8 * __popc(needed);
+                    for (int kb = 0; kb < kids; kb += 32) {
+                        const int ki = kb + lane;
+                        int k0 = 0, klen = 0;
+                        float4 klo = make_float4(0.f, 0.f, 0.f, 0.f), khi = klo;
+                        const int src = __fns(needed, 0, (ki >> 3) + 1); // lane holding the (ki / 8)-th needed cell
+                        const int pcell = __shfl_sync(full, cell, src & 31);
+                        if (ki < kids) {
+                            const int fine = pcell * 8 + (ki & 7);
+                            k0 = __ldg(&gstart[fine]);
+                            klen = __ldg(&gstart[fine + 1]) - k0;
+                            if (klen > 0) { klo = __ldg(&gbox[2 * (size_t)fine]); khi = __ldg(&gbox[2 * (size_t)fine + 1]); }
+                        }
+                        const bool kneed = reaches(klo.x, klo.y, klo.z, khi.x, khi.y, khi.z) && klen > 0;
+                        if (__any_sync(full, kneed)) stage_runs(k0, kneed ? klen : 0);
                     }
                 }
             }

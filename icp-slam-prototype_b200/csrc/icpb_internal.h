@@ -83,7 +83,8 @@ struct GridMeta {
     float mn[3];   // lower corner of the target's bounding box
     float h;       // cell edge
     int dim[3];    // cells per axis (x fastest in the cell index)
-    int ncells;
+    int ncells;    // coarse cells
+    int sub;       // sorted-array slots per coarse cell: 1, or 8 = every cell split into 2x2x2 children (child index in the low 3 bits)
     int max_r;     // shells needed to cover the acceptance radius
     int light_r;   // shells every query walks on its own thread before it is handed to a whole warp
     float max_nn;  // acceptance radius (MAX_NN_COLOR_DISTANCE, icp.hpp:8)
@@ -119,7 +120,8 @@ struct RegDesc {
     const GridMeta *grid;    // ICPB_NN_GRID only
     const float4 *gsorted;   // targets sorted by cell, w = original index
     const int *gstart;       // [ncells+1] first sorted slot of every cell
-    const float4 *gbox;      // [2 * ncells] tight bounding box of every cell's targets: (lo.xyz, -), (hi.xyz, -)
+    const float4 *gbox;      // [2 * ncells * sub] tight bounding box of every (child) cell's targets: (lo.xyz, -), (hi.xyz, -)
+    const float4 *gboxc;     // [2 * ncells] the same per coarse cell (sub == 8)
     float4 *gnb;             // [n] cooperative search: the nearest target's coordinates, w = its distance (original query order)
     float4 *gseed;           // [n] the same in SORTED slot order, w = its index bits: the next pass's search ball
     int *gheavy;             // [n] queries still open after the per-thread shells
@@ -146,7 +148,7 @@ void launch_center(const float4 *pts, int n, double *chunk_sums, double *out3, u
 void launch_fp32_peak(float *out, int blocks, int threads, int iters, cudaStream_t s);
 void launch_grid_bbox(const float4 *tgt, int m, unsigned int *bbox, cudaStream_t s);
 void launch_grid_build(const float4 *tgt, int m, const GridMeta &g, int *counts, int *cursor, int *block_sums,
-                       float4 *sorted, float4 *boxes, cudaStream_t s);
+                       float4 *sorted, float4 *boxes, float4 *coarse_boxes, cudaStream_t s);
 // coop_r > 0: warp-cooperative search for balls up to coop_r metres (grid.cu); 0: the per-thread shell walk
 void launch_nn_grid(const RegDesc *descs, int batch, int max_n, int pass, int sm_count, cudaStream_t s, float coop_r);
 size_t spatial_sort_work_ints(int max_n, int batch); // ints of scratch launch_spatial_sort needs

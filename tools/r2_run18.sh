@@ -1,0 +1,8 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_icp.py tests/test_gpu_fullshape.py -m gpu -x -q -k "grid or fullres" > gpurun_out/r2_tests18.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_tests18.log
+tail -4 gpurun_out/r2_tests18.log
+echo "# sub8"; python tools/profile_case.py --grid 0 --iters 20 --repeat 3 | tail -2
+echo "# sub1"; ICPB_GRID_SUB=1 python tools/profile_case.py --grid 0 --iters 20 --repeat 3 | tail -2
+for cell in 0.125 0.15; do echo "# sub8 cell=$cell"; python tools/profile_case.py --grid $cell --iters 20 --repeat 3 | tail -2; done
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:nn_grid_coop -s 5 -c 1 -o gpurun_out/r2_nn_coop18 -f python tools/profile_case.py --grid 0 --iters 8 --noprof > gpurun_out/r2_ncu_coop18.log 2>&1
