@@ -286,6 +286,13 @@ def run_b200(args, rank, world, local):
             grid_ms.append(ms)
     grid_same_pose = bool(np.array_equal(res_g["pose_R"], res["pose_R"]) and np.array_equal(res_g["pose_t"], res["pose_t"])
                           and res_g["n_assoc"] == res["n_assoc"])
+    # what the search kernels do with their time: CUDA events around every pass + the pairs they evaluate, counted on the device
+    ctx.set_profiling(True)
+    work.copy_from(pristine)
+    res_gp, _, _ = ctx.icp_register(work, target, ITERS, 0.0, 0.75, icpb200.SOLVE_REFERENCE, nn_mode=icpb200.NN_GRID)
+    grid_fin_ms, grid_fin_k = ctx.profile_read(icpb200.PROF_NN_FINALIZE)
+    ctx.profile_read(icpb200.PROF_NN_GRID)
+    ctx.set_profiling(False)
 
     # ---- e2e: host frames -> C-ABI -> pose on the host, copies inside the timed region
     e2e_ms = []
@@ -400,6 +407,15 @@ def run_b200(args, rank, world, local):
                                           "e2e_ms_per_step": float(np.mean(grid_e2e_ms)),
                                           "e2e_registrations_per_s": 1000.0 / float(np.mean(grid_e2e_ms)),
                                           "kernel": "nn_grid_coop_kernel (warp-cooperative, staged candidates, temporal seeds) + nn_finalize_coop_kernel",
+                                          "search_ms_per_pass": res_gp["nn_partial_ms"] / max(res_gp["nn_partial_launches"], 1),
+                                          "sums_and_solve_ms_per_pass": grid_fin_ms / max(grid_fin_k, 1),
+                                          "pairs_evaluated_per_pass": res_gp["grid_pairs"] / max(res_gp["nn_partial_launches"], 1),
+                                          "roofline": {"bound": "fp32", "kernel": "nn_grid_coop_kernel",
+                                                       "achieved": 8.0 * res_gp["grid_pairs"] / max(res_gp["nn_partial_ms"] * 1e-3, 1e-12) / 1e12,
+                                                       "peak": peak, "unit": "TFLOP/s",
+                                                       "frac": 8.0 * res_gp["grid_pairs"] / max(res_gp["nn_partial_ms"] * 1e-3, 1e-12) / 1e12 / peak,
+                                                       "note": "8 flop for each (query, candidate) pair the search puts through its filter -- "
+                                                               "0.5 % of the n x m pairs of the scan -- over the search kernels' own time"},
                                           "cell_m": res_g["grid_cell_used"], "pose_identical_to_brute_force": grid_same_pose}},
             "roofline": {"bound": "fp32",
                          "kernel": {icpb200.FILTER_DIRECT: "nn_partial_kernel", icpb200.FILTER_WARP: "nn_partial_warp_kernel",

@@ -103,14 +103,18 @@ def run_batch10k(args, rank, world, local, emit=True):
         host.append((dp, tp))
         datas.append(ctx.cloud_from_points(dp)); targets.append(ctx.cloud_from_points(tp)); pristine.append(ctx.cloud_from_points(dp))
     chunk = args.batch_chunk if getattr(args, "batch_chunk", 0) else 128
+    # ICPB_NN_AUTO: the library's own choice -- for a batch of clouds this size the exact cooperative cell-grid search
+    # (same associations as the scan); ICPB_BATCH_NN=brute times the scan as the headline instead
+    nn_mode = {"brute": icpb200.NN_BRUTE, "grid": icpb200.NN_GRID, "auto": icpb200.NN_AUTO}[os.environ.get("ICPB_BATCH_NN", "auto")]
 
-    def step():
+    def step(mode=None):
         ctx.timer_start()
         res = []
         for b in range(0, len(datas), chunk):
             for dcl, pcl in zip(datas[b:b + chunk], pristine[b:b + chunk]):
                 dcl.copy_from(pcl)
-            res += ctx.icp_register_batch(datas[b:b + chunk], targets[b:b + chunk], ITERS, 0.0, 0.75, icpb200.SOLVE_REFERENCE)
+            res += ctx.icp_register_batch(datas[b:b + chunk], targets[b:b + chunk], ITERS, 0.0, 0.75, icpb200.SOLVE_REFERENCE,
+                                          nn_mode=nn_mode if mode is None else mode)
         return ctx.timer_stop(), res
 
     for _ in range(args.warmup):
@@ -124,16 +128,35 @@ def run_batch10k(args, rank, world, local, emit=True):
     l1 = ctx.launch_count()
     _barrier(torch, world)
     tot = _max_over_ranks(torch, world, local, float(np.sum(ms_all)))
-    # roofline of the scan kernel: the same steps again with CUDA events around every nn_partial launch
+    # roofline of the dominant kernel: the same steps again with CUDA events around every search launch (one set of
+    # events and one pair counter per batch call: every registration of a call reports the call's figures)
+    used_grid = res[0]["nn_mode_used"] == icpb200.NN_GRID
     ctx.set_profiling(True)
-    nn_ms, nn_launches, qpt, splits, filt = 0.0, 0, 0, 0, 0
+    nn_ms, nn_launches, qpt, splits, filt, pairs = 0.0, 0, 0, 0, 0, 0
     for _ in range(max(1, min(args.steps, 2))):
         _, rp = step()
-        # one set of events per batch call: every registration of a call reports the call's figures
         for b in range(0, len(rp), chunk):
-            nn_ms += rp[b]["nn_partial_ms"]; nn_launches += rp[b]["nn_partial_launches"]
+            nn_ms += rp[b]["nn_partial_ms"]; nn_launches += rp[b]["nn_partial_launches"]; pairs += rp[b]["grid_pairs"]
         qpt, splits, filt = rp[0]["nn_qpt"], rp[0]["nn_splits"], rp[0]["nn_filter_used"]
     ctx.set_profiling(False)
+    # the brute-force scan on the same batch (the north star's kernel), for the record
+    brute = None
+    if used_grid:
+        for _ in range(2):
+            step(icpb200.NN_BRUTE)
+        b_ms = [step(icpb200.NN_BRUTE)[0] for _ in range(2)]
+        ctx.set_profiling(True)
+        _, rb = step(icpb200.NN_BRUTE)
+        ctx.set_profiling(False)
+        b_nn = sum(rb[b]["nn_partial_ms"] for b in range(0, len(rb), chunk))
+        b_launches = sum(rb[b]["nn_partial_launches"] for b in range(0, len(rb), chunk))
+        b_tot = _max_over_ranks(torch, world, local, float(np.mean(b_ms)))
+        b_ach = 8.0 * 1e4 * 1e4 * min(chunk, len(datas)) / max(b_nn / max(b_launches, 1) * 1e-3, 1e-12) / 1e12
+        brute = {"registrations_per_s": total * 1000.0 / b_tot, "ms_per_step": b_tot,
+                 "same_poses": bool(all(np.array_equal(x["pose_R"], y["pose_R"]) and np.array_equal(x["pose_t"], y["pose_t"])
+                                        for x, y in zip(rb, res))),
+                 "roofline": {"bound": "fp32", "kernel": f"nn_partial_warp_kernel<{rb[0]['nn_qpt']}>, {rb[0]['nn_splits']} splits",
+                              "achieved": b_ach, "peak": _fp32_nominal(), "unit": "TFLOP/s", "frac": b_ach / _fp32_nominal()}}
     # e2e: host point lists in, poses out -- uploads and the result blocks inside the timed region
     e2e_ms = []
     for s in range(2):
@@ -142,7 +165,8 @@ def run_batch10k(args, rank, world, local, emit=True):
         for b in range(0, len(datas), chunk):
             for (dp, tp), dcl, tcl in zip(host[b:b + chunk], datas[b:b + chunk], targets[b:b + chunk]):
                 dcl.upload(dp); tcl.upload(tp)
-            ctx.icp_register_batch(datas[b:b + chunk], targets[b:b + chunk], ITERS, 0.0, 0.75, icpb200.SOLVE_REFERENCE)
+            ctx.icp_register_batch(datas[b:b + chunk], targets[b:b + chunk], ITERS, 0.0, 0.75, icpb200.SOLVE_REFERENCE,
+                                   nn_mode=nn_mode)
         ctx.sync()
         e2e_ms.append((time.perf_counter() - t0) * 1e3)
     e2e_tot = _max_over_ranks(torch, world, local, float(e2e_ms[-1]))
@@ -177,7 +201,10 @@ def run_batch10k(args, rank, world, local, emit=True):
             cpu = {"unavailable": str(e)}
         assert oracle_ok is not False, "batch registration 0 differs from the oracle"
         n_loc = len(datas)
-        flop_per_launch = 8.0 * 1e4 * 1e4 * min(chunk, n_loc)
+        if used_grid:   # the search evaluates the pairs it stages, not n x m: 8 flop for each of THOSE (counted on the device)
+            flop_per_launch = 8.0 * pairs / max(nn_launches, 1)
+        else:
+            flop_per_launch = 8.0 * 1e4 * 1e4 * min(chunk, n_loc)
         avg_s = nn_ms / max(nn_launches, 1) * 1e-3
         ach = flop_per_launch / max(avg_s, 1e-12) / 1e12
         line = {"metric": "icp_registrations_per_s", "value": total * 1000.0 / ms_per_step, "unit": "registrations/s",
@@ -187,7 +214,10 @@ def run_batch10k(args, rank, world, local, emit=True):
                                        "20 iterations, sharded by index", "per_call_batch": chunk,
                            "pose_sha256": digest, "registration_0_equals_oracle": oracle_ok,
                            "l2": "working set (batch clouds + partials) exceeds L2"},
-                "roofline": {"bound": "fp32", "kernel": f"nn_partial ({'warp' if filt == icpb200.FILTER_WARP else 'centred'}-filter)<{qpt}>, {splits} splits",
+                "roofline": {"bound": "fp32",
+                             "kernel": ("nn_grid_coop_kernel + nn_grid_heavy_kernel (exact cooperative cell-grid search; flops = 8 x the "
+                                        "pairs it evaluates, counted on the device)") if used_grid else
+                                       f"nn_partial ({'warp' if filt == icpb200.FILTER_WARP else 'centred'}-filter)<{qpt}>, {splits} splits",
                              "achieved": ach, "peak": _fp32_nominal(), "unit": "TFLOP/s", "frac": ach / _fp32_nominal(),
                              "traffic": None, "flop_per_launch": flop_per_launch, "avg_launch_ms": avg_s * 1e3,
                              "launches_timed": nn_launches,
@@ -195,6 +225,8 @@ def run_batch10k(args, rank, world, local, emit=True):
                 "cpu_baseline": cpu,
                 "e2e": {"value": total * 1000.0 / e2e_tot, "unit": "registrations/s",
                         "h2d_bytes_per_step": int(total * 2 * 10000 * 16), "d2h_bytes_per_step": int(total * 304)},
+                "extra": {"nn_mode": "ICPB_NN_AUTO -> " + ("cell-grid search" if used_grid else "brute-force scan"),
+                          "brute_force_scan": brute},
                 "gpu_launches": int(l1 - l0)}
         if emit:
             print(json.dumps(line), flush=True)
@@ -622,6 +654,30 @@ def run_live(args, rank, world, local, emit=True):
                                  f"of the same sequence, {n_kp} key-points ({cdt:.2f} s)"}
         except Exception as e:  # the library is test infrastructure; the GPU number stands without it
             cpu = {"unavailable": str(e)}
+        # the same frames through the C++ drop-in layer (icp::getTransformation of include/icpb200/icp.hpp, the call of
+        # SLAM.cpp:277), both association modes: tests/cpp/bench_compat.cpp
+        compat = None
+        try:
+            import struct
+            import subprocess
+            import tempfile
+            binp = os.path.join(ROOT, "icp-slam-prototype_b200", "lib", "bench_compat")
+            kf = min(frames, 12)
+            with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
+                f.write(struct.pack("iiii", w, h, kf, len(kxy)))
+                for d in depths[:kf]:
+                    f.write(np.ascontiguousarray(d, np.uint16).tobytes())
+                f.write(bgr.tobytes()); f.write(np.ascontiguousarray(kxy, np.float32).tobytes())
+                tmp = f.name
+            out = subprocess.run([binp, tmp], capture_output=True, text=True, timeout=300)
+            os.unlink(tmp)
+            kv = dict(tok.split("=") for tok in out.stdout.split() if "=" in tok)
+            compat = {"all_points_ms_per_frame": float(kv["all_points_ms"]), "keypoints_ms_per_frame": float(kv["keypoints_ms"]),
+                      "frames": int(kv["frames"]),
+                      "what": "icp::getTransformation through the C++ drop-in headers (host vectors in and out on every "
+                              "call, as the reference's signatures demand), per frame"}
+        except Exception as e:  # the harness is optional: the C-ABI number stands without it
+            compat = {"unavailable": str(e)}
         line = {"metric": "live_loop_frames_per_s", "value": world * (frames - 1) / (tot * 1e-3), "unit": "frames/s",
                 "n_gpus": world, "steps": 1, "warmup": 1, "ms_per_step": tot, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -630,7 +686,7 @@ def run_live(args, rank, world, local, emit=True):
                                        "16 iterations max, threshold 1e-4, rule-C map update on the 300^3 grid); includes "
                                        "host->device copies of every frame",
                            "map_keypoints_at_end": int(n_map), "per_rank": "replica of the same sequence"},
-                "cpu_baseline": cpu}
+                "cpu_baseline": cpu, "extra": {"cpp_drop_in": compat}}
         if emit:
             print(json.dumps(line), flush=True)
     ctx.close()

@@ -219,93 +219,131 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         if ((rc = ws_get(ctx, WS_PERM, sizeof(int) * tot_n, (void **)&d_perm))) return rc;
     }
 
-    // ---- ICPB_NN_GRID: bucket the (fixed) target once per registration
-    bool grid_mode = (prm->nn_mode == ICPB_NN_GRID) && count == 1;
-    if (prm->nn_mode == ICPB_NN_AUTO && count == 1)
-        grid_mode = (double)regs[0].data->n * (double)regs[0].target->n >= 2.0e9; // ~45k x 45k: measured crossover region
-    GridMeta gm;
-    memset(&gm, 0, sizeof(gm));
+    // ---- ICPB_NN_GRID: bucket the (fixed) targets once per registration.  Batches take the cooperative search only
+    //      (the per-thread walk of round 1 stays a single-registration path).
+    const bool coop_mode = env_int("ICPB_GRID_COOP_CM", 1000) > 0;
+    bool grid_mode = (prm->nn_mode == ICPB_NN_GRID) && (count == 1 || coop_mode) && !kp_mode;
+    if (prm->nn_mode == ICPB_NN_AUTO && !kp_mode) {
+        // measured crossover regions: ~45k x 45k for one registration (set-up of ~0.3 ms against a scan of milliseconds);
+        // in a batch the set-up is shared and the search wins from a few thousand points per cloud on
+        if (count == 1) grid_mode = (double)max_n * (double)max_m >= 2.0e9;
+        else grid_mode = coop_mode && max_n >= 4096 && max_m >= 4096;
+    }
+    std::vector<GridMeta> gms;
+    std::vector<size_t> cell_off, n_off, m_off; // per registration: first entry in the counts array, first query, first target
     GridMeta *d_gmeta = nullptr;
     int *d_gcounts = nullptr, *d_gcursor = nullptr, *d_gsums = nullptr;
     float4 *d_gsorted = nullptr;
     int *d_gheavy = nullptr;
     float4 *d_gnb = nullptr, *d_gseed = nullptr, *d_gbox = nullptr, *d_gboxc = nullptr;
     long long grid_launches = 0;
+    size_t total_entries = 0, total_coarse = 0, tot_m = 0;
+    int max_ncells = 0;
+    bool any_children = false;
     if (grid_mode) {
-        const int m = regs[0].target->n;
+        // bounding boxes of all targets: one batched kernel, ONE host round trip
         unsigned int *d_bbox;
-        if ((rc = ws_get(ctx, WS_GRID_BBOX, 64, (void **)&d_bbox))) return rc;
+        TgtRef *d_refs;
+        if ((rc = ws_get(ctx, WS_GRID_BBOX, (sizeof(unsigned int) * 6 + sizeof(TgtRef)) * (size_t)count + 64, (void **)&d_bbox))) return rc;
+        d_refs = (TgtRef *)(d_bbox + 6 * (size_t)count + 2);
         void *hpb;
-        if ((rc = pinned_get(ctx, 64, &hpb))) return rc;
+        if ((rc = pinned_get(ctx, (sizeof(unsigned int) * 6 + sizeof(TgtRef)) * (size_t)count + 64, &hpb))) return rc;
         unsigned int *hb = (unsigned int *)hpb;
-        for (int k = 0; k < 3; ++k) { hb[k] = 0xffffffffu; hb[3 + k] = 0u; }
-        CU(ctx, cudaMemcpyAsync(d_bbox, hb, 24, cudaMemcpyHostToDevice, ctx->stream));
-        launch_grid_bbox(regs[0].target->d_pts, m, d_bbox, ctx->stream);
-        CU(ctx, cudaMemcpyAsync(hb, d_bbox, 24, cudaMemcpyDeviceToHost, ctx->stream));
+        TgtRef *hrefs = (TgtRef *)(hb + 6 * (size_t)count + 2);
+        for (int b = 0; b < count; ++b) {
+            for (int k = 0; k < 3; ++k) { hb[6 * b + k] = 0xffffffffu; hb[6 * b + 3 + k] = 0u; }
+            hrefs[b].pts = regs[b].target->d_pts;
+            hrefs[b].m = regs[b].target->n;
+        }
+        CU(ctx, cudaMemcpyAsync(d_bbox, hb, (sizeof(unsigned int) * 6 + sizeof(TgtRef)) * (size_t)count + 64, cudaMemcpyHostToDevice, ctx->stream));
+        launch_grid_bbox_batch(d_refs, count, max_m, d_bbox, ctx->stream);
+        CU(ctx, cudaMemcpyAsync(hb, d_bbox, sizeof(unsigned int) * 6 * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
-        float lo[3], hi[3];
-        for (int k = 0; k < 6; ++k) {
-            unsigned int u = hb[k];
-            u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u; // inverse of the ordered-uint map
-            float f;
-            memcpy(&f, &u, 4);
-            (k < 3 ? lo[k] : hi[k - 3]) = f;
-        }
-        // default cell: ~50 points per occupied cell (at most 0.2 m), taking a third of the bounding box's surface as the area
-        // the (surface-sampled) cloud covers; sweeps on full-resolution and 10k-point Kinect clouds sit near this
-        float h = prm->grid_cell;
-        if (!(h > 0.f)) {
-            const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
-            const float area = 2.f * (ex * ey + ey * ez + ez * ex) / 3.f;
-            // ~90 points per occupied cell for the cooperative search (its cost per cell is a fixed few dozen
-            // instructions per warp; measured optimum 0.10 m on the full-resolution pair), ~50 for the per-thread walk
-            const float per_cell = env_int("ICPB_GRID_COOP_CM", 1000) > 0 ? (float)env_int("ICPB_GRID_CELL_PTS", 90) : 50.f;
-            h = sqrtf(per_cell * std::max(area, 1e-6f) / (float)m);
-            h = std::min(std::max(h, 0.01f), 0.2f);
-        }
-        // the cooperative search splits every cell into 2 x 2 x 2 children (ICPB_GRID_SUB=1: no children)
-        const bool coop_mode = env_int("ICPB_GRID_COOP_CM", 1000) > 0;
-        gm.sub = (coop_mode && env_int("ICPB_GRID_SUB", 8) == 8) ? 8 : 1;
-        const double cell_cap = gm.sub == 8 ? 4.0e6 : 48.0e6; // counters + boxes stay below ~1.3 GB / ~200 MB
-        for (;;) {
-            double cells = 1.0;
-            for (int k = 0; k < 3; ++k) {
-                gm.dim[k] = std::max(1, (int)floorf((hi[k] - lo[k]) / h) + 1);
-                cells *= gm.dim[k];
+        gms.resize((size_t)count);
+        cell_off.resize((size_t)count); n_off.resize((size_t)count); m_off.resize((size_t)count);
+        size_t acc_n = 0;
+        for (int b = 0; b < count; ++b) {
+            GridMeta &gm = gms[(size_t)b];
+            memset(&gm, 0, sizeof(gm));
+            const int m = regs[b].target->n;
+            float lo[3], hi[3];
+            for (int k = 0; k < 6; ++k) {
+                unsigned int u = hb[6 * b + k];
+                u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u; // inverse of the ordered-uint map
+                float f;
+                memcpy(&f, &u, 4);
+                (k < 3 ? lo[k] : hi[k - 3]) = f;
             }
-            if (cells <= cell_cap) break;
-            h *= 1.26f; // coarser cells until the tables fit
+            // default cell: ~90 points per occupied cell for the cooperative search (its cost per cell is a fixed few dozen
+            // instructions per warp; measured optimum 0.10 - 0.125 m on the full-resolution pair), ~50 for the per-thread
+            // walk, at most 0.2 m; a third of the bounding box's surface stands for the area the (surface-sampled) cloud covers
+            float h = prm->grid_cell;
+            bool clamped = false;
+            if (!(h > 0.f)) {
+                const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+                const float area = 2.f * (ex * ey + ey * ez + ez * ex) / 3.f;
+                const float per_cell = coop_mode ? (float)env_int("ICPB_GRID_CELL_PTS", 90) : 50.f;
+                h = sqrtf(per_cell * std::max(area, 1e-6f) / (float)m);
+                clamped = h > 0.2f;
+                h = std::min(std::max(h, 0.01f), 0.2f);
+            }
+            // the cooperative search splits every cell into 2 x 2 x 2 children (ICPB_GRID_SUB=1: no children); a sparse
+            // cloud (cell edge clamped: a handful of points per cell) has nothing to split
+            gm.sub = (coop_mode && !clamped && env_int("ICPB_GRID_SUB", 8) == 8) ? 8 : 1;
+            const double cell_cap = (gm.sub == 8 ? 4.0e6 : 48.0e6) / std::max(1, std::min(count, 64)); // tables stay in the GB range
+            for (;;) {
+                double cells = 1.0;
+                for (int k = 0; k < 3; ++k) {
+                    gm.dim[k] = std::max(1, (int)floorf((hi[k] - lo[k]) / h) + 1);
+                    cells *= gm.dim[k];
+                }
+                if (cells <= cell_cap) break;
+                h *= 1.26f; // coarser cells until the tables fit
+            }
+            for (int k = 0; k < 3; ++k) gm.mn[k] = lo[k];
+            gm.h = h;
+            gm.ncells = gm.dim[0] * gm.dim[1] * gm.dim[2];
+            gm.max_nn = prm->max_nn_distance;
+            gm.max_r = (int)ceilf(prm->max_nn_distance / h) + 2;
+            // per-thread shells out to ~ICPB_GRID_LIGHT_CM (default 45 cm): typical ICP residuals resolve there;
+            // the few queries still open (no overlap, far from the target) are finished by one warp each
+            gm.light_r = std::max(2, (int)ceilf(0.01f * env_int("ICPB_GRID_LIGHT_CM", 45) / h));
+            cell_off[(size_t)b] = total_entries;
+            n_off[(size_t)b] = acc_n;
+            m_off[(size_t)b] = tot_m;
+            total_entries += (size_t)gm.ncells * gm.sub + 1;
+            total_coarse += (size_t)gm.ncells;
+            tot_m += (size_t)m;
+            acc_n += ((size_t)regs[b].data->n + 31) / 32 * 32;
+            max_ncells = std::max(max_ncells, gm.ncells);
+            any_children |= gm.sub == 8;
         }
-        for (int k = 0; k < 3; ++k) gm.mn[k] = lo[k];
-        gm.h = h;
-        gm.ncells = gm.dim[0] * gm.dim[1] * gm.dim[2];
-        gm.max_nn = prm->max_nn_distance;
-        gm.max_r = (int)ceilf(prm->max_nn_distance / h) + 2;
-        // per-thread shells out to ~ICPB_GRID_LIGHT_CM (default 45 cm): typical ICP residuals resolve there;
-        // the few queries still open (no overlap, far from the target) are finished by one warp each
-        gm.light_r = std::max(2, (int)ceilf(0.01f * env_int("ICPB_GRID_LIGHT_CM", 45) / h));
-        const size_t slots = (size_t)gm.ncells * gm.sub; // sorted-array cells (children included)
-        const size_t cbytes = sizeof(int) * (slots + 1);
-        if ((rc = ws_get(ctx, WS_GRID_META, sizeof(GridMeta), (void **)&d_gmeta))) return rc;
+        if (total_entries >= (size_t)1 << 31) return fail(ctx, ICPB_ERR_CAPACITY, "cell tables of the batch exceed 2^31 entries");
+        const size_t cbytes = sizeof(int) * total_entries;
+        if ((rc = ws_get(ctx, WS_GRID_META, sizeof(GridMeta) * (size_t)count, (void **)&d_gmeta))) return rc;
         if ((rc = ws_get(ctx, WS_GRID_COUNTS, cbytes, (void **)&d_gcounts))) return rc;
         if ((rc = ws_get(ctx, WS_GRID_CURSOR, cbytes, (void **)&d_gcursor))) return rc;
-        if ((rc = ws_get(ctx, WS_GRID_SUMS, sizeof(int) * (slots / 4096 + 8), (void **)&d_gsums))) return rc;
-        if ((rc = ws_get(ctx, WS_GRID_SORTED, sizeof(float4) * (size_t)m, (void **)&d_gsorted))) return rc;
-        if ((rc = ws_get(ctx, WS_GRID_HEAVY, sizeof(int) * ((size_t)regs[0].data->n + passes + 8), (void **)&d_gheavy))) return rc;
-        if ((rc = ws_get(ctx, WS_GRID_NB, sizeof(float4) * (size_t)regs[0].data->n, (void **)&d_gnb))) return rc;
-        if ((rc = ws_get(ctx, WS_GRID_BOX, sizeof(float4) * 2 * slots, (void **)&d_gbox))) return rc;
-        if (gm.sub == 8 && (rc = ws_get(ctx, WS_GRID_BOXC, sizeof(float4) * 2 * (size_t)gm.ncells, (void **)&d_gboxc))) return rc;
-        if ((rc = ws_get(ctx, WS_GRID_SEED, sizeof(float4) * ((size_t)regs[0].data->n + 32), (void **)&d_gseed))) return rc;
-        grid_launches = gm.sub == 8 ? 9 : 8;
+        if ((rc = ws_get(ctx, WS_GRID_SUMS, sizeof(int) * (total_entries / 4096 + 16), (void **)&d_gsums))) return rc;
+        if ((rc = ws_get(ctx, WS_GRID_SORTED, sizeof(float4) * tot_m, (void **)&d_gsorted))) return rc;
+        if ((rc = ws_get(ctx, WS_GRID_HEAVY, sizeof(int) * (tot_n + (size_t)count * (passes + 8)), (void **)&d_gheavy))) return rc;
+        if ((rc = ws_get(ctx, WS_GRID_NB, sizeof(float4) * tot_n, (void **)&d_gnb))) return rc;
+        if ((rc = ws_get(ctx, WS_GRID_BOX, sizeof(float4) * 2 * total_entries, (void **)&d_gbox))) return rc;
+        if (any_children && (rc = ws_get(ctx, WS_GRID_BOXC, sizeof(float4) * 2 * total_coarse, (void **)&d_gboxc))) return rc;
+        if ((rc = ws_get(ctx, WS_GRID_SEED, sizeof(float4) * (tot_n + 32), (void **)&d_gseed))) return rc;
+        grid_launches = 8 + (any_children ? 1 : 0);
     }
 
     // host staging: descs | states | params in one pinned block
-    const size_t hb = sizeof(RegDesc) * count + sizeof(IcpState) * count + sizeof(IcpParamsDev);
+    const size_t hb = sizeof(RegDesc) * count + sizeof(IcpState) * count + sizeof(IcpParamsDev) + 64 +
+                      sizeof(GridMeta) * (size_t)count + 64;
     void *hp;
     if ((rc = pinned_get(ctx, hb, &hp))) return rc;
     RegDesc *h_descs = (RegDesc *)hp;
     IcpState *h_states = (IcpState *)(h_descs + count);
     IcpParamsDev *h_prm = (IcpParamsDev *)(h_states + count);
+    void *hp_metas = (void *)(((uintptr_t)(h_prm + 1) + 63) & ~(uintptr_t)63);
+    unsigned long long *h_pairs = (unsigned long long *)(((uintptr_t)((GridMeta *)hp_metas + count) + 15) & ~(uintptr_t)15);
+    *h_pairs = 0;
 
     size_t off_n = 0, off_g = 0, off_c = 0;
     for (int b = 0; b < count; ++b) {
@@ -332,15 +370,25 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         d.st = d_states + b;
         d.idx_trace = d_idx_trace;
         d.dist_trace = d_dist_trace;
-        d.grid = d_gmeta;
-        d.gsorted = d_gsorted;
-        d.gstart = d_gcounts;
-        d.gbox = d_gbox;
-        d.gboxc = d_gboxc;
-        d.gnb = d_gnb;
-        d.gseed = d_gseed;
-        d.gheavy = d_gheavy ? d_gheavy + passes + 8 : nullptr;
-        d.gheavy_count = d_gheavy;
+        if (grid_mode) {
+            size_t coarse_before = 0;
+            for (int bb = 0; bb < b; ++bb) coarse_before += (size_t)gms[(size_t)bb].ncells;
+            d.grid = d_gmeta + b;
+            d.gsorted = d_gsorted; // one sorted array for the whole batch: the start values are positions in it
+            d.gstart = d_gcounts + cell_off[(size_t)b];
+            d.gcursor = d_gcursor + cell_off[(size_t)b];
+            d.gbox = d_gbox + 2 * cell_off[(size_t)b];
+            d.gboxc = d_gboxc ? d_gboxc + 2 * coarse_before : nullptr;
+            d.gnb = d_gnb + off_n;
+            d.gseed = d_gseed + off_n;
+            // pair counter (profiling mode): the eight bytes behind the scan's block sums, 8-byte aligned
+            d.gpairs = ctx->profiling ? (unsigned long long *)(d_gsums + ((total_entries / 4096 + 8 + 1) & ~(size_t)1)) : nullptr;
+            d.gheavy_count = d_gheavy + (size_t)b * (passes + 8);
+            d.gheavy = d_gheavy + (size_t)count * (passes + 8) + off_n;
+        } else {
+            d.grid = nullptr; d.gsorted = nullptr; d.gstart = nullptr; d.gcursor = nullptr; d.gbox = nullptr; d.gboxc = nullptr;
+            d.gnb = nullptr; d.gseed = nullptr; d.gheavy = nullptr; d.gheavy_count = nullptr; d.gpairs = nullptr;
+        }
         d.carry = (kp_mode && regs[b].carry) ? regs[b].carry->d_pts : nullptr;
         d.n_carry = (kp_mode && regs[b].carry) ? regs[b].carry->n : 0;
         d.mlog = d_mlog;
@@ -377,10 +425,16 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         launches += 15;
     }
     if (grid_mode) {
-        CU(ctx, cudaMemcpyAsync(d_gmeta, &gm, sizeof(gm), cudaMemcpyHostToDevice, st));
-        CU(ctx, cudaMemsetAsync(d_gcounts, 0, sizeof(int) * ((size_t)gm.ncells * gm.sub + 1), st));
-        CU(ctx, cudaMemsetAsync(d_gheavy, 0, sizeof(int) * ((size_t)passes + 8), st));
-        launch_grid_build(h_descs[0].tgt, h_descs[0].m, gm, d_gcounts, d_gcursor, d_gsums, d_gsorted, d_gbox, d_gboxc, st);
+        // the metas ride in pinned memory behind the descriptors' block (the call returns only after the stream is done)
+        GridMeta *h_gm = (GridMeta *)hp_metas;
+        for (int b = 0; b < count; ++b) h_gm[b] = gms[(size_t)b];
+        CU(ctx, cudaMemcpyAsync(d_gmeta, h_gm, sizeof(GridMeta) * (size_t)count, cudaMemcpyHostToDevice, st));
+        CU(ctx, cudaMemsetAsync(d_gcounts, 0, sizeof(int) * total_entries, st));
+        CU(ctx, cudaMemsetAsync(d_gheavy, 0, sizeof(int) * (size_t)count * ((size_t)passes + 8), st));
+        launch_grid_build_batch(d_descs, count, max_m, max_ncells, d_gcounts, d_gcursor, (long long)total_entries, d_gsums,
+                                d_gsorted, d_gbox, any_children, st);
+        if (ctx->profiling) // after the scans are done with the block sums
+            CU(ctx, cudaMemsetAsync(d_gsums + ((total_entries / 4096 + 8 + 1) & ~(size_t)1), 0, sizeof(unsigned long long), st));
         launches += grid_launches;
     } else {
         for (int b = 0; b < count; ++b) {
@@ -422,6 +476,9 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
     CU(ctx, cudaGetLastError());
 
     CU(ctx, cudaMemcpyAsync(h_states, d_states, sizeof(IcpState) * count, cudaMemcpyDeviceToHost, st));
+    if (grid_mode && ctx->profiling)
+        CU(ctx, cudaMemcpyAsync(h_pairs, d_gsums + ((total_entries / 4096 + 8 + 1) & ~(size_t)1), sizeof(unsigned long long),
+                                cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaStreamSynchronize(st));
     float ms = 0.f;
     CU(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
@@ -472,9 +529,11 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
             r.nn_qpt = qpt;
             r.nn_splits = splits;
             r.nn_mode_used = grid_mode ? ICPB_NN_GRID : ICPB_NN_BRUTE;
-            r.grid_cell_used = grid_mode ? gm.h : 0.f;
+            r.grid_cell_used = grid_mode ? gms[(size_t)b].h : 0.f;
             r.nn_filter_used = filter;
             r.n_nonassoc = s.n_nonassoc;
+            r.grid_pairs = grid_mode ? (long long)*h_pairs : 0; // the whole call's (a batch shares one counter)
+            r.nn_grid_ms = grid_mode ? nn_ms : 0.f;
         }
     }
     if (trace) {

@@ -230,6 +230,100 @@ void launch_grid_build(const float4 *tgt, int m, const GridMeta &g, int *counts,
         grid_coarse_boxes_kernel<<<(g.ncells + 255) / 256, 256, 0, s>>>(boxes, g.ncells, coarse_boxes);
 }
 
+// ---- batched cell build (ICPB_NN_GRID for icpb_icp_register_batch) -----------------------------------------------------
+__global__ void __launch_bounds__(256) grid_bbox_batch_kernel(const TgtRef *__restrict__ refs, unsigned int *bbox)
+{
+    __shared__ unsigned int s_lo[3][8], s_hi[3][8];
+    const TgtRef t = refs[blockIdx.y];
+    unsigned int *bb = bbox + 6 * blockIdx.y;
+    unsigned int lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < t.m; i += gridDim.x * blockDim.x) {
+        const float4 p = t.pts[i];
+        const unsigned int v[3] = {f2ord(p.x), f2ord(p.y), f2ord(p.z)};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { lo[k] = min(lo[k], v[k]); hi[k] = max(hi[k], v[k]); }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        lo[k] = __reduce_min_sync(0xffffffffu, lo[k]);
+        hi[k] = __reduce_max_sync(0xffffffffu, hi[k]);
+        if ((threadIdx.x & 31) == 0) { s_lo[k][threadIdx.x >> 5] = lo[k]; s_hi[k][threadIdx.x >> 5] = hi[k]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int k = threadIdx.x;
+        unsigned int a = s_lo[k][0], b = s_hi[k][0];
+        for (int w = 1; w < 8; ++w) { a = min(a, s_lo[k][w]); b = max(b, s_hi[k][w]); }
+        atomicMin(&bb[k], a);
+        atomicMax(&bb[3 + k], b);
+    }
+}
+
+void launch_grid_bbox_batch(const TgtRef *refs, int batch, int max_m, unsigned int *bbox, cudaStream_t s)
+{
+    dim3 grid(max(1, min((max_m + 255) / 256, 296 / max(1, min(batch, 296)) + 1)), batch);
+    grid_bbox_batch_kernel<<<grid, 256, 0, s>>>(refs, bbox);
+}
+
+__global__ void grid_count_batch_kernel(const RegDesc *__restrict__ descs)
+{
+    const RegDesc &d = descs[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.m) return;
+    const float4 p = d.tgt[i];
+    atomicAdd(const_cast<int *>(d.gstart) + cell_of(*d.grid, p.x, p.y, p.z), 1);
+}
+
+__global__ void grid_scatter_batch_kernel(const RegDesc *__restrict__ descs)
+{
+    const RegDesc &d = descs[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.m) return;
+    float4 p = d.tgt[i];
+    const int pos = atomicAdd(&d.gcursor[cell_of(*d.grid, p.x, p.y, p.z)], 1);
+    p.w = __int_as_float(i);
+    const_cast<float4 *>(d.gsorted)[pos] = p;
+}
+
+__global__ void grid_coarse_boxes_batch_kernel(const RegDesc *__restrict__ descs)
+{
+    const RegDesc &d = descs[blockIdx.y];
+    const GridMeta &g = *d.grid;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g.sub != 8 || c >= g.ncells) return;
+    const float4 *boxes = d.gbox;
+    float4 lo = boxes[16 * (size_t)c], hi = boxes[16 * (size_t)c + 1];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+        const float4 l = boxes[16 * (size_t)c + 2 * k], h = boxes[16 * (size_t)c + 2 * k + 1];
+        lo.x = fminf(lo.x, l.x); lo.y = fminf(lo.y, l.y); lo.z = fminf(lo.z, l.z);
+        hi.x = fmaxf(hi.x, h.x); hi.y = fmaxf(hi.y, h.y); hi.z = fmaxf(hi.z, h.z);
+    }
+    const_cast<float4 *>(d.gboxc)[2 * (size_t)c] = lo;
+    const_cast<float4 *>(d.gboxc)[2 * (size_t)c + 1] = hi;
+}
+
+// counts: `total_entries` ints (every registration's cells + 1, back to back), zeroed by the caller.  After the call
+// counts[] holds the start of every cell in the shared sorted array; boxes[] the tight box of every entry.
+void launch_grid_build_batch(const RegDesc *descs, int batch, int max_m, int max_ncells, int *counts, int *cursor,
+                             long long total_entries, int *block_sums, const float4 *sorted, float4 *boxes, bool any_children,
+                             cudaStream_t s)
+{
+    const int n = (int)total_entries;
+    dim3 pgrid((max_m + 255) / 256, batch);
+    grid_count_batch_kernel<<<pgrid, 256, 0, s>>>(descs);
+    const int nblocks = (n + kScanTile - 1) / kScanTile;
+    scan_reduce_kernel<<<nblocks, kScanThreads, 0, s>>>(counts, n, block_sums);
+    scan_sums_kernel<<<1, kScanThreads, 0, s>>>(block_sums, nblocks);
+    scan_apply_kernel<<<nblocks, kScanThreads, 0, s>>>(counts, n, block_sums);
+    cudaMemcpyAsync(cursor, counts, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, s);
+    grid_scatter_batch_kernel<<<pgrid, 256, 0, s>>>(descs);
+    // every entry but the last has a successor: its box is that of the points between the two starts (the entry that
+    // closes a registration holds no points: start == next start, an inverted box)
+    grid_boxes_kernel<<<(n - 1 + 255) / 256, 256, 0, s>>>(sorted, counts, n - 1, boxes);
+    if (any_children) grid_coarse_boxes_batch_kernel<<<dim3((max_ncells + 255) / 256, batch), 256, 0, s>>>(descs);
+}
+
 // ---- spatial order of the QUERIES (warp-centred brute-force filter of nn.cu, cooperative grid search) ---------------
 // The order is a performance matter only -- it decides which queries share a warp, never what any query's result is.
 // d.perm[slot] = original index.  blockIdx.y = registration.
@@ -885,6 +979,7 @@ __global__ void __launch_bounds__(32 * kCoopWarps, ICPB_COOP_MINB) nn_grid_coop_
     const float A = ((ax * ax + ay * ay) + az * az) * 1.000001f;
     const float qx = -2.f * ax, qy = -2.f * ay, qz = -2.f * az; // W = |t'|^2 - 2 a'.t'
 
+    unsigned long long staged = 0; // candidates this warp put through the filter (x 32 lanes = pairs), profiling only
     for (int round = 0; round < 8; ++round) {
         // lanes whose ball outgrew the cooperative phase go to the warp-per-query kernel with their partial best
         const float rr = fminf(rad, max_reach);
@@ -1038,6 +1133,7 @@ __global__ void __launch_bounds__(32 * kCoopWarps, ICPB_COOP_MINB) nn_grid_coop_
                             __syncwarp();
                             coop_batch(buf, fill, sorted, p, qx, qy, qz, A, live, best, bb);
                             __syncwarp();
+                            staged += fill;
                             fill = 0;
                         }
                     }
@@ -1076,6 +1172,7 @@ __global__ void __launch_bounds__(32 * kCoopWarps, ICPB_COOP_MINB) nn_grid_coop_
             __syncwarp();
             coop_batch(buf, (fill + 3) & ~3, sorted, p, qx, qy, qz, A, live, best, bb);
             __syncwarp();
+            staged += fill;
         }
         // a lane that found nothing borrows its neighbours' finds: their best targets are real candidates a few
         // centimetres further away, which bounds the lane's next ball far better than quadrupling the radius
@@ -1094,6 +1191,7 @@ __global__ void __launch_bounds__(32 * kCoopWarps, ICPB_COOP_MINB) nn_grid_coop_
             else rad = (best.d < CUDART_INF_F) ? best.d : 4.f * rad;
         }
     }
+    if (d.gpairs && lane == 0 && staged) atomicAdd(d.gpairs, staged * 32ull);
     if (!valid) return;
     if (!done) deferred = true; // round limit (not reachable with radii that quadruple up to the acceptance radius)
     if (deferred) {

@@ -119,11 +119,13 @@ struct RegDesc {
     int nonassoc_capacity;
     const GridMeta *grid;    // ICPB_NN_GRID only
     const float4 *gsorted;   // targets sorted by cell, w = original index
-    const int *gstart;       // [ncells+1] first sorted slot of every cell
+    const int *gstart;       // [ncells*sub+1] first sorted slot of every cell (positions in gsorted)
+    int *gcursor;            // build scratch: running insert position per cell
     const float4 *gbox;      // [2 * ncells * sub] tight bounding box of every (child) cell's targets: (lo.xyz, -), (hi.xyz, -)
     const float4 *gboxc;     // [2 * ncells] the same per coarse cell (sub == 8)
     float4 *gnb;             // [n] cooperative search: the nearest target's coordinates, w = its distance (original query order)
     float4 *gseed;           // [n] the same in SORTED slot order, w = its index bits: the next pass's search ball
+    unsigned long long *gpairs; // profiling mode: (query, candidate) pairs the cooperative search put through its filter
     int *gheavy;             // [n] queries still open after the per-thread shells
     int *gheavy_count;       // [passes] length of that list per pass (zeroed once per registration)
 };
@@ -147,6 +149,18 @@ void launch_center(const float4 *pts, int n, double *chunk_sums, double *out3, u
                    cudaStream_t s);
 void launch_fp32_peak(float *out, int blocks, int threads, int iters, cudaStream_t s);
 void launch_grid_bbox(const float4 *tgt, int m, unsigned int *bbox, cudaStream_t s);
+// batched forms for `batch` registrations (blockIdx.y): bounding boxes of the targets (bbox: batch x 6 ordered uints,
+// initialised by the caller), and the cell build of all registrations at once -- counts / starts of all registrations
+// form ONE array (desc.gstart points into it) scanned as a whole, so that start values are positions in the shared
+// sorted array desc.gsorted
+struct TgtRef {
+    const float4 *pts;
+    int m;
+};
+void launch_grid_bbox_batch(const TgtRef *refs, int batch, int max_m, unsigned int *bbox, cudaStream_t s);
+void launch_grid_build_batch(const RegDesc *descs, int batch, int max_m, int max_ncells, int *counts, int *cursor,
+                             long long total_entries, int *block_sums, const float4 *sorted, float4 *boxes, bool any_children,
+                             cudaStream_t s);
 void launch_grid_build(const float4 *tgt, int m, const GridMeta &g, int *counts, int *cursor, int *block_sums,
                        float4 *sorted, float4 *boxes, float4 *coarse_boxes, cudaStream_t s);
 // coop_r > 0: warp-cooperative search for balls up to coop_r metres (grid.cu); 0: the per-thread shell walk

@@ -55,7 +55,7 @@ class IcpResult(C.Structure):
                 ("small_assoc_exit", C.c_int), ("exact_rescans", C.c_int), ("gpu_ms", C.c_float),
                 ("kernel_launches", C.c_int), ("nn_partial_ms", C.c_float), ("nn_partial_launches", C.c_int),
                 ("nn_qpt", C.c_int), ("nn_splits", C.c_int), ("nn_mode_used", C.c_int), ("grid_cell_used", C.c_float),
-                ("nn_filter_used", C.c_int), ("n_nonassoc", C.c_int)]
+                ("nn_filter_used", C.c_int), ("n_nonassoc", C.c_int), ("grid_pairs", C.c_longlong), ("nn_grid_ms", C.c_float)]
 
     def to_dict(self):
         return {
@@ -70,7 +70,7 @@ class IcpResult(C.Structure):
             "nn_partial_ms": self.nn_partial_ms, "nn_partial_launches": self.nn_partial_launches,
             "nn_qpt": self.nn_qpt, "nn_splits": self.nn_splits, "nn_mode_used": self.nn_mode_used,
             "grid_cell_used": self.grid_cell_used, "nn_filter_used": self.nn_filter_used,
-            "n_nonassoc": self.n_nonassoc,
+            "n_nonassoc": self.n_nonassoc, "grid_pairs": self.grid_pairs, "nn_grid_ms": self.nn_grid_ms,
         }
 
 
@@ -255,10 +255,10 @@ class Context:
         return res.to_dict()
 
     def icp_register_batch(self, datas, targets, max_iterations=20, threshold=0.0, max_nn_distance=0.75,
-                           solve_mode=SOLVE_REFERENCE):
+                           solve_mode=SOLVE_REFERENCE, nn_mode=NN_BRUTE, grid_cell=0.0):
         n = len(datas)
         prm = IcpParams(max_iterations, threshold, max_nn_distance, solve_mode, (C.c_float * 3)(0, 0, 0), None, None,
-                        NN_BRUTE, 0.0, FILTER_AUTO)
+                        nn_mode, grid_cell, FILTER_AUTO)
         dh = (C.c_void_p * n)(*[d.h for d in datas])
         th = (C.c_void_p * n)(*[t.h for t in targets])
         res = (IcpResult * n)()

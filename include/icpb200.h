@@ -122,6 +122,9 @@ typedef struct {
     float grid_cell_used;
     int nn_filter_used;     /* ICPB_FILTER_* of the BRUTE scan */
     int n_nonassoc;         /* icpb_icp_register_keypoints: length of the accumulated reject list */
+    long long grid_pairs;   /* profiling mode, ICPB_NN_GRID: (query, candidate) pairs the cooperative search evaluated over
+                             * all passes of the call (8 flop each: the work behind its roofline figure) */
+    float nn_grid_ms;       /* profiling mode: summed device time of the search kernels of the call */
 } icpb_icp_result;
 
 /* ---- library / context ------------------------------------------------- */

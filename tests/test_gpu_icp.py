@@ -216,3 +216,29 @@ def test_icp_randomized_differential(ctx, orc, monkeypatch, flt):
         assert np.array_equal(res["pose_R"], want["pose_R"]) and np.array_equal(res["pose_t"], want["pose_t"]), case
         assert np.array_equal(dc.download().view(np.uint8), wout.view(np.uint8)), case
         dc.close(); tc.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_icp_batch_in_grid_mode_matches_the_oracle(ctx, orc, pair10k, mode):
+    """ICPB_NN_GRID for a batch (round 2: the cells of all registrations are built together, one sorted array, one scan):
+    ragged sizes, one registration with partial overlap, every pose / association count / transformed cloud bit-equal
+    to the oracle's brute-force loop."""
+    import icpb200
+    data, target = pair10k
+    rng = np.random.default_rng(7)
+    cases = [(data[:6000], target[:7000]), (data[100:4196], target[:4096]), (data[::3], target[::2]),
+             (data[:3000].copy(), target[5000:]), (data[:64], target[:33]), (data, target)]
+    shifted = cases[3][0].copy()
+    shifted["x"] += np.float32(0.4)                    # partial overlap: many queries without a neighbour inside 0.75 m
+    cases[3] = (shifted, cases[3][1])
+    datas = [ctx.cloud_from_points(d) for d, _ in cases]
+    targets = [ctx.cloud_from_points(t) for _, t in cases]
+    res = ctx.icp_register_batch(datas, targets, 8, 0.0, 0.75, mode, nn_mode=icpb200.NN_GRID)
+    for k, (d, t) in enumerate(cases):
+        assert res[k]["nn_mode_used"] == icpb200.NN_GRID
+        ref, rout, _, _ = orc.icp(d, t, 8, 0.0, 0.75, mode, n_threads=8)
+        assert res[k]["n_assoc"] == ref["n_assoc"], k
+        assert np.array_equal(res[k]["pose_R"], ref["pose_R"]) and np.array_equal(res[k]["pose_t"], ref["pose_t"]), k
+        assert np.array_equal(datas[k].download().view(np.uint8), rout.view(np.uint8)), k
+    for c in datas + targets:
+        c.close()
