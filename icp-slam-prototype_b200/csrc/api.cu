@@ -157,7 +157,8 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
     if (prm->max_iterations < 0) return fail(ctx, ICPB_ERR_INVALID, "max_iterations < 0");
     const int passes = prm->max_iterations + 1;
     const bool trace = (prm->idx_trace != nullptr) || (prm->dist_trace != nullptr);
-    if (trace && count != 1) return fail(ctx, ICPB_ERR_INVALID, "traces are only supported for a single registration");
+    // in a batch the traces record ONE registration: number ICPB_TRACE_REG (default 0), shape (max_iterations+1) x its n
+    const int trace_reg = trace ? std::min(std::max(env_int("ICPB_TRACE_REG", 0), 0), count - 1) : 0;
 
     int qpt, splits;
     int filter = env_int("ICPB_NN_FILTER", prm->nn_filter);
@@ -368,8 +369,8 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         d.dist = d_dist + off_n;
         d.chunk_sums = d_chunks + off_c * kTerms;
         d.st = d_states + b;
-        d.idx_trace = d_idx_trace;
-        d.dist_trace = d_dist_trace;
+        d.idx_trace = (b == trace_reg) ? d_idx_trace : nullptr;
+        d.dist_trace = (b == trace_reg) ? d_dist_trace : nullptr;
         if (grid_mode) {
             size_t coarse_before = 0;
             for (int bb = 0; bb < b; ++bb) coarse_before += (size_t)gms[(size_t)bb].ncells;
@@ -537,7 +538,7 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         }
     }
     if (trace) {
-        const int n = regs[0].data->n;
+        const int n = regs[trace_reg].data->n;
         if (prm->idx_trace)
             CU(ctx, cudaMemcpyAsync(prm->idx_trace, d_idx_trace, (size_t)passes * n * sizeof(int),
                                     cudaMemcpyDeviceToHost, st));

@@ -1164,10 +1164,13 @@ __global__ void __launch_bounds__(32 * kCoopWarps, ICPB_COOP_MINB) nn_grid_coop_
             }
         }
         if (fill > 0) {
-            // pad to a multiple of four with candidates that can never be the minimum
+            // pad to a multiple of four with candidates that can never be the filter's minimum.  The exact stage evaluates
+            // all four members of the best group, pads included, so a pad must still name a REAL target of THIS
+            // registration: the first one of its cells (in a batch position 0 of the shared array is another
+            // registration's point)
             if (lane < 4 && (fill & 3) != 0 && fill + lane < ((fill + 3) & ~3)) {
                 buf.xs[fill + lane] = 0.f; buf.ys[fill + lane] = 0.f; buf.zs[fill + lane] = 0.f;
-                buf.ns[fill + lane] = CUDART_INF_F; buf.gp[fill + lane] = 0;
+                buf.ns[fill + lane] = CUDART_INF_F; buf.gp[fill + lane] = __ldg(&gstart[0]);
             }
             __syncwarp();
             coop_batch(buf, (fill + 3) & ~3, sorted, p, qx, qy, qz, A, live, best, bb);
