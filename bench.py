@@ -427,7 +427,7 @@ def run_b200(args, rank, world, local):
                          "unit": "TFLOP/s", "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one nn_partial launch at this workload, from the
                          # ncu --set full capture summarised in profiles/r01_ncu_nn_warp_fullres.txt (targets stay in L2; 9.6 MB read + 26.3 MB of per-split records written)
-                         "traffic": 35862784 if not wl["points"] else None,
+                         "traffic": 34666496 if not wl["points"] else None,  # dram read + write, profiles/r02_ncu_nn_partial_warp.txt
                          "peak_source": "FFMA micro-benchmark measured in this run (MEASURED_PEAKS.json holds "
                                         "only HBM and bf16 tensor peaks; the NN scan is FP32 CUDA-core bound)",
                          "flop_per_launch": flop_per_launch, "avg_launch_ms": avg_launch_s * 1e3,

@@ -413,7 +413,9 @@ def run_map1cm(args, rank, world, local, emit=True):
                           "stage_ms_per_pass": {"map_rays_max_over_ranks": rays_ms, "map_rays_per_rank": per_rank_rays,
                                                 "map_endpoints_rank0": ends_ms}},
                 "roofline": {"bound": "hbm", "kernel": "map_rays_brick_kernel", "achieved": rays_gbs, "peak": peak,
-                             "unit": "GB/s", "frac": rays_gbs / peak, "traffic": None,
+                             "unit": "GB/s", "frac": rays_gbs / peak,
+                             # dram__bytes_read + write of one launch at N=1, profiles/r02_ncu_map_rays_brick.txt
+                             "traffic": 22297088 if world == 1 else None,
                              "bytes_per_launch": rays_bytes / max(rays_launches, 1),
                              "avg_launch_ms": rays_ms / max(rays_launches, 1), "launches_timed": rays_launches,
                              "note": "algorithmic bytes = 2 B per voxel the walk passes + 12 B per ray (SURVEY.md 8d), whole "
