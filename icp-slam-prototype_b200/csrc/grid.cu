@@ -634,6 +634,7 @@ __device__ __forceinline__ bool beyond_reach(const GridMeta &g, const float4 &p)
 // partial best in (idx, dist) and append themselves to the heavy list of this pass.
 __global__ void __launch_bounds__(128) nn_grid_kernel(const RegDesc *__restrict__ descs, int pass)
 {
+    pdl_enter(); // icpb_internal.h: the grid before this one is complete from here on
     const RegDesc d = descs[blockIdx.z];
     IcpState *st = d.st;
     if (st->done) return;
@@ -682,6 +683,7 @@ __global__ void __launch_bounds__(128) nn_grid_kernel(const RegDesc *__restrict_
 // over the 32 lanes; the warp's lexicographic (distance, index) minimum is exchanged after every shell.
 __global__ void __launch_bounds__(128) nn_grid_heavy_kernel(const RegDesc *__restrict__ descs, int pass, int first_shell)
 {
+    pdl_enter(); // icpb_internal.h: the grid before this one is complete from here on
     const RegDesc d = descs[blockIdx.z];
     IcpState *st = d.st;
     if (st->done) return;
@@ -892,6 +894,7 @@ __device__ __forceinline__ void coop_batch(const CoopBuf &b, int fill, const flo
 
 __global__ void __launch_bounds__(32 * kCoopWarps, ICPB_COOP_MINB) nn_grid_coop_kernel(const RegDesc *__restrict__ descs, int pass, float coop_r)
 {
+    pdl_enter(); // icpb_internal.h: the grid before this one is complete from here on
     const RegDesc &d = descs[blockIdx.z];
     IcpState *st = d.st;
     if (st->done) return;
@@ -1218,13 +1221,13 @@ void launch_nn_grid(const RegDesc *descs, int batch, int max_n, int pass, int sm
     if (coop_r > 0.f) {
         hgrid.x = sm_count * 2; // a handful of queries at most reach the fall-back (it strides over its list) // warp-cooperative search (default), open queries finished from shell 0
         dim3 grid((max_n + 32 * kCoopWarps - 1) / (32 * kCoopWarps), 1, batch);
-        nn_grid_coop_kernel<<<grid, 32 * kCoopWarps, 0, s>>>(descs, pass, coop_r);
-        nn_grid_heavy_kernel<<<hgrid, 128, 0, s>>>(descs, pass, 0);
+        launch_pdl(nn_grid_coop_kernel, grid, dim3(32 * kCoopWarps), 0, s, descs, pass, coop_r);
+        launch_pdl(nn_grid_heavy_kernel, hgrid, dim3(128), 0, s, descs, pass, 0);
         return;
     }
     dim3 grid((max_n + 127) / 128, 1, batch);
-    nn_grid_kernel<<<grid, 128, 0, s>>>(descs, pass);
-    nn_grid_heavy_kernel<<<hgrid, 128, 0, s>>>(descs, pass, -1);
+    launch_pdl(nn_grid_kernel, grid, dim3(128), 0, s, descs, pass);
+    launch_pdl(nn_grid_heavy_kernel, hgrid, dim3(128), 0, s, descs, pass, -1);
 }
 
 } // namespace icpb

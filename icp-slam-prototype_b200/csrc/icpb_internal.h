@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -144,6 +145,7 @@ void launch_pack_band(const float4 *pts, int n, float4 *dst, cudaStream_t s);
 void launch_assemble_bands(const float4 *bands, int world, int band_capacity, float4 *out, int out_capacity, int *total,
                            cudaStream_t s);
 void launch_pending_translate(const RegDesc *descs, int batch, int max_n, cudaStream_t s);
+void launch_copy_back(const RegDesc *descs, int batch, int max_n, cudaStream_t s);
 void launch_keypoint_epilogue(const RegDesc *descs, int batch, int max_carry, cudaStream_t s);
 void launch_center(const float4 *pts, int n, double *chunk_sums, double *out3, unsigned int *counter,
                    cudaStream_t s);
@@ -240,6 +242,41 @@ void launch_map_rays(const MapDev &m, const PointSrc &src, const float origin[3]
                      unsigned int *layer_work = nullptr);
 extern unsigned int *const kCounterIsZero; // pass as layer_work: next_ray is already zero, skip the memset
 
+// ---- programmatic dependent launch (the kernels of the pass loop) -------------------------------------------
+// A pass is a chain of short kernels (search / scan -> sums -> solve -> next pass) whose launch latencies and drain
+// times add up to a tenth of a small registration.  Every kernel of the chain is launched with the programmatic
+// stream-serialisation attribute and starts with pdl_enter(): wait until the grid before it has completed and its
+// writes are visible (griddepcontrol.wait -- before ANY read of data the chain produces, the done flag included), then
+// let the grid after it be scheduled (griddepcontrol.launch_dependents: it fires once the LAST CTA of this grid is
+// resident, so the successor's CTAs fill the SMs as this grid's tail drains and sit in their own wait).  Because the
+// trigger comes after the wait, a grid never becomes resident before its grandparent has finished.
+// Decided per call by run_registrations (api.cu): small jobs only; ICPB_PDL=0 / 1 forces it off / on.  Launched
+// without the attribute the same kernels are fully serialised and the two instructions are no-ops.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_enter()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
+bool pdl_enabled();
+void pdl_set(bool on);
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- helpers of api.cu used by comm.cu ------------------------------------------------------------------------
 int api_fail(icpb_ctx *ctx, int status, const char *what, cudaError_t ce = cudaSuccess);
 int api_ws_get(icpb_ctx *ctx, int id, size_t bytes, void **out, bool zero_new = false);
@@ -267,6 +304,12 @@ struct icpb_ctx {
     std::vector<Buf> ws; // indexed by the WS_* ids in api.cu
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
+    // the registration loop's own staging block (descriptors, states, results read-back): not shared with the upload
+    // paths, so it stays valid while a registration started by icpb_icp_register_async is in flight
+    void *pinned_reg = nullptr;
+    size_t pinned_reg_bytes = 0;
+    icpb_pending *inflight = nullptr; // at most one per context; drained by the next registration / wait / destroy
+    cudaEvent_t ev_reg_done = nullptr;
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;
     // profiling mode: CUDA-event spans around individual kernels other than nn_partial (icpb_ctx_profile_read)
@@ -276,6 +319,16 @@ struct icpb_ctx {
     };
     std::vector<Span> spans;          // recorded, not yet read
     std::vector<cudaEvent_t> ev_pool; // recycled events
+};
+
+// A registration (or batch) whose kernels are enqueued and whose results have not been read yet.
+struct icpb_pending {
+    icpb_ctx *ctx = nullptr;
+    int count = 0;
+    std::function<int(icpb_icp_result *)> finish; // waits for the stream work, fills `count` results
+    std::vector<icpb_icp_result> results;          // filled when the context drains it before the owner waits
+    bool finished = false;
+    int status = 0;
 };
 
 struct icpb_cloud {

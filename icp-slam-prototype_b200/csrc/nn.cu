@@ -174,6 +174,7 @@ template <int QPT>
 __global__ void __launch_bounds__(kNnThreads) nn_partial_kernel(const RegDesc *__restrict__ descs, IcpState *states,
                                                                 int splits, int pass)
 {
+    pdl_enter(); // icpb_internal.h: the grid before this one is complete from here on
     // the loop state sits at states[blockIdx.z] (== d.st): addressed from the kernel argument, its load does not wait
     // for the descriptor's
     IcpState *st = states + blockIdx.z;
@@ -324,6 +325,7 @@ template <int QPT>
 __global__ void __launch_bounds__(kNnThreads, (QPT >= 16 ? 2 : QPT >= 12 ? 3 : 4)) nn_partial_centred_kernel(const RegDesc *__restrict__ descs,
                                                                         IcpState *states, int splits, int pass)
 {
+    pdl_enter(); // icpb_internal.h: the grid before this one is complete from here on
     // the loop state sits at states[blockIdx.z] (== d.st): addressed from the kernel argument, its load does not wait
     // for the descriptor's
     IcpState *st = states + blockIdx.z;
@@ -500,6 +502,7 @@ template <int QPT>
 __global__ void __launch_bounds__(kNnThreads, (QPT >= 16 ? 2 : QPT >= 12 ? 3 : 4)) nn_partial_warp_kernel(
     const RegDesc *__restrict__ descs, IcpState *states, int splits, int pass)
 {
+    pdl_enter(); // icpb_internal.h: the grid before this one is complete from here on
     // the loop state sits at states[blockIdx.z] (== d.st): addressed from the kernel argument, its load does not wait
     // for the descriptor's
     IcpState *st = states + blockIdx.z;
@@ -684,13 +687,13 @@ __global__ void __launch_bounds__(kNnThreads, (QPT >= 16 ? 2 : QPT >= 12 ? 3 : 4
 template <int QPT>
 static void launch_warp(dim3 grid, const RegDesc *descs, IcpState *states, int splits, int pass, cudaStream_t s)
 {
-    nn_partial_warp_kernel<QPT><<<grid, kNnThreads, 0, s>>>(descs, states, splits, pass);
+    launch_pdl(nn_partial_warp_kernel<QPT>, grid, dim3(kNnThreads), 0, s, descs, states, splits, pass);
 }
 
 template <int QPT>
 static void launch_centred(dim3 grid, const RegDesc *descs, IcpState *states, int splits, int pass, cudaStream_t s)
 {
-    nn_partial_centred_kernel<QPT><<<grid, kNnThreads, 0, s>>>(descs, states, splits, pass);
+    launch_pdl(nn_partial_centred_kernel<QPT>, grid, dim3(kNnThreads), 0, s, descs, states, splits, pass);
 }
 
 void launch_nn_partial(const RegDesc *descs, IcpState *states, int batch, int max_n, int qpt, int splits, int pass,
@@ -716,9 +719,9 @@ void launch_nn_partial(const RegDesc *descs, IcpState *states, int batch, int ma
         }
     } else {
         switch (qpt) {
-        case 8: nn_partial_kernel<8><<<grid, block, 0, s>>>(descs, states, splits, pass); break;
-        case 4: nn_partial_kernel<4><<<grid, block, 0, s>>>(descs, states, splits, pass); break;
-        default: nn_partial_kernel<2><<<grid, block, 0, s>>>(descs, states, splits, pass); break;
+        case 8: launch_pdl(nn_partial_kernel<8>, grid, block, 0, s, descs, states, splits, pass); break;
+        case 4: launch_pdl(nn_partial_kernel<4>, grid, block, 0, s, descs, states, splits, pass); break;
+        default: launch_pdl(nn_partial_kernel<2>, grid, block, 0, s, descs, states, splits, pass); break;
         }
     }
 }
@@ -786,6 +789,9 @@ __device__ __forceinline__ void swap_cols(double (&A)[9], double (&V)[9], double
     }
 }
 
+#ifdef ICPB_SOLVE_CLOCKS
+__device__ long long g_svd_clocks;
+#endif
 __device__ void svd3(const double *Ain, double (&U)[9], double (&w)[3], double (&Vt)[9])
 {
     double A[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -922,7 +928,13 @@ __device__ __forceinline__ void solve_step_local(IcpState *st, const IcpParamsDe
     float Rf[9], tf[3];
     double U[9], w[3], Vt[9], Rd[9];
     if (prm->solve_mode == ICPB_SOLVE_REFERENCE) {
+#ifdef ICPB_SOLVE_CLOCKS
+        const long long cs = clock64();
+#endif
         svd3(&sums[6], U, w, Vt); // icp.cpp:212-215, M = sum b a^T (uncentred)
+#ifdef ICPB_SOLVE_CLOCKS
+        g_svd_clocks = clock64() - cs;
+#endif
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -1065,7 +1077,7 @@ __device__ __forceinline__ void finalize_tail(const RegDesc &d, IcpState *st, co
     if (tid < kTerms) {
         double s = s_w[0][tid];
         for (int wv = 1; wv < kChunk / 32; ++wv) s = s + s_w[wv][tid];
-        d.chunk_sums[(size_t)chunk * kTerms + tid] = s;
+        d.chunk_sums[(size_t)tid * nchunks + chunk] = s; // term-major: level 2 reads every term coalesced
     }
     if (!kTicket) return; // the second level and the solve run as their own one-CTA kernel (nn_solve_kernel)
     // the barrier orders the chunk sums written by threads 0..19 before thread 0's fence, and the fence (cumulative)
@@ -1091,6 +1103,9 @@ __device__ __forceinline__ void finalize_last_cta_body(const double *chunk_sums,
 {
     double (&s_w)[kChunk / 32][kTerms] = sh.w;
     double (&s_tot)[kTerms] = sh.tot;
+#ifdef ICPB_SOLVE_CLOCKS
+    const long long sh_clock0 = clock64();
+#endif
     __threadfence();
     {
         double acc[kTerms];
@@ -1099,7 +1114,7 @@ __device__ __forceinline__ void finalize_last_cta_body(const double *chunk_sums,
         for (int c = tid; c < nchunks; c += kChunk) {
             double v[kTerms];
 #pragma unroll
-            for (int k = 0; k < kTerms; ++k) v[k] = __ldcg(&chunk_sums[(size_t)c * kTerms + k]); // issued together
+            for (int k = 0; k < kTerms; ++k) v[k] = __ldcg(&chunk_sums[(size_t)k * nchunks + c]); // issued together, coalesced
 #pragma unroll
             for (int k = 0; k < kTerms; ++k) acc[k] = acc[k] + v[k];
         }
@@ -1118,7 +1133,14 @@ __device__ __forceinline__ void finalize_last_cta_body(const double *chunk_sums,
     __syncthreads();
     if (tid == 0) {
         if (rearm_ticket) st->block_counter = 0; // re-armed before solve_step copies the state
+#ifdef ICPB_SOLVE_CLOCKS
+        const long long c1 = clock64();
+#endif
         solve_step(st, prm, s_tot, pass, mlog);
+#ifdef ICPB_SOLVE_CLOCKS
+        const long long c2 = clock64();
+        if (pass == 5) printf("solve clocks: level2 %lld  solve %lld of which svd3 %lld\n", c1 - sh_clock0, c2 - c1, g_svd_clocks);
+#endif
     }
 }
 
@@ -1140,6 +1162,7 @@ __global__ void __launch_bounds__(2 * kChunk) nn_finalize_kernel(const RegDesc *
                                                                  const IcpParamsDev *__restrict__ prm, int splits,
                                                                  int pass, int filter)
 {
+    pdl_enter(); // icpb_internal.h: the grid before this one is complete from here on
     IcpState *st = states + blockIdx.z;  // == d.st; see nn_partial*
     const RegDesc d = descs[blockIdx.z]; // by value: no pointer reloads after stores
     if (st->done) return;
@@ -1383,6 +1406,7 @@ __global__ void __launch_bounds__(kChunk, 5) nn_finalize_coop_kernel(const RegDe
                                                                   const float4 *__restrict__ q_cur,
                                                                   const float4 *__restrict__ q_nb, int q_n)
 {
+    pdl_enter(); // icpb_internal.h: the grid before this one is complete from here on
     IcpState *st = states + blockIdx.z;
     const int chunk = blockIdx.x;
     float4 a_early = make_float4(0.f, 0.f, 0.f, 0.f), nb_early = a_early;
@@ -1422,6 +1446,7 @@ __global__ void __launch_bounds__(kChunk, 5) nn_finalize_coop_kernel(const RegDe
 __global__ void __launch_bounds__(kChunk, 1) nn_solve_kernel(const RegDesc *__restrict__ descs, IcpState *states,
                                                              const IcpParamsDev *__restrict__ prm, int pass)
 {
+    pdl_enter(); // icpb_internal.h: the grid before this one is complete from here on
     IcpState *st = states + blockIdx.z;
     if (st->done) return;
     const RegDesc &d = descs[blockIdx.z];
@@ -1435,15 +1460,15 @@ void launch_nn_finalize(const RegDesc *descs, IcpState *states, const IcpParamsD
 {
     dim3 grid((max_n + kChunk - 1) / kChunk, 1, batch);
     if (splits < 0) { // cooperative cell-grid search
-        nn_finalize_coop_kernel<<<grid, kChunk, 0, s>>>(descs, states, prm, pass, batch == 1 ? q_cur : nullptr, q_nb, max_n);
-        nn_solve_kernel<<<dim3(1, 1, batch), kChunk, 0, s>>>(descs, states, prm, pass);
+        launch_pdl(nn_finalize_coop_kernel, grid, dim3(kChunk), 0, s, descs, states, prm, pass, batch == 1 ? q_cur : nullptr, q_nb, max_n);
+        launch_pdl(nn_solve_kernel, dim3(1, 1, batch), dim3(kChunk), 0, s, descs, states, prm, pass);
         return;
     }
     // brute-force modes on few CTAs (a small cloud; latency-bound: 10k points are 40 CTAs on 148 SMs): a pair of
     // threads per query for the group selection and the exact stage.  Many CTAs (full resolution, batches) are
     // throughput-bound and keep one thread per query (measured: pairs -6 % on the 1024-registration batch).
     const bool paired = splits > 0 && (long long)grid.x * batch <= 2 * 148;
-    nn_finalize_kernel<<<grid, paired ? 2 * kChunk : kChunk, 0, s>>>(descs, states, prm, splits, pass, filter);
+    launch_pdl(nn_finalize_kernel, grid, dim3(paired ? 2 * kChunk : kChunk), 0, s, descs, states, prm, splits, pass, filter);
 }
 
 // --------------------------------------------------------------------------
@@ -1522,6 +1547,7 @@ void launch_assemble_bands(const float4 *bands, int world, int band_capacity, fl
 
 __global__ void pending_translate_kernel(const RegDesc *__restrict__ descs)
 {
+    pdl_enter(); // icpb_internal.h: the grid before this one is complete from here on
     const RegDesc &d = descs[blockIdx.z];
     const IcpState *st = d.st;
     if (!st->pending_translate) return;
@@ -1539,6 +1565,7 @@ __global__ void pending_translate_kernel(const RegDesc *__restrict__ descs)
 // passes, pass-major and in query order, into the non-association list (icp.cpp:96,508).
 __global__ void __launch_bounds__(256) keypoint_epilogue_kernel(const RegDesc *__restrict__ descs)
 {
+    pdl_enter(); // icpb_internal.h: the grid before this one is complete from here on
     const RegDesc &d = descs[blockIdx.z];
     const IcpState *st = d.st;
     if (blockIdx.y + 1 < gridDim.y) {
@@ -1579,13 +1606,29 @@ void launch_keypoint_epilogue(const RegDesc *descs, int batch, int max_carry, cu
 {
     const int blocks = (max_carry + 255) / 256;
     dim3 grid(blocks > 0 ? blocks : 1, 2, batch); // y = 0: carried points; y = 1: reject compaction
-    keypoint_epilogue_kernel<<<grid, 256, 0, s>>>(descs);
+    launch_pdl(keypoint_epilogue_kernel, grid, dim3(256), 0, s, descs);
+}
+
+// The associated cloud back into the caller's buffer when the loop ended with it in the alternate one.
+__global__ void copy_back_kernel(const RegDesc *__restrict__ descs)
+{
+    pdl_enter(); // icpb_internal.h
+    const RegDesc &d = descs[blockIdx.z];
+    if (d.st->last_buf != 1) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < d.n) d.D[0][i] = d.D[1][i];
+}
+
+void launch_copy_back(const RegDesc *descs, int batch, int max_n, cudaStream_t s)
+{
+    dim3 grid((max_n + 255) / 256, 1, batch);
+    launch_pdl(copy_back_kernel, grid, dim3(256), 0, s, descs);
 }
 
 void launch_pending_translate(const RegDesc *descs, int batch, int max_n, cudaStream_t s)
 {
     dim3 grid((max_n + 255) / 256, 1, batch);
-    pending_translate_kernel<<<grid, 256, 0, s>>>(descs);
+    launch_pdl(pending_translate_kernel, grid, dim3(256), 0, s, descs);
 }
 
 // --------------------------------------------------------------------------

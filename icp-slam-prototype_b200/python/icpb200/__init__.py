@@ -265,6 +265,26 @@ class Context:
         self.check(self.lib.icpb_icp_register_batch(self.h, dh, th, n, C.byref(prm), res))
         return [r.to_dict() for r in res]
 
+    def icp_register_async(self, data, target, max_iterations=20, threshold=0.0, max_nn_distance=0.75,
+                           solve_mode=SOLVE_REFERENCE, nn_mode=NN_BRUTE, grid_cell=0.0):
+        """icpb_icp_register_async: returns a Pending as soon as the loop is enqueued; .wait() -> result dict."""
+        prm = IcpParams(max_iterations, threshold, max_nn_distance, solve_mode, (C.c_float * 3)(0, 0, 0), None, None,
+                        nn_mode, grid_cell, FILTER_AUTO)
+        h = C.c_void_p()
+        self.check(self.lib.icpb_icp_register_async(self.h, data.h, target.h, C.byref(prm), C.byref(h)))
+        return Pending(self, h, 1, (data, target))
+
+    def icp_register_batch_async(self, datas, targets, max_iterations=20, threshold=0.0, max_nn_distance=0.75,
+                                 solve_mode=SOLVE_REFERENCE, nn_mode=NN_BRUTE, grid_cell=0.0):
+        n = len(datas)
+        prm = IcpParams(max_iterations, threshold, max_nn_distance, solve_mode, (C.c_float * 3)(0, 0, 0), None, None,
+                        nn_mode, grid_cell, FILTER_AUTO)
+        dh = (C.c_void_p * n)(*[d.h for d in datas])
+        th = (C.c_void_p * n)(*[t.h for t in targets])
+        h = C.c_void_p()
+        self.check(self.lib.icpb_icp_register_batch_async(self.h, dh, th, n, C.byref(prm), C.byref(h)))
+        return Pending(self, h, n, (list(datas), list(targets)))
+
     # ---- map
     def map(self, dims, cell, z_lo=0, z_hi=None):
         return Map(self, dims, cell, z_lo, dims[2] if z_hi is None else z_hi)
@@ -356,6 +376,28 @@ class Cloud:
         self.ctx.check(self.ctx.lib.icpb_cloud_center(self.h, c))
         return np.array(c[:])
 
+
+
+class Pending:
+    """A registration in flight (icpb_pending).  Keeps its clouds alive until the wait."""
+
+    def __init__(self, ctx, h, count, keep):
+        self.ctx, self.h, self.count, self._keep = ctx, h, count, keep
+
+    def ready(self):
+        r = C.c_int(0)
+        self.ctx.check(self.ctx.lib.icpb_icp_pending_ready(self.h, C.byref(r)))
+        return bool(r.value)
+
+    def wait(self):
+        if self.h is None:
+            raise RuntimeError("already waited for")
+        res = (IcpResult * self.count)()
+        h, self.h = self.h, None
+        self.ctx.check(self.ctx.lib.icpb_icp_pending_wait(h, res))
+        self._keep = None
+        out = [r.to_dict() for r in res]
+        return out[0] if self.count == 1 else out
 
 class Map:
     def __init__(self, ctx, dims, cell, z_lo, z_hi):

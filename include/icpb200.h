@@ -39,6 +39,7 @@ enum {
 typedef struct icpb_ctx icpb_ctx;
 typedef struct icpb_cloud icpb_cloud;
 typedef struct icpb_map icpb_map;
+typedef struct icpb_pending icpb_pending; /* a registration that has been enqueued and not yet waited for */
 typedef struct icpb_comm icpb_comm;       /* one rank of a multi-GPU job: an NCCL communicator bound to a context */
 typedef struct icpb_slabmap icpb_slabmap; /* the rank's z-slab of a certainty map shared by the job */
 
@@ -235,6 +236,22 @@ int icpb_icp_register_carry(icpb_ctx *ctx, icpb_cloud *data, const icpb_cloud *t
 /* `count` independent registrations (BASELINE config 4); results[i] for pair i. */
 int icpb_icp_register_batch(icpb_ctx *ctx, icpb_cloud *const *data, const icpb_cloud *const *target,
                             int count, const icpb_icp_params *params, icpb_icp_result *results);
+/* Non-blocking forms of icpb_icp_register / icpb_icp_register_batch.  The reference's getTransformation
+ * (icp.cpp:28-285) blocks its caller for the whole loop; here the loop runs on the device without host involvement,
+ * so the call returns as soon as the kernels and the read-back of the result block are enqueued on the context's
+ * stream and the host may prepare the next frame (upload, back-projection: they queue behind it on the same stream)
+ * or run another context.  One registration can be in flight per context; whatever registration call comes next on
+ * the context first completes it.  The clouds must stay alive, and params' trace buffers valid, until the wait.
+ * (With ICPB_NN_GRID / ICPB_NN_AUTO on large clouds the call still waits once, ~30 us, for the bounding box of
+ * the targets that sizes the cell tables.)
+ * icpb_icp_pending_wait blocks until the work is done, fills `results` (count entries, nullable) and frees the
+ * handle; icpb_icp_pending_ready returns 1 in *ready when the wait would not block. */
+int icpb_icp_register_async(icpb_ctx *ctx, icpb_cloud *data, const icpb_cloud *target,
+                            const icpb_icp_params *params, icpb_pending **out);
+int icpb_icp_register_batch_async(icpb_ctx *ctx, icpb_cloud *const *data, const icpb_cloud *const *target,
+                                  int count, const icpb_icp_params *params, icpb_pending **out);
+int icpb_icp_pending_ready(icpb_pending *pending, int *ready);
+int icpb_icp_pending_wait(icpb_pending *pending, icpb_icp_result *results);
 /* The loop as the reference runs it (icp.cpp:98,155-258): the data cloud's KEY-POINTS are
  * associated with the map cloud's key-points (findGlobalKeyPointAssociations, icp.cpp:488-539; pass
  * max_nn_distance = MAX_NN_KEYPOINT_DISTANCE 0.1, icp.hpp:10), `points` (nullable) follow every motion like

@@ -242,3 +242,75 @@ def test_icp_batch_in_grid_mode_matches_the_oracle(ctx, orc, pair10k, mode):
         assert np.array_equal(datas[k].download().view(np.uint8), rout.view(np.uint8)), k
     for c in datas + targets:
         c.close()
+
+
+# ---- icpb_icp_register_async: the same loop, the host not blocked ---------------------------------------------------
+def _same_result(a, b):
+    for k in ("iterations", "nn_passes", "n_assoc", "mse"):
+        assert a[k] == b[k], k
+    for k in ("pose_R", "pose_t", "rigid", "cam_rotation", "cam_position"):
+        assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("nn_mode", [0, 1])
+def test_icp_async_equals_blocking_call_and_the_oracle(ctx, orc, pair10k, nn_mode):
+    data, target = pair10k
+    data, target = data[:6000], target[:7000]
+    ref, rout, _, _ = orc.icp(data, target, 12, 0.0, 0.75, 0, n_threads=8)
+    tc = ctx.cloud_from_points(target)
+    d_sync, d_async = ctx.cloud_from_points(data), ctx.cloud_from_points(data)
+    r_sync, _, _ = ctx.icp_register(d_sync, tc, 12, 0.0, 0.75, 0, nn_mode=nn_mode)
+    pend = ctx.icp_register_async(d_async, tc, 12, 0.0, 0.75, 0, nn_mode=nn_mode)
+    # work queued behind the registration on the same stream while it is in flight
+    other = ctx.cloud_from_points(target[:100])
+    other.transform(None, np.array([1, 2, 3], np.float32))
+    r_async = pend.wait()
+    assert pend.h is None
+    _same_result(r_async, r_sync)
+    assert np.array_equal(r_async["pose_R"], ref["pose_R"]) and np.array_equal(r_async["pose_t"], ref["pose_t"])
+    assert np.array_equal(d_async.download().view(np.uint8), rout.view(np.uint8))
+    assert np.array_equal(d_sync.download().view(np.uint8), rout.view(np.uint8))
+    moved = other.download()
+    assert np.array_equal(moved["x"], target[:100]["x"] + np.float32(1))
+    for c in (tc, d_sync, d_async, other):
+        c.close()
+
+
+def test_icp_async_is_drained_by_the_next_registration(ctx, orc, pair10k):
+    """One registration in flight per context: a later call completes the earlier one first; its results wait in the
+    handle."""
+    data, target = pair10k
+    a = (data[:3000], target[:4000])
+    b = (data[2000:7000], target[1000:8000])
+    refs = [orc.icp(d, t, 8, 0.0, 0.75, 0, n_threads=8)[0] for d, t in (a, b)]
+    ca, ta = ctx.cloud_from_points(a[0]), ctx.cloud_from_points(a[1])
+    cb, tb = ctx.cloud_from_points(b[0]), ctx.cloud_from_points(b[1])
+    pa = ctx.icp_register_async(ca, ta, 8, 0.0, 0.75, 0)
+    rb, _, _ = ctx.icp_register(cb, tb, 8, 0.0, 0.75, 0)      # drains pa
+    assert pa.ready()
+    ra = pa.wait()
+    for r, ref in ((ra, refs[0]), (rb, refs[1])):
+        assert r["n_assoc"] == ref["n_assoc"]
+        assert np.array_equal(r["pose_R"], ref["pose_R"]) and np.array_equal(r["pose_t"], ref["pose_t"])
+    with pytest.raises(RuntimeError):
+        pa.wait()
+    for c in (ca, ta, cb, tb):
+        c.close()
+
+
+def test_icp_batch_async_equals_batch(ctx, pair10k):
+    data, target = pair10k
+    cases = [(data[:4000], target[:5000]), (data[3000:9000], target), (data[::2], target[::3])]
+    def clouds():
+        return [ctx.cloud_from_points(d) for d, _ in cases], [ctx.cloud_from_points(t) for _, t in cases]
+    d1, t1 = clouds()
+    d2, t2 = clouds()
+    sync = ctx.icp_register_batch(d1, t1, 10, 0.0, 0.75, 0)
+    pend = ctx.icp_register_batch_async(d2, t2, 10, 0.0, 0.75, 0)
+    res = pend.wait()
+    assert len(res) == len(cases)
+    for k in range(len(cases)):
+        _same_result(res[k], sync[k])
+        assert np.array_equal(d1[k].download().view(np.uint8), d2[k].download().view(np.uint8))
+    for c in d1 + t1 + d2 + t2:
+        c.close()
