@@ -373,7 +373,7 @@ def run_map1cm(args, rank, world, local, emit=True):
         updates = visited + npts  # voxels visited by rays + endpoint updates, per pass over the sequence
         alg_bytes = 2.0 * visited + 12.0 * npts + 14.0 * npts
         rays_bytes = 2.0 * visited + 12.0 * npts        # 2 B per visited voxel + 12 B per ray
-        peak = _hbm_peak()
+        peak = _hbm_peak() * world  # whole-job bytes over the slowest rank's time: against the N GPUs' aggregate bandwidth
         rays_gbs = rays_bytes / max(rays_ms * 1e-3, 1e-12) / 1e9
         # the whole sequence through the oracle: every slab must equal the oracle grid's slab
         cb, oracle_ok = None, None
@@ -419,7 +419,8 @@ def run_map1cm(args, rank, world, local, emit=True):
                              "bytes_per_launch": rays_bytes / max(rays_launches, 1),
                              "avg_launch_ms": rays_ms / max(rays_launches, 1), "launches_timed": rays_launches,
                              "note": "algorithmic bytes = 2 B per voxel the walk passes + 12 B per ray (SURVEY.md 8d), whole "
-                                     "job; time = the slowest rank's summed launches.  The brick-skipping walk does not touch "
+                                     "job; time = the slowest rank's summed launches; peak = n_gpus x the measured copy "
+                                     "bandwidth of one GPU.  The brick-skipping walk does not touch "
                                      "the voxels of empty bricks, so the figure can exceed what the memory system moves"},
                 "cpu_baseline": cb,
                 "e2e": {"value": updates / (e2e_tot * 1e-3), "unit": "voxel updates/s",
