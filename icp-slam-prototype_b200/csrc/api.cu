@@ -18,7 +18,7 @@ thread_local std::string g_create_error;
 enum WsId {
     WS_DESCS = 0, WS_STATES, WS_PARAMS, WS_TGT_SOA, WS_PM1, WS_PM2, WS_PG, WS_IDX, WS_DIST, WS_CHUNKS, WS_ALT,
     WS_IDX_TRACE, WS_DIST_TRACE, WS_MISC, WS_DEPTH, WS_BGR, WS_KEEP, WS_TILESTATE, WS_IMG_A, WS_IMG_B, WS_NORMALS,
-    WS_RT, WS_GRID_META, WS_GRID_COUNTS, WS_GRID_CURSOR, WS_GRID_SUMS, WS_GRID_SORTED, WS_GRID_BBOX, WS_GRID_HEAVY, WS_BATCHSTATE, WS_TRACK, WS_PA, WS_PM3, WS_PG2, WS_MLOG, WS_REJ_FLAG, WS_REJ_PTS, WS_FRAME, WS_PERM, WS_SORT_COUNTS, WS_SORT_SUMS, WS_GRID_NB, WS_GRID_SEED, WS_GRID_BOX, WS_GRID_BOXC, WS_COUNT
+    WS_RT, WS_GRID_META, WS_GRID_COUNTS, WS_GRID_CURSOR, WS_GRID_SUMS, WS_GRID_SORTED, WS_GRID_BBOX, WS_GRID_HEAVY, WS_BATCHSTATE, WS_TRACK, WS_PA, WS_PM3, WS_PG2, WS_MLOG, WS_REJ_FLAG, WS_REJ_PTS, WS_FRAME, WS_PERM, WS_SORT_COUNTS, WS_SORT_SUMS, WS_GRID_NB, WS_GRID_SEED, WS_GRID_BOX, WS_GRID_BOXC, WS_GRID_ORD, WS_GRID_ORDCNT, WS_COUNT
 };
 
 int fail(icpb_ctx *ctx, int status, const char *what, cudaError_t ce = cudaSuccess)
@@ -266,6 +266,12 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
     float4 *d_gsorted = nullptr;
     int *d_gheavy = nullptr;
     float4 *d_gnb = nullptr, *d_gseed = nullptr, *d_gbox = nullptr, *d_gboxc = nullptr;
+    int *d_gord = nullptr, *d_gordcnt = nullptr;
+    // Work order of the cooperative search (grid.cu): heaviest warps first from the second pass on, when the pass is more
+    // than one wave of warps deep (full resolution: 3.78 -> 3.50 ms; a single 10k-point cloud is a tenth of a wave and
+    // only pays the two extra loads).  ICPB_GRID_ORDER=0 / 1 forces natural order / ordering.
+    const int order_knob = env_int("ICPB_GRID_ORDER", 2);
+    const bool grid_ordered = order_knob == 1 || (order_knob == 2 && tot_n / 32 > (size_t)ctx->sm_count * 20);
     long long grid_launches = 0;
     size_t total_entries = 0, total_coarse = 0, tot_m = 0;
     int max_ncells = 0;
@@ -360,6 +366,10 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         if ((rc = ws_get(ctx, WS_GRID_BOX, sizeof(float4) * 2 * total_entries, (void **)&d_gbox))) return rc;
         if (any_children && (rc = ws_get(ctx, WS_GRID_BOXC, sizeof(float4) * 2 * total_coarse, (void **)&d_gboxc))) return rc;
         if ((rc = ws_get(ctx, WS_GRID_SEED, sizeof(float4) * (tot_n + 32), (void **)&d_gseed))) return rc;
+        if (grid_ordered) {
+            if ((rc = ws_get(ctx, WS_GRID_ORD, sizeof(int) * 2 * kOrderBins * (tot_n / 32), (void **)&d_gord))) return rc;
+            if ((rc = ws_get(ctx, WS_GRID_ORDCNT, sizeof(int) * (size_t)count * passes * kOrderBins, (void **)&d_gordcnt))) return rc;
+        }
         grid_launches = 8 + (any_children ? 1 : 0);
     }
 
@@ -415,9 +425,12 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
             d.gpairs = ctx->profiling ? (unsigned long long *)(d_gsums + ((total_entries / 4096 + 8 + 1) & ~(size_t)1)) : nullptr;
             d.gheavy_count = d_gheavy + (size_t)b * (passes + 8);
             d.gheavy = d_gheavy + (size_t)count * (passes + 8) + off_n;
+            d.gord = d_gord ? d_gord + 2 * kOrderBins * (off_n / 32) : nullptr;
+            d.gord_count = d_gordcnt ? d_gordcnt + (size_t)b * passes * kOrderBins : nullptr;
         } else {
             d.grid = nullptr; d.gsorted = nullptr; d.gstart = nullptr; d.gcursor = nullptr; d.gbox = nullptr; d.gboxc = nullptr;
             d.gnb = nullptr; d.gseed = nullptr; d.gheavy = nullptr; d.gheavy_count = nullptr; d.gpairs = nullptr;
+            d.gord = nullptr; d.gord_count = nullptr;
         }
         d.carry = (kp_mode && regs[b].carry) ? regs[b].carry->d_pts : nullptr;
         d.n_carry = (kp_mode && regs[b].carry) ? regs[b].carry->n : 0;
@@ -469,6 +482,7 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         CU(ctx, cudaMemcpyAsync(d_gmeta, h_gm, sizeof(GridMeta) * (size_t)count, cudaMemcpyHostToDevice, st));
         CU(ctx, cudaMemsetAsync(d_gcounts, 0, sizeof(int) * total_entries, st));
         CU(ctx, cudaMemsetAsync(d_gheavy, 0, sizeof(int) * (size_t)count * ((size_t)passes + 8), st));
+        if (d_gordcnt) CU(ctx, cudaMemsetAsync(d_gordcnt, 0, sizeof(int) * (size_t)count * passes * kOrderBins, st));
         launch_grid_build_batch(d_descs, count, max_m, max_ncells, d_gcounts, d_gcursor, (long long)total_entries, d_gsums,
                                 d_gsorted, d_gbox, any_children, st);
         if (ctx->profiling) // after the scans are done with the block sums

@@ -789,7 +789,10 @@ __device__ __forceinline__ float sqrt_approx(float x)
 #define ICPB_COOP_CAP 512
 #endif
 constexpr int kCoopCap = ICPB_COOP_CAP;   // candidates per warp batch (20 B each in shared memory)
-constexpr int kCoopWarps = 4;
+#ifndef ICPB_COOP_WARPS
+#define ICPB_COOP_WARPS 4
+#endif
+constexpr int kCoopWarps = ICPB_COOP_WARPS;
 #ifndef ICPB_COOP_GROUP
 #define ICPB_COOP_GROUP 4
 #endif
@@ -798,6 +801,10 @@ constexpr int kCoopGroup = ICPB_COOP_GROUP; // lanes per bounding sphere of the 
 #define ICPB_COOP_MINB 5
 #endif
 
+#ifdef ICPB_COOP_CLOCKS
+__device__ int g_coop_dbg[16384 * 8];
+__device__ __forceinline__ unsigned __smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+#endif
 struct CoopBuf {
     float xs[kCoopCap], ys[kCoopCap], zs[kCoopCap], ns[kCoopCap]; // centred candidates, SoA
     int gp[kCoopCap];                                              // their slot in the sorted target array
@@ -892,18 +899,31 @@ __device__ __forceinline__ void coop_batch(const CoopBuf &b, int fill, const flo
     if (__any_sync(0xffffffffu, amb)) coop_rescan(b, fill, sorted, p, qx, qy, qz, amb ? lim : -CUDART_INF_F, best, bb);
 }
 
-__global__ void __launch_bounds__(32 * kCoopWarps, ICPB_COOP_MINB) nn_grid_coop_kernel(const RegDesc *__restrict__ descs, int pass, float coop_r)
+// One warp's share of a pass: the 32 queries of work item `wpos`.
+__device__ __forceinline__ void coop_warp(const RegDesc &d, IcpState *st, CoopBuf &buf, const int pass, const float coop_r,
+                                          const int wpos, const int lane)
 {
-    pdl_enter(); // icpb_internal.h: the grid before this one is complete from here on
-    const RegDesc &d = descs[blockIdx.z];
-    IcpState *st = d.st;
-    if (st->done) return;
-    __shared__ __align__(16) CoopBuf s_buf[kCoopWarps];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    CoopBuf &buf = s_buf[wid];
     const int n = d.n;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k - lane >= n) return; // whole warp past the end
+    // ---- which 32 sorted slots this warp takes.  From the second pass on the warps are handed out heaviest first:
+    //      a warp's cost (the candidates it stages, the cells it tests: up to five times the mean) changes little from
+    //      pass to pass, and a heavy warp that starts late runs on while the rest of the GPU idles (measured with
+    //      %globaltimer per warp: in natural order the last 28 % of the kernel's duration had < 4 of 20 warps per SM
+    //      resident; tools/coop_clocks.py).  Classes by the cycles the warp took in the previous pass.
+    const int ord_stride = d.n_stride >> 5;
+    int wsel = wpos;
+    if (d.gord && pass > 0) {
+        const int *cnt = d.gord_count + (pass - 1) * kOrderBins;
+        const int *lists = d.gord + ((pass - 1) & 1) * kOrderBins * ord_stride;
+        int before = 0;
+#pragma unroll
+        for (int b = 0; b < kOrderBins; ++b) {
+            const int c = __ldcg(&cnt[b]);
+            if (wpos >= before && wpos < before + c) wsel = __ldcg(&lists[b * ord_stride + (wpos - before)]);
+            before += c;
+        }
+    }
+    const long long ord_clk0 = clock64();
+    const int k = wsel * 32 + lane;
     const bool valid = k < n;
     const int *perm = d.perm;
     const int i = valid ? (perm ? perm[k] : k) : 0;
@@ -983,6 +1003,11 @@ __global__ void __launch_bounds__(32 * kCoopWarps, ICPB_COOP_MINB) nn_grid_coop_
     const float qx = -2.f * ax, qy = -2.f * ay, qz = -2.f * az; // W = |t'|^2 - 2 a'.t'
 
     unsigned long long staged = 0; // candidates this warp put through the filter (x 32 lanes = pairs), profiling only
+#ifdef ICPB_COOP_CLOCKS
+    const long long clk0 = clock64();
+    unsigned long long gt0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
+    int dbg_rounds = 0, dbg_rows = 0, dbg_cells = 0, dbg_box = 0;
+#endif
     for (int round = 0; round < 8; ++round) {
         // lanes whose ball outgrew the cooperative phase go to the warp-per-query kernel with their partial best
         const float rr = fminf(rad, max_reach);
@@ -1053,6 +1078,9 @@ __global__ void __launch_bounds__(32 * kCoopWarps, ICPB_COOP_MINB) nn_grid_coop_
         bz0 = __reduce_min_sync(full, bz0); bz1 = __reduce_max_sync(full, bz1);
         const int nyb = by1 - by0 + 1, nzb = bz1 - bz0 + 1;
         const int nrows = nyb * nzb;
+#ifdef ICPB_COOP_CLOCKS
+        ++dbg_rounds; dbg_rows += nrows; dbg_box = max(dbg_box, nrows * (bx1 - bx0 + 1));
+#endif
         const float xlo = g.mn[0] + bx0 * g.h, xhi = g.mn[0] + (bx1 + 1) * g.h;
         const float slack = 1e-3f * g.h; // float rounding of the cell assignment (as in axis_gap)
         const bool live = !done; // a lane that is done must not pick anything up any more
@@ -1076,6 +1104,9 @@ __global__ void __launch_bounds__(32 * kCoopWarps, ICPB_COOP_MINB) nn_grid_coop_
             }
             const int total = __shfl_sync(full, incl, 31);
             const int excl = incl - cnt;
+#ifdef ICPB_COOP_CLOCKS
+            dbg_cells += total;
+#endif
             const int rowbase_l = (zz * ny + yy) * nx + bx0;
             for (int cb = 0; cb < total; cb += 32) {
                 const int ci = cb + lane;
@@ -1197,6 +1228,25 @@ __global__ void __launch_bounds__(32 * kCoopWarps, ICPB_COOP_MINB) nn_grid_coop_
             else rad = (best.d < CUDART_INF_F) ? best.d : 4.f * rad;
         }
     }
+#ifdef ICPB_COOP_CLOCKS
+    {
+        const long long dt = clock64() - clk0;
+        if (lane == 0 && pass == 5 && k / 32 < 16384) {
+            int *o = g_coop_dbg + 8 * (k / 32);
+            o[0] = (int)dt; o[1] = dbg_rounds; o[2] = dbg_rows; o[3] = dbg_cells; o[4] = dbg_box; o[5] = (int)staged;
+            unsigned long long gt1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+            o[6] = (int)(gt0 & 0x7fffffff); o[7] = (int)__smid() | ((int)((gt1 - gt0) & 0xfffff) << 8);
+        }
+    }
+#endif
+    if (d.gord && lane == 0) {
+        // this warp's class for the next pass (0 = heaviest), by the time it took: candidates staged AND cells visited
+        // (a warp across a jump of the Morton curve stages little and tests thousands of rows)
+        const long long c = clock64() - ord_clk0;
+        const int b = c >= 131072 ? 0 : c >= 98304 ? 1 : c >= 73728 ? 2 : c >= 57344 ? 3 : c >= 45056 ? 4 : c >= 34816 ? 5 : c >= 24576 ? 6 : 7;
+        const int slot = atomicAdd(&d.gord_count[pass * kOrderBins + b], 1);
+        d.gord[((pass & 1) * kOrderBins + b) * ord_stride + slot] = wsel;
+    }
     if (d.gpairs && lane == 0 && staged) atomicAdd(d.gpairs, staged * 32ull);
     if (!valid) return;
     if (!done) deferred = true; // round limit (not reachable with radii that quadruple up to the acceptance radius)
@@ -1215,6 +1265,21 @@ __global__ void __launch_bounds__(32 * kCoopWarps, ICPB_COOP_MINB) nn_grid_coop_
     d.gseed[k] = accepted ? rec : make_float4(0.f, 0.f, 0.f, __int_as_float(beyond_reach(g, p) ? -1 : -2));
 }
 
+__global__ void __launch_bounds__(32 * kCoopWarps, ICPB_COOP_MINB) nn_grid_coop_kernel(const RegDesc *__restrict__ descs, int pass, float coop_r)
+{
+    pdl_enter(); // icpb_internal.h: the grid before this one is complete from here on
+    const RegDesc &d = descs[blockIdx.z];
+    IcpState *st = d.st;
+    if (st->done) return;
+    __shared__ __align__(16) CoopBuf s_buf[kCoopWarps];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // one work item (32 sorted query slots) per warp.  Resident warps drawing items from a counter instead measured
+    // slower (154 against 141 us per pass at full resolution): the relaunch of CTAs is not what the SMs wait for, and
+    // the counter adds one more round trip to every item's chain of dependent loads.
+    const int wpos = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wpos < ((d.n + 31) >> 5)) coop_warp(d, st, s_buf[wid], pass, coop_r, wpos, lane);
+}
+
 void launch_nn_grid(const RegDesc *descs, int batch, int max_n, int pass, int sm_count, cudaStream_t s, float coop_r)
 {
     dim3 hgrid(sm_count * 8, 1, batch);
@@ -1231,3 +1296,10 @@ void launch_nn_grid(const RegDesc *descs, int batch, int max_n, int pass, int sm
 }
 
 } // namespace icpb
+
+#ifdef ICPB_COOP_CLOCKS
+extern "C" int icpb_debug_coop_clocks(int *out, int n_ints)
+{
+    return (int)cudaMemcpyFromSymbol(out, icpb::g_coop_dbg, sizeof(int) * (size_t)n_ints);
+}
+#endif

@@ -129,7 +129,13 @@ struct RegDesc {
     unsigned long long *gpairs; // profiling mode: (query, candidate) pairs the cooperative search put through its filter
     int *gheavy;             // [n] queries still open after the per-thread shells
     int *gheavy_count;       // [passes] length of that list per pass (zeroed once per registration)
+    // cooperative search, work order: the warps of pass p are launched heaviest first, by the number of candidates they
+    // staged in pass p-1 (kOrderBins classes).  gord: [2][kOrderBins][n_stride/32] warp numbers (ping-pong by pass),
+    // gord_count: [passes][kOrderBins] class sizes (zeroed once per registration).  Null: natural order.
+    int *gord;
+    int *gord_count;
 };
+constexpr int kOrderBins = 8;
 
 // ---- launchers (defined in the .cu files) ---------------------------------
 void launch_target_prep(const float4 *tgt, int m, float *soa, int ngroups, cudaStream_t s);
