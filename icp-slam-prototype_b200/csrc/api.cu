@@ -18,7 +18,7 @@ thread_local std::string g_create_error;
 enum WsId {
     WS_DESCS = 0, WS_STATES, WS_PARAMS, WS_TGT_SOA, WS_PM1, WS_PM2, WS_PG, WS_IDX, WS_DIST, WS_CHUNKS, WS_ALT,
     WS_IDX_TRACE, WS_DIST_TRACE, WS_MISC, WS_DEPTH, WS_BGR, WS_KEEP, WS_TILESTATE, WS_IMG_A, WS_IMG_B, WS_NORMALS,
-    WS_RT, WS_GRID_META, WS_GRID_COUNTS, WS_GRID_CURSOR, WS_GRID_SUMS, WS_GRID_SORTED, WS_GRID_BBOX, WS_GRID_HEAVY, WS_BATCHSTATE, WS_TRACK, WS_PA, WS_PM3, WS_PG2, WS_MLOG, WS_REJ_FLAG, WS_REJ_PTS, WS_FRAME, WS_PERM, WS_SORT_COUNTS, WS_SORT_SUMS, WS_GRID_NB, WS_GRID_SEED, WS_GRID_BOX, WS_GRID_BOXC, WS_GRID_ORD, WS_GRID_ORDCNT, WS_COUNT
+    WS_RT, WS_GRID_META, WS_GRID_COUNTS, WS_GRID_CURSOR, WS_GRID_SUMS, WS_GRID_SORTED, WS_GRID_BBOX, WS_GRID_HEAVY, WS_BATCHSTATE, WS_TRACK, WS_PA, WS_PM3, WS_PG2, WS_MLOG, WS_REJ_FLAG, WS_REJ_PTS, WS_FRAME, WS_PERM, WS_SORT_COUNTS, WS_SORT_SUMS, WS_GRID_NB, WS_GRID_SEED, WS_GRID_BOX, WS_GRID_BOXC, WS_GRID_ORD, WS_GRID_ORDCNT, WS_GRID_Q, WS_COUNT
 };
 
 int fail(icpb_ctx *ctx, int status, const char *what, cudaError_t ce = cudaSuccess)
@@ -267,6 +267,7 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
     int *d_gheavy = nullptr;
     float4 *d_gnb = nullptr, *d_gseed = nullptr, *d_gbox = nullptr, *d_gboxc = nullptr;
     int *d_gord = nullptr, *d_gordcnt = nullptr;
+    float4 *d_gq = nullptr;
     // Work order of the cooperative search (grid.cu): heaviest warps first from the second pass on, when the pass is more
     // than one wave of warps deep (full resolution: 3.78 -> 3.50 ms; a single 10k-point cloud is a tenth of a wave and
     // only pays the two extra loads).  ICPB_GRID_ORDER=0 / 1 forces natural order / ordering.
@@ -366,8 +367,9 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         if ((rc = ws_get(ctx, WS_GRID_BOX, sizeof(float4) * 2 * total_entries, (void **)&d_gbox))) return rc;
         if (any_children && (rc = ws_get(ctx, WS_GRID_BOXC, sizeof(float4) * 2 * total_coarse, (void **)&d_gboxc))) return rc;
         if ((rc = ws_get(ctx, WS_GRID_SEED, sizeof(float4) * (tot_n + 32), (void **)&d_gseed))) return rc;
+        if (coop_mode && (rc = ws_get(ctx, WS_GRID_Q, sizeof(float4) * (tot_n + 32), (void **)&d_gq))) return rc;
         if (grid_ordered) {
-            if ((rc = ws_get(ctx, WS_GRID_ORD, sizeof(int) * 2 * kOrderBins * (tot_n / 32), (void **)&d_gord))) return rc;
+            if ((rc = ws_get(ctx, WS_GRID_ORD, sizeof(int) * (2 * kOrderBins + 1) * (tot_n / 32), (void **)&d_gord))) return rc;
             if ((rc = ws_get(ctx, WS_GRID_ORDCNT, sizeof(int) * (size_t)count * passes * kOrderBins, (void **)&d_gordcnt))) return rc;
         }
         grid_launches = 8 + (any_children ? 1 : 0);
@@ -421,16 +423,18 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
             d.gboxc = d_gboxc ? d_gboxc + 2 * coarse_before : nullptr;
             d.gnb = d_gnb + off_n;
             d.gseed = d_gseed + off_n;
+            d.gq = d_gq ? d_gq + off_n : nullptr;
             // pair counter (profiling mode): the eight bytes behind the scan's block sums, 8-byte aligned
             d.gpairs = ctx->profiling ? (unsigned long long *)(d_gsums + ((total_entries / 4096 + 8 + 1) & ~(size_t)1)) : nullptr;
             d.gheavy_count = d_gheavy + (size_t)b * (passes + 8);
             d.gheavy = d_gheavy + (size_t)count * (passes + 8) + off_n;
             d.gord = d_gord ? d_gord + 2 * kOrderBins * (off_n / 32) : nullptr;
+            d.gord_flat = d_gord ? d_gord + 2 * kOrderBins * (tot_n / 32) + off_n / 32 : nullptr;
             d.gord_count = d_gordcnt ? d_gordcnt + (size_t)b * passes * kOrderBins : nullptr;
         } else {
             d.grid = nullptr; d.gsorted = nullptr; d.gstart = nullptr; d.gcursor = nullptr; d.gbox = nullptr; d.gboxc = nullptr;
-            d.gnb = nullptr; d.gseed = nullptr; d.gheavy = nullptr; d.gheavy_count = nullptr; d.gpairs = nullptr;
-            d.gord = nullptr; d.gord_count = nullptr;
+            d.gnb = nullptr; d.gseed = nullptr; d.gq = nullptr; d.gheavy = nullptr; d.gheavy_count = nullptr; d.gpairs = nullptr;
+            d.gord = nullptr; d.gord_count = nullptr; d.gord_flat = nullptr;
         }
         d.carry = (kp_mode && regs[b].carry) ? regs[b].carry->d_pts : nullptr;
         d.n_carry = (kp_mode && regs[b].carry) ? regs[b].carry->n : 0;

@@ -911,17 +911,7 @@ __device__ __forceinline__ void coop_warp(const RegDesc &d, IcpState *st, CoopBu
     //      resident; tools/coop_clocks.py).  Classes by the cycles the warp took in the previous pass.
     const int ord_stride = d.n_stride >> 5;
     int wsel = wpos;
-    if (d.gord && pass > 0) {
-        const int *cnt = d.gord_count + (pass - 1) * kOrderBins;
-        const int *lists = d.gord + ((pass - 1) & 1) * kOrderBins * ord_stride;
-        int before = 0;
-#pragma unroll
-        for (int b = 0; b < kOrderBins; ++b) {
-            const int c = __ldcg(&cnt[b]);
-            if (wpos >= before && wpos < before + c) wsel = __ldcg(&lists[b * ord_stride + (wpos - before)]);
-            before += c;
-        }
-    }
+    if (d.gord && pass > 0) wsel = __ldcg(&d.gord_flat[wpos]); // written by nn_finalize_coop_kernel from last pass's classes
     const long long ord_clk0 = clock64();
     const int k = wsel * 32 + lane;
     const bool valid = k < n;
@@ -936,7 +926,9 @@ __device__ __forceinline__ void coop_warp(const RegDesc &d, IcpState *st, CoopBu
     // P2 fused into the query load (pointcloud.cpp:321-359), as in nn_grid_kernel
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) {
-        p = d.D[pass & 1][i];
+        // after the first pass the query comes from gq, the copy of the cloud in SORTED slot order this kernel keeps
+        // up to date: a coalesced read that does not wait for perm[k]
+        p = (d.gq && pass > 0) ? d.gq[k] : d.D[pass & 1][i];
         if (st->apply) {
             const float *R = st->Rf, *T = st->tf;
             const float x = ((R[0] * p.x + R[1] * p.y) + R[2] * p.z) + T[0];
@@ -945,6 +937,7 @@ __device__ __forceinline__ void coop_warp(const RegDesc &d, IcpState *st, CoopBu
             p.x = x; p.y = y; p.z = z;
         }
         d.D[(pass + 1) & 1][i] = p;
+        if (d.gq) d.gq[k] = p;
     }
 
     // ---- the lane's ball: seeded by the previous pass's neighbour (kept per SORTED slot: a coalesced read, and the
@@ -1123,8 +1116,10 @@ __device__ __forceinline__ void coop_warp(const RegDesc &d, IcpState *st, CoopBu
                     cell = r_base + (ci - r_excl);
                     t0 = __ldg(&gstart[cell * g.sub]);
                     len = __ldg(&gstart[(cell + 1) * g.sub]) - t0;
+                    // unconditionally: an empty cell's box is inverted and reaches nothing, and the loads leave together
+                    // with the two above instead of one round trip later
                     const float4 *bx = g.sub == 8 ? gboxc : gbox;
-                    if (len > 0) { blo = __ldg(&bx[2 * (size_t)cell]); bhi = __ldg(&bx[2 * (size_t)cell + 1]); }
+                    blo = __ldg(&bx[2 * (size_t)cell]); bhi = __ldg(&bx[2 * (size_t)cell + 1]);
                 }
                 const bool need = reaches(blo.x, blo.y, blo.z, bhi.x, bhi.y, bhi.z) && len > 0;
                 // stage: the runs of the lanes that hold a needed cell (my_pos, my_len; 0 = none), FLATTENED over the warp
@@ -1189,7 +1184,7 @@ __device__ __forceinline__ void coop_warp(const RegDesc &d, IcpState *st, CoopBu
                             const int fine = pcell * 8 + (ki & 7);
                             k0 = __ldg(&gstart[fine]);
                             klen = __ldg(&gstart[fine + 1]) - k0;
-                            if (klen > 0) { klo = __ldg(&gbox[2 * (size_t)fine]); khi = __ldg(&gbox[2 * (size_t)fine + 1]); }
+                            klo = __ldg(&gbox[2 * (size_t)fine]); khi = __ldg(&gbox[2 * (size_t)fine + 1]);
                         }
                         const bool kneed = reaches(klo.x, klo.y, klo.z, khi.x, khi.y, khi.z) && klen > 0;
                         if (__any_sync(full, kneed)) stage_runs(k0, kneed ? klen : 0);

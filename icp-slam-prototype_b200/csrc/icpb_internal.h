@@ -126,6 +126,7 @@ struct RegDesc {
     const float4 *gboxc;     // [2 * ncells] the same per coarse cell (sub == 8)
     float4 *gnb;             // [n] cooperative search: the nearest target's coordinates, w = its distance (original query order)
     float4 *gseed;           // [n] the same in SORTED slot order, w = its index bits: the next pass's search ball
+    float4 *gq;              // [n] the data cloud as of the last pass, in SORTED slot order (cooperative search only)
     unsigned long long *gpairs; // profiling mode: (query, candidate) pairs the cooperative search put through its filter
     int *gheavy;             // [n] queries still open after the per-thread shells
     int *gheavy_count;       // [passes] length of that list per pass (zeroed once per registration)
@@ -134,6 +135,7 @@ struct RegDesc {
     // gord_count: [passes][kOrderBins] class sizes (zeroed once per registration).  Null: natural order.
     int *gord;
     int *gord_count;
+    int *gord_flat;          // [n_stride/32] the classes of the last pass concatenated, heaviest first (nn_finalize_coop_kernel)
 };
 constexpr int kOrderBins = 8;
 

@@ -1418,6 +1418,24 @@ __global__ void __launch_bounds__(kChunk, 5) nn_finalize_coop_kernel(const RegDe
     const RegDesc &d = descs[blockIdx.z];
     const int n = q_cur ? q_n : d.n;
     if (chunk * kChunk >= n) return;
+    if (d.gord) {
+        // work order of the next pass's search (grid.cu): this pass's cost classes, heaviest first, as one flat list --
+        // one entry per thread of the first CTAs, its two round trips under the loads above
+        const int e = chunk * kChunk + (int)threadIdx.x;
+        if (e < ((n + 31) >> 5)) {
+            const int stride = d.n_stride >> 5;
+            const int *cnt = d.gord_count + pass * kOrderBins;
+            const int *lists = d.gord + (pass & 1) * kOrderBins * stride;
+            int before = 0, src = -1;
+#pragma unroll
+            for (int b = 0; b < kOrderBins; ++b) {
+                const int c = __ldcg(&cnt[b]);
+                if (e >= before && e < before + c) src = b * stride + (e - before);
+                before += c;
+            }
+            if (src >= 0) d.gord_flat[e] = __ldcg(&lists[src]);
+        }
+    }
     const int nchunks = (n + kChunk - 1) / kChunk;
     const int tid = threadIdx.x;
     const int i = chunk * kChunk + tid;
