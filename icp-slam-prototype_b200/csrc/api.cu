@@ -512,7 +512,7 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
         if (prof) CU(ctx, cudaEventRecord(ctx->prof_events[2 * pass], st));
         if (grid_mode) {
             const int sp = span_begin(ctx, ICPB_PROF_NN_GRID);
-            launch_nn_grid(d_descs, count, max_n, pass, ctx->sm_count, st, coop_r);
+            launch_nn_grid(d_descs, d_states, d_gmeta, count, max_n, pass, ctx->sm_count, st, coop_r, &h_descs[0], &gms[0]);
             span_end(ctx, sp);
         } else launch_nn_partial(d_descs, d_states, count, max_n, qpt, splits, pass, filter, st);
         if (prof) CU(ctx, cudaEventRecord(ctx->prof_events[2 * pass + 1], st));

@@ -900,8 +900,13 @@ __device__ __forceinline__ void coop_batch(const CoopBuf &b, int fill, const flo
 }
 
 // One warp's share of a pass: the 32 queries of work item `wpos`.
-__device__ __forceinline__ void coop_warp(const RegDesc &d, IcpState *st, CoopBuf &buf, const int pass, const float coop_r,
-                                          const int wpos, const int lane)
+struct CoopMotion { // the head of IcpState (one cache line), read together with the done flag
+    float R[9], T[3];
+    int apply;
+};
+
+__device__ __forceinline__ void coop_warp(const RegDesc &d, const GridMeta &g, const CoopMotion &mo, CoopBuf &buf, const int pass,
+                                          const float coop_r, const int wsel, const int lane)
 {
     const int n = d.n;
     // ---- which 32 sorted slots this warp takes.  From the second pass on the warps are handed out heaviest first:
@@ -910,14 +915,11 @@ __device__ __forceinline__ void coop_warp(const RegDesc &d, IcpState *st, CoopBu
     //      %globaltimer per warp: in natural order the last 28 % of the kernel's duration had < 4 of 20 warps per SM
     //      resident; tools/coop_clocks.py).  Classes by the cycles the warp took in the previous pass.
     const int ord_stride = d.n_stride >> 5;
-    int wsel = wpos;
-    if (d.gord && pass > 0) wsel = __ldcg(&d.gord_flat[wpos]); // written by nn_finalize_coop_kernel from last pass's classes
     const long long ord_clk0 = clock64();
     const int k = wsel * 32 + lane;
     const bool valid = k < n;
     const int *perm = d.perm;
     const int i = valid ? (perm ? perm[k] : k) : 0;
-    const GridMeta g = *d.grid;
     const float4 *__restrict__ sorted = d.gsorted;
     const int *__restrict__ gstart = d.gstart;
     const float4 *__restrict__ gbox = d.gbox;
@@ -929,8 +931,8 @@ __device__ __forceinline__ void coop_warp(const RegDesc &d, IcpState *st, CoopBu
         // after the first pass the query comes from gq, the copy of the cloud in SORTED slot order this kernel keeps
         // up to date: a coalesced read that does not wait for perm[k]
         p = (d.gq && pass > 0) ? d.gq[k] : d.D[pass & 1][i];
-        if (st->apply) {
-            const float *R = st->Rf, *T = st->tf;
+        if (mo.apply) {
+            const float *R = mo.R, *T = mo.T;
             const float x = ((R[0] * p.x + R[1] * p.y) + R[2] * p.z) + T[0];
             const float y = ((R[3] * p.x + R[4] * p.y) + R[5] * p.z) + T[1];
             const float z = ((R[6] * p.x + R[7] * p.y) + R[8] * p.z) + T[2];
@@ -1260,28 +1262,56 @@ __device__ __forceinline__ void coop_warp(const RegDesc &d, IcpState *st, CoopBu
     d.gseed[k] = accepted ? rec : make_float4(0.f, 0.f, 0.f, __int_as_float(beyond_reach(g, p) ? -1 : -2));
 }
 
-__global__ void __launch_bounds__(32 * kCoopWarps, ICPB_COOP_MINB) nn_grid_coop_kernel(const RegDesc *__restrict__ descs, int pass, float coop_r)
+// kSingle: one registration -- its descriptor and cell geometry arrive BY VALUE as kernel parameters (constant bank) and
+// the loop state is addressed from an argument, so a warp's first useful load (its work item, its queries) does not wait
+// behind a chain of pointer loads (descriptor -> state, descriptor -> geometry): two round trips of ~8 per work item.
+template <bool kSingle>
+__global__ void __launch_bounds__(32 * kCoopWarps, ICPB_COOP_MINB) nn_grid_coop_kernel(const RegDesc *__restrict__ descs, const IcpState *states,
+                                                                                     const GridMeta *__restrict__ gmetas, int pass, float coop_r,
+                                                                                     const RegDesc d1, const GridMeta g1)
 {
     pdl_enter(); // icpb_internal.h: the grid before this one is complete from here on
-    const RegDesc &d = descs[blockIdx.z];
-    IcpState *st = d.st;
-    if (st->done) return;
-    __shared__ __align__(16) CoopBuf s_buf[kCoopWarps];
+    const IcpState *st = states + blockIdx.z; // == d.st
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     // one work item (32 sorted query slots) per warp.  Resident warps drawing items from a counter instead measured
     // slower (154 against 141 us per pass at full resolution): the relaunch of CTAs is not what the SMs wait for, and
     // the counter adds one more round trip to every item's chain of dependent loads.
     const int wpos = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (wpos < ((d.n + 31) >> 5)) coop_warp(d, st, s_buf[wid], pass, coop_r, wpos, lane);
+    // everything the first round trip can fetch goes out together: the motion and the flags (one line of the state)
+    // and, where the descriptor is a parameter, the work item
+    int wsel = wpos;
+    if (kSingle && d1.gord && pass > 0 && wpos < ((d1.n + 31) >> 5)) wsel = __ldcg(&d1.gord_flat[wpos]);
+    CoopMotion mo;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) mo.R[k] = st->Rf[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) mo.T[k] = st->tf[k];
+    mo.apply = st->apply;
+    if (st->done) return;
+    __shared__ __align__(16) CoopBuf s_buf[kCoopWarps];
+    if (kSingle) {
+        if (wpos < ((d1.n + 31) >> 5)) coop_warp(d1, g1, mo, s_buf[wid], pass, coop_r, wsel, lane);
+    } else {
+        const RegDesc &d = descs[blockIdx.z];
+        if (wpos < ((d.n + 31) >> 5)) {
+            if (d.gord && pass > 0) wsel = __ldcg(&d.gord_flat[wpos]); // written by nn_finalize_coop_kernel from last pass's classes
+            const GridMeta g = gmetas[blockIdx.z]; // == *d.grid, addressed from the argument
+            coop_warp(d, g, mo, s_buf[wid], pass, coop_r, wsel, lane);
+        }
+    }
 }
 
-void launch_nn_grid(const RegDesc *descs, int batch, int max_n, int pass, int sm_count, cudaStream_t s, float coop_r)
+void launch_nn_grid(const RegDesc *descs, const IcpState *states, const GridMeta *gmetas, int batch, int max_n, int pass,
+                    int sm_count, cudaStream_t s, float coop_r, const RegDesc *h_desc0, const GridMeta *h_grid0)
 {
     dim3 hgrid(sm_count * 8, 1, batch);
     if (coop_r > 0.f) {
         hgrid.x = sm_count * 2; // a handful of queries at most reach the fall-back (it strides over its list) // warp-cooperative search (default), open queries finished from shell 0
         dim3 grid((max_n + 32 * kCoopWarps - 1) / (32 * kCoopWarps), 1, batch);
-        launch_pdl(nn_grid_coop_kernel, grid, dim3(32 * kCoopWarps), 0, s, descs, pass, coop_r);
+        if (batch == 1 && h_desc0 && h_grid0)
+            launch_pdl(nn_grid_coop_kernel<true>, grid, dim3(32 * kCoopWarps), 0, s, descs, states, gmetas, pass, coop_r, *h_desc0, *h_grid0);
+        else
+            launch_pdl(nn_grid_coop_kernel<false>, grid, dim3(32 * kCoopWarps), 0, s, descs, states, gmetas, pass, coop_r, RegDesc{}, GridMeta{});
         launch_pdl(nn_grid_heavy_kernel, hgrid, dim3(128), 0, s, descs, pass, 0);
         return;
     }

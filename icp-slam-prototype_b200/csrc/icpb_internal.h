@@ -174,7 +174,8 @@ void launch_grid_build_batch(const RegDesc *descs, int batch, int max_m, int max
 void launch_grid_build(const float4 *tgt, int m, const GridMeta &g, int *counts, int *cursor, int *block_sums,
                        float4 *sorted, float4 *boxes, float4 *coarse_boxes, cudaStream_t s);
 // coop_r > 0: warp-cooperative search for balls up to coop_r metres (grid.cu); 0: the per-thread shell walk
-void launch_nn_grid(const RegDesc *descs, int batch, int max_n, int pass, int sm_count, cudaStream_t s, float coop_r);
+void launch_nn_grid(const RegDesc *descs, const IcpState *states, const GridMeta *gmetas, int batch, int max_n, int pass,
+                    int sm_count, cudaStream_t s, float coop_r, const RegDesc *h_desc0 = nullptr, const GridMeta *h_grid0 = nullptr);
 size_t spatial_sort_work_ints(int max_n, int batch); // ints of scratch launch_spatial_sort needs
 void launch_spatial_sort(const RegDesc *descs, int batch, int max_n, int *work, cudaStream_t s); // 15 launches
 
