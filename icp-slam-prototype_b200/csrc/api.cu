@@ -463,12 +463,14 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
     CU(ctx, cudaMemcpyAsync(d_prm, h_prm, sizeof(IcpParamsDev), cudaMemcpyHostToDevice, st));
 
     // programmatic dependent launch for the kernels of the pass loop (icpb_internal.h).  Measured: -7 % on a 10k-point
-    // registration (brute force), -9 % with the cell-grid search; +3 % on the full-resolution pair, where the
-    // successors' CTAs take residency from a search kernel that runs three waves deep -- so: small jobs only.
-    // ICPB_PDL=0 / 1 forces it off / on.
+    // registration (brute force), -9 % with the cell-grid search; +3 % on the full-resolution pair when every kernel
+    // takes part, because the successor's CTAs take residency from a search kernel that runs three waves deep.  So:
+    // level 2 (every launch) for small jobs, level 1 for large ones -- only the launches whose predecessor is small
+    // (sums after the fall-back, solve after the sums, the next search after the one-CTA solve).
+    // ICPB_PDL=0 / 1 forces none / all.
     {
         const int knob = env_int("ICPB_PDL", 2);
-        pdl_set(knob == 1 || (knob == 2 && tot_n <= 65536));
+        pdl_set(knob == 0 ? 0 : (knob == 1 || tot_n <= 65536) ? 2 : 1);
     }
     long long launches = 0;
     CU(ctx, cudaEventRecord(ctx->ev0, st));
@@ -628,9 +630,9 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
 
 namespace icpb {
 // per calling thread: run_registrations decides per call (the launches happen on the caller's thread)
-static thread_local bool tl_pdl = false;
-bool pdl_enabled() { return tl_pdl; }
-void pdl_set(bool on) { tl_pdl = on; }
+static thread_local int tl_pdl = 0;
+int pdl_level() { return tl_pdl; }
+void pdl_set(int level) { tl_pdl = level; }
 
 int api_fail(icpb_ctx *ctx, int status, const char *what, cudaError_t ce) { return fail(ctx, status, what, ce); }
 

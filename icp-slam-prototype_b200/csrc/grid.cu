@@ -1312,12 +1312,12 @@ void launch_nn_grid(const RegDesc *descs, const IcpState *states, const GridMeta
             launch_pdl(nn_grid_coop_kernel<true>, grid, dim3(32 * kCoopWarps), 0, s, descs, states, gmetas, pass, coop_r, *h_desc0, *h_grid0);
         else
             launch_pdl(nn_grid_coop_kernel<false>, grid, dim3(32 * kCoopWarps), 0, s, descs, states, gmetas, pass, coop_r, RegDesc{}, GridMeta{});
-        launch_pdl(nn_grid_heavy_kernel, hgrid, dim3(128), 0, s, descs, pass, 0);
+        launch_pdl<true>(nn_grid_heavy_kernel, hgrid, dim3(128), 0, s, descs, pass, 0);
         return;
     }
     dim3 grid((max_n + 127) / 128, 1, batch);
-    launch_pdl(nn_grid_kernel, grid, dim3(128), 0, s, descs, pass);
-    launch_pdl(nn_grid_heavy_kernel, hgrid, dim3(128), 0, s, descs, pass, -1);
+    launch_pdl<true>(nn_grid_kernel, grid, dim3(128), 0, s, descs, pass);
+    launch_pdl<true>(nn_grid_heavy_kernel, hgrid, dim3(128), 0, s, descs, pass, -1);
 }
 
 } // namespace icpb

@@ -259,7 +259,8 @@ extern unsigned int *const kCounterIsZero; // pass as layer_work: next_ray is al
 // let the grid after it be scheduled (griddepcontrol.launch_dependents: it fires once the LAST CTA of this grid is
 // resident, so the successor's CTAs fill the SMs as this grid's tail drains and sit in their own wait).  Because the
 // trigger comes after the wait, a grid never becomes resident before its grandparent has finished.
-// Decided per call by run_registrations (api.cu): small jobs only; ICPB_PDL=0 / 1 forces it off / on.  Launched
+// Decided per call by run_registrations (api.cu): all launches for small jobs, the ones behind a small grid for large
+// jobs; ICPB_PDL=0 / 1 forces none / all.  Launched
 // without the attribute the same kernels are fully serialised and the two instructions are no-ops.
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_enter()
@@ -268,9 +269,10 @@ __device__ __forceinline__ void pdl_enter()
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 #endif
-bool pdl_enabled();
-void pdl_set(bool on);
-template <typename... KArgs, typename... Args>
+int pdl_level();          // 0: no launch takes part, 1: those whose predecessor grid is small, 2: all
+void pdl_set(int level);
+// after_big: the grid launched before this one fills the GPU several waves deep (level 1 leaves such launches serialised)
+template <bool after_big = false, typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args)
 {
     cudaLaunchConfig_t cfg = {};
@@ -280,7 +282,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    attr[0].val.programmaticStreamSerializationAllowed = (pdl_level() >= (after_big ? 2 : 1)) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);

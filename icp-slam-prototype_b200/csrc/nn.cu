@@ -687,13 +687,13 @@ __global__ void __launch_bounds__(kNnThreads, (QPT >= 16 ? 2 : QPT >= 12 ? 3 : 4
 template <int QPT>
 static void launch_warp(dim3 grid, const RegDesc *descs, IcpState *states, int splits, int pass, cudaStream_t s)
 {
-    launch_pdl(nn_partial_warp_kernel<QPT>, grid, dim3(kNnThreads), 0, s, descs, states, splits, pass);
+    launch_pdl<true>(nn_partial_warp_kernel<QPT>, grid, dim3(kNnThreads), 0, s, descs, states, splits, pass);
 }
 
 template <int QPT>
 static void launch_centred(dim3 grid, const RegDesc *descs, IcpState *states, int splits, int pass, cudaStream_t s)
 {
-    launch_pdl(nn_partial_centred_kernel<QPT>, grid, dim3(kNnThreads), 0, s, descs, states, splits, pass);
+    launch_pdl<true>(nn_partial_centred_kernel<QPT>, grid, dim3(kNnThreads), 0, s, descs, states, splits, pass);
 }
 
 void launch_nn_partial(const RegDesc *descs, IcpState *states, int batch, int max_n, int qpt, int splits, int pass,
@@ -719,9 +719,9 @@ void launch_nn_partial(const RegDesc *descs, IcpState *states, int batch, int ma
         }
     } else {
         switch (qpt) {
-        case 8: launch_pdl(nn_partial_kernel<8>, grid, block, 0, s, descs, states, splits, pass); break;
-        case 4: launch_pdl(nn_partial_kernel<4>, grid, block, 0, s, descs, states, splits, pass); break;
-        default: launch_pdl(nn_partial_kernel<2>, grid, block, 0, s, descs, states, splits, pass); break;
+        case 8: launch_pdl<true>(nn_partial_kernel<8>, grid, block, 0, s, descs, states, splits, pass); break;
+        case 4: launch_pdl<true>(nn_partial_kernel<4>, grid, block, 0, s, descs, states, splits, pass); break;
+        default: launch_pdl<true>(nn_partial_kernel<2>, grid, block, 0, s, descs, states, splits, pass); break;
         }
     }
 }
@@ -1486,7 +1486,7 @@ void launch_nn_finalize(const RegDesc *descs, IcpState *states, const IcpParamsD
     // threads per query for the group selection and the exact stage.  Many CTAs (full resolution, batches) are
     // throughput-bound and keep one thread per query (measured: pairs -6 % on the 1024-registration batch).
     const bool paired = splits > 0 && (long long)grid.x * batch <= 2 * 148;
-    launch_pdl(nn_finalize_kernel, grid, dim3(paired ? 2 * kChunk : kChunk), 0, s, descs, states, prm, splits, pass, filter);
+    launch_pdl<true>(nn_finalize_kernel, grid, dim3(paired ? 2 * kChunk : kChunk), 0, s, descs, states, prm, splits, pass, filter);
 }
 
 // --------------------------------------------------------------------------
