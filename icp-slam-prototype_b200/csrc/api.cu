@@ -474,27 +474,45 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
     }
     long long launches = 0;
     CU(ctx, cudaEventRecord(ctx->ev0, st));
-    if ((filter == kFilterWarp && !grid_mode) || (grid_mode && grid_sorted)) {
-        // Morton order of every data cloud, once per registration (inside the timed region)
-        int *d_swork;
-        if ((rc = ws_get(ctx, WS_SORT_COUNTS, sizeof(int) * spatial_sort_work_ints(max_n, count), (void **)&d_swork))) return rc;
-        launch_spatial_sort(d_descs, count, max_n, d_swork, st);
-        launches += 15;
-    }
+    const bool sorted_queries = (filter == kFilterWarp && !grid_mode) || (grid_mode && grid_sorted);
+    int *d_swork = nullptr;
+    if (sorted_queries &&
+        (rc = ws_get(ctx, WS_SORT_COUNTS, sizeof(int) * spatial_sort_work_ints(max_n, count), (void **)&d_swork))) return rc;
     if (grid_mode) {
+        // The cells of the targets and the Morton order of the queries have nothing to do with each other and are two
+        // dozen short launches each: the cell build runs on the context's side stream while the sort runs on the main
+        // one (fork / join by events; ICPB_GRID_FORK=0: one after the other).
+        const bool fork = sorted_queries && env_int("ICPB_GRID_FORK", 1) != 0;
+        cudaStream_t sb = fork ? ctx->stream2 : st;
+        if (fork) {
+            CU(ctx, cudaEventRecord(ctx->ev_fork, st));
+            CU(ctx, cudaStreamWaitEvent(sb, ctx->ev_fork, 0));
+        } else if (sorted_queries) {
+            launch_spatial_sort(d_descs, count, max_n, d_swork, st);
+        }
         // the metas ride in pinned memory behind the descriptors' block (the call returns only after the stream is done)
         GridMeta *h_gm = (GridMeta *)hp_metas;
         for (int b = 0; b < count; ++b) h_gm[b] = gms[(size_t)b];
-        CU(ctx, cudaMemcpyAsync(d_gmeta, h_gm, sizeof(GridMeta) * (size_t)count, cudaMemcpyHostToDevice, st));
-        CU(ctx, cudaMemsetAsync(d_gcounts, 0, sizeof(int) * total_entries, st));
-        CU(ctx, cudaMemsetAsync(d_gheavy, 0, sizeof(int) * (size_t)count * ((size_t)passes + 8), st));
-        if (d_gordcnt) CU(ctx, cudaMemsetAsync(d_gordcnt, 0, sizeof(int) * (size_t)count * passes * kOrderBins, st));
+        CU(ctx, cudaMemcpyAsync(d_gmeta, h_gm, sizeof(GridMeta) * (size_t)count, cudaMemcpyHostToDevice, sb));
+        CU(ctx, cudaMemsetAsync(d_gcounts, 0, sizeof(int) * total_entries, sb));
+        CU(ctx, cudaMemsetAsync(d_gheavy, 0, sizeof(int) * (size_t)count * ((size_t)passes + 8), sb));
+        if (d_gordcnt) CU(ctx, cudaMemsetAsync(d_gordcnt, 0, sizeof(int) * (size_t)count * passes * kOrderBins, sb));
         launch_grid_build_batch(d_descs, count, max_m, max_ncells, d_gcounts, d_gcursor, (long long)total_entries, d_gsums,
-                                d_gsorted, d_gbox, any_children, st);
+                                d_gsorted, d_gbox, any_children, sb);
         if (ctx->profiling) // after the scans are done with the block sums
-            CU(ctx, cudaMemsetAsync(d_gsums + ((total_entries / 4096 + 8 + 1) & ~(size_t)1), 0, sizeof(unsigned long long), st));
+            CU(ctx, cudaMemsetAsync(d_gsums + ((total_entries / 4096 + 8 + 1) & ~(size_t)1), 0, sizeof(unsigned long long), sb));
+        if (fork) {
+            CU(ctx, cudaEventRecord(ctx->ev_join, sb));
+            launch_spatial_sort(d_descs, count, max_n, d_swork, st);
+            CU(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+        }
+        if (sorted_queries) launches += 15;
         launches += grid_launches;
-    } else {
+    } else if (sorted_queries) {
+        launch_spatial_sort(d_descs, count, max_n, d_swork, st); // Morton order of every data cloud, once per registration
+        launches += 15;
+    }
+    if (!grid_mode) {
         for (int b = 0; b < count; ++b) {
             launch_target_prep(h_descs[b].tgt, h_descs[b].m, const_cast<float *>(h_descs[b].tgt_soa), h_descs[b].ngroups, st);
             ++launches;
@@ -738,6 +756,9 @@ static int ctx_create_common(int device, void *stream, bool own, icpb_ctx **out)
     cudaEventCreate(&ctx->evt0);
     cudaEventCreate(&ctx->evt1);
     cudaEventCreateWithFlags(&ctx->ev_reg_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
     *out = ctx;
     return ICPB_OK;
 }
@@ -760,6 +781,9 @@ int icpb_ctx_destroy(icpb_ctx *ctx)
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->pinned_reg) cudaFreeHost(ctx->pinned_reg);
     cudaEventDestroy(ctx->ev_reg_done);
+    cudaEventDestroy(ctx->ev_fork);
+    cudaEventDestroy(ctx->ev_join);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->evt0);

@@ -1228,7 +1228,7 @@ __device__ __forceinline__ void coop_warp(const RegDesc &d, const GridMeta &g, c
 #ifdef ICPB_COOP_CLOCKS
     {
         const long long dt = clock64() - clk0;
-        if (lane == 0 && pass == 5 && k / 32 < 16384) {
+        if (lane == 0 && pass == ICPB_COOP_CLOCKS && k / 32 < 16384) {
             int *o = g_coop_dbg + 8 * (k / 32);
             o[0] = (int)dt; o[1] = dbg_rounds; o[2] = dbg_rows; o[3] = dbg_cells; o[4] = dbg_box; o[5] = (int)staged;
             unsigned long long gt1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));

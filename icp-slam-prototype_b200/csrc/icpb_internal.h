@@ -321,6 +321,8 @@ struct icpb_ctx {
     size_t pinned_reg_bytes = 0;
     icpb_pending *inflight = nullptr; // at most one per context; drained by the next registration / wait / destroy
     cudaEvent_t ev_reg_done = nullptr;
+    cudaStream_t stream2 = nullptr; // side stream of the registration set-up (cell build beside the query sort)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;
     // profiling mode: CUDA-event spans around individual kernels other than nn_partial (icpb_ctx_profile_read)

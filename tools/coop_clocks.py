@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Per-warp durations of nn_grid_coop_kernel at pass 5 (needs the -DICPB_COOP_CLOCKS build: see tools/README.md)."""
+"""Per-warp durations of nn_grid_coop_kernel at the pass the instrumented build names (-DICPB_COOP_CLOCKS=<pass>, see
+tools/README.md)."""
 import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "icp-slam-prototype_b200", "python"))
