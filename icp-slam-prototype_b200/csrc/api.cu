@@ -345,6 +345,14 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
             // per-thread shells out to ~ICPB_GRID_LIGHT_CM (default 45 cm): typical ICP residuals resolve there;
             // the few queries still open (no overlap, far from the target) are finished by one warp each
             gm.light_r = std::max(2, (int)ceilf(0.01f * env_int("ICPB_GRID_LIGHT_CM", 45) / h));
+            // probe rounds of the cooperative search (grid.cu): ICPB_GRID_PROBE_PCT = ball radius in percent of the cell
+            // edge from which a ball is probed first; 0 = never
+            {
+                const int pp = env_int("ICPB_GRID_PROBE_PCT", 150);
+                gm.probe_r = pp > 0 ? 0.01f * (float)pp * h : 3.0e38f;
+                const int pp2 = env_int("ICPB_GRID_PROBE2_PCT", 550);
+                gm.probe_r2 = pp2 > 0 ? 0.01f * (float)pp2 * h : 3.0e38f;
+            }
             cell_off[(size_t)b] = total_entries;
             n_off[(size_t)b] = acc_n;
             m_off[(size_t)b] = tot_m;

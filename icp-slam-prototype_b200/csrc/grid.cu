@@ -948,6 +948,7 @@ __device__ __forceinline__ void coop_warp(const RegDesc &d, const GridMeta &g, c
     BestB bb = {0.f, 0.f, 0.f};
     bool done = !valid || beyond_reach(g, p);
     bool deferred = false;
+    bool loose_seed = true; // the ball's radius is not last pass's neighbour distance
     float rad = g.h;
     if (!done && pass > 0) {
         const float4 sd = d.gseed[k];
@@ -958,6 +959,7 @@ __device__ __forceinline__ void coop_warp(const RegDesc &d, const GridMeta &g, c
             best.i = j;
             bb.x = sd.x; bb.y = sd.y; bb.z = sd.z;
             rad = best.d;
+            loose_seed = false;
         } else if (j == -2) { // nothing inside the acceptance radius last time: not worth widening the warp's search for
             deferred = true; done = true;
         }
@@ -1003,12 +1005,25 @@ __device__ __forceinline__ void coop_warp(const RegDesc &d, const GridMeta &g, c
     unsigned long long gt0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
     int dbg_rounds = 0, dbg_rows = 0, dbg_cells = 0, dbg_box = 0;
 #endif
-    for (int round = 0; round < 8; ++round) {
+    // ---- probe rounds.  A ball of radius r around a query d away from the surface cuts a disc of area pi (r^2 - d^2)
+    //      out of it and every target in the disc is a candidate: harmless for the usual query a few centimetres off
+    //      the surface, ruinous for one 30 cm off whose ball was GUESSED (no seed, nothing found yet, radius
+    //      quadrupled) -- such warps staged 12 - 20 thousand candidates and ran 0.5 ms, alone, at the end of the first
+    //      pass.  When an active ball is wider than probe_r the round stages ONE target per child cell the balls
+    //      reach: samples 5 cm apart, the nearest of which lies within millimetres of the true distance
+    //      (sqrt(d^2 + s^2) - d ~ s^2 / 2d); it becomes the lane's seed and the real round that follows searches a ball
+    //      that hugs the surface.  Exactness is untouched: the last round always covers the whole final ball.
+    const float probe_r = g.probe_r;
+    bool probed = false; // the previous round was a probe: this one is real
+    for (int round = 0; round < 12; ++round) {
         // lanes whose ball outgrew the cooperative phase go to the warp-per-query kernel with their partial best
         const float rr = fminf(rad, max_reach);
         if (!done && rr > coop_r) { deferred = true; done = true; }
         const unsigned active = __ballot_sync(full, !done);
         if (active == 0u) break;
+        // a ball whose radius is a guess (no seed, a first-cell or borrowed candidate) from probe_r on; any ball from
+        // probe_r2 on (a temporal seed that far away still leaves a wide disc after a few centimetres of drift)
+        const bool probe = !probed && __any_sync(full, !done && ((loose_seed && rr > probe_r) || rr > g.probe_r2));
         // ---- the union of the active balls.  A group of kCoopGroup consecutive lanes (Morton neighbours) is normally
         //      covered by ONE sphere: centre = middle of the group's queries, radius = the farthest reach of a member.
         //      A group that straddles a jump of the Morton curve would get a sphere metres wide: it is "loose" and its
@@ -1171,7 +1186,7 @@ __device__ __forceinline__ void coop_warp(const RegDesc &d, const GridMeta &g, c
                 };
                 const unsigned needed = __ballot_sync(full, need);
                 if (g.sub == 1) {
-                    if (needed) stage_runs(t0, need ? len : 0);
+                    if (needed) stage_runs(t0, need ? (probe ? 1 : len) : 0);
                 } else {
                     // ---- step 3: the eight children of the needed cells, flattened over the lanes again: their own tight
                     //      boxes decide (half the edge: a quarter of the points a cell would bring along for its rim)
@@ -1189,7 +1204,7 @@ __device__ __forceinline__ void coop_warp(const RegDesc &d, const GridMeta &g, c
                             klo = __ldg(&gbox[2 * (size_t)fine]); khi = __ldg(&gbox[2 * (size_t)fine + 1]);
                         }
                         const bool kneed = reaches(klo.x, klo.y, klo.z, khi.x, khi.y, khi.z) && klen > 0;
-                        if (__any_sync(full, kneed)) stage_runs(k0, kneed ? klen : 0);
+                        if (__any_sync(full, kneed)) stage_runs(k0, kneed ? (probe ? 1 : klen) : 0);
                     }
                 }
             }
@@ -1219,6 +1234,19 @@ __device__ __forceinline__ void coop_warp(const RegDesc &d, const GridMeta &g, c
                 if (empty_handed) coop_take(p, t, best, bb);
             }
         }
+        if (probe) {
+            // only samples were looked at: nothing is finished.  The nearest sample is a real target and bounds the
+            // ball; a lane that saw none grows its ball as after an empty real round and the warp probes again (unless
+            // the lane is at the cap already: then the real round comes next)
+            bool again = false;
+            if (!done) {
+                if (best.d < CUDART_INF_F) { rad = fminf(rad, best.d); loose_seed = false; }
+                else if (rr < max_reach) { rad = 4.f * rad; again = true; }
+            }
+            probed = !__any_sync(full, again); // warp-uniform
+            continue;
+        }
+        probed = false;
         if (!done) {
             // finished: the best lies inside the searched ball (or the whole acceptance ball was searched)
             if (best.d <= rr || rr >= max_reach) done = true;

@@ -88,6 +88,8 @@ struct GridMeta {
     int sub;       // sorted-array slots per coarse cell: 1, or 8 = every cell split into 2x2x2 children (child index in the low 3 bits)
     int max_r;     // shells needed to cover the acceptance radius
     int light_r;   // shells every query walks on its own thread before it is handed to a whole warp
+    float probe_r; // cooperative search: guessed balls wider than this are probed (one sample per child cell) before they are searched
+    float probe_r2; // ... and any ball wider than this
     float max_nn;  // acceptance radius (MAX_NN_COLOR_DISTANCE, icp.hpp:8)
 };
 
