@@ -73,8 +73,9 @@ enum { ICPB_SOLVE_REFERENCE = 0, /* icp.cpp:199-246: uncentred SVD, offset = mea
  * max_nn_distance - those are rejected by icp.cpp:553 in either mode. */
 enum { ICPB_NN_BRUTE = 0, ICPB_NN_GRID = 1,
        ICPB_NN_AUTO = 2 }; /* GRID when n*m is large enough for the bucketing to pay off, else BRUTE */
-/* The cell build is per registration: icpb_icp_register_batch with count > 1 runs the BRUTE scan whatever nn_mode
- * says, and says so in icpb_icp_result.nn_mode_used (same associations either way). */
+/* AUTO: one registration takes GRID from n*m >= 2e9 on (about 45k x 45k points); a batch builds the cells of all its
+ * registrations together and takes GRID when its clouds hold >= 4,096 points.  icpb_icp_result.nn_mode_used says which
+ * one ran (same associations either way).  The key-point variants always scan (a few thousand points). */
 
 /* Approximate FP32 filter in front of the exact re-evaluation of the BRUTE scan (never visible in the results):
  * CENTRED evaluates |t'|^2 - 2a'.t' about one centre per THREAD (3 FMA per pair + the centring of the targets per
@@ -96,7 +97,7 @@ typedef struct {
     float last_translation[3]; /* icp.cpp:25, consumed by the <3 associations rule (icp.cpp:163-182) */
     int32_t *idx_trace;        /* optional host buffer (max_iterations+1)*n: nearest index per pass */
     float *dist_trace;         /* optional host buffer, same shape */
-    int nn_mode;               /* ICPB_NN_BRUTE (default 0) or ICPB_NN_GRID */
+    int nn_mode;               /* ICPB_NN_BRUTE (default 0), ICPB_NN_GRID or ICPB_NN_AUTO */
     float grid_cell;           /* ICPB_NN_GRID: cell edge in metres (0 = chosen from the target's density) */
     int nn_filter;             /* ICPB_FILTER_* (default 0 = AUTO); env ICPB_NN_FILTER overrides */
 } icpb_icp_params;
