@@ -252,8 +252,11 @@ int run_registrations(icpb_ctx *ctx, const RegHost *regs, int count, const icpb_
     // ---- ICPB_NN_GRID: bucket the (fixed) targets once per registration.  Batches take the cooperative search only
     //      (the per-thread walk of round 1 stays a single-registration path).
     const bool coop_mode = env_int("ICPB_GRID_COOP_CM", 1000) > 0;
-    bool grid_mode = (prm->nn_mode == ICPB_NN_GRID) && (count == 1 || coop_mode) && !kp_mode;
-    if (prm->nn_mode == ICPB_NN_AUTO && !kp_mode) {
+    // a carried cloud (icpb_icp_register_carry) only replays the motions afterwards and goes with either search; the
+    // reject lists of the key-point loop are filled by the scan's finalize kernel alone
+    const bool rejects_wanted = count == 1 && regs[0].nonassoc;
+    bool grid_mode = (prm->nn_mode == ICPB_NN_GRID) && (count == 1 || coop_mode) && !rejects_wanted && (!kp_mode || coop_mode);
+    if (prm->nn_mode == ICPB_NN_AUTO && !rejects_wanted && (!kp_mode || coop_mode)) {
         // measured crossover regions: ~45k x 45k for one registration (set-up of ~0.3 ms against a scan of milliseconds);
         // in a batch the set-up is shared and the search wins from a few thousand points per cloud on
         if (count == 1) grid_mode = (double)max_n * (double)max_m >= 2.0e9;

@@ -491,7 +491,7 @@ cv::Mat getTransformation(cv::Mat &data, cv::Mat &previous, cv::Mat color, std::
     for (int k = 0; k < 3; ++k) prm.last_translation[k] = g.lastTranslation[k];
     prm.idx_trace = nullptr;
     prm.dist_trace = nullptr;
-    prm.nn_mode = ICPB_NN_BRUTE;
+    prm.nn_mode = ICPB_NN_AUTO; // the exact cell-grid search from ~45k x 45k points on, the scan below: same associations
     prm.grid_cell = 0.f;
     prm.nn_filter = ICPB_FILTER_AUTO;
     icpb_icp_result res;

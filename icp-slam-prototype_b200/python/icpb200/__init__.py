@@ -242,6 +242,16 @@ class Context:
         self.check(self.lib.icpb_icp_register(self.h, data.h, target.h, C.byref(prm), C.byref(res)))
         return res.to_dict(), it, dt
 
+    def icp_register_carry(self, data, target, carry, max_iterations=20, threshold=0.0, max_nn_distance=0.75,
+                           solve_mode=SOLVE_REFERENCE, nn_mode=NN_BRUTE):
+        """icpb_icp_register_carry: the all-point loop; `carry` receives every motion `data` receives."""
+        prm = IcpParams(max_iterations, threshold, max_nn_distance, solve_mode, (C.c_float * 3)(0, 0, 0), None, None,
+                        nn_mode, 0.0, FILTER_AUTO)
+        res = IcpResult()
+        self.check(self.lib.icpb_icp_register_carry(self.h, data.h, target.h, carry.h if carry is not None else None,
+                                                    C.byref(prm), C.byref(res)))
+        return res.to_dict()
+
     def icp_register_keypoints(self, keypoints, points, map_keypoints, max_iterations=16, threshold=1e-4,
                                max_nn_distance=0.1, solve_mode=SOLVE_REFERENCE, last_translation=(0, 0, 0),
                                non_associations=None):

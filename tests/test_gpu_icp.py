@@ -314,3 +314,23 @@ def test_icp_batch_async_equals_batch(ctx, pair10k):
         assert np.array_equal(d1[k].download().view(np.uint8), d2[k].download().view(np.uint8))
     for c in d1 + t1 + d2 + t2:
         c.close()
+
+
+@pytest.mark.parametrize("nn_mode", [0, 1])
+def test_icp_register_carry_in_both_search_modes(ctx, orc, pair10k, nn_mode):
+    """icpb_icp_register_carry (dataCloud.rotate / translate move points AND key-points, pointcloud.cpp:321-359): the
+    carried cloud ends where the oracle puts it, with the brute-force scan and with the exact cell-grid search."""
+    data, target = pair10k
+    data, target = data[:6000], target[:7000]
+    carry = data[::7].copy()
+    carry["x"] += np.float32(0.01)
+    ref, rdata, rcarry = orc.icp_carry(data, carry, target, 10, 0.0, 0.75, 0, n_threads=8)
+    dc, tc, cc = ctx.cloud_from_points(data), ctx.cloud_from_points(target), ctx.cloud_from_points(carry)
+    res = ctx.icp_register_carry(dc, tc, cc, 10, 0.0, 0.75, 0, nn_mode=nn_mode)
+    assert res["nn_mode_used"] == nn_mode
+    assert res["n_assoc"] == ref["n_assoc"]
+    assert np.array_equal(res["pose_R"], ref["pose_R"]) and np.array_equal(res["pose_t"], ref["pose_t"])
+    assert np.array_equal(dc.download().view(np.uint8), rdata.view(np.uint8))
+    assert np.array_equal(cc.download().view(np.uint8), rcarry.view(np.uint8))
+    for c in (dc, tc, cc):
+        c.close()
