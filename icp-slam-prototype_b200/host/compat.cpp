@@ -16,8 +16,10 @@ namespace {
 
 struct Host {
     icpb_ctx *ctx = nullptr;
-    icpb_cloud *slot[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    int cap[5] = {0, 0, 0, 0, 0};
+    // device scratch clouds: 0-4 are transients of the PointCloud / Map methods and the association scans,
+    // 5-6 hold the frame's clouds for the length of one icp::getTransformation call
+    icpb_cloud *slot[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int cap[7] = {0, 0, 0, 0, 0, 0, 0};
 };
 
 Host &H()
@@ -112,27 +114,147 @@ void lift(const cv::Mat &data, const cv::Mat &colorMat, int x, int y, color_poin
     out.color = colorMat.empty() ? cv::Vec3b() : colorMat.at<cv::Vec3b>(y, x);
 }
 
+// ---- the subsample draws of pointcloud.cpp:22-28 -------------------------------------------------------------------
+// The reference draws one rand() per non-zero pixel, in raster order, from the process-wide generator; the caller's
+// srand() and any rand() it draws itself belong to the same stream, so the drop-in must leave that generator exactly
+// where the reference's loop leaves it.  Calling rand() 290,000 times costs 6-7 ms a frame (glibc takes a lock per
+// call) -- more than everything else icp::getTransformation does.  glibc's rand() is random(): an additive-feedback
+// generator r[i] = r[i-deg] + r[i-deg+sep] over a state array that setstate() hands to the caller.  So the draws are
+// made in bulk on that array: park the generator on a spare state, advance the real one m steps here, hand it back.
+// Same values, same final state (tests/cpp/test_compat_host.cpp checks both against rand() itself); a start-up
+// self-check on a private state falls back to rand() per pixel if this libc's generator is not the one described.
+// Like rand() itself in a multi-threaded caller, the order of draws across threads is not defined.
+#if defined(__GLIBC__)
+// m steps of glibc's random_r() on the state block `word` (word[0]: 5 * rear + type, then the state array);
+// out[i] = (draw % factor) == 0.  Returns false for a layout it does not know.
+bool advance_glibc_state(int32_t *word, uint8_t *out, size_t m, int factor)
+{
+    static const int kDeg[5] = {0, 7, 15, 31, 63}, kSep[5] = {0, 3, 1, 3, 1};
+    const int type = word[0] % 5, rear = word[0] / 5;
+    if (word[0] < 0 || type < 0 || type > 4) return false;
+    uint32_t *s = reinterpret_cast<uint32_t *>(word + 1);
+    if (type == 0) { // TYPE_0: the linear congruential generator, one state word
+        uint32_t x = s[0];
+        for (size_t i = 0; i < m; ++i) {
+            x = (x * 1103515245u + 12345u) & 0x7fffffffu;
+            out[i] = ((int)x % factor) == 0;
+        }
+        s[0] = x;
+        return true;
+    }
+    const int deg = kDeg[type], sep = kSep[type];
+    if (rear >= deg) return false;
+    int r = rear, f = (rear + sep) % deg;
+    if (factor == SUBSAMPLE_FACTOR) { // the one factor the reference uses: a compile-time divisor (no idiv per draw)
+        for (size_t i = 0; i < m; ++i) {
+            const uint32_t val = (s[f] += s[r]);
+            out[i] = ((val >> 1) % (uint32_t)SUBSAMPLE_FACTOR) == 0;
+            if (++f == deg) f = 0;
+            if (++r == deg) r = 0;
+        }
+    } else {
+        for (size_t i = 0; i < m; ++i) {
+            const uint32_t val = (s[f] += s[r]);
+            out[i] = ((int)(val >> 1) % factor) == 0;
+            if (++f == deg) f = 0;
+            if (++r == deg) r = 0;
+        }
+    }
+    word[0] = 5 * r + type;
+    return true;
+}
+
+int32_t g_parked[34] = {3}; // a valid TYPE_3 state (rear 0) for glibc to hold while the real one is advanced here
+
+// One-time check on private states that never touch the caller's stream: 64 draws of rand() against 64 bulk draws.
+bool bulk_draws_usable()
+{
+    static int usable = -1;
+    if (usable >= 0) return usable == 1;
+    alignas(8) static char a[128], b[128];
+    char *caller = initstate(20161u, a, sizeof a); // glibc now on `a`; the caller's state is set aside untouched
+    if (!caller) { usable = 0; return false; }
+    uint8_t want[64], got[64];
+    for (int i = 0; i < 64; ++i) want[i] = (rand() % 7) == 0;
+    const int tail = rand();
+    initstate(20161u, b, sizeof b);                                   // the same seed on a second block
+    char *blk = setstate(reinterpret_cast<char *>(g_parked));        // ... which is handed back here
+    bool ok = blk == b && advance_glibc_state(reinterpret_cast<int32_t *>(blk), got, 64, 7);
+    if (ok) {
+        setstate(blk);
+        ok = rand() == tail; // the state handed back continues where rand() itself would
+        for (int i = 0; i < 64; ++i) ok = ok && want[i] == got[i];
+    }
+    setstate(caller);
+    usable = ok ? 1 : 0;
+    return ok;
+}
+#endif
+
+// keep[i] = (rand() % factor) == 0 for m successive draws of the process-wide generator.
+void draw_keep(uint8_t *keep, size_t m, int factor)
+{
+#if defined(__GLIBC__)
+    static const bool forced_off = getenv("ICPB_COMPAT_RAND_CALLS") != nullptr; // A/B switch: one rand() call per draw
+    if (m >= 64 && !forced_off && bulk_draws_usable()) {
+        char *blk = setstate(reinterpret_cast<char *>(g_parked));
+        if (blk) {
+            const bool ok = advance_glibc_state(reinterpret_cast<int32_t *>(blk), keep, m, factor);
+            setstate(blk);
+            if (ok) return; // (a refused layout leaves the state untouched: fall through to rand())
+        }
+    }
+#endif
+    for (size_t i = 0; i < m; ++i) keep[i] = (rand() % factor) == 0;
+}
+
 } // namespace
+
+// test hook (tests/cpp/test_compat_host.cpp): the subsample decisions of one depth image, as build_from_depth draws them
+extern "C" int icpb_compat_draw_keep(const uint16_t *depth, int n_px, int factor, uint8_t *keep)
+{
+    size_t m = 0;
+    for (int i = 0; i < n_px; ++i) m += depth[i] != 0;
+    draw_keep(keep, m, factor);
+    return (int)m;
+}
 
 // ================================================================ pointcloud.hpp
 namespace icp {
 
-static void build_from_depth(PointCloud &pc, cv::Mat &data, cv::Mat &colorMat)
+// pointcloud.cpp:19-52 on the device: the subsampled cloud of a depth image, left in scratch slot `slot`.
+static icpb_cloud *device_cloud_from_depth(int slot, cv::Mat &data, cv::Mat &colorMat, int *count)
 {
     const int w = data.cols, h = data.rows;
     const uint16_t *d = reinterpret_cast<const uint16_t *>(data.data);
     // One rand() per non-zero pixel in raster order, exactly where the reference draws it (pointcloud.cpp:22-28)
-    std::vector<uint8_t> keep;
-    keep.reserve((size_t)w * h);
-    for (int i = 0; i < w * h; ++i)
-        if (d[i] != 0) keep.push_back((rand() % SUBSAMPLE_FACTOR) == 0);
-    if (keep.empty()) keep.push_back(0);
+    size_t m = 0;
+    for (int i = 0; i < w * h; ++i) m += d[i] != 0;
+    std::vector<uint8_t> keep(std::max<size_t>(m, 1), 0);
+    draw_keep(keep.data(), m, SUBSAMPLE_FACTOR);
     icpb_intrinsics K;
     icpb_intrinsics_reference_v1(&K);
-    icpb_cloud *c = scratch(0, w * h);
+    icpb_cloud *c = scratch(slot, w * h);
     check(icpb_cloud_from_depth(c, d, colorMat.empty() ? nullptr : colorMat.data, w, h, &K, ICPB_SUB_STREAM, SUBSAMPLE_FACTOR, 0,
                                 keep.data(), (int)keep.size()),
           "icpb_cloud_from_depth");
+    if (count) check(icpb_cloud_size(c, count), "icpb_cloud_size");
+    return c;
+}
+
+// The draws of a PointCloud whose points nothing reads (the reference constructs it all the same, icp.cpp:39).
+static void draw_only(cv::Mat &data)
+{
+    const uint16_t *d = reinterpret_cast<const uint16_t *>(data.data);
+    size_t m = 0;
+    for (int i = 0; i < data.cols * data.rows; ++i) m += d[i] != 0;
+    std::vector<uint8_t> keep(std::max<size_t>(m, 1), 0);
+    draw_keep(keep.data(), m, SUBSAMPLE_FACTOR);
+}
+
+static void build_from_depth(PointCloud &pc, cv::Mat &data, cv::Mat &colorMat)
+{
+    icpb_cloud *c = device_cloud_from_depth(0, data, colorMat, nullptr);
     download(c, pc.points);
     // center: float running sum, then / count (pointcloud.cpp:43-45,100-102; 0/0 = NaN when empty, as there)
     pc.center = cv::Point3f(0, 0, 0);
@@ -141,16 +263,21 @@ static void build_from_depth(PointCloud &pc, cv::Mat &data, cv::Mat &colorMat)
     pc.center.x /= index; pc.center.y /= index; pc.center.z /= index;
 }
 
-PointCloud::PointCloud(cv::Mat &data, cv::Mat colorMat, std::vector<cv::KeyPoint> keypointsList)
+static void lift_keypoints(cv::Mat &data, cv::Mat &colorMat, const std::vector<cv::KeyPoint> &keypointsList, point_list_t &out)
 {
-    build_from_depth(*this, data, colorMat);
     for (const cv::KeyPoint &kp : keypointsList) { // pointcloud.cpp:64-97
         int x = (int)std::lrint(kp.pt.x), y = (int)std::lrint(kp.pt.y); // Point2f -> Point2i rounds (saturate_cast)
         if (data.at<uint16_t>(y, x) == 0) continue;
         color_point_t p;
         lift(data, colorMat, x, y, p);
-        keypoints.push_back(p);
+        out.push_back(p);
     }
+}
+
+PointCloud::PointCloud(cv::Mat &data, cv::Mat colorMat, std::vector<cv::KeyPoint> keypointsList)
+{
+    build_from_depth(*this, data, colorMat);
+    lift_keypoints(data, colorMat, keypointsList, keypoints);
     center_points();
 }
 
@@ -398,9 +525,14 @@ static cv::Mat getTransformationKeyPoints(cv::Mat &data, cv::Mat &previous, cv::
 {
     IcpGlobals &g = G();
     map::Map &m = *g.map;
-    PointCloud dataCloud(data, color, keypoints);         // :38
-    PointCloud previousCloud(previous, color, keypoints); // :39
+    // :38 -- the data cloud stays on the device (the loop moves it along with the key-points and nothing reads it back);
+    // its key-points are lifted on the host as in the reference
+    int n_points = 0;
+    icpb_cloud *pc = device_cloud_from_depth(5, data, color, &n_points);
+    point_list_t dataKeypoints;
+    lift_keypoints(data, color, keypoints, dataKeypoints);
     if (m.mapCloud.points.size() == 0) {                  // :47-68
+        PointCloud previousCloud(previous, color, keypoints); // :39
         const float I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
         for (int k = 0; k < 9; ++k) g.cameraRotation[k] = I[k];
         g.cameraPosition = cv::Point3f(5, 5, 5);
@@ -411,17 +543,18 @@ static cv::Mat getTransformationKeyPoints(cv::Mat &data, cv::Mat &previous, cv::
         m.update(previousCloud, MAX_CONFIDENCE, depthWindow);
         m.mapCloud.points = previousCloud.points;
         g.started = true;
+    } else {
+        draw_only(previous); // :39 -- with the map seeded nothing reads previousCloud; its rand() draws are all that shows
     }
     cv::Mat rigid(4, 4, CV_32FC1);
     for (int k = 0; k < 16; ++k) rigid.at<float>(k / 4, k % 4) = (k % 5 == 0) ? 1.f : 0.f;
     // :70-71 and the loop, on the device
     const float cp[3] = {g.cameraPosition.x, g.cameraPosition.y, g.cameraPosition.z};
-    icpb_cloud *kc = upload(0, dataCloud.keypoints);
-    icpb_cloud *pc = upload(1, dataCloud.points);
+    icpb_cloud *kc = upload(0, dataKeypoints);
     icpb_cloud *mc = upload(3, m.mapCloud.keypoints);
-    icpb_cloud *nc = scratch(4, (maxIterations + 1) * (int)std::max<size_t>(dataCloud.keypoints.size(), 1));
-    if (!dataCloud.keypoints.empty()) check(icpb_cloud_transform(kc, g.cameraRotation, cp), "icpb_cloud_transform");
-    if (!dataCloud.points.empty()) check(icpb_cloud_transform(pc, g.cameraRotation, cp), "icpb_cloud_transform");
+    icpb_cloud *nc = scratch(4, (maxIterations + 1) * (int)std::max<size_t>(dataKeypoints.size(), 1));
+    if (!dataKeypoints.empty()) check(icpb_cloud_transform(kc, g.cameraRotation, cp), "icpb_cloud_transform");
+    if (n_points > 0) check(icpb_cloud_transform(pc, g.cameraRotation, cp), "icpb_cloud_transform");
     icpb_icp_params prm;
     prm.max_iterations = maxIterations;
     prm.threshold = threshold;
@@ -434,7 +567,7 @@ static cv::Mat getTransformationKeyPoints(cv::Mat &data, cv::Mat &previous, cv::
     prm.grid_cell = 0.f;
     prm.nn_filter = ICPB_FILTER_AUTO;
     icpb_icp_result res;
-    check(icpb_icp_register_keypoints(H().ctx, kc, dataCloud.points.empty() ? nullptr : pc, mc, &prm, &res, nc),
+    check(icpb_icp_register_keypoints(H().ctx, kc, n_points > 0 ? pc : nullptr, mc, &prm, &res, nc),
           "icpb_icp_register_keypoints");
     mul33(g.cameraRotation, res.cam_rotation, g.cameraRotation);                                  // :237
     g.cameraPosition += cv::Point3f(res.cam_position[0], res.cam_position[1], res.cam_position[2]); // :246
@@ -460,9 +593,16 @@ cv::Mat getTransformation(cv::Mat &data, cv::Mat &previous, cv::Mat color, std::
     IcpGlobals &g = G();
     if (g.mode == ASSOCIATE_KEYPOINTS)
         return getTransformationKeyPoints(data, previous, color, keypoints, maxIterations, threshold, depthWindow);
-    PointCloud dataCloud(data, color, keypoints);       // :38
-    PointCloud previousCloud(previous, color, keypoints); // :39 (previous depth with the CURRENT colour / key-points)
+    // :38-39 -- both clouds are built on the device and stay there: the loop reads and moves them in HBM, and of the
+    // registered data cloud only the key-points come back (for the map update of :270)
+    int n_data = 0, n_prev = 0;
+    icpb_cloud *dc = device_cloud_from_depth(5, data, color, &n_data);
+    point_list_t dataKeypoints;
+    lift_keypoints(data, color, keypoints, dataKeypoints);
+    const float cp0[3] = {g.cameraPosition.x, g.cameraPosition.y, g.cameraPosition.z};
+    icpb_cloud *tc = nullptr;
     if (!g.started) {                                   // :47-68
+        PointCloud previousCloud(previous, color, keypoints); // :39 (previous depth with the CURRENT colour / key-points)
         const float I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
         for (int k = 0; k < 9; ++k) g.cameraRotation[k] = I[k];
         g.cameraPosition = cv::Point3f(5, 5, 5);
@@ -473,16 +613,16 @@ cv::Mat getTransformation(cv::Mat &data, cv::Mat &previous, cv::Mat color, std::
         g.map->update(previousCloud, MAX_CONFIDENCE, depthWindow);
         g.map->mapCloud.points = previousCloud.points;
         g.started = true;
+        tc = upload(6, previousCloud.points);
+        n_prev = (int)previousCloud.points.size();
     } else {
-        cv::Mat Rc = mat33(g.cameraRotation);
-        previousCloud.rotate(Rc);
-        previousCloud.translate(g.cameraPosition);
+        // the previous frame's cloud placed at the current camera pose: rotate, then translate (pointcloud.cpp:321-359)
+        tc = device_cloud_from_depth(6, previous, color, &n_prev);
+        if (n_prev > 0) check(icpb_cloud_transform(tc, g.cameraRotation, cp0), "icpb_cloud_transform");
     }
     // :70-71 on the device, then the loop
-    icpb_cloud *dc = upload(0, dataCloud.points);
-    icpb_cloud *tc = upload(1, previousCloud.points);
     const float cp[3] = {g.cameraPosition.x, g.cameraPosition.y, g.cameraPosition.z};
-    check(icpb_cloud_transform(dc, g.cameraRotation, cp), "icpb_cloud_transform");
+    if (n_data > 0) check(icpb_cloud_transform(dc, g.cameraRotation, cp), "icpb_cloud_transform");
     icpb_icp_params prm;
     prm.max_iterations = maxIterations;
     prm.threshold = threshold;
@@ -496,15 +636,15 @@ cv::Mat getTransformation(cv::Mat &data, cv::Mat &previous, cv::Mat color, std::
     prm.nn_filter = ICPB_FILTER_AUTO;
     icpb_icp_result res;
     cv::Mat rigid(4, 4, CV_32FC1);
-    if (dataCloud.points.empty() || previousCloud.points.empty()) {
+    if (n_data == 0 || n_prev == 0) {
         for (int k = 0; k < 16; ++k) rigid.at<float>(k / 4, k % 4) = (k % 5 == 0) ? 1.f : 0.f;
         return rigid;
     }
     // the key-points ride along: dataCloud.rotate / translate move points and key-points together (pointcloud.cpp:321-359),
     // so they receive (cameraRotation, cameraPosition) of :70-71 and then every motion of the loop, in order
     icpb_cloud *kc = nullptr;
-    if (!dataCloud.keypoints.empty()) {
-        kc = upload(2, dataCloud.keypoints);
+    if (!dataKeypoints.empty()) {
+        kc = upload(2, dataKeypoints);
         check(icpb_cloud_transform(kc, g.cameraRotation, cp), "icpb_cloud_transform");
     }
     check(icpb_icp_register_carry(H().ctx, dc, tc, kc, &prm, &res), "icpb_icp_register_carry");
@@ -514,10 +654,10 @@ cv::Mat getTransformation(cv::Mat &data, cv::Mat &previous, cv::Mat color, std::
     for (int k = 0; k < 3; ++k) g.lastTranslation[k] = -res.offset[k]; // :260
     std::cout << res.mse;                                               // :264
     // :270 (the all-point twin of :271): certainty update from the registered key-points
-    download(dc, dataCloud.points);
     if (kc) {
-        download(kc, dataCloud.keypoints);
-        g.map->update(dataCloud, DELTA_CONFIDENCE, depthWindow);
+        PointCloud registered;
+        download(kc, registered.keypoints);
+        g.map->update(registered, DELTA_CONFIDENCE, depthWindow);
     }
     std::cout << std::endl << g.map->mapCloud.points.size() << std::endl; // :279
     for (int k = 0; k < 16; ++k) rigid.at<float>(k / 4, k % 4) = res.rigid[k];

@@ -4,11 +4,15 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <vector>
 
 #include "icpb200/icp.hpp"
 #include "icpb200/map.hpp"
 #include "icpb200/pointcloud.hpp"
 #include "icpb200/quaternion.hpp"
+
+// test hook of the drop-in layer (host/compat.cpp): the subsample decisions of pointcloud.cpp:22-28 for one depth image
+extern "C" int icpb_compat_draw_keep(const uint16_t *depth, int n_px, int factor, uint8_t *keep);
 
 #define CHECK(c) do { if (!(c)) { std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); return 1; } } while (0)
 
@@ -63,9 +67,51 @@ static int dump()
     return 0;
 }
 
+// The subsample draws (pointcloud.cpp:22-28): the drop-in makes them in bulk on the generator's own state array; the
+// decisions AND the stream the caller sees afterwards must be those of one rand() per non-zero pixel.
+static int check_draws(int n_px, int zero_every, int factor)
+{
+    std::vector<uint16_t> depth((size_t)n_px);
+    for (int i = 0; i < n_px; ++i) depth[(size_t)i] = (zero_every && i % zero_every == 0) ? 0 : (uint16_t)(1 + i % 4000);
+    // where the generator stands now is unknown to this function: remember it by cloning the caller-visible stream
+    const unsigned seed = 100u + (unsigned)n_px;
+    srand(seed);
+    std::vector<uint8_t> want;
+    for (int i = 0; i < n_px; ++i)
+        if (depth[(size_t)i] != 0) want.push_back((rand() % factor) == 0);
+    const int w0 = rand(), w1 = rand(), w2 = rand();
+    srand(seed);
+    std::vector<uint8_t> got((size_t)n_px + 1, 0xff);
+    const int m = icpb_compat_draw_keep(depth.data(), n_px, factor, got.data());
+    CHECK(m == (int)want.size());
+    for (int i = 0; i < m; ++i) CHECK(got[(size_t)i] == want[(size_t)i]);
+    CHECK(got[(size_t)m] == 0xff);
+    CHECK(rand() == w0 && rand() == w1 && rand() == w2);
+    return 0;
+}
+
+static int check_draws_all()
+{
+    if (check_draws(640 * 480, 20, SUBSAMPLE_FACTOR)) return 1; // a Kinect v1 frame with holes
+    if (check_draws(512 * 424, 0, SUBSAMPLE_FACTOR)) return 1;
+    if (check_draws(1000, 3, 40) || check_draws(63, 0, 40) || check_draws(0, 0, 40)) return 1; // below and above the bulk threshold
+    if (check_draws(31 * 7 + 5, 0, 3)) return 1;
+    // the other generator types a caller may have selected with initstate(): 8 / 32 / 64 / 256-byte state blocks
+    alignas(8) static char blocks[4][256];
+    const size_t sizes[4] = {8, 32, 64, 256};
+    for (int k = 0; k < 4; ++k) {
+        char *before = initstate(7u + (unsigned)k, blocks[k], sizes[k]);
+        const int rc = check_draws(5000 + k, 5, SUBSAMPLE_FACTOR);
+        setstate(before);
+        if (rc) { std::printf("generator type %d\n", k); return 1; }
+    }
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
     if (argc > 1 && std::string(argv[1]) == "dump") return dump();
+    if (check_draws_all()) return 1;
     // distance (icp.cpp:595-620), meanSquareError (:622-638), calculateOffset (:314-344)
     CHECK(icp::distance(cv::Point3f(0, 0, 0), cv::Point3f(3, 4, 0)) == 5.0f);
     CHECK(icp::distance(cp(1, 1, 1), cp(1, 1, 3)) == 2.0f);
