@@ -144,23 +144,36 @@ bool advance_glibc_state(int32_t *word, uint8_t *out, size_t m, int factor)
     }
     const int deg = kDeg[type], sep = kSep[type];
     if (rear >= deg) return false;
-    int r = rear, f = (rear + sep) % deg;
-    if (factor == SUBSAMPLE_FACTOR) { // the one factor the reference uses: a compile-time divisor (no idiv per draw)
-        for (size_t i = 0; i < m; ++i) {
-            const uint32_t val = (s[f] += s[r]);
-            out[i] = ((val >> 1) % (uint32_t)SUBSAMPLE_FACTOR) == 0;
-            if (++f == deg) f = 0;
-            if (++r == deg) r = 0;
+    // x[n] = x[n-deg] + x[n-sep], draw = x[n] >> 1.  The circular state is unrolled, oldest first, in front of a
+    // linear block buffer, so that the recurrence is a plain streaming loop (no wrap tests, three independent add
+    // chains for sep = 3) and the decisions are a second pass over the block.
+    enum { kBlock = 8192 };
+    uint32_t G[kBlock + 64];
+    const int f = (rear + sep) % deg, lag = deg - sep;
+    for (int j = 0; j < deg; ++j) G[j] = s[(f + j) % deg];
+    for (size_t done = 0; done < m;) {
+        const size_t n = std::min<size_t>(kBlock, m - done);
+        size_t i = 0;
+        if (deg == 31) { // TYPE_3, glibc's default: the three newest values ride in registers (no store-to-load stall)
+            uint32_t a = G[28], b = G[29], c = G[30];
+            for (; i + 3 <= n; i += 3) {
+                a += G[i]; b += G[i + 1]; c += G[i + 2];
+                G[i + 31] = a; G[i + 32] = b; G[i + 33] = c;
+            }
         }
-    } else {
-        for (size_t i = 0; i < m; ++i) {
-            const uint32_t val = (s[f] += s[r]);
-            out[i] = ((int)(val >> 1) % factor) == 0;
-            if (++f == deg) f = 0;
-            if (++r == deg) r = 0;
-        }
+        for (; i < n; ++i) G[i + deg] = G[i] + G[i + lag];
+        const uint32_t *x = G + deg;
+        uint8_t *o = out + done;
+        if (factor == SUBSAMPLE_FACTOR) // the one factor the reference uses: a compile-time divisor (no idiv per draw)
+            for (size_t i = 0; i < n; ++i) o[i] = ((x[i] >> 1) % (uint32_t)SUBSAMPLE_FACTOR) == 0;
+        else
+            for (size_t i = 0; i < n; ++i) o[i] = ((int)(x[i] >> 1) % factor) == 0;
+        for (int j = 0; j < deg; ++j) G[j] = G[n + j]; // the newest deg values lead the next block (n >= 1: no overlap hazard going up)
+        done += n;
     }
-    word[0] = 5 * r + type;
+    const int f_new = (int)((f + m) % (size_t)deg);
+    for (int j = 0; j < deg; ++j) s[(f_new + j) % deg] = G[j];
+    word[0] = 5 * (int)((rear + m) % (size_t)deg) + type;
     return true;
 }
 

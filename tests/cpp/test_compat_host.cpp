@@ -95,7 +95,7 @@ static int check_draws_all()
     if (check_draws(640 * 480, 20, SUBSAMPLE_FACTOR)) return 1; // a Kinect v1 frame with holes
     if (check_draws(512 * 424, 0, SUBSAMPLE_FACTOR)) return 1;
     if (check_draws(1000, 3, 40) || check_draws(63, 0, 40) || check_draws(0, 0, 40)) return 1; // below and above the bulk threshold
-    if (check_draws(31 * 7 + 5, 0, 3)) return 1;
+    if (check_draws(31 * 7 + 5, 0, 3) || check_draws(100, 0, 40) || check_draws(8192 * 2 + 1, 0, 40)) return 1; // block and unroll tails
     // the other generator types a caller may have selected with initstate(): 8 / 32 / 64 / 256-byte state blocks
     alignas(8) static char blocks[4][256];
     const size_t sizes[4] = {8, 32, 64, 256};
