@@ -673,12 +673,20 @@ def run_live(args, rank, world, local, emit=True):
                 f.write(bgr.tobytes()); f.write(np.ascontiguousarray(kxy, np.float32).tobytes())
                 tmp = f.name
             out = subprocess.run([binp, tmp], capture_output=True, text=True, timeout=300)
+            # A/B: the same frames with one rand() call per pixel for the subsample draws (pointcloud.cpp:22-28) instead
+            # of the bulk draws on the generator's state (host/compat.cpp, draw_keep): same stream, same results
+            out_ab = subprocess.run([binp, tmp], capture_output=True, text=True, timeout=300,
+                                    env=dict(os.environ, ICPB_COMPAT_RAND_CALLS="1"))
             os.unlink(tmp)
             kv = dict(tok.split("=") for tok in out.stdout.split() if "=" in tok)
+            kv_ab = dict(tok.split("=") for tok in out_ab.stdout.split() if "=" in tok)
             compat = {"all_points_ms_per_frame": float(kv["all_points_ms"]), "keypoints_ms_per_frame": float(kv["keypoints_ms"]),
                       "frames": int(kv["frames"]),
-                      "what": "icp::getTransformation through the C++ drop-in headers (host vectors in and out on every "
-                              "call, as the reference's signatures demand), per frame"}
+                      "with_one_rand_call_per_pixel": {"all_points_ms_per_frame": float(kv_ab["all_points_ms"]),
+                                                       "keypoints_ms_per_frame": float(kv_ab["keypoints_ms"])},
+                      "what": "icp::getTransformation through the C++ drop-in headers (depth, colour and key-point "
+                              "images in, 4x4 matrix out, as the reference's signature demands; the clouds stay on the "
+                              "device, the subsample draws are made in bulk on the C library's generator state), per frame"}
         except Exception as e:  # the harness is optional: the C-ABI number stands without it
             compat = {"unavailable": str(e)}
         line = {"metric": "live_loop_frames_per_s", "value": world * (frames - 1) / (tot * 1e-3), "unit": "frames/s",
