@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <algorithm>
 
 #include "icpb200.h"
@@ -107,6 +108,7 @@ IcpGlobals &G()
 void lift(const cv::Mat &data, const cv::Mat &colorMat, int x, int y, color_point_t &out)
 {
     // pointcloud.cpp:37-39 / 85-87 (CX and FX on both axes)
+    std::memset(static_cast<void *>(&out), 0, sizeof out); // the 16th byte is padding: keep it defined (and equal to the device's 0)
     float p_z = ((float)data.at<uint16_t>(y, x)) / 5000.0f;
     float p_x = (x - CX) * p_z / FX;
     float p_y = (y - CX) * p_z / FX;
