@@ -8,6 +8,11 @@
 #include "icp.hpp"
 #include "pointcloud.hpp"
 
+// The grid is 300^3 cells of 10 m / 300 because the reference fixes it with these macros and a static array member
+// (map.hpp:9-10,25: `unsigned char world[MAP_HEIGHT][MAP_HEIGHT][MAP_HEIGHT]`), which cannot express a non-cubic grid.
+// The grids of the README / BASELINE configs (300x300x250 at 2 cm, 600x600x500 at 1 cm) and z-slab sharding are a
+// run-time choice of the C-ABI underneath: icpb_map_create(ctx, dims, cell, z_lo, z_hi, ...) and icpb_slabmap_*
+// (include/icpb200.h; INTEGRATION.md sections B and C).
 #define MAP_HEIGHT 300
 #define PHYSICAL_HEIGHT 10.0f
 #define DELTA_CONFIDENCE 25
