@@ -1,0 +1,52 @@
+"""The error band of the centred NN filter (kBandCentredA / kBandCentredX, csrc/icpb_internal.h),
+hunted for counterexamples on the CPU: tools/checks/filter_band_check.c reproduces the kernels' filter value and the
+reference's distance (icp.cpp:606-620) operation for operation.  The long run is profiles/r02_check_filter_band.txt;
+this keeps a short one in the suite and ties the program's constants to the header's.  No GPU."""
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tools", "checks", "filter_band_check.c")
+HDR = os.path.join(ROOT, "icp-slam-prototype_b200", "csrc", "icpb_internal.h")
+
+
+def _build(tmp_path):
+    exe = str(tmp_path / "filter_band_check")
+    try:
+        has_fma = " fma " in open("/proc/cpuinfo").read()
+    except OSError:
+        has_fma = False
+    # without the FMA instruction fmaf() goes through libm: the same values, slower
+    flags = ["-mfma"] if has_fma else []
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", *flags, "-fopenmp", "-o", exe, SRC, "-lm"])
+    return exe
+
+
+def _run(exe, samples, scale=None):
+    cmd = [exe, str(samples)] + ([str(scale)] if scale is not None else [])
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    rows = [ln.split() for ln in r.stdout.splitlines() if ln.startswith("  ")]
+    return r.returncode, [(int(c[-4]), int(c[-3]), int(c[-2]), float(c[-1])) for c in rows]
+
+
+def test_check_uses_the_constants_the_library_ships():
+    hdr, src = open(HDR).read(), open(SRC).read()
+    for name, short in (("kBandCentredA", "kA"), ("kBandCentredX", "kX")):
+        h = re.search(r"%s\s*=\s*([0-9.]+)f\s*\*\s*([0-9.e+-]+)f" % name, hdr)
+        s = re.search(r"%s\s*=\s*([0-9.]+)f\s*\*\s*([0-9.e+-]+)f" % short, src)
+        assert h and s and h.groups() == s.groups(), (name, h and h.groups(), s and s.groups())
+    assert re.search(r"kBandAbs\s*=\s*1\.0e-30f", hdr) and "kAbs = 1.0e-30f" in src
+    assert "1.000001f" in src and "1.000001f" in open(os.path.join(os.path.dirname(HDR), "nn.cu")).read()
+
+
+def test_band_holds_and_the_hunt_has_teeth(tmp_path):
+    exe = _build(tmp_path)
+    rc, rows = _run(exe, 2000000)
+    assert rc == 0 and len(rows) == 7
+    assert all(v == 0 for _, v, _, _ in rows), rows                 # nothing declared farther that the reference keeps
+    assert sum(d for d, _, _, _ in rows) > 1000000 and all(m > 100000 for _, _, m, _ in rows)
+    assert max(t for *_, t in rows) < 0.5, rows                      # the band is not grazed
+    # control: a tenth of the band -- pairs the reference ties now fall outside it
+    rc, rows = _run(exe, 2000000, 0.1)
+    assert max(t for *_, t in rows) > 1.0, rows
