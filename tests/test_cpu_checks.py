@@ -1,7 +1,12 @@
-"""The error band of the centred NN filter (kBandCentredA / kBandCentredX, csrc/icpb_internal.h),
+"""Host-side proofs behind two device shortcuts (tools/checks/*.c), kept in the CPU suite.
+
+1. The error band of the centred NN filter (kBandCentredA / kBandCentredX, csrc/icpb_internal.h),
 hunted for counterexamples on the CPU: tools/checks/filter_band_check.c reproduces the kernels' filter value and the
 reference's distance (icp.cpp:606-620) operation for operation.  The long run is profiles/r02_check_filter_band.txt;
-this keeps a short one in the suite and ties the program's constants to the header's.  No GPU."""
+this keeps a short one in the suite and ties the program's constants to the header's.
+2. The five-instruction FMA division of the back-projection kernel (csrc/cloud.cu, div_by) against `/` for every depth
+and every column / row it can meet (pointcloud.cpp:37-39) -- the host twin of the device sweep in test_gpu_cloud.py.
+No GPU."""
 import os
 import re
 import subprocess
@@ -11,15 +16,15 @@ SRC = os.path.join(ROOT, "tools", "checks", "filter_band_check.c")
 HDR = os.path.join(ROOT, "icp-slam-prototype_b200", "csrc", "icpb_internal.h")
 
 
-def _build(tmp_path):
-    exe = str(tmp_path / "filter_band_check")
+def _build(tmp_path, src=SRC, name="filter_band_check"):
+    exe = str(tmp_path / name)
     try:
         has_fma = " fma " in open("/proc/cpuinfo").read()
     except OSError:
         has_fma = False
     # without the FMA instruction fmaf() goes through libm: the same values, slower
     flags = ["-mfma"] if has_fma else []
-    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", *flags, "-fopenmp", "-o", exe, SRC, "-lm"])
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", *flags, "-fopenmp", "-o", exe, src, "-lm"])
     return exe
 
 
@@ -50,3 +55,15 @@ def test_band_holds_and_the_hunt_has_teeth(tmp_path):
     # control: a tenth of the band -- pairs the reference ties now fall outside it
     rc, rows = _run(exe, 2000000, 0.1)
     assert max(t for *_, t in rows) > 1.0, rows
+
+
+def test_fma_division_is_correctly_rounded_for_every_input_of_the_back_projection(tmp_path):
+    src = os.path.join(ROOT, "tools", "checks", "fast_div_check.c")
+    cu = open(os.path.join(os.path.dirname(HDR), "cloud.cu")).read()
+    # the sequence checked is the sequence shipped
+    body = re.search(r"float q = __fmul_rn\(a, d\.rc\);(.*?)return __fmaf_rn\(r, d\.rc, q\);", cu, re.S)
+    assert body and body.group(1).count("__fmaf_rn") == 3
+    exe = _build(tmp_path, src, "fast_div_check")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and r.stdout.startswith("ok "), r.stdout[-500:]
+    assert int(r.stdout.split()[1]) > 2000000000
