@@ -6,6 +6,8 @@ reference's distance (icp.cpp:606-620) operation for operation.  The long run is
 this keeps a short one in the suite and ties the program's constants to the header's.
 2. The five-instruction FMA division of the back-projection kernel (csrc/cloud.cu, div_by) against `/` for every depth
 and every column / row it can meet (pointcloud.cpp:37-39) -- the host twin of the device sweep in test_gpu_cloud.py.
+3. The brick-jumping ray walk (csrc/map.cu, map_rays_brick_kernel) as pure integer arithmetic against the plain
+voxel-by-voxel walk of the oracle, on random rays, occupancy and z-slabs (tools/checks/brick_walk_emulation.py).
 No GPU."""
 import os
 import re
@@ -67,3 +69,10 @@ def test_fma_division_is_correctly_rounded_for_every_input_of_the_back_projectio
     r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and r.stdout.startswith("ok "), r.stdout[-500:]
     assert int(r.stdout.split()[1]) > 2000000000
+
+
+def test_brick_jump_walk_reads_the_voxels_the_plain_walk_reads():
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "checks", "brick_walk_emulation.py"), "3000"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "3000 cases, 0 mismatches" in r.stdout, r.stdout[-500:] + r.stderr[-500:]
